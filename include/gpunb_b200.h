@@ -1,0 +1,104 @@
+/*
+ * gpunb_b200.h -- C-ABI of libgpunb_b200.so, a B200-native (sm_100a) drop-in
+ * for the regular-force library of NBODY6++GPU.
+ *
+ * Part 1 is EXACTLY the Fortran-callable ABI the reference exports (lower
+ * case, trailing underscore, every scalar by reference, INTEGER*4 / REAL*8,
+ * column-major X(3,N) == C x[N][3]).  Each prototype cites the reference
+ * definition it replaces.  Part 2 are additive extension entry points
+ * (prefix gpunb_b200_) used by the harness, bench.py and the multi-process
+ * NCCL mode; a Fortran caller never needs them.
+ *
+ * All buffers are caller-owned, pageable, valid only during the call.
+ */
+#ifndef GPUNB_B200_H
+#define GPUNB_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------- Part 1: the reference ABI (drop-in) ---------------- */
+
+/* reference: src/Main/gpunb.velocity.cu:905 (GPUNB_devinit, :574-626).
+ * Device discovery; honours GPU_LIST="0 1 ..." (:582-591); prints the banner. Idempotent. */
+void gpunb_devinit_(int *irank);
+
+/* reference: gpunb.velocity.cu:908 (GPUNB_open, :628-666). nbmax = largest nj of the session
+ * (NTOT+10).  Re-open while open only warns (:636-639). */
+void gpunb_open_(int *nbmax, int *irank);
+
+/* reference: gpunb.velocity.cu:911 (GPUNB_close, :668-701). Close while closed only warns. */
+void gpunb_close_(void);
+
+/* reference: gpunb.velocity.cu:914 (GPUNB_send, :703-729). Uploads ALL nj j-particles
+ * (mass, position, velocity; fp64) -- the snapshot every following regf call sums over. */
+void gpunb_send_(int *nj, double mj[], double xj[][3], double vj[][3]);
+
+/* reference: gpunb.velocity.cu:921-935 (GPUNB_regf, :731-880).
+ * For i in [0,ni): acc/jrk/pot over all j outside the neighbour sphere; list[i*lmax+0] =
+ * count (or -(count) when count > nnbmax, the reg.avx.cpp:320-321 encoding), list[i*lmax+1..] =
+ * 0-based j indices, strictly ascending, self included.  m_flag=1: criterion r2min < mj*h2. */
+void gpunb_regf_(int *ni, double h2[], double dtr[], double xi[][3], double vi[][3],
+                 double acc[][3], double jrk[][3], double pot[],
+                 int *lmax, int *nnbmax, int *list, int *m_flag);
+
+/* reference: gpunb.velocity.cu:936 (GPUNB_profile, :882-902). stderr perf line, counters reset. */
+void gpunb_profile_(int *irank);
+
+/* reference: src/Main/gpupot.gpu.cu:117-126 (gpupot, :61-114). pot[ii] = sum_{j, r>0} m_j/r_ij
+ * for i = istart-1+ii (istart is 1-based), ii in [0,ni), over all n particles. */
+void gpupot_(int *irank, int *istart, int *ni, int *n, double m[], double x[][3], double pot[]);
+
+/* ---------------- Part 2: additive extensions ---------------- */
+
+/* Library/ABI version and a string naming the kernels compiled in. */
+int         gpunb_b200_version(void);
+const char *gpunb_b200_build_info(void);
+
+/* Number of GPUs this process drives (after devinit). */
+int gpunb_b200_num_devices(void);
+
+/* Counters since the last reset (doubles, see GPUNB_B200_CTR_*): device time of the pair kernel
+ * measured with CUDA events on its launching stream, launches, bytes moved, interactions. */
+enum {
+    GPUNB_B200_CTR_GRAV_MS = 0,     /* sum of regf pair-kernel durations, ms (device 0)      */
+    GPUNB_B200_CTR_GRAV_LAUNCHES,   /* pair-kernel launches (device 0)                        */
+    GPUNB_B200_CTR_LAUNCHES,        /* all kernel launches by this library (all devices)      */
+    GPUNB_B200_CTR_H2D_BYTES,
+    GPUNB_B200_CTR_D2H_BYTES,
+    GPUNB_B200_CTR_INTERACTIONS,    /* sum ni*nj as the reference counts (gpunb.velocity.cu:747) */
+    GPUNB_B200_CTR_MERGE_MS,        /* sum of merge-kernel durations, ms (device 0)           */
+    GPUNB_B200_CTR_POT_MS,          /* sum of gpupot kernel durations, ms                     */
+    GPUNB_B200_CTR_COUNT
+};
+void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);
+void gpunb_b200_reset_counters(void);
+
+/* Device-resident sweep (bench "value" leg): i-particles are j-particles [i0, i0+ni) of the
+ * snapshot already uploaded by gpunb_send_; h2/dtr (length nj, host) are uploaded once by
+ * gpunb_b200_set_radii.  Blocks of `block` i-particles are launched back to back with no host
+ * synchronisation; results stay on the device (last block readable with fetch).  Returns the
+ * device time in ms between the first and the last kernel (CUDA events). */
+void  gpunb_b200_set_radii(int *nj, double h2[], double dtr[]);
+float gpunb_b200_sweep_resident(int *i0, int *ni, int *block, int *lmax, int *nnbmax, int *m_flag);
+/* Copy the results of the LAST resident block (n_last rows) to host arrays laid out as regf's. */
+void  gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double pot[],
+                            int *lmax, int *list);
+
+/* FP32 pipe microbenchmark: returns achieved scalar/packed FFMA TFLOP/s on device 0
+ * (mode 0: FFMA, 1: FFMA2 (f32x2), 2: FADD2, 3: FMUL2, 4: MUFU.RSQ Gop/s, 5: FFMA2+ALU mix). */
+double gpunb_b200_fp32_microbench(int mode, int iters);
+
+/* Multi-process j-sharding over NCCL (one process per GPU).  id128 is a 128-byte ncclUniqueId
+ * created by rank 0 (gpunb_b200_nccl_unique_id) and broadcast by the caller. After init, each
+ * rank sends ITS OWN j-shard (global index offset joff) and every rank calls regf with the same
+ * i-block; rank 0 receives the combined result. */
+int  gpunb_b200_nccl_unique_id(unsigned char id128[128]);
+int  gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128]);
+void gpunb_b200_set_shard(int joff_global);
+void gpunb_b200_nccl_finalize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

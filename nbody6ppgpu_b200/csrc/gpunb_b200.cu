@@ -1,0 +1,944 @@
+// gpunb_b200.cu -- B200-native (sm_100a) regular-force library for NBODY6++GPU.
+//
+// Drop-in for the reference's gpunb.velocity.cu / gpupot.gpu.cu behind the same
+// Fortran-callable C-ABI (include/gpunb_b200.h).  Written from scratch; the
+// reference (file:line cited below) defines WHAT is computed, not how.
+//
+// Data layout in HBM (per device)
+//   jraw   : the caller's fp64 snapshot, m[nj] | x[nj][3] | v[nj][3]            56 B/j
+//   jtile  : AoSoA tiles of TJ=64 j-particles, 10 float arrays per tile
+//            {xh,yh,zh, xl,yl,zl, vx,vy,vz, m}[64]  = 2560 B/tile                40 B/j
+//            xh=(float)x, xl=(float)(x-xh): float-float positions, so that close
+//            pairs keep ~48 bits in dx; xh alone is what the reference's FP32
+//            cast sees (gpunb.velocity.cu:62-64), so its neighbour predicate can
+//            be evaluated bit-for-bit.  One tile = ONE 1-D TMA bulk copy.
+//   part   : per (j-slice s, i) partial sums, 7 doubles, + count               [S][ni]
+//   seg    : per (i, s) neighbour-index segment, capacity segcap ints
+//   res_f  : per i  acc[3] jrk[3] pot  (fp64)   ; res_list : [ni][lmax] int32 (the ABI layout)
+//
+// Kernels
+//   jpack_kernel   fp64 snapshot -> jtile (+ NaN check, reference asserts: gpunb.velocity.cu:72-78)
+//   regf_kernel    the O(ni*nj) pair kernel.  One WARP = one work item (i-tile of 32*IT
+//                  i-particles, contiguous range of j-tiles).  j-tiles are staged through
+//                  warp-private shared memory by TMA bulk copies (cp.async.bulk + mbarrier,
+//                  double buffered); lanes own i-particles, j is broadcast from smem; two
+//                  j-particles are processed per instruction with packed f32x2 FMA/ADD/MUL.
+//                  FP32 chains are 128 terms long, then flushed into fp64 accumulators.
+//   merge_kernel   per i: fp64 sum of the S partials in fixed order, exclusive scan of the S
+//                  segment counts, concatenation in slice order (= ascending j), overflow
+//                  encoding -(count) (reg.avx.cpp:320-321).
+//   pot_kernel     gpupot: float-float dx, FP32 rsqrt + one Newton step, fp64 flush.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <cmath>
+#include <vector>
+#include <sys/time.h>
+#include <unistd.h>
+#include "../../include/gpunb_b200.h"
+
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "gpunb_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, \
+            cudaGetErrorString(e_)); abort(); } } while (0)
+#define FATAL(...) do { fprintf(stderr, "gpunb_b200: " __VA_ARGS__); fprintf(stderr, "\n"); abort(); } while (0)
+
+namespace {
+
+constexpr int TJ          = 64;               // j-particles per tile
+constexpr int NCOMP       = 10;               // float arrays per tile
+constexpr int TILE_FLOATS = TJ * NCOMP;       // 640
+constexpr int TILE_BYTES  = TILE_FLOATS * 4;  // 2560
+constexpr int NSTAGE      = 2;                // smem stages per warp
+constexpr int WARPS       = 4;                // warps per CTA (warp-autonomous: no CTA-wide sync)
+constexpr int IT          = 2;                // i-particles per lane
+constexpr int ITILE       = 32 * IT;          // i-particles per work item
+constexpr int FLUSH_TILES = 4;                // FP32 chains: 4 tiles * 64 j / 2 lanes-of-f32x2 = 128 terms
+constexpr int NIMAX       = 2048;             // capacity per call (reference: gpunb.velocity.cu:24)
+constexpr int PART_STRIDE = 8;                // doubles per partial record (7 used)
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+
+// ---------------------------------------------------------------------------------------------
+// jpack_kernel: fp64 snapshot -> float-float AoSoA tiles.  Ghost slots (j >= nj) get mass 0 and a
+// far-away position; they are additionally excluded from lists by index.
+// ---------------------------------------------------------------------------------------------
+__global__ void jpack_kernel(int nj, int ntiles, const double *__restrict__ m, const double *__restrict__ x,
+                             const double *__restrict__ v, float *__restrict__ tiles, int *__restrict__ nanflag)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ntiles * TJ) return;
+    float *t = tiles + (size_t)(j / TJ) * TILE_FLOATS + (j % TJ);
+    if (j < nj) {
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            double xd = x[3 * (size_t)j + k], vd = v[3 * (size_t)j + k];
+            float hi = (float)xd;
+            float lo = (float)(xd - (double)hi);
+            t[(0 + k) * TJ] = hi;
+            t[(3 + k) * TJ] = lo;
+            t[(6 + k) * TJ] = (float)vd;
+            bad |= (xd != xd) | (vd != vd);
+        }
+        double md = m[j];
+        t[9 * TJ] = (float)md;
+        bad |= (md != md);
+        if (bad) atomicExch(nanflag, 1);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { t[k * TJ] = 1.0e6f; t[(3 + k) * TJ] = 0.f; t[(6 + k) * TJ] = 0.f; }
+        t[9 * TJ] = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// regf_kernel
+// ---------------------------------------------------------------------------------------------
+struct RegfArgs {
+    const float  *tiles;     // jtile
+    int           ntiles, nj;
+    int           joff;      // global index of this device's first j (multi-GPU shards)
+    // i-particles (fp64, device): element i at h2[i], dtr[i], xi[3i..], vi[3i..]
+    const double *h2, *dtr, *xi, *vi;
+    int           ni, n_itiles, S, n_items;
+    double       *part;      // [S][ni][PART_STRIDE]
+    int          *cnt;       // [S][ni]
+    int          *seg;       // [ni][S][segcap]
+    int           segcap;
+};
+
+struct IState {               // loop invariants of one i-particle, duplicated for f32x2 operands
+    float2 nxh, nyh, nzh;     // -x_i (hi)
+    float2 nxl, nyl, nzl;     // -x_i (lo)
+    float2 nvx, nvy, nvz;     // -v_i
+    float2 dtr, h2;
+};
+struct Acc {                  // FP32 partial chains (f32x2: one chain per j parity)
+    float2 ax, ay, az, p, j1x, j1y, j1z, j2x, j2y, j2z;
+    __device__ __forceinline__ void clear() {
+        ax = ay = az = p = j1x = j1y = j1z = j2x = j2y = j2z = make_float2(0.f, 0.f);
+    }
+};
+
+// One i-particle against a packed pair of j-particles.
+//   Predicate: the reference's, bit for bit, on the fp32-rounded inputs (gpunb.velocity.cu:168-187,
+//   :235 for m_flag): r2 = fma(dz,dz,fma(dy,dy,dx*dx)), dxp = fma(dtr,dvx,dx), min(r2,r2p) < h2 [*mj].
+//   Force: same formula (gpunb.velocity.cu:192-207) but from the float-float dx; the jerk is
+//   accumulated as J1 = sum m r^-3 dv and J2 = sum m r^-5 (r.v) dx, jrk = J1 - 3 J2 at flush.
+//   Pairs at r2 == 0 (self) never contribute (regint.f:40 skips J.EQ.I); the reference GPU code
+//   returns NaN for a self pair with h2 == 0.
+// Returns a 2-bit mask of neighbour hits.
+template <bool MFLAG>
+__device__ __forceinline__ unsigned interact(const IState &I, Acc &A,
+                                             float2 XH, float2 YH, float2 ZH, float2 XL, float2 YL, float2 ZL,
+                                             float2 VX, float2 VY, float2 VZ, float2 M)
+{
+    const float2 dxr = add2(XH, I.nxh), dyr = add2(YH, I.nyh), dzr = add2(ZH, I.nzh);
+    const float2 dx = add2(dxr, add2(XL, I.nxl));
+    const float2 dy = add2(dyr, add2(YL, I.nyl));
+    const float2 dz = add2(dzr, add2(ZL, I.nzl));
+    const float2 dvx = add2(VX, I.nvx), dvy = add2(VY, I.nvy), dvz = add2(VZ, I.nvz);
+
+    const float2 r2r = fma2(dzr, dzr, fma2(dyr, dyr, mul2(dxr, dxr)));
+    const float2 dxp = fma2(I.dtr, dvx, dxr), dyp = fma2(I.dtr, dvy, dyr), dzp = fma2(I.dtr, dvz, dzr);
+    const float2 r2p = fma2(dzp, dzp, fma2(dyp, dyp, mul2(dxp, dxp)));
+    const float2 r2  = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    const float2 rv  = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
+
+    float2 lim = I.h2;
+    if (MFLAG) lim = mul2(M, I.h2);
+    const bool nb0 = fminf(r2r.x, r2p.x) < lim.x;
+    const bool nb1 = fminf(r2r.y, r2p.y) < lim.y;
+    float2 rinv;
+    rinv.x = (nb0 || !(r2.x > 0.f)) ? 0.f : rsqrt_approx(r2.x);
+    rinv.y = (nb1 || !(r2.y > 0.f)) ? 0.f : rsqrt_approx(r2.y);
+
+    const float2 rinv2  = mul2(rinv, rinv);
+    const float2 mrinv  = mul2(M, rinv);
+    const float2 mrinv3 = mul2(mrinv, rinv2);
+    const float2 w      = mul2(mul2(rv, rinv2), mrinv3);
+    A.p   = add2(A.p, mrinv);
+    A.ax  = fma2(mrinv3, dx, A.ax);   A.ay  = fma2(mrinv3, dy, A.ay);   A.az  = fma2(mrinv3, dz, A.az);
+    A.j1x = fma2(mrinv3, dvx, A.j1x); A.j1y = fma2(mrinv3, dvy, A.j1y); A.j1z = fma2(mrinv3, dvz, A.j1z);
+    A.j2x = fma2(w, dx, A.j2x);       A.j2y = fma2(w, dy, A.j2y);       A.j2z = fma2(w, dz, A.j2z);
+    return (nb0 ? 1u : 0u) | (nb1 ? 2u : 0u);
+}
+
+template <bool MFLAG>
+__global__ void __launch_bounds__(WARPS * 32) regf_kernel(const RegfArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * WARPS + warp;
+    if (w >= a.n_items) return;                       // warp-uniform; no CTA-wide barrier is used below
+    float    *buf  = reinterpret_cast<float *>(smem_raw) + warp * NSTAGE * TILE_FLOATS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + WARPS * NSTAGE * TILE_BYTES) + warp * NSTAGE;
+
+    const int it = w / a.S, s = w - it * a.S;
+    const int t0 = (int)(((long long)s * a.ntiles) / a.S);
+    const int t1 = (int)(((long long)(s + 1) * a.ntiles) / a.S);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NSTAGE; k++) mbar_init(&bars[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NSTAGE; k++)
+            if (t0 + k < t1) {
+                mbar_expect_tx(&bars[k], TILE_BYTES);
+                tma_bulk_g2s(buf + k * TILE_FLOATS, a.tiles + (size_t)(t0 + k) * TILE_FLOATS, TILE_BYTES, &bars[k]);
+            }
+    }
+
+    // i-particles of this lane
+    IState I[IT];
+    Acc    A[IT];
+    double D[IT][7];
+    int    cnt[IT];
+    int   *segp[IT];
+    bool   valid[IT];
+#pragma unroll
+    for (int k = 0; k < IT; k++) {
+        const int i = it * ITILE + k * 32 + lane;
+        valid[k] = i < a.ni;
+        double x[3] = {0, 0, 0}, v[3] = {0, 0, 0}, h2 = 0, dtr = 0;
+        if (valid[k]) {
+            h2 = a.h2[i]; dtr = a.dtr[i];
+#pragma unroll
+            for (int c = 0; c < 3; c++) { x[c] = a.xi[3 * (size_t)i + c]; v[c] = a.vi[3 * (size_t)i + c]; }
+        }
+        float xh[3], xl[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { xh[c] = (float)x[c]; xl[c] = (float)(x[c] - (double)xh[c]); }
+        I[k].nxh = dup2(-xh[0]); I[k].nyh = dup2(-xh[1]); I[k].nzh = dup2(-xh[2]);
+        I[k].nxl = dup2(-xl[0]); I[k].nyl = dup2(-xl[1]); I[k].nzl = dup2(-xl[2]);
+        I[k].nvx = dup2(-(float)v[0]); I[k].nvy = dup2(-(float)v[1]); I[k].nvz = dup2(-(float)v[2]);
+        I[k].dtr = dup2((float)dtr);
+        I[k].h2  = dup2(valid[k] ? (float)h2 : 0.f);
+        A[k].clear();
+#pragma unroll
+        for (int c = 0; c < 7; c++) D[k][c] = 0.0;
+        cnt[k]  = 0;
+        segp[k] = a.seg + ((size_t)(valid[k] ? i : 0) * a.S + s) * a.segcap;
+    }
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+            D[k][0] += (double)(A[k].ax.x + A[k].ax.y);
+            D[k][1] += (double)(A[k].ay.x + A[k].ay.y);
+            D[k][2] += (double)(A[k].az.x + A[k].az.y);
+            D[k][3] += (double)(A[k].j1x.x + A[k].j1x.y) - 3.0 * (double)(A[k].j2x.x + A[k].j2x.y);
+            D[k][4] += (double)(A[k].j1y.x + A[k].j1y.y) - 3.0 * (double)(A[k].j2y.x + A[k].j2y.y);
+            D[k][5] += (double)(A[k].j1z.x + A[k].j1z.y) - 3.0 * (double)(A[k].j2z.x + A[k].j2z.y);
+            D[k][6] += (double)(A[k].p.x + A[k].p.y);
+            A[k].clear();
+        }
+    };
+
+    int since_flush = 0;
+    for (int t = t0; t < t1; t++) {
+        const int st = (t - t0) % NSTAGE;
+        const uint32_t parity = ((t - t0) / NSTAGE) & 1;
+        mbar_wait(&bars[st], parity);
+        const float4 *c = reinterpret_cast<const float4 *>(buf + st * TILE_FLOATS);
+        const int jtile0 = t * TJ;
+#pragma unroll 1
+        for (int q = 0; q < TJ / 4; q++) {
+            const float4 XH = c[0 * 16 + q], YH = c[1 * 16 + q], ZH = c[2 * 16 + q];
+            const float4 XL = c[3 * 16 + q], YL = c[4 * 16 + q], ZL = c[5 * 16 + q];
+            const float4 VX = c[6 * 16 + q], VY = c[7 * 16 + q], VZ = c[8 * 16 + q];
+            const float4 M  = c[9 * 16 + q];
+            unsigned hit = 0;
+#pragma unroll
+            for (int k = 0; k < IT; k++) {
+                const unsigned h0 = interact<MFLAG>(I[k], A[k],
+                    make_float2(XH.x, XH.y), make_float2(YH.x, YH.y), make_float2(ZH.x, ZH.y),
+                    make_float2(XL.x, XL.y), make_float2(YL.x, YL.y), make_float2(ZL.x, ZL.y),
+                    make_float2(VX.x, VX.y), make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y),
+                    make_float2(M.x, M.y));
+                const unsigned h1 = interact<MFLAG>(I[k], A[k],
+                    make_float2(XH.z, XH.w), make_float2(YH.z, YH.w), make_float2(ZH.z, ZH.w),
+                    make_float2(XL.z, XL.w), make_float2(YL.z, YL.w), make_float2(ZL.z, ZL.w),
+                    make_float2(VX.z, VX.w), make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w),
+                    make_float2(M.z, M.w));
+                hit |= (h0 | (h1 << 2)) << (4 * k);
+            }
+            if (hit) {                                 // rare: ~2e-4 of pairs are neighbours
+                const int jb = jtile0 + q * 4;
+#pragma unroll
+                for (int k = 0; k < IT; k++) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        if ((hit >> (4 * k + b)) & 1u) {
+                            const int j = jb + b;
+                            if (j < a.nj) {            // ghosts of the last tile are never neighbours
+                                if (cnt[k] < a.segcap) segp[k][cnt[k]] = a.joff + j;
+                                cnt[k]++;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();                                  // every lane is done reading stage st
+        if (lane == 0 && t + NSTAGE < t1) {
+            mbar_expect_tx(&bars[st], TILE_BYTES);
+            tma_bulk_g2s(buf + st * TILE_FLOATS, a.tiles + (size_t)(t + NSTAGE) * TILE_FLOATS, TILE_BYTES, &bars[st]);
+        }
+        if (++since_flush == FLUSH_TILES) { flush(); since_flush = 0; }
+    }
+    flush();
+
+#pragma unroll
+    for (int k = 0; k < IT; k++) {
+        const int i = it * ITILE + k * 32 + lane;
+        if (valid[k]) {
+            double *o = a.part + ((size_t)s * a.ni + i) * PART_STRIDE;
+#pragma unroll
+            for (int c = 0; c < 7; c++) o[c] = D[k][c];
+            a.cnt[(size_t)s * a.ni + i] = cnt[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge_kernel: one warp per i-particle.
+//   fp64 sum over the S slices in a fixed order; scan of the S counts; concatenation of the
+//   segments in slice order, which IS ascending j because slices are contiguous j ranges and
+//   each warp visits its j ascending (the caller's two-pointer list diff needs strictly
+//   ascending order, regcor_gpu.F:299-336).
+//   count > nnbmax  ->  list[0] = -count, no entries written (reg.avx.cpp:320-321).
+// ---------------------------------------------------------------------------------------------
+struct MergeArgs {
+    const double *part; const int *cnt; const int *seg;
+    int ni, S, segcap, lmax, nnbmax;
+    double *res_f;      // [ni][7]
+    int    *res_list;   // [ni][lmax]
+};
+
+__global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= a.ni) return;
+    double f[7] = {0, 0, 0, 0, 0, 0, 0};
+    int total = 0;
+    for (int s = lane; s < a.S; s += 32) {
+        const double *p = a.part + ((size_t)s * a.ni + i) * PART_STRIDE;
+#pragma unroll
+        for (int c = 0; c < 7; c++) f[c] += p[c];
+        total += a.cnt[(size_t)s * a.ni + i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) f[c] += __shfl_xor_sync(0xffffffffu, f[c], o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    if (lane < 7) a.res_f[(size_t)i * 7 + lane] = f[lane];   // f[] is uniform after the butterfly
+    int *row = a.res_list + (size_t)i * a.lmax;
+    if (total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
+    if (lane == 0) row[0] = total;
+    int base = 1;
+    for (int s0 = 0; s0 < a.S; s0 += 32) {
+        const int s = s0 + lane;
+        const int n = (s < a.S) ? a.cnt[(size_t)s * a.ni + i] : 0;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const int off = base + incl - n;
+        const int *src = a.seg + ((size_t)i * a.S + s) * a.segcap;
+        for (int k = 0; k < n; k++) row[off + k] = src[k];
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pot_kernel (gpupot): phi_i = sum_{j, r>0} m_j / r_ij.  Reuses the jtile layout (velocities
+// unused).  Lanes own i-particles, j broadcast from smem tiles staged by the CTA; rsqrt.approx +
+// one Newton step (the AVX twin does the same, pot.avx.cpp:22-25), FP32 chains of 64 terms
+// flushed to fp64.  Work item = (32 i, j-slice); partial sums combined by pot_merge_kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pot_kernel(const float *__restrict__ tiles, int ntiles, int S,
+                                                   int i0, int ni, double *__restrict__ part)
+{
+    __shared__ __align__(16) float sb[4][4 * TJ];        // per warp: xh|yh|zh|... staged 64 j at a time
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 4 + warp;
+    const int n_it = (ni + 31) / 32;
+    if (w >= n_it * S) return;
+    const int it = w / S, s = w - it * S;
+    const int t0 = (int)(((long long)s * ntiles) / S), t1 = (int)(((long long)(s + 1) * ntiles) / S);
+    const int ii = it * 32 + lane;
+    const int i = i0 + (ii < ni ? ii : 0);
+    const float *ti = tiles + (size_t)(i / TJ) * TILE_FLOATS + (i % TJ);
+    const float xh = ti[0], yh = ti[TJ], zh = ti[2 * TJ], xl = ti[3 * TJ], yl = ti[4 * TJ], zl = ti[5 * TJ];
+    double phi = 0.0;
+    float *b = sb[warp];
+    for (int t = t0; t < t1; t++) {
+        const float *tp = tiles + (size_t)t * TILE_FLOATS;
+        __syncwarp();
+        // stage: 7 arrays of 64 floats needed (xh yh zh xl yl zl m); 64 floats = 2 per lane
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int jj = lane + 32 * c;
+            b[jj]          = tp[jj];                 // xh
+            b[TJ + jj]     = tp[TJ + jj];            // yh
+            b[2 * TJ + jj] = tp[2 * TJ + jj];        // zh
+            b[3 * TJ + jj] = tp[9 * TJ + jj];        // m
+        }
+        float lo[6];
+#pragma unroll
+        for (int c = 0; c < 2; c++) { lo[3*c] = tp[3 * TJ + lane + 32 * c]; lo[3*c+1] = tp[4 * TJ + lane + 32 * c]; lo[3*c+2] = tp[5 * TJ + lane + 32 * c]; }
+        __syncwarp();
+        float acc = 0.f;
+#pragma unroll 8
+        for (int jj = 0; jj < TJ; jj++) {
+            const float jxl = __shfl_sync(0xffffffffu, lo[3 * (jj >> 5)],     jj & 31);
+            const float jyl = __shfl_sync(0xffffffffu, lo[3 * (jj >> 5) + 1], jj & 31);
+            const float jzl = __shfl_sync(0xffffffffu, lo[3 * (jj >> 5) + 2], jj & 31);
+            const float dx = (b[jj] - xh) + (jxl - xl);
+            const float dy = (b[TJ + jj] - yh) + (jyl - yl);
+            const float dz = (b[2 * TJ + jj] - zh) + (jzl - zl);
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            float y = rsqrt_approx(r2);
+            y = y * fmaf(-0.5f * r2 * y, y, 1.5f);      // one Newton step
+            acc += (r2 > 0.f) ? b[3 * TJ + jj] * y : 0.f;
+        }
+        phi += (double)acc;
+    }
+    if (ii < ni) part[(size_t)s * ni + ii] = phi;
+}
+
+__global__ void pot_merge_kernel(const double *__restrict__ part, int S, int ni, double *__restrict__ out)
+{
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii >= ni) return;
+    double p = 0.0;
+    for (int s = 0; s < S; s++) p += part[(size_t)s * ni + ii];
+    out[ii] = p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+double wtime() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + 1e-6 * tv.tv_usec; }
+
+struct Dev {
+    int id = -1;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evs0 = nullptr, evs1 = nullptr;
+    int nsm = 0, warps_resident = 0;
+    // j
+    int jcap = 0;                 // capacity in particles (multiple of TJ)
+    double *jraw = nullptr;       // 7*jcap doubles
+    float *jtile = nullptr;
+    double *radii = nullptr;      // h2[jcap] | dtr[jcap]  (resident sweeps)
+    int nj = 0, ntiles = 0, joff = 0;
+    // i
+    double *ibuf = nullptr;       // 8*NIMAX doubles: h2 | dtr | x | v
+    // partials
+    int items_cap = 0;            // work items the partial buffers are sized for
+    double *part = nullptr; int *cnt = nullptr;
+    int *seg = nullptr; int segcap = 0; size_t seg_ints = 0;
+    double *res_f = nullptr; int *res_list = nullptr; size_t res_list_ints = 0;
+    int *nanflag = nullptr;
+    // gpupot scratch
+    double *pot_part = nullptr, *pot_out = nullptr; size_t pot_part_n = 0, pot_out_n = 0;
+};
+
+struct Lib {
+    bool devinit = false, is_open = false;
+    std::vector<Dev> devs;
+    int nbmax = 0, nbody = 0;
+    // pinned staging
+    double *h_j = nullptr; size_t h_j_n = 0;          // 7*jcap doubles
+    double *h_i = nullptr;                            // 8*NIMAX doubles
+    double *h_f = nullptr;                            // 7*NIMAX doubles
+    int *h_list = nullptr; size_t h_list_n = 0;
+    int *h_flag = nullptr;
+    // profile counters (reference: gpunb.velocity.cu:557-559)
+    double time_send = 0, time_grav = 0, time_reduce = 0, time_out = 0;
+    long long numInter = 0; int icall = 0, ini = 0, isend = 0;
+    double ctr[GPUNB_B200_CTR_COUNT] = {0};
+    int last_ni = 0, last_lmax = 0;
+} L;
+
+template <class T> void dev_alloc(T *&p, size_t n) { CUDA_CHECK(cudaMalloc((void **)&p, n * sizeof(T))); }
+template <class T> void dev_free(T *&p) { if (p) CUDA_CHECK(cudaFree(p)); p = nullptr; }
+template <class T> void host_alloc(T *&p, size_t n) { CUDA_CHECK(cudaMallocHost((void **)&p, n * sizeof(T))); }
+template <class T> void host_free(T *&p) { if (p) CUDA_CHECK(cudaFreeHost(p)); p = nullptr; }
+
+void set_dev(const Dev &d) { CUDA_CHECK(cudaSetDevice(d.id)); }
+
+void lib_devinit(int irank)
+{
+    if (L.devinit) return;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        FATAL("no CUDA device available (%s). This library has no CPU fallback.", cudaGetErrorString(e));
+    std::vector<int> ids;
+    const char *gl = getenv("GPU_LIST");               // reference: gpunb.velocity.cu:582-591
+    if (gl && *gl) {
+        char *tmp = strdup(gl);
+        for (char *p = strtok(tmp, " ,"); p; p = strtok(nullptr, " ,")) ids.push_back(atoi(p));
+        free(tmp);
+    } else {
+        for (int i = 0; i < ndev; i++) ids.push_back(i);
+    }
+    // Multi-device j-sharding inside one process is enabled with GPUNB_B200_MULTI=1; default is
+    // the first listed device (one process per GPU, as under MPI or torchrun).
+    const char *multi = getenv("GPUNB_B200_MULTI");
+    if (!(multi && atoi(multi) > 0) && ids.size() > 1) ids.resize(1);
+    char host[150] = {0};
+    gethostname(host, 149);
+    for (size_t k = 0; k < ids.size(); k++) {
+        if (ids[k] < 0 || ids[k] >= ndev) FATAL("GPU_LIST names device %d but only %d are visible", ids[k], ndev);
+        Dev d; d.id = ids[k];
+        cudaDeviceProp prop; CUDA_CHECK(cudaGetDeviceProperties(&prop, d.id));
+        if (prop.major < 10) FATAL("device %d (%s) is sm_%d%d; this library is built for sm_100a only", d.id, prop.name, prop.major, prop.minor);
+        d.nsm = prop.multiProcessorCount;
+        CUDA_CHECK(cudaSetDevice(d.id));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreate(&d.ev0)); CUDA_CHECK(cudaEventCreate(&d.ev1)); CUDA_CHECK(cudaEventCreate(&d.ev2));
+        CUDA_CHECK(cudaEventCreate(&d.evs0)); CUDA_CHECK(cudaEventCreate(&d.evs1));
+        const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
+        int nb0 = 0, nb1 = 0;
+        CUDA_CHECK(cudaFuncSetAttribute(regf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_CHECK(cudaFuncSetAttribute(regf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, regf_kernel<false>, WARPS * 32, smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, regf_kernel<true>, WARPS * 32, smem));
+        const int nb = nb0 < nb1 ? nb0 : nb1;
+        if (nb < 1) FATAL("regf_kernel does not fit on an SM");
+        d.warps_resident = d.nsm * nb * WARPS;
+        fprintf(stderr, "# GPU initialization - rank: %d; HOST %s; NGPU %d; device: %d %s; B200-native regf: %d SMs x %d CTAs x %d warps\n",
+                irank, host, (int)ids.size(), d.id, prop.name, d.nsm, nb, WARPS);
+        L.devs.push_back(d);
+    }
+    CUDA_CHECK(cudaSetDevice(L.devs[0].id));
+    host_alloc(L.h_flag, 16);
+    memset(L.h_flag, 0, 16 * sizeof(int));
+    L.devinit = true;
+}
+
+
+void ensure_j_capacity(Dev &d, int nj)
+{
+    const int need = ((nj + TJ - 1) / TJ) * TJ;
+    if (need <= d.jcap) return;
+    set_dev(d);
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    dev_free(d.jraw); dev_free(d.jtile); dev_free(d.radii);
+    d.jcap = need;
+    dev_alloc(d.jraw, (size_t)7 * d.jcap);
+    dev_alloc(d.jtile, (size_t)(d.jcap / TJ) * TILE_FLOATS);
+    dev_alloc(d.radii, (size_t)2 * d.jcap);
+}
+
+void ensure_work_buffers(Dev &d, int lmax, int nnbmax)
+{
+    set_dev(d);
+    // The product n_itiles * S never exceeds warps_resident (+ n_itiles when S=1 and many i-tiles).
+    const int items = d.warps_resident + NIMAX / ITILE;
+    const int segcap = ((nnbmax > 0 ? nnbmax : 1) + 3) & ~3;
+    if (items > d.items_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        dev_free(d.part); dev_free(d.cnt);
+        d.items_cap = items;
+        dev_alloc(d.part, (size_t)items * ITILE * PART_STRIDE);
+        dev_alloc(d.cnt, (size_t)items * ITILE);
+    }
+    const size_t seg_need = (size_t)d.items_cap * ITILE * segcap;
+    if (seg_need > d.seg_ints) {
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        dev_free(d.seg);
+        d.seg_ints = seg_need;
+        dev_alloc(d.seg, seg_need);
+    }
+    d.segcap = segcap;
+    const size_t rl = (size_t)NIMAX * lmax;
+    if (rl > d.res_list_ints) {
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        dev_free(d.res_list);
+        d.res_list_ints = rl;
+        dev_alloc(d.res_list, rl);
+    }
+    if (rl > L.h_list_n) {
+        host_free(L.h_list);
+        L.h_list_n = rl;
+        host_alloc(L.h_list, rl);
+    }
+}
+
+void lib_open(int nbmax, int irank)
+{
+    L.time_send = L.time_grav = L.time_reduce = L.time_out = 0.0;      // reference: :629-632
+    L.numInter = 0; L.icall = L.ini = L.isend = 0;
+    lib_devinit(irank);
+    if (L.is_open) { fprintf(stderr, "gpunb: it is already open\n"); return; }   // reference: :636-639
+    L.is_open = true;
+    L.nbmax = nbmax;
+    const int G = (int)L.devs.size();
+    for (int g = 0; g < G; g++) {
+        Dev &d = L.devs[g];
+        set_dev(d);
+        const int share = (int)(((long long)(g + 1) * nbmax) / G - ((long long)g * nbmax) / G) + TJ;
+        ensure_j_capacity(d, share);
+        if (!d.ibuf)    dev_alloc(d.ibuf, (size_t)8 * NIMAX);
+        if (!d.res_f)   dev_alloc(d.res_f, (size_t)7 * NIMAX);
+        if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
+    }
+    const size_t hj = (size_t)7 * (((size_t)nbmax + TJ) / TJ + 1) * TJ;
+    if (hj > L.h_j_n) { host_free(L.h_j); L.h_j_n = hj; host_alloc(L.h_j, hj); }
+    if (!L.h_i) host_alloc(L.h_i, (size_t)8 * NIMAX);
+    if (!L.h_f) host_alloc(L.h_f, (size_t)7 * NIMAX);
+    fprintf(stderr, "# Open GPU regular force - rank: %d; nbmax: %d\n", irank, nbmax);
+}
+
+void lib_close()
+{
+    if (!L.is_open) { fprintf(stderr, "gpunb: it is already close\n"); return; }   // reference: :669-672
+    L.is_open = false;
+    for (Dev &d : L.devs) {
+        set_dev(d);
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        dev_free(d.jraw); dev_free(d.jtile); dev_free(d.radii); d.jcap = 0; d.nj = d.ntiles = 0;
+        dev_free(d.ibuf); dev_free(d.part); dev_free(d.cnt); d.items_cap = 0;
+        dev_free(d.seg); d.seg_ints = 0; dev_free(d.res_f); dev_free(d.res_list); d.res_list_ints = 0;
+        dev_free(d.nanflag);
+    }
+    host_free(L.h_j); L.h_j_n = 0; host_free(L.h_i); host_free(L.h_f); host_free(L.h_list); L.h_list_n = 0;
+    L.nbmax = 0;
+}
+
+// Copy the snapshot into pinned staging (m | x | v, each slice contiguous per device), async H2D,
+// convert on the device.  The reference converts fp64->fp32 on ONE host thread per GPU
+// (gpunb.velocity.cu:721-724) and uses a blocking copy (:726).
+void lib_send(int nj, const double *mj, const double *xj, const double *vj)
+{
+    if (!L.is_open) FATAL("gpunb_send called while the library is closed");
+    if (nj > L.nbmax) FATAL("gpunb_send: nj=%d exceeds nbmax=%d given to gpunb_open", nj, L.nbmax);
+    L.time_send -= wtime();
+    L.isend++;
+    L.nbody = nj;
+    const int G = (int)L.devs.size();
+    size_t hoff = 0;
+    for (int g = 0; g < G; g++) {
+        Dev &d = L.devs[g];
+        set_dev(d);
+        const int j0 = (int)(((long long)g * nj) / G), j1 = (int)(((long long)(g + 1) * nj) / G);   // reference: :713-715
+        const int n = j1 - j0;
+        ensure_j_capacity(d, n);
+        d.nj = n; d.ntiles = (n + TJ - 1) / TJ;
+        if (G > 1) d.joff = j0;                 // single-device: joff is owned by gpunb_b200_set_shard
+        double *h = L.h_j + hoff;
+        memcpy(h, mj + j0, sizeof(double) * n);
+        memcpy(h + n, xj + 3 * (size_t)j0, sizeof(double) * 3 * n);
+        memcpy(h + 4 * (size_t)n, vj + 3 * (size_t)j0, sizeof(double) * 3 * n);
+        CUDA_CHECK(cudaMemcpyAsync(d.jraw, h, sizeof(double) * 7 * n, cudaMemcpyHostToDevice, d.st));
+        L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * n;
+        if (d.ntiles > 0) {
+            const int threads = 256, blocks = (d.ntiles * TJ + threads - 1) / threads;
+            jpack_kernel<<<blocks, threads, 0, d.st>>>(n, d.ntiles, d.jraw, d.jraw + n, d.jraw + 4 * (size_t)n, d.jtile, d.nanflag);
+            CUDA_CHECK(cudaGetLastError());
+            L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, d.nanflag, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+        hoff += (size_t)7 * n;
+    }
+    for (int g = 0; g < G; g++) {
+        CUDA_CHECK(cudaStreamSynchronize(L.devs[g].st));
+        if (L.h_flag[g]) FATAL("gpunb_send: NaN in j-particle data (reference asserts here, gpunb.velocity.cu:72-78)");
+    }
+    L.time_send += wtime();
+}
+
+struct Plan { int n_itiles, S, n_items; };
+Plan make_plan(const Dev &d, int ni)
+{
+    Plan p;
+    p.n_itiles = (ni + ITILE - 1) / ITILE;
+    int S = d.warps_resident / p.n_itiles;
+    if (S < 1) S = 1;
+    if (S > d.ntiles) S = d.ntiles > 0 ? d.ntiles : 1;
+    p.S = S;
+    p.n_items = p.n_itiles * S;
+    return p;
+}
+
+// Launch pair kernel + merge kernel for one i-block on device d (async on d.st).
+void launch_regf(Dev &d, int ni, const double *h2, const double *dtr, const double *xi, const double *vi,
+                 int lmax, int nnbmax, int m_flag, bool time_it)
+{
+    const Plan p = make_plan(d, ni);
+    RegfArgs a;
+    a.tiles = d.jtile; a.ntiles = d.ntiles; a.nj = d.nj; a.joff = d.joff;
+    a.h2 = h2; a.dtr = dtr; a.xi = xi; a.vi = vi;
+    a.ni = ni; a.n_itiles = p.n_itiles; a.S = p.S; a.n_items = p.n_items;
+    a.part = d.part; a.cnt = d.cnt; a.seg = d.seg; a.segcap = d.segcap;
+    const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
+    const int blocks = (p.n_items + WARPS - 1) / WARPS;
+    if (time_it) CUDA_CHECK(cudaEventRecord(d.ev0, d.st));
+    if (m_flag) regf_kernel<true><<<blocks, WARPS * 32, smem, d.st>>>(a);
+    else        regf_kernel<false><<<blocks, WARPS * 32, smem, d.st>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    if (time_it) CUDA_CHECK(cudaEventRecord(d.ev1, d.st));
+    MergeArgs m;
+    m.part = d.part; m.cnt = d.cnt; m.seg = d.seg; m.ni = ni; m.S = p.S; m.segcap = d.segcap;
+    m.lmax = lmax; m.nnbmax = nnbmax; m.res_f = d.res_f; m.res_list = d.res_list;
+    merge_kernel<<<(ni + 3) / 4, 128, 0, d.st>>>(m);
+    CUDA_CHECK(cudaGetLastError());
+    if (time_it) CUDA_CHECK(cudaEventRecord(d.ev2, d.st));
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
+}
+
+void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, const double *vi,
+              double *acc, double *jrk, double *pot, int lmax, int nnbmax, int *list, int m_flag)
+{
+    if (!L.is_open) FATAL("gpunb_regf called while the library is closed");
+    if (!(0 < ni && ni <= NIMAX)) FATAL("gpunb_regf: ni=%d out of range (0, %d]", ni, NIMAX);
+    if (nnbmax + 1 > lmax) FATAL("gpunb_regf: nnbmax=%d does not fit rows of lmax=%d", nnbmax, lmax);
+    if (L.devs.size() != 1) FATAL("in-process multi-device combine is not built yet (unset GPUNB_B200_MULTI)");
+    L.time_grav -= wtime();
+    L.numInter += (long long)ni * L.nbody;       // reference counts every pair, self included (:747)
+    L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)ni * L.nbody;
+    L.ini += ni; L.icall++;
+
+    Dev &d = L.devs[0];
+    set_dev(d);
+    ensure_work_buffers(d, lmax, nnbmax);
+    // NaN check + pack of the i-block (reference asserts per element, gpunb.velocity.cu:109-115)
+    double *h = L.h_i;
+    memcpy(h, h2, sizeof(double) * ni);
+    memcpy(h + ni, dtr, sizeof(double) * ni);
+    memcpy(h + 2 * (size_t)ni, xi, sizeof(double) * 3 * ni);
+    memcpy(h + 5 * (size_t)ni, vi, sizeof(double) * 3 * ni);
+    for (int k = 0; k < 8 * ni; k++) if (h[k] != h[k]) FATAL("gpunb_regf: NaN in i-particle data");
+    CUDA_CHECK(cudaMemcpyAsync(d.ibuf, h, sizeof(double) * 8 * ni, cudaMemcpyHostToDevice, d.st));
+    L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 8.0 * ni;
+
+    launch_regf(d, ni, d.ibuf, d.ibuf + ni, d.ibuf + 2 * (size_t)ni, d.ibuf + 5 * (size_t)ni, lmax, nnbmax, m_flag, true);
+
+    CUDA_CHECK(cudaMemcpyAsync(L.h_f, d.res_f, sizeof(double) * 7 * ni, cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaMemcpyAsync(L.h_list, d.res_list, sizeof(int) * (size_t)ni * lmax, cudaMemcpyDeviceToHost, d.st));
+    L.ctr[GPUNB_B200_CTR_D2H_BYTES] += sizeof(double) * 7.0 * ni + sizeof(int) * (double)ni * lmax;
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev0, d.ev1)); L.ctr[GPUNB_B200_CTR_GRAV_MS] += ms;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev1, d.ev2)); L.ctr[GPUNB_B200_CTR_MERGE_MS] += ms;
+    L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += 1;
+
+    const double wt = wtime();
+    L.time_grav += wt; L.time_reduce -= wt;
+    for (int i = 0; i < ni; i++) {
+        const double *f = L.h_f + 7 * (size_t)i;
+        acc[3 * i] = f[0]; acc[3 * i + 1] = f[1]; acc[3 * i + 2] = f[2];
+        jrk[3 * i] = f[3]; jrk[3 * i + 1] = f[4]; jrk[3 * i + 2] = f[5];
+        pot[i] = f[6];
+        const int *src = L.h_list + (size_t)i * lmax;
+        int *dst = list + (size_t)i * lmax;
+        const int n = src[0];
+        dst[0] = n;
+        if (n > 0) memcpy(dst + 1, src + 1, sizeof(int) * n);
+    }
+    L.time_reduce += wtime();
+    L.last_ni = ni; L.last_lmax = lmax;
+}
+
+void lib_profile(int irank)
+{
+    if (L.icall) {        // same line format as the reference (gpunb.velocity.cu:894)
+        fprintf(stderr, "[R.%d GPU Reg.F ] Nsend %d  Ngrav %d  <Ni> %d   send(s) %f grav(s) %f  nb(s) %f  out(s) %f  Perf.(Gflops) %f\n",
+                irank, L.isend, L.icall, L.isend ? L.ini / L.isend : L.ini, L.time_send, L.time_grav, L.time_reduce, L.time_out,
+                60.e-9 * L.numInter / L.time_grav);
+    }
+    L.time_send = L.time_grav = L.time_reduce = L.time_out = 0.0;
+    L.numInter = 0; L.icall = L.ini = L.isend = 0;
+}
+
+// gpupot: may be called with the library closed (reference: gpupot.gpu.cu:69 only needs devinit).
+void lib_pot(int irank, int istart, int ni, int n, const double *m, const double *x, double *pot)
+{
+    lib_devinit(irank);
+    const double t0 = wtime();
+    if (ni <= 0) return;
+    if (istart < 1 || istart - 1 + ni > n) FATAL("gpupot: istart=%d ni=%d outside 1..n=%d", istart, ni, n);
+    Dev &d = L.devs[0];
+    set_dev(d);
+    // private buffers so that gpupot never disturbs the regf j-snapshot
+    static double *jraw = nullptr; static float *jtile = nullptr; static int cap = 0; static double *hpin = nullptr; static size_t hpin_n = 0;
+    const int ntiles = (n + TJ - 1) / TJ;
+    if (ntiles * TJ > cap) {
+        dev_free(jraw); dev_free(jtile);
+        cap = ntiles * TJ;
+        dev_alloc(jraw, (size_t)4 * cap); dev_alloc(jtile, (size_t)ntiles * TILE_FLOATS);
+    }
+    if ((size_t)4 * n + ni > hpin_n) { host_free(hpin); hpin_n = (size_t)4 * n + ni + 1024; host_alloc(hpin, hpin_n); }
+    if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
+    memcpy(hpin, m, sizeof(double) * n);
+    memcpy(hpin + n, x, sizeof(double) * 3 * n);
+    CUDA_CHECK(cudaMemcpyAsync(jraw, hpin, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, d.st));
+    // velocities are not needed: pass the position array as "v" (finite, ignored by pot_kernel)
+    jpack_kernel<<<(ntiles * TJ + 255) / 256, 256, 0, d.st>>>(n, ntiles, jraw, jraw + n, jraw + n, jtile, d.nanflag);
+    CUDA_CHECK(cudaGetLastError());
+    const int n_it = (ni + 31) / 32;
+    int S = (d.nsm * 16 * 4) / n_it; if (S < 1) S = 1; if (S > ntiles) S = ntiles;
+    if ((size_t)S * ni > d.pot_part_n) { dev_free(d.pot_part); d.pot_part_n = (size_t)S * ni; dev_alloc(d.pot_part, d.pot_part_n); }
+    if ((size_t)ni > d.pot_out_n) { dev_free(d.pot_out); d.pot_out_n = ni; dev_alloc(d.pot_out, d.pot_out_n); }
+    CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
+    pot_kernel<<<(n_it * S + 3) / 4, 128, 0, d.st>>>(jtile, ntiles, S, istart - 1, ni, d.pot_part);
+    CUDA_CHECK(cudaGetLastError());
+    pot_merge_kernel<<<(ni + 127) / 128, 128, 0, d.st>>>(d.pot_part, S, ni, d.pot_out);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(d.evs1, d.st));
+    double *hout = hpin + 4 * (size_t)n;
+    CUDA_CHECK(cudaMemcpyAsync(hout, d.pot_out, sizeof(double) * ni, cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaMemcpyAsync(L.h_flag, d.nanflag, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    if (L.h_flag[0]) FATAL("gpupot: NaN in particle data");
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, d.evs0, d.evs1));
+    L.ctr[GPUNB_B200_CTR_POT_MS] += ms;
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 3;
+    L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 4.0 * n;
+    L.ctr[GPUNB_B200_CTR_D2H_BYTES] += sizeof(double) * (double)ni;
+    memcpy(pot, hout, sizeof(double) * ni);
+    const double t1 = wtime();
+    fprintf(stderr, "[R.%d GPU Pot.A] Ni %d  NTOT %d  pot(s) %f\n", irank, ni, n, t1 - t0);   // reference: gpupot.gpu.cu:112
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+void gpunb_devinit_(int *irank) { lib_devinit(*irank); }
+void gpunb_open_(int *nbmax, int *irank) { lib_open(*nbmax, *irank); }
+void gpunb_close_(void) { lib_close(); }
+void gpunb_send_(int *nj, double mj[], double xj[][3], double vj[][3]) { lib_send(*nj, mj, &xj[0][0], &vj[0][0]); }
+void gpunb_regf_(int *ni, double h2[], double dtr[], double xi[][3], double vi[][3], double acc[][3], double jrk[][3],
+                 double pot[], int *lmax, int *nnbmax, int *list, int *m_flag)
+{
+    lib_regf(*ni, h2, dtr, &xi[0][0], &vi[0][0], &acc[0][0], &jrk[0][0], pot, *lmax, *nnbmax, list, *m_flag);
+}
+void gpunb_profile_(int *irank) { lib_profile(*irank); }
+void gpupot_(int *irank, int *istart, int *ni, int *n, double m[], double x[][3], double pot[])
+{
+    lib_pot(*irank, *istart, *ni, *n, m, &x[0][0], pot);
+}
+
+int gpunb_b200_version(void) { return 100; }
+const char *gpunb_b200_build_info(void)
+{
+    return "gpunb_b200 sm_100a: regf_kernel<f32x2, TMA bulk j-tiles, IT=2, TJ=64>, merge_kernel, pot_kernel, jpack_kernel";
+}
+int gpunb_b200_num_devices(void) { return (int)L.devs.size(); }
+void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]) { for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) out[k] = L.ctr[k]; }
+void gpunb_b200_reset_counters(void) { for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) L.ctr[k] = 0; }
+
+void gpunb_b200_set_radii(int *njp, double h2[], double dtr[])
+{
+    if (!L.is_open) FATAL("gpunb_b200_set_radii: library closed");
+    Dev &d = L.devs[0];
+    const int nj = *njp;
+    if (nj != d.nj) FATAL("gpunb_b200_set_radii: nj=%d differs from the snapshot (%d)", nj, d.nj);
+    set_dev(d);
+    CUDA_CHECK(cudaMemcpyAsync(d.radii, h2, sizeof(double) * nj, cudaMemcpyHostToDevice, d.st));
+    CUDA_CHECK(cudaMemcpyAsync(d.radii + d.jcap, dtr, sizeof(double) * nj, cudaMemcpyHostToDevice, d.st));
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+}
+
+float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int *nnbmaxp, int *m_flagp)
+{
+    if (!L.is_open) FATAL("gpunb_b200_sweep_resident: library closed");
+    Dev &d = L.devs[0];
+    set_dev(d);
+    const int i0 = *i0p, ni = *nip, block = *blockp;
+    if (i0 < 0 || i0 + ni > d.nj || block < 1 || block > NIMAX) FATAL("gpunb_b200_sweep_resident: bad range");
+    ensure_work_buffers(d, *lmaxp, *nnbmaxp);
+    const double *x = d.jraw + d.nj, *v = d.jraw + 4 * (size_t)d.nj;
+    CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
+    int nlaunch = 0, last = 0;
+    for (int b = i0; b < i0 + ni; b += block) {
+        const int n = (i0 + ni - b < block) ? i0 + ni - b : block;
+        launch_regf(d, n, d.radii + b, d.radii + d.jcap + b, x + 3 * (size_t)b, v + 3 * (size_t)b, *lmaxp, *nnbmaxp, *m_flagp, false);
+        L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)n * d.nj;
+        nlaunch++; last = n;
+    }
+    CUDA_CHECK(cudaEventRecord(d.evs1, d.st));
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, d.evs0, d.evs1));
+    L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += nlaunch;
+    L.last_ni = last; L.last_lmax = *lmaxp;
+    return ms;
+}
+
+void gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double pot[], int *lmaxp, int *list)
+{
+    Dev &d = L.devs[0];
+    set_dev(d);
+    const int ni = L.last_ni, lmax = L.last_lmax;
+    *n_last = ni; *lmaxp = lmax;
+    if (ni <= 0) return;
+    CUDA_CHECK(cudaMemcpyAsync(L.h_f, d.res_f, sizeof(double) * 7 * ni, cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaMemcpyAsync(L.h_list, d.res_list, sizeof(int) * (size_t)ni * lmax, cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    for (int i = 0; i < ni; i++) {
+        const double *f = L.h_f + 7 * (size_t)i;
+        for (int c = 0; c < 3; c++) { acc[i][c] = f[c]; jrk[i][c] = f[3 + c]; }
+        pot[i] = f[6];
+        const int *src = L.h_list + (size_t)i * lmax;
+        list[(size_t)i * lmax] = src[0];
+        if (src[0] > 0) memcpy(list + (size_t)i * lmax + 1, src + 1, sizeof(int) * src[0]);
+    }
+}
+
+void gpunb_b200_set_shard(int joff_global)
+{
+    if (!L.devinit) FATAL("gpunb_b200_set_shard before devinit");
+    L.devs[0].joff = joff_global;
+}
+
+}  // extern "C"

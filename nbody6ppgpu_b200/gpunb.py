@@ -1,0 +1,212 @@
+"""ctypes mirror of the regular-force C-ABI.
+
+``ForceLib(path)`` binds ANY shared library that exports the reference's seven symbols
+(gpunb_devinit_ is optional, reg.avx.cpp does not have it), so the same Python calls drive
+
+* ``nbody6ppgpu_b200/libgpunb_b200.so``  -- this repo's CUDA library (the product),
+* ``oracle/_ref/libgpunb_ref_avx.so``    -- the reference's CPU library (tests / CPU baseline only),
+* ``oracle/_ref/libgpunb_ref_gpu.so``    -- the reference's CUDA library (tests / comparison only).
+
+Argument meaning follows the reference (src/Main/gpunb.velocity.cu:904-939, gpupot.gpu.cu:116-127):
+all scalars by reference, REAL*8 arrays, ``X(3,N)`` == C ``x[N][3]``, neighbour rows ``list[i*lmax]``
+= count (negative on overflow) followed by 0-based ascending j.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_c_int_p = C.POINTER(C.c_int)
+_c_dbl_p = C.POINTER(C.c_double)
+
+N_COUNTERS = 8
+CTR = dict(grav_ms=0, grav_launches=1, launches=2, h2d_bytes=3, d2h_bytes=4, interactions=5,
+           merge_ms=6, pot_ms=7)
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _HERE / "libgpunb_b200.so"
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_c_dbl_p)
+
+
+def _f64(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class ForceLib:
+    """One loaded regular-force library (file-static state, like the reference: one per process)."""
+
+    def __init__(self, path: os.PathLike | str, mode: int = C.RTLD_LOCAL):
+        path = Path(path)
+        if not path.exists():
+            raise LibraryMissing(f"{path} not found -- build it first (python -c 'import __graft_entry__ as g; g.build()')")
+        self.path = path
+        self.lib = C.CDLL(str(path), mode=mode)
+        L = self.lib
+        self.has_devinit = hasattr(L, "gpunb_devinit_")
+        self.is_b200 = hasattr(L, "gpunb_b200_version")
+        L.gpunb_open_.argtypes = [_c_int_p, _c_int_p]
+        L.gpunb_close_.argtypes = []
+        L.gpunb_send_.argtypes = [_c_int_p, _c_dbl_p, _c_dbl_p, _c_dbl_p]
+        L.gpunb_regf_.argtypes = [_c_int_p] + [_c_dbl_p] * 7 + [_c_int_p, _c_int_p, _c_int_p, _c_int_p]
+        L.gpunb_profile_.argtypes = [_c_int_p]
+        L.gpupot_.argtypes = [_c_int_p] * 4 + [_c_dbl_p] * 3
+        for f in (L.gpunb_open_, L.gpunb_close_, L.gpunb_send_, L.gpunb_regf_, L.gpunb_profile_, L.gpupot_):
+            f.restype = None
+        if self.has_devinit:
+            L.gpunb_devinit_.argtypes = [_c_int_p]
+            L.gpunb_devinit_.restype = None
+        if self.is_b200:
+            L.gpunb_b200_version.restype = C.c_int
+            L.gpunb_b200_build_info.restype = C.c_char_p
+            L.gpunb_b200_num_devices.restype = C.c_int
+            L.gpunb_b200_get_counters.argtypes = [_c_dbl_p]
+            L.gpunb_b200_set_radii.argtypes = [_c_int_p, _c_dbl_p, _c_dbl_p]
+            L.gpunb_b200_sweep_resident.argtypes = [_c_int_p] * 6
+            L.gpunb_b200_sweep_resident.restype = C.c_float
+            L.gpunb_b200_fetch_last.argtypes = [_c_int_p, _c_dbl_p, _c_dbl_p, _c_dbl_p, _c_int_p, _c_int_p]
+            L.gpunb_b200_fp32_microbench.argtypes = [C.c_int, C.c_int]
+            L.gpunb_b200_fp32_microbench.restype = C.c_double
+            L.gpunb_b200_nccl_unique_id.argtypes = [C.c_char_p]
+            L.gpunb_b200_nccl_unique_id.restype = C.c_int
+            L.gpunb_b200_nccl_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
+            L.gpunb_b200_nccl_init.restype = C.c_int
+            L.gpunb_b200_set_shard.argtypes = [C.c_int]
+        self.nj = 0
+
+    # ---- the reference interface -------------------------------------------------------------
+    def devinit(self, irank: int = 0):
+        if self.has_devinit:
+            self.lib.gpunb_devinit_(C.byref(C.c_int(irank)))
+
+    def open(self, nbmax: int, irank: int = 0):
+        self.lib.gpunb_open_(C.byref(C.c_int(nbmax)), C.byref(C.c_int(irank)))
+
+    def close(self):
+        self.lib.gpunb_close_()
+
+    def send(self, m, x, v):
+        m = _f64(m)
+        nj = m.shape[0]
+        x = _f64(x, (nj, 3))
+        v = _f64(v, (nj, 3))
+        self.nj = nj
+        self.lib.gpunb_send_(C.byref(C.c_int(nj)), _dp(m), _dp(x), _dp(v))
+
+    def regf(self, h2, dtr, xi, vi, lmax: int, nnbmax: int, m_flag: int = 0, pad: int = 8):
+        """Returns (acc[ni,3], jrk[ni,3], pot[ni], list[ni,lmax]).
+
+        ``pad`` extra rows are allocated behind every array because the reference's AVX library
+        reads/writes up to 3 elements past ni (reg.avx.cpp:204-314); rows >= ni are never returned.
+        """
+        h2 = _f64(h2)
+        ni = h2.shape[0]
+        n = ni + pad
+
+        def padded(a, shape):
+            out = np.zeros((n,) + shape, dtype=np.float64)
+            out[:ni] = _f64(a, (ni,) + shape)
+            return out
+
+        h2p, dtrp = padded(h2, ()), padded(dtr, ())
+        xip, vip = padded(xi, (3,)), padded(vi, (3,))
+        acc = np.zeros((n, 3)); jrk = np.zeros((n, 3)); pot = np.zeros(n)
+        lst = np.zeros((n, lmax), dtype=np.int32)
+        self.lib.gpunb_regf_(C.byref(C.c_int(ni)), _dp(h2p), _dp(dtrp), _dp(xip), _dp(vip),
+                             _dp(acc), _dp(jrk), _dp(pot),
+                             C.byref(C.c_int(lmax)), C.byref(C.c_int(nnbmax)),
+                             lst.ctypes.data_as(_c_int_p), C.byref(C.c_int(m_flag)))
+        return acc[:ni], jrk[:ni], pot[:ni], lst[:ni]
+
+    def profile(self, irank: int = 0):
+        self.lib.gpunb_profile_(C.byref(C.c_int(irank)))
+
+    def gpupot(self, istart: int, ni: int, m, x, irank: int = 0, pad: int = 8):
+        """pot[ii] = sum_{j, r>0} m_j / r_ij for i = istart-1+ii (istart is 1-based)."""
+        m = _f64(m)
+        n = m.shape[0]
+        # pot.avx.cpp:90-137 reads ptcl[i..i+7] and writes pot[i..i+7] past ni: pad both.
+        mp = np.zeros(n + pad); mp[:n] = m
+        xp = np.zeros((n + pad, 3)); xp[:n] = _f64(x, (n, 3))
+        # Quirk of the reference: the CUDA library (and the MPI caller, energy_mpi.F:100-101, which passes
+        # phidbl(istart+ifirst-1)) index pot[] RELATIVE to istart (gpupot.gpu.cu:102-105); the AVX twin
+        # writes pot[istart-1+ii] (pot.avx.cpp:88-137: pot_reduce(..., pot+i) with absolute i).  This
+        # library follows the CUDA/caller convention; the wrapper hides the AVX twin's offset.
+        avx_abs = (not self.is_b200) and (not self.has_devinit)
+        pot = np.zeros((n if avx_abs else ni) + pad)
+        self.lib.gpupot_(C.byref(C.c_int(irank)), C.byref(C.c_int(istart)), C.byref(C.c_int(ni)),
+                         C.byref(C.c_int(n)), _dp(mp), _dp(xp), _dp(pot))
+        return pot[istart - 1:istart - 1 + ni].copy() if avx_abs else pot[:ni]
+
+    # ---- gpunb_b200 extensions ---------------------------------------------------------------
+    def _need_b200(self):
+        if not self.is_b200:
+            raise RuntimeError(f"{self.path.name} is not libgpunb_b200.so")
+
+    def version(self) -> int:
+        self._need_b200()
+        return int(self.lib.gpunb_b200_version())
+
+    def build_info(self) -> str:
+        self._need_b200()
+        return self.lib.gpunb_b200_build_info().decode()
+
+    def num_devices(self) -> int:
+        self._need_b200()
+        return int(self.lib.gpunb_b200_num_devices())
+
+    def counters(self) -> dict:
+        self._need_b200()
+        buf = np.zeros(N_COUNTERS)
+        self.lib.gpunb_b200_get_counters(_dp(buf))
+        return {k: float(buf[i]) for k, i in CTR.items()}
+
+    def reset_counters(self):
+        self._need_b200()
+        self.lib.gpunb_b200_reset_counters()
+
+    def set_radii(self, h2, dtr):
+        self._need_b200()
+        h2 = _f64(h2); dtr = _f64(dtr)
+        self.lib.gpunb_b200_set_radii(C.byref(C.c_int(h2.shape[0])), _dp(h2), _dp(dtr))
+
+    def sweep_resident(self, i0: int, ni: int, block: int, lmax: int, nnbmax: int, m_flag: int = 0) -> float:
+        """Device-resident regular-force sweep over i = j[i0:i0+ni]; returns device milliseconds."""
+        self._need_b200()
+        a = [C.c_int(v) for v in (i0, ni, block, lmax, nnbmax, m_flag)]
+        return float(self.lib.gpunb_b200_sweep_resident(*[C.byref(v) for v in a]))
+
+    def fetch_last(self, lmax: int, nimax: int = 2048):
+        self._need_b200()
+        acc = np.zeros((nimax, 3)); jrk = np.zeros((nimax, 3)); pot = np.zeros(nimax)
+        lst = np.zeros((nimax, lmax), dtype=np.int32)
+        n = C.c_int(0); lm = C.c_int(lmax)
+        self.lib.gpunb_b200_fetch_last(C.byref(n), _dp(acc), _dp(jrk), _dp(pot), C.byref(lm),
+                                       lst.ctypes.data_as(_c_int_p))
+        if lm.value != lmax:
+            raise ValueError("lmax differs from the one used by the sweep")
+        k = n.value
+        return acc[:k], jrk[:k], pot[:k], lst[:k]
+
+    def fp32_microbench(self, mode: int, iters: int = 4096) -> float:
+        self._need_b200()
+        return float(self.lib.gpunb_b200_fp32_microbench(mode, iters))
+
+
+def load() -> ForceLib:
+    """Load this repo's CUDA library; raises LibraryMissing (no fallback) when it is not built."""
+    return ForceLib(lib_path())

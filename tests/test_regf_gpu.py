@@ -1,0 +1,197 @@
+"""GPU parity: libgpunb_b200.so (through the C-ABI) against the oracle on identical snapshots.
+
+Bars (BASELINE.json north_star):
+  * neighbour lists bit-exact in membership and order vs the reference FP32 predicate
+    (gpunb.velocity.cu:168-187); pairs within BAND_ULP ulps of the RS boundary are the stated
+    band and are reported, not tolerated silently: rows may differ ONLY if the oracle saw a
+    pair inside the band on that row;
+  * acc / jrk / pot within 1e-6 relative (per-particle vector norm, max over i) of the fp64
+    statement (regint.f:39-79).
+"""
+import numpy as np
+import pytest
+
+import oracle_lib
+from nbody6ppgpu_b200 import snapshots as S
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.0e-6      # north_star: relative force/jerk/potential error vs fp64
+BAND_ULP = 4.0    # stated ulp band of the RS boundary
+
+
+def check_block(b200, oracle, m, x, v, h2, dtr, isel, lmax, nnbmax, m_flag, tol=TOL):
+    xi, vi = x[isel], v[isel]
+    acc, jrk, pot, lst = b200.regf(h2[isel], dtr[isel], xi, vi, lmax, nnbmax, m_flag)
+    a64, j64, p64, l64, band, nband = oracle.regf_f64(m, x, v, h2[isel], dtr[isel], xi, vi, lmax, nnbmax, m_flag, BAND_ULP)
+    bad = oracle_lib.list_rows_equal(lst, l64)
+    outside = [i for i in bad if band[i] > BAND_ULP]
+    assert not outside, f"{len(outside)} list rows differ outside the {BAND_ULP}-ulp band (first: {outside[:5]})"
+    # ascending order, the caller's list diff depends on it (regcor_gpu.F:299-336)
+    for i in range(lst.shape[0]):
+        n = lst[i, 0]
+        if n > 1:
+            assert np.all(np.diff(lst[i, 1:1 + n]) > 0)
+    ok = lst[:, 0] >= 0
+    if bad:   # force oracle over OUR membership for the rows inside the band
+        a64, j64, p64 = oracle.regf_f64_given_list(m, x, v, xi, vi, np.where(ok[:, None], lst, l64))
+    # rows in overflow carry forces over the full predicate membership as well
+    ea, ej, ep = oracle_lib.relerr(acc, a64), oracle_lib.relerr(jrk, j64), oracle_lib.relerr(pot, p64)
+    assert ea <= tol and ej <= tol and ep <= tol, (ea, ej, ep)
+    return dict(err=(ea, ej, ep), band_rows=len(bad), nband=nband, mean_nnb=float(np.abs(lst[:, 0]).mean()))
+
+
+@pytest.mark.parametrize("n,imf,m_flag", [(2048, "equal", 0), (2048, "kroupa", 1), (16384, "kroupa", 0), (16384, "kroupa", 1)])
+def test_parity_plummer(b200, oracle, n, imf, m_flag):
+    m, x, v = S.plummer(n, 1, imf)
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 100.0), 0.125, m_flag)
+    b200.open(n + 10, 0)
+    b200.send(m, x, v)
+    try:
+        for i0 in (0, n - 1024):
+            r = check_block(b200, oracle, m, x, v, h2, dtr, slice(i0, i0 + 1024), 400, 350, m_flag)
+            print(n, imf, m_flag, r)
+    finally:
+        b200.close()
+
+
+@pytest.mark.parametrize("ni", [1, 3, 63, 64, 65, 1023, 1024, 2048])
+def test_ragged_ni(b200, oracle, ni):
+    n = 4099                      # odd nj: the AVX twin pads here (reg.avx.cpp:154-158); last tile is ragged
+    m, x, v = S.plummer(n, 2, "kroupa")
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 60.0))
+    b200.open(n + 10, 0)
+    b200.send(m, x, v)
+    try:
+        check_block(b200, oracle, m, x, v, h2, dtr, slice(7, 7 + ni), 400, 350, 0)
+    finally:
+        b200.close()
+
+
+def test_i_not_in_j_and_gathered(b200, oracle):
+    """i-particles that are NOT members of the j set, in scrambled order (util_gpu.F:41-56 gathers)."""
+    n = 8192
+    m, x, v = S.plummer(n, 3, "kroupa")
+    rng = np.random.default_rng(5)
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 80.0))
+    b200.open(n + 10, 0)
+    b200.send(m[:6000], x[:6000], v[:6000])
+    try:
+        isel = rng.permutation(np.arange(5000, 8192))[:700]
+        xi, vi = x[isel], v[isel]
+        acc, jrk, pot, lst = b200.regf(h2[isel], dtr[isel], xi, vi, 400, 350, 0)
+        a64, j64, p64, l64, band, _ = oracle.regf_f64(m[:6000], x[:6000], v[:6000], h2[isel], dtr[isel], xi, vi, 400, 350, 0, BAND_ULP)
+        bad = [i for i in oracle_lib.list_rows_equal(lst, l64) if band[i] > BAND_ULP]
+        assert not bad
+        assert oracle_lib.relerr(acc, a64) <= TOL and oracle_lib.relerr(jrk, j64) <= TOL and oracle_lib.relerr(pot, p64) <= TOL
+    finally:
+        b200.close()
+
+
+def test_overflow_encoding(b200, oracle):
+    """count > nnbmax -> list[0] = -(count) (reg.avx.cpp:320-321); RS shrink and retry (util_gpu.F:66-101)."""
+    n = 4096
+    m, x, v = S.plummer(n, 4, "equal")
+    h2, dtr = S.radii(x, m, 0.6)          # huge spheres: hundreds to thousands of neighbours
+    b200.open(n + 10, 0)
+    b200.send(m, x, v)
+    try:
+        ni = 256
+        acc, jrk, pot, lst = b200.regf(h2[:ni], dtr[:ni], x[:ni], v[:ni], 128, 78, 0)
+        _, _, _, l64, band, _ = oracle.regf_f64(m, x, v, h2[:ni], dtr[:ni], x[:ni], v[:ni], 128, 78, 0, BAND_ULP)
+        assert (l64[:, 0] < 0).any(), "test must exercise overflow"
+        assert not [i for i in oracle_lib.list_rows_equal(lst, l64) if band[i] > BAND_ULP]
+        # caller's retry: shrink RS like util_gpu.F:83-87 until no row overflows
+        h2r = h2[:ni].copy()
+        for _ in range(20):
+            acc, jrk, pot, lst = b200.regf(h2r, dtr[:ni], x[:ni], v[:ni], 128, 78, 0)
+            over = lst[:, 0] < 0
+            if not over.any():
+                break
+            h2r[over] *= (0.9 * (78.0 / -lst[over, 0]) ** (1.0 / 3.0)) ** 2
+        assert not (lst[:, 0] < 0).any()
+        check_block(b200, oracle, m, x, v, np.concatenate([h2r, h2[ni:]]), dtr, slice(0, ni), 128, 78, 0)
+        # everything inside the sphere: h2 enormous -> every j (but no ghost) is a neighbour
+        acc, jrk, pot, lst = b200.regf(np.full(4, 1e12), dtr[:4], x[:4], v[:4], 128, 78, 0)
+        assert (lst[:, 0] == -n).all()
+        assert np.all(acc == 0) and np.all(pot == 0)
+    finally:
+        b200.close()
+
+
+def test_h2_zero_duplicates_and_ghost_masses(b200, oracle):
+    n = 3000
+    m, x, v = S.plummer(n, 6, "kroupa")
+    x[10] = x[11]                    # duplicate positions
+    m[20:30] = 0.0                   # zero-mass ghosts
+    x[20:30] += 100.0
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 50.0))
+    h2[:8] = 0.0                     # empty neighbour sphere: self pair must not poison the sums
+    b200.open(n + 10, 0)
+    b200.send(m, x, v)
+    try:
+        acc, jrk, pot, lst = b200.regf(h2[:64], dtr[:64], x[:64], v[:64], 400, 350, 0)
+        a64, j64, p64, l64, band, _ = oracle.regf_f64(m, x, v, h2[:64], dtr[:64], x[:64], v[:64], 400, 350, 0, BAND_ULP)
+        assert np.isfinite(acc).all() and np.isfinite(jrk).all() and np.isfinite(pot).all()
+        assert (lst[:8, 0] == 0).all()
+        assert not [i for i in oracle_lib.list_rows_equal(lst, l64) if band[i] > BAND_ULP]
+        assert oracle_lib.relerr(acc, a64) <= TOL and oracle_lib.relerr(pot, p64) <= TOL
+    finally:
+        b200.close()
+
+
+def test_lifecycle_tolerance(b200):
+    """Double open / double close only warn (gpunb.velocity.cu:636-639, :669-672); nj may change between sends."""
+    m, x, v = S.plummer(1024, 7, "equal")
+    h2, dtr = S.radii(x, m, 0.2)
+    b200.open(1100, 0)
+    b200.open(1100, 0)
+    b200.send(m, x, v)
+    r1 = b200.regf(h2[:100], dtr[:100], x[:100], v[:100], 400, 350, 0)
+    b200.send(m[:700], x[:700], v[:700])
+    r2 = b200.regf(h2[:100], dtr[:100], x[:100], v[:100], 400, 350, 0)
+    assert (r2[3][:, 0] <= r1[3][:, 0]).all() and r2[3][:, 1:].max() < 700
+    b200.profile(0)
+    b200.close()
+    b200.close()
+    b200.open(1100, 0)
+    b200.send(m, x, v)
+    r3 = b200.regf(h2[:100], dtr[:100], x[:100], v[:100], 400, 350, 0)
+    assert np.array_equal(r1[0], r3[0]) and np.array_equal(r1[3], r3[3])   # deterministic
+    b200.close()
+
+
+def test_against_reference_avx_library(b200, ref_avx):
+    """Same snapshot through both libraries' identical C-ABI: lists identical, forces within the FP32
+    accumulation error of the REFERENCE (~1e-5 at large N)."""
+    n = 16384
+    m, x, v = S.plummer(n, 8, "kroupa")
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 100.0), 0.125, 1)
+    out = {}
+    for name, lib in (("b200", b200), ("avx", ref_avx)):
+        lib.open(n + 10, 0)
+        lib.send(m, x, v)
+        out[name] = lib.regf(h2[:1024], dtr[:1024], x[:1024], v[:1024], 400, 350, 1)
+        lib.close()
+    bad = oracle_lib.list_rows_equal(out["b200"][3], out["avx"][3])
+    assert len(bad) <= 1, bad            # band flips only (contraction order of r2 may differ by 1 ulp)
+    assert oracle_lib.relerr(out["b200"][0], out["avx"][0]) < 3e-5
+    assert oracle_lib.relerr(out["b200"][2], out["avx"][2]) < 3e-5
+
+
+def test_resident_sweep_matches_abi(b200):
+    n = 8192
+    m, x, v = S.plummer(n, 9, "kroupa")
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 100.0))
+    b200.open(n + 10, 0)
+    b200.send(m, x, v)
+    try:
+        b200.set_radii(h2, dtr)
+        ms = b200.sweep_resident(0, n, 1024, 400, 350, 0)
+        assert ms > 0
+        a, j, p, l = b200.fetch_last(400)
+        a2, j2, p2, l2 = b200.regf(h2[n - 1024:], dtr[n - 1024:], x[n - 1024:], v[n - 1024:], 400, 350, 0)
+        assert np.array_equal(a, a2) and np.array_equal(j, j2) and np.array_equal(p, p2)
+        assert not oracle_lib.list_rows_equal(l, l2)
+    finally:
+        b200.close()
