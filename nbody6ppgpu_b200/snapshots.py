@@ -100,3 +100,19 @@ def rs0_for_nnb(n: int, nnb: float) -> float:
     """
     a = 3.0 * np.pi / 16.0
     return a * (nnb / n) ** (1.0 / 3.0)
+
+
+def radii_nnb(x: np.ndarray, m: np.ndarray, nnb: float, smax: float = 0.125, m_flag: int = 0):
+    """Neighbour spheres holding about `nnb` members everywhere: RS_i from the local Plummer density,
+    n(r) = 3N/(4 pi a^3) (1 + r^2/a^2)^(-5/2), a = 3 pi/16 -- the state the integrator's RS control
+    (NNBOPT, regcor_gpu.F:623-760) converges to, as opposed to FPOLY0's first guess RS0 sqrt(1+r^2).
+    dtr as in fpoly0.F:53-56."""
+    n = x.shape[0]
+    a = 3.0 * np.pi / 16.0
+    ri2 = (x * x).sum(1)
+    rs = a * (nnb / n) ** (1.0 / 3.0) * (1.0 + ri2 / (a * a)) ** (5.0 / 6.0)
+    dtr = np.minimum(smax / 8.0 * np.sqrt(1.0 + ri2), smax)
+    h2 = rs * rs
+    if m_flag:
+        h2 = h2 / m.mean()
+    return h2, dtr

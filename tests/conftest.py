@@ -4,6 +4,9 @@ from pathlib import Path
 
 import pytest
 
+# the reference AVX library asserts omp threads <= 32 (reg.avx.cpp:7,103); set before libgomp loads
+os.environ["OMP_NUM_THREADS"] = str(max(1, min(len(os.sched_getaffinity(0)), 32)))
+
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))

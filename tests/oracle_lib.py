@@ -55,11 +55,12 @@ class Oracle:
         acc = np.zeros((ni, 3)); jrk = np.zeros((ni, 3)); pot = np.zeros(ni)
         lst = np.zeros((ni, lmax), dtype=np.int32)
         band = np.zeros(ni, dtype=np.float32)
+        self.scale = np.zeros((ni, 2))
         nband = C.c_longlong(0)
         self.lib.oracle_regf_f64(C.c_int(ni), C.c_int(nj), _d(m), _d(x), _d(v), _d(h2), _d(dtr), _d(xi), _d(vi),
                                  _d(acc), _d(jrk), _d(pot), C.c_int(lmax), C.c_int(nnbmax),
                                  lst.ctypes.data_as(_ip), C.c_int(m_flag),
-                                 band.ctypes.data_as(_fp), C.c_float(band_k), C.byref(nband))
+                                 band.ctypes.data_as(_fp), C.c_float(band_k), C.byref(nband), _d(self.scale))
         return acc, jrk, pot, lst, band, int(nband.value)
 
     def regf_f64_given_list(self, m, x, v, xi, vi, lst):
@@ -68,8 +69,9 @@ class Oracle:
         lst = np.ascontiguousarray(lst, dtype=np.int32)
         ni, nj, lmax = xi.shape[0], m.shape[0], lst.shape[1]
         acc = np.zeros((ni, 3)); jrk = np.zeros((ni, 3)); pot = np.zeros(ni)
+        self.scale = np.zeros((ni, 2))
         self.lib.oracle_regf_f64_given_list(C.c_int(ni), C.c_int(nj), _d(m), _d(x), _d(v), _d(xi), _d(vi),
-                                            _d(acc), _d(jrk), _d(pot), C.c_int(lmax), lst.ctypes.data_as(_ip))
+                                            _d(acc), _d(jrk), _d(pot), C.c_int(lmax), lst.ctypes.data_as(_ip), _d(self.scale))
         return acc, jrk, pot
 
     def pot_f64(self, istart, ni, m, x):
@@ -106,6 +108,14 @@ def relerr(a, b):
     if a.ndim == 1:
         return float(np.max(np.abs(a - b) / np.abs(b)))
     return float(np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)))
+
+
+def relerr_scaled(a, b, scale):
+    """max over rows of |a-b| / max(|b|, scale): `scale` is the quadrature sum of the row's pair terms
+    (Oracle.scale), the natural magnitude of a random-walk sum.  Equals relerr() except for rows whose
+    fp64 sum cancels below that magnitude, where no FP32 pair arithmetic can hold 1e-6 of |b|."""
+    d = np.linalg.norm(np.asarray(a) - np.asarray(b), axis=1)
+    return float(np.max(d / np.maximum(np.linalg.norm(b, axis=1), scale)))
 
 
 def list_rows_equal(la, lb):
