@@ -112,9 +112,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_THREADS = None
+
+
 def cpu_threads():
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    return max(1, min(n, 32))                 # reg.avx.cpp:7,103 asserts threads <= TMAX = 32
+    """Host threads for the AVX baseline, read ONCE (OMP_PROC_BIND later narrows the main thread's affinity)."""
+    global _THREADS
+    if _THREADS is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        _THREADS = max(1, min(n, 32))         # reg.avx.cpp:7,103 asserts threads <= TMAX = 32
+    return _THREADS
 
 
 def load_reference_avx():

@@ -52,8 +52,7 @@ constexpr int TILE_FLOATS = TJ * NCOMP;       // 640
 constexpr int TILE_BYTES  = TILE_FLOATS * 4;  // 2560
 constexpr int NSTAGE      = 2;                // smem stages per warp
 constexpr int WARPS       = 4;                // warps per CTA (warp-autonomous: no CTA-wide sync)
-constexpr int IT          = 2;                // i-particles per lane
-constexpr int ITILE       = 32 * IT;          // i-particles per work item
+constexpr int ITILE_MAX   = 64;               // largest i-tile of any kernel variant (32 lanes * IT)
 constexpr int FLUSH_TILES = 4;                // FP32 chains: 4 tiles * 64 j / 2 lanes-of-f32x2 = 128 terms
 constexpr int NIMAX       = 2048;             // capacity per call (reference: gpunb.velocity.cu:24)
 constexpr int PART_STRIDE = 8;                // doubles per partial record (7 used)
@@ -189,6 +188,9 @@ __device__ __forceinline__ unsigned interact(const IState &I, Acc &A,
     rinv.x = (nb0 || !(r2.x > 0.f)) ? 0.f : rsqrt_approx(r2.x);
     rinv.y = (nb1 || !(r2.y > 0.f)) ? 0.f : rsqrt_approx(r2.y);
 
+    // one Newton step: y <- y - y/2 (r2 y^2 - 1); rsqrt.approx alone (2^-22.9) leaves 5 ulp on the r^-5 term
+    const float2 e = fma2(mul2(r2, rinv), rinv, dup2(-1.f));
+    rinv = fma2(mul2(rinv, e), dup2(-0.5f), rinv);
     const float2 rinv2  = mul2(rinv, rinv);
     const float2 mrinv  = mul2(M, rinv);
     const float2 mrinv3 = mul2(mrinv, rinv2);
@@ -200,9 +202,10 @@ __device__ __forceinline__ unsigned interact(const IState &I, Acc &A,
     return (nb0 ? 1u : 0u) | (nb1 ? 2u : 0u);
 }
 
-template <bool MFLAG>
-__global__ void __launch_bounds__(WARPS * 32) regf_kernel(const RegfArgs a)
+template <int IT, bool MFLAG, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a)
 {
+    constexpr int ITILE = 32 * IT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * WARPS + warp;
@@ -464,11 +467,25 @@ __global__ void pot_merge_kernel(const double *__restrict__ part, int S, int ni,
 // ---------------------------------------------------------------------------------------------
 double wtime() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + 1e-6 * tv.tv_usec; }
 
+// Kernel variants (i-particles per lane x minimum resident CTAs per SM); GPUNB_B200_VARIANT selects one by
+// name for tuning runs, the default is the fastest measured on B200 (see profiles/).
+typedef void (*RegfKernel)(const RegfArgs);
+struct Variant { const char *name; int it; RegfKernel k[2]; };
+const Variant VARIANTS[] = {
+    {"it2",   2, {regf_kernel<2, false, 1>, regf_kernel<2, true, 1>}},
+    {"it2b3", 2, {regf_kernel<2, false, 3>, regf_kernel<2, true, 3>}},
+    {"it1",   1, {regf_kernel<1, false, 1>, regf_kernel<1, true, 1>}},
+    {"it1b5", 1, {regf_kernel<1, false, 5>, regf_kernel<1, true, 5>}},
+    {"it1b6", 1, {regf_kernel<1, false, 6>, regf_kernel<1, true, 6>}},
+};
+constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
+constexpr int DEFAULT_VARIANT = 2;     // it1: best at small ni, equal at ni=1024 (profiles/r01b_variants.txt)
+
 struct Dev {
     int id = -1;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evs0 = nullptr, evs1 = nullptr;
-    int nsm = 0, warps_resident = 0;
+    int nsm = 0, warps_resident = 0, variant = DEFAULT_VARIANT, itile = 32;
     // j
     int jcap = 0;                 // capacity in particles (multiple of TJ)
     double *jraw = nullptr;       // 7*jcap doubles
@@ -544,16 +561,26 @@ void lib_devinit(int irank)
         CUDA_CHECK(cudaEventCreate(&d.ev0)); CUDA_CHECK(cudaEventCreate(&d.ev1)); CUDA_CHECK(cudaEventCreate(&d.ev2));
         CUDA_CHECK(cudaEventCreate(&d.evs0)); CUDA_CHECK(cudaEventCreate(&d.evs1));
         const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
-        int nb0 = 0, nb1 = 0;
-        CUDA_CHECK(cudaFuncSetAttribute(regf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUDA_CHECK(cudaFuncSetAttribute(regf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, regf_kernel<false>, WARPS * 32, smem));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, regf_kernel<true>, WARPS * 32, smem));
-        const int nb = nb0 < nb1 ? nb0 : nb1;
+        const char *vn = getenv("GPUNB_B200_VARIANT");
+        if (vn && *vn) {
+            int f = -1;
+            for (int q = 0; q < NVARIANTS; q++) if (!strcmp(vn, VARIANTS[q].name)) f = q;
+            if (f < 0) FATAL("GPUNB_B200_VARIANT=%s is not a kernel variant", vn);
+            d.variant = f;
+        }
+        const Variant &V = VARIANTS[d.variant];
+        d.itile = 32 * V.it;
+        int nb = 1 << 30;
+        for (int q = 0; q < 2; q++) {
+            int nbq = 0;
+            CUDA_CHECK(cudaFuncSetAttribute(V.k[q], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbq, V.k[q], WARPS * 32, smem));
+            if (nbq < nb) nb = nbq;
+        }
         if (nb < 1) FATAL("regf_kernel does not fit on an SM");
         d.warps_resident = d.nsm * nb * WARPS;
-        fprintf(stderr, "# GPU initialization - rank: %d; HOST %s; NGPU %d; device: %d %s; B200-native regf: %d SMs x %d CTAs x %d warps\n",
-                irank, host, (int)ids.size(), d.id, prop.name, d.nsm, nb, WARPS);
+        fprintf(stderr, "# GPU initialization - rank: %d; HOST %s; NGPU %d; device: %d %s; B200-native regf[%s]: %d SMs x %d CTAs x %d warps\n",
+                irank, host, (int)ids.size(), d.id, prop.name, V.name, d.nsm, nb, WARPS);
         L.devs.push_back(d);
     }
     CUDA_CHECK(cudaSetDevice(L.devs[0].id));
@@ -580,6 +607,7 @@ void ensure_work_buffers(Dev &d, int lmax, int nnbmax)
 {
     set_dev(d);
     // The product n_itiles * S never exceeds warps_resident (+ n_itiles when S=1 and many i-tiles).
+    const int ITILE = d.itile;
     const int items = d.warps_resident + NIMAX / ITILE;
     const int segcap = ((nnbmax > 0 ? nnbmax : 1) + 3) & ~3;
     if (items > d.items_cap) {
@@ -698,7 +726,7 @@ struct Plan { int n_itiles, S, n_items; };
 Plan make_plan(const Dev &d, int ni)
 {
     Plan p;
-    p.n_itiles = (ni + ITILE - 1) / ITILE;
+    p.n_itiles = (ni + d.itile - 1) / d.itile;
     int S = d.warps_resident / p.n_itiles;
     if (S < 1) S = 1;
     if (S > d.ntiles) S = d.ntiles > 0 ? d.ntiles : 1;
@@ -720,8 +748,7 @@ void launch_regf(Dev &d, int ni, const double *h2, const double *dtr, const doub
     const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
     const int blocks = (p.n_items + WARPS - 1) / WARPS;
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev0, d.st));
-    if (m_flag) regf_kernel<true><<<blocks, WARPS * 32, smem, d.st>>>(a);
-    else        regf_kernel<false><<<blocks, WARPS * 32, smem, d.st>>>(a);
+    VARIANTS[d.variant].k[m_flag ? 1 : 0]<<<blocks, WARPS * 32, smem, d.st>>>(a);
     CUDA_CHECK(cudaGetLastError());
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev1, d.st));
     MergeArgs m;
@@ -872,7 +899,7 @@ void gpupot_(int *irank, int *istart, int *ni, int *n, double m[], double x[][3]
 int gpunb_b200_version(void) { return 100; }
 const char *gpunb_b200_build_info(void)
 {
-    return "gpunb_b200 sm_100a: regf_kernel<f32x2, TMA bulk j-tiles, IT=2, TJ=64>, merge_kernel, pot_kernel, jpack_kernel";
+    return "gpunb_b200 sm_100a: regf_kernel<f32x2, TMA bulk j-tiles, TJ=64>, merge_kernel, pot_kernel, jpack_kernel";
 }
 int gpunb_b200_num_devices(void) { return (int)L.devs.size(); }
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]) { for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) out[k] = L.ctr[k]; }
