@@ -207,19 +207,38 @@ def main():
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    if world > 1:
-        raise SystemExit("bench.py: multi-GPU j-sharding over NCCL is not wired yet")
     os.environ["GPU_LIST"] = str(local)              # same mechanism as the reference (gpunb.velocity.cu:582-591)
     torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from nbody6ppgpu_b200 import load
     lib = load()
     lib.devinit(rank)
+    if world > 1:                                    # j sharded over ranks, every rank makes identical calls
+        from nbody6ppgpu_b200.sharding import nccl_bootstrap
+        nccl_bootstrap(lib, rank, world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(val):
+        if dist is None:
+            return val
+        t = torch.tensor([val], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     n = args.n
     ni_total = args.ni_total if args.ni_total > 0 else n
     m, x, v, h2, dtr, rs0 = make_snapshot(n, args.m_flag)
     lib.open(n + 10, rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    interactions_scale = 1.0 / world                 # roofline per GPU: each rank's kernel sums nj/world j
 
     def flush_l2():
         flush.fill_(rank + 1)
@@ -235,7 +254,9 @@ def main():
     ms_steps = []
     for _ in range(args.steps):
         flush_l2()
-        ms_steps.append(lib.sweep_resident(0, ni_total, BLOCK, LMAX, NNBMAX, args.m_flag))
+        barrier()
+        ms_steps.append(max_over_ranks(lib.sweep_resident(0, ni_total, BLOCK, LMAX, NNBMAX, args.m_flag)))
+        barrier()
     clocks = sampler.stop()
     c_res = lib.counters()
     inter_step = float(ni_total) * n
@@ -253,7 +274,7 @@ def main():
     c_probe = lib.counters()
     kern_ms = c_probe["grav_ms"] / c_probe["grav_launches"]
     merge_ms = c_probe["merge_ms"] / c_probe["grav_launches"]
-    int_per_launch = float(BLOCK) * n
+    int_per_launch = float(BLOCK) * n * interactions_scale
 
     # ---------------- end-to-end leg through the C-ABI with host buffers: `e2e` ----------------
     def abi_step():
@@ -275,9 +296,12 @@ def main():
     nnb_sum = 0
     for _ in range(e2e_steps):
         flush_l2()
+        barrier()
         t0 = time.perf_counter()
         nnb_sum = abi_step()
-        t_e2e += time.perf_counter() - t0
+        torch.cuda.synchronize()
+        t_e2e += max_over_ranks(time.perf_counter() - t0)
+        barrier()
     c_e2e = lib.counters()
     e2e_val = inter_step * e2e_steps / t_e2e * 1e-9
     lib.profile(rank)
@@ -285,13 +309,19 @@ def main():
     # ---------------- FP32 pipe microbenchmark (roofline denominator measured in the same run) ----------------
     ffma_tflops = max(lib.fp32_microbench(0, 8192) for _ in range(3))
     lib.close()
+    if world > 1:
+        barrier()
+        lib.nccl_finalize()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
 
     peaks, peak_src = measured_peaks()
     sm_max = clocks.get("sm_max_mhz") or 1965.0
     fp32_nominal = 2.0 * 128 * 148 * sm_max * 1e6 * 1e-12
     achieved_tflops = FLOP_PER_INT * int_per_launch / (kern_ms * 1e-3) * 1e-12
     mean_nnb = nnb_sum / float(ni_total)
-    alg_bytes = n * 40.0 + BLOCK * (64.0 + 56.0 + 4.0 * (1 + mean_nnb))     # j tiles once + i in + forces/list out
+    alg_bytes = n * interactions_scale * 40.0 + BLOCK * (64.0 + 56.0 + 4.0 * (1 + mean_nnb))     # j tiles once + i in + forces/list out
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
         "bound": "fp32", "kernel": "regf_kernel", "achieved": achieved_tflops, "peak": fp32_nominal, "unit": "TFLOP/s",

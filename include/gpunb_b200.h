@@ -89,13 +89,21 @@ void  gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], doubl
  * (mode 0: FFMA, 1: FFMA2 (f32x2), 2: FADD2, 3: FMUL2, 4: MUFU.RSQ Gop/s, 5: FFMA2+ALU mix). */
 double gpunb_b200_fp32_microbench(int mode, int iters);
 
-/* Multi-process j-sharding over NCCL (one process per GPU).  id128 is a 128-byte ncclUniqueId
- * created by rank 0 (gpunb_b200_nccl_unique_id) and broadcast by the caller. After init, each
- * rank sends ITS OWN j-shard (global index offset joff) and every rank calls regf with the same
- * i-block; rank 0 receives the combined result. */
+/* Multi-GPU j-sharding (the exchange step of the path; reference: the j split over GPUs inside
+ * gpunb.velocity.cu:713-715 and its host-side fp64 combine :822-879).
+ *
+ *  (A) one process, several GPUs (the reference's own model): export GPUNB_B200_MULTI=1 (and optionally
+ *      GPU_LIST); nothing else changes for the caller.  Shards are combined by a kernel on the first GPU
+ *      that pulls partial sums and neighbour rows from the peers over NVLink P2P.
+ *  (B) one process per GPU (MPI / torchrun): rank 0 creates a 128-byte ncclUniqueId with
+ *      gpunb_b200_nccl_unique_id, the caller broadcasts it, every rank calls gpunb_b200_nccl_init after
+ *      gpunb_devinit_ and before gpunb_open_.  From then on EVERY rank makes identical calls (same snapshot,
+ *      same i-blocks) and every rank receives the complete result; rank r sums over j in
+ *      [r*nj/R, (r+1)*nj/R).  Partials (64 B per i) travel by ncclAllGather, neighbour rows are pulled from
+ *      cudaIpc-mapped peer memory by the combine kernel.
+ * Return 0 on success. */
 int  gpunb_b200_nccl_unique_id(unsigned char id128[128]);
 int  gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128]);
-void gpunb_b200_set_shard(int joff_global);
 void gpunb_b200_nccl_finalize(void);
 
 #ifdef __cplusplus

@@ -37,6 +37,7 @@
 #include <vector>
 #include <sys/time.h>
 #include <unistd.h>
+#include <dlfcn.h>
 #include "../../include/gpunb_b200.h"
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -355,7 +356,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
 struct MergeArgs {
     const double *part; const int *cnt; const int *seg;
     int ni, S, segcap, lmax, nnbmax;
-    double *res_f;      // [ni][7]
+    double *res_f;      // [ni][f_stride]; f_stride = 8 stores the (signed) count in slot 7 for the shard combine
+    int     f_stride;
     int    *res_list;   // [ni][lmax]
 };
 
@@ -378,7 +380,8 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
         for (int c = 0; c < 7; c++) f[c] += __shfl_xor_sync(0xffffffffu, f[c], o);
         total += __shfl_xor_sync(0xffffffffu, total, o);
     }
-    if (lane < 7) a.res_f[(size_t)i * 7 + lane] = f[lane];   // f[] is uniform after the butterfly
+    if (lane < 7) a.res_f[(size_t)i * a.f_stride + lane] = f[lane];   // f[] is uniform after the butterfly
+    if (a.f_stride == 8 && lane == 7) a.res_f[(size_t)i * 8 + 7] = (double)(total > a.nnbmax ? -total : total);
     int *row = a.res_list + (size_t)i * a.lmax;
     if (total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
     if (lane == 0) row[0] = total;
@@ -393,6 +396,55 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
         const int *src = a.seg + ((size_t)i * a.S + s) * a.segcap;
         for (int k = 0; k < n; k++) row[off + k] = src[k];
         base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// combine_kernel: j-shard exchange step (multi-GPU).  Every shard r (a GPU holding j in
+// [r*nj/R, (r+1)*nj/R), reference split: gpunb.velocity.cu:713-715) has produced, per i-particle,
+// 7 fp64 partial sums + its signed neighbour count (fr[r][i][8]) and an ascending row of GLOBAL j
+// indices (rows[r][i][lmax]).  One warp per i: fp64 sum over shards in rank order (the reference
+// sums GPUs in fp64 on the host, :823-845), counts scanned in rank order, rows concatenated -- rank
+// order is ascending j, so the concatenation is the index-ordered merge (:852-871).
+// fr[r] / rows[r] are PEER pointers (NVLink P2P: cudaIpc-mapped across processes, or peer-enabled
+// devices of one process): the kernel pulls only the `count` valid entries of each remote row, so the
+// exchange moves ~4*nnb bytes per i instead of whole rows.  Overflow: any shard negative or
+// total > nnbmax -> -(sum |count_r|) (reg.avx.cpp:320-321 encoding of the true count).
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_RANKS = 16;
+struct CombineArgs {
+    int ni, R, lmax, nnbmax;
+    const double *fr[MAX_RANKS];     // [ni][8]
+    const int    *rows[MAX_RANKS];   // [ni][lmax]
+    double *res_f;                   // [ni][7]
+    int    *res_list;                // [ni][lmax]
+};
+
+__global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= a.ni) return;
+    double f = 0.0;
+    int total = 0;
+    bool over = false;
+    int off[MAX_RANKS], cnt[MAX_RANKS];
+    for (int r = 0; r < a.R; r++) {
+        const double *p = a.fr[r] + (size_t)i * 8;
+        if (lane < 7) f += p[lane];
+        const int c = (int)p[7];
+        over |= c < 0;
+        cnt[r] = c < 0 ? -c : c;
+        off[r] = 1 + total;
+        total += cnt[r];
+    }
+    if (lane < 7) a.res_f[(size_t)i * 7 + lane] = f;
+    int *row = a.res_list + (size_t)i * a.lmax;
+    if (over || total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
+    if (lane == 0) row[0] = total;
+    for (int r = 0; r < a.R; r++) {
+        const int *src = a.rows[r] + (size_t)i * a.lmax + 1;
+        for (int k = lane; k < cnt[r]; k += 32) row[off[r] + k] = src[k];
     }
 }
 
@@ -461,7 +513,6 @@ __global__ void pot_merge_kernel(const double *__restrict__ part, int S, int ni,
     for (int s = 0; s < S; s++) p += part[(size_t)s * ni + ii];
     out[ii] = p;
 }
-
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
@@ -476,46 +527,66 @@ const Variant VARIANTS[] = {
     {"it2b3", 2, {regf_kernel<2, false, 3>, regf_kernel<2, true, 3>}},
     {"it1",   1, {regf_kernel<1, false, 1>, regf_kernel<1, true, 1>}},
     {"it1b5", 1, {regf_kernel<1, false, 5>, regf_kernel<1, true, 5>}},
-    {"it1b6", 1, {regf_kernel<1, false, 6>, regf_kernel<1, true, 6>}},
 };
 constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
 constexpr int DEFAULT_VARIANT = 2;     // it1: best at small ni, equal at ni=1024 (profiles/r01b_variants.txt)
+constexpr int ROWS_LMAX_CAP = 1024;    // row stride capacity of the IPC-exported shard rows (NCCL mode)
 
 struct Dev {
     int id = -1;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evs0 = nullptr, evs1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs0 = nullptr, evs1 = nullptr, evdone = nullptr;
     int nsm = 0, warps_resident = 0, variant = DEFAULT_VARIANT, itile = 32;
-    // j
-    int jcap = 0;                 // capacity in particles (multiple of TJ)
-    double *jraw = nullptr;       // 7*jcap doubles
+    // j: full fp64 snapshot (m | x | v, packed for the current nj_total) and the tiles of this device's shard
+    int raw_cap = 0, tile_cap = 0;
+    double *jraw = nullptr;
     float *jtile = nullptr;
-    double *radii = nullptr;      // h2[jcap] | dtr[jcap]  (resident sweeps)
-    int nj = 0, ntiles = 0, joff = 0;
-    // i
+    double *radii = nullptr;      // h2[raw_cap] | dtr[raw_cap]  (resident sweeps)
+    int nj_total = 0, j0 = 0, nj = 0, ntiles = 0;
     double *ibuf = nullptr;       // 8*NIMAX doubles: h2 | dtr | x | v
-    // partials
-    int items_cap = 0;            // work items the partial buffers are sized for
+    int items_cap = 0;
     double *part = nullptr; int *cnt = nullptr;
     int *seg = nullptr; int segcap = 0; size_t seg_ints = 0;
-    double *res_f = nullptr; int *res_list = nullptr; size_t res_list_ints = 0;
+    double *res_f = nullptr; int *res_list = nullptr; size_t res_list_ints = 0;   // final results (root)
+    double *fr = nullptr;         // [NIMAX][8] shard partial + count (multi-GPU)
+    int *rows = nullptr; size_t rows_ints = 0;                                     // shard rows (in-process multi-GPU)
     int *nanflag = nullptr;
-    // gpupot scratch
     double *pot_part = nullptr, *pot_out = nullptr; size_t pot_part_n = 0, pot_out_n = 0;
+};
+
+// NCCL types / entry points, resolved with dlopen so that the library has no link-time NCCL dependency
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int (*pfn_ncclGetUniqueId)(ncclUniqueId *);
+typedef int (*pfn_ncclCommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+typedef int (*pfn_ncclAllGather)(const void *, void *, size_t, int /*datatype*/, ncclComm_t, cudaStream_t);
+typedef int (*pfn_ncclCommDestroy)(ncclComm_t);
+typedef const char *(*pfn_ncclGetErrorString)(int);
+constexpr int NCCL_INT8 = 0, NCCL_FLOAT64 = 8;
+
+struct Shard {                     // one process per GPU, j sharded over ranks
+    bool on = false;
+    int rank = 0, R = 1;
+    void *dl = nullptr;
+    pfn_ncclGetUniqueId getid = nullptr; pfn_ncclCommInitRank init = nullptr; pfn_ncclAllGather allgather = nullptr;
+    pfn_ncclCommDestroy destroy = nullptr; pfn_ncclGetErrorString errstr = nullptr;
+    ncclComm_t comm = nullptr;
+    double *fr_all = nullptr;      // [R][NIMAX*8]
+    int *rows_local = nullptr;     // [2][NIMAX][ROWS_LMAX_CAP], exported with cudaIpc
+    int *rows_peer[MAX_RANKS] = {nullptr};
+    int parity = 0;
 };
 
 struct Lib {
     bool devinit = false, is_open = false;
     std::vector<Dev> devs;
+    Shard sh;
     int nbmax = 0, nbody = 0;
-    // pinned staging
-    double *h_j = nullptr; size_t h_j_n = 0;          // 7*jcap doubles
-    double *h_i = nullptr;                            // 8*NIMAX doubles
-    double *h_f = nullptr;                            // 7*NIMAX doubles
+    double *h_j = nullptr; size_t h_j_n = 0;          // pinned staging: 7*nj doubles
+    double *h_i = nullptr, *h_f = nullptr;            // 8*NIMAX, 7*NIMAX doubles
     int *h_list = nullptr; size_t h_list_n = 0;
     int *h_flag = nullptr;
-    // profile counters (reference: gpunb.velocity.cu:557-559)
-    double time_send = 0, time_grav = 0, time_reduce = 0, time_out = 0;
+    double time_send = 0, time_grav = 0, time_reduce = 0, time_out = 0;      // reference: gpunb.velocity.cu:557-559
     long long numInter = 0; int icall = 0, ini = 0, isend = 0;
     double ctr[GPUNB_B200_CTR_COUNT] = {0};
     int last_ni = 0, last_lmax = 0;
@@ -527,6 +598,7 @@ template <class T> void host_alloc(T *&p, size_t n) { CUDA_CHECK(cudaMallocHost(
 template <class T> void host_free(T *&p) { if (p) CUDA_CHECK(cudaFreeHost(p)); p = nullptr; }
 
 void set_dev(const Dev &d) { CUDA_CHECK(cudaSetDevice(d.id)); }
+int  total_ranks() { return L.sh.on ? L.sh.R : (int)L.devs.size(); }
 
 void lib_devinit(int irank)
 {
@@ -544,10 +616,12 @@ void lib_devinit(int irank)
     } else {
         for (int i = 0; i < ndev; i++) ids.push_back(i);
     }
-    // Multi-device j-sharding inside one process is enabled with GPUNB_B200_MULTI=1; default is
-    // the first listed device (one process per GPU, as under MPI or torchrun).
+    // One process driving several GPUs (the reference's gpunb.velocity.cu model, j split across them) is
+    // enabled with GPUNB_B200_MULTI=1; default is the first listed device (one process per GPU, as under
+    // MPI or torchrun, where ranks are joined with gpunb_b200_nccl_init).
     const char *multi = getenv("GPUNB_B200_MULTI");
     if (!(multi && atoi(multi) > 0) && ids.size() > 1) ids.resize(1);
+    if ((int)ids.size() > MAX_RANKS) ids.resize(MAX_RANKS);
     char host[150] = {0};
     gethostname(host, 149);
     for (size_t k = 0; k < ids.size(); k++) {
@@ -558,8 +632,9 @@ void lib_devinit(int irank)
         d.nsm = prop.multiProcessorCount;
         CUDA_CHECK(cudaSetDevice(d.id));
         CUDA_CHECK(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
-        CUDA_CHECK(cudaEventCreate(&d.ev0)); CUDA_CHECK(cudaEventCreate(&d.ev1)); CUDA_CHECK(cudaEventCreate(&d.ev2));
-        CUDA_CHECK(cudaEventCreate(&d.evs0)); CUDA_CHECK(cudaEventCreate(&d.evs1));
+        cudaEvent_t *evs[] = {&d.ev0, &d.ev1, &d.ev2, &d.ev3, &d.evs0, &d.evs1};
+        for (cudaEvent_t *ev : evs) CUDA_CHECK(cudaEventCreate(ev));
+        CUDA_CHECK(cudaEventCreateWithFlags(&d.evdone, cudaEventDisableTiming));
         const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
         const char *vn = getenv("GPUNB_B200_VARIANT");
         if (vn && *vn) {
@@ -583,41 +658,61 @@ void lib_devinit(int irank)
                 irank, host, (int)ids.size(), d.id, prop.name, V.name, d.nsm, nb, WARPS);
         L.devs.push_back(d);
     }
+    // in-process multi-GPU: the root device pulls shard results over NVLink P2P
+    for (size_t g = 1; g < L.devs.size(); g++) {
+        int can = 0;
+        CUDA_CHECK(cudaDeviceCanAccessPeer(&can, L.devs[0].id, L.devs[g].id));
+        if (!can) FATAL("device %d cannot access device %d (P2P needed for the j-shard combine)", L.devs[0].id, L.devs[g].id);
+        CUDA_CHECK(cudaSetDevice(L.devs[0].id));
+        cudaError_t pe = cudaDeviceEnablePeerAccess(L.devs[g].id, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(pe);
+        (void)cudaGetLastError();
+    }
     CUDA_CHECK(cudaSetDevice(L.devs[0].id));
     host_alloc(L.h_flag, 16);
     memset(L.h_flag, 0, 16 * sizeof(int));
     L.devinit = true;
 }
 
-
-void ensure_j_capacity(Dev &d, int nj)
-{
-    const int need = ((nj + TJ - 1) / TJ) * TJ;
-    if (need <= d.jcap) return;
-    set_dev(d);
-    CUDA_CHECK(cudaStreamSynchronize(d.st));
-    dev_free(d.jraw); dev_free(d.jtile); dev_free(d.radii);
-    d.jcap = need;
-    dev_alloc(d.jraw, (size_t)7 * d.jcap);
-    dev_alloc(d.jtile, (size_t)(d.jcap / TJ) * TILE_FLOATS);
-    dev_alloc(d.radii, (size_t)2 * d.jcap);
+void shard_range(int r, int R, int nj, int &j0, int &j1)
+{   // reference split: joff[id] = id*nbody/numGPU (gpunb.velocity.cu:713-715)
+    j0 = (int)(((long long)r * nj) / R);
+    j1 = (int)(((long long)(r + 1) * nj) / R);
 }
 
-void ensure_work_buffers(Dev &d, int lmax, int nnbmax)
+void ensure_j_capacity(Dev &d, int nj_total, int shard_n)
 {
     set_dev(d);
-    // The product n_itiles * S never exceeds warps_resident (+ n_itiles when S=1 and many i-tiles).
-    const int ITILE = d.itile;
-    const int items = d.warps_resident + NIMAX / ITILE;
+    if (nj_total > d.raw_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        dev_free(d.jraw); dev_free(d.radii);
+        d.raw_cap = nj_total + 64;
+        dev_alloc(d.jraw, (size_t)7 * d.raw_cap);
+        dev_alloc(d.radii, (size_t)2 * d.raw_cap);
+    }
+    const int tiles = (shard_n + TJ - 1) / TJ + 1;
+    if (tiles > d.tile_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        dev_free(d.jtile);
+        d.tile_cap = tiles;
+        dev_alloc(d.jtile, (size_t)tiles * TILE_FLOATS);
+    }
+}
+
+void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root)
+{
+    set_dev(d);
+    // n_itiles * S never exceeds warps_resident (+ n_itiles when S = 1)
+    const int items = d.warps_resident + NIMAX / d.itile;
     const int segcap = ((nnbmax > 0 ? nnbmax : 1) + 3) & ~3;
     if (items > d.items_cap) {
         CUDA_CHECK(cudaStreamSynchronize(d.st));
         dev_free(d.part); dev_free(d.cnt);
         d.items_cap = items;
-        dev_alloc(d.part, (size_t)items * ITILE * PART_STRIDE);
-        dev_alloc(d.cnt, (size_t)items * ITILE);
+        dev_alloc(d.part, (size_t)items * d.itile * PART_STRIDE);
+        dev_alloc(d.cnt, (size_t)items * d.itile);
     }
-    const size_t seg_need = (size_t)d.items_cap * ITILE * segcap;
+    const size_t seg_need = (size_t)d.items_cap * d.itile * segcap;
     if (seg_need > d.seg_ints) {
         CUDA_CHECK(cudaStreamSynchronize(d.st));
         dev_free(d.seg);
@@ -626,17 +721,24 @@ void ensure_work_buffers(Dev &d, int lmax, int nnbmax)
     }
     d.segcap = segcap;
     const size_t rl = (size_t)NIMAX * lmax;
-    if (rl > d.res_list_ints) {
+    if (is_root && rl > d.res_list_ints) {
         CUDA_CHECK(cudaStreamSynchronize(d.st));
         dev_free(d.res_list);
         d.res_list_ints = rl;
         dev_alloc(d.res_list, rl);
     }
-    if (rl > L.h_list_n) {
+    if (L.devs.size() > 1 && rl > d.rows_ints) {
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        dev_free(d.rows);
+        d.rows_ints = rl;
+        dev_alloc(d.rows, rl);
+    }
+    if (is_root && rl > L.h_list_n) {
         host_free(L.h_list);
         L.h_list_n = rl;
         host_alloc(L.h_list, rl);
     }
+    if (L.sh.on && lmax > ROWS_LMAX_CAP) FATAL("lmax=%d exceeds the shard-row capacity %d of the NCCL mode", lmax, ROWS_LMAX_CAP);
 }
 
 void lib_open(int nbmax, int irank)
@@ -647,17 +749,16 @@ void lib_open(int nbmax, int irank)
     if (L.is_open) { fprintf(stderr, "gpunb: it is already open\n"); return; }   // reference: :636-639
     L.is_open = true;
     L.nbmax = nbmax;
-    const int G = (int)L.devs.size();
-    for (int g = 0; g < G; g++) {
-        Dev &d = L.devs[g];
+    const int R = total_ranks();
+    for (Dev &d : L.devs) {
         set_dev(d);
-        const int share = (int)(((long long)(g + 1) * nbmax) / G - ((long long)g * nbmax) / G) + TJ;
-        ensure_j_capacity(d, share);
+        ensure_j_capacity(d, nbmax, nbmax / R + TJ);
         if (!d.ibuf)    dev_alloc(d.ibuf, (size_t)8 * NIMAX);
         if (!d.res_f)   dev_alloc(d.res_f, (size_t)7 * NIMAX);
+        if (!d.fr)      dev_alloc(d.fr, (size_t)8 * NIMAX);
         if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
     }
-    const size_t hj = (size_t)7 * (((size_t)nbmax + TJ) / TJ + 1) * TJ;
+    const size_t hj = (size_t)7 * ((size_t)nbmax + 64);
     if (hj > L.h_j_n) { host_free(L.h_j); L.h_j_n = hj; host_alloc(L.h_j, hj); }
     if (!L.h_i) host_alloc(L.h_i, (size_t)8 * NIMAX);
     if (!L.h_f) host_alloc(L.h_f, (size_t)7 * NIMAX);
@@ -671,18 +772,19 @@ void lib_close()
     for (Dev &d : L.devs) {
         set_dev(d);
         CUDA_CHECK(cudaStreamSynchronize(d.st));
-        dev_free(d.jraw); dev_free(d.jtile); dev_free(d.radii); d.jcap = 0; d.nj = d.ntiles = 0;
+        dev_free(d.jraw); dev_free(d.jtile); dev_free(d.radii); d.raw_cap = d.tile_cap = 0; d.nj = d.ntiles = d.nj_total = 0;
         dev_free(d.ibuf); dev_free(d.part); dev_free(d.cnt); d.items_cap = 0;
         dev_free(d.seg); d.seg_ints = 0; dev_free(d.res_f); dev_free(d.res_list); d.res_list_ints = 0;
+        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0;
         dev_free(d.nanflag);
     }
     host_free(L.h_j); L.h_j_n = 0; host_free(L.h_i); host_free(L.h_f); host_free(L.h_list); L.h_list_n = 0;
     L.nbmax = 0;
 }
 
-// Copy the snapshot into pinned staging (m | x | v, each slice contiguous per device), async H2D,
-// convert on the device.  The reference converts fp64->fp32 on ONE host thread per GPU
-// (gpunb.velocity.cu:721-724) and uses a blocking copy (:726).
+// The snapshot is staged once in pinned memory (m | x | v), copied to every local device asynchronously and
+// converted there; each device tiles only its own j-shard.  The reference converts fp64->fp32 on ONE host
+// thread per GPU (gpunb.velocity.cu:721-724) and uses a blocking copy (:726).
 void lib_send(int nj, const double *mj, const double *xj, const double *vj)
 {
     if (!L.is_open) FATAL("gpunb_send called while the library is closed");
@@ -690,32 +792,31 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
     L.time_send -= wtime();
     L.isend++;
     L.nbody = nj;
-    const int G = (int)L.devs.size();
-    size_t hoff = 0;
-    for (int g = 0; g < G; g++) {
+    double *h = L.h_j;
+    memcpy(h, mj, sizeof(double) * nj);
+    memcpy(h + nj, xj, sizeof(double) * 3 * nj);
+    memcpy(h + 4 * (size_t)nj, vj, sizeof(double) * 3 * nj);
+    const int R = total_ranks();
+    for (size_t g = 0; g < L.devs.size(); g++) {
         Dev &d = L.devs[g];
         set_dev(d);
-        const int j0 = (int)(((long long)g * nj) / G), j1 = (int)(((long long)(g + 1) * nj) / G);   // reference: :713-715
-        const int n = j1 - j0;
-        ensure_j_capacity(d, n);
-        d.nj = n; d.ntiles = (n + TJ - 1) / TJ;
-        if (G > 1) d.joff = j0;                 // single-device: joff is owned by gpunb_b200_set_shard
-        double *h = L.h_j + hoff;
-        memcpy(h, mj + j0, sizeof(double) * n);
-        memcpy(h + n, xj + 3 * (size_t)j0, sizeof(double) * 3 * n);
-        memcpy(h + 4 * (size_t)n, vj + 3 * (size_t)j0, sizeof(double) * 3 * n);
-        CUDA_CHECK(cudaMemcpyAsync(d.jraw, h, sizeof(double) * 7 * n, cudaMemcpyHostToDevice, d.st));
-        L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * n;
+        int j0, j1;
+        shard_range(L.sh.on ? L.sh.rank : (int)g, R, nj, j0, j1);
+        ensure_j_capacity(d, nj, j1 - j0);
+        d.nj_total = nj; d.j0 = j0; d.nj = j1 - j0; d.ntiles = (d.nj + TJ - 1) / TJ;
+        CUDA_CHECK(cudaMemcpyAsync(d.jraw, h, sizeof(double) * 7 * nj, cudaMemcpyHostToDevice, d.st));
+        L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * nj;
         if (d.ntiles > 0) {
             const int threads = 256, blocks = (d.ntiles * TJ + threads - 1) / threads;
-            jpack_kernel<<<blocks, threads, 0, d.st>>>(n, d.ntiles, d.jraw, d.jraw + n, d.jraw + 4 * (size_t)n, d.jtile, d.nanflag);
+            jpack_kernel<<<blocks, threads, 0, d.st>>>(d.nj, d.ntiles, d.jraw + j0, d.jraw + nj + 3 * (size_t)j0,
+                                                       d.jraw + 4 * (size_t)nj + 3 * (size_t)j0, d.jtile, d.nanflag);
             CUDA_CHECK(cudaGetLastError());
             L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
         }
         CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, d.nanflag, sizeof(int), cudaMemcpyDeviceToHost, d.st));
-        hoff += (size_t)7 * n;
     }
-    for (int g = 0; g < G; g++) {
+    for (size_t g = 0; g < L.devs.size(); g++) {
+        set_dev(L.devs[g]);
         CUDA_CHECK(cudaStreamSynchronize(L.devs[g].st));
         if (L.h_flag[g]) FATAL("gpunb_send: NaN in j-particle data (reference asserts here, gpunb.velocity.cu:72-78)");
     }
@@ -735,14 +836,16 @@ Plan make_plan(const Dev &d, int ni)
     return p;
 }
 
-// Launch pair kernel + merge kernel for one i-block on device d (async on d.st).
-void launch_regf(Dev &d, int ni, const double *h2, const double *dtr, const double *xi, const double *vi,
-                 int lmax, int nnbmax, int m_flag, bool time_it)
+struct IBlock { const double *h2, *dtr, *xi, *vi; };
+
+// Pair kernel + shard-local merge for one i-block on device d (async on d.st).
+void launch_regf(Dev &d, int ni, const IBlock &ib, int lmax, int nnbmax, int m_flag, bool time_it,
+                 double *out_f, int f_stride, int *out_rows)
 {
     const Plan p = make_plan(d, ni);
     RegfArgs a;
-    a.tiles = d.jtile; a.ntiles = d.ntiles; a.nj = d.nj; a.joff = d.joff;
-    a.h2 = h2; a.dtr = dtr; a.xi = xi; a.vi = vi;
+    a.tiles = d.jtile; a.ntiles = d.ntiles; a.nj = d.nj; a.joff = d.j0;
+    a.h2 = ib.h2; a.dtr = ib.dtr; a.xi = ib.xi; a.vi = ib.vi;
     a.ni = ni; a.n_itiles = p.n_itiles; a.S = p.S; a.n_items = p.n_items;
     a.part = d.part; a.cnt = d.cnt; a.seg = d.seg; a.segcap = d.segcap;
     const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
@@ -753,51 +856,70 @@ void launch_regf(Dev &d, int ni, const double *h2, const double *dtr, const doub
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev1, d.st));
     MergeArgs m;
     m.part = d.part; m.cnt = d.cnt; m.seg = d.seg; m.ni = ni; m.S = p.S; m.segcap = d.segcap;
-    m.lmax = lmax; m.nnbmax = nnbmax; m.res_f = d.res_f; m.res_list = d.res_list;
+    m.lmax = lmax; m.nnbmax = nnbmax; m.res_f = out_f; m.f_stride = f_stride; m.res_list = out_rows;
     merge_kernel<<<(ni + 3) / 4, 128, 0, d.st>>>(m);
     CUDA_CHECK(cudaGetLastError());
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev2, d.st));
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
 }
 
-void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, const double *vi,
-              double *acc, double *jrk, double *pot, int lmax, int nnbmax, int *list, int m_flag)
+// One i-block on all shards + the exchange step.  ib[g] are DEVICE pointers valid on local device g.
+// On return (asynchronously, on the root stream) root.res_f / root.res_list hold the combined result.
+void regf_block(int ni, const IBlock *ib, int lmax, int nnbmax, int m_flag, bool time_it)
 {
-    if (!L.is_open) FATAL("gpunb_regf called while the library is closed");
-    if (!(0 < ni && ni <= NIMAX)) FATAL("gpunb_regf: ni=%d out of range (0, %d]", ni, NIMAX);
-    if (nnbmax + 1 > lmax) FATAL("gpunb_regf: nnbmax=%d does not fit rows of lmax=%d", nnbmax, lmax);
-    if (L.devs.size() != 1) FATAL("in-process multi-device combine is not built yet (unset GPUNB_B200_MULTI)");
-    L.time_grav -= wtime();
-    L.numInter += (long long)ni * L.nbody;       // reference counts every pair, self included (:747)
-    L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)ni * L.nbody;
-    L.ini += ni; L.icall++;
+    const int G = (int)L.devs.size();
+    Dev &root = L.devs[0];
+    if (!L.sh.on && G == 1) {          // single GPU: the shard-local merge IS the final result
+        set_dev(root);
+        launch_regf(root, ni, ib[0], lmax, nnbmax, m_flag, time_it, root.res_f, 7, root.res_list);
+        if (time_it) CUDA_CHECK(cudaEventRecord(root.ev3, root.st));
+        return;
+    }
+    CombineArgs c;
+    c.ni = ni; c.lmax = lmax; c.nnbmax = nnbmax; c.res_f = root.res_f; c.res_list = root.res_list;
+    if (L.sh.on) {                     // one process per GPU: NCCL all-gather of the 64 B/i partials, P2P pull of rows
+        Shard &sh = L.sh;
+        set_dev(root);
+        int *rows = sh.rows_local + (size_t)sh.parity * NIMAX * ROWS_LMAX_CAP;
+        launch_regf(root, ni, ib[0], lmax, nnbmax, m_flag, time_it, root.fr, 8, rows);
+        int rc = sh.allgather(root.fr, sh.fr_all, (size_t)ni * 8, NCCL_FLOAT64, sh.comm, root.st);
+        if (rc != 0) FATAL("ncclAllGather failed: %s", sh.errstr ? sh.errstr(rc) : "?");
+        c.R = sh.R;
+        for (int r = 0; r < sh.R; r++) {
+            c.fr[r] = sh.fr_all + (size_t)r * ni * 8;
+            c.rows[r] = sh.rows_peer[r] + (size_t)sh.parity * NIMAX * ROWS_LMAX_CAP;
+        }
+        sh.parity ^= 1;                // rows are double buffered: a peer may still be pulling the previous block
+    } else {                           // one process, G GPUs: root waits for every shard, pulls over P2P
+        for (int g = 0; g < G; g++) {
+            Dev &d = L.devs[g];
+            set_dev(d);
+            if (g > 0) CUDA_CHECK(cudaStreamWaitEvent(d.st, root.evdone, 0));     // previous combine has consumed d.fr / d.rows
+            launch_regf(d, ni, ib[g], lmax, nnbmax, m_flag, time_it && g == 0, d.fr, 8, d.rows);
+            if (g > 0) {
+                CUDA_CHECK(cudaEventRecord(d.evdone, d.st));
+                CUDA_CHECK(cudaStreamWaitEvent(root.st, d.evdone, 0));
+            }
+            c.fr[g] = d.fr; c.rows[g] = d.rows;
+        }
+        c.R = G;
+        set_dev(root);
+    }
+    combine_kernel<<<(ni + 3) / 4, 128, 0, root.st>>>(c);
+    CUDA_CHECK(cudaGetLastError());
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+    if (!L.sh.on) CUDA_CHECK(cudaEventRecord(root.evdone, root.st));
+    if (time_it) CUDA_CHECK(cudaEventRecord(root.ev3, root.st));
+}
 
-    Dev &d = L.devs[0];
-    set_dev(d);
-    ensure_work_buffers(d, lmax, nnbmax);
-    // NaN check + pack of the i-block (reference asserts per element, gpunb.velocity.cu:109-115)
-    double *h = L.h_i;
-    memcpy(h, h2, sizeof(double) * ni);
-    memcpy(h + ni, dtr, sizeof(double) * ni);
-    memcpy(h + 2 * (size_t)ni, xi, sizeof(double) * 3 * ni);
-    memcpy(h + 5 * (size_t)ni, vi, sizeof(double) * 3 * ni);
-    for (int k = 0; k < 8 * ni; k++) if (h[k] != h[k]) FATAL("gpunb_regf: NaN in i-particle data");
-    CUDA_CHECK(cudaMemcpyAsync(d.ibuf, h, sizeof(double) * 8 * ni, cudaMemcpyHostToDevice, d.st));
-    L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 8.0 * ni;
-
-    launch_regf(d, ni, d.ibuf, d.ibuf + ni, d.ibuf + 2 * (size_t)ni, d.ibuf + 5 * (size_t)ni, lmax, nnbmax, m_flag, true);
-
-    CUDA_CHECK(cudaMemcpyAsync(L.h_f, d.res_f, sizeof(double) * 7 * ni, cudaMemcpyDeviceToHost, d.st));
-    CUDA_CHECK(cudaMemcpyAsync(L.h_list, d.res_list, sizeof(int) * (size_t)ni * lmax, cudaMemcpyDeviceToHost, d.st));
+void fetch_results(int ni, int lmax, double *acc, double *jrk, double *pot, int *list)
+{
+    Dev &root = L.devs[0];
+    set_dev(root);
+    CUDA_CHECK(cudaMemcpyAsync(L.h_f, root.res_f, sizeof(double) * 7 * ni, cudaMemcpyDeviceToHost, root.st));
+    CUDA_CHECK(cudaMemcpyAsync(L.h_list, root.res_list, sizeof(int) * (size_t)ni * lmax, cudaMemcpyDeviceToHost, root.st));
     L.ctr[GPUNB_B200_CTR_D2H_BYTES] += sizeof(double) * 7.0 * ni + sizeof(int) * (double)ni * lmax;
-    CUDA_CHECK(cudaStreamSynchronize(d.st));
-    float ms = 0.f;
-    CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev0, d.ev1)); L.ctr[GPUNB_B200_CTR_GRAV_MS] += ms;
-    CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev1, d.ev2)); L.ctr[GPUNB_B200_CTR_MERGE_MS] += ms;
-    L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += 1;
-
-    const double wt = wtime();
-    L.time_grav += wt; L.time_reduce -= wt;
+    CUDA_CHECK(cudaStreamSynchronize(root.st));
     for (int i = 0; i < ni; i++) {
         const double *f = L.h_f + 7 * (size_t)i;
         acc[3 * i] = f[0]; acc[3 * i + 1] = f[1]; acc[3 * i + 2] = f[2];
@@ -809,7 +931,45 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         dst[0] = n;
         if (n > 0) memcpy(dst + 1, src + 1, sizeof(int) * n);
     }
-    L.time_reduce += wtime();
+}
+
+void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, const double *vi,
+              double *acc, double *jrk, double *pot, int lmax, int nnbmax, int *list, int m_flag)
+{
+    if (!L.is_open) FATAL("gpunb_regf called while the library is closed");
+    if (!(0 < ni && ni <= NIMAX)) FATAL("gpunb_regf: ni=%d out of range (0, %d]", ni, NIMAX);
+    if (nnbmax + 1 > lmax) FATAL("gpunb_regf: nnbmax=%d does not fit rows of lmax=%d", nnbmax, lmax);
+    L.time_grav -= wtime();
+    L.numInter += (long long)ni * L.nbody;       // reference counts every pair, self included (:747)
+    L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)ni * L.nbody;
+    L.ini += ni; L.icall++;
+
+    // NaN check + pack of the i-block (reference asserts per element, gpunb.velocity.cu:109-115)
+    double *h = L.h_i;
+    memcpy(h, h2, sizeof(double) * ni);
+    memcpy(h + ni, dtr, sizeof(double) * ni);
+    memcpy(h + 2 * (size_t)ni, xi, sizeof(double) * 3 * ni);
+    memcpy(h + 5 * (size_t)ni, vi, sizeof(double) * 3 * ni);
+    for (int k = 0; k < 8 * ni; k++) if (h[k] != h[k]) FATAL("gpunb_regf: NaN in i-particle data");
+    IBlock ib[MAX_RANKS];
+    for (size_t g = 0; g < L.devs.size(); g++) {
+        Dev &d = L.devs[g];
+        set_dev(d);
+        ensure_work_buffers(d, lmax, nnbmax, g == 0);
+        CUDA_CHECK(cudaMemcpyAsync(d.ibuf, h, sizeof(double) * 8 * ni, cudaMemcpyHostToDevice, d.st));
+        L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 8.0 * ni;
+        ib[g] = IBlock{d.ibuf, d.ibuf + ni, d.ibuf + 2 * (size_t)ni, d.ibuf + 5 * (size_t)ni};
+    }
+    regf_block(ni, ib, lmax, nnbmax, m_flag, true);
+    const double wt0 = wtime();
+    fetch_results(ni, lmax, acc, jrk, pot, list);
+    Dev &root = L.devs[0];
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, root.ev0, root.ev1)); L.ctr[GPUNB_B200_CTR_GRAV_MS] += ms;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, root.ev1, root.ev3)); L.ctr[GPUNB_B200_CTR_MERGE_MS] += ms;
+    L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += 1;
+    const double wt = wtime();
+    L.time_grav += wt0; L.time_reduce += wt - wt0;
     L.last_ni = ni; L.last_lmax = lmax;
 }
 
@@ -874,6 +1034,23 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
     fprintf(stderr, "[R.%d GPU Pot.A] Ni %d  NTOT %d  pot(s) %f\n", irank, ni, n, t1 - t0);   // reference: gpupot.gpu.cu:112
 }
 
+// ---- NCCL mode -------------------------------------------------------------------------------
+void nccl_load()
+{
+    Shard &sh = L.sh;
+    if (sh.dl) return;
+    sh.dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);            // the copy torch already loaded, if any
+    if (!sh.dl) sh.dl = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!sh.dl) sh.dl = dlopen("libnccl.so", RTLD_NOW);
+    if (!sh.dl) FATAL("cannot load libnccl.so.2: %s", dlerror());
+    sh.getid = (pfn_ncclGetUniqueId)dlsym(sh.dl, "ncclGetUniqueId");
+    sh.init = (pfn_ncclCommInitRank)dlsym(sh.dl, "ncclCommInitRank");
+    sh.allgather = (pfn_ncclAllGather)dlsym(sh.dl, "ncclAllGather");
+    sh.destroy = (pfn_ncclCommDestroy)dlsym(sh.dl, "ncclCommDestroy");
+    sh.errstr = (pfn_ncclGetErrorString)dlsym(sh.dl, "ncclGetErrorString");
+    if (!sh.getid || !sh.init || !sh.allgather || !sh.destroy) FATAL("libnccl.so.2 lacks the expected entry points");
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -896,10 +1073,10 @@ void gpupot_(int *irank, int *istart, int *ni, int *n, double m[], double x[][3]
     lib_pot(*irank, *istart, *ni, *n, m, &x[0][0], pot);
 }
 
-int gpunb_b200_version(void) { return 100; }
+int gpunb_b200_version(void) { return 101; }
 const char *gpunb_b200_build_info(void)
 {
-    return "gpunb_b200 sm_100a: regf_kernel<f32x2, TMA bulk j-tiles, TJ=64>, merge_kernel, pot_kernel, jpack_kernel";
+    return "gpunb_b200 sm_100a: regf_kernel<f32x2, TMA bulk j-tiles, TJ=64>, merge_kernel, combine_kernel (P2P), pot_kernel, jpack_kernel";
 }
 int gpunb_b200_num_devices(void) { return (int)L.devs.size(); }
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]) { for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) out[k] = L.ctr[k]; }
@@ -908,35 +1085,42 @@ void gpunb_b200_reset_counters(void) { for (int k = 0; k < GPUNB_B200_CTR_COUNT;
 void gpunb_b200_set_radii(int *njp, double h2[], double dtr[])
 {
     if (!L.is_open) FATAL("gpunb_b200_set_radii: library closed");
-    Dev &d = L.devs[0];
     const int nj = *njp;
-    if (nj != d.nj) FATAL("gpunb_b200_set_radii: nj=%d differs from the snapshot (%d)", nj, d.nj);
-    set_dev(d);
-    CUDA_CHECK(cudaMemcpyAsync(d.radii, h2, sizeof(double) * nj, cudaMemcpyHostToDevice, d.st));
-    CUDA_CHECK(cudaMemcpyAsync(d.radii + d.jcap, dtr, sizeof(double) * nj, cudaMemcpyHostToDevice, d.st));
-    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    for (Dev &d : L.devs) {
+        if (nj != d.nj_total) FATAL("gpunb_b200_set_radii: nj=%d differs from the snapshot (%d)", nj, d.nj_total);
+        set_dev(d);
+        CUDA_CHECK(cudaMemcpyAsync(d.radii, h2, sizeof(double) * nj, cudaMemcpyHostToDevice, d.st));
+        CUDA_CHECK(cudaMemcpyAsync(d.radii + d.raw_cap, dtr, sizeof(double) * nj, cudaMemcpyHostToDevice, d.st));
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+    }
 }
 
 float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int *nnbmaxp, int *m_flagp)
 {
     if (!L.is_open) FATAL("gpunb_b200_sweep_resident: library closed");
-    Dev &d = L.devs[0];
-    set_dev(d);
+    Dev &root = L.devs[0];
     const int i0 = *i0p, ni = *nip, block = *blockp;
-    if (i0 < 0 || i0 + ni > d.nj || block < 1 || block > NIMAX) FATAL("gpunb_b200_sweep_resident: bad range");
-    ensure_work_buffers(d, *lmaxp, *nnbmaxp);
-    const double *x = d.jraw + d.nj, *v = d.jraw + 4 * (size_t)d.nj;
-    CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
+    if (i0 < 0 || i0 + ni > root.nj_total || block < 1 || block > NIMAX) FATAL("gpunb_b200_sweep_resident: bad range");
+    for (size_t g = 0; g < L.devs.size(); g++) ensure_work_buffers(L.devs[g], *lmaxp, *nnbmaxp, g == 0);
+    set_dev(root);
+    CUDA_CHECK(cudaEventRecord(root.evs0, root.st));
     int nlaunch = 0, last = 0;
     for (int b = i0; b < i0 + ni; b += block) {
         const int n = (i0 + ni - b < block) ? i0 + ni - b : block;
-        launch_regf(d, n, d.radii + b, d.radii + d.jcap + b, x + 3 * (size_t)b, v + 3 * (size_t)b, *lmaxp, *nnbmaxp, *m_flagp, false);
-        L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)n * d.nj;
+        IBlock ib[MAX_RANKS];
+        for (size_t g = 0; g < L.devs.size(); g++) {
+            Dev &d = L.devs[g];
+            const double *x = d.jraw + d.nj_total, *v = d.jraw + 4 * (size_t)d.nj_total;
+            ib[g] = IBlock{d.radii + b, d.radii + d.raw_cap + b, x + 3 * (size_t)b, v + 3 * (size_t)b};
+        }
+        regf_block(n, ib, *lmaxp, *nnbmaxp, *m_flagp, false);
+        L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)n * root.nj_total;
         nlaunch++; last = n;
     }
-    CUDA_CHECK(cudaEventRecord(d.evs1, d.st));
-    CUDA_CHECK(cudaStreamSynchronize(d.st));
-    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, d.evs0, d.evs1));
+    set_dev(root);
+    CUDA_CHECK(cudaEventRecord(root.evs1, root.st));
+    CUDA_CHECK(cudaStreamSynchronize(root.st));
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, root.evs0, root.evs1));
     L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += nlaunch;
     L.last_ni = last; L.last_lmax = *lmaxp;
     return ms;
@@ -944,28 +1128,81 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
 
 void gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double pot[], int *lmaxp, int *list)
 {
-    Dev &d = L.devs[0];
-    set_dev(d);
     const int ni = L.last_ni, lmax = L.last_lmax;
     *n_last = ni; *lmaxp = lmax;
     if (ni <= 0) return;
-    CUDA_CHECK(cudaMemcpyAsync(L.h_f, d.res_f, sizeof(double) * 7 * ni, cudaMemcpyDeviceToHost, d.st));
-    CUDA_CHECK(cudaMemcpyAsync(L.h_list, d.res_list, sizeof(int) * (size_t)ni * lmax, cudaMemcpyDeviceToHost, d.st));
-    CUDA_CHECK(cudaStreamSynchronize(d.st));
-    for (int i = 0; i < ni; i++) {
-        const double *f = L.h_f + 7 * (size_t)i;
-        for (int c = 0; c < 3; c++) { acc[i][c] = f[c]; jrk[i][c] = f[3 + c]; }
-        pot[i] = f[6];
-        const int *src = L.h_list + (size_t)i * lmax;
-        list[(size_t)i * lmax] = src[0];
-        if (src[0] > 0) memcpy(list + (size_t)i * lmax + 1, src + 1, sizeof(int) * src[0]);
-    }
+    fetch_results(ni, lmax, &acc[0][0], &jrk[0][0], pot, list);
 }
 
-void gpunb_b200_set_shard(int joff_global)
+int gpunb_b200_nccl_unique_id(unsigned char id128[128])
 {
-    if (!L.devinit) FATAL("gpunb_b200_set_shard before devinit");
-    L.devs[0].joff = joff_global;
+    nccl_load();
+    ncclUniqueId id;
+    const int rc = L.sh.getid(&id);
+    if (rc != 0) return rc;
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+// Join `nranks` processes (one GPU each) into one j-sharded force library.  Call after gpunb_devinit_
+// and before gpunb_open_.  Every rank then makes IDENTICAL calls (same snapshot, same i-blocks) and every
+// rank receives the complete result; rank r sums over j in [r*nj/R, (r+1)*nj/R).
+int gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128])
+{
+    if (!L.devinit) FATAL("gpunb_b200_nccl_init before gpunb_devinit_");
+    if (L.devs.size() != 1) FATAL("NCCL mode drives one GPU per process (unset GPUNB_B200_MULTI)");
+    if (nranks < 1 || nranks > MAX_RANKS) FATAL("nranks=%d outside 1..%d", nranks, MAX_RANKS);
+    if (L.is_open) FATAL("gpunb_b200_nccl_init while the library is open");
+    nccl_load();
+    Shard &sh = L.sh;
+    Dev &d = L.devs[0];
+    set_dev(d);
+    ncclUniqueId id; memcpy(id.internal, id128, 128);
+    int rc = sh.init(&sh.comm, nranks, id, rank);
+    if (rc != 0) FATAL("ncclCommInitRank failed: %s", sh.errstr ? sh.errstr(rc) : "?");
+    sh.rank = rank; sh.R = nranks; sh.parity = 0;
+    dev_alloc(sh.fr_all, (size_t)nranks * NIMAX * 8);
+    dev_alloc(sh.rows_local, (size_t)2 * NIMAX * ROWS_LMAX_CAP);
+    // exchange cudaIpc handles of the row buffers with an all-gather, then map every peer's buffer
+    cudaIpcMemHandle_t mine;
+    CUDA_CHECK(cudaIpcGetMemHandle(&mine, sh.rows_local));
+    unsigned char *hbuf = nullptr; dev_alloc(hbuf, (size_t)(nranks + 1) * sizeof(cudaIpcMemHandle_t));
+    CUDA_CHECK(cudaMemcpyAsync(hbuf + (size_t)nranks * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, d.st));
+    rc = sh.allgather(hbuf + (size_t)nranks * sizeof(mine), hbuf, sizeof(mine), NCCL_INT8, sh.comm, d.st);
+    if (rc != 0) FATAL("ncclAllGather(ipc handles) failed: %s", sh.errstr ? sh.errstr(rc) : "?");
+    std::vector<cudaIpcMemHandle_t> all(nranks);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), hbuf, (size_t)nranks * sizeof(mine), cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    dev_free(hbuf);
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) { sh.rows_peer[r] = sh.rows_local; continue; }
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) FATAL("cudaIpcOpenMemHandle(rank %d) failed: %s (NVLink P2P between ranks is required)", r, cudaGetErrorString(e));
+        sh.rows_peer[r] = (int *)p;
+    }
+    sh.on = true;
+    return 0;
+}
+
+void gpunb_b200_nccl_finalize(void)
+{
+    Shard &sh = L.sh;
+    if (!sh.on) return;
+    Dev &d = L.devs[0];
+    set_dev(d);
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    for (int r = 0; r < sh.R; r++)
+        if (r != sh.rank && sh.rows_peer[r]) CUDA_CHECK(cudaIpcCloseMemHandle(sh.rows_peer[r]));
+    dev_free(sh.fr_all);
+    // the exported buffer is released only after every peer closed its mapping: a final all-gather is the barrier
+    dev_alloc(sh.fr_all, 2 * (size_t)sh.R);
+    sh.allgather(sh.fr_all + sh.R, sh.fr_all, 1, NCCL_FLOAT64, sh.comm, d.st);
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    dev_free(sh.fr_all);
+    dev_free(sh.rows_local);
+    sh.destroy(sh.comm);
+    sh.comm = nullptr; sh.on = false; sh.R = 1; sh.rank = 0;
 }
 
 }  // extern "C"

@@ -85,7 +85,8 @@ class ForceLib:
             L.gpunb_b200_nccl_unique_id.restype = C.c_int
             L.gpunb_b200_nccl_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
             L.gpunb_b200_nccl_init.restype = C.c_int
-            L.gpunb_b200_set_shard.argtypes = [C.c_int]
+            L.gpunb_b200_nccl_finalize.argtypes = []
+            L.gpunb_b200_nccl_finalize.restype = None
         self.nj = 0
 
     # ---- the reference interface -------------------------------------------------------------
@@ -201,6 +202,27 @@ class ForceLib:
             raise ValueError("lmax differs from the one used by the sweep")
         k = n.value
         return acc[:k], jrk[:k], pot[:k], lst[:k]
+
+    def nccl_unique_id(self) -> bytes:
+        """128-byte ncclUniqueId (call on rank 0, broadcast to the other ranks)."""
+        self._need_b200()
+        buf = C.create_string_buffer(128)
+        rc = self.lib.gpunb_b200_nccl_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"ncclGetUniqueId failed ({rc})")
+        return buf.raw
+
+    def nccl_init(self, rank: int, nranks: int, uid: bytes):
+        """Join one-GPU-per-process ranks into one j-sharded library (after devinit, before open)."""
+        self._need_b200()
+        assert len(uid) == 128
+        rc = self.lib.gpunb_b200_nccl_init(rank, nranks, uid)
+        if rc != 0:
+            raise RuntimeError(f"gpunb_b200_nccl_init failed ({rc})")
+
+    def nccl_finalize(self):
+        self._need_b200()
+        self.lib.gpunb_b200_nccl_finalize()
 
     def fp32_microbench(self, mode: int, iters: int = 4096) -> float:
         self._need_b200()

@@ -1,0 +1,70 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes, each computing ITS j-shard with the oracle, exchanged
+with torch.distributed all_gather and merged by the Python mirror of combine_kernel; the result must equal the
+single-process oracle (lists identical, sums equal to fp64 rounding)."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+from nbody6ppgpu_b200 import snapshots as S  # noqa: E402
+from nbody6ppgpu_b200.sharding import combine_shards, shard_range  # noqa: E402
+
+
+def test_shard_range_matches_reference_split():
+    for nj in (1, 7, 1000, 16385):
+        for R in (1, 2, 3, 8):
+            edges = [shard_range(r, R, nj) for r in range(R)]
+            assert edges[0][0] == 0 and edges[-1][1] == nj
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(R - 1))
+            assert all(e == ((r * nj) // R, ((r + 1) * nj) // R) for r, e in enumerate(edges))
+
+
+def _worker(rank, world, port, nnbmax, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib
+    o = oracle_lib.Oracle()
+    n, ni, lmax = 3001, 200, 128
+    m, x, v = S.plummer(n, 21, "kroupa")
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 60.0))
+    j0, j1 = shard_range(rank, world, n)
+    a, j, p, l, band, _ = o.regf_f64(m[j0:j1], x[j0:j1], v[j0:j1], h2[:ni], dtr[:ni], x[:ni], v[:ni], lmax, nnbmax, 0)
+    for i in range(ni):                       # shard-local indices -> global, as regf_kernel does with joff
+        c = l[i, 0]
+        if c > 0:
+            l[i, 1:1 + c] += j0
+    f = torch.from_numpy(np.concatenate([a, j, p[:, None]], axis=1))
+    lt = torch.from_numpy(l)
+    fs = [torch.zeros_like(f) for _ in range(world)]
+    ls = [torch.zeros_like(lt) for _ in range(world)]
+    dist.all_gather(fs, f); dist.all_gather(ls, lt)
+    fc, lc = combine_shards([t.numpy() for t in fs], [t.numpy() for t in ls], nnbmax)
+    a1, j1_, p1, l1, _, _ = o.regf_f64(m, x, v, h2[:ni], dtr[:ni], x[:ni], v[:ni], lmax, nnbmax, 0)
+    ok = not oracle_lib.list_rows_equal(lc, l1)
+    err = max(oracle_lib.relerr(fc[:, 0:3], a1), oracle_lib.relerr(fc[:, 6], p1))
+    # every rank holds the complete result (replicated semantics of the NCCL mode)
+    res = torch.tensor([1.0 if ok else 0.0, err, float((l1[:, 0] < 0).sum())], dtype=torch.float64)
+    gathered = [torch.zeros_like(res) for _ in range(world)]
+    dist.all_gather(gathered, res)
+    if rank == 0:
+        np.save(out, np.stack([g.numpy() for g in gathered]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nnbmax", [100, 40])
+def test_two_rank_gloo_shard_combine(tmp_path, nnbmax):
+    out = str(tmp_path / "res.npy")
+    port = 29500 + (os.getpid() % 2000) + nnbmax
+    mp.spawn(_worker, args=(2, port, nnbmax, out), nprocs=2, join=True)
+    res = np.load(out)
+    assert (res[:, 0] == 1.0).all(), "combined lists differ from the single-process oracle"
+    assert (res[:, 1] < 1e-13).all()
+    if nnbmax == 40:
+        assert res[0, 2] > 0, "the small-nnbmax case must exercise overflow rows"
