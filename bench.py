@@ -152,7 +152,6 @@ def run_reference(args, rank, world):
         return
     threads = cpu_threads()
     os.environ["OMP_NUM_THREADS"] = str(threads)
-    os.environ.setdefault("OMP_PROC_BIND", "close")
     ref = load_reference_avx()
     if ref is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgpunb_ref_avx.so not built"}))
@@ -195,7 +194,6 @@ def main():
     args = parse()
     # before torch/numpy pull in libgomp: the reference AVX library asserts threads <= 32 (reg.avx.cpp:7,103)
     os.environ["OMP_NUM_THREADS"] = str(cpu_threads())
-    os.environ.setdefault("OMP_PROC_BIND", "close")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -54,7 +54,7 @@ constexpr int TILE_BYTES  = TILE_FLOATS * 4;  // 2560
 constexpr int NSTAGE      = 2;                // smem stages per warp
 constexpr int WARPS       = 4;                // warps per CTA (warp-autonomous: no CTA-wide sync)
 constexpr int ITILE_MAX   = 64;               // largest i-tile of any kernel variant (32 lanes * IT)
-constexpr int FLUSH_TILES = 4;                // FP32 chains: 4 tiles * 64 j / 2 lanes-of-f32x2 = 128 terms
+constexpr int FLUSH_TILES = 1;                // FP32 chains: 1 tile * 64 j / 2 (f32x2 halves) = 32 terms, then fp64
 constexpr int NIMAX       = 2048;             // capacity per call (reference: gpunb.velocity.cu:24)
 constexpr int PART_STRIDE = 8;                // doubles per partial record (7 used)
 
@@ -141,6 +141,7 @@ struct RegfArgs {
     int          *cnt;       // [S][ni]
     int          *seg;       // [ni][S][segcap]
     int           segcap;
+    int           flush_tiles;   // FP32 chains are flushed into fp64 every flush_tiles j-tiles
 };
 
 struct IState {               // loop invariants of one i-particle, duplicated for f32x2 operands
@@ -150,17 +151,14 @@ struct IState {               // loop invariants of one i-particle, duplicated f
     float2 dtr, h2;
 };
 struct Acc {                  // FP32 partial chains (f32x2: one chain per j parity)
-    float2 ax, ay, az, p, j1x, j1y, j1z, j2x, j2y, j2z;
-    __device__ __forceinline__ void clear() {
-        ax = ay = az = p = j1x = j1y = j1z = j2x = j2y = j2z = make_float2(0.f, 0.f);
-    }
+    float2 ax, ay, az, p, jx, jy, jz;
+    __device__ __forceinline__ void clear() { ax = ay = az = p = jx = jy = jz = make_float2(0.f, 0.f); }
 };
 
 // One i-particle against a packed pair of j-particles.
 //   Predicate: the reference's, bit for bit, on the fp32-rounded inputs (gpunb.velocity.cu:168-187,
 //   :235 for m_flag): r2 = fma(dz,dz,fma(dy,dy,dx*dx)), dxp = fma(dtr,dvx,dx), min(r2,r2p) < h2 [*mj].
-//   Force: same formula (gpunb.velocity.cu:192-207) but from the float-float dx; the jerk is
-//   accumulated as J1 = sum m r^-3 dv and J2 = sum m r^-5 (r.v) dx, jrk = J1 - 3 J2 at flush.
+//   Force: same formula (gpunb.velocity.cu:192-207) but from the float-float dx and a Newton-refined rsqrt.
 //   Pairs at r2 == 0 (self) never contribute (regint.f:40 skips J.EQ.I); the reference GPU code
 //   returns NaN for a self pair with h2 == 0.
 // Returns a 2-bit mask of neighbour hits.
@@ -195,11 +193,12 @@ __device__ __forceinline__ unsigned interact(const IState &I, Acc &A,
     const float2 rinv2  = mul2(rinv, rinv);
     const float2 mrinv  = mul2(M, rinv);
     const float2 mrinv3 = mul2(mrinv, rinv2);
-    const float2 w      = mul2(mul2(rv, rinv2), mrinv3);
-    A.p   = add2(A.p, mrinv);
-    A.ax  = fma2(mrinv3, dx, A.ax);   A.ay  = fma2(mrinv3, dy, A.ay);   A.az  = fma2(mrinv3, dz, A.az);
-    A.j1x = fma2(mrinv3, dvx, A.j1x); A.j1y = fma2(mrinv3, dvy, A.j1y); A.j1z = fma2(mrinv3, dvz, A.j1z);
-    A.j2x = fma2(w, dx, A.j2x);       A.j2y = fma2(w, dy, A.j2y);       A.j2z = fma2(w, dz, A.j2z);
+    const float2 rv3    = mul2(rv, mul2(rinv2, dup2(-3.f)));          // -3 (r.v)/r^2
+    A.p  = add2(A.p, mrinv);
+    A.ax = fma2(mrinv3, dx, A.ax);   A.ay = fma2(mrinv3, dy, A.ay);   A.az = fma2(mrinv3, dz, A.az);
+    A.jx = fma2(mrinv3, fma2(rv3, dx, dvx), A.jx);
+    A.jy = fma2(mrinv3, fma2(rv3, dy, dvy), A.jy);
+    A.jz = fma2(mrinv3, fma2(rv3, dz, dvz), A.jz);
     return (nb0 ? 1u : 0u) | (nb1 ? 2u : 0u);
 }
 
@@ -271,9 +270,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             D[k][0] += (double)(A[k].ax.x + A[k].ax.y);
             D[k][1] += (double)(A[k].ay.x + A[k].ay.y);
             D[k][2] += (double)(A[k].az.x + A[k].az.y);
-            D[k][3] += (double)(A[k].j1x.x + A[k].j1x.y) - 3.0 * (double)(A[k].j2x.x + A[k].j2x.y);
-            D[k][4] += (double)(A[k].j1y.x + A[k].j1y.y) - 3.0 * (double)(A[k].j2y.x + A[k].j2y.y);
-            D[k][5] += (double)(A[k].j1z.x + A[k].j1z.y) - 3.0 * (double)(A[k].j2z.x + A[k].j2z.y);
+            D[k][3] += (double)(A[k].jx.x + A[k].jx.y);
+            D[k][4] += (double)(A[k].jy.x + A[k].jy.y);
+            D[k][5] += (double)(A[k].jz.x + A[k].jz.y);
             D[k][6] += (double)(A[k].p.x + A[k].p.y);
             A[k].clear();
         }
@@ -329,7 +328,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             mbar_expect_tx(&bars[st], TILE_BYTES);
             tma_bulk_g2s(buf + st * TILE_FLOATS, a.tiles + (size_t)(t + NSTAGE) * TILE_FLOATS, TILE_BYTES, &bars[st]);
         }
-        if (++since_flush == FLUSH_TILES) { flush(); since_flush = 0; }
+        if (++since_flush == a.flush_tiles) { flush(); since_flush = 0; }
     }
     flush();
 
@@ -848,6 +847,7 @@ void launch_regf(Dev &d, int ni, const IBlock &ib, int lmax, int nnbmax, int m_f
     a.h2 = ib.h2; a.dtr = ib.dtr; a.xi = ib.xi; a.vi = ib.vi;
     a.ni = ni; a.n_itiles = p.n_itiles; a.S = p.S; a.n_items = p.n_items;
     a.part = d.part; a.cnt = d.cnt; a.seg = d.seg; a.segcap = d.segcap;
+    { static int ft = 0; if (!ft) { const char *e = getenv("GPUNB_B200_FLUSH"); ft = e ? atoi(e) : FLUSH_TILES; if (ft < 1) ft = 1; } a.flush_tiles = ft; }
     const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
     const int blocks = (p.n_items + WARPS - 1) / WARPS;
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev0, d.st));
