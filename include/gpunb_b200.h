@@ -69,6 +69,8 @@ enum {
     GPUNB_B200_CTR_INTERACTIONS,    /* sum ni*nj as the reference counts (gpunb.velocity.cu:747) */
     GPUNB_B200_CTR_MERGE_MS,        /* sum of merge-kernel durations, ms (device 0)           */
     GPUNB_B200_CTR_POT_MS,          /* sum of gpupot kernel durations, ms                     */
+    GPUNB_B200_CTR_NEAR_TILES,      /* (warp, j-tile) visits that ran the full NEAR body (GPUNB_B200_STATS=1) */
+    GPUNB_B200_CTR_ALL_TILES,       /* all (warp, j-tile) visits (GPUNB_B200_STATS=1)          */
     GPUNB_B200_CTR_COUNT
 };
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);

@@ -5,35 +5,48 @@
 // reference (file:line cited below) defines WHAT is computed, not how.
 //
 // Data layout in HBM (per device)
-//   jraw   : the caller's fp64 snapshot, m[nj] | x[nj][3] | v[nj][3]            56 B/j
-//   jtile  : AoSoA tiles of TJ=64 j-particles, 10 float arrays per tile
-//            {xh,yh,zh, xl,yl,zl, vx,vy,vz, m}[64]  = 2560 B/tile                40 B/j
-//            xh=(float)x, xl=(float)(x-xh): float-float positions, so that close
-//            pairs keep ~48 bits in dx; xh alone is what the reference's FP32
-//            cast sees (gpunb.velocity.cu:62-64), so its neighbour predicate can
-//            be evaluated bit-for-bit.  One tile = ONE 1-D TMA bulk copy.
-//   part   : per (j-slice s, i) partial sums, 7 doubles, + count               [S][ni]
+//   jraw   : the caller's fp64 snapshot, m[nj] | x[nj][3] | v[nj][3]                          56 B/j
+//   jtile  : the device's j-shard, SORTED ALONG A HILBERT CURVE and cut into tiles of TJ=64.
+//            One tile = 64 B header + 10 float arrays of 64                                  ~41 B/j
+//              header : tile origin O (3 doubles, centre of the tile's bounding box), box half-extents,
+//                       velocity box (centre, half-extents), largest mass
+//              arrays : dx,dy,dz = (float)(x - O)   tile-local offsets: |offset| <= tile extent, so the
+//                                                   pair separation (O - x_i) + offset keeps a relative
+//                                                   precision of 2^-24 no matter how large |x| is;
+//                       vx,vy,vz, m                 fp32;
+//                       xh,yh,zh = (float)x         exactly what the reference's FP32 cast sees
+//                                                   (gpunb.velocity.cu:62-64): only read by tiles that
+//                                                   can hold neighbours, to evaluate the reference's
+//                                                   neighbour predicate bit for bit.
+//            A tile is contiguous: ONE 1-D TMA bulk copy brings header and data.
+//   jidx   : sorted slot -> global j index (ghost slots of the last tile: -1)
+//   part   : per (j-slice s, i) partial sums, 7 doubles, + count                            [S][ni]
 //   seg    : per (i, s) neighbour-index segment, capacity segcap ints
 //   res_f  : per i  acc[3] jrk[3] pot  (fp64)   ; res_list : [ni][lmax] int32 (the ABI layout)
 //
 // Kernels
-//   jpack_kernel   fp64 snapshot -> jtile (+ NaN check, reference asserts: gpunb.velocity.cu:72-78)
-//   regf_kernel    the O(ni*nj) pair kernel.  One WARP = one work item (i-tile of 32*IT
-//                  i-particles, contiguous range of j-tiles).  j-tiles are staged through
-//                  warp-private shared memory by TMA bulk copies (cp.async.bulk + mbarrier,
-//                  double buffered); lanes own i-particles, j is broadcast from smem; two
-//                  j-particles are processed per instruction with packed f32x2 FMA/ADD/MUL.
-//                  FP32 chains are 128 terms long, then flushed into fp64 accumulators.
-//   merge_kernel   per i: fp64 sum of the S partials in fixed order, exclusive scan of the S
-//                  segment counts, concatenation in slice order (= ascending j), overflow
+//   absmax/mortonkey/tilepack   fp64 snapshot -> sorted tiles (radix sort of the keys: CUB, plumbing)
+//   isort_kernel   Morton order of the i-block, so that the 32 i-particles of a warp are close in space
+//   regf_kernel    the O(ni*nj) pair kernel.  One WARP = one work item (32*IT i-particles, every S-th
+//                  j-tile).  Tiles stream through warp-private shared memory by TMA bulk copies
+//                  (cp.async.bulk + mbarrier, double buffered); lanes own i-particles, j is broadcast
+//                  from smem; two j per instruction with packed f32x2 FMA/ADD/MUL.
+//                  Per (warp, tile) the bounding boxes decide: FAR tiles (no pair can satisfy the
+//                  neighbour criterion, with margin) run a 27-op force-only body; NEAR tiles run the
+//                  full body with the reference predicate.  FP32 chains are 32 terms, then fp64.
+//   merge_kernel   per i: fp64 sum of the S partials in fixed order, gather of the S segments, sort
+//                  ascending (lists must be strictly ascending: regcor_gpu.F:299-336), overflow
 //                  encoding -(count) (reg.avx.cpp:320-321).
-//   pot_kernel     gpupot: float-float dx, FP32 rsqrt + one Newton step, fp64 flush.
+//   combine_kernel multi-GPU exchange step over NVLink peer pointers.
+//   pot_kernel     gpupot: tile-local dx, rsqrt + one Newton step, fp64 flush.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cstdint>
 #include <cmath>
+#include <climits>
 #include <vector>
 #include <sys/time.h>
 #include <unistd.h>
@@ -47,23 +60,22 @@
 
 namespace {
 
-constexpr int TJ          = 64;               // j-particles per tile
-constexpr int NCOMP       = 10;               // float arrays per tile
-constexpr int TILE_FLOATS = TJ * NCOMP;       // 640
-constexpr int TILE_BYTES  = TILE_FLOATS * 4;  // 2560
-constexpr int NSTAGE      = 2;                // smem stages per warp
-constexpr int WARPS       = 4;                // warps per CTA (warp-autonomous: no CTA-wide sync)
-constexpr int ITILE_MAX   = 64;               // largest i-tile of any kernel variant (32 lanes * IT)
-constexpr int FLUSH_TILES = 1;                // FP32 chains: 1 tile * 64 j / 2 (f32x2 halves) = 32 terms, then fp64
-constexpr int NIMAX       = 2048;             // capacity per call (reference: gpunb.velocity.cu:24)
-constexpr int PART_STRIDE = 8;                // doubles per partial record (7 used)
+constexpr int TJ          = 64;                   // j-particles per tile
+constexpr int HDR         = 16;                   // header floats
+constexpr int NCOMP       = 10;                   // float arrays per tile
+constexpr int TILE_FLOATS = HDR + TJ * NCOMP;     // 656
+constexpr int TILE_BYTES  = TILE_FLOATS * 4;      // 2624 (multiple of 16: one TMA bulk copy)
+enum { C_DX = 0, C_DY, C_DZ, C_VX, C_VY, C_VZ, C_M, C_XH, C_YH, C_ZH };
+constexpr int NSTAGE      = 2;                    // smem stages per warp
+constexpr int WARPS       = 4;                    // warps per CTA (warp-autonomous: no CTA-wide sync)
+constexpr int NIMAX       = 2048;                 // capacity per call (reference: gpunb.velocity.cu:24)
+constexpr int PART_STRIDE = 8;                    // doubles per partial record (7 used)
+constexpr int SORT_CAP    = 1024;                 // merge_kernel sorts up to this many neighbours per i
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -93,38 +105,193 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 
 // ---------------------------------------------------------------------------------------------
-// jpack_kernel: fp64 snapshot -> float-float AoSoA tiles.  Ghost slots (j >= nj) get mass 0 and a
-// far-away position; they are additionally excluded from lists by index.
+// Tile construction: |x|max -> Morton keys -> (CUB radix sort) -> tilepack
 // ---------------------------------------------------------------------------------------------
-__global__ void jpack_kernel(int nj, int ntiles, const double *__restrict__ m, const double *__restrict__ x,
-                             const double *__restrict__ v, float *__restrict__ tiles, int *__restrict__ nanflag)
+// largest |coordinate| (as float bits; non-negative floats order like unsigned ints) + NaN check of the
+// whole record (reference asserts on NaN input: gpunb.velocity.cu:72-78)
+__global__ void absmax_kernel(int n, const double *__restrict__ m, const double *__restrict__ x,
+                              const double *__restrict__ v, unsigned *__restrict__ out, int *__restrict__ nanflag)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ntiles * TJ) return;
-    float *t = tiles + (size_t)(j / TJ) * TILE_FLOATS + (j % TJ);
-    if (j < nj) {
-        bool bad = false;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    float a = 0.f;
+    bool bad = false;
+    if (j < n) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            double xd = x[3 * (size_t)j + k], vd = v[3 * (size_t)j + k];
-            float hi = (float)xd;
-            float lo = (float)(xd - (double)hi);
-            t[(0 + k) * TJ] = hi;
-            t[(3 + k) * TJ] = lo;
-            t[(6 + k) * TJ] = (float)vd;
-            bad |= (xd != xd) | (vd != vd);
+            const double xd = x[3 * (size_t)j + k];
+            a = fmaxf(a, fabsf((float)xd));
+            bad |= (xd != xd);
+            if (v) { const double vd = v[3 * (size_t)j + k]; bad |= (vd != vd); }
         }
-        double md = m[j];
-        t[9 * TJ] = (float)md;
+        const double md = m[j];
         bad |= (md != md);
-        if (bad) atomicExch(nanflag, 1);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 3; k++) { t[k * TJ] = 1.0e6f; t[(3 + k) * TJ] = 0.f; t[(6 + k) * TJ] = 0.f; }
-        t[9 * TJ] = 0.f;
     }
+    a = warp_max(a);
+    if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(out, __float_as_uint(a));
+    if (bad) atomicExch(nanflag, 1);
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned v)
+{   // 21 bits -> every third bit
+    unsigned long long x = v & 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8)  & 0x100f00f00f00f00full;
+    x = (x | x << 4)  & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2)  & 0x1249249249249249ull;
+    return x;
+}
+// Hilbert-curve key (Skilling's transpose algorithm, 21 bits per axis).  Unlike the Morton curve the Hilbert
+// curve has no jumps: 64 consecutive particles form a compact tile, which is what keeps the tile-local
+// offsets small (precision) and the bounding boxes tight (few NEAR tiles).
+__device__ __forceinline__ unsigned long long morton_key(double px, double py, double pz, float H)
+{
+    const float s = 1048575.5f / H;      // 2^20 cells per half box
+    unsigned X[3];
+    X[0] = (unsigned)fminf(fmaxf((float)px * s + 1048576.f, 0.f), 2097151.f);
+    X[1] = (unsigned)fminf(fmaxf((float)py * s + 1048576.f, 0.f), 2097151.f);
+    X[2] = (unsigned)fminf(fmaxf((float)pz * s + 1048576.f, 0.f), 2097151.f);
+    const unsigned Mtop = 1u << 20;
+    for (unsigned Q = Mtop; Q > 1; Q >>= 1) {
+        const unsigned P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const unsigned t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0]; X[2] ^= X[1];
+    unsigned t = 0;
+    for (unsigned Q = Mtop; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    return (spread21(X[0]) << 2) | (spread21(X[1]) << 1) | spread21(X[2]);
+}
+__global__ void mortonkey_kernel(int n, const double *__restrict__ x, const unsigned *__restrict__ hbits,
+                                 unsigned long long *__restrict__ keys, int *__restrict__ vals)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float H = fmaxf(__uint_as_float(*hbits), 1e-30f);
+    keys[j] = morton_key(x[3 * (size_t)j], x[3 * (size_t)j + 1], x[3 * (size_t)j + 2], H);
+    vals[j] = j;
+}
+
+// One warp per tile: gathers its 64 particles through the sort permutation, finds the bounding boxes,
+// writes header + arrays.  Ghost slots of the last tile replicate the tile's first particle with mass 0
+// and index -1 (never listed, no force).  v may be NULL (gpupot tiles).
+__global__ void __launch_bounds__(128) tilepack_kernel(int n, int ntiles, int joff, const double *__restrict__ m,
+                                                        const double *__restrict__ x, const double *__restrict__ v,
+                                                        const int *__restrict__ perm, float *__restrict__ tiles,
+                                                        int *__restrict__ jidx)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= ntiles) return;
+    double px[2][3], mn[3], mx[3];
+    float pv[2][3], pm[2], vmn[3], vmx[3], mmax = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { mn[c] = 1e300; mx[c] = -1e300; vmn[c] = 3e38f; vmx[c] = -3e38f; }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = t * TJ + h * 32 + lane;
+        const bool real = p < n;
+        const int src = perm[real ? p : t * TJ];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            px[h][c] = x[3 * (size_t)src + c];
+            pv[h][c] = v ? (float)v[3 * (size_t)src + c] : 0.f;
+            mn[c] = fmin(mn[c], px[h][c]); mx[c] = fmax(mx[c], px[h][c]);
+            vmn[c] = fminf(vmn[c], pv[h][c]); vmx[c] = fmaxf(vmx[c], pv[h][c]);
+        }
+        pm[h] = real ? (float)m[src] : 0.f;
+        mmax = fmaxf(mmax, pm[h]);
+        jidx[p] = real ? joff + src : -1;
+    }
+    float *tb = tiles + (size_t)t * TILE_FLOATS;
+    double O[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]);
+        vmn[c] = warp_min(vmn[c]); vmx[c] = warp_max(vmx[c]);
+        O[c] = 0.5 * (mn[c] + mx[c]);
+    }
+    mmax = warp_max(mmax);
+    if (lane == 0) {
+        double *od = reinterpret_cast<double *>(tb);
+        od[0] = O[0]; od[1] = O[1]; od[2] = O[2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            // half-extents rounded up (conservative): fp32-rounded coordinates may sit 1 ulp outside
+            tb[6 + c]  = (float)(0.5 * (mx[c] - mn[c])) * 1.000001f + 1.2e-7f * (float)fmax(fabs(mn[c]), fabs(mx[c])) + 1e-30f;
+            tb[9 + c]  = 0.5f * (vmn[c] + vmx[c]);
+            tb[12 + c] = 0.5f * (vmx[c] - vmn[c]) * 1.000001f + 1.2e-7f * fmaxf(fabsf(vmn[c]), fabsf(vmx[c])) + 1e-30f;
+        }
+        tb[15] = mmax;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int k = h * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            tb[HDR + (C_DX + c) * TJ + k] = (float)(px[h][c] - O[c]);
+            tb[HDR + (C_VX + c) * TJ + k] = pv[h][c];
+            tb[HDR + (C_XH + c) * TJ + k] = (float)px[h][c];
+        }
+        tb[HDR + C_M * TJ + k] = pm[h];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// isort_kernel: Morton order of the i-block (one CTA, bitonic sort of <= 2048 keys in shared memory).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) isort_kernel(int ni, const double *__restrict__ xi, const unsigned *__restrict__ hbits,
+                                                      int *__restrict__ iperm)
+{
+    __shared__ unsigned long long key[NIMAX];
+    __shared__ int idx[NIMAX];
+    const float H = fmaxf(__uint_as_float(*hbits), 1e-30f);
+    int n2 = 64;
+    while (n2 < ni) n2 <<= 1;
+    for (int k = threadIdx.x; k < n2; k += blockDim.x) {
+        key[k] = k < ni ? morton_key(xi[3 * (size_t)k], xi[3 * (size_t)k + 1], xi[3 * (size_t)k + 2], H) : ~0ull;
+        idx[k] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = threadIdx.x; k < (n2 >> 1); k += blockDim.x) {
+                const int lo = 2 * k - (k & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = key[lo], b = key[hi];
+                if ((a > b) == up) { key[lo] = b; key[hi] = a; const int q = idx[lo]; idx[lo] = idx[hi]; idx[hi] = q; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int k = threadIdx.x; k < ni; k += blockDim.x) iperm[k] = idx[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -132,22 +299,24 @@ __global__ void jpack_kernel(int nj, int ntiles, const double *__restrict__ m, c
 // ---------------------------------------------------------------------------------------------
 struct RegfArgs {
     const float  *tiles;     // jtile
-    int           ntiles, nj;
-    int           joff;      // global index of this device's first j (multi-GPU shards)
+    const int    *jidx;      // sorted slot -> global j (or -1)
+    int           ntiles;
     // i-particles (fp64, device): element i at h2[i], dtr[i], xi[3i..], vi[3i..]
     const double *h2, *dtr, *xi, *vi;
+    const int    *iperm;     // Morton order of the i-block
     int           ni, n_itiles, S, n_items;
     double       *part;      // [S][ni][PART_STRIDE]
     int          *cnt;       // [S][ni]
     int          *seg;       // [ni][S][segcap]
     int           segcap;
-    int           flush_tiles;   // FP32 chains are flushed into fp64 every flush_tiles j-tiles
+    int           force_near;  // debugging/tuning: classify every tile as NEAR
+    unsigned long long *stats; // optional: [0] near tiles, [1] all tiles (per warp-tile visit)
 };
 
 struct IState {               // loop invariants of one i-particle, duplicated for f32x2 operands
-    float2 nxh, nyh, nzh;     // -x_i (hi)
-    float2 nxl, nyl, nzl;     // -x_i (lo)
-    float2 nvx, nvy, nvz;     // -v_i
+    float2 cx, cy, cz;        // (O_tile - x_i), refreshed per tile
+    float2 nxh, nyh, nzh;     // -(float)x_i : the reference's FP32 position
+    float2 nvx, nvy, nvz;     // -(float)v_i
     float2 dtr, h2;
 };
 struct Acc {                  // FP32 partial chains (f32x2: one chain per j parity)
@@ -155,22 +324,49 @@ struct Acc {                  // FP32 partial chains (f32x2: one chain per j par
     __device__ __forceinline__ void clear() { ax = ay = az = p = jx = jy = jz = make_float2(0.f, 0.f); }
 };
 
-// One i-particle against a packed pair of j-particles.
-//   Predicate: the reference's, bit for bit, on the fp32-rounded inputs (gpunb.velocity.cu:168-187,
-//   :235 for m_flag): r2 = fma(dz,dz,fma(dy,dy,dx*dx)), dxp = fma(dtr,dvx,dx), min(r2,r2p) < h2 [*mj].
-//   Force: same formula (gpunb.velocity.cu:192-207) but from the float-float dx and a Newton-refined rsqrt.
-//   Pairs at r2 == 0 (self) never contribute (regint.f:40 skips J.EQ.I); the reference GPU code
-//   returns NaN for a self pair with h2 == 0.
-// Returns a 2-bit mask of neighbour hits.
-template <bool MFLAG>
-__device__ __forceinline__ unsigned interact(const IState &I, Acc &A,
-                                             float2 XH, float2 YH, float2 ZH, float2 XL, float2 YL, float2 ZL,
+__device__ __forceinline__ void accumulate(Acc &A, float2 rinv, float2 M, float2 rv, float2 dx, float2 dy, float2 dz,
+                                           float2 dvx, float2 dvy, float2 dvz)
+{   // gpunb.velocity.cu:192-207
+    const float2 rinv2  = mul2(rinv, rinv);
+    const float2 mrinv  = mul2(M, rinv);
+    const float2 mrinv3 = mul2(mrinv, rinv2);
+    const float2 rv3    = mul2(rv, mul2(rinv2, dup2(-3.f)));          // -3 (r.v)/r^2
+    A.p  = add2(A.p, mrinv);
+    A.ax = fma2(mrinv3, dx, A.ax);   A.ay = fma2(mrinv3, dy, A.ay);   A.az = fma2(mrinv3, dz, A.az);
+    A.jx = fma2(mrinv3, fma2(rv3, dx, dvx), A.jx);
+    A.jy = fma2(mrinv3, fma2(rv3, dy, dvy), A.jy);
+    A.jz = fma2(mrinv3, fma2(rv3, dz, dvz), A.jz);
+}
+
+// FAR tile: the bounding boxes prove that no pair of (this warp's i-particles, this tile) can satisfy the
+// neighbour criterion, so the body is the force alone: 27 FP32 lane-ops + 1 MUFU per pair.
+__device__ __forceinline__ void interact_far(const IState &I, Acc &A, float2 DX, float2 DY, float2 DZ,
                                              float2 VX, float2 VY, float2 VZ, float2 M)
 {
+    const float2 dx = add2(DX, I.cx), dy = add2(DY, I.cy), dz = add2(DZ, I.cz);
+    const float2 dvx = add2(VX, I.nvx), dvy = add2(VY, I.nvy), dvz = add2(VZ, I.nvz);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    const float2 rv = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
+    float2 rinv;
+    rinv.x = rsqrt_approx(r2.x);
+    rinv.y = rsqrt_approx(r2.y);
+    accumulate(A, rinv, M, rv, dx, dy, dz, dvx, dvy, dvz);
+}
+
+// NEAR tile: full body.
+//   Predicate: the reference's, bit for bit, on the fp32-rounded inputs (gpunb.velocity.cu:168-187,
+//   :235 for m_flag): r2 = fma(dz,dz,fma(dy,dy,dx*dx)), dxp = fma(dtr,dvx,dx), min(r2,r2p) < h2 [*mj].
+//   Force: from the tile-local separation, with a Newton-refined rsqrt (a close massive perturber can
+//   dominate the sum, so the single term must hold ~1e-7).  Pairs at r2 == 0 (self) never contribute
+//   (regint.f:40 skips J.EQ.I); the reference GPU code returns NaN for a self pair with h2 == 0.
+// Returns a 2-bit mask of neighbour hits.
+template <bool MFLAG>
+__device__ __forceinline__ unsigned interact_near(const IState &I, Acc &A, float2 DX, float2 DY, float2 DZ,
+                                                  float2 VX, float2 VY, float2 VZ, float2 M,
+                                                  float2 XH, float2 YH, float2 ZH)
+{
     const float2 dxr = add2(XH, I.nxh), dyr = add2(YH, I.nyh), dzr = add2(ZH, I.nzh);
-    const float2 dx = add2(dxr, add2(XL, I.nxl));
-    const float2 dy = add2(dyr, add2(YL, I.nyl));
-    const float2 dz = add2(dzr, add2(ZL, I.nzl));
+    const float2 dx = add2(DX, I.cx), dy = add2(DY, I.cy), dz = add2(DZ, I.cz);
     const float2 dvx = add2(VX, I.nvx), dvy = add2(VY, I.nvy), dvz = add2(VZ, I.nvz);
 
     const float2 r2r = fma2(dzr, dzr, fma2(dyr, dyr, mul2(dxr, dxr)));
@@ -186,19 +382,10 @@ __device__ __forceinline__ unsigned interact(const IState &I, Acc &A,
     float2 rinv;
     rinv.x = (nb0 || !(r2.x > 0.f)) ? 0.f : rsqrt_approx(r2.x);
     rinv.y = (nb1 || !(r2.y > 0.f)) ? 0.f : rsqrt_approx(r2.y);
-
-    // one Newton step: y <- y - y/2 (r2 y^2 - 1); rsqrt.approx alone (2^-22.9) leaves 5 ulp on the r^-5 term
+    // one Newton step: y <- y - y/2 (r2 y^2 - 1)
     const float2 e = fma2(mul2(r2, rinv), rinv, dup2(-1.f));
     rinv = fma2(mul2(rinv, e), dup2(-0.5f), rinv);
-    const float2 rinv2  = mul2(rinv, rinv);
-    const float2 mrinv  = mul2(M, rinv);
-    const float2 mrinv3 = mul2(mrinv, rinv2);
-    const float2 rv3    = mul2(rv, mul2(rinv2, dup2(-3.f)));          // -3 (r.v)/r^2
-    A.p  = add2(A.p, mrinv);
-    A.ax = fma2(mrinv3, dx, A.ax);   A.ay = fma2(mrinv3, dy, A.ay);   A.az = fma2(mrinv3, dz, A.az);
-    A.jx = fma2(mrinv3, fma2(rv3, dx, dvx), A.jx);
-    A.jy = fma2(mrinv3, fma2(rv3, dy, dvy), A.jy);
-    A.jz = fma2(mrinv3, fma2(rv3, dz, dvz), A.jz);
+    accumulate(A, rinv, M, rv, dx, dy, dz, dvx, dvy, dvz);
     return (nb0 ? 1u : 0u) | (nb1 ? 2u : 0u);
 }
 
@@ -213,9 +400,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
     float    *buf  = reinterpret_cast<float *>(smem_raw) + warp * NSTAGE * TILE_FLOATS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + WARPS * NSTAGE * TILE_BYTES) + warp * NSTAGE;
 
-    const int it = w / a.S, s = w - it * a.S;
-    const int t0 = (int)(((long long)s * a.ntiles) / a.S);
-    const int t1 = (int)(((long long)(s + 1) * a.ntiles) / a.S);
+    const int it = w / a.S, s = w - it * a.S;         // this warp visits tiles s, s+S, s+2S, ...
 
     if (lane == 0) {
 #pragma unroll
@@ -226,44 +411,45 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < NSTAGE; k++)
-            if (t0 + k < t1) {
+            if (s + k * a.S < a.ntiles) {
                 mbar_expect_tx(&bars[k], TILE_BYTES);
-                tma_bulk_g2s(buf + k * TILE_FLOATS, a.tiles + (size_t)(t0 + k) * TILE_FLOATS, TILE_BYTES, &bars[k]);
+                tma_bulk_g2s(buf + k * TILE_FLOATS, a.tiles + (size_t)(s + k * a.S) * TILE_FLOATS, TILE_BYTES, &bars[k]);
             }
     }
 
-    // i-particles of this lane
+    // i-particles of this lane (Morton-ordered block: the warp's i-particles are close in space)
     IState I[IT];
     Acc    A[IT];
-    double D[IT][7];
-    int    cnt[IT];
+    double D[IT][7], xid[IT][3];
+    float  islack[IT];        // fp32 rounding of x_i itself (the predicate sees (float)x_i)
+    int    cnt[IT], iidx[IT];
     int   *segp[IT];
-    bool   valid[IT];
 #pragma unroll
     for (int k = 0; k < IT; k++) {
-        const int i = it * ITILE + k * 32 + lane;
-        valid[k] = i < a.ni;
-        double x[3] = {0, 0, 0}, v[3] = {0, 0, 0}, h2 = 0, dtr = 0;
-        if (valid[k]) {
+        const int slot = it * ITILE + k * 32 + lane;
+        const bool valid = slot < a.ni;
+        const int i = valid ? a.iperm[slot] : -1;
+        iidx[k] = i;
+        double v[3] = {0, 0, 0}, h2 = 0, dtr = 0;
+        xid[k][0] = xid[k][1] = xid[k][2] = 0.0;
+        if (valid) {
             h2 = a.h2[i]; dtr = a.dtr[i];
 #pragma unroll
-            for (int c = 0; c < 3; c++) { x[c] = a.xi[3 * (size_t)i + c]; v[c] = a.vi[3 * (size_t)i + c]; }
+            for (int c = 0; c < 3; c++) { xid[k][c] = a.xi[3 * (size_t)i + c]; v[c] = a.vi[3 * (size_t)i + c]; }
         }
-        float xh[3], xl[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) { xh[c] = (float)x[c]; xl[c] = (float)(x[c] - (double)xh[c]); }
+        const float xh[3] = {(float)xid[k][0], (float)xid[k][1], (float)xid[k][2]};
+        const float vf[3] = {(float)v[0], (float)v[1], (float)v[2]};
         I[k].nxh = dup2(-xh[0]); I[k].nyh = dup2(-xh[1]); I[k].nzh = dup2(-xh[2]);
-        I[k].nxl = dup2(-xl[0]); I[k].nyl = dup2(-xl[1]); I[k].nzl = dup2(-xl[2]);
-        I[k].nvx = dup2(-(float)v[0]); I[k].nvy = dup2(-(float)v[1]); I[k].nvz = dup2(-(float)v[2]);
+        islack[k] = 1.2e-7f * fmaxf(fabsf(xh[0]), fmaxf(fabsf(xh[1]), fabsf(xh[2])));
+        I[k].nvx = dup2(-vf[0]); I[k].nvy = dup2(-vf[1]); I[k].nvz = dup2(-vf[2]);
         I[k].dtr = dup2((float)dtr);
-        I[k].h2  = dup2(valid[k] ? (float)h2 : 0.f);
+        I[k].h2  = dup2(valid ? (float)h2 : 0.f);
         A[k].clear();
 #pragma unroll
         for (int c = 0; c < 7; c++) D[k][c] = 0.0;
         cnt[k]  = 0;
-        segp[k] = a.seg + ((size_t)(valid[k] ? i : 0) * a.S + s) * a.segcap;
+        segp[k] = a.seg + ((size_t)(valid ? i : 0) * a.S + s) * a.segcap;
     }
-
     auto flush = [&]() {
 #pragma unroll
         for (int k = 0; k < IT; k++) {
@@ -278,45 +464,104 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         }
     };
 
-    int since_flush = 0;
-    for (int t = t0; t < t1; t++) {
-        const int st = (t - t0) % NSTAGE;
-        const uint32_t parity = ((t - t0) / NSTAGE) & 1;
+    unsigned n_near = 0, n_all = 0;
+    int n = 0;
+    for (int t = s; t < a.ntiles; t += a.S, n++) {
+        const int st = n % NSTAGE;
+        const uint32_t parity = (n / NSTAGE) & 1;
         mbar_wait(&bars[st], parity);
-        const float4 *c = reinterpret_cast<const float4 *>(buf + st * TILE_FLOATS);
-        const int jtile0 = t * TJ;
-#pragma unroll 1
-        for (int q = 0; q < TJ / 4; q++) {
-            const float4 XH = c[0 * 16 + q], YH = c[1 * 16 + q], ZH = c[2 * 16 + q];
-            const float4 XL = c[3 * 16 + q], YL = c[4 * 16 + q], ZL = c[5 * 16 + q];
-            const float4 VX = c[6 * 16 + q], VY = c[7 * 16 + q], VZ = c[8 * 16 + q];
-            const float4 M  = c[9 * 16 + q];
-            unsigned hit = 0;
+        const float *tb = buf + st * TILE_FLOATS;
+        // ---- header: classify the (warp, tile) pair -------------------------------------------------
+        const double Ox = reinterpret_cast<const double *>(tb)[0];
+        const double Oy = reinterpret_cast<const double *>(tb)[1];
+        const double Oz = reinterpret_cast<const double *>(tb)[2];
+        const float4 h1 = reinterpret_cast<const float4 *>(tb)[1];      // Oz(2 words) | hx hy   (only .z,.w used)
+        const float4 h2v = reinterpret_cast<const float4 *>(tb)[2];     // hz | vcx vcy vcz
+        const float4 h3 = reinterpret_cast<const float4 *>(tb)[3];      // hvx hvy hvz | mmax
+        // Separation (tile origin - x_i) in fp64, rounded once: |c| ~ pair distance, so c + offset keeps a
+        // relative precision of 2^-24 whatever |x| is.
+        float cf[IT][3];
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+            cf[k][0] = (float)(Ox - xid[k][0]); cf[k][1] = (float)(Oy - xid[k][1]); cf[k][2] = (float)(Oz - xid[k][2]);
+            I[k].cx = dup2(cf[k][0]); I[k].cy = dup2(cf[k][1]); I[k].cz = dup2(cf[k][2]);
+        }
+        // Per-lane test of i against the tile's boxes: FAR iff no j of the tile can satisfy the reference
+        // criterion min(|dx|^2, |dx + dtr dv|^2) < h2 [* mj], with margins that dominate every fp32 rounding
+        // (positions/velocities rounded to fp32 by the predicate, this arithmetic itself).
+        bool lane_far = true;
+        {
+            const float jh[3] = {h1.z, h1.w, h2v.x};
+            const float jvc[3] = {h2v.y, h2v.z, h2v.w};
+            const float jvh[3] = {h3.x, h3.y, h3.z};
 #pragma unroll
             for (int k = 0; k < IT; k++) {
-                const unsigned h0 = interact<MFLAG>(I[k], A[k],
-                    make_float2(XH.x, XH.y), make_float2(YH.x, YH.y), make_float2(ZH.x, ZH.y),
-                    make_float2(XL.x, XL.y), make_float2(YL.x, YL.y), make_float2(ZL.x, ZL.y),
-                    make_float2(VX.x, VX.y), make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y),
-                    make_float2(M.x, M.y));
-                const unsigned h1 = interact<MFLAG>(I[k], A[k],
-                    make_float2(XH.z, XH.w), make_float2(YH.z, YH.w), make_float2(ZH.z, ZH.w),
-                    make_float2(XL.z, XL.w), make_float2(YL.z, YL.w), make_float2(ZL.z, ZL.w),
-                    make_float2(VX.z, VX.w), make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w),
-                    make_float2(M.z, M.w));
-                hit |= (h0 | (h1 << 2)) << (4 * k);
+                float d2 = 0.f, dv2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float g = fmaxf(fabsf(cf[k][c]) - jh[c] - 2.4e-7f * (fabsf(cf[k][c]) + jh[c]) - islack[k], 0.f);
+                    d2 = fmaf(g, g, d2);
+                    const float u = fabsf(jvc[c] + (c == 0 ? I[k].nvx.x : c == 1 ? I[k].nvy.x : I[k].nvz.x)) + jvh[c];
+                    dv2 = fmaf(u, u, dv2);
+                }
+                const float d = sqrtf(d2);
+                const float reach = fabsf(I[k].dtr.x) * sqrtf(dv2) * 1.00001f;
+                const float lim = (MFLAG ? h3.w * I[k].h2.x : I[k].h2.x) * 1.0001f;
+                const float dd = d - reach;
+                const bool f = (dd > 0.f) && (dd * dd > lim) && (d2 > 0.f);
+                lane_far &= (f || iidx[k] < 0);
             }
-            if (hit) {                                 // rare: ~2e-4 of pairs are neighbours
-                const int jb = jtile0 + q * 4;
+        }
+        const bool far = __all_sync(0xffffffffu, lane_far) && !a.force_near;
+        n_all++;
+        const float4 *c = reinterpret_cast<const float4 *>(tb + HDR);
+        if (far) {
+#pragma unroll 2
+            for (int q = 0; q < TJ / 4; q++) {
+                const float4 DX = c[C_DX * 16 + q], DY = c[C_DY * 16 + q], DZ = c[C_DZ * 16 + q];
+                const float4 VX = c[C_VX * 16 + q], VY = c[C_VY * 16 + q], VZ = c[C_VZ * 16 + q];
+                const float4 M  = c[C_M * 16 + q];
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
+                    interact_far(I[k], A[k], make_float2(DX.x, DX.y), make_float2(DY.x, DY.y), make_float2(DZ.x, DZ.y),
+                                 make_float2(VX.x, VX.y), make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), make_float2(M.x, M.y));
+                    interact_far(I[k], A[k], make_float2(DX.z, DX.w), make_float2(DY.z, DY.w), make_float2(DZ.z, DZ.w),
+                                 make_float2(VX.z, VX.w), make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), make_float2(M.z, M.w));
+                }
+            }
+        } else {
+            n_near++;
+#pragma unroll 1
+            for (int q = 0; q < TJ / 4; q++) {
+                const float4 DX = c[C_DX * 16 + q], DY = c[C_DY * 16 + q], DZ = c[C_DZ * 16 + q];
+                const float4 VX = c[C_VX * 16 + q], VY = c[C_VY * 16 + q], VZ = c[C_VZ * 16 + q];
+                const float4 M  = c[C_M * 16 + q];
+                const float4 XH = c[C_XH * 16 + q], YH = c[C_YH * 16 + q], ZH = c[C_ZH * 16 + q];
+                unsigned hit = 0;
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        if ((hit >> (4 * k + b)) & 1u) {
-                            const int j = jb + b;
-                            if (j < a.nj) {            // ghosts of the last tile are never neighbours
-                                if (cnt[k] < a.segcap) segp[k][cnt[k]] = a.joff + j;
-                                cnt[k]++;
+                for (int k = 0; k < IT; k++) {
+                    const unsigned h0 = interact_near<MFLAG>(I[k], A[k],
+                        make_float2(DX.x, DX.y), make_float2(DY.x, DY.y), make_float2(DZ.x, DZ.y),
+                        make_float2(VX.x, VX.y), make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), make_float2(M.x, M.y),
+                        make_float2(XH.x, XH.y), make_float2(YH.x, YH.y), make_float2(ZH.x, ZH.y));
+                    const unsigned h1b = interact_near<MFLAG>(I[k], A[k],
+                        make_float2(DX.z, DX.w), make_float2(DY.z, DY.w), make_float2(DZ.z, DZ.w),
+                        make_float2(VX.z, VX.w), make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), make_float2(M.z, M.w),
+                        make_float2(XH.z, XH.w), make_float2(YH.z, YH.w), make_float2(ZH.z, ZH.w));
+                    hit |= (h0 | (h1b << 2)) << (4 * k);
+                }
+                if (hit) {                             // rare: ~2e-4 of pairs are neighbours
+                    const int pb = t * TJ + q * 4;
+#pragma unroll
+                    for (int k = 0; k < IT; k++) {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            if ((hit >> (4 * k + b)) & 1u) {
+                                const int jg = a.jidx[pb + b];
+                                if (jg >= 0) {         // ghost slots of the last tile are never neighbours
+                                    if (cnt[k] < a.segcap) segp[k][cnt[k]] = jg;
+                                    cnt[k]++;
+                                }
                             }
                         }
                     }
@@ -324,32 +569,31 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             }
         }
         __syncwarp();                                  // every lane is done reading stage st
-        if (lane == 0 && t + NSTAGE < t1) {
+        if (lane == 0 && t + NSTAGE * a.S < a.ntiles) {
             mbar_expect_tx(&bars[st], TILE_BYTES);
-            tma_bulk_g2s(buf + st * TILE_FLOATS, a.tiles + (size_t)(t + NSTAGE) * TILE_FLOATS, TILE_BYTES, &bars[st]);
+            tma_bulk_g2s(buf + st * TILE_FLOATS, a.tiles + (size_t)(t + NSTAGE * a.S) * TILE_FLOATS, TILE_BYTES, &bars[st]);
         }
-        if (++since_flush == a.flush_tiles) { flush(); since_flush = 0; }
+        flush();                                       // FP32 chains of 32 terms -> fp64
     }
-    flush();
 
 #pragma unroll
     for (int k = 0; k < IT; k++) {
-        const int i = it * ITILE + k * 32 + lane;
-        if (valid[k]) {
+        const int i = iidx[k];
+        if (i >= 0) {
             double *o = a.part + ((size_t)s * a.ni + i) * PART_STRIDE;
 #pragma unroll
             for (int c = 0; c < 7; c++) o[c] = D[k][c];
             a.cnt[(size_t)s * a.ni + i] = cnt[k];
         }
     }
+    if (a.stats && lane == 0) { atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all); }
 }
 
 // ---------------------------------------------------------------------------------------------
 // merge_kernel: one warp per i-particle.
-//   fp64 sum over the S slices in a fixed order; scan of the S counts; concatenation of the
-//   segments in slice order, which IS ascending j because slices are contiguous j ranges and
-//   each warp visits its j ascending (the caller's two-pointer list diff needs strictly
-//   ascending order, regcor_gpu.F:299-336).
+//   fp64 sum over the S slices in a fixed order (deterministic); gather of the S neighbour segments into
+//   shared memory; bitonic sort ascending -- tiles are visited in Morton order, the caller needs strictly
+//   ascending j (its two-pointer list diff: regcor_gpu.F:299-336).
 //   count > nnbmax  ->  list[0] = -count, no entries written (reg.avx.cpp:320-321).
 // ---------------------------------------------------------------------------------------------
 struct MergeArgs {
@@ -362,8 +606,9 @@ struct MergeArgs {
 
 __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
 {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ int sbuf[4][SORT_CAP];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int i = blockIdx.x * 4 + wq;
     if (i >= a.ni) return;
     double f[7] = {0, 0, 0, 0, 0, 0, 0};
     int total = 0;
@@ -384,7 +629,9 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
     int *row = a.res_list + (size_t)i * a.lmax;
     if (total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
     if (lane == 0) row[0] = total;
-    int base = 1;
+    if (total == 0) return;
+    int *sb = sbuf[wq];
+    int base = 0;
     for (int s0 = 0; s0 < a.S; s0 += 32) {
         const int s = s0 + lane;
         const int n = (s < a.S) ? a.cnt[(size_t)s * a.ni + i] : 0;
@@ -393,9 +640,26 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
         for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
         const int off = base + incl - n;
         const int *src = a.seg + ((size_t)i * a.S + s) * a.segcap;
-        for (int k = 0; k < n; k++) row[off + k] = src[k];
+        for (int k = 0; k < n; k++) sb[off + k] = src[k];
         base += __shfl_sync(0xffffffffu, incl, 31);
     }
+    int n2 = 32;
+    while (n2 < total) n2 <<= 1;
+    for (int k = total + lane; k < n2; k += 32) sb[k] = INT_MAX;
+    __syncwarp();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = lane; k < (n2 >> 1); k += 32) {
+                const int lo = 2 * k - (k & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const int x = sb[lo], y = sb[hi];
+                if ((x > y) == up) { sb[lo] = y; sb[hi] = x; }
+            }
+            __syncwarp();
+        }
+    }
+    for (int k = lane; k < total; k += 32) row[1 + k] = sb[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,56 +712,56 @@ __global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// pot_kernel (gpupot): phi_i = sum_{j, r>0} m_j / r_ij.  Reuses the jtile layout (velocities
-// unused).  Lanes own i-particles, j broadcast from smem tiles staged by the CTA; rsqrt.approx +
-// one Newton step (the AVX twin does the same, pot.avx.cpp:22-25), FP32 chains of 64 terms
-// flushed to fp64.  Work item = (32 i, j-slice); partial sums combined by pot_merge_kernel.
+// pot_kernel (gpupot): phi_i = sum_{j, r>0} m_j / r_ij (gpupot.gpu.cu:32-57).  Same sorted tiles
+// (velocities unused).  Work item = warp: 32 i-particles x every S-th tile; separation from the
+// tile-local offsets, rsqrt.approx + one Newton step (the AVX twin does the same, pot.avx.cpp:22-25),
+// FP32 chains of 64 terms flushed to fp64.  A self pair gives dx = fl(O-x_i) + fl(x_i-O) = 0 exactly and
+// is skipped by r2 > 0 like the reference (:52).  Partial sums are combined by pot_merge_kernel.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) pot_kernel(const float *__restrict__ tiles, int ntiles, int S,
-                                                   int i0, int ni, double *__restrict__ part)
+                                                   const double *__restrict__ x, int i0, int ni, double *__restrict__ part)
 {
-    __shared__ __align__(16) float sb[4][4 * TJ];        // per warp: xh|yh|zh|... staged 64 j at a time
+    __shared__ __align__(16) float sb[4][HDR + 4 * TJ];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * 4 + warp;
     const int n_it = (ni + 31) / 32;
     if (w >= n_it * S) return;
     const int it = w / S, s = w - it * S;
-    const int t0 = (int)(((long long)s * ntiles) / S), t1 = (int)(((long long)(s + 1) * ntiles) / S);
     const int ii = it * 32 + lane;
-    const int i = i0 + (ii < ni ? ii : 0);
-    const float *ti = tiles + (size_t)(i / TJ) * TILE_FLOATS + (i % TJ);
-    const float xh = ti[0], yh = ti[TJ], zh = ti[2 * TJ], xl = ti[3 * TJ], yl = ti[4 * TJ], zl = ti[5 * TJ];
+    const int i = i0 + (ii < ni ? ii : ni - 1);
+    const double xd = x[3 * (size_t)i], yd = x[3 * (size_t)i + 1], zd = x[3 * (size_t)i + 2];
     double phi = 0.0;
     float *b = sb[warp];
-    for (int t = t0; t < t1; t++) {
+    for (int t = s; t < ntiles; t += S) {
         const float *tp = tiles + (size_t)t * TILE_FLOATS;
         __syncwarp();
-        // stage: 7 arrays of 64 floats needed (xh yh zh xl yl zl m); 64 floats = 2 per lane
+        if (lane < HDR) b[lane] = tp[lane];
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const int jj = lane + 32 * c;
-            b[jj]          = tp[jj];                 // xh
-            b[TJ + jj]     = tp[TJ + jj];            // yh
-            b[2 * TJ + jj] = tp[2 * TJ + jj];        // zh
-            b[3 * TJ + jj] = tp[9 * TJ + jj];        // m
+        for (int h = 0; h < 2; h++) {
+            const int jj = lane + 32 * h;
+            b[HDR + jj]          = tp[HDR + C_DX * TJ + jj];
+            b[HDR + TJ + jj]     = tp[HDR + C_DY * TJ + jj];
+            b[HDR + 2 * TJ + jj] = tp[HDR + C_DZ * TJ + jj];
+            b[HDR + 3 * TJ + jj] = tp[HDR + C_M * TJ + jj];
         }
-        float lo[6];
-#pragma unroll
-        for (int c = 0; c < 2; c++) { lo[3*c] = tp[3 * TJ + lane + 32 * c]; lo[3*c+1] = tp[4 * TJ + lane + 32 * c]; lo[3*c+2] = tp[5 * TJ + lane + 32 * c]; }
         __syncwarp();
+        const double *od = reinterpret_cast<const double *>(b);
+        const float cx = (float)(od[0] - xd), cy = (float)(od[1] - yd), cz = (float)(od[2] - zd);
+        const float4 *c = reinterpret_cast<const float4 *>(b + HDR);
         float acc = 0.f;
-#pragma unroll 8
-        for (int jj = 0; jj < TJ; jj++) {
-            const float jxl = __shfl_sync(0xffffffffu, lo[3 * (jj >> 5)],     jj & 31);
-            const float jyl = __shfl_sync(0xffffffffu, lo[3 * (jj >> 5) + 1], jj & 31);
-            const float jzl = __shfl_sync(0xffffffffu, lo[3 * (jj >> 5) + 2], jj & 31);
-            const float dx = (b[jj] - xh) + (jxl - xl);
-            const float dy = (b[TJ + jj] - yh) + (jyl - yl);
-            const float dz = (b[2 * TJ + jj] - zh) + (jzl - zl);
-            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            float y = rsqrt_approx(r2);
-            y = y * fmaf(-0.5f * r2 * y, y, 1.5f);      // one Newton step
-            acc += (r2 > 0.f) ? b[3 * TJ + jj] * y : 0.f;
+#pragma unroll 4
+        for (int q = 0; q < TJ / 4; q++) {
+            const float4 DX = c[q], DY = c[16 + q], DZ = c[32 + q], M = c[48 + q];
+            const float dxs[4] = {DX.x, DX.y, DX.z, DX.w}, dys[4] = {DY.x, DY.y, DY.z, DY.w};
+            const float dzs[4] = {DZ.x, DZ.y, DZ.z, DZ.w}, ms[4] = {M.x, M.y, M.z, M.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float dx = dxs[e] + cx, dy = dys[e] + cy, dz = dzs[e] + cz;
+                const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                float y = rsqrt_approx(r2);
+                y = y * fmaf(-0.5f * r2 * y, y, 1.5f);      // one Newton step
+                acc += (r2 > 0.f) ? ms[e] * y : 0.f;
+            }
         }
         phi += (double)acc;
     }
@@ -512,6 +776,7 @@ __global__ void pot_merge_kernel(const double *__restrict__ part, int S, int ni,
     for (int s = 0; s < S; s++) p += part[(size_t)s * ni + ii];
     out[ii] = p;
 }
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
@@ -542,6 +807,14 @@ struct Dev {
     float *jtile = nullptr;
     double *radii = nullptr;      // h2[raw_cap] | dtr[raw_cap]  (resident sweeps)
     int nj_total = 0, j0 = 0, nj = 0, ntiles = 0;
+    int *jidx = nullptr;          // sorted slot -> global j
+    // Morton sort scratch
+    unsigned *hbits = nullptr;    // largest |coordinate| of the shard (float bits)
+    unsigned long long *keys_in = nullptr, *keys_out = nullptr;
+    int *vals_in = nullptr, *perm = nullptr; int sort_cap = 0;
+    void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+    int *iperm = nullptr;         // Morton order of the current i-block
+    unsigned long long *stats = nullptr;   // [0] near (warp,tile) visits, [1] all visits (GPUNB_B200_STATS=1)
     double *ibuf = nullptr;       // 8*NIMAX doubles: h2 | dtr | x | v
     int items_cap = 0;
     double *part = nullptr; int *cnt = nullptr;
@@ -692,10 +965,45 @@ void ensure_j_capacity(Dev &d, int nj_total, int shard_n)
     const int tiles = (shard_n + TJ - 1) / TJ + 1;
     if (tiles > d.tile_cap) {
         CUDA_CHECK(cudaStreamSynchronize(d.st));
-        dev_free(d.jtile);
+        dev_free(d.jtile); dev_free(d.jidx);
         d.tile_cap = tiles;
         dev_alloc(d.jtile, (size_t)tiles * TILE_FLOATS);
+        dev_alloc(d.jidx, (size_t)tiles * TJ);
     }
+}
+
+void ensure_sort_capacity(Dev &d, int n)
+{
+    set_dev(d);
+    if (!d.hbits) dev_alloc(d.hbits, 1);
+    if (n <= d.sort_cap) return;
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    dev_free(d.keys_in); dev_free(d.keys_out); dev_free(d.vals_in); dev_free(d.perm);
+    if (d.cub_tmp) CUDA_CHECK(cudaFree(d.cub_tmp)); d.cub_tmp = nullptr;
+    d.sort_cap = n + 1024;
+    dev_alloc(d.keys_in, d.sort_cap); dev_alloc(d.keys_out, d.sort_cap);
+    dev_alloc(d.vals_in, d.sort_cap); dev_alloc(d.perm, d.sort_cap);
+    size_t bytes = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d.keys_in, d.keys_out, d.vals_in, d.perm, d.sort_cap, 0, 63, d.st));
+    d.cub_tmp_bytes = bytes;
+    CUDA_CHECK(cudaMalloc(&d.cub_tmp, bytes));
+}
+
+// fp64 particles (m, x, v or NULL; n of them, device pointers) -> Morton-sorted tiles + slot->index map.
+// The radix sort of the 63-bit keys is CUB (plumbing, not the hot path).
+void build_tiles(Dev &d, int n, int joff, const double *m, const double *x, const double *v, float *tiles, int *jidx)
+{
+    if (n <= 0) return;
+    ensure_sort_capacity(d, n);
+    const int ntiles = (n + TJ - 1) / TJ;
+    CUDA_CHECK(cudaMemsetAsync(d.hbits, 0, sizeof(unsigned), d.st));
+    absmax_kernel<<<(n + 255) / 256, 256, 0, d.st>>>(n, m, x, v, d.hbits, d.nanflag);
+    mortonkey_kernel<<<(n + 255) / 256, 256, 0, d.st>>>(n, x, d.hbits, d.keys_in, d.vals_in);
+    size_t bytes = d.cub_tmp_bytes;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d.cub_tmp, bytes, d.keys_in, d.keys_out, d.vals_in, d.perm, n, 0, 63, d.st));
+    tilepack_kernel<<<(ntiles + 3) / 4, 128, 0, d.st>>>(n, ntiles, joff, m, x, v, d.perm, tiles, jidx);
+    CUDA_CHECK(cudaGetLastError());
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 4;       // + the CUB sort passes (library code, not counted)
 }
 
 void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root)
@@ -755,6 +1063,8 @@ void lib_open(int nbmax, int irank)
         if (!d.ibuf)    dev_alloc(d.ibuf, (size_t)8 * NIMAX);
         if (!d.res_f)   dev_alloc(d.res_f, (size_t)7 * NIMAX);
         if (!d.fr)      dev_alloc(d.fr, (size_t)8 * NIMAX);
+        if (!d.iperm)   dev_alloc(d.iperm, (size_t)NIMAX);
+        if (!d.stats && getenv("GPUNB_B200_STATS")) { dev_alloc(d.stats, 2); CUDA_CHECK(cudaMemsetAsync(d.stats, 0, 16, d.st)); }
         if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
     }
     const size_t hj = (size_t)7 * ((size_t)nbmax + 64);
@@ -774,7 +1084,8 @@ void lib_close()
         dev_free(d.jraw); dev_free(d.jtile); dev_free(d.radii); d.raw_cap = d.tile_cap = 0; d.nj = d.ntiles = d.nj_total = 0;
         dev_free(d.ibuf); dev_free(d.part); dev_free(d.cnt); d.items_cap = 0;
         dev_free(d.seg); d.seg_ints = 0; dev_free(d.res_f); dev_free(d.res_list); d.res_list_ints = 0;
-        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0;
+        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.stats);
+        dev_free(d.jidx);
         dev_free(d.nanflag);
     }
     host_free(L.h_j); L.h_j_n = 0; host_free(L.h_i); host_free(L.h_f); host_free(L.h_list); L.h_list_n = 0;
@@ -805,13 +1116,8 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
         d.nj_total = nj; d.j0 = j0; d.nj = j1 - j0; d.ntiles = (d.nj + TJ - 1) / TJ;
         CUDA_CHECK(cudaMemcpyAsync(d.jraw, h, sizeof(double) * 7 * nj, cudaMemcpyHostToDevice, d.st));
         L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * nj;
-        if (d.ntiles > 0) {
-            const int threads = 256, blocks = (d.ntiles * TJ + threads - 1) / threads;
-            jpack_kernel<<<blocks, threads, 0, d.st>>>(d.nj, d.ntiles, d.jraw + j0, d.jraw + nj + 3 * (size_t)j0,
-                                                       d.jraw + 4 * (size_t)nj + 3 * (size_t)j0, d.jtile, d.nanflag);
-            CUDA_CHECK(cudaGetLastError());
-            L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
-        }
+        build_tiles(d, d.nj, j0, d.jraw + j0, d.jraw + nj + 3 * (size_t)j0, d.jraw + 4 * (size_t)nj + 3 * (size_t)j0,
+                    d.jtile, d.jidx);
         CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, d.nanflag, sizeof(int), cudaMemcpyDeviceToHost, d.st));
     }
     for (size_t g = 0; g < L.devs.size(); g++) {
@@ -843,13 +1149,15 @@ void launch_regf(Dev &d, int ni, const IBlock &ib, int lmax, int nnbmax, int m_f
 {
     const Plan p = make_plan(d, ni);
     RegfArgs a;
-    a.tiles = d.jtile; a.ntiles = d.ntiles; a.nj = d.nj; a.joff = d.j0;
+    a.tiles = d.jtile; a.jidx = d.jidx; a.ntiles = d.ntiles; a.iperm = d.iperm;
+    { static int fn = -1; if (fn < 0) { const char *e = getenv("GPUNB_B200_FORCE_NEAR"); fn = e ? atoi(e) : 0; } a.force_near = fn; }
+    a.stats = d.stats;
     a.h2 = ib.h2; a.dtr = ib.dtr; a.xi = ib.xi; a.vi = ib.vi;
     a.ni = ni; a.n_itiles = p.n_itiles; a.S = p.S; a.n_items = p.n_items;
     a.part = d.part; a.cnt = d.cnt; a.seg = d.seg; a.segcap = d.segcap;
-    { static int ft = 0; if (!ft) { const char *e = getenv("GPUNB_B200_FLUSH"); ft = e ? atoi(e) : FLUSH_TILES; if (ft < 1) ft = 1; } a.flush_tiles = ft; }
     const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
     const int blocks = (p.n_items + WARPS - 1) / WARPS;
+    isort_kernel<<<1, 1024, 0, d.st>>>(ni, ib.xi, d.hbits, d.iperm);
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev0, d.st));
     VARIANTS[d.variant].k[m_flag ? 1 : 0]<<<blocks, WARPS * 32, smem, d.st>>>(a);
     CUDA_CHECK(cudaGetLastError());
@@ -860,7 +1168,7 @@ void launch_regf(Dev &d, int ni, const IBlock &ib, int lmax, int nnbmax, int m_f
     merge_kernel<<<(ni + 3) / 4, 128, 0, d.st>>>(m);
     CUDA_CHECK(cudaGetLastError());
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev2, d.st));
-    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 3;
 }
 
 // One i-block on all shards + the exchange step.  ib[g] are DEVICE pointers valid on local device g.
@@ -939,6 +1247,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     if (!L.is_open) FATAL("gpunb_regf called while the library is closed");
     if (!(0 < ni && ni <= NIMAX)) FATAL("gpunb_regf: ni=%d out of range (0, %d]", ni, NIMAX);
     if (nnbmax + 1 > lmax) FATAL("gpunb_regf: nnbmax=%d does not fit rows of lmax=%d", nnbmax, lmax);
+    if (nnbmax > SORT_CAP) FATAL("gpunb_regf: nnbmax=%d exceeds the list capacity %d of this build", nnbmax, SORT_CAP);
     L.time_grav -= wtime();
     L.numInter += (long long)ni * L.nbody;       // reference counts every pair, self included (:747)
     L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)ni * L.nbody;
@@ -994,27 +1303,26 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
     Dev &d = L.devs[0];
     set_dev(d);
     // private buffers so that gpupot never disturbs the regf j-snapshot
-    static double *jraw = nullptr; static float *jtile = nullptr; static int cap = 0; static double *hpin = nullptr; static size_t hpin_n = 0;
+    static double *jraw = nullptr; static float *jtile = nullptr; static int *jidx = nullptr; static int cap = 0;
+    static double *hpin = nullptr; static size_t hpin_n = 0;
     const int ntiles = (n + TJ - 1) / TJ;
     if (ntiles * TJ > cap) {
-        dev_free(jraw); dev_free(jtile);
+        dev_free(jraw); dev_free(jtile); dev_free(jidx);
         cap = ntiles * TJ;
-        dev_alloc(jraw, (size_t)4 * cap); dev_alloc(jtile, (size_t)ntiles * TILE_FLOATS);
+        dev_alloc(jraw, (size_t)4 * cap); dev_alloc(jtile, (size_t)ntiles * TILE_FLOATS); dev_alloc(jidx, (size_t)cap);
     }
     if ((size_t)4 * n + ni > hpin_n) { host_free(hpin); hpin_n = (size_t)4 * n + ni + 1024; host_alloc(hpin, hpin_n); }
     if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
     memcpy(hpin, m, sizeof(double) * n);
     memcpy(hpin + n, x, sizeof(double) * 3 * n);
     CUDA_CHECK(cudaMemcpyAsync(jraw, hpin, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, d.st));
-    // velocities are not needed: pass the position array as "v" (finite, ignored by pot_kernel)
-    jpack_kernel<<<(ntiles * TJ + 255) / 256, 256, 0, d.st>>>(n, ntiles, jraw, jraw + n, jraw + n, jtile, d.nanflag);
-    CUDA_CHECK(cudaGetLastError());
+    build_tiles(d, n, 0, jraw, jraw + n, nullptr, jtile, jidx);
     const int n_it = (ni + 31) / 32;
     int S = (d.nsm * 16 * 4) / n_it; if (S < 1) S = 1; if (S > ntiles) S = ntiles;
     if ((size_t)S * ni > d.pot_part_n) { dev_free(d.pot_part); d.pot_part_n = (size_t)S * ni; dev_alloc(d.pot_part, d.pot_part_n); }
     if ((size_t)ni > d.pot_out_n) { dev_free(d.pot_out); d.pot_out_n = ni; dev_alloc(d.pot_out, d.pot_out_n); }
     CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
-    pot_kernel<<<(n_it * S + 3) / 4, 128, 0, d.st>>>(jtile, ntiles, S, istart - 1, ni, d.pot_part);
+    pot_kernel<<<(n_it * S + 3) / 4, 128, 0, d.st>>>(jtile, ntiles, S, jraw + n, istart - 1, ni, d.pot_part);
     CUDA_CHECK(cudaGetLastError());
     pot_merge_kernel<<<(ni + 127) / 128, 128, 0, d.st>>>(d.pot_part, S, ni, d.pot_out);
     CUDA_CHECK(cudaGetLastError());
@@ -1026,7 +1334,7 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
     if (L.h_flag[0]) FATAL("gpupot: NaN in particle data");
     float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, d.evs0, d.evs1));
     L.ctr[GPUNB_B200_CTR_POT_MS] += ms;
-    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 3;
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
     L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 4.0 * n;
     L.ctr[GPUNB_B200_CTR_D2H_BYTES] += sizeof(double) * (double)ni;
     memcpy(pot, hout, sizeof(double) * ni);
@@ -1076,11 +1384,30 @@ void gpupot_(int *irank, int *istart, int *ni, int *n, double m[], double x[][3]
 int gpunb_b200_version(void) { return 101; }
 const char *gpunb_b200_build_info(void)
 {
-    return "gpunb_b200 sm_100a: regf_kernel<f32x2, TMA bulk j-tiles, TJ=64>, merge_kernel, combine_kernel (P2P), pot_kernel, jpack_kernel";
+    return "gpunb_b200 sm_100a: regf_kernel<f32x2, TMA bulk Morton tiles TJ=64, near/far bodies>, isort, merge(sort), combine (P2P), pot, tilepack";
 }
 int gpunb_b200_num_devices(void) { return (int)L.devs.size(); }
-void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]) { for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) out[k] = L.ctr[k]; }
-void gpunb_b200_reset_counters(void) { for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) L.ctr[k] = 0; }
+void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT])
+{
+    if (L.devinit && !L.devs.empty() && L.devs[0].stats) {
+        Dev &d = L.devs[0];
+        set_dev(d);
+        unsigned long long h[2];
+        CUDA_CHECK(cudaMemcpyAsync(h, d.stats, 16, cudaMemcpyDeviceToHost, d.st));
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        L.ctr[GPUNB_B200_CTR_NEAR_TILES] = (double)h[0];
+        L.ctr[GPUNB_B200_CTR_ALL_TILES] = (double)h[1];
+    }
+    for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) out[k] = L.ctr[k];
+}
+void gpunb_b200_reset_counters(void)
+{
+    for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) L.ctr[k] = 0;
+    if (L.devinit && !L.devs.empty() && L.devs[0].stats) {
+        set_dev(L.devs[0]);
+        CUDA_CHECK(cudaMemsetAsync(L.devs[0].stats, 0, 16, L.devs[0].st));
+    }
+}
 
 void gpunb_b200_set_radii(int *njp, double h2[], double dtr[])
 {

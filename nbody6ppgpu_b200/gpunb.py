@@ -23,9 +23,9 @@ _HERE = Path(__file__).resolve().parent
 _c_int_p = C.POINTER(C.c_int)
 _c_dbl_p = C.POINTER(C.c_double)
 
-N_COUNTERS = 8
+N_COUNTERS = 10
 CTR = dict(grav_ms=0, grav_launches=1, launches=2, h2d_bytes=3, d2h_bytes=4, interactions=5,
-           merge_ms=6, pot_ms=7)
+           merge_ms=6, pot_ms=7, near_tiles=8, all_tiles=9)
 
 
 class LibraryMissing(RuntimeError):

@@ -25,6 +25,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     for rep in range(4):
         ms = lib.sweep_resident(0, nis, 1024, 600, 550, 0)
         best = max(best, nis * n / ms * 1e-6)
+    c = lib.counters()
+    nearfrac = c["near_tiles"] / c["all_tiles"] if c.get("all_tiles", 0) > 0 else None
     small = {}
     for ni in (32, 128, 512):
         lib.reset_counters()
@@ -34,7 +36,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         small[ni] = ni * n * 20 / c["grav_ms"] * 1e-6
     lib.close()
     print(json.dumps({"variant": os.environ.get("GPUNB_B200_VARIANT", "default"), "n": n, "gint_s": best, "lists_exact": ok,
-                      "err_acc_jrkS_jrk_pot": errs, "small_ni_kernel_gints": small}))
+                      "err_acc_jrkS_jrk_pot": errs, "small_ni_kernel_gints": small, "near_frac": nearfrac}))
 else:
     n = sys.argv[1] if len(sys.argv) > 1 else "262144"
     for var in sys.argv[2:] or ["it2", "it2b3", "it1", "it1b5", "it1b6"]:
