@@ -91,6 +91,13 @@ void  gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], doubl
  * (mode 0: FFMA, 1: FFMA2 (f32x2), 2: FADD2, 3: FMUL2, 4: MUFU.RSQ Gop/s, 5: FFMA2+ALU mix). */
 double gpunb_b200_fp32_microbench(int mode, int iters);
 
+/* Far-body microbenchmark (the 27-op pair body in isolation); returns Gint/s.  mode bit0: no MUFU, bit1: operands
+ * from registers instead of LDS.128, mode>=4: two i-particles per lane. */
+double gpunb_b200_farbody_microbench(int mode, int iters, int ctas_per_sm);
+
+/* Tuning aid: per-work-item {start, end} %globaltimer of the last pair-kernel launch (GPUNB_B200_STATS=2). */
+int gpunb_b200_debug_wtimes(unsigned long long *out, int max_items);
+
 /* Multi-GPU j-sharding (the exchange step of the path; reference: the j split over GPUs inside
  * gpunb.velocity.cu:713-715 and its host-side fp64 combine :822-879).
  *

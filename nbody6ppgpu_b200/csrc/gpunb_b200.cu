@@ -30,7 +30,7 @@
 //   regf_kernel    the O(ni*nj) pair kernel.  One WARP = one work item (32*IT i-particles, every S-th
 //                  j-tile).  Tiles stream through warp-private shared memory by TMA bulk copies
 //                  (cp.async.bulk + mbarrier, double buffered); lanes own i-particles, j is broadcast
-//                  from smem; two j per instruction with packed f32x2 FMA/ADD/MUL.
+//                  from smem; scalar FP32 FMA stream (see the note above accumulate()).
 //                  Per (warp, tile) the bounding boxes decide: FAR tiles (no pair can satisfy the
 //                  neighbour criterion, with margin) run a 27-op force-only body; NEAR tiles run the
 //                  full body with the reference predicate.  FP32 chains are 32 terms, then fp64.
@@ -70,6 +70,7 @@ constexpr int NSTAGE      = 2;                    // smem stages per warp
 constexpr int WARPS       = 4;                    // warps per CTA (warp-autonomous: no CTA-wide sync)
 constexpr int NIMAX       = 2048;                 // capacity per call (reference: gpunb.velocity.cu:24)
 constexpr int PART_STRIDE = 8;                    // doubles per partial record (7 used)
+constexpr int OVERSUB     = 1;                    // work items per resident warp (GPUNB_B200_OVERSUB; >1 measured no gain)
 constexpr int SORT_CAP    = 1024;                 // merge_kernel sorts up to this many neighbours per i
 
 // ---------------------------------------------------------------------------------------------
@@ -105,6 +106,10 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+// An FFMA2 whose three operands are three DIFFERENT register pairs runs at ~45 % of the FP32 rate on B200
+// (register-file bandwidth; measured by gpunb_b200_fp32_microbench mode 7: 31 vs 70 TFLOP/s), while two scalar
+// FFMAs run at full rate.  FFMA2 is kept where an operand repeats (squares, broadcast scalars, immediates).
+__device__ __forceinline__ float2 fma2s(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -311,46 +316,49 @@ struct RegfArgs {
     int           segcap;
     int           force_near;  // debugging/tuning: classify every tile as NEAR
     unsigned long long *stats; // optional: [0] near tiles, [1] all tiles (per warp-tile visit)
+    unsigned long long *wtime; // optional: per work item start/end %globaltimer (tuning)
 };
 
-struct IState {               // loop invariants of one i-particle, duplicated for f32x2 operands
-    float2 cx, cy, cz;        // (O_tile - x_i), refreshed per tile
-    float2 nxh, nyh, nzh;     // -(float)x_i : the reference's FP32 position
-    float2 nvx, nvy, nvz;     // -(float)v_i
-    float2 dtr, h2;
+struct IState {               // loop invariants of one i-particle
+    float cx, cy, cz;         // (O_tile - x_i), refreshed per tile
+    float nxh, nyh, nzh;      // -(float)x_i : the reference's FP32 position
+    float nvx, nvy, nvz;      // -(float)v_i
+    float dtr, h2;
 };
-struct Acc {                  // FP32 partial chains (f32x2: one chain per j parity)
-    float2 ax, ay, az, p, jx, jy, jz;
-    __device__ __forceinline__ void clear() { ax = ay = az = p = jx = jy = jz = make_float2(0.f, 0.f); }
+struct Acc {                  // FP32 partial chains
+    float ax, ay, az, p, jx, jy, jz;
+    __device__ __forceinline__ void clear() { ax = ay = az = p = jx = jy = jz = 0.f; }
 };
 
-__device__ __forceinline__ void accumulate(Acc &A, float2 rinv, float2 M, float2 rv, float2 dx, float2 dy, float2 dz,
-                                           float2 dvx, float2 dvy, float2 dvz)
+// All pair arithmetic is SCALAR FP32 on purpose.  Measured on B200 (gpunb_b200_fp32_microbench, profiles/):
+// packed f32x2 instructions give no extra FLOP/s (FFMA2 = 2 pipe cycles), an FFMA2 with three different
+// register pairs runs at 45 % of the FP32 rate, and packed ops interleaved with scalar ones stall on
+// "math pipe throttle" (they need both 16-lane FMA pipes at once).  A scalar stream issues one FP32 op per
+// cycle per SM sub-partition, which is the roofline.
+__device__ __forceinline__ void accumulate(Acc &A, float rinv, float m, float rv, float dx, float dy, float dz,
+                                           float dvx, float dvy, float dvz)
 {   // gpunb.velocity.cu:192-207
-    const float2 rinv2  = mul2(rinv, rinv);
-    const float2 mrinv  = mul2(M, rinv);
-    const float2 mrinv3 = mul2(mrinv, rinv2);
-    const float2 rv3    = mul2(rv, mul2(rinv2, dup2(-3.f)));          // -3 (r.v)/r^2
-    A.p  = add2(A.p, mrinv);
-    A.ax = fma2(mrinv3, dx, A.ax);   A.ay = fma2(mrinv3, dy, A.ay);   A.az = fma2(mrinv3, dz, A.az);
-    A.jx = fma2(mrinv3, fma2(rv3, dx, dvx), A.jx);
-    A.jy = fma2(mrinv3, fma2(rv3, dy, dvy), A.jy);
-    A.jz = fma2(mrinv3, fma2(rv3, dz, dvz), A.jz);
+    const float rinv2  = rinv * rinv;
+    const float mrinv  = m * rinv;
+    const float mrinv3 = mrinv * rinv2;
+    const float rv3    = rv * (rinv2 * -3.f);                 // -3 (r.v)/r^2
+    A.p += mrinv;
+    A.ax = fmaf(mrinv3, dx, A.ax);   A.ay = fmaf(mrinv3, dy, A.ay);   A.az = fmaf(mrinv3, dz, A.az);
+    A.jx = fmaf(mrinv3, fmaf(rv3, dx, dvx), A.jx);
+    A.jy = fmaf(mrinv3, fmaf(rv3, dy, dvy), A.jy);
+    A.jz = fmaf(mrinv3, fmaf(rv3, dz, dvz), A.jz);
 }
 
 // FAR tile: the bounding boxes prove that no pair of (this warp's i-particles, this tile) can satisfy the
-// neighbour criterion, so the body is the force alone: 27 FP32 lane-ops + 1 MUFU per pair.
-__device__ __forceinline__ void interact_far(const IState &I, Acc &A, float2 DX, float2 DY, float2 DZ,
-                                             float2 VX, float2 VY, float2 VZ, float2 M)
+// neighbour criterion, so the body is the force alone: 27 FP32 ops + 1 MUFU per pair.
+__device__ __forceinline__ void interact_far(const IState &I, Acc &A, float DX, float DY, float DZ,
+                                             float VX, float VY, float VZ, float M)
 {
-    const float2 dx = add2(DX, I.cx), dy = add2(DY, I.cy), dz = add2(DZ, I.cz);
-    const float2 dvx = add2(VX, I.nvx), dvy = add2(VY, I.nvy), dvz = add2(VZ, I.nvz);
-    const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-    const float2 rv = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
-    float2 rinv;
-    rinv.x = rsqrt_approx(r2.x);
-    rinv.y = rsqrt_approx(r2.y);
-    accumulate(A, rinv, M, rv, dx, dy, dz, dvx, dvy, dvz);
+    const float dx = DX + I.cx, dy = DY + I.cy, dz = DZ + I.cz;
+    const float dvx = VX + I.nvx, dvy = VY + I.nvy, dvz = VZ + I.nvz;
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float rv = fmaf(dz, dvz, fmaf(dy, dvy, dx * dvx));
+    accumulate(A, rsqrt_approx(r2), M, rv, dx, dy, dz, dvx, dvy, dvz);
 }
 
 // NEAR tile: full body.
@@ -359,34 +367,29 @@ __device__ __forceinline__ void interact_far(const IState &I, Acc &A, float2 DX,
 //   Force: from the tile-local separation, with a Newton-refined rsqrt (a close massive perturber can
 //   dominate the sum, so the single term must hold ~1e-7).  Pairs at r2 == 0 (self) never contribute
 //   (regint.f:40 skips J.EQ.I); the reference GPU code returns NaN for a self pair with h2 == 0.
-// Returns a 2-bit mask of neighbour hits.
+// Returns true for a neighbour hit.
 template <bool MFLAG>
-__device__ __forceinline__ unsigned interact_near(const IState &I, Acc &A, float2 DX, float2 DY, float2 DZ,
-                                                  float2 VX, float2 VY, float2 VZ, float2 M,
-                                                  float2 XH, float2 YH, float2 ZH)
+__device__ __forceinline__ bool interact_near(const IState &I, Acc &A, float DX, float DY, float DZ,
+                                              float VX, float VY, float VZ, float M, float XH, float YH, float ZH)
 {
-    const float2 dxr = add2(XH, I.nxh), dyr = add2(YH, I.nyh), dzr = add2(ZH, I.nzh);
-    const float2 dx = add2(DX, I.cx), dy = add2(DY, I.cy), dz = add2(DZ, I.cz);
-    const float2 dvx = add2(VX, I.nvx), dvy = add2(VY, I.nvy), dvz = add2(VZ, I.nvz);
+    const float dxr = XH + I.nxh, dyr = YH + I.nyh, dzr = ZH + I.nzh;
+    const float dx = DX + I.cx, dy = DY + I.cy, dz = DZ + I.cz;
+    const float dvx = VX + I.nvx, dvy = VY + I.nvy, dvz = VZ + I.nvz;
 
-    const float2 r2r = fma2(dzr, dzr, fma2(dyr, dyr, mul2(dxr, dxr)));
-    const float2 dxp = fma2(I.dtr, dvx, dxr), dyp = fma2(I.dtr, dvy, dyr), dzp = fma2(I.dtr, dvz, dzr);
-    const float2 r2p = fma2(dzp, dzp, fma2(dyp, dyp, mul2(dxp, dxp)));
-    const float2 r2  = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-    const float2 rv  = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
+    const float r2r = fmaf(dzr, dzr, fmaf(dyr, dyr, dxr * dxr));
+    const float dxp = fmaf(I.dtr, dvx, dxr), dyp = fmaf(I.dtr, dvy, dyr), dzp = fmaf(I.dtr, dvz, dzr);
+    const float r2p = fmaf(dzp, dzp, fmaf(dyp, dyp, dxp * dxp));
+    const float r2  = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float rv  = fmaf(dz, dvz, fmaf(dy, dvy, dx * dvx));
 
-    float2 lim = I.h2;
-    if (MFLAG) lim = mul2(M, I.h2);
-    const bool nb0 = fminf(r2r.x, r2p.x) < lim.x;
-    const bool nb1 = fminf(r2r.y, r2p.y) < lim.y;
-    float2 rinv;
-    rinv.x = (nb0 || !(r2.x > 0.f)) ? 0.f : rsqrt_approx(r2.x);
-    rinv.y = (nb1 || !(r2.y > 0.f)) ? 0.f : rsqrt_approx(r2.y);
+    const float lim = MFLAG ? M * I.h2 : I.h2;
+    const bool nb = fminf(r2r, r2p) < lim;
+    float rinv = (nb || !(r2 > 0.f)) ? 0.f : rsqrt_approx(r2);
     // one Newton step: y <- y - y/2 (r2 y^2 - 1)
-    const float2 e = fma2(mul2(r2, rinv), rinv, dup2(-1.f));
-    rinv = fma2(mul2(rinv, e), dup2(-0.5f), rinv);
+    const float e = fmaf(r2 * rinv, rinv, -1.f);
+    rinv = fmaf(rinv * e, -0.5f, rinv);
     accumulate(A, rinv, M, rv, dx, dy, dz, dvx, dvy, dvz);
-    return (nb0 ? 1u : 0u) | (nb1 ? 2u : 0u);
+    return nb;
 }
 
 template <int IT, bool MFLAG, int MINB>
@@ -401,6 +404,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + WARPS * NSTAGE * TILE_BYTES) + warp * NSTAGE;
 
     const int it = w / a.S, s = w - it * a.S;         // this warp visits tiles s, s+S, s+2S, ...
+    if (a.wtime && lane == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); a.wtime[3 * w] = t0; }
 
     if (lane == 0) {
 #pragma unroll
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
 
     // i-particles of this lane (Morton-ordered block: the warp's i-particles are close in space)
     IState I[IT];
-    Acc    A[IT];
+    Acc    A[IT][2];          // two chains per quantity (even / odd j): 32-term FP32 chains, more ILP
     double D[IT][7], xid[IT][3];
     float  islack[IT];        // fp32 rounding of x_i itself (the predicate sees (float)x_i)
     int    cnt[IT], iidx[IT];
@@ -439,12 +443,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         }
         const float xh[3] = {(float)xid[k][0], (float)xid[k][1], (float)xid[k][2]};
         const float vf[3] = {(float)v[0], (float)v[1], (float)v[2]};
-        I[k].nxh = dup2(-xh[0]); I[k].nyh = dup2(-xh[1]); I[k].nzh = dup2(-xh[2]);
+        I[k].nxh = -xh[0]; I[k].nyh = -xh[1]; I[k].nzh = -xh[2];
         islack[k] = 1.2e-7f * fmaxf(fabsf(xh[0]), fmaxf(fabsf(xh[1]), fabsf(xh[2])));
-        I[k].nvx = dup2(-vf[0]); I[k].nvy = dup2(-vf[1]); I[k].nvz = dup2(-vf[2]);
-        I[k].dtr = dup2((float)dtr);
-        I[k].h2  = dup2(valid ? (float)h2 : 0.f);
-        A[k].clear();
+        I[k].nvx = -vf[0]; I[k].nvy = -vf[1]; I[k].nvz = -vf[2];
+        I[k].dtr = (float)dtr;
+        I[k].h2  = valid ? (float)h2 : 0.f;
+        A[k][0].clear(); A[k][1].clear();
 #pragma unroll
         for (int c = 0; c < 7; c++) D[k][c] = 0.0;
         cnt[k]  = 0;
@@ -453,14 +457,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
     auto flush = [&]() {
 #pragma unroll
         for (int k = 0; k < IT; k++) {
-            D[k][0] += (double)(A[k].ax.x + A[k].ax.y);
-            D[k][1] += (double)(A[k].ay.x + A[k].ay.y);
-            D[k][2] += (double)(A[k].az.x + A[k].az.y);
-            D[k][3] += (double)(A[k].jx.x + A[k].jx.y);
-            D[k][4] += (double)(A[k].jy.x + A[k].jy.y);
-            D[k][5] += (double)(A[k].jz.x + A[k].jz.y);
-            D[k][6] += (double)(A[k].p.x + A[k].p.y);
-            A[k].clear();
+            D[k][0] += (double)(A[k][0].ax + A[k][1].ax);
+            D[k][1] += (double)(A[k][0].ay + A[k][1].ay);
+            D[k][2] += (double)(A[k][0].az + A[k][1].az);
+            D[k][3] += (double)(A[k][0].jx + A[k][1].jx);
+            D[k][4] += (double)(A[k][0].jy + A[k][1].jy);
+            D[k][5] += (double)(A[k][0].jz + A[k][1].jz);
+            D[k][6] += (double)(A[k][0].p + A[k][1].p);
+            A[k][0].clear(); A[k][1].clear();
         }
     };
 
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
 #pragma unroll
         for (int k = 0; k < IT; k++) {
             cf[k][0] = (float)(Ox - xid[k][0]); cf[k][1] = (float)(Oy - xid[k][1]); cf[k][2] = (float)(Oz - xid[k][2]);
-            I[k].cx = dup2(cf[k][0]); I[k].cy = dup2(cf[k][1]); I[k].cz = dup2(cf[k][2]);
+            I[k].cx = cf[k][0]; I[k].cy = cf[k][1]; I[k].cz = cf[k][2];
         }
         // Per-lane test of i against the tile's boxes: FAR iff no j of the tile can satisfy the reference
         // criterion min(|dx|^2, |dx + dtr dv|^2) < h2 [* mj], with margins that dominate every fp32 rounding
@@ -501,12 +505,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 for (int c = 0; c < 3; c++) {
                     const float g = fmaxf(fabsf(cf[k][c]) - jh[c] - 2.4e-7f * (fabsf(cf[k][c]) + jh[c]) - islack[k], 0.f);
                     d2 = fmaf(g, g, d2);
-                    const float u = fabsf(jvc[c] + (c == 0 ? I[k].nvx.x : c == 1 ? I[k].nvy.x : I[k].nvz.x)) + jvh[c];
+                    const float u = fabsf(jvc[c] + (c == 0 ? I[k].nvx : c == 1 ? I[k].nvy : I[k].nvz)) + jvh[c];
                     dv2 = fmaf(u, u, dv2);
                 }
                 const float d = sqrtf(d2);
-                const float reach = fabsf(I[k].dtr.x) * sqrtf(dv2) * 1.00001f;
-                const float lim = (MFLAG ? h3.w * I[k].h2.x : I[k].h2.x) * 1.0001f;
+                const float reach = fabsf(I[k].dtr) * sqrtf(dv2) * 1.00001f;
+                const float lim = (MFLAG ? h3.w * I[k].h2 : I[k].h2) * 1.0001f;
                 const float dd = d - reach;
                 const bool f = (dd > 0.f) && (dd * dd > lim) && (d2 > 0.f);
                 lane_far &= (f || iidx[k] < 0);
@@ -523,10 +527,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 const float4 M  = c[C_M * 16 + q];
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
-                    interact_far(I[k], A[k], make_float2(DX.x, DX.y), make_float2(DY.x, DY.y), make_float2(DZ.x, DZ.y),
-                                 make_float2(VX.x, VX.y), make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), make_float2(M.x, M.y));
-                    interact_far(I[k], A[k], make_float2(DX.z, DX.w), make_float2(DY.z, DY.w), make_float2(DZ.z, DZ.w),
-                                 make_float2(VX.z, VX.w), make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), make_float2(M.z, M.w));
+                    interact_far(I[k], A[k][0], DX.x, DY.x, DZ.x, VX.x, VY.x, VZ.x, M.x);
+                    interact_far(I[k], A[k][1], DX.y, DY.y, DZ.y, VX.y, VY.y, VZ.y, M.y);
+                    interact_far(I[k], A[k][0], DX.z, DY.z, DZ.z, VX.z, VY.z, VZ.z, M.z);
+                    interact_far(I[k], A[k][1], DX.w, DY.w, DZ.w, VX.w, VY.w, VZ.w, M.w);
                 }
             }
         } else {
@@ -540,15 +544,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 unsigned hit = 0;
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
-                    const unsigned h0 = interact_near<MFLAG>(I[k], A[k],
-                        make_float2(DX.x, DX.y), make_float2(DY.x, DY.y), make_float2(DZ.x, DZ.y),
-                        make_float2(VX.x, VX.y), make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), make_float2(M.x, M.y),
-                        make_float2(XH.x, XH.y), make_float2(YH.x, YH.y), make_float2(ZH.x, ZH.y));
-                    const unsigned h1b = interact_near<MFLAG>(I[k], A[k],
-                        make_float2(DX.z, DX.w), make_float2(DY.z, DY.w), make_float2(DZ.z, DZ.w),
-                        make_float2(VX.z, VX.w), make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), make_float2(M.z, M.w),
-                        make_float2(XH.z, XH.w), make_float2(YH.z, YH.w), make_float2(ZH.z, ZH.w));
-                    hit |= (h0 | (h1b << 2)) << (4 * k);
+                    const bool h0 = interact_near<MFLAG>(I[k], A[k][0], DX.x, DY.x, DZ.x, VX.x, VY.x, VZ.x, M.x, XH.x, YH.x, ZH.x);
+                    const bool h1b = interact_near<MFLAG>(I[k], A[k][1], DX.y, DY.y, DZ.y, VX.y, VY.y, VZ.y, M.y, XH.y, YH.y, ZH.y);
+                    const bool h2b = interact_near<MFLAG>(I[k], A[k][0], DX.z, DY.z, DZ.z, VX.z, VY.z, VZ.z, M.z, XH.z, YH.z, ZH.z);
+                    const bool h3b = interact_near<MFLAG>(I[k], A[k][1], DX.w, DY.w, DZ.w, VX.w, VY.w, VZ.w, M.w, XH.w, YH.w, ZH.w);
+                    hit |= ((h0 ? 1u : 0u) | (h1b ? 2u : 0u) | (h2b ? 4u : 0u) | (h3b ? 8u : 0u)) << (4 * k);
                 }
                 if (hit) {                             // rare: ~2e-4 of pairs are neighbours
                     const int pb = t * TJ + q * 4;
@@ -587,6 +587,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         }
     }
     if (a.stats && lane == 0) { atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all); }
+    if (a.wtime && lane == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); a.wtime[3 * w + 1] = t1; a.wtime[3 * w + 2] = n_near; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -800,7 +801,7 @@ struct Dev {
     int id = -1;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs0 = nullptr, evs1 = nullptr, evdone = nullptr;
-    int nsm = 0, warps_resident = 0, variant = DEFAULT_VARIANT, itile = 32;
+    int nsm = 0, warps_resident = 0, variant = DEFAULT_VARIANT, itile = 32, oversub = OVERSUB;
     // j: full fp64 snapshot (m | x | v, packed for the current nj_total) and the tiles of this device's shard
     int raw_cap = 0, tile_cap = 0;
     double *jraw = nullptr;
@@ -815,6 +816,7 @@ struct Dev {
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     int *iperm = nullptr;         // Morton order of the current i-block
     unsigned long long *stats = nullptr;   // [0] near (warp,tile) visits, [1] all visits (GPUNB_B200_STATS=1)
+    unsigned long long *wtime = nullptr;   // per work item start/end timestamps (GPUNB_B200_STATS=2)
     double *ibuf = nullptr;       // 8*NIMAX doubles: h2 | dtr | x | v
     int items_cap = 0;
     double *part = nullptr; int *cnt = nullptr;
@@ -926,6 +928,7 @@ void lib_devinit(int irank)
         }
         if (nb < 1) FATAL("regf_kernel does not fit on an SM");
         d.warps_resident = d.nsm * nb * WARPS;
+        { const char *e = getenv("GPUNB_B200_OVERSUB"); if (e && atoi(e) >= 1 && atoi(e) <= 32) d.oversub = atoi(e); }
         fprintf(stderr, "# GPU initialization - rank: %d; HOST %s; NGPU %d; device: %d %s; B200-native regf[%s]: %d SMs x %d CTAs x %d warps\n",
                 irank, host, (int)ids.size(), d.id, prop.name, V.name, d.nsm, nb, WARPS);
         L.devs.push_back(d);
@@ -1010,7 +1013,7 @@ void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root)
 {
     set_dev(d);
     // n_itiles * S never exceeds warps_resident (+ n_itiles when S = 1)
-    const int items = d.warps_resident + NIMAX / d.itile;
+    const int items = d.warps_resident * d.oversub + NIMAX / d.itile;
     const int segcap = ((nnbmax > 0 ? nnbmax : 1) + 3) & ~3;
     if (items > d.items_cap) {
         CUDA_CHECK(cudaStreamSynchronize(d.st));
@@ -1065,6 +1068,7 @@ void lib_open(int nbmax, int irank)
         if (!d.fr)      dev_alloc(d.fr, (size_t)8 * NIMAX);
         if (!d.iperm)   dev_alloc(d.iperm, (size_t)NIMAX);
         if (!d.stats && getenv("GPUNB_B200_STATS")) { dev_alloc(d.stats, 2); CUDA_CHECK(cudaMemsetAsync(d.stats, 0, 16, d.st)); }
+        if (!d.wtime && getenv("GPUNB_B200_STATS") && atoi(getenv("GPUNB_B200_STATS")) >= 2) dev_alloc(d.wtime, (size_t)3 * 65536);
         if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
     }
     const size_t hj = (size_t)7 * ((size_t)nbmax + 64);
@@ -1084,7 +1088,7 @@ void lib_close()
         dev_free(d.jraw); dev_free(d.jtile); dev_free(d.radii); d.raw_cap = d.tile_cap = 0; d.nj = d.ntiles = d.nj_total = 0;
         dev_free(d.ibuf); dev_free(d.part); dev_free(d.cnt); d.items_cap = 0;
         dev_free(d.seg); d.seg_ints = 0; dev_free(d.res_f); dev_free(d.res_list); d.res_list_ints = 0;
-        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.stats);
+        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.stats); dev_free(d.wtime);
         dev_free(d.jidx);
         dev_free(d.nanflag);
     }
@@ -1133,7 +1137,7 @@ Plan make_plan(const Dev &d, int ni)
 {
     Plan p;
     p.n_itiles = (ni + d.itile - 1) / d.itile;
-    int S = d.warps_resident / p.n_itiles;
+    int S = (d.warps_resident * d.oversub) / p.n_itiles;
     if (S < 1) S = 1;
     if (S > d.ntiles) S = d.ntiles > 0 ? d.ntiles : 1;
     p.S = S;
@@ -1151,7 +1155,7 @@ void launch_regf(Dev &d, int ni, const IBlock &ib, int lmax, int nnbmax, int m_f
     RegfArgs a;
     a.tiles = d.jtile; a.jidx = d.jidx; a.ntiles = d.ntiles; a.iperm = d.iperm;
     { static int fn = -1; if (fn < 0) { const char *e = getenv("GPUNB_B200_FORCE_NEAR"); fn = e ? atoi(e) : 0; } a.force_near = fn; }
-    a.stats = d.stats;
+    a.stats = d.stats; a.wtime = d.wtime;
     a.h2 = ib.h2; a.dtr = ib.dtr; a.xi = ib.xi; a.vi = ib.vi;
     a.ni = ni; a.n_itiles = p.n_itiles; a.S = p.S; a.n_items = p.n_items;
     a.part = d.part; a.cnt = d.cnt; a.seg = d.seg; a.segcap = d.segcap;
@@ -1459,6 +1463,18 @@ void gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double
     *n_last = ni; *lmaxp = lmax;
     if (ni <= 0) return;
     fetch_results(ni, lmax, &acc[0][0], &jrk[0][0], pot, list);
+}
+
+// tuning aid: per-work-item start/end timestamps (ns) of the LAST regf_kernel launch (GPUNB_B200_STATS=2)
+int gpunb_b200_debug_wtimes(unsigned long long *out, int max_items)
+{
+    if (!L.devinit || L.devs.empty() || !L.devs[0].wtime) return 0;
+    Dev &d = L.devs[0];
+    set_dev(d);
+    const int n = max_items < 65536 ? max_items : 65536;
+    CUDA_CHECK(cudaMemcpyAsync(out, d.wtime, sizeof(unsigned long long) * 3 * n, cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    return n;
 }
 
 int gpunb_b200_nccl_unique_id(unsigned char id128[128])
