@@ -7,7 +7,7 @@
 // Data layout in HBM (per device)
 //   jraw   : the caller's fp64 snapshot, m[nj] | x[nj][3] | v[nj][3]                          56 B/j
 //   jtile  : the device's j-shard, SORTED ALONG A HILBERT CURVE and cut into tiles of TJ=64.
-//            One tile = 64 B header + 10 float arrays of 64                                  ~41 B/j
+//            One tile = 64 B header + 13 float arrays of 64                                  ~53 B/j
 //              header : tile origin O (3 doubles, centre of the tile's bounding box), box half-extents,
 //                       velocity box (centre, half-extents), largest mass
 //              arrays : dx,dy,dz = (float)(x - O)   tile-local offsets: |offset| <= tile extent, so the
@@ -17,7 +17,8 @@
 //                       xh,yh,zh = (float)x         exactly what the reference's FP32 cast sees
 //                                                   (gpunb.velocity.cu:62-64): only read by tiles that
 //                                                   can hold neighbours, to evaluate the reference's
-//                                                   neighbour predicate bit for bit.
+//                                                   neighbour predicate bit for bit;
+//                       xl,yl,zl = (float)(x - xh)  low words: NEAR pairs use the float-float separation.
 //            A tile is contiguous: ONE 1-D TMA bulk copy brings header and data.
 //   jidx   : sorted slot -> global j index (ghost slots of the last tile: -1)
 //   part   : per (j-slice s, i) partial sums, 7 doubles, + count                            [S][ni]
@@ -62,10 +63,10 @@ namespace {
 
 constexpr int TJ          = 64;                   // j-particles per tile
 constexpr int HDR         = 16;                   // header floats
-constexpr int NCOMP       = 10;                   // float arrays per tile
-constexpr int TILE_FLOATS = HDR + TJ * NCOMP;     // 656
-constexpr int TILE_BYTES  = TILE_FLOATS * 4;      // 2624 (multiple of 16: one TMA bulk copy)
-enum { C_DX = 0, C_DY, C_DZ, C_VX, C_VY, C_VZ, C_M, C_XH, C_YH, C_ZH };
+constexpr int NCOMP       = 13;                   // float arrays per tile
+constexpr int TILE_FLOATS = HDR + TJ * NCOMP;     // 848
+constexpr int TILE_BYTES  = TILE_FLOATS * 4;      // 3392 (multiple of 16: one TMA bulk copy)
+enum { C_DX = 0, C_DY, C_DZ, C_VX, C_VY, C_VZ, C_M, C_XH, C_YH, C_ZH, C_XL, C_YL, C_ZL };
 constexpr int NSTAGE      = 2;                    // smem stages per warp
 constexpr int WARPS       = 4;                    // warps per CTA (warp-autonomous: no CTA-wide sync)
 constexpr int NIMAX       = 2048;                 // capacity per call (reference: gpunb.velocity.cu:24)
@@ -262,7 +263,9 @@ __global__ void __launch_bounds__(128) tilepack_kernel(int n, int ntiles, int jo
         for (int c = 0; c < 3; c++) {
             tb[HDR + (C_DX + c) * TJ + k] = (float)(px[h][c] - O[c]);
             tb[HDR + (C_VX + c) * TJ + k] = pv[h][c];
-            tb[HDR + (C_XH + c) * TJ + k] = (float)px[h][c];
+            const float xh = (float)px[h][c];
+            tb[HDR + (C_XH + c) * TJ + k] = xh;
+            tb[HDR + (C_XL + c) * TJ + k] = (float)(px[h][c] - (double)xh);
         }
         tb[HDR + C_M * TJ + k] = pm[h];
     }
@@ -322,6 +325,7 @@ struct RegfArgs {
 struct IState {               // loop invariants of one i-particle
     float cx, cy, cz;         // (O_tile - x_i), refreshed per tile
     float nxh, nyh, nzh;      // -(float)x_i : the reference's FP32 position
+    float nxl, nyl, nzl;      // -(x_i - (float)x_i): low word, so that NEAR pairs get a float-float separation
     float nvx, nvy, nvz;      // -(float)v_i
     float dtr, h2;
 };
@@ -364,16 +368,18 @@ __device__ __forceinline__ void interact_far(const IState &I, Acc &A, float DX, 
 // NEAR tile: full body.
 //   Predicate: the reference's, bit for bit, on the fp32-rounded inputs (gpunb.velocity.cu:168-187,
 //   :235 for m_flag): r2 = fma(dz,dz,fma(dy,dy,dx*dx)), dxp = fma(dtr,dvx,dx), min(r2,r2p) < h2 [*mj].
-//   Force: from the tile-local separation, with a Newton-refined rsqrt (a close massive perturber can
-//   dominate the sum, so the single term must hold ~1e-7).  Pairs at r2 == 0 (self) never contribute
+//   Force: from the float-float separation (xh_j - xh_i) + (xl_j - xl_i) -- exact to ~2^-48 whatever the tile
+//   extent -- with a Newton-refined rsqrt (a close massive perturber can dominate the sum, so the single
+//   term must hold ~1e-7).  Pairs at r2 == 0 (self) never contribute
 //   (regint.f:40 skips J.EQ.I); the reference GPU code returns NaN for a self pair with h2 == 0.
 // Returns true for a neighbour hit.
 template <bool MFLAG>
-__device__ __forceinline__ bool interact_near(const IState &I, Acc &A, float DX, float DY, float DZ,
-                                              float VX, float VY, float VZ, float M, float XH, float YH, float ZH)
+__device__ __forceinline__ bool interact_near(const IState &I, Acc &A,
+                                              float VX, float VY, float VZ, float M, float XH, float YH, float ZH,
+                                              float XL, float YL, float ZL)
 {
     const float dxr = XH + I.nxh, dyr = YH + I.nyh, dzr = ZH + I.nzh;
-    const float dx = DX + I.cx, dy = DY + I.cy, dz = DZ + I.cz;
+    const float dx = dxr + (XL + I.nxl), dy = dyr + (YL + I.nyl), dz = dzr + (ZL + I.nzl);
     const float dvx = VX + I.nvx, dvy = VY + I.nvy, dvz = VZ + I.nvz;
 
     const float r2r = fmaf(dzr, dzr, fmaf(dyr, dyr, dxr * dxr));
@@ -444,6 +450,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         const float xh[3] = {(float)xid[k][0], (float)xid[k][1], (float)xid[k][2]};
         const float vf[3] = {(float)v[0], (float)v[1], (float)v[2]};
         I[k].nxh = -xh[0]; I[k].nyh = -xh[1]; I[k].nzh = -xh[2];
+        I[k].nxl = -(float)(xid[k][0] - (double)xh[0]); I[k].nyl = -(float)(xid[k][1] - (double)xh[1]);
+        I[k].nzl = -(float)(xid[k][2] - (double)xh[2]);
         islack[k] = 1.2e-7f * fmaxf(fabsf(xh[0]), fmaxf(fabsf(xh[1]), fabsf(xh[2])));
         I[k].nvx = -vf[0]; I[k].nvy = -vf[1]; I[k].nvz = -vf[2];
         I[k].dtr = (float)dtr;
@@ -508,11 +516,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                     const float u = fabsf(jvc[c] + (c == 0 ? I[k].nvx : c == 1 ? I[k].nvy : I[k].nvz)) + jvh[c];
                     dv2 = fmaf(u, u, dv2);
                 }
+                // precision: the FAR body forms dx = c + offset in fp32 (error ~2^-24 (|c|+h)); keep that below
+                // ~1e-7 of the smallest separation by sending tiles closer than half their own reach NEAR
+                const float sreach = fmaxf(fabsf(cf[k][0]) + jh[0], fmaxf(fabsf(cf[k][1]) + jh[1], fabsf(cf[k][2]) + jh[2]));
                 const float d = sqrtf(d2);
                 const float reach = fabsf(I[k].dtr) * sqrtf(dv2) * 1.00001f;
                 const float lim = (MFLAG ? h3.w * I[k].h2 : I[k].h2) * 1.0001f;
                 const float dd = d - reach;
-                const bool f = (dd > 0.f) && (dd * dd > lim) && (d2 > 0.f);
+                const bool f = (dd > 0.f) && (dd * dd > lim) && (d2 > 0.25f * sreach * sreach);
                 lane_far &= (f || iidx[k] < 0);
             }
         }
@@ -537,17 +548,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             n_near++;
 #pragma unroll 1
             for (int q = 0; q < TJ / 4; q++) {
-                const float4 DX = c[C_DX * 16 + q], DY = c[C_DY * 16 + q], DZ = c[C_DZ * 16 + q];
                 const float4 VX = c[C_VX * 16 + q], VY = c[C_VY * 16 + q], VZ = c[C_VZ * 16 + q];
                 const float4 M  = c[C_M * 16 + q];
                 const float4 XH = c[C_XH * 16 + q], YH = c[C_YH * 16 + q], ZH = c[C_ZH * 16 + q];
+                const float4 XL = c[C_XL * 16 + q], YL = c[C_YL * 16 + q], ZL = c[C_ZL * 16 + q];
                 unsigned hit = 0;
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
-                    const bool h0 = interact_near<MFLAG>(I[k], A[k][0], DX.x, DY.x, DZ.x, VX.x, VY.x, VZ.x, M.x, XH.x, YH.x, ZH.x);
-                    const bool h1b = interact_near<MFLAG>(I[k], A[k][1], DX.y, DY.y, DZ.y, VX.y, VY.y, VZ.y, M.y, XH.y, YH.y, ZH.y);
-                    const bool h2b = interact_near<MFLAG>(I[k], A[k][0], DX.z, DY.z, DZ.z, VX.z, VY.z, VZ.z, M.z, XH.z, YH.z, ZH.z);
-                    const bool h3b = interact_near<MFLAG>(I[k], A[k][1], DX.w, DY.w, DZ.w, VX.w, VY.w, VZ.w, M.w, XH.w, YH.w, ZH.w);
+                    const bool h0 = interact_near<MFLAG>(I[k], A[k][0], VX.x, VY.x, VZ.x, M.x, XH.x, YH.x, ZH.x, XL.x, YL.x, ZL.x);
+                    const bool h1b = interact_near<MFLAG>(I[k], A[k][1], VX.y, VY.y, VZ.y, M.y, XH.y, YH.y, ZH.y, XL.y, YL.y, ZL.y);
+                    const bool h2b = interact_near<MFLAG>(I[k], A[k][0], VX.z, VY.z, VZ.z, M.z, XH.z, YH.z, ZH.z, XL.z, YL.z, ZL.z);
+                    const bool h3b = interact_near<MFLAG>(I[k], A[k][1], VX.w, VY.w, VZ.w, M.w, XH.w, YH.w, ZH.w, XL.w, YL.w, ZL.w);
                     hit |= ((h0 ? 1u : 0u) | (h1b ? 2u : 0u) | (h2b ? 4u : 0u) | (h3b ? 8u : 0u)) << (4 * k);
                 }
                 if (hit) {                             // rare: ~2e-4 of pairs are neighbours
