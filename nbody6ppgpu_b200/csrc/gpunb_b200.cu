@@ -8,8 +8,8 @@
 //   jraw   : the caller's fp64 snapshot, m[nj] | x[nj][3] | v[nj][3]                          56 B/j
 //   jtile  : the device's j-shard, SORTED ALONG A HILBERT CURVE and cut into tiles of TJ=64.
 //            One tile = 64 B header + 13 float arrays of 64                                  ~53 B/j
-//              header : tile origin O (3 doubles, centre of the tile's bounding box), box half-extents,
-//                       velocity box (centre, half-extents), largest mass
+//              header : tile origin O = Oh + Ol (two floats per axis, centre of the tile's bounding box), box
+//                       half-extents, velocity box (centre, half-extents), sqrt of the largest mass
 //              arrays : dx,dy,dz = (float)(x - O)   tile-local offsets: |offset| <= tile extent, so the
 //                                                   pair separation (O - x_i) + offset keeps a relative
 //                                                   precision of 2^-24 no matter how large |x| is;
@@ -67,12 +67,16 @@ constexpr int NCOMP       = 13;                   // float arrays per tile
 constexpr int TILE_FLOATS = HDR + TJ * NCOMP;     // 848
 constexpr int TILE_BYTES  = TILE_FLOATS * 4;      // 3392 (multiple of 16: one TMA bulk copy)
 enum { C_DX = 0, C_DY, C_DZ, C_VX, C_VY, C_VZ, C_M, C_XH, C_YH, C_ZH, C_XL, C_YL, C_ZL };
-constexpr int NSTAGE      = 2;                    // smem stages per warp
+constexpr int NSTAGE      = 3;                    // smem stages per warp
 constexpr int WARPS       = 4;                    // warps per CTA (warp-autonomous: no CTA-wide sync)
 constexpr int NIMAX       = 2048;                 // capacity per call (reference: gpunb.velocity.cu:24)
 constexpr int PART_STRIDE = 8;                    // doubles per partial record (7 used)
 constexpr int OVERSUB     = 1;                    // work items per resident warp (GPUNB_B200_OVERSUB; >1 measured no gain)
-constexpr int SORT_CAP    = 1024;                 // merge_kernel sorts up to this many neighbours per i
+constexpr int SORT_CAP    = 1024;
+#ifndef FAR_UNROLL
+#define FAR_UNROLL 2
+#endif
+constexpr int FAR_UNROLL_Q = FAR_UNROLL;          // quads of j per iteration of the FAR loop                 // merge_kernel sorts up to this many neighbours per i
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
@@ -237,24 +241,28 @@ __global__ void __launch_bounds__(128) tilepack_kernel(int n, int ntiles, int jo
     }
     float *tb = tiles + (size_t)t * TILE_FLOATS;
     double O[3];
+    float Oh[3], Ol[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         mn[c] = warp_min(mn[c]); mx[c] = warp_max(mx[c]);
         vmn[c] = warp_min(vmn[c]); vmx[c] = warp_max(vmx[c]);
-        O[c] = 0.5 * (mn[c] + mx[c]);
+        // tile origin = centre of the bounding box, REPRESENTED AS TWO FLOATS (Oh + Ol): the pair kernel forms
+        // (O - x_i) in fp32 as (Oh - xh_i) + (Ol - xl_i); the tile-local offsets are taken from exactly that O
+        const double oc = 0.5 * (mn[c] + mx[c]);
+        Oh[c] = (float)oc; Ol[c] = (float)(oc - (double)Oh[c]);
+        O[c] = (double)Oh[c] + (double)Ol[c];
     }
     mmax = warp_max(mmax);
     if (lane == 0) {
-        double *od = reinterpret_cast<double *>(tb);
-        od[0] = O[0]; od[1] = O[1]; od[2] = O[2];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
+            tb[c] = Oh[c]; tb[3 + c] = Ol[c];
             // half-extents rounded up (conservative): fp32-rounded coordinates may sit 1 ulp outside
-            tb[6 + c]  = (float)(0.5 * (mx[c] - mn[c])) * 1.000001f + 1.2e-7f * (float)fmax(fabs(mn[c]), fabs(mx[c])) + 1e-30f;
+            tb[6 + c]  = (float)fmax(mx[c] - O[c], O[c] - mn[c]) * 1.000002f + 1.2e-7f * (float)fmax(fabs(mn[c]), fabs(mx[c])) + 1e-30f;
             tb[9 + c]  = 0.5f * (vmn[c] + vmx[c]);
             tb[12 + c] = 0.5f * (vmx[c] - vmn[c]) * 1.000001f + 1.2e-7f * fmaxf(fabsf(vmn[c]), fabsf(vmx[c])) + 1e-30f;
         }
-        tb[15] = mmax;
+        tb[15] = sqrtf(mmax) * 1.000001f;          // sqrt of the largest mass (m_flag criterion h2*mj), rounded up
     }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -328,17 +336,25 @@ struct IState {               // loop invariants of one i-particle
     float nxl, nyl, nzl;      // -(x_i - (float)x_i): low word, so that NEAR pairs get a float-float separation
     float nvx, nvy, nvz;      // -(float)v_i
     float dtr, h2;
+    float rs, adtr, slack;    // classification: sqrt(h2) and |dtr| with their safety margins, fp32 rounding of x_i
 };
-struct Acc {                  // FP32 partial chains
+struct Acc {                  // FP32 partial chains (scalar view: NEAR body)
     float ax, ay, az, p, jx, jy, jz;
     __device__ __forceinline__ void clear() { ax = ay = az = p = jx = jy = jz = 0.f; }
 };
+struct Acc2 {                 // the same two chains (.x: even j, .y: odd j) as aligned register pairs: FAR body (f32x2)
+    float2 ax, ay, az, p, jx, jy, jz;
+    __device__ __forceinline__ void clear() { ax = ay = az = p = jx = jy = jz = make_float2(0.f, 0.f); }
+};
 
-// All pair arithmetic is SCALAR FP32 on purpose.  Measured on B200 (gpunb_b200_fp32_microbench, profiles/):
-// packed f32x2 instructions give no extra FLOP/s (FFMA2 = 2 pipe cycles), an FFMA2 with three different
-// register pairs runs at 45 % of the FP32 rate, and packed ops interleaved with scalar ones stall on
-// "math pipe throttle" (they need both 16-lane FMA pipes at once).  A scalar stream issues one FP32 op per
-// cycle per SM sub-partition, which is the roofline.
+// Instruction shapes are chosen from measurements on B200 (scripts/exp/farbody_exp.cu, profiles/r01d_farbody_exp.txt):
+//   * the register file delivers one 32-bit register per bank (even / odd) per cycle and sub-partition, so an FFMA
+//     with three distinct register operands costs 1.4-2 issue cycles (scalar FFMA stream: 70 % of the lane rate,
+//     FMUL/FADD streams: 96 %); the scalar 27-op far body runs at 38 cycles per pair and warp, issue-bound;
+//   * packed f32x2 (FFMA2/FADD2/FMUL2 on aligned register pairs, two j per instruction) reads both banks in
+//     lock-step: <= 2 distinct operand pairs cost the 2 pipe cycles, 3 distinct pairs ~4.8.  The packed far body
+//     runs at 34 cycles per pair (+9 %) and needs half the issue slots, which leaves room for the LDS/MUFU/
+//     header instructions.  The far body is therefore packed over j; the NEAR body stays scalar.
 __device__ __forceinline__ void accumulate(Acc &A, float rinv, float m, float rv, float dx, float dy, float dz,
                                            float dvx, float dvy, float dvz)
 {   // gpunb.velocity.cu:192-207
@@ -354,15 +370,25 @@ __device__ __forceinline__ void accumulate(Acc &A, float rinv, float m, float rv
 }
 
 // FAR tile: the bounding boxes prove that no pair of (this warp's i-particles, this tile) can satisfy the
-// neighbour criterion, so the body is the force alone: 27 FP32 ops + 1 MUFU per pair.
-__device__ __forceinline__ void interact_far(const IState &I, Acc &A, float DX, float DY, float DZ,
-                                             float VX, float VY, float VZ, float M)
+// neighbour criterion, so the body is the force alone: 27 FP32 ops + 1 MUFU per pair, two pairs per instruction.
+// Order of the accumulating FFMA2s: the triples share their first operand (reuse cache -> 2 distinct pairs).
+__device__ __forceinline__ void interact_far2(const float2 cx, const float2 cy, const float2 cz,
+                                              const float2 nvx, const float2 nvy, const float2 nvz, Acc2 &A,
+                                              float2 DX, float2 DY, float2 DZ, float2 VX, float2 VY, float2 VZ, float2 M)
 {
-    const float dx = DX + I.cx, dy = DY + I.cy, dz = DZ + I.cz;
-    const float dvx = VX + I.nvx, dvy = VY + I.nvy, dvz = VZ + I.nvz;
-    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const float rv = fmaf(dz, dvz, fmaf(dy, dvy, dx * dvx));
-    accumulate(A, rsqrt_approx(r2), M, rv, dx, dy, dz, dvx, dvy, dvz);
+    const float2 dx = add2(DX, cx), dy = add2(DY, cy), dz = add2(DZ, cz);
+    const float2 dvx = add2(VX, nvx), dvy = add2(VY, nvy), dvz = add2(VZ, nvz);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    const float2 rv = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
+    const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+    const float2 rinv2  = mul2(rinv, rinv);
+    const float2 mrinv  = mul2(M, rinv);
+    const float2 mrinv3 = mul2(mrinv, rinv2);
+    const float2 rv3    = mul2(rv, mul2(rinv2, dup2(-3.f)));            // -3 (r.v)/r^2   (gpunb.velocity.cu:192-207)
+    A.p = add2(A.p, mrinv);
+    const float2 ix = fma2(rv3, dx, dvx), iy = fma2(rv3, dy, dvy), iz = fma2(rv3, dz, dvz);
+    A.ax = fma2(mrinv3, dx, A.ax);   A.ay = fma2(mrinv3, dy, A.ay);   A.az = fma2(mrinv3, dz, A.az);
+    A.jx = fma2(mrinv3, ix, A.jx);   A.jy = fma2(mrinv3, iy, A.jy);   A.jz = fma2(mrinv3, iz, A.jz);
 }
 
 // NEAR tile: full body.
@@ -429,9 +455,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
 
     // i-particles of this lane (Morton-ordered block: the warp's i-particles are close in space)
     IState I[IT];
-    Acc    A[IT][2];          // two chains per quantity (even / odd j): 32-term FP32 chains, more ILP
-    double D[IT][7], xid[IT][3];
-    float  islack[IT];        // fp32 rounding of x_i itself (the predicate sees (float)x_i)
+    Acc2   P[IT];             // two chains per quantity (.x even / .y odd j): 32-term FP32 chains
+    double D[IT][7];
     int    cnt[IT], iidx[IT];
     int   *segp[IT];
 #pragma unroll
@@ -440,23 +465,24 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         const bool valid = slot < a.ni;
         const int i = valid ? a.iperm[slot] : -1;
         iidx[k] = i;
-        double v[3] = {0, 0, 0}, h2 = 0, dtr = 0;
-        xid[k][0] = xid[k][1] = xid[k][2] = 0.0;
+        double xd[3] = {0, 0, 0}, v[3] = {0, 0, 0}, h2 = 0, dtr = 0;
         if (valid) {
             h2 = a.h2[i]; dtr = a.dtr[i];
 #pragma unroll
-            for (int c = 0; c < 3; c++) { xid[k][c] = a.xi[3 * (size_t)i + c]; v[c] = a.vi[3 * (size_t)i + c]; }
+            for (int c = 0; c < 3; c++) { xd[c] = a.xi[3 * (size_t)i + c]; v[c] = a.vi[3 * (size_t)i + c]; }
         }
-        const float xh[3] = {(float)xid[k][0], (float)xid[k][1], (float)xid[k][2]};
+        const float xh[3] = {(float)xd[0], (float)xd[1], (float)xd[2]};
         const float vf[3] = {(float)v[0], (float)v[1], (float)v[2]};
         I[k].nxh = -xh[0]; I[k].nyh = -xh[1]; I[k].nzh = -xh[2];
-        I[k].nxl = -(float)(xid[k][0] - (double)xh[0]); I[k].nyl = -(float)(xid[k][1] - (double)xh[1]);
-        I[k].nzl = -(float)(xid[k][2] - (double)xh[2]);
-        islack[k] = 1.2e-7f * fmaxf(fabsf(xh[0]), fmaxf(fabsf(xh[1]), fabsf(xh[2])));
+        I[k].nxl = -(float)(xd[0] - (double)xh[0]); I[k].nyl = -(float)(xd[1] - (double)xh[1]);
+        I[k].nzl = -(float)(xd[2] - (double)xh[2]);
         I[k].nvx = -vf[0]; I[k].nvy = -vf[1]; I[k].nvz = -vf[2];
         I[k].dtr = (float)dtr;
         I[k].h2  = valid ? (float)h2 : 0.f;
-        A[k][0].clear(); A[k][1].clear();
+        I[k].slack = 1.2e-7f * fmaxf(fabsf(xh[0]), fmaxf(fabsf(xh[1]), fabsf(xh[2])));
+        I[k].rs    = sqrtf(fmaxf(I[k].h2, 0.f)) * 1.0001f;
+        I[k].adtr  = fabsf(I[k].dtr) * 1.00002f;
+        P[k].clear();
 #pragma unroll
         for (int c = 0; c < 7; c++) D[k][c] = 0.0;
         cnt[k]  = 0;
@@ -465,14 +491,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
     auto flush = [&]() {
 #pragma unroll
         for (int k = 0; k < IT; k++) {
-            D[k][0] += (double)(A[k][0].ax + A[k][1].ax);
-            D[k][1] += (double)(A[k][0].ay + A[k][1].ay);
-            D[k][2] += (double)(A[k][0].az + A[k][1].az);
-            D[k][3] += (double)(A[k][0].jx + A[k][1].jx);
-            D[k][4] += (double)(A[k][0].jy + A[k][1].jy);
-            D[k][5] += (double)(A[k][0].jz + A[k][1].jz);
-            D[k][6] += (double)(A[k][0].p + A[k][1].p);
-            A[k][0].clear(); A[k][1].clear();
+            D[k][0] += (double)(P[k].ax.x + P[k].ax.y);
+            D[k][1] += (double)(P[k].ay.x + P[k].ay.y);
+            D[k][2] += (double)(P[k].az.x + P[k].az.y);
+            D[k][3] += (double)(P[k].jx.x + P[k].jx.y);
+            D[k][4] += (double)(P[k].jy.x + P[k].jy.y);
+            D[k][5] += (double)(P[k].jz.x + P[k].jz.y);
+            D[k][6] += (double)(P[k].p.x + P[k].p.y);
+            P[k].clear();
         }
     };
 
@@ -483,24 +509,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         const uint32_t parity = (n / NSTAGE) & 1;
         mbar_wait(&bars[st], parity);
         const float *tb = buf + st * TILE_FLOATS;
-        // ---- header: classify the (warp, tile) pair -------------------------------------------------
-        const double Ox = reinterpret_cast<const double *>(tb)[0];
-        const double Oy = reinterpret_cast<const double *>(tb)[1];
-        const double Oz = reinterpret_cast<const double *>(tb)[2];
-        const float4 h1 = reinterpret_cast<const float4 *>(tb)[1];      // Oz(2 words) | hx hy   (only .z,.w used)
+        // ---- header: classify the (warp, tile) pair (branch-free, fp32 only) -------------------------
+        const float4 h0 = reinterpret_cast<const float4 *>(tb)[0];      // Oh.xyz | Ol.x
+        const float4 h1 = reinterpret_cast<const float4 *>(tb)[1];      // Ol.yz  | hx hy
         const float4 h2v = reinterpret_cast<const float4 *>(tb)[2];     // hz | vcx vcy vcz
-        const float4 h3 = reinterpret_cast<const float4 *>(tb)[3];      // hvx hvy hvz | mmax
-        // Separation (tile origin - x_i) in fp64, rounded once: |c| ~ pair distance, so c + offset keeps a
-        // relative precision of 2^-24 whatever |x| is.
-        float cf[IT][3];
+        const float4 h3 = reinterpret_cast<const float4 *>(tb)[3];      // hvx hvy hvz | sqrt(mmax)
+        // Separation (tile origin - x_i) from the two-float representations: |c| ~ pair distance, so c + offset
+        // keeps a relative precision of ~2^-23 whatever |x| is.
 #pragma unroll
         for (int k = 0; k < IT; k++) {
-            cf[k][0] = (float)(Ox - xid[k][0]); cf[k][1] = (float)(Oy - xid[k][1]); cf[k][2] = (float)(Oz - xid[k][2]);
-            I[k].cx = cf[k][0]; I[k].cy = cf[k][1]; I[k].cz = cf[k][2];
+            I[k].cx = (h0.x + I[k].nxh) + (h0.w + I[k].nxl);
+            I[k].cy = (h0.y + I[k].nyh) + (h1.x + I[k].nyl);
+            I[k].cz = (h0.z + I[k].nzh) + (h1.y + I[k].nzl);
         }
         // Per-lane test of i against the tile's boxes: FAR iff no j of the tile can satisfy the reference
-        // criterion min(|dx|^2, |dx + dtr dv|^2) < h2 [* mj], with margins that dominate every fp32 rounding
-        // (positions/velocities rounded to fp32 by the predicate, this arithmetic itself).
+        // criterion min(|dx|^2, |dx + dtr dv|^2) < h2 [* mj]:  gap(i, box) > sqrt(h2 [* mmax]) + |dtr| max|dv|,
+        // with margins that dominate every fp32 rounding (positions/velocities rounded to fp32 by the predicate,
+        // this arithmetic itself, the approximate sqrt).
         bool lane_far = true;
         {
             const float jh[3] = {h1.z, h1.w, h2v.x};
@@ -508,22 +533,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             const float jvh[3] = {h3.x, h3.y, h3.z};
 #pragma unroll
             for (int k = 0; k < IT; k++) {
-                float d2 = 0.f, dv2 = 0.f;
+                const float cf[3] = {I[k].cx, I[k].cy, I[k].cz};
+                const float nv[3] = {I[k].nvx, I[k].nvy, I[k].nvz};
+                float d2 = 0.f, dv2 = 0.f, sreach = 0.f;
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const float g = fmaxf(fabsf(cf[k][c]) - jh[c] - 2.4e-7f * (fabsf(cf[k][c]) + jh[c]) - islack[k], 0.f);
+                    const float g = fmaxf(fmaf(fabsf(cf[c]), 0.9999996f, -(jh[c] + I[k].slack)), 0.f);
                     d2 = fmaf(g, g, d2);
-                    const float u = fabsf(jvc[c] + (c == 0 ? I[k].nvx : c == 1 ? I[k].nvy : I[k].nvz)) + jvh[c];
+                    const float u = fabsf(jvc[c] + nv[c]) + jvh[c];
                     dv2 = fmaf(u, u, dv2);
+                    sreach = fmaxf(sreach, fabsf(cf[c]) + jh[c]);
                 }
-                // precision: the FAR body forms dx = c + offset in fp32 (error ~2^-24 (|c|+h)); keep that below
+                float sq; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(dv2));
+                const float rr = fmaf(I[k].adtr, sq, MFLAG ? I[k].rs * h3.w : I[k].rs);
+                // precision: the FAR body forms dx = c + offset in fp32 (error ~2^-23 (|c|+h)); keep that below
                 // ~1e-7 of the smallest separation by sending tiles closer than half their own reach NEAR
-                const float sreach = fmaxf(fabsf(cf[k][0]) + jh[0], fmaxf(fabsf(cf[k][1]) + jh[1], fabsf(cf[k][2]) + jh[2]));
-                const float d = sqrtf(d2);
-                const float reach = fabsf(I[k].dtr) * sqrtf(dv2) * 1.00001f;
-                const float lim = (MFLAG ? h3.w * I[k].h2 : I[k].h2) * 1.0001f;
-                const float dd = d - reach;
-                const bool f = (dd > 0.f) && (dd * dd > lim) && (d2 > 0.25f * sreach * sreach);
+                const bool f = (d2 > rr * rr) && (d2 > 0.25f * sreach * sreach);
                 lane_far &= (f || iidx[k] < 0);
             }
         }
@@ -531,21 +556,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         n_all++;
         const float4 *c = reinterpret_cast<const float4 *>(tb + HDR);
         if (far) {
-#pragma unroll 2
+            float2 cx2[IT], cy2[IT], cz2[IT], nvx2[IT], nvy2[IT], nvz2[IT];
+#pragma unroll
+            for (int k = 0; k < IT; k++) {
+                cx2[k] = dup2(I[k].cx); cy2[k] = dup2(I[k].cy); cz2[k] = dup2(I[k].cz);
+                nvx2[k] = dup2(I[k].nvx); nvy2[k] = dup2(I[k].nvy); nvz2[k] = dup2(I[k].nvz);
+            }
+#pragma unroll FAR_UNROLL_Q
             for (int q = 0; q < TJ / 4; q++) {
                 const float4 DX = c[C_DX * 16 + q], DY = c[C_DY * 16 + q], DZ = c[C_DZ * 16 + q];
                 const float4 VX = c[C_VX * 16 + q], VY = c[C_VY * 16 + q], VZ = c[C_VZ * 16 + q];
                 const float4 M  = c[C_M * 16 + q];
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
-                    interact_far(I[k], A[k][0], DX.x, DY.x, DZ.x, VX.x, VY.x, VZ.x, M.x);
-                    interact_far(I[k], A[k][1], DX.y, DY.y, DZ.y, VX.y, VY.y, VZ.y, M.y);
-                    interact_far(I[k], A[k][0], DX.z, DY.z, DZ.z, VX.z, VY.z, VZ.z, M.z);
-                    interact_far(I[k], A[k][1], DX.w, DY.w, DZ.w, VX.w, VY.w, VZ.w, M.w);
+                    interact_far2(cx2[k], cy2[k], cz2[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(DX.x, DX.y),
+                                  make_float2(DY.x, DY.y), make_float2(DZ.x, DZ.y), make_float2(VX.x, VX.y),
+                                  make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), make_float2(M.x, M.y));
+                    interact_far2(cx2[k], cy2[k], cz2[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(DX.z, DX.w),
+                                  make_float2(DY.z, DY.w), make_float2(DZ.z, DZ.w), make_float2(VX.z, VX.w),
+                                  make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), make_float2(M.z, M.w));
                 }
             }
         } else {
             n_near++;
+            Acc A[IT][2];
+#pragma unroll
+            for (int k = 0; k < IT; k++) {
+                A[k][0] = Acc{P[k].ax.x, P[k].ay.x, P[k].az.x, P[k].p.x, P[k].jx.x, P[k].jy.x, P[k].jz.x};
+                A[k][1] = Acc{P[k].ax.y, P[k].ay.y, P[k].az.y, P[k].p.y, P[k].jx.y, P[k].jy.y, P[k].jz.y};
+            }
 #pragma unroll 1
             for (int q = 0; q < TJ / 4; q++) {
                 const float4 VX = c[C_VX * 16 + q], VY = c[C_VY * 16 + q], VZ = c[C_VZ * 16 + q];
@@ -577,6 +616,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                         }
                     }
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < IT; k++) {
+                P[k].ax = make_float2(A[k][0].ax, A[k][1].ax); P[k].ay = make_float2(A[k][0].ay, A[k][1].ay);
+                P[k].az = make_float2(A[k][0].az, A[k][1].az); P[k].p  = make_float2(A[k][0].p,  A[k][1].p);
+                P[k].jx = make_float2(A[k][0].jx, A[k][1].jx); P[k].jy = make_float2(A[k][0].jy, A[k][1].jy);
+                P[k].jz = make_float2(A[k][0].jz, A[k][1].jz);
             }
         }
         __syncwarp();                                  // every lane is done reading stage st
@@ -757,8 +803,9 @@ __global__ void __launch_bounds__(128) pot_kernel(const float *__restrict__ tile
             b[HDR + 3 * TJ + jj] = tp[HDR + C_M * TJ + jj];
         }
         __syncwarp();
-        const double *od = reinterpret_cast<const double *>(b);
-        const float cx = (float)(od[0] - xd), cy = (float)(od[1] - yd), cz = (float)(od[2] - zd);
+        // origin = Oh + Ol exactly (tilepack takes the offsets from this sum): one rounding of the exact separation
+        const float cx = (float)(((double)b[0] + (double)b[3]) - xd), cy = (float)(((double)b[1] + (double)b[4]) - yd),
+                    cz = (float)(((double)b[2] + (double)b[5]) - zd);
         const float4 *c = reinterpret_cast<const float4 *>(b + HDR);
         float acc = 0.f;
 #pragma unroll 4
@@ -803,9 +850,11 @@ const Variant VARIANTS[] = {
     {"it2b3", 2, {regf_kernel<2, false, 3>, regf_kernel<2, true, 3>}},
     {"it1",   1, {regf_kernel<1, false, 1>, regf_kernel<1, true, 1>}},
     {"it1b5", 1, {regf_kernel<1, false, 5>, regf_kernel<1, true, 5>}},
+    {"it1b4", 1, {regf_kernel<1, false, 4>, regf_kernel<1, true, 4>}},
+    {"it1b3", 1, {regf_kernel<1, false, 3>, regf_kernel<1, true, 3>}},
 };
 constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
-constexpr int DEFAULT_VARIANT = 2;     // it1: best at small ni, equal at ni=1024 (profiles/r01b_variants.txt)
+constexpr int DEFAULT_VARIANT = 4;     // it1b4: 4 CTAs/SM (<= 128 registers), fastest at every ni (profiles/r01e_variants.txt)
 constexpr int ROWS_LMAX_CAP = 1024;    // row stride capacity of the IPC-exported shard rows (NCCL mode)
 
 struct Dev {

@@ -1,0 +1,296 @@
+// farbody_exp.cu -- standalone tuning experiments for the FAR pair body of regf_kernel (not part of the library).
+// Build:  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o build/farbody_exp scripts/exp/farbody_exp.cu
+// Run on the GPU box:  build/farbody_exp
+// Prints lane-instruction rates of FP32 instruction mixes and Gint/s of far-body code shapes, so that the shape
+// used in the product kernel is chosen from measurements (results are copied to profiles/).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s line %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// instruction-mix kernels: NCH independent chains, three distinct register operands per instruction
+// ------------------------------------------------------------------------------------------------
+constexpr int NCH = 24;
+template <int MODE>
+__global__ void __launch_bounds__(256) mix_kernel(int iters, float seed, float *out)
+{
+    float a[NCH], b[NCH], c[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; k++) { a[k] = seed + k + threadIdx.x; b[k] = seed * 0.25f + 1e-3f * k; c[k] = 1e-4f * (k + 1 + threadIdx.x); }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < NCH; k++) {
+            if (MODE == 0) a[k] = fmaf(b[k], c[k], a[k]);
+            if (MODE == 1) a[k] = a[k] * b[k];
+            if (MODE == 2) a[k] = a[k] + b[k];
+            if (MODE == 3) { if (k & 1) a[k] = fmaf(b[k], c[k], a[k]); else a[k] = a[k] * b[k]; }
+            if (MODE == 4) { if (k & 1) a[k] = fmaf(b[k], c[k], a[k]); else a[k] = a[k] + b[k]; }
+            if (MODE == 5) { if (k & 1) a[k] = a[k] * c[k]; else a[k] = a[k] + b[k]; }
+            if (MODE == 6) { if (k % 3 == 0) a[k] = a[k] * b[k]; else a[k] = fmaf(b[k], c[k], a[k]); }
+            if (MODE == 7) { if ((k & 3) == 0) a[k] = a[k] + b[k]; else if ((k & 3) == 1) a[k] = a[k] * b[k]; else a[k] = fmaf(b[k], c[k], a[k]); }
+            if (MODE == 8) { if (k & 1) a[k] = fmaf(b[k], c[k], a[k]); else a[k] = a[k] * -3.f; }          // FMUL with immediate
+            if (MODE == 9) { if (k & 1) a[k] = fmaf(a[k], a[k], b[k]); else a[k] = fmaf(b[k], c[k], a[k]); } // squares
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; k++) s += a[k] + b[k] + c[k];
+    if (s == 12345.678f) out[0] = s;
+}
+
+template <int MODE> void run_mix(const char *name, int nsm)
+{
+    float *out; CK(cudaMalloc(&out, 4));
+    const int iters = 8192, blocks = nsm * 8;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 4; r++) {
+        cudaEventRecord(e0);
+        mix_kernel<MODE><<<blocks, 256>>>(iters, 1.0001f, out);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    const double ops = (double)blocks * 256 * iters * NCH;
+    printf("mix %-34s %7.2f T lane-instr/s  (%.1f %% of 128 lanes x SMs x 1965 MHz)\n", name, ops / (best * 1e-3) * 1e-12,
+           100.0 * ops / (best * 1e-3) / (128.0 * nsm * 1.965e9));
+    cudaFree(out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// far-body shapes
+// ------------------------------------------------------------------------------------------------
+struct FAcc { float ax, ay, az, p, jx, jy, jz; };
+
+// SHAPE 0: product body.  1: FMUL -> FFMA(x,y,zero).  2: FADD -> FFMA(x,one,y).  3: both.
+template <int SHAPE>
+__device__ __forceinline__ void far1(FAcc &A, float cx, float cy, float cz, float nvx, float nvy, float nvz,
+                                     float DX, float DY, float DZ, float VX, float VY, float VZ, float M, float zero, float one)
+{
+    auto MUL = [&](float x, float y) { return (SHAPE & 1) ? fmaf(x, y, zero) : x * y; };
+    auto ADD = [&](float x, float y) { return (SHAPE & 2) ? fmaf(x, one, y) : x + y; };
+    const float dx = ADD(DX, cx), dy = ADD(DY, cy), dz = ADD(DZ, cz);
+    const float dvx = ADD(VX, nvx), dvy = ADD(VY, nvy), dvz = ADD(VZ, nvz);
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, MUL(dx, dx)));
+    const float rv = fmaf(dz, dvz, fmaf(dy, dvy, MUL(dx, dvx)));
+    float rinv; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));
+    const float rinv2 = MUL(rinv, rinv), mrinv = MUL(M, rinv), mrinv3 = MUL(mrinv, rinv2), rv3 = MUL(rv, MUL(rinv2, -3.f));
+    A.p = ADD(A.p, mrinv);
+    A.ax = fmaf(mrinv3, dx, A.ax); A.ay = fmaf(mrinv3, dy, A.ay); A.az = fmaf(mrinv3, dz, A.az);
+    A.jx = fmaf(mrinv3, fmaf(rv3, dx, dvx), A.jx);
+    A.jy = fmaf(mrinv3, fmaf(rv3, dy, dvy), A.jy);
+    A.jz = fmaf(mrinv3, fmaf(rv3, dz, dvz), A.jz);
+}
+
+// SHAPE 4: potential folded into an FFMA (p = fma(M, rinv, p)), -3 folded into the flush:
+//          jerk kept as two sums  JA += mrinv3*dv ,  JB += (mrinv3*rv*rinv2)*dx   (j = JA - 3 JB): 26 ops, all but 5 are FFMA
+struct FAcc2 { float ax, ay, az, p, jx, jy, jz, bx, by, bz; };
+__device__ __forceinline__ void far2(FAcc2 &A, float cx, float cy, float cz, float nvx, float nvy, float nvz,
+                                     float DX, float DY, float DZ, float VX, float VY, float VZ, float M)
+{
+    const float dx = DX + cx, dy = DY + cy, dz = DZ + cz;
+    const float dvx = VX + nvx, dvy = VY + nvy, dvz = VZ + nvz;
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float rv = fmaf(dz, dvz, fmaf(dy, dvy, dx * dvx));
+    float rinv; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));
+    const float rinv2 = rinv * rinv, mrinv = M * rinv, mrinv3 = mrinv * rinv2, w = mrinv3 * (rv * rinv2);
+    A.p += mrinv;
+    A.ax = fmaf(mrinv3, dx, A.ax); A.ay = fmaf(mrinv3, dy, A.ay); A.az = fmaf(mrinv3, dz, A.az);
+    A.jx = fmaf(mrinv3, dvx, A.jx); A.jy = fmaf(mrinv3, dvy, A.jy); A.jz = fmaf(mrinv3, dvz, A.jz);
+    A.bx = fmaf(w, dx, A.bx); A.by = fmaf(w, dy, A.by); A.bz = fmaf(w, dz, A.bz);
+}
+
+template <int SHAPE, int UNROLL, int NACC>
+__global__ void __launch_bounds__(128) far_kernel(int ntile_iters, float seed, float zero, float one, float *out)
+{
+    __shared__ __align__(16) float tile[4][7 * 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *tb = tile[warp];
+    for (int k = lane; k < 7 * 64; k += 32) tb[k] = seed * (1.f + 0.001f * k) + 0.01f * warp;
+    __syncwarp();
+    FAcc A[NACC];
+    FAcc2 B[2];
+#pragma unroll
+    for (int k = 0; k < NACC; k++) A[k] = FAcc{0, 0, 0, 0, 0, 0, 0};
+    B[0] = FAcc2{0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; B[1] = B[0];
+    float cx = seed + lane, cy = seed - lane, cz = 0.5f * seed, nvx = 0.1f * lane, nvy = -0.2f * lane, nvz = 0.3f;
+    const float4 *c = reinterpret_cast<const float4 *>(tb);
+    for (int t = 0; t < ntile_iters; t++) {
+#pragma unroll UNROLL
+        for (int q = 0; q < 16; q++) {
+            const float4 DX = c[q], DY = c[16 + q], DZ = c[32 + q], VX = c[48 + q], VY = c[64 + q], VZ = c[80 + q], M = c[96 + q];
+            if (SHAPE == 4) {
+                far2(B[0], cx, cy, cz, nvx, nvy, nvz, DX.x, DY.x, DZ.x, VX.x, VY.x, VZ.x, M.x);
+                far2(B[1], cx, cy, cz, nvx, nvy, nvz, DX.y, DY.y, DZ.y, VX.y, VY.y, VZ.y, M.y);
+                far2(B[0], cx, cy, cz, nvx, nvy, nvz, DX.z, DY.z, DZ.z, VX.z, VY.z, VZ.z, M.z);
+                far2(B[1], cx, cy, cz, nvx, nvy, nvz, DX.w, DY.w, DZ.w, VX.w, VY.w, VZ.w, M.w);
+            } else {
+                far1<SHAPE>(A[0 % NACC], cx, cy, cz, nvx, nvy, nvz, DX.x, DY.x, DZ.x, VX.x, VY.x, VZ.x, M.x, zero, one);
+                far1<SHAPE>(A[1 % NACC], cx, cy, cz, nvx, nvy, nvz, DX.y, DY.y, DZ.y, VX.y, VY.y, VZ.y, M.y, zero, one);
+                far1<SHAPE>(A[2 % NACC], cx, cy, cz, nvx, nvy, nvz, DX.z, DY.z, DZ.z, VX.z, VY.z, VZ.z, M.z, zero, one);
+                far1<SHAPE>(A[3 % NACC], cx, cy, cz, nvx, nvy, nvz, DX.w, DY.w, DZ.w, VX.w, VY.w, VZ.w, M.w, zero, one);
+            }
+        }
+        cx += 1e-3f;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < NACC; h++) s += A[h].ax + A[h].ay + A[h].az + A[h].p + A[h].jx + A[h].jy + A[h].jz;
+    for (int h = 0; h < 2; h++) s += B[h].ax + B[h].ay + B[h].az + B[h].p + B[h].jx + B[h].jy + B[h].jz + B[h].bx + B[h].by + B[h].bz;
+    if (s == 12345.678f) out[0] = s;
+}
+
+template <int SHAPE, int UNROLL, int NACC> void run_far(const char *name, int nsm, int ctas)
+{
+    float *out; CK(cudaMalloc(&out, 4));
+    const int iters = 2000, blocks = nsm * ctas;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 4; r++) {
+        cudaEventRecord(e0);
+        far_kernel<SHAPE, UNROLL, NACC><<<blocks, 128>>>(iters, 1.0001f, 0.f, 1.f, out);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    const double pairs = (double)blocks * 128 * iters * 64;
+    printf("far %-44s %d CTAs/SM: %7.1f Gint/s\n", name, ctas, pairs / (best * 1e-3) * 1e-9);
+    cudaFree(out);
+}
+
+// SHAPE 5: packed f32x2 over j (two j per instruction; LDS.128 quads give aligned pairs (x,y) and (z,w)).
+struct PAcc { float2 ax, ay, az, p, jx, jy, jz; };
+__device__ __forceinline__ void far_packed(PAcc &A, float2 cx, float2 cy, float2 cz, float2 nvx, float2 nvy, float2 nvz,
+                                           float2 DX, float2 DY, float2 DZ, float2 VX, float2 VY, float2 VZ, float2 M)
+{
+    const float2 dx = __fadd2_rn(DX, cx), dy = __fadd2_rn(DY, cy), dz = __fadd2_rn(DZ, cz);
+    const float2 dvx = __fadd2_rn(VX, nvx), dvy = __fadd2_rn(VY, nvy), dvz = __fadd2_rn(VZ, nvz);
+    const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+    const float2 rv = __ffma2_rn(dz, dvz, __ffma2_rn(dy, dvy, __fmul2_rn(dx, dvx)));
+    float2 rinv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.x) : "f"(r2.x));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.y) : "f"(r2.y));
+    const float2 rinv2 = __fmul2_rn(rinv, rinv), mrinv = __fmul2_rn(M, rinv), mrinv3 = __fmul2_rn(mrinv, rinv2);
+    const float2 rv3 = __fmul2_rn(rv, __fmul2_rn(rinv2, make_float2(-3.f, -3.f)));
+    A.p = __fadd2_rn(A.p, mrinv);
+    A.ax = __ffma2_rn(mrinv3, dx, A.ax); A.ay = __ffma2_rn(mrinv3, dy, A.ay); A.az = __ffma2_rn(mrinv3, dz, A.az);
+    const float2 ix = __ffma2_rn(rv3, dx, dvx), iy = __ffma2_rn(rv3, dy, dvy), iz = __ffma2_rn(rv3, dz, dvz);
+    A.jx = __ffma2_rn(mrinv3, ix, A.jx); A.jy = __ffma2_rn(mrinv3, iy, A.jy); A.jz = __ffma2_rn(mrinv3, iz, A.jz);
+}
+
+// SHAPE 6: mixed -- packed for the <= 2-operand ops, scalar for the accumulating FFMAs
+__device__ __forceinline__ void far_mixed(FAcc &A0, FAcc &A1, float2 cx, float2 cy, float2 cz, float2 nvx, float2 nvy, float2 nvz,
+                                          float2 DX, float2 DY, float2 DZ, float2 VX, float2 VY, float2 VZ, float2 M)
+{
+    const float2 dx = __fadd2_rn(DX, cx), dy = __fadd2_rn(DY, cy), dz = __fadd2_rn(DZ, cz);
+    const float2 dvx = __fadd2_rn(VX, nvx), dvy = __fadd2_rn(VY, nvy), dvz = __fadd2_rn(VZ, nvz);
+    const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+    float2 rv = __fmul2_rn(dx, dvx);
+    rv.x = fmaf(dy.x, dvy.x, rv.x); rv.y = fmaf(dy.y, dvy.y, rv.y);
+    rv.x = fmaf(dz.x, dvz.x, rv.x); rv.y = fmaf(dz.y, dvz.y, rv.y);
+    float2 rinv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.x) : "f"(r2.x));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.y) : "f"(r2.y));
+    const float2 rinv2 = __fmul2_rn(rinv, rinv), mrinv = __fmul2_rn(M, rinv), mrinv3 = __fmul2_rn(mrinv, rinv2);
+    const float2 rv3 = __fmul2_rn(rv, __fmul2_rn(rinv2, make_float2(-3.f, -3.f)));
+    A0.p += mrinv.x; A1.p += mrinv.y;
+    A0.ax = fmaf(mrinv3.x, dx.x, A0.ax); A0.ay = fmaf(mrinv3.x, dy.x, A0.ay); A0.az = fmaf(mrinv3.x, dz.x, A0.az);
+    A1.ax = fmaf(mrinv3.y, dx.y, A1.ax); A1.ay = fmaf(mrinv3.y, dy.y, A1.ay); A1.az = fmaf(mrinv3.y, dz.y, A1.az);
+    A0.jx = fmaf(mrinv3.x, fmaf(rv3.x, dx.x, dvx.x), A0.jx); A0.jy = fmaf(mrinv3.x, fmaf(rv3.x, dy.x, dvy.x), A0.jy);
+    A0.jz = fmaf(mrinv3.x, fmaf(rv3.x, dz.x, dvz.x), A0.jz);
+    A1.jx = fmaf(mrinv3.y, fmaf(rv3.y, dx.y, dvx.y), A1.jx); A1.jy = fmaf(mrinv3.y, fmaf(rv3.y, dy.y, dvy.y), A1.jy);
+    A1.jz = fmaf(mrinv3.y, fmaf(rv3.y, dz.y, dvz.y), A1.jz);
+}
+
+template <int SHAPE, int UNROLL>
+__global__ void __launch_bounds__(128) farp_kernel(int ntile_iters, float seed, float *out)
+{
+    __shared__ __align__(16) float tile[4][7 * 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *tb = tile[warp];
+    for (int k = lane; k < 7 * 64; k += 32) tb[k] = seed * (1.f + 0.001f * k) + 0.01f * warp;
+    __syncwarp();
+    PAcc P[2];
+    FAcc A[2];
+    for (int h = 0; h < 2; h++) { P[h] = PAcc{{0,0},{0,0},{0,0},{0,0},{0,0},{0,0},{0,0}}; A[h] = FAcc{0,0,0,0,0,0,0}; }
+    float cxs = seed + lane, cys = seed - lane, czs = 0.5f * seed;
+    const float2 nvx = make_float2(0.1f * lane, 0.1f * lane), nvy = make_float2(-0.2f * lane, -0.2f * lane), nvz = make_float2(0.3f, 0.3f);
+    const float4 *c = reinterpret_cast<const float4 *>(tb);
+    for (int t = 0; t < ntile_iters; t++) {
+        const float2 cx = make_float2(cxs, cxs), cy = make_float2(cys, cys), cz = make_float2(czs, czs);
+#pragma unroll UNROLL
+        for (int q = 0; q < 16; q++) {
+            const float4 DX = c[q], DY = c[16 + q], DZ = c[32 + q], VX = c[48 + q], VY = c[64 + q], VZ = c[80 + q], M = c[96 + q];
+#define LO(v) make_float2(v.x, v.y)
+#define HI(v) make_float2(v.z, v.w)
+            if (SHAPE == 5) {
+                far_packed(P[0], cx, cy, cz, nvx, nvy, nvz, LO(DX), LO(DY), LO(DZ), LO(VX), LO(VY), LO(VZ), LO(M));
+                far_packed(P[1], cx, cy, cz, nvx, nvy, nvz, HI(DX), HI(DY), HI(DZ), HI(VX), HI(VY), HI(VZ), HI(M));
+            } else {
+                far_mixed(A[0], A[1], cx, cy, cz, nvx, nvy, nvz, LO(DX), LO(DY), LO(DZ), LO(VX), LO(VY), LO(VZ), LO(M));
+                far_mixed(A[0], A[1], cx, cy, cz, nvx, nvy, nvz, HI(DX), HI(DY), HI(DZ), HI(VX), HI(VY), HI(VZ), HI(M));
+            }
+        }
+        cxs += 1e-3f;
+    }
+    float s = 0.f;
+    for (int h = 0; h < 2; h++) {
+        s += A[h].ax + A[h].ay + A[h].az + A[h].p + A[h].jx + A[h].jy + A[h].jz;
+        s += P[h].ax.x + P[h].ay.x + P[h].az.x + P[h].p.x + P[h].jx.x + P[h].jy.x + P[h].jz.x;
+        s += P[h].ax.y + P[h].ay.y + P[h].az.y + P[h].p.y + P[h].jx.y + P[h].jy.y + P[h].jz.y;
+    }
+    if (s == 12345.678f) out[0] = s;
+}
+
+template <int SHAPE, int UNROLL> void run_farp(const char *name, int nsm, int ctas)
+{
+    float *out; CK(cudaMalloc(&out, 4));
+    const int iters = 2000, blocks = nsm * ctas;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 4; r++) {
+        cudaEventRecord(e0);
+        farp_kernel<SHAPE, UNROLL><<<blocks, 128>>>(iters, 1.0001f, out);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    const double pairs = (double)blocks * 128 * iters * 64;
+    printf("far %-44s %d CTAs/SM: %7.1f Gint/s\n", name, ctas, pairs / (best * 1e-3) * 1e-9);
+    cudaFree(out);
+}
+
+int main()
+{
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    const int nsm = prop.multiProcessorCount;
+    printf("%s, %d SMs\n", prop.name, nsm);
+    run_mix<0>("FFMA", nsm); run_mix<1>("FMUL", nsm); run_mix<2>("FADD", nsm);
+    run_mix<3>("FMUL,FFMA alternating", nsm); run_mix<4>("FADD,FFMA alternating", nsm); run_mix<5>("FADD,FMUL alternating", nsm);
+    run_mix<6>("FMUL,FFMA,FFMA", nsm); run_mix<7>("FADD,FMUL,FFMA,FFMA", nsm); run_mix<8>("FMUL imm,FFMA alternating", nsm);
+    run_mix<9>("FFMA square,FFMA alternating", nsm);
+    for (int ctas = 3; ctas <= 4; ctas++) {
+        run_far<0, 2, 2>("product body, unroll 2 quads, 2 chains", nsm, ctas);
+        run_far<0, 1, 2>("product body, unroll 1 quad, 2 chains", nsm, ctas);
+        run_far<0, 4, 2>("product body, unroll 4 quads, 2 chains", nsm, ctas);
+        run_far<0, 2, 4>("product body, unroll 2, 4 chains", nsm, ctas);
+        run_far<0, 2, 1>("product body, unroll 2, 1 chain", nsm, ctas);
+        run_far<1, 2, 2>("FMUL->FFMA, unroll 2", nsm, ctas);
+        run_far<2, 2, 2>("FADD->FFMA, unroll 2", nsm, ctas);
+        run_far<3, 2, 2>("all FFMA, unroll 2", nsm, ctas);
+        run_far<4, 2, 2>("split jerk sums (26 ops), unroll 2", nsm, ctas);
+    }
+    for (int ctas = 2; ctas <= 4; ctas++) {
+        run_farp<5, 1>("packed f32x2 over j, unroll 1 quad", nsm, ctas);
+        run_farp<5, 2>("packed f32x2 over j, unroll 2 quads", nsm, ctas);
+        run_farp<5, 4>("packed f32x2 over j, unroll 4 quads", nsm, ctas);
+        run_farp<6, 1>("mixed packed/scalar, unroll 1 quad", nsm, ctas);
+        run_farp<6, 2>("mixed packed/scalar, unroll 2 quads", nsm, ctas);
+    }
+    return 0;
+}
