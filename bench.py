@@ -136,12 +136,13 @@ def load_reference_avx():
 def time_reference(ref, m, x, v, h2, dtr, blocks, m_flag, first_block=0):
     """One bounded sample: send + `blocks` regf calls of 1024 on the AVX library.  Returns (s, interactions)."""
     n = m.shape[0]
+    out = ref.caller_arrays(BLOCK, LMAX)          # caller-owned arrays allocated once, as for the b200 arm
     t0 = time.perf_counter()
     ref.send(m, x, v)
     inter = 0
     for b in range(blocks):
-        i0 = ((first_block + b) * BLOCK) % max(n - BLOCK, 1)
-        ref.regf(h2[i0:i0 + BLOCK], dtr[i0:i0 + BLOCK], x[i0:i0 + BLOCK], v[i0:i0 + BLOCK], LMAX, NNBMAX, m_flag)
+        i0 = ((first_block + b) * BLOCK) % max(n - BLOCK - 8, 1)      # the AVX library reads 3 rows past ni
+        ref.regf_into(out, h2[i0:i0 + BLOCK], dtr[i0:i0 + BLOCK], x[i0:i0 + BLOCK], v[i0:i0 + BLOCK], LMAX, NNBMAX, m_flag)
         inter += BLOCK * n
     return time.perf_counter() - t0, inter
 
@@ -275,12 +276,14 @@ def main():
     int_per_launch = float(BLOCK) * n * interactions_scale
 
     # ---------------- end-to-end leg through the C-ABI with host buffers: `e2e` ----------------
+    out_arrays = lib.caller_arrays(BLOCK, LMAX)      # caller-owned, allocated once (the Fortran caller's static arrays)
+
     def abi_step():
         lib.send(m, x, v)
         nnb_sum = 0
         for i0 in range(0, ni_total, BLOCK):
             i1 = min(i0 + BLOCK, ni_total)
-            acc, jrk, pot, lst = lib.regf(h2[i0:i1], dtr[i0:i1], x[i0:i1], v[i0:i1], LMAX, NNBMAX, args.m_flag, pad=0)
+            acc, jrk, pot, lst = lib.regf_into(out_arrays, h2[i0:i1], dtr[i0:i1], x[i0:i1], v[i0:i1], LMAX, NNBMAX, args.m_flag)
             nnb_sum += int(lst[:, 0].sum())
         return nnb_sum
 
@@ -346,7 +349,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": c_e2e["h2d_bytes"] / e2e_steps,
                 "d2h_bytes_per_step": c_e2e["d2h_bytes"] / e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
-                "api": "gpunb_send_ + gpunb_regf_ (ctypes, pageable host buffers)"},
+                "api": "gpunb_send_ + gpunb_regf_ (ctypes, pageable caller-owned host arrays)"},
         "gpu_launches": int(launches_res),
         "roofline": roofline,
     }

@@ -133,6 +133,27 @@ class ForceLib:
                              lst.ctypes.data_as(_c_int_p), C.byref(C.c_int(m_flag)))
         return acc[:ni], jrk[:ni], pot[:ni], lst[:ni]
 
+    def caller_arrays(self, nimax: int, lmax: int, pad: int = 8):
+        """Caller-owned output arrays, allocated ONCE like the Fortran caller's static GPUACC/GPUJRK/GPUPHI/LISTGP
+        (util_gpu.F:14, fpoly0.F:11): (acc[n,3], jrk[n,3], pot[n], list[n,lmax]) with n = nimax + pad."""
+        n = nimax + pad
+        return (np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(n), np.zeros((n, lmax), dtype=np.int32))
+
+    def regf_into(self, out, h2, dtr, xi, vi, lmax: int, nnbmax: int, m_flag: int = 0):
+        """gpunb_regf_ on caller-owned arrays (see caller_arrays); inputs must be C-contiguous float64 and, for the
+        reference AVX library, followed by >= 3 readable rows (slices of larger arrays are).  Returns views [:ni]."""
+        acc, jrk, pot, lst = out
+        ni = h2.shape[0]
+        if lst.shape[1] != lmax or acc.shape[0] < ni:
+            raise ValueError("caller arrays do not match ni/lmax")
+        for a in (h2, dtr, xi, vi):
+            if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("regf_into needs C-contiguous float64 inputs")
+        self.lib.gpunb_regf_(C.byref(C.c_int(ni)), _dp(h2), _dp(dtr), _dp(xi), _dp(vi), _dp(acc), _dp(jrk), _dp(pot),
+                             C.byref(C.c_int(lmax)), C.byref(C.c_int(nnbmax)),
+                             lst.ctypes.data_as(_c_int_p), C.byref(C.c_int(m_flag)))
+        return acc[:ni], jrk[:ni], pot[:ni], lst[:ni]
+
     def profile(self, irank: int = 0):
         self.lib.gpunb_profile_(C.byref(C.c_int(irank)))
 

@@ -4,9 +4,11 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 from nbody6ppgpu_b200 import load, snapshots as S
-lib = load(); lib.devinit(0)
-n = 1000000
-m, x, v = S.plummer(n, 1, "kroupa"); h2, dtr = S.radii_nnb(x, m, 200.0)
+from nbody6ppgpu_b200.gpunb import ForceLib
+lib = ForceLib(os.environ["GPUNB_PROBE_LIB"]) if os.environ.get("GPUNB_PROBE_LIB") else load()
+lib.devinit(0)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+m, x, v = S.plummer(n, 1, "kroupa"); h2, dtr = S.radii_nnb(x, m, 200.0 * n / 1e6)
 lib.open(n + 10, 0); lib.send(m, x, v)
 for b in range(3):
     lib.regf(h2[b*1024:(b+1)*1024], dtr[b*1024:(b+1)*1024], x[b*1024:(b+1)*1024], v[b*1024:(b+1)*1024], 600, 550, 0)
