@@ -71,6 +71,12 @@ enum {
     GPUNB_B200_CTR_POT_MS,          /* sum of gpupot kernel durations, ms                     */
     GPUNB_B200_CTR_NEAR_TILES,      /* (warp, j-tile) visits that ran the full NEAR body (GPUNB_B200_STATS=1) */
     GPUNB_B200_CTR_ALL_TILES,       /* all (warp, j-tile) visits (GPUNB_B200_STATS=1)          */
+    /* per-kernel device timeline of resident sweeps (GPUNB_B200_TIMELINE=1: CUDA events around every kernel) */
+    GPUNB_B200_CTR_TL_BLOCKS,       /* i-blocks timed                                          */
+    GPUNB_B200_CTR_TL_ISORT_MS,     /* isort_kernel                                            */
+    GPUNB_B200_CTR_TL_REGF_MS,      /* regf_kernel                                             */
+    GPUNB_B200_CTR_TL_MERGE_MS,     /* merge_kernel                                            */
+    GPUNB_B200_CTR_TL_EXCH_MS,      /* signal_kernel + combine_kernel (multi-GPU; includes waiting for the slowest shard) */
     GPUNB_B200_CTR_COUNT
 };
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);

@@ -211,14 +211,15 @@ __global__ void mortonkey_kernel(int n, const double *__restrict__ x, const unsi
 // One warp per tile: gathers its 64 particles through the sort permutation, finds the bounding boxes,
 // writes header + arrays.  Ghost slots of the last tile replicate the tile's first particle with mass 0
 // and index -1 (never listed, no force).  v may be NULL (gpupot tiles).
-__global__ void __launch_bounds__(128) tilepack_kernel(int n, int ntiles, int joff, const double *__restrict__ m,
+__global__ void __launch_bounds__(128) tilepack_kernel(int n, int t0, int tstride, int nloc, const double *__restrict__ m,
                                                         const double *__restrict__ x, const double *__restrict__ v,
                                                         const int *__restrict__ perm, float *__restrict__ tiles,
                                                         int *__restrict__ jidx)
-{
+{   // packs tiles t = t0 + l * tstride (l < nloc) of the sorted order into tiles[l], jidx[l * TJ ..]
     const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (t >= ntiles) return;
+    const int l = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (l >= nloc) return;
+    const int t = t0 + l * tstride;
     double px[2][3], mn[3], mx[3];
     float pv[2][3], pm[2], vmn[3], vmx[3], mmax = 0.f;
 #pragma unroll
@@ -237,9 +238,9 @@ __global__ void __launch_bounds__(128) tilepack_kernel(int n, int ntiles, int jo
         }
         pm[h] = real ? (float)m[src] : 0.f;
         mmax = fmaxf(mmax, pm[h]);
-        jidx[p] = real ? joff + src : -1;
+        jidx[l * TJ + h * 32 + lane] = real ? src : -1;
     }
-    float *tb = tiles + (size_t)t * TILE_FLOATS;
+    float *tb = tiles + (size_t)l * TILE_FLOATS;
     double O[3];
     float Oh[3], Ol[3];
 #pragma unroll
@@ -280,34 +281,64 @@ __global__ void __launch_bounds__(128) tilepack_kernel(int n, int ntiles, int jo
 }
 
 // ---------------------------------------------------------------------------------------------
-// isort_kernel: Morton order of the i-block (one CTA, bitonic sort of <= 2048 keys in shared memory).
+// isort_kernel: Morton order of the i-block, so that the 32 i-particles of a warp are close in space (fewer
+// NEAR tiles per warp when the block is spatially correlated).  One CTA; every thread keeps its one or two
+// composite keys (30-bit Morton code << 11 | index) in registers; bitonic strides < 32 are warp shuffles, larger
+// strides go through shared memory.  ~6 us for 1024 particles (the 63-bit Hilbert version took 23 us).
 // ---------------------------------------------------------------------------------------------
+__global__ void iota_kernel(int n, int *__restrict__ p) { const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k < n) p[k] = k; }
+__device__ __forceinline__ unsigned spread10(unsigned v)
+{   // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8))  & 0x0300f00fu;
+    v = (v | (v << 4))  & 0x030c30c3u;
+    v = (v | (v << 2))  & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ unsigned long long isort_key(const double *__restrict__ xi, int k, int ni, float sc)
+{
+    if (k >= ni) return ~0ull;
+    unsigned q[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) q[c] = (unsigned)fminf(fmaxf(fmaf((float)xi[3 * (size_t)k + c], sc, 512.f), 0.f), 1023.f);
+    const unsigned mkey = (spread10(q[0]) << 2) | (spread10(q[1]) << 1) | spread10(q[2]);
+    return ((unsigned long long)mkey << 11) | (unsigned)k;
+}
+__device__ __forceinline__ unsigned long long bitonic_pick(unsigned long long v, unsigned long long o, int e, int size, int stride)
+{
+    const bool up = (e & size) == 0, lower = (e & stride) == 0;
+    return (lower == up) ? (v < o ? v : o) : (v < o ? o : v);
+}
 __global__ void __launch_bounds__(1024) isort_kernel(int ni, const double *__restrict__ xi, const unsigned *__restrict__ hbits,
                                                       int *__restrict__ iperm)
 {
     __shared__ unsigned long long key[NIMAX];
-    __shared__ int idx[NIMAX];
-    const float H = fmaxf(__uint_as_float(*hbits), 1e-30f);
+    const int t = threadIdx.x;
+    const float sc = 511.5f / fmaxf(__uint_as_float(*hbits), 1e-30f);
     int n2 = 64;
     while (n2 < ni) n2 <<= 1;
-    for (int k = threadIdx.x; k < n2; k += blockDim.x) {
-        key[k] = k < ni ? morton_key(xi[3 * (size_t)k], xi[3 * (size_t)k + 1], xi[3 * (size_t)k + 2], H) : ~0ull;
-        idx[k] = k;
-    }
-    __syncthreads();
+    const bool two = n2 > 1024;                        // second element of this thread: t + 1024
+    unsigned long long v0 = isort_key(xi, t, ni, sc), v1 = two ? isort_key(xi, t + 1024, ni, sc) : ~0ull;
     for (int size = 2; size <= n2; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int k = threadIdx.x; k < (n2 >> 1); k += blockDim.x) {
-                const int lo = 2 * k - (k & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const unsigned long long a = key[lo], b = key[hi];
-                if ((a > b) == up) { key[lo] = b; key[hi] = a; const int q = idx[lo]; idx[lo] = idx[hi]; idx[hi] = q; }
+            if (stride >= 32) {
+                key[t] = v0; if (two) key[t + 1024] = v1;
+                __syncthreads();
+                const unsigned long long o0 = key[(t ^ stride) & (NIMAX - 1)];
+                const unsigned long long o1 = two ? key[((t + 1024) ^ stride) & (NIMAX - 1)] : ~0ull;
+                __syncthreads();
+                if (t < n2) v0 = bitonic_pick(v0, o0, t, size, stride);
+                if (two) v1 = bitonic_pick(v1, o1, t + 1024, size, stride);
+            } else {
+                const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, v0, stride);
+                v0 = bitonic_pick(v0, o0, t, size, stride);
+                if (two) { const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, v1, stride); v1 = bitonic_pick(v1, o1, t + 1024, size, stride); }
             }
-            __syncthreads();
         }
     }
-    for (int k = threadIdx.x; k < ni; k += blockDim.x) iperm[k] = idx[k];
+    if (t < ni) iperm[t] = (int)(v0 & 2047ull);
+    if (two && t + 1024 < ni) iperm[t + 1024] = (int)(v1 & 2047ull);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -648,6 +679,75 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-wide ascending sort of `total` ints held in shared memory sb[0..n2) (n2 = power of two >= 32,
+// entries >= total set to INT_MAX by the caller).  Up to 512 elements are sorted in REGISTERS (element
+// e = lane + 32 k lives in v[k] of lane): bitonic strides < 32 are warp shuffles, larger strides are
+// register swaps -- no shared-memory round trips or warp barriers inside the network.  Larger rows fall
+// back to the shared-memory network.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void warp_bitonic_regs(int *sb, int lane)
+{
+    int v[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = sb[lane + 32 * k];
+#pragma unroll
+    for (int size = 2; size <= 32 * K; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int ks = stride >> 5;
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    if ((k & ks) == 0) {
+                        const bool up = (((lane + 32 * k) & size) == 0);
+                        const int x = v[k], y = v[k | ks];
+                        const bool sw = (x > y) == up;
+                        v[k] = sw ? y : x; v[k | ks] = sw ? x : y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const int o = __shfl_xor_sync(0xffffffffu, v[k], stride);
+                    const bool up = (((lane + 32 * k) & size) == 0);
+                    const bool lower = (lane & stride) == 0;
+                    v[k] = (lower == up) ? min(v[k], o) : max(v[k], o);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) sb[lane + 32 * k] = v[k];
+}
+
+__device__ __noinline__ void warp_sort_smem(int *sb, int n2, int lane)
+{
+    __syncwarp();
+    switch (n2) {
+        case 32:  warp_bitonic_regs<1>(sb, lane); break;
+        case 64:  warp_bitonic_regs<2>(sb, lane); break;
+        case 128: warp_bitonic_regs<4>(sb, lane); break;
+        case 256: warp_bitonic_regs<8>(sb, lane); break;
+        case 512: warp_bitonic_regs<16>(sb, lane); break;
+        default:
+            for (int size = 2; size <= n2; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int k = lane; k < (n2 >> 1); k += 32) {
+                        const int lo = 2 * k - (k & (stride - 1));
+                        const int hi = lo + stride;
+                        const bool up = (lo & size) == 0;
+                        const int x = sb[lo], y = sb[hi];
+                        if ((x > y) == up) { sb[lo] = y; sb[hi] = x; }
+                    }
+                    __syncwarp();
+                }
+            }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // merge_kernel: one warp per i-particle.
 //   fp64 sum over the S slices in a fixed order (deterministic); gather of the S neighbour segments into
 //   shared memory; bitonic sort ascending -- tiles are visited in Morton order, the caller needs strictly
@@ -660,6 +760,7 @@ struct MergeArgs {
     double *res_f;      // [ni][f_stride]; f_stride = 8 stores the (signed) count in slot 7 for the shard combine
     int     f_stride;
     int    *res_list;   // [ni][lmax]
+    int     sort;       // 0: leave the row in arrival order (a shard row: combine_kernel sorts the union)
 };
 
 __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
@@ -670,7 +771,8 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
     if (i >= a.ni) return;
     double f[7] = {0, 0, 0, 0, 0, 0, 0};
     int total = 0;
-    for (int s = lane; s < a.S; s += 32) {
+#pragma unroll 4
+    for (int s = lane; s < a.S; s += 32) {             // loads of several rounds in flight
         const double *p = a.part + ((size_t)s * a.ni + i) * PART_STRIDE;
 #pragma unroll
         for (int c = 0; c < 7; c++) f[c] += p[c];
@@ -701,32 +803,24 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
         for (int k = 0; k < n; k++) sb[off + k] = src[k];
         base += __shfl_sync(0xffffffffu, incl, 31);
     }
-    int n2 = 32;
-    while (n2 < total) n2 <<= 1;
-    for (int k = total + lane; k < n2; k += 32) sb[k] = INT_MAX;
-    __syncwarp();
-    for (int size = 2; size <= n2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int k = lane; k < (n2 >> 1); k += 32) {
-                const int lo = 2 * k - (k & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const int x = sb[lo], y = sb[hi];
-                if ((x > y) == up) { sb[lo] = y; sb[hi] = x; }
-            }
-            __syncwarp();
-        }
+    if (a.sort) {
+        int n2 = 32;
+        while (n2 < total) n2 <<= 1;
+        for (int k = total + lane; k < n2; k += 32) sb[k] = INT_MAX;
+        warp_sort_smem(sb, n2, lane);
+    } else {
+        __syncwarp();
     }
     for (int k = lane; k < total; k += 32) row[1 + k] = sb[k];
 }
 
 // ---------------------------------------------------------------------------------------------
-// combine_kernel: j-shard exchange step (multi-GPU).  Every shard r (a GPU holding j in
-// [r*nj/R, (r+1)*nj/R), reference split: gpunb.velocity.cu:713-715) has produced, per i-particle,
-// 7 fp64 partial sums + its signed neighbour count (fr[r][i][8]) and an ascending row of GLOBAL j
-// indices (rows[r][i][lmax]).  One warp per i: fp64 sum over shards in rank order (the reference
-// sums GPUs in fp64 on the host, :823-845), counts scanned in rank order, rows concatenated -- rank
-// order is ascending j, so the concatenation is the index-ordered merge (:852-871).
+// combine_kernel: j-shard exchange step (multi-GPU).  Every shard r (a GPU holding every R-th tile of the
+// Hilbert-sorted j-set, see shard_tiles) has produced, per i-particle, 7 fp64 partial sums + its signed
+// neighbour count (fr[r][i][8]) and an ascending row of GLOBAL j indices (rows[r][i][lmax]).  One warp per i:
+// fp64 sum over shards in rank order (the reference sums GPUs in fp64 on the host, :823-845), counts scanned in
+// rank order, rows gathered and sorted ascending (the reference's index-range shards only need concatenating,
+// :852-871; spatial shards interleave in j).
 // fr[r] / rows[r] are PEER pointers (NVLink P2P: cudaIpc-mapped across processes, or peer-enabled
 // devices of one process): the kernel pulls only the `count` valid entries of each remote row, so the
 // exchange moves ~4*nnb bytes per i instead of whole rows.  Overflow: any shard negative or
@@ -739,34 +833,98 @@ struct CombineArgs {
     const int    *rows[MAX_RANKS];   // [ni][lmax]
     double *res_f;                   // [ni][7]
     int    *res_list;                // [ni][lmax]
+    // one process per GPU: flags[r] (in THIS rank's exchange buffer) is set to `seq` by rank r, over NVLink, once
+    // its fr/rows of this call are complete (signal_kernel).  NULL: ordering is done with stream events.
+    const unsigned long long *flags;
+    unsigned long long seq;
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Loads of peer memory that another GPU wrote during this kernel's lifetime: system-scope, never served from a
+// stale L1 line.  (ld.global.cv / .cg / ld.volatile measured the same on NVLink 5.)
+__device__ __forceinline__ double peer_ld(const double *p)
+{
+    double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ int peer_ld(const int *p)
+{
+    int v; asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+
+// Tells every peer that this rank's shard results of call `seq` are in its exchange buffer (launched after
+// merge_kernel on the same stream).  Thread r stores into rank r's flag slot for this rank, over NVLink.
+struct PeerFlags { unsigned long long *p[MAX_RANKS]; };
+__global__ void signal_kernel(const PeerFlags pf, int R, int rank, unsigned long long seq)
+{
+    if ((int)threadIdx.x < R) {
+        __threadfence_system();
+        st_release_sys(pf.p[threadIdx.x] + rank, seq);
+    }
+}
 
 __global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
 {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ int sbuf[4][SORT_CAP];
+    __shared__ int soff[4][MAX_RANKS], scnt[4][MAX_RANKS];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int i = blockIdx.x * 4 + wq;
     if (i >= a.ni) return;
+    if (a.flags) {                                     // wait until every shard has published this call
+        if (lane < a.R) while (ld_acquire_sys(a.flags + lane) < a.seq) { }
+        __syncwarp();
+    }
+    // records are requested four shards at a time before any is used: R/4 NVLink round trips, not R
     double f = 0.0;
     int total = 0;
     bool over = false;
-    int off[MAX_RANKS], cnt[MAX_RANKS];
-    for (int r = 0; r < a.R; r++) {
-        const double *p = a.fr[r] + (size_t)i * 8;
-        if (lane < 7) f += p[lane];
-        const int c = (int)p[7];
-        over |= c < 0;
-        cnt[r] = c < 0 ? -c : c;
-        off[r] = 1 + total;
-        total += cnt[r];
+    int *sb = sbuf[wq];
+    int *offs = soff[wq], *cnts = scnt[wq];           // per-shard offsets / counts of this i
+    for (int r0 = 0; r0 < a.R; r0 += 4) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            v[q] = (r0 + q < a.R && lane < 8) ? peer_ld(a.fr[r0 + q] + (size_t)i * 8 + lane) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (r0 + q < a.R) {
+                f += v[q];                             // rank order: deterministic
+                const int c = (int)__shfl_sync(0xffffffffu, v[q], 7);
+                over |= c < 0;
+                const int ca = c < 0 ? -c : c;
+                if (lane == 0) { offs[r0 + q] = total; cnts[r0 + q] = ca; }
+                total += ca;
+            }
+        }
     }
     if (lane < 7) a.res_f[(size_t)i * 7 + lane] = f;
     int *row = a.res_list + (size_t)i * a.lmax;
     if (over || total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
     if (lane == 0) row[0] = total;
-    for (int r = 0; r < a.R; r++) {
-        const int *src = a.rows[r] + (size_t)i * a.lmax + 1;
-        for (int k = lane; k < cnt[r]; k += 32) row[off[r] + k] = src[k];
+    if (total == 0) return;
+    __syncwarp();
+    // flat gather: entry e of the union comes from the shard whose [off, off + cnt) contains it
+    {
+        int r = 0, o = offs[0], c = cnts[0];
+        for (int e = lane; e < total; e += 32) {
+            while (e >= o + c) { r++; o = offs[r]; c = cnts[r]; }
+            sb[e] = peer_ld(a.rows[r] + (size_t)i * a.lmax + 1 + (e - o));
+        }
     }
+    __syncwarp();
+    int n2 = 32;
+    while (n2 < total) n2 <<= 1;
+    for (int k = total + lane; k < n2; k += 32) sb[k] = INT_MAX;
+    warp_sort_smem(sb, n2, lane);
+    for (int k = lane; k < total; k += 32) row[1 + k] = sb[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -867,7 +1025,7 @@ struct Dev {
     double *jraw = nullptr;
     float *jtile = nullptr;
     double *radii = nullptr;      // h2[raw_cap] | dtr[raw_cap]  (resident sweeps)
-    int nj_total = 0, j0 = 0, nj = 0, ntiles = 0;
+    int nj_total = 0, nj = 0, ntiles = 0;
     int *jidx = nullptr;          // sorted slot -> global j
     // Morton sort scratch
     unsigned *hbits = nullptr;    // largest |coordinate| of the shard (float bits)
@@ -905,9 +1063,12 @@ struct Shard {                     // one process per GPU, j sharded over ranks
     pfn_ncclGetUniqueId getid = nullptr; pfn_ncclCommInitRank init = nullptr; pfn_ncclAllGather allgather = nullptr;
     pfn_ncclCommDestroy destroy = nullptr; pfn_ncclGetErrorString errstr = nullptr;
     ncclComm_t comm = nullptr;
-    double *fr_all = nullptr;      // [R][NIMAX*8]
-    int *rows_local = nullptr;     // [2][NIMAX][ROWS_LMAX_CAP], exported with cudaIpc
-    int *rows_peer[MAX_RANKS] = {nullptr};
+    // Exchange buffer of this rank (one allocation, exported with cudaIpc, mapped by every peer):
+    //   [2 parities] x { fr[NIMAX][8] doubles | rows[NIMAX][ROWS_LMAX_CAP] ints }  |  flags[MAX_RANKS] u64
+    unsigned char *xbuf = nullptr;
+    unsigned char *xbuf_peer[MAX_RANKS] = {nullptr};
+    unsigned long long seq = 0;    // regf calls so far (every rank makes the same calls)
+    double *scratch = nullptr;     // bootstrap / finalize all-gathers
     int parity = 0;
 };
 
@@ -1009,10 +1170,17 @@ void lib_devinit(int irank)
     L.devinit = true;
 }
 
-void shard_range(int r, int R, int nj, int &j0, int &j1)
-{   // reference split: joff[id] = id*nbody/numGPU (gpunb.velocity.cu:713-715)
-    j0 = (int)(((long long)r * nj) / R);
-    j1 = (int)(((long long)(r + 1) * nj) / R);
+// j-shards.  The reference cuts the j ARRAY into contiguous index ranges (joff[id] = id*nbody/numGPU,
+// gpunb.velocity.cu:713-715).  Here the WHOLE j-set is Hilbert-sorted and cut into tiles of TJ, and shard r owns
+// the tiles t = r, r+R, r+2R, ... of the T = ceil(nj/TJ) tiles.  Every tile is as compact as on one GPU (an
+// index-range shard is a random 1/R subsample of space: measured 15 % NEAR tiles at R = 8 against 5 % for the
+// whole set), and every shard samples every region of the cluster, so the NEAR work of any i-block is spread evenly
+// over the shards (contiguous curve ranges left one shard 6 % slower than the others at R = 4).  The result is the
+// same function of the input; neighbour rows of different shards interleave in j and are merged by sorting.
+void shard_tiles(int r, int R, int nj, int &nloc)
+{
+    const int T = (nj + TJ - 1) / TJ;
+    nloc = r < T ? (T - r + R - 1) / R : 0;
 }
 
 void ensure_j_capacity(Dev &d, int nj_total, int shard_n)
@@ -1052,19 +1220,20 @@ void ensure_sort_capacity(Dev &d, int n)
     CUDA_CHECK(cudaMalloc(&d.cub_tmp, bytes));
 }
 
-// fp64 particles (m, x, v or NULL; n of them, device pointers) -> Morton-sorted tiles + slot->index map.
-// The radix sort of the 63-bit keys is CUB (plumbing, not the hot path).
-void build_tiles(Dev &d, int n, int joff, const double *m, const double *x, const double *v, float *tiles, int *jidx)
+// fp64 particles (m, x, v or NULL; n of them, device pointers) -> Hilbert-sorted tiles + slot->index map.
+// ALL n particles are sorted; tiles t0, t0 + tstride, ... (nloc of them) of the sorted order are packed (the tiles
+// of one j-shard, see shard_tiles).  The radix sort of the 63-bit keys is CUB (plumbing, not the hot path).
+void build_tiles(Dev &d, int n, const double *m, const double *x, const double *v, float *tiles, int *jidx,
+                 int t0, int tstride, int nloc)
 {
     if (n <= 0) return;
     ensure_sort_capacity(d, n);
-    const int ntiles = (n + TJ - 1) / TJ;
     CUDA_CHECK(cudaMemsetAsync(d.hbits, 0, sizeof(unsigned), d.st));
     absmax_kernel<<<(n + 255) / 256, 256, 0, d.st>>>(n, m, x, v, d.hbits, d.nanflag);
     mortonkey_kernel<<<(n + 255) / 256, 256, 0, d.st>>>(n, x, d.hbits, d.keys_in, d.vals_in);
     size_t bytes = d.cub_tmp_bytes;
     CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d.cub_tmp, bytes, d.keys_in, d.keys_out, d.vals_in, d.perm, n, 0, 63, d.st));
-    tilepack_kernel<<<(ntiles + 3) / 4, 128, 0, d.st>>>(n, ntiles, joff, m, x, v, d.perm, tiles, jidx);
+    if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx);
     CUDA_CHECK(cudaGetLastError());
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 4;       // + the CUB sort passes (library code, not counted)
 }
@@ -1174,14 +1343,14 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
     for (size_t g = 0; g < L.devs.size(); g++) {
         Dev &d = L.devs[g];
         set_dev(d);
-        int j0, j1;
-        shard_range(L.sh.on ? L.sh.rank : (int)g, R, nj, j0, j1);
-        ensure_j_capacity(d, nj, j1 - j0);
-        d.nj_total = nj; d.j0 = j0; d.nj = j1 - j0; d.ntiles = (d.nj + TJ - 1) / TJ;
+        const int r = L.sh.on ? L.sh.rank : (int)g;
+        int nloc;
+        shard_tiles(r, R, nj, nloc);
+        ensure_j_capacity(d, nj, nloc * TJ);
+        d.nj_total = nj; d.ntiles = nloc; d.nj = nloc * TJ;
         CUDA_CHECK(cudaMemcpyAsync(d.jraw, h, sizeof(double) * 7 * nj, cudaMemcpyHostToDevice, d.st));
         L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * nj;
-        build_tiles(d, d.nj, j0, d.jraw + j0, d.jraw + nj + 3 * (size_t)j0, d.jraw + 4 * (size_t)nj + 3 * (size_t)j0,
-                    d.jtile, d.jidx);
+        build_tiles(d, nj, d.jraw, d.jraw + nj, d.jraw + 4 * (size_t)nj, d.jtile, d.jidx, r, R, nloc);
         CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, d.nanflag, sizeof(int), cudaMemcpyDeviceToHost, d.st));
     }
     for (size_t g = 0; g < L.devs.size(); g++) {
@@ -1207,10 +1376,20 @@ Plan make_plan(const Dev &d, int ni)
 
 struct IBlock { const double *h2, *dtr, *xi, *vi; };
 
+// exchange-buffer layout (NCCL mode)
+constexpr size_t XB_FR_BYTES   = (size_t)NIMAX * 8 * sizeof(double);
+constexpr size_t XB_ROWS_BYTES = (size_t)NIMAX * 1024 /*ROWS_LMAX_CAP*/ * sizeof(int);
+constexpr size_t XB_PARITY     = XB_FR_BYTES + XB_ROWS_BYTES;
+constexpr size_t XB_FLAGS_OFF  = 2 * XB_PARITY;
+constexpr size_t XB_BYTES      = XB_FLAGS_OFF + 16 /*MAX_RANKS*/ * sizeof(unsigned long long);
+inline double *xb_fr(unsigned char *b, int parity)   { return reinterpret_cast<double *>(b + parity * XB_PARITY); }
+inline int    *xb_rows(unsigned char *b, int parity) { return reinterpret_cast<int *>(b + parity * XB_PARITY + XB_FR_BYTES); }
+inline unsigned long long *xb_flags(unsigned char *b) { return reinterpret_cast<unsigned long long *>(b + XB_FLAGS_OFF); }
+
 // Pair kernel + shard-local merge for one i-block on device d (async on d.st).
 void launch_regf(Dev &d, int ni, const IBlock &ib, int lmax, int nnbmax, int m_flag, bool time_it,
-                 double *out_f, int f_stride, int *out_rows)
-{
+                 double *out_f, int f_stride, int *out_rows, bool sort_rows, cudaEvent_t *tl = nullptr)
+{   // tl (optional): 5 events; [0] before isort, [1] after isort, [2] after regf, [3] after merge ([4]: regf_block)
     const Plan p = make_plan(d, ni);
     RegfArgs a;
     a.tiles = d.jtile; a.jidx = d.jidx; a.ntiles = d.ntiles; a.iperm = d.iperm;
@@ -1221,53 +1400,72 @@ void launch_regf(Dev &d, int ni, const IBlock &ib, int lmax, int nnbmax, int m_f
     a.part = d.part; a.cnt = d.cnt; a.seg = d.seg; a.segcap = d.segcap;
     const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
     const int blocks = (p.n_items + WARPS - 1) / WARPS;
-    isort_kernel<<<1, 1024, 0, d.st>>>(ni, ib.xi, d.hbits, d.iperm);
+    if (tl) CUDA_CHECK(cudaEventRecord(tl[0], d.st));
+    static int noisort = -1;
+    if (noisort < 0) { const char *e = getenv("GPUNB_B200_NOISORT"); noisort = (e && atoi(e) > 0) ? 1 : 0; }
+    if (noisort) iota_kernel<<<(ni + 255) / 256, 256, 0, d.st>>>(ni, d.iperm);     // tuning: i-block in caller order
+    else isort_kernel<<<1, 1024, 0, d.st>>>(ni, ib.xi, d.hbits, d.iperm);
+    if (tl) CUDA_CHECK(cudaEventRecord(tl[1], d.st));
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev0, d.st));
     VARIANTS[d.variant].k[m_flag ? 1 : 0]<<<blocks, WARPS * 32, smem, d.st>>>(a);
     CUDA_CHECK(cudaGetLastError());
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev1, d.st));
+    if (tl) CUDA_CHECK(cudaEventRecord(tl[2], d.st));
     MergeArgs m;
     m.part = d.part; m.cnt = d.cnt; m.seg = d.seg; m.ni = ni; m.S = p.S; m.segcap = d.segcap;
-    m.lmax = lmax; m.nnbmax = nnbmax; m.res_f = out_f; m.f_stride = f_stride; m.res_list = out_rows;
+    m.lmax = lmax; m.nnbmax = nnbmax; m.res_f = out_f; m.f_stride = f_stride; m.res_list = out_rows; m.sort = sort_rows ? 1 : 0;
     merge_kernel<<<(ni + 3) / 4, 128, 0, d.st>>>(m);
     CUDA_CHECK(cudaGetLastError());
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev2, d.st));
+    if (tl) CUDA_CHECK(cudaEventRecord(tl[3], d.st));
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 3;
 }
 
 // One i-block on all shards + the exchange step.  ib[g] are DEVICE pointers valid on local device g.
 // On return (asynchronously, on the root stream) root.res_f / root.res_list hold the combined result.
-void regf_block(int ni, const IBlock *ib, int lmax, int nnbmax, int m_flag, bool time_it)
+void regf_block(int ni, const IBlock *ib, int lmax, int nnbmax, int m_flag, bool time_it, cudaEvent_t *tl = nullptr)
 {
     const int G = (int)L.devs.size();
     Dev &root = L.devs[0];
     if (!L.sh.on && G == 1) {          // single GPU: the shard-local merge IS the final result
         set_dev(root);
-        launch_regf(root, ni, ib[0], lmax, nnbmax, m_flag, time_it, root.res_f, 7, root.res_list);
+        launch_regf(root, ni, ib[0], lmax, nnbmax, m_flag, time_it, root.res_f, 7, root.res_list, true, tl);
         if (time_it) CUDA_CHECK(cudaEventRecord(root.ev3, root.st));
+        if (tl) CUDA_CHECK(cudaEventRecord(tl[4], root.st));
         return;
     }
     CombineArgs c;
     c.ni = ni; c.lmax = lmax; c.nnbmax = nnbmax; c.res_f = root.res_f; c.res_list = root.res_list;
-    if (L.sh.on) {                     // one process per GPU: NCCL all-gather of the 64 B/i partials, P2P pull of rows
+    c.flags = nullptr; c.seq = 0;
+    if (L.sh.on) {
+        // One process per GPU.  No collective call in the data path: every rank writes its shard result into its
+        // own exchange buffer, raises a flag in every peer's buffer over NVLink (signal_kernel), and
+        // combine_kernel -- after seeing all R flags of this call -- pulls partial sums and the valid part of the
+        // neighbour rows straight from the peers' HBM.  Buffers alternate by call parity: a rank can only be
+        // overwriting parity p of call k+2 after its combine of call k+1 has seen every peer's flag k+1, which
+        // each peer raises after its own combine of call k.
         Shard &sh = L.sh;
         set_dev(root);
-        int *rows = sh.rows_local + (size_t)sh.parity * NIMAX * ROWS_LMAX_CAP;
-        launch_regf(root, ni, ib[0], lmax, nnbmax, m_flag, time_it, root.fr, 8, rows);
-        int rc = sh.allgather(root.fr, sh.fr_all, (size_t)ni * 8, NCCL_FLOAT64, sh.comm, root.st);
-        if (rc != 0) FATAL("ncclAllGather failed: %s", sh.errstr ? sh.errstr(rc) : "?");
+        const unsigned long long seq = ++sh.seq;
+        const int parity = (int)(seq & 1ull);
+        launch_regf(root, ni, ib[0], lmax, nnbmax, m_flag, time_it, xb_fr(sh.xbuf, parity), 8, xb_rows(sh.xbuf, parity), false, tl);
+        PeerFlags pf;
+        for (int r = 0; r < MAX_RANKS; r++) pf.p[r] = r < sh.R ? xb_flags(sh.xbuf_peer[r]) : nullptr;
+        signal_kernel<<<1, 32, 0, root.st>>>(pf, sh.R, sh.rank, seq);
+        CUDA_CHECK(cudaGetLastError());
         c.R = sh.R;
         for (int r = 0; r < sh.R; r++) {
-            c.fr[r] = sh.fr_all + (size_t)r * ni * 8;
-            c.rows[r] = sh.rows_peer[r] + (size_t)sh.parity * NIMAX * ROWS_LMAX_CAP;
+            c.fr[r] = xb_fr(sh.xbuf_peer[r], parity);
+            c.rows[r] = xb_rows(sh.xbuf_peer[r], parity);
         }
-        sh.parity ^= 1;                // rows are double buffered: a peer may still be pulling the previous block
+        c.flags = xb_flags(sh.xbuf); c.seq = seq;
+        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
     } else {                           // one process, G GPUs: root waits for every shard, pulls over P2P
         for (int g = 0; g < G; g++) {
             Dev &d = L.devs[g];
             set_dev(d);
             if (g > 0) CUDA_CHECK(cudaStreamWaitEvent(d.st, root.evdone, 0));     // previous combine has consumed d.fr / d.rows
-            launch_regf(d, ni, ib[g], lmax, nnbmax, m_flag, time_it && g == 0, d.fr, 8, d.rows);
+            launch_regf(d, ni, ib[g], lmax, nnbmax, m_flag, time_it && g == 0, d.fr, 8, d.rows, false);
             if (g > 0) {
                 CUDA_CHECK(cudaEventRecord(d.evdone, d.st));
                 CUDA_CHECK(cudaStreamWaitEvent(root.st, d.evdone, 0));
@@ -1277,11 +1475,12 @@ void regf_block(int ni, const IBlock *ib, int lmax, int nnbmax, int m_flag, bool
         c.R = G;
         set_dev(root);
     }
-    combine_kernel<<<(ni + 3) / 4, 128, 0, root.st>>>(c);
+    combine_kernel<<<(ni + 3) / 4, 128, 0, root.st>>>(c);      // 4 warps per CTA: one i each
     CUDA_CHECK(cudaGetLastError());
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
     if (!L.sh.on) CUDA_CHECK(cudaEventRecord(root.evdone, root.st));
     if (time_it) CUDA_CHECK(cudaEventRecord(root.ev3, root.st));
+    if (tl) CUDA_CHECK(cudaEventRecord(tl[4], root.st));
 }
 
 void fetch_results(int ni, int lmax, double *acc, double *jrk, double *pot, int *list)
@@ -1380,7 +1579,7 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
     memcpy(hpin, m, sizeof(double) * n);
     memcpy(hpin + n, x, sizeof(double) * 3 * n);
     CUDA_CHECK(cudaMemcpyAsync(jraw, hpin, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, d.st));
-    build_tiles(d, n, 0, jraw, jraw + n, nullptr, jtile, jidx);
+    build_tiles(d, n, jraw, jraw + n, nullptr, jtile, jidx, 0, 1, ntiles);
     const int n_it = (ni + 31) / 32;
     int S = (d.nsm * 16 * 4) / n_it; if (S < 1) S = 1; if (S > ntiles) S = ntiles;
     if ((size_t)S * ni > d.pot_part_n) { dev_free(d.pot_part); d.pot_part_n = (size_t)S * ni; dev_alloc(d.pot_part, d.pot_part_n); }
@@ -1496,6 +1695,15 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
     set_dev(root);
     CUDA_CHECK(cudaEventRecord(root.evs0, root.st));
     int nlaunch = 0, last = 0;
+    static int timeline = -1;
+    if (timeline < 0) { const char *e = getenv("GPUNB_B200_TIMELINE"); timeline = (e && atoi(e) > 0 && L.devs.size() == 1) ? 1 : 0; }
+    static std::vector<cudaEvent_t> tlev;
+    const int nblocks = (ni + block - 1) / block;
+    if (timeline && (int)tlev.size() < 5 * nblocks) {
+        const size_t old = tlev.size();
+        tlev.resize((size_t)5 * nblocks);
+        for (size_t k = old; k < tlev.size(); k++) CUDA_CHECK(cudaEventCreate(&tlev[k]));
+    }
     for (int b = i0; b < i0 + ni; b += block) {
         const int n = (i0 + ni - b < block) ? i0 + ni - b : block;
         IBlock ib[MAX_RANKS];
@@ -1504,7 +1712,7 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
             const double *x = d.jraw + d.nj_total, *v = d.jraw + 4 * (size_t)d.nj_total;
             ib[g] = IBlock{d.radii + b, d.radii + d.raw_cap + b, x + 3 * (size_t)b, v + 3 * (size_t)b};
         }
-        regf_block(n, ib, *lmaxp, *nnbmaxp, *m_flagp, false);
+        regf_block(n, ib, *lmaxp, *nnbmaxp, *m_flagp, false, timeline ? &tlev[(size_t)5 * nlaunch] : nullptr);
         L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)n * root.nj_total;
         nlaunch++; last = n;
     }
@@ -1512,6 +1720,15 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
     CUDA_CHECK(cudaEventRecord(root.evs1, root.st));
     CUDA_CHECK(cudaStreamSynchronize(root.st));
     float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, root.evs0, root.evs1));
+    if (timeline) {
+        for (int k = 0; k < nlaunch; k++) {
+            float t[4];
+            for (int q = 0; q < 4; q++) CUDA_CHECK(cudaEventElapsedTime(&t[q], tlev[(size_t)5 * k + q], tlev[(size_t)5 * k + q + 1]));
+            L.ctr[GPUNB_B200_CTR_TL_ISORT_MS] += t[0]; L.ctr[GPUNB_B200_CTR_TL_REGF_MS] += t[1];
+            L.ctr[GPUNB_B200_CTR_TL_MERGE_MS] += t[2]; L.ctr[GPUNB_B200_CTR_TL_EXCH_MS] += t[3];
+        }
+        L.ctr[GPUNB_B200_CTR_TL_BLOCKS] += nlaunch;
+    }
     L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += nlaunch;
     L.last_ni = last; L.last_lmax = *lmaxp;
     return ms;
@@ -1563,12 +1780,12 @@ int gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128])
     ncclUniqueId id; memcpy(id.internal, id128, 128);
     int rc = sh.init(&sh.comm, nranks, id, rank);
     if (rc != 0) FATAL("ncclCommInitRank failed: %s", sh.errstr ? sh.errstr(rc) : "?");
-    sh.rank = rank; sh.R = nranks; sh.parity = 0;
-    dev_alloc(sh.fr_all, (size_t)nranks * NIMAX * 8);
-    dev_alloc(sh.rows_local, (size_t)2 * NIMAX * ROWS_LMAX_CAP);
-    // exchange cudaIpc handles of the row buffers with an all-gather, then map every peer's buffer
+    sh.rank = rank; sh.R = nranks; sh.seq = 0;
+    CUDA_CHECK(cudaMalloc((void **)&sh.xbuf, XB_BYTES));
+    CUDA_CHECK(cudaMemsetAsync(sh.xbuf, 0, XB_BYTES, d.st));
+    // exchange cudaIpc handles of the exchange buffers with an all-gather (bootstrap only), then map every peer's
     cudaIpcMemHandle_t mine;
-    CUDA_CHECK(cudaIpcGetMemHandle(&mine, sh.rows_local));
+    CUDA_CHECK(cudaIpcGetMemHandle(&mine, sh.xbuf));
     unsigned char *hbuf = nullptr; dev_alloc(hbuf, (size_t)(nranks + 1) * sizeof(cudaIpcMemHandle_t));
     CUDA_CHECK(cudaMemcpyAsync(hbuf + (size_t)nranks * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, d.st));
     rc = sh.allgather(hbuf + (size_t)nranks * sizeof(mine), hbuf, sizeof(mine), NCCL_INT8, sh.comm, d.st);
@@ -1578,12 +1795,17 @@ int gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128])
     CUDA_CHECK(cudaStreamSynchronize(d.st));
     dev_free(hbuf);
     for (int r = 0; r < nranks; r++) {
-        if (r == rank) { sh.rows_peer[r] = sh.rows_local; continue; }
+        if (r == rank) { sh.xbuf_peer[r] = sh.xbuf; continue; }
         void *p = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) FATAL("cudaIpcOpenMemHandle(rank %d) failed: %s (NVLink P2P between ranks is required)", r, cudaGetErrorString(e));
-        sh.rows_peer[r] = (int *)p;
+        sh.xbuf_peer[r] = (unsigned char *)p;
     }
+    // every rank has zeroed its flags and mapped its peers before anybody can signal: one more all-gather as barrier
+    dev_alloc(sh.scratch, 2 * (size_t)MAX_RANKS);
+    rc = sh.allgather(sh.scratch + MAX_RANKS, sh.scratch, 1, NCCL_FLOAT64, sh.comm, d.st);
+    if (rc != 0) FATAL("ncclAllGather(barrier) failed: %s", sh.errstr ? sh.errstr(rc) : "?");
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
     sh.on = true;
     return 0;
 }
@@ -1595,15 +1817,15 @@ void gpunb_b200_nccl_finalize(void)
     Dev &d = L.devs[0];
     set_dev(d);
     CUDA_CHECK(cudaStreamSynchronize(d.st));
-    for (int r = 0; r < sh.R; r++)
-        if (r != sh.rank && sh.rows_peer[r]) CUDA_CHECK(cudaIpcCloseMemHandle(sh.rows_peer[r]));
-    dev_free(sh.fr_all);
-    // the exported buffer is released only after every peer closed its mapping: a final all-gather is the barrier
-    dev_alloc(sh.fr_all, 2 * (size_t)sh.R);
-    sh.allgather(sh.fr_all + sh.R, sh.fr_all, 1, NCCL_FLOAT64, sh.comm, d.st);
+    // nobody unmaps or frees while a peer may still be pulling: all-gather as barrier, before and after the unmap
+    sh.allgather(sh.scratch + MAX_RANKS, sh.scratch, 1, NCCL_FLOAT64, sh.comm, d.st);
     CUDA_CHECK(cudaStreamSynchronize(d.st));
-    dev_free(sh.fr_all);
-    dev_free(sh.rows_local);
+    for (int r = 0; r < sh.R; r++)
+        if (r != sh.rank && sh.xbuf_peer[r]) { CUDA_CHECK(cudaIpcCloseMemHandle(sh.xbuf_peer[r])); sh.xbuf_peer[r] = nullptr; }
+    sh.allgather(sh.scratch + MAX_RANKS, sh.scratch, 1, NCCL_FLOAT64, sh.comm, d.st);
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    dev_free(sh.scratch);
+    CUDA_CHECK(cudaFree(sh.xbuf)); sh.xbuf = nullptr;
     sh.destroy(sh.comm);
     sh.comm = nullptr; sh.on = false; sh.R = 1; sh.rank = 0;
 }

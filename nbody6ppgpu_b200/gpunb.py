@@ -23,9 +23,10 @@ _HERE = Path(__file__).resolve().parent
 _c_int_p = C.POINTER(C.c_int)
 _c_dbl_p = C.POINTER(C.c_double)
 
-N_COUNTERS = 10
+N_COUNTERS = 15
 CTR = dict(grav_ms=0, grav_launches=1, launches=2, h2d_bytes=3, d2h_bytes=4, interactions=5,
-           merge_ms=6, pot_ms=7, near_tiles=8, all_tiles=9)
+           merge_ms=6, pot_ms=7, near_tiles=8, all_tiles=9,
+           tl_blocks=10, tl_isort_ms=11, tl_regf_ms=12, tl_merge_ms=13, tl_exch_ms=14)
 
 
 class LibraryMissing(RuntimeError):

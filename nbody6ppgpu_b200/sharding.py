@@ -1,18 +1,75 @@
 """Host-side mirror of the multi-GPU exchange step (used by bench.py's launcher logic and by the CPU tests).
 
-The j-set is split into contiguous index ranges exactly like the reference
-(gpunb.velocity.cu:713-715: joff[id] = id*nbody/numGPU); every shard produces, per i-particle, partial
-sums, a signed neighbour count and an ascending row of global j indices.  ``combine_shards`` restates what
-``combine_kernel`` does on the GPU: fp64 sum in rank order, counts scanned in rank order, rows concatenated
-(rank order IS ascending j), overflow -> -(sum |count_r|).
+The reference splits the j ARRAY into contiguous index ranges (gpunb.velocity.cu:713-715: joff[id] =
+id*nbody/numGPU).  This library sorts the j-set along a Hilbert curve, cuts it into tiles of 64 and gives shard r
+the tiles r, r+R, r+2R, ... (``shard_tiles``): every tile is as compact as on one GPU, so the tile culling of the
+pair kernel works as well on a shard as on the whole set, and every shard samples every region of the cluster.  Every shard produces, per i-particle, partial sums, a signed
+neighbour count and an ascending row of global j indices.  ``combine_shards`` restates what ``combine_kernel``
+does on the GPU: fp64 sum in rank order, rows gathered and sorted ascending, overflow -> -(sum |count_r|).
 """
 from __future__ import annotations
 
 import numpy as np
 
+TJ = 64
+
 
 def shard_range(rank: int, nranks: int, nj: int) -> tuple[int, int]:
+    """The reference's index-range split (kept for comparison and for the gpupot/legacy tests)."""
     return (rank * nj) // nranks, ((rank + 1) * nj) // nranks
+
+
+def shard_tiles(rank: int, nranks: int, nj: int) -> range:
+    """Tiles of shard `rank`: every nranks-th tile of the Hilbert-sorted j-set (mirror of shard_tiles() in
+    gpunb_b200.cu)."""
+    T = (nj + TJ - 1) // TJ
+    return range(rank, T, nranks)
+
+
+def hilbert_keys(x: np.ndarray) -> np.ndarray:
+    """63-bit Hilbert keys (Skilling's transpose algorithm, 21 bits per axis) -- numpy mirror of morton_key() in
+    gpunb_b200.cu, same fp32 quantisation."""
+    x32 = np.asarray(x, dtype=np.float64).astype(np.float32)
+    H = np.float32(max(float(np.abs(x32).max()), 1e-30))
+    sc = np.float32(1048575.5) / H
+    X = [np.clip(x32[:, c] * sc + np.float32(1048576.0), np.float32(0.0), np.float32(2097151.0)).astype(np.uint64) for c in range(3)]
+    M = 1 << 20
+    Q = M
+    while Q > 1:
+        P = np.uint64(Q - 1)
+        for i in range(3):
+            hit = (X[i] & np.uint64(Q)) != 0
+            X[0] = np.where(hit, X[0] ^ P, X[0])
+            t = np.where(hit, np.uint64(0), (X[0] ^ X[i]) & P)
+            X[0] = X[0] ^ t
+            X[i] = X[i] ^ t
+        Q >>= 1
+    X[1] ^= X[0]
+    X[2] ^= X[1]
+    t = np.zeros_like(X[0])
+    Q = M
+    while Q > 1:
+        t = np.where((X[2] & np.uint64(Q)) != 0, t ^ np.uint64(Q - 1), t)
+        Q >>= 1
+    X = [v ^ t for v in X]
+
+    def spread(v):
+        v = v & np.uint64(0x1fffff)
+        v = (v | (v << np.uint64(32))) & np.uint64(0x1f00000000ffff)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x1f0000ff0000ff)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x100f00f00f00f00f)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x10c30c30c30c30c3)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+        return v
+    return (spread(X[0]) << np.uint64(2)) | (spread(X[1]) << np.uint64(1)) | spread(X[2])
+
+
+def shard_members(x: np.ndarray, rank: int, nranks: int) -> np.ndarray:
+    """Global j indices (ascending) of the particles in shard `rank`."""
+    nj = x.shape[0]
+    order = np.argsort(hilbert_keys(x), kind="stable")
+    parts = [order[t * TJ:min((t + 1) * TJ, nj)] for t in shard_tiles(rank, nranks, nj)]
+    return np.sort(np.concatenate(parts)) if parts else np.zeros(0, dtype=np.int64)
 
 
 def combine_shards(f_parts, lists, nnbmax: int):
@@ -31,10 +88,7 @@ def combine_shards(f_parts, lists, nnbmax: int):
             out[i, 0] = -total
             continue
         out[i, 0] = total
-        k = 1
-        for r in range(R):
-            out[i, k:k + cnts[r]] = lists[r][i, 1:1 + cnts[r]]
-            k += cnts[r]
+        out[i, 1:1 + total] = np.sort(np.concatenate([lists[r][i, 1:1 + cnts[r]] for r in range(R)]))
     return f, out
 
 

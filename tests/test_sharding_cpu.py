@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from nbody6ppgpu_b200 import snapshots as S  # noqa: E402
-from nbody6ppgpu_b200.sharding import combine_shards, shard_range  # noqa: E402
+from nbody6ppgpu_b200.sharding import combine_shards, shard_members, shard_range, shard_tiles  # noqa: E402
 
 
 def test_shard_range_matches_reference_split():
@@ -26,6 +26,25 @@ def test_shard_range_matches_reference_split():
             assert all(e == ((r * nj) // R, ((r + 1) * nj) // R) for r, e in enumerate(edges))
 
 
+def test_shard_tiles_partition_the_curve():
+    m, x, v = S.plummer(5003, 5, "kroupa")
+    T = (5003 + 63) // 64
+    for R in (1, 2, 3, 8):
+        tiles = [list(shard_tiles(r, R, 5003)) for r in range(R)]
+        assert sorted(t for ts in tiles for t in ts) == list(range(T))                   # every tile owned once
+        assert max(len(ts) for ts in tiles) - min(len(ts) for ts in tiles) <= 1
+        members = [shard_members(x, r, R) for r in range(R)]
+        allm = np.concatenate(members)
+        assert allm.size == 5003 and np.array_equal(np.sort(allm), np.arange(5003))      # a partition of the j-set
+        assert all(np.all(np.diff(mm) > 0) for mm in members)
+    # tiles are compact whatever the shard count: 64 consecutive particles of the curve span a small box
+    from nbody6ppgpu_b200.sharding import hilbert_keys
+    order = np.argsort(hilbert_keys(x), kind="stable")
+    inner = [order[t * 64:(t + 1) * 64] for t in range(T - 1)]
+    ext = np.array([np.ptp(x[ix], axis=0).max() for ix in inner])
+    assert np.median(ext) < 0.25 * np.ptp(x[np.linalg.norm(x, axis=1) < 2.0], axis=0).max()
+
+
 def _worker(rank, world, port, nnbmax, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -34,12 +53,12 @@ def _worker(rank, world, port, nnbmax, out):
     n, ni, lmax = 3001, 200, 128
     m, x, v = S.plummer(n, 21, "kroupa")
     h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 60.0))
-    j0, j1 = shard_range(rank, world, n)
-    a, j, p, l, band, _ = o.regf_f64(m[j0:j1], x[j0:j1], v[j0:j1], h2[:ni], dtr[:ni], x[:ni], v[:ni], lmax, nnbmax, 0)
-    for i in range(ni):                       # shard-local indices -> global, as regf_kernel does with joff
+    mem = shard_members(x, rank, world)       # a contiguous range of the Hilbert-sorted tiles, like lib_send
+    a, j, p, l, band, _ = o.regf_f64(m[mem], x[mem], v[mem], h2[:ni], dtr[:ni], x[:ni], v[:ni], lmax, nnbmax, 0)
+    for i in range(ni):                       # shard-local indices -> global, as regf_kernel does through jidx
         c = l[i, 0]
         if c > 0:
-            l[i, 1:1 + c] += j0
+            l[i, 1:1 + c] = mem[l[i, 1:1 + c]]
     f = torch.from_numpy(np.concatenate([a, j, p[:, None]], axis=1))
     lt = torch.from_numpy(l)
     fs = [torch.zeros_like(f) for _ in range(world)]
