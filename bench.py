@@ -308,7 +308,9 @@ def main():
     lib.profile(rank)
 
     # ---------------- FP32 pipe microbenchmark (roofline denominator measured in the same run) ----------------
-    ffma_tflops = max(lib.fp32_microbench(0, 8192) for _ in range(3))
+    # best of the FMA shapes that do not starve on register-file bandwidth (packed FFMA2 with a shared / repeated
+    # operand; a scalar FFMA with three distinct registers only reaches ~70 % of the lane rate on this part)
+    ffma_tflops = max(lib.fp32_microbench(mode, 8192) for mode in (1, 8, 10) for _ in range(2))
     lib.close()
     if world > 1:
         barrier()
@@ -322,17 +324,25 @@ def main():
     fp32_nominal = 2.0 * 128 * 148 * sm_max * 1e6 * 1e-12
     achieved_tflops = FLOP_PER_INT * int_per_launch / (kern_ms * 1e-3) * 1e-12
     mean_nnb = nnb_sum / float(ni_total)
-    alg_bytes = n * interactions_scale * 40.0 + BLOCK * (64.0 + 56.0 + 4.0 * (1 + mean_nnb))     # j tiles once + i in + forces/list out
+    # j tiles once (3392 B per 64 j) + i-block in + partial sums/lists out
+    alg_bytes = n * interactions_scale * (3392.0 / 64.0) + BLOCK * (64.0 + 56.0 + 4.0 * (1 + mean_nnb))
+    traffic = None                                   # dram bytes of one regf_kernel launch from the committed ncu capture
+    try:
+        prof = json.loads((ROOT / "profiles" / "regf_kernel_ncu_latest.json").read_text())
+        if world == 1 and prof.get("nj") == n:
+            traffic = float(prof["dram_bytes_read"]) + float(prof["dram_bytes_write"])
+    except Exception:
+        pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
         "bound": "fp32", "kernel": "regf_kernel", "achieved": achieved_tflops, "peak": fp32_nominal, "unit": "TFLOP/s",
         "frac": achieved_tflops / fp32_nominal,
         "peak_source": f"nominal 2*128 lanes*148 SM*{sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 entry)",
-        "peak_measured_ffma": ffma_tflops, "frac_of_measured_ffma": achieved_tflops / ffma_tflops,
+        "peak_measured_ffma": ffma_tflops, "peak_measured_ffma_how": "library microbenchmark, packed FFMA2 with <= 2 distinct register operands", "frac_of_measured_ffma": achieved_tflops / ffma_tflops,
         "flop_per_interaction": FLOP_PER_INT, "interactions_per_launch": int_per_launch, "launch_ms": kern_ms,
         "gint_per_s_kernel": int_per_launch / (kern_ms * 1e-3) * 1e-9,
         "roofline_gint_per_s": fp32_nominal * 1e12 / FLOP_PER_INT * 1e-9,
-        "traffic": None,
+        "traffic": traffic,
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms * 1e-3) * 1e-9,
                 "peak_gbs": hbm_peak, "peak_source": peak_src, "frac": alg_bytes / (kern_ms * 1e-3) * 1e-9 / hbm_peak},
         "merge_kernel_ms": merge_ms,

@@ -1533,6 +1533,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         ib[g] = IBlock{d.ibuf, d.ibuf + ni, d.ibuf + 2 * (size_t)ni, d.ibuf + 5 * (size_t)ni};
     }
     regf_block(ni, ib, lmax, nnbmax, m_flag, true);
+    CUDA_CHECK(cudaEventSynchronize(L.devs[0].ev1));          // "grav" ends with the pair kernel, like the reference's bucket
     const double wt0 = wtime();
     fetch_results(ni, lmax, acc, jrk, pot, list);
     Dev &root = L.devs[0];
@@ -1644,10 +1645,10 @@ void gpupot_(int *irank, int *istart, int *ni, int *n, double m[], double x[][3]
     lib_pot(*irank, *istart, *ni, *n, m, &x[0][0], pot);
 }
 
-int gpunb_b200_version(void) { return 101; }
+int gpunb_b200_version(void) { return 102; }
 const char *gpunb_b200_build_info(void)
 {
-    return "gpunb_b200 sm_100a: regf_kernel<f32x2, TMA bulk Morton tiles TJ=64, near/far bodies>, isort, merge(sort), combine (P2P), pot, tilepack";
+    return "gpunb_b200 sm_100a: regf_kernel<TMA bulk Hilbert tiles TJ=64, packed f32x2 FAR body, scalar float-float NEAR body>, isort, merge (register bitonic), combine (NVLink peer pulls + flags), pot, tilepack";
 }
 int gpunb_b200_num_devices(void) { return (int)L.devs.size(); }
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT])
