@@ -43,6 +43,8 @@ UNIT = "Gint/s"
 LMAX, NNBMAX, BLOCK = 600, 550, 1024          # --with-par=1m: LMAX=600 (configure.ac:390-394); NNBMAX=min(N/2,LMAX-50)
 NNB_TARGET = 200.0
 FLOP_PER_INT = 60.0                           # reference convention, gpunb.velocity.cu:894
+NSLOT = int(os.environ.get("GPUNB_B200_NSLOT", "3"))     # pipeline slots of the resident sweep
+NSUB = int(os.environ.get("GPUNB_B200_NSUB", "2"))       # sub-blocks of one gpunb_regf_ call
 
 
 def parse():
@@ -236,6 +238,7 @@ def main():
     ni_total = args.ni_total if args.ni_total > 0 else n
     m, x, v, h2, dtr, rs0 = make_snapshot(n, args.m_flag)
     lib.open(n + 10, rank)
+    lib.set_tuning(NSLOT, NSUB)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
     interactions_scale = 1.0 / world                 # roofline per GPU: each rank's kernel sums nj/world j
 
@@ -266,6 +269,7 @@ def main():
     # per-launch duration of the dominant kernel (regf_kernel): CUDA events around each launch on its stream,
     # taken from a timed pass of ABI calls (the resident sweep does not break the stream to read events)
     lib.reset_counters()
+    lib.set_tuning(0, 1)                             # ONE pair-kernel launch per call for this probe
     nprobe = min(32, (ni_total + BLOCK - 1) // BLOCK)
     for b in range(nprobe):
         i0 = b * BLOCK
@@ -273,6 +277,7 @@ def main():
     c_probe = lib.counters()
     kern_ms = c_probe["grav_ms"] / c_probe["grav_launches"]
     merge_ms = c_probe["merge_ms"] / c_probe["grav_launches"]
+    lib.set_tuning(NSLOT, NSUB)
     int_per_launch = float(BLOCK) * n * interactions_scale
 
     # ---------------- end-to-end leg through the C-ABI with host buffers: `e2e` ----------------
@@ -355,11 +360,13 @@ def main():
         "config": {"workload": f"synthetic Plummer N={n} Kroupa IMF, regular-force sweep", "nj": n, "ni_per_step": ni_total,
                    "block": BLOCK, "lmax": LMAX, "nnbmax": NNBMAX, "m_flag": args.m_flag, "rs_min": rs0, "mean_nnb": mean_nnb,
                    "interactions_per_step": inter_step, "l2": "flushed between timed steps (256 MB fill)",
-                   "parallelism": f"j-shard x{world}"},
+                   "parallelism": f"j-shard x{world}",
+                   "pipeline": {"sweep_slots": NSLOT, "regf_subblocks": NSUB}},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": c_e2e["h2d_bytes"] / e2e_steps,
                 "d2h_bytes_per_step": c_e2e["d2h_bytes"] / e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
-                "api": "gpunb_send_ + gpunb_regf_ (ctypes, pageable caller-owned host arrays)"},
+                "api": "gpunb_send_ + gpunb_regf_ (ctypes, pageable caller-owned host arrays; result rows written by the "
+                       "kernels into mapped pinned memory, d2h = bytes of valid rows)"},
         "gpu_launches": int(launches_res),
         "roofline": roofline,
     }

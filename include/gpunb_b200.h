@@ -93,6 +93,11 @@ float gpunb_b200_sweep_resident(int *i0, int *ni, int *block, int *lmax, int *nn
 void  gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double pot[],
                             int *lmax, int *list);
 
+/* Pipeline depth: nslot = pipeline slots a resident sweep cycles through (1 = one block after the other on one
+ * stream), nsub = sub-blocks one gpunb_regf_ call is split into (1 = the whole i-block in one pair-kernel launch).
+ * Values outside 1..4 leave the setting unchanged.  Environment: GPUNB_B200_NSLOT / GPUNB_B200_NSUB. */
+void  gpunb_b200_set_tuning(int nslot, int nsub);
+
 /* FP32 pipe microbenchmark: returns achieved scalar/packed FFMA TFLOP/s on device 0
  * (mode 0: FFMA, 1: FFMA2 (f32x2), 2: FADD2, 3: FMUL2, 4: MUFU.RSQ Gop/s, 5: FFMA2+ALU mix). */
 double gpunb_b200_fp32_microbench(int mode, int iters);

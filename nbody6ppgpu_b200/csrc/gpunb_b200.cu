@@ -286,7 +286,11 @@ __global__ void __launch_bounds__(128) tilepack_kernel(int n, int t0, int tstrid
 // composite keys (30-bit Morton code << 11 | index) in registers; bitonic strides < 32 are warp shuffles, larger
 // strides go through shared memory.  ~6 us for 1024 particles (the 63-bit Hilbert version took 23 us).
 // ---------------------------------------------------------------------------------------------
-__global__ void iota_kernel(int n, int *__restrict__ p) { const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k < n) p[k] = k; }
+__global__ void iota_kernel(int n, int block, int *__restrict__ p, int *__restrict__ p_host)
+{   // tuning (GPUNB_B200_NOISORT): every i-block in caller order
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { p[k] = k % block; if (p_host) p_host[k] = k % block; }
+}
 __device__ __forceinline__ unsigned spread10(unsigned v)
 {   // 10 bits -> every third bit
     v &= 0x3ffu;
@@ -310,11 +314,18 @@ __device__ __forceinline__ unsigned long long bitonic_pick(unsigned long long v,
     const bool up = (e & size) == 0, lower = (e & stride) == 0;
     return (lower == up) ? (v < o ? v : o) : (v < o ? o : v);
 }
-__global__ void __launch_bounds__(1024) isort_kernel(int ni, const double *__restrict__ xi, const unsigned *__restrict__ hbits,
-                                                      int *__restrict__ iperm)
-{
+__global__ void __launch_bounds__(1024) isort_kernel(int ni_total, int block, const double *__restrict__ xi_all,
+                                                      const unsigned *__restrict__ hbits, int *__restrict__ iperm_all,
+                                                      int *__restrict__ iperm_host)
+{   // CTA b sorts the i-block [b*block, b*block + ni): one launch orders every block of a resident sweep.
+    // iperm holds indices LOCAL to the block.  iperm_host (optional, mapped pinned memory): the same order for the
+    // host side of gpunb_regf_, which receives its result rows in sorted order.
     __shared__ unsigned long long key[NIMAX];
     const int t = threadIdx.x;
+    const int off = blockIdx.x * block;
+    const int ni = min(block, ni_total - off);
+    const double *xi = xi_all + 3 * (size_t)off;
+    int *iperm = iperm_all + off;
     const float sc = 511.5f / fmaxf(__uint_as_float(*hbits), 1e-30f);
     int n2 = 64;
     while (n2 < ni) n2 <<= 1;
@@ -337,8 +348,8 @@ __global__ void __launch_bounds__(1024) isort_kernel(int ni, const double *__res
             }
         }
     }
-    if (t < ni) iperm[t] = (int)(v0 & 2047ull);
-    if (two && t + 1024 < ni) iperm[t + 1024] = (int)(v1 & 2047ull);
+    if (t < ni) { iperm[t] = (int)(v0 & 2047ull); if (iperm_host) iperm_host[off + t] = (int)(v0 & 2047ull); }
+    if (two && t + 1024 < ni) { iperm[t + 1024] = (int)(v1 & 2047ull); if (iperm_host) iperm_host[off + t + 1024] = (int)(v1 & 2047ull); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -350,11 +361,13 @@ struct RegfArgs {
     int           ntiles;
     // i-particles (fp64, device): element i at h2[i], dtr[i], xi[3i..], vi[3i..]
     const double *h2, *dtr, *xi, *vi;
-    const int    *iperm;     // Morton order of the i-block
-    int           ni, n_itiles, S, n_items;
-    double       *part;      // [S][ni][PART_STRIDE]
-    int          *cnt;       // [S][ni]
-    int          *seg;       // [ni][S][segcap]
+    const int    *iperm;     // Morton order of the i-block (indices local to the block)
+    int           slot0, nloc;   // this launch covers the sorted slots [slot0, slot0 + nloc) of the block; everything
+                                 // it writes is indexed by the LOCAL slot kl = slot - slot0 (merge maps kl -> i)
+    int           n_itiles, S, n_items;
+    double       *part;      // [S][nloc][PART_STRIDE]
+    int          *cnt;       // [S][nloc]
+    int          *seg;       // [nloc][S][segcap]
     int           segcap;
     int           force_near;  // debugging/tuning: classify every tile as NEAR
     unsigned long long *stats; // optional: [0] near tiles, [1] all tiles (per warp-tile visit)
@@ -488,14 +501,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
     IState I[IT];
     Acc2   P[IT];             // two chains per quantity (.x even / .y odd j): 32-term FP32 chains
     double D[IT][7];
-    int    cnt[IT], iidx[IT];
+    int    cnt[IT], iidx[IT];     // iidx: local slot kl of the lane's i-particle (-1: padding lane)
     int   *segp[IT];
 #pragma unroll
     for (int k = 0; k < IT; k++) {
-        const int slot = it * ITILE + k * 32 + lane;
-        const bool valid = slot < a.ni;
-        const int i = valid ? a.iperm[slot] : -1;
-        iidx[k] = i;
+        const int kl = it * ITILE + k * 32 + lane;
+        const bool valid = kl < a.nloc;
+        const int i = valid ? a.iperm[a.slot0 + kl] : -1;
+        iidx[k] = valid ? kl : -1;
         double xd[3] = {0, 0, 0}, v[3] = {0, 0, 0}, h2 = 0, dtr = 0;
         if (valid) {
             h2 = a.h2[i]; dtr = a.dtr[i];
@@ -517,7 +530,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
 #pragma unroll
         for (int c = 0; c < 7; c++) D[k][c] = 0.0;
         cnt[k]  = 0;
-        segp[k] = a.seg + ((size_t)(valid ? i : 0) * a.S + s) * a.segcap;
+        segp[k] = a.seg + ((size_t)(valid ? kl : 0) * a.S + s) * a.segcap;
     }
     auto flush = [&]() {
 #pragma unroll
@@ -666,12 +679,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
 
 #pragma unroll
     for (int k = 0; k < IT; k++) {
-        const int i = iidx[k];
-        if (i >= 0) {
-            double *o = a.part + ((size_t)s * a.ni + i) * PART_STRIDE;
+        const int kl = iidx[k];
+        if (kl >= 0) {
+            double *o = a.part + ((size_t)s * a.nloc + kl) * PART_STRIDE;
 #pragma unroll
             for (int c = 0; c < 7; c++) o[c] = D[k][c];
-            a.cnt[(size_t)s * a.ni + i] = cnt[k];
+            a.cnt[(size_t)s * a.nloc + kl] = cnt[k];
         }
     }
     if (a.stats && lane == 0) { atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all); }
@@ -754,90 +767,7 @@ __device__ __noinline__ void warp_sort_smem(int *sb, int n2, int lane)
 //   ascending j (its two-pointer list diff: regcor_gpu.F:299-336).
 //   count > nnbmax  ->  list[0] = -count, no entries written (reg.avx.cpp:320-321).
 // ---------------------------------------------------------------------------------------------
-struct MergeArgs {
-    const double *part; const int *cnt; const int *seg;
-    int ni, S, segcap, lmax, nnbmax;
-    double *res_f;      // [ni][f_stride]; f_stride = 8 stores the (signed) count in slot 7 for the shard combine
-    int     f_stride;
-    int    *res_list;   // [ni][lmax]
-    int     sort;       // 0: leave the row in arrival order (a shard row: combine_kernel sorts the union)
-};
-
-__global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
-{
-    __shared__ int sbuf[4][SORT_CAP];
-    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int i = blockIdx.x * 4 + wq;
-    if (i >= a.ni) return;
-    double f[7] = {0, 0, 0, 0, 0, 0, 0};
-    int total = 0;
-#pragma unroll 4
-    for (int s = lane; s < a.S; s += 32) {             // loads of several rounds in flight
-        const double *p = a.part + ((size_t)s * a.ni + i) * PART_STRIDE;
-#pragma unroll
-        for (int c = 0; c < 7; c++) f[c] += p[c];
-        total += a.cnt[(size_t)s * a.ni + i];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int c = 0; c < 7; c++) f[c] += __shfl_xor_sync(0xffffffffu, f[c], o);
-        total += __shfl_xor_sync(0xffffffffu, total, o);
-    }
-    if (lane < 7) a.res_f[(size_t)i * a.f_stride + lane] = f[lane];   // f[] is uniform after the butterfly
-    if (a.f_stride == 8 && lane == 7) a.res_f[(size_t)i * 8 + 7] = (double)(total > a.nnbmax ? -total : total);
-    int *row = a.res_list + (size_t)i * a.lmax;
-    if (total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
-    if (lane == 0) row[0] = total;
-    if (total == 0) return;
-    int *sb = sbuf[wq];
-    int base = 0;
-    for (int s0 = 0; s0 < a.S; s0 += 32) {
-        const int s = s0 + lane;
-        const int n = (s < a.S) ? a.cnt[(size_t)s * a.ni + i] : 0;
-        int incl = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        const int off = base + incl - n;
-        const int *src = a.seg + ((size_t)i * a.S + s) * a.segcap;
-        for (int k = 0; k < n; k++) sb[off + k] = src[k];
-        base += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (a.sort) {
-        int n2 = 32;
-        while (n2 < total) n2 <<= 1;
-        for (int k = total + lane; k < n2; k += 32) sb[k] = INT_MAX;
-        warp_sort_smem(sb, n2, lane);
-    } else {
-        __syncwarp();
-    }
-    for (int k = lane; k < total; k += 32) row[1 + k] = sb[k];
-}
-
-// ---------------------------------------------------------------------------------------------
-// combine_kernel: j-shard exchange step (multi-GPU).  Every shard r (a GPU holding every R-th tile of the
-// Hilbert-sorted j-set, see shard_tiles) has produced, per i-particle, 7 fp64 partial sums + its signed
-// neighbour count (fr[r][i][8]) and an ascending row of GLOBAL j indices (rows[r][i][lmax]).  One warp per i:
-// fp64 sum over shards in rank order (the reference sums GPUs in fp64 on the host, :823-845), counts scanned in
-// rank order, rows gathered and sorted ascending (the reference's index-range shards only need concatenating,
-// :852-871; spatial shards interleave in j).
-// fr[r] / rows[r] are PEER pointers (NVLink P2P: cudaIpc-mapped across processes, or peer-enabled
-// devices of one process): the kernel pulls only the `count` valid entries of each remote row, so the
-// exchange moves ~4*nnb bytes per i instead of whole rows.  Overflow: any shard negative or
-// total > nnbmax -> -(sum |count_r|) (reg.avx.cpp:320-321 encoding of the true count).
-// ---------------------------------------------------------------------------------------------
 constexpr int MAX_RANKS = 16;
-struct CombineArgs {
-    int ni, R, lmax, nnbmax;
-    const double *fr[MAX_RANKS];     // [ni][8]
-    const int    *rows[MAX_RANKS];   // [ni][lmax]
-    double *res_f;                   // [ni][7]
-    int    *res_list;                // [ni][lmax]
-    // one process per GPU: flags[r] (in THIS rank's exchange buffer) is set to `seq` by rank r, over NVLink, once
-    // its fr/rows of this call are complete (signal_kernel).  NULL: ordering is done with stream events.
-    const unsigned long long *flags;
-    unsigned long long seq;
-};
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
@@ -860,39 +790,150 @@ __device__ __forceinline__ int peer_ld(const int *p)
     int v; asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
 
-// Tells every peer that this rank's shard results of call `seq` are in its exchange buffer (launched after
-// merge_kernel on the same stream).  Thread r stores into rank r's flag slot for this rank, over NVLink.
-struct PeerFlags { unsigned long long *p[MAX_RANKS]; };
-__global__ void signal_kernel(const PeerFlags pf, int R, int rank, unsigned long long seq)
-{
-    if ((int)threadIdx.x < R) {
+// In-kernel publication to the peers (one process per GPU; see run_job).  The LAST CTA of a launch to finish
+// stores `seq` into this rank's entry of every peer's flag (merge: "my shard rows of call seq are complete") or ack
+// (combine: "I have finished reading everybody's rows of call seq") array over NVLink -- no extra launch.
+struct ExchSignal {
+    unsigned *done_ctr;                        // device-local count of finished CTAs (reset by the last one); NULL: off
+    unsigned long long *peer[MAX_RANKS];       // &array_of_peer_r[this rank]
+    int R;
+    unsigned long long seq;
+};
+__device__ __forceinline__ void publish_when_last(const ExchSignal &g)
+{   // called by EVERY thread of EVERY CTA, after its last global write / peer read
+    if (!g.done_ctr) return;
+    __shared__ int is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(g.done_ctr, 1u);
+        is_last = (prev == gridDim.x - 1);
+        if (is_last) { *g.done_ctr = 0; __threadfence(); }
+    }
+    __syncthreads();
+    if (is_last && (int)threadIdx.x < g.R) {
         __threadfence_system();
-        st_release_sys(pf.p[threadIdx.x] + rank, seq);
+        st_release_sys(g.peer[threadIdx.x], g.seq);
     }
 }
+__device__ __forceinline__ void wait_all_ranks(const unsigned long long *flags, int R, long long need, int lane)
+{   // every warp for itself: lanes < R spin on the R entries of a flag array in LOCAL memory (written by the peers)
+    if (lane < R) while ((long long)ld_acquire_sys(flags + lane) < need) { }
+    __syncwarp();
+}
 
-__global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
+struct MergeArgs {
+    const double *part; const int *cnt; const int *seg;
+    int nloc, S, segcap, lmax, nnbmax;
+    const int *iperm;   // output row of local slot kl: i = iperm[kl] (the caller passes iperm + slot0); NULL: i = kl
+    double *res_f;      // [.][f_stride]; f_stride = 8 stores the (signed) count in slot 7 for the shard combine
+    int     f_stride;
+    int    *res_list;   // [.][lmax]
+    int     sort;       // 0: leave the row in arrival order (a shard row: combine_kernel sorts the union)
+    // exchange slot reuse (one process per GPU): wait until every peer has acknowledged reading the previous
+    // contents (acks[r] >= ack_need) before overwriting res_f / res_list.  NULL: no wait.
+    const unsigned long long *acks; long long ack_need; int R;
+    ExchSignal sig;
+};
+
+__device__ __forceinline__ void merge_row(const MergeArgs &a, int kl, int lane, int *sb)
 {
-    __shared__ int sbuf[4][SORT_CAP];
-    __shared__ int soff[4][MAX_RANKS], scnt[4][MAX_RANKS];
-    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int i = blockIdx.x * 4 + wq;
-    if (i >= a.ni) return;
-    if (a.flags) {                                     // wait until every shard has published this call
-        if (lane < a.R) while (ld_acquire_sys(a.flags + lane) < a.seq) { }
+    double f[7] = {0, 0, 0, 0, 0, 0, 0};
+    int total = 0;
+#pragma unroll 4
+    for (int s = lane; s < a.S; s += 32) {             // loads of several rounds in flight
+        const double *p = a.part + ((size_t)s * a.nloc + kl) * PART_STRIDE;
+#pragma unroll
+        for (int c = 0; c < 7; c++) f[c] += p[c];
+        total += a.cnt[(size_t)s * a.nloc + kl];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) f[c] += __shfl_xor_sync(0xffffffffu, f[c], o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    const int i = a.iperm ? a.iperm[kl] : kl;
+    if (lane < 7) a.res_f[(size_t)i * a.f_stride + lane] = f[lane];   // f[] is uniform after the butterfly
+    if (a.f_stride == 8 && lane == 7) a.res_f[(size_t)i * 8 + 7] = (double)(total > a.nnbmax ? -total : total);
+    int *row = a.res_list + (size_t)i * a.lmax;
+    if (total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
+    if (lane == 0) row[0] = total;
+    if (total == 0) return;
+    int base = 0;
+    for (int s0 = 0; s0 < a.S; s0 += 32) {
+        const int s = s0 + lane;
+        const int n = (s < a.S) ? a.cnt[(size_t)s * a.nloc + kl] : 0;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const int off = base + incl - n;
+        const int *src = a.seg + ((size_t)kl * a.S + s) * a.segcap;
+        for (int k = 0; k < n; k++) sb[off + k] = src[k];
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (a.sort) {
+        int n2 = 32;
+        while (n2 < total) n2 <<= 1;
+        for (int k = total + lane; k < n2; k += 32) sb[k] = INT_MAX;
+        warp_sort_smem(sb, n2, lane);
+    } else {
         __syncwarp();
     }
+    for (int k = lane; k < total; k += 32) row[1 + k] = sb[k];
+}
+
+__global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
+{
+    __shared__ int sbuf[4][SORT_CAP];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int kl = blockIdx.x * 4 + wq;
+    if (kl < a.nloc) {
+        if (a.acks) wait_all_ranks(a.acks, a.R, a.ack_need, lane);
+        merge_row(a, kl, lane, sbuf[wq]);
+    }
+    publish_when_last(a.sig);
+}
+
+// ---------------------------------------------------------------------------------------------
+// combine_kernel: j-shard exchange step (multi-GPU).  Every shard r (a GPU holding every R-th tile of the
+// Hilbert-sorted j-set, see shard_tiles) has produced, per i-particle, 7 fp64 partial sums + its signed
+// neighbour count (fr[r][.][8]) and a row of GLOBAL j indices (rows[r][.][lmax]).  One warp per i:
+// fp64 sum over shards in rank order (the reference sums GPUs in fp64 on the host, :823-845), counts scanned in
+// rank order, rows gathered and sorted ascending (the reference's index-range shards only need concatenating,
+// :852-871; spatial shards interleave in j).
+// fr[r] / rows[r] are PEER pointers (NVLink P2P: cudaIpc-mapped across processes, or peer-enabled
+// devices of one process): the kernel pulls only the `count` valid entries of each remote row, so the
+// exchange moves ~4*nnb bytes per i instead of whole rows.  Overflow: any shard negative or
+// total > nnbmax -> -(sum |count_r|) (reg.avx.cpp:320-321 encoding of the true count).
+// Shard records are indexed by the local sorted slot kl (every rank computes the same order); the combined row goes
+// to output row iperm[kl].
+// ---------------------------------------------------------------------------------------------
+struct CombineArgs {
+    int nloc, R, lmax, nnbmax;
+    const double *fr[MAX_RANKS];     // [nloc][8]
+    const int    *rows[MAX_RANKS];   // [nloc][lmax]
+    const int    *iperm;             // output row of kl (NULL: kl)
+    double *res_f;                   // [.][7]
+    int    *res_list;                // [.][lmax]
+    // one process per GPU: flags[r] (in THIS rank's exchange buffer) is set to `seq` by rank r, over NVLink, once
+    // its fr/rows of this call are complete (last CTA of its merge_kernel).  NULL: ordering is done with stream events.
+    const unsigned long long *flags;
+    unsigned long long seq;
+    ExchSignal ack;                  // tells every peer that this rank is done reading call `seq`
+};
+
+__device__ __forceinline__ void combine_row(const CombineArgs &a, int kl, int lane, int *sb, int *offs, int *cnts)
+{
     // records are requested four shards at a time before any is used: R/4 NVLink round trips, not R
     double f = 0.0;
     int total = 0;
     bool over = false;
-    int *sb = sbuf[wq];
-    int *offs = soff[wq], *cnts = scnt[wq];           // per-shard offsets / counts of this i
     for (int r0 = 0; r0 < a.R; r0 += 4) {
         double v[4];
 #pragma unroll
         for (int q = 0; q < 4; q++)
-            v[q] = (r0 + q < a.R && lane < 8) ? peer_ld(a.fr[r0 + q] + (size_t)i * 8 + lane) : 0.0;
+            v[q] = (r0 + q < a.R && lane < 8) ? peer_ld(a.fr[r0 + q] + (size_t)kl * 8 + lane) : 0.0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (r0 + q < a.R) {
@@ -905,6 +946,7 @@ __global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
             }
         }
     }
+    const int i = a.iperm ? a.iperm[kl] : kl;
     if (lane < 7) a.res_f[(size_t)i * 7 + lane] = f;
     int *row = a.res_list + (size_t)i * a.lmax;
     if (over || total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
@@ -916,7 +958,7 @@ __global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
         int r = 0, o = offs[0], c = cnts[0];
         for (int e = lane; e < total; e += 32) {
             while (e >= o + c) { r++; o = offs[r]; c = cnts[r]; }
-            sb[e] = peer_ld(a.rows[r] + (size_t)i * a.lmax + 1 + (e - o));
+            sb[e] = peer_ld(a.rows[r] + (size_t)kl * a.lmax + 1 + (e - o));
         }
     }
     __syncwarp();
@@ -925,6 +967,19 @@ __global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
     for (int k = total + lane; k < n2; k += 32) sb[k] = INT_MAX;
     warp_sort_smem(sb, n2, lane);
     for (int k = lane; k < total; k += 32) row[1 + k] = sb[k];
+}
+
+__global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
+{
+    __shared__ int sbuf[4][SORT_CAP];
+    __shared__ int soff[4][MAX_RANKS], scnt[4][MAX_RANKS];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int kl = blockIdx.x * 4 + wq;
+    if (kl < a.nloc) {
+        if (a.flags) wait_all_ranks(a.flags, a.R, (long long)a.seq, lane);    // every shard has published this call
+        combine_row(a, kl, lane, sbuf[wq], soff[wq], scnt[wq]);
+    }
+    publish_when_last(a.ack);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1015,9 +1070,30 @@ constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
 constexpr int DEFAULT_VARIANT = 4;     // it1b4: 4 CTAs/SM (<= 128 registers), fastest at every ni (profiles/r01e_variants.txt)
 constexpr int ROWS_LMAX_CAP = 1024;    // row stride capacity of the IPC-exported shard rows (NCCL mode)
 
+// Pipeline slot: the work buffers one i-block (or sub-block) needs from the pair kernel to the merged result, and the
+// two streams it runs on.  Consecutive blocks go to different slots so that the pair kernel of block b+1 (low
+// priority stream `lo`) fills the SMs as the CTAs of block b retire, while merge / exchange of block b (high
+// priority stream `hi`, latency-bound kernels) run beside it.
+constexpr int MAX_SLOTS = 4;
+constexpr int DEFAULT_NSLOT = 3;       // slots a resident sweep cycles through (GPUNB_B200_NSLOT)
+constexpr int DEFAULT_NSUB  = 2;       // sub-blocks of one gpunb_regf_ call (GPUNB_B200_NSUB)
+struct Slot {
+    cudaStream_t lo = nullptr, hi = nullptr;
+    cudaEvent_t ev_regf = nullptr, ev_done = nullptr;
+    bool used = false;                 // ev_done has been recorded at least once
+    int items_cap = 0;
+    double *part = nullptr; int *cnt = nullptr;
+    int *seg = nullptr; size_t seg_ints = 0;
+    double *res_f = nullptr; int *res_list = nullptr; size_t res_list_ints = 0;   // device-resident results (sweeps)
+    unsigned *done_ctr = nullptr;      // [2]: finished-CTA counters of merge / combine (in-kernel publication)
+};
+
 struct Dev {
     int id = -1;
     cudaStream_t st = nullptr;
+    Slot slots[MAX_SLOTS];
+    cudaEvent_t ev_fork = nullptr;
+    int *iperm_all = nullptr; size_t iperm_all_n = 0;   // Morton order of every block of a resident sweep
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs0 = nullptr, evs1 = nullptr, evdone = nullptr;
     int nsm = 0, warps_resident = 0, variant = DEFAULT_VARIANT, itile = 32, oversub = OVERSUB;
     // j: full fp64 snapshot (m | x | v, packed for the current nj_total) and the tiles of this device's shard
@@ -1036,10 +1112,7 @@ struct Dev {
     unsigned long long *stats = nullptr;   // [0] near (warp,tile) visits, [1] all visits (GPUNB_B200_STATS=1)
     unsigned long long *wtime = nullptr;   // per work item start/end timestamps (GPUNB_B200_STATS=2)
     double *ibuf = nullptr;       // 8*NIMAX doubles: h2 | dtr | x | v
-    int items_cap = 0;
-    double *part = nullptr; int *cnt = nullptr;
-    int *seg = nullptr; int segcap = 0; size_t seg_ints = 0;
-    double *res_f = nullptr; int *res_list = nullptr; size_t res_list_ints = 0;   // final results (root)
+    int segcap = 0;
     double *fr = nullptr;         // [NIMAX][8] shard partial + count (multi-GPU)
     int *rows = nullptr; size_t rows_ints = 0;                                     // shard rows (in-process multi-GPU)
     int *nanflag = nullptr;
@@ -1064,12 +1137,12 @@ struct Shard {                     // one process per GPU, j sharded over ranks
     pfn_ncclCommDestroy destroy = nullptr; pfn_ncclGetErrorString errstr = nullptr;
     ncclComm_t comm = nullptr;
     // Exchange buffer of this rank (one allocation, exported with cudaIpc, mapped by every peer):
-    //   [2 parities] x { fr[NIMAX][8] doubles | rows[NIMAX][ROWS_LMAX_CAP] ints }  |  flags[MAX_RANKS] u64
+    //   [XSLOTS] x { fr[NIMAX][8] doubles | rows[NIMAX][ROWS_LMAX_CAP] ints }  |  flags[XSLOTS][MAX_RANKS] u64
+    //   | acks[XSLOTS][MAX_RANKS] u64
     unsigned char *xbuf = nullptr;
     unsigned char *xbuf_peer[MAX_RANKS] = {nullptr};
-    unsigned long long seq = 0;    // regf calls so far (every rank makes the same calls)
+    unsigned long long seq = 0;    // exchange steps so far (every rank makes the same calls)
     double *scratch = nullptr;     // bootstrap / finalize all-gathers
-    int parity = 0;
 };
 
 struct Lib {
@@ -1078,9 +1151,15 @@ struct Lib {
     Shard sh;
     int nbmax = 0, nbody = 0;
     double *h_j = nullptr; size_t h_j_n = 0;          // pinned staging: 7*nj doubles
-    double *h_i = nullptr, *h_f = nullptr;            // 8*NIMAX, 7*NIMAX doubles
-    int *h_list = nullptr; size_t h_list_n = 0;
+    double *h_i = nullptr;                            // 8*NIMAX doubles (pinned staging of the i-block)
+    // results of gpunb_regf_: MAPPED pinned host memory that merge / combine write straight over PCIe (zero copy),
+    // and the device-side aliases of those buffers
+    double *h_f = nullptr, *h_f_dev = nullptr;        // [NIMAX][7]
+    int *h_list = nullptr, *h_list_dev = nullptr; size_t h_list_n = 0;
+    int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
+    int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB;
+    int last_slot = 0; bool last_on_host = false;
     double time_send = 0, time_grav = 0, time_reduce = 0, time_out = 0;      // reference: gpunb.velocity.cu:557-559
     long long numInter = 0; int icall = 0, ini = 0, isend = 0;
     double ctr[GPUNB_B200_CTR_COUNT] = {0};
@@ -1130,6 +1209,15 @@ void lib_devinit(int irank)
         cudaEvent_t *evs[] = {&d.ev0, &d.ev1, &d.ev2, &d.ev3, &d.evs0, &d.evs1};
         for (cudaEvent_t *ev : evs) CUDA_CHECK(cudaEventCreate(ev));
         CUDA_CHECK(cudaEventCreateWithFlags(&d.evdone, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
+        int prio_least = 0, prio_greatest = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        for (Slot &sl : d.slots) {
+            CUDA_CHECK(cudaStreamCreateWithPriority(&sl.lo, cudaStreamNonBlocking, prio_least));
+            CUDA_CHECK(cudaStreamCreateWithPriority(&sl.hi, cudaStreamNonBlocking, prio_greatest));
+            CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_regf, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        }
         const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
         const char *vn = getenv("GPUNB_B200_VARIANT");
         if (vn && *vn) {
@@ -1167,6 +1255,8 @@ void lib_devinit(int irank)
     CUDA_CHECK(cudaSetDevice(L.devs[0].id));
     host_alloc(L.h_flag, 16);
     memset(L.h_flag, 0, 16 * sizeof(int));
+    { const char *e = getenv("GPUNB_B200_NSLOT"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nslot = atoi(e); }
+    { const char *e = getenv("GPUNB_B200_NSUB");  if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nsub = atoi(e); }
     L.devinit = true;
 }
 
@@ -1238,44 +1328,59 @@ void build_tiles(Dev &d, int n, const double *m, const double *x, const double *
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 4;       // + the CUB sort passes (library code, not counted)
 }
 
-void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root)
+template <class T> void host_alloc_mapped(T *&h, T *&dptr, size_t n)
+{
+    CUDA_CHECK(cudaHostAlloc((void **)&h, n * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable));
+    CUDA_CHECK(cudaHostGetDevicePointer((void **)&dptr, (void *)h, 0));
+}
+
+// Work buffers of the first `nslots` pipeline slots of device d, and (root) the mapped host result buffers.
+void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root, int nslots, bool device_results)
 {
     set_dev(d);
     // n_itiles * S never exceeds warps_resident (+ n_itiles when S = 1)
     const int items = d.warps_resident * d.oversub + NIMAX / d.itile;
     const int segcap = ((nnbmax > 0 ? nnbmax : 1) + 3) & ~3;
-    if (items > d.items_cap) {
-        CUDA_CHECK(cudaStreamSynchronize(d.st));
-        dev_free(d.part); dev_free(d.cnt);
-        d.items_cap = items;
-        dev_alloc(d.part, (size_t)items * d.itile * PART_STRIDE);
-        dev_alloc(d.cnt, (size_t)items * d.itile);
-    }
-    const size_t seg_need = (size_t)d.items_cap * d.itile * segcap;
-    if (seg_need > d.seg_ints) {
-        CUDA_CHECK(cudaStreamSynchronize(d.st));
-        dev_free(d.seg);
-        d.seg_ints = seg_need;
-        dev_alloc(d.seg, seg_need);
+    const size_t rl = (size_t)NIMAX * lmax;
+    for (int q = 0; q < nslots; q++) {
+        Slot &sl = d.slots[q];
+        if (items > sl.items_cap) {
+            CUDA_CHECK(cudaDeviceSynchronize());
+            dev_free(sl.part); dev_free(sl.cnt);
+            sl.items_cap = items;
+            dev_alloc(sl.part, (size_t)items * d.itile * PART_STRIDE);
+            dev_alloc(sl.cnt, (size_t)items * d.itile);
+        }
+        const size_t seg_need = (size_t)sl.items_cap * d.itile * segcap;
+        if (seg_need > sl.seg_ints) {
+            CUDA_CHECK(cudaDeviceSynchronize());
+            dev_free(sl.seg);
+            sl.seg_ints = seg_need;
+            dev_alloc(sl.seg, seg_need);
+        }
+        if (!sl.done_ctr) { dev_alloc(sl.done_ctr, 2); CUDA_CHECK(cudaMemset(sl.done_ctr, 0, 2 * sizeof(unsigned))); }
+        if (is_root && device_results) {
+            if (!sl.res_f) dev_alloc(sl.res_f, (size_t)7 * NIMAX);
+            if (rl > sl.res_list_ints) {
+                CUDA_CHECK(cudaDeviceSynchronize());
+                dev_free(sl.res_list);
+                sl.res_list_ints = rl;
+                dev_alloc(sl.res_list, rl);
+            }
+        }
     }
     d.segcap = segcap;
-    const size_t rl = (size_t)NIMAX * lmax;
-    if (is_root && rl > d.res_list_ints) {
-        CUDA_CHECK(cudaStreamSynchronize(d.st));
-        dev_free(d.res_list);
-        d.res_list_ints = rl;
-        dev_alloc(d.res_list, rl);
-    }
     if (L.devs.size() > 1 && rl > d.rows_ints) {
-        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        CUDA_CHECK(cudaDeviceSynchronize());
         dev_free(d.rows);
         d.rows_ints = rl;
         dev_alloc(d.rows, rl);
     }
     if (is_root && rl > L.h_list_n) {
+        CUDA_CHECK(cudaDeviceSynchronize());
         host_free(L.h_list);
         L.h_list_n = rl;
-        host_alloc(L.h_list, rl);
+        host_alloc_mapped(L.h_list, L.h_list_dev, rl);
     }
     if (L.sh.on && lmax > ROWS_LMAX_CAP) FATAL("lmax=%d exceeds the shard-row capacity %d of the NCCL mode", lmax, ROWS_LMAX_CAP);
 }
@@ -1293,7 +1398,6 @@ void lib_open(int nbmax, int irank)
         set_dev(d);
         ensure_j_capacity(d, nbmax, nbmax / R + TJ);
         if (!d.ibuf)    dev_alloc(d.ibuf, (size_t)8 * NIMAX);
-        if (!d.res_f)   dev_alloc(d.res_f, (size_t)7 * NIMAX);
         if (!d.fr)      dev_alloc(d.fr, (size_t)8 * NIMAX);
         if (!d.iperm)   dev_alloc(d.iperm, (size_t)NIMAX);
         if (!d.stats && getenv("GPUNB_B200_STATS")) { dev_alloc(d.stats, 2); CUDA_CHECK(cudaMemsetAsync(d.stats, 0, 16, d.st)); }
@@ -1303,7 +1407,8 @@ void lib_open(int nbmax, int irank)
     const size_t hj = (size_t)7 * ((size_t)nbmax + 64);
     if (hj > L.h_j_n) { host_free(L.h_j); L.h_j_n = hj; host_alloc(L.h_j, hj); }
     if (!L.h_i) host_alloc(L.h_i, (size_t)8 * NIMAX);
-    if (!L.h_f) host_alloc(L.h_f, (size_t)7 * NIMAX);
+    if (!L.h_f) host_alloc_mapped(L.h_f, L.h_f_dev, (size_t)7 * NIMAX);
+    if (!L.h_iperm) host_alloc_mapped(L.h_iperm, L.h_iperm_dev, (size_t)NIMAX);
     fprintf(stderr, "# Open GPU regular force - rank: %d; nbmax: %d\n", irank, nbmax);
 }
 
@@ -1313,15 +1418,21 @@ void lib_close()
     L.is_open = false;
     for (Dev &d : L.devs) {
         set_dev(d);
-        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        CUDA_CHECK(cudaDeviceSynchronize());
         dev_free(d.jraw); dev_free(d.jtile); dev_free(d.radii); d.raw_cap = d.tile_cap = 0; d.nj = d.ntiles = d.nj_total = 0;
-        dev_free(d.ibuf); dev_free(d.part); dev_free(d.cnt); d.items_cap = 0;
-        dev_free(d.seg); d.seg_ints = 0; dev_free(d.res_f); dev_free(d.res_list); d.res_list_ints = 0;
+        dev_free(d.ibuf);
+        for (Slot &sl : d.slots) {
+            dev_free(sl.part); dev_free(sl.cnt); sl.items_cap = 0;
+            dev_free(sl.seg); sl.seg_ints = 0; dev_free(sl.res_f); dev_free(sl.res_list); sl.res_list_ints = 0;
+            dev_free(sl.done_ctr); sl.used = false;
+        }
+        dev_free(d.iperm_all); d.iperm_all_n = 0;
         dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.stats); dev_free(d.wtime);
         dev_free(d.jidx);
         dev_free(d.nanflag);
     }
     host_free(L.h_j); L.h_j_n = 0; host_free(L.h_i); host_free(L.h_f); host_free(L.h_list); L.h_list_n = 0;
+    host_free(L.h_iperm);
     L.nbmax = 0;
 }
 
@@ -1362,10 +1473,10 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
 }
 
 struct Plan { int n_itiles, S, n_items; };
-Plan make_plan(const Dev &d, int ni)
+Plan make_plan(const Dev &d, int nloc)
 {
     Plan p;
-    p.n_itiles = (ni + d.itile - 1) / d.itile;
+    p.n_itiles = (nloc + d.itile - 1) / d.itile;
     int S = (d.warps_resident * d.oversub) / p.n_itiles;
     if (S < 1) S = 1;
     if (S > d.ntiles) S = d.ntiles > 0 ? d.ntiles : 1;
@@ -1376,122 +1487,158 @@ Plan make_plan(const Dev &d, int ni)
 
 struct IBlock { const double *h2, *dtr, *xi, *vi; };
 
-// exchange-buffer layout (NCCL mode)
+// exchange-buffer layout (one process per GPU).  XSLOTS exchange slots are used round robin by call number, so that
+// several i-blocks can be in flight (pipelined sweeps); a slot is overwritten only after every peer has acknowledged
+// reading its previous contents (acks, checked inside merge_kernel).
+constexpr int    XSLOTS        = 8;
 constexpr size_t XB_FR_BYTES   = (size_t)NIMAX * 8 * sizeof(double);
 constexpr size_t XB_ROWS_BYTES = (size_t)NIMAX * 1024 /*ROWS_LMAX_CAP*/ * sizeof(int);
-constexpr size_t XB_PARITY     = XB_FR_BYTES + XB_ROWS_BYTES;
-constexpr size_t XB_FLAGS_OFF  = 2 * XB_PARITY;
-constexpr size_t XB_BYTES      = XB_FLAGS_OFF + 16 /*MAX_RANKS*/ * sizeof(unsigned long long);
-inline double *xb_fr(unsigned char *b, int parity)   { return reinterpret_cast<double *>(b + parity * XB_PARITY); }
-inline int    *xb_rows(unsigned char *b, int parity) { return reinterpret_cast<int *>(b + parity * XB_PARITY + XB_FR_BYTES); }
-inline unsigned long long *xb_flags(unsigned char *b) { return reinterpret_cast<unsigned long long *>(b + XB_FLAGS_OFF); }
+constexpr size_t XB_SLOT       = XB_FR_BYTES + XB_ROWS_BYTES;
+constexpr size_t XB_FLAGS_OFF  = XSLOTS * XB_SLOT;
+constexpr size_t XB_ACKS_OFF   = XB_FLAGS_OFF + (size_t)XSLOTS * 16 /*MAX_RANKS*/ * sizeof(unsigned long long);
+constexpr size_t XB_BYTES      = XB_ACKS_OFF + (size_t)XSLOTS * 16 /*MAX_RANKS*/ * sizeof(unsigned long long);
+inline double *xb_fr(unsigned char *b, int xs)   { return reinterpret_cast<double *>(b + xs * XB_SLOT); }
+inline int    *xb_rows(unsigned char *b, int xs) { return reinterpret_cast<int *>(b + xs * XB_SLOT + XB_FR_BYTES); }
+inline unsigned long long *xb_flags(unsigned char *b, int xs) { return reinterpret_cast<unsigned long long *>(b + XB_FLAGS_OFF) + xs * 16; }
+inline unsigned long long *xb_acks(unsigned char *b, int xs)  { return reinterpret_cast<unsigned long long *>(b + XB_ACKS_OFF) + xs * 16; }
 
-// Pair kernel + shard-local merge for one i-block on device d (async on d.st).
-void launch_regf(Dev &d, int ni, const IBlock &ib, int lmax, int nnbmax, int m_flag, bool time_it,
-                 double *out_f, int f_stride, int *out_rows, bool sort_rows, cudaEvent_t *tl = nullptr)
-{   // tl (optional): 5 events; [0] before isort, [1] after isort, [2] after regf, [3] after merge ([4]: regf_block)
-    const Plan p = make_plan(d, ni);
+void launch_isort(Dev &d, cudaStream_t st, int ni_total, int block, const double *xi, int *iperm, int *iperm_host)
+{
+    static int noisort = -1;
+    if (noisort < 0) { const char *e = getenv("GPUNB_B200_NOISORT"); noisort = (e && atoi(e) > 0) ? 1 : 0; }
+    const int nblocks = (ni_total + block - 1) / block;
+    if (noisort) iota_kernel<<<(ni_total + 255) / 256, 256, 0, st>>>(ni_total, block, iperm, iperm_host);
+    else isort_kernel<<<nblocks, 1024, 0, st>>>(ni_total, block, xi, d.hbits, iperm, iperm_host);
+    CUDA_CHECK(cudaGetLastError());
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+}
+
+// What one launch group works on: the sorted slots [slot0, slot0 + nloc) of an i-block whose Morton order is iperm.
+struct Job {
+    int slot0, nloc;
+    int lmax, nnbmax, m_flag;
+    double *out_f; int *out_list;      // final results, row i = iperm[slot] (device memory or mapped host memory)
+};
+
+// Pair kernel (stream lo) + shard-local merge (stream hi) of one job on device d, pipeline slot sl.
+void launch_regf(Dev &d, Slot &sl, cudaStream_t lo, cudaStream_t hi, const Job &j, const IBlock &ib, const int *iperm,
+                 MergeArgs m, bool time_it, cudaEvent_t *tl)
+{   // tl (optional): [2] after regf, [3] after merge.  m arrives with its outputs / exchange fields set.
+    const Plan p = make_plan(d, j.nloc);
     RegfArgs a;
-    a.tiles = d.jtile; a.jidx = d.jidx; a.ntiles = d.ntiles; a.iperm = d.iperm;
+    a.tiles = d.jtile; a.jidx = d.jidx; a.ntiles = d.ntiles; a.iperm = iperm;
     { static int fn = -1; if (fn < 0) { const char *e = getenv("GPUNB_B200_FORCE_NEAR"); fn = e ? atoi(e) : 0; } a.force_near = fn; }
     a.stats = d.stats; a.wtime = d.wtime;
     a.h2 = ib.h2; a.dtr = ib.dtr; a.xi = ib.xi; a.vi = ib.vi;
-    a.ni = ni; a.n_itiles = p.n_itiles; a.S = p.S; a.n_items = p.n_items;
-    a.part = d.part; a.cnt = d.cnt; a.seg = d.seg; a.segcap = d.segcap;
+    a.slot0 = j.slot0; a.nloc = j.nloc; a.n_itiles = p.n_itiles; a.S = p.S; a.n_items = p.n_items;
+    a.part = sl.part; a.cnt = sl.cnt; a.seg = sl.seg; a.segcap = d.segcap;
     const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
     const int blocks = (p.n_items + WARPS - 1) / WARPS;
-    if (tl) CUDA_CHECK(cudaEventRecord(tl[0], d.st));
-    static int noisort = -1;
-    if (noisort < 0) { const char *e = getenv("GPUNB_B200_NOISORT"); noisort = (e && atoi(e) > 0) ? 1 : 0; }
-    if (noisort) iota_kernel<<<(ni + 255) / 256, 256, 0, d.st>>>(ni, d.iperm);     // tuning: i-block in caller order
-    else isort_kernel<<<1, 1024, 0, d.st>>>(ni, ib.xi, d.hbits, d.iperm);
-    if (tl) CUDA_CHECK(cudaEventRecord(tl[1], d.st));
-    if (time_it) CUDA_CHECK(cudaEventRecord(d.ev0, d.st));
-    VARIANTS[d.variant].k[m_flag ? 1 : 0]<<<blocks, WARPS * 32, smem, d.st>>>(a);
+    if (time_it) CUDA_CHECK(cudaEventRecord(d.ev0, lo));
+    VARIANTS[d.variant].k[j.m_flag ? 1 : 0]<<<blocks, WARPS * 32, smem, lo>>>(a);
     CUDA_CHECK(cudaGetLastError());
-    if (time_it) CUDA_CHECK(cudaEventRecord(d.ev1, d.st));
-    if (tl) CUDA_CHECK(cudaEventRecord(tl[2], d.st));
-    MergeArgs m;
-    m.part = d.part; m.cnt = d.cnt; m.seg = d.seg; m.ni = ni; m.S = p.S; m.segcap = d.segcap;
-    m.lmax = lmax; m.nnbmax = nnbmax; m.res_f = out_f; m.f_stride = f_stride; m.res_list = out_rows; m.sort = sort_rows ? 1 : 0;
-    merge_kernel<<<(ni + 3) / 4, 128, 0, d.st>>>(m);
+    if (time_it) CUDA_CHECK(cudaEventRecord(d.ev1, lo));
+    if (tl) CUDA_CHECK(cudaEventRecord(tl[2], lo));
+    if (lo != hi) {
+        CUDA_CHECK(cudaEventRecord(sl.ev_regf, lo));
+        CUDA_CHECK(cudaStreamWaitEvent(hi, sl.ev_regf, 0));
+    }
+    m.part = sl.part; m.cnt = sl.cnt; m.seg = sl.seg; m.nloc = j.nloc; m.S = p.S; m.segcap = d.segcap;
+    m.lmax = j.lmax; m.nnbmax = j.nnbmax;
+    merge_kernel<<<(j.nloc + 3) / 4, 128, 0, hi>>>(m);
     CUDA_CHECK(cudaGetLastError());
-    if (time_it) CUDA_CHECK(cudaEventRecord(d.ev2, d.st));
-    if (tl) CUDA_CHECK(cudaEventRecord(tl[3], d.st));
-    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 3;
+    if (time_it) CUDA_CHECK(cudaEventRecord(d.ev2, hi));
+    if (tl) CUDA_CHECK(cudaEventRecord(tl[3], hi));
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
 }
 
-// One i-block on all shards + the exchange step.  ib[g] are DEVICE pointers valid on local device g.
-// On return (asynchronously, on the root stream) root.res_f / root.res_list hold the combined result.
-void regf_block(int ni, const IBlock *ib, int lmax, int nnbmax, int m_flag, bool time_it, cudaEvent_t *tl = nullptr)
+MergeArgs merge_defaults()
+{
+    MergeArgs m;
+    memset(&m, 0, sizeof(m));
+    return m;
+}
+
+// One job on all shards + the exchange step, in pipeline slot q.  ib[g] / iperm[g] are DEVICE pointers valid on local
+// device g.  own_streams: the job runs on the slot's own (lo, hi) stream pair and slot.ev_done marks its end;
+// otherwise everything is queued on the device's main stream.  On completion j.out_f / j.out_list hold the combined
+// result rows of the job's i-particles.
+void run_job(const Job &j, const IBlock *ib, const int *const *iperm, int q, bool own_streams, bool time_it,
+             cudaEvent_t *tl = nullptr)
 {
     const int G = (int)L.devs.size();
     Dev &root = L.devs[0];
+    Slot &sl = root.slots[q];
+    set_dev(root);
+    cudaStream_t lo = own_streams ? sl.lo : root.st, hi = own_streams ? sl.hi : root.st;
     if (!L.sh.on && G == 1) {          // single GPU: the shard-local merge IS the final result
-        set_dev(root);
-        launch_regf(root, ni, ib[0], lmax, nnbmax, m_flag, time_it, root.res_f, 7, root.res_list, true, tl);
-        if (time_it) CUDA_CHECK(cudaEventRecord(root.ev3, root.st));
-        if (tl) CUDA_CHECK(cudaEventRecord(tl[4], root.st));
-        return;
-    }
-    CombineArgs c;
-    c.ni = ni; c.lmax = lmax; c.nnbmax = nnbmax; c.res_f = root.res_f; c.res_list = root.res_list;
-    c.flags = nullptr; c.seq = 0;
-    if (L.sh.on) {
-        // One process per GPU.  No collective call in the data path: every rank writes its shard result into its
-        // own exchange buffer, raises a flag in every peer's buffer over NVLink (signal_kernel), and
-        // combine_kernel -- after seeing all R flags of this call -- pulls partial sums and the valid part of the
-        // neighbour rows straight from the peers' HBM.  Buffers alternate by call parity: a rank can only be
-        // overwriting parity p of call k+2 after its combine of call k+1 has seen every peer's flag k+1, which
-        // each peer raises after its own combine of call k.
-        Shard &sh = L.sh;
-        set_dev(root);
-        const unsigned long long seq = ++sh.seq;
-        const int parity = (int)(seq & 1ull);
-        launch_regf(root, ni, ib[0], lmax, nnbmax, m_flag, time_it, xb_fr(sh.xbuf, parity), 8, xb_rows(sh.xbuf, parity), false, tl);
-        PeerFlags pf;
-        for (int r = 0; r < MAX_RANKS; r++) pf.p[r] = r < sh.R ? xb_flags(sh.xbuf_peer[r]) : nullptr;
-        signal_kernel<<<1, 32, 0, root.st>>>(pf, sh.R, sh.rank, seq);
-        CUDA_CHECK(cudaGetLastError());
-        c.R = sh.R;
-        for (int r = 0; r < sh.R; r++) {
-            c.fr[r] = xb_fr(sh.xbuf_peer[r], parity);
-            c.rows[r] = xb_rows(sh.xbuf_peer[r], parity);
-        }
-        c.flags = xb_flags(sh.xbuf); c.seq = seq;
-        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
-    } else {                           // one process, G GPUs: root waits for every shard, pulls over P2P
-        for (int g = 0; g < G; g++) {
-            Dev &d = L.devs[g];
-            set_dev(d);
-            if (g > 0) CUDA_CHECK(cudaStreamWaitEvent(d.st, root.evdone, 0));     // previous combine has consumed d.fr / d.rows
-            launch_regf(d, ni, ib[g], lmax, nnbmax, m_flag, time_it && g == 0, d.fr, 8, d.rows, false);
-            if (g > 0) {
-                CUDA_CHECK(cudaEventRecord(d.evdone, d.st));
-                CUDA_CHECK(cudaStreamWaitEvent(root.st, d.evdone, 0));
+        MergeArgs m = merge_defaults();
+        m.iperm = iperm[0] + j.slot0; m.res_f = j.out_f; m.f_stride = 7; m.res_list = j.out_list; m.sort = 1;
+        launch_regf(root, sl, lo, hi, j, ib[0], iperm[0], m, time_it, tl);
+    } else {
+        CombineArgs c;
+        memset(&c, 0, sizeof(c));
+        c.nloc = j.nloc; c.lmax = j.lmax; c.nnbmax = j.nnbmax; c.res_f = j.out_f; c.res_list = j.out_list;
+        c.iperm = iperm[0] + j.slot0;
+        if (L.sh.on) {
+            // One process per GPU.  No collective call in the data path: merge_kernel writes the shard result into
+            // this rank's exchange slot and its last CTA raises this rank's flag in every peer's buffer over NVLink;
+            // combine_kernel -- after seeing all R flags of this call -- pulls partial sums and the valid part of the
+            // neighbour rows straight from the peers' HBM and its last CTA acknowledges to every peer.  Exchange
+            // slots are reused every XSLOTS calls: merge_kernel first waits for every peer's ack of call seq-XSLOTS.
+            Shard &sh = L.sh;
+            const unsigned long long seq = ++sh.seq;
+            const int xs = (int)(seq % XSLOTS);
+            MergeArgs m = merge_defaults();
+            m.iperm = nullptr; m.res_f = xb_fr(sh.xbuf, xs); m.f_stride = 8; m.res_list = xb_rows(sh.xbuf, xs); m.sort = 0;
+            m.R = sh.R;
+            if (seq > (unsigned long long)XSLOTS) { m.acks = xb_acks(sh.xbuf, xs); m.ack_need = (long long)seq - XSLOTS; }
+            m.sig.done_ctr = sl.done_ctr; m.sig.R = sh.R; m.sig.seq = seq;
+            c.ack.done_ctr = sl.done_ctr + 1; c.ack.R = sh.R; c.ack.seq = seq;
+            for (int r = 0; r < sh.R; r++) {
+                m.sig.peer[r] = xb_flags(sh.xbuf_peer[r], xs) + sh.rank;
+                c.ack.peer[r] = xb_acks(sh.xbuf_peer[r], xs) + sh.rank;
+                c.fr[r] = xb_fr(sh.xbuf_peer[r], xs);
+                c.rows[r] = xb_rows(sh.xbuf_peer[r], xs);
             }
-            c.fr[g] = d.fr; c.rows[g] = d.rows;
+            launch_regf(root, sl, lo, hi, j, ib[0], iperm[0], m, time_it, tl);
+            c.R = sh.R;
+            c.flags = xb_flags(sh.xbuf, xs); c.seq = seq;
+        } else {                       // one process, G GPUs: root waits for every shard, pulls over P2P
+            if (own_streams) FATAL("internal: in-process multi-GPU jobs run on the main streams");
+            for (int g = 0; g < G; g++) {
+                Dev &d = L.devs[g];
+                set_dev(d);
+                if (g > 0) CUDA_CHECK(cudaStreamWaitEvent(d.st, root.evdone, 0));     // previous combine has consumed d.fr / d.rows
+                MergeArgs m = merge_defaults();
+                m.iperm = nullptr; m.res_f = d.fr; m.f_stride = 8; m.res_list = d.rows; m.sort = 0;
+                launch_regf(d, d.slots[q], d.st, d.st, j, ib[g], iperm[g], m, time_it && g == 0, g == 0 ? tl : nullptr);
+                if (g > 0) {
+                    CUDA_CHECK(cudaEventRecord(d.evdone, d.st));
+                    CUDA_CHECK(cudaStreamWaitEvent(root.st, d.evdone, 0));
+                }
+                c.fr[g] = d.fr; c.rows[g] = d.rows;
+            }
+            c.R = G;
+            set_dev(root);
         }
-        c.R = G;
-        set_dev(root);
+        combine_kernel<<<(j.nloc + 3) / 4, 128, 0, hi>>>(c);      // 4 warps per CTA: one i each
+        CUDA_CHECK(cudaGetLastError());
+        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+        if (!L.sh.on) CUDA_CHECK(cudaEventRecord(root.evdone, root.st));
     }
-    combine_kernel<<<(ni + 3) / 4, 128, 0, root.st>>>(c);      // 4 warps per CTA: one i each
-    CUDA_CHECK(cudaGetLastError());
-    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
-    if (!L.sh.on) CUDA_CHECK(cudaEventRecord(root.evdone, root.st));
-    if (time_it) CUDA_CHECK(cudaEventRecord(root.ev3, root.st));
-    if (tl) CUDA_CHECK(cudaEventRecord(tl[4], root.st));
+    if (time_it) CUDA_CHECK(cudaEventRecord(root.ev3, hi));
+    if (tl) CUDA_CHECK(cudaEventRecord(tl[4], hi));
+    if (own_streams) { CUDA_CHECK(cudaEventRecord(sl.ev_done, hi)); sl.used = true; }
 }
 
-void fetch_results(int ni, int lmax, double *acc, double *jrk, double *pot, int *list)
+// Host side of gpunb_regf_: rows [k0, k1) of the sorted order from the mapped staging buffers (indexed by i) to the
+// caller's arrays.  order == NULL: identity.
+void scatter_rows(const int *order, int k0, int k1, int lmax, double *acc, double *jrk, double *pot, int *list)
 {
-    Dev &root = L.devs[0];
-    set_dev(root);
-    CUDA_CHECK(cudaMemcpyAsync(L.h_f, root.res_f, sizeof(double) * 7 * ni, cudaMemcpyDeviceToHost, root.st));
-    CUDA_CHECK(cudaMemcpyAsync(L.h_list, root.res_list, sizeof(int) * (size_t)ni * lmax, cudaMemcpyDeviceToHost, root.st));
-    L.ctr[GPUNB_B200_CTR_D2H_BYTES] += sizeof(double) * 7.0 * ni + sizeof(int) * (double)ni * lmax;
-    CUDA_CHECK(cudaStreamSynchronize(root.st));
-    for (int i = 0; i < ni; i++) {
+    double bytes = 0;
+    for (int k = k0; k < k1; k++) {
+        const int i = order ? order[k] : k;
         const double *f = L.h_f + 7 * (size_t)i;
         acc[3 * i] = f[0]; acc[3 * i + 1] = f[1]; acc[3 * i + 2] = f[2];
         jrk[3 * i] = f[3]; jrk[3 * i + 1] = f[4]; jrk[3 * i + 2] = f[5];
@@ -1501,7 +1648,9 @@ void fetch_results(int ni, int lmax, double *acc, double *jrk, double *pot, int 
         const int n = src[0];
         dst[0] = n;
         if (n > 0) memcpy(dst + 1, src + 1, sizeof(int) * n);
+        bytes += 56.0 + 4.0 * (1 + (n > 0 ? n : 0));
     }
+    L.ctr[GPUNB_B200_CTR_D2H_BYTES] += bytes;      // what the kernels wrote over PCIe into the mapped buffers
 }
 
 void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, const double *vi,
@@ -1511,7 +1660,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     if (!(0 < ni && ni <= NIMAX)) FATAL("gpunb_regf: ni=%d out of range (0, %d]", ni, NIMAX);
     if (nnbmax + 1 > lmax) FATAL("gpunb_regf: nnbmax=%d does not fit rows of lmax=%d", nnbmax, lmax);
     if (nnbmax > SORT_CAP) FATAL("gpunb_regf: nnbmax=%d exceeds the list capacity %d of this build", nnbmax, SORT_CAP);
-    L.time_grav -= wtime();
+    const double wt_in = wtime();
     L.numInter += (long long)ni * L.nbody;       // reference counts every pair, self included (:747)
     L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)ni * L.nbody;
     L.ini += ni; L.icall++;
@@ -1523,27 +1672,67 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     memcpy(h + 2 * (size_t)ni, xi, sizeof(double) * 3 * ni);
     memcpy(h + 5 * (size_t)ni, vi, sizeof(double) * 3 * ni);
     for (int k = 0; k < 8 * ni; k++) if (h[k] != h[k]) FATAL("gpunb_regf: NaN in i-particle data");
+    const int G = (int)L.devs.size();
+    Dev &root = L.devs[0];
+    // One call = nsub sub-blocks of the Morton-sorted i-block, each in its own pipeline slot: the pair kernel of
+    // sub-block q+1 fills the SMs as the CTAs of sub-block q retire, and merge, the PCIe writes of the result rows
+    // and the host-side copy into the caller's arrays of sub-block q all run beside it.
+    int nsub = (G == 1) ? L.nsub : 1;
+    if (nsub > ni / 256) nsub = ni / 256;
+    if (nsub < 1) nsub = 1;
     IBlock ib[MAX_RANKS];
-    for (size_t g = 0; g < L.devs.size(); g++) {
+    const int *ipm[MAX_RANKS];
+    for (int g = 0; g < G; g++) {
         Dev &d = L.devs[g];
         set_dev(d);
-        ensure_work_buffers(d, lmax, nnbmax, g == 0);
+        ensure_work_buffers(d, lmax, nnbmax, g == 0, nsub, false);
         CUDA_CHECK(cudaMemcpyAsync(d.ibuf, h, sizeof(double) * 8 * ni, cudaMemcpyHostToDevice, d.st));
         L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 8.0 * ni;
         ib[g] = IBlock{d.ibuf, d.ibuf + ni, d.ibuf + 2 * (size_t)ni, d.ibuf + 5 * (size_t)ni};
+        launch_isort(d, d.st, ni, ni, ib[g].xi, d.iperm, g == 0 ? L.h_iperm_dev : nullptr);
+        ipm[g] = d.iperm;
     }
-    regf_block(ni, ib, lmax, nnbmax, m_flag, true);
-    CUDA_CHECK(cudaEventSynchronize(L.devs[0].ev1));          // "grav" ends with the pair kernel, like the reference's bucket
-    const double wt0 = wtime();
-    fetch_results(ni, lmax, acc, jrk, pot, list);
-    Dev &root = L.devs[0];
+    set_dev(root);
+    Job j;
+    j.lmax = lmax; j.nnbmax = nnbmax; j.m_flag = m_flag; j.out_f = L.h_f_dev; j.out_list = L.h_list_dev;
+    double t_scatter = 0.0;
+    if (nsub == 1) {
+        j.slot0 = 0; j.nloc = ni;
+        run_job(j, ib, ipm, 0, false, true);
+        CUDA_CHECK(cudaStreamSynchronize(root.st));
+        const double t0 = wtime();
+        scatter_rows(L.h_iperm, 0, ni, lmax, acc, jrk, pot, list);
+        t_scatter = wtime() - t0;
+    } else {
+        const int per = (((ni + nsub - 1) / nsub) + 31) & ~31;       // whole i-tiles per sub-block
+        CUDA_CHECK(cudaEventRecord(root.ev_fork, root.st));
+        int nq = 0;
+        for (int q = 0; q < nsub && q * per < ni; q++, nq++) {
+            Slot &sl = root.slots[q];
+            CUDA_CHECK(cudaStreamWaitEvent(sl.lo, root.ev_fork, 0));
+            j.slot0 = q * per; j.nloc = (ni - j.slot0 < per) ? ni - j.slot0 : per;
+            if (q == 0) CUDA_CHECK(cudaEventRecord(root.ev0, sl.lo));       // "grav" span: start of the first pair kernel ...
+            run_job(j, ib, ipm, q, true, false);
+        }
+        CUDA_CHECK(cudaEventRecord(root.ev1, root.slots[nq - 1].lo));       // ... to the end of the last one
+        CUDA_CHECK(cudaEventRecord(root.ev3, root.slots[nq - 1].hi));
+        for (int q = 0; q < nq; q++) {
+            CUDA_CHECK(cudaEventSynchronize(root.slots[q].ev_done));
+            const double t0 = wtime();
+            const int k0 = q * per, k1 = (k0 + per < ni) ? k0 + per : ni;
+            scatter_rows(L.h_iperm, k0, k1, lmax, acc, jrk, pot, list);
+            t_scatter += wtime() - t0;
+        }
+        for (int q = 0; q < nq; q++) CUDA_CHECK(cudaStreamWaitEvent(root.st, root.slots[q].ev_done, 0));
+        CUDA_CHECK(cudaEventSynchronize(root.ev3));
+    }
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, root.ev0, root.ev1)); L.ctr[GPUNB_B200_CTR_GRAV_MS] += ms;
     CUDA_CHECK(cudaEventElapsedTime(&ms, root.ev1, root.ev3)); L.ctr[GPUNB_B200_CTR_MERGE_MS] += ms;
     L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += 1;
     const double wt = wtime();
-    L.time_grav += wt0; L.time_reduce += wt - wt0;
-    L.last_ni = ni; L.last_lmax = lmax;
+    L.time_grav += (wt - wt_in) - t_scatter; L.time_reduce += t_scatter;      // reference buckets: grav(s), nb(s)
+    L.last_ni = ni; L.last_lmax = lmax; L.last_on_host = true;
 }
 
 void lib_profile(int irank)
@@ -1690,32 +1879,79 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
 {
     if (!L.is_open) FATAL("gpunb_b200_sweep_resident: library closed");
     Dev &root = L.devs[0];
+    const int G = (int)L.devs.size();
     const int i0 = *i0p, ni = *nip, block = *blockp;
     if (i0 < 0 || i0 + ni > root.nj_total || block < 1 || block > NIMAX) FATAL("gpunb_b200_sweep_resident: bad range");
-    for (size_t g = 0; g < L.devs.size(); g++) ensure_work_buffers(L.devs[g], *lmaxp, *nnbmaxp, g == 0);
-    set_dev(root);
-    CUDA_CHECK(cudaEventRecord(root.evs0, root.st));
-    int nlaunch = 0, last = 0;
     static int timeline = -1;
     if (timeline < 0) { const char *e = getenv("GPUNB_B200_TIMELINE"); timeline = (e && atoi(e) > 0 && L.devs.size() == 1) ? 1 : 0; }
-    static std::vector<cudaEvent_t> tlev;
+    // Pipelined (default, one GPU per process): every block's Morton order comes from ONE batched isort launch, then
+    // the blocks cycle through nslot pipeline slots (see Slot).  Sequential (GPUNB_B200_NSLOT=1, the per-kernel
+    // timeline, or one process driving several GPUs): one block after the other on the main stream.
+    const int nslot = (G == 1 && !timeline) ? L.nslot : 1;
+    const bool pipelined = nslot > 1;
+    for (int g = 0; g < G; g++) ensure_work_buffers(L.devs[g], *lmaxp, *nnbmaxp, g == 0, nslot, true);
+    set_dev(root);
     const int nblocks = (ni + block - 1) / block;
+    static std::vector<cudaEvent_t> tlev;
     if (timeline && (int)tlev.size() < 5 * nblocks) {
         const size_t old = tlev.size();
         tlev.resize((size_t)5 * nblocks);
         for (size_t k = old; k < tlev.size(); k++) CUDA_CHECK(cudaEventCreate(&tlev[k]));
     }
-    for (int b = i0; b < i0 + ni; b += block) {
-        const int n = (i0 + ni - b < block) ? i0 + ni - b : block;
-        IBlock ib[MAX_RANKS];
-        for (size_t g = 0; g < L.devs.size(); g++) {
-            Dev &d = L.devs[g];
-            const double *x = d.jraw + d.nj_total, *v = d.jraw + 4 * (size_t)d.nj_total;
-            ib[g] = IBlock{d.radii + b, d.radii + d.raw_cap + b, x + 3 * (size_t)b, v + 3 * (size_t)b};
+    Job j;
+    j.lmax = *lmaxp; j.nnbmax = *nnbmaxp; j.m_flag = *m_flagp; j.slot0 = 0;
+    auto iblock_of = [&](Dev &d, int b0) {
+        const double *x = d.jraw + d.nj_total, *v = d.jraw + 4 * (size_t)d.nj_total;
+        return IBlock{d.radii + b0, d.radii + d.raw_cap + b0, x + 3 * (size_t)b0, v + 3 * (size_t)b0};
+    };
+    CUDA_CHECK(cudaEventRecord(root.evs0, root.st));
+    int nlaunch = 0, last = 0;
+    if (pipelined) {
+        if ((size_t)ni > root.iperm_all_n) {
+            CUDA_CHECK(cudaDeviceSynchronize());
+            dev_free(root.iperm_all);
+            root.iperm_all_n = (size_t)ni + 4096;
+            dev_alloc(root.iperm_all, root.iperm_all_n);
         }
-        regf_block(n, ib, *lmaxp, *nnbmaxp, *m_flagp, false, timeline ? &tlev[(size_t)5 * nlaunch] : nullptr);
-        L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)n * root.nj_total;
-        nlaunch++; last = n;
+        launch_isort(root, root.st, ni, block, root.jraw + root.nj_total + 3 * (size_t)i0, root.iperm_all, nullptr);
+        CUDA_CHECK(cudaEventRecord(root.ev_fork, root.st));
+        for (int q = 0; q < nslot && q < nblocks; q++) CUDA_CHECK(cudaStreamWaitEvent(root.slots[q].lo, root.ev_fork, 0));
+        for (int b = 0; b < nblocks; b++) {
+            const int q = b % nslot;
+            Slot &sl = root.slots[q];
+            const int b0 = i0 + b * block;
+            const int n = (i0 + ni - b0 < block) ? i0 + ni - b0 : block;
+            // the slot's buffers are free once merge / combine of its previous block are done
+            if (sl.used) CUDA_CHECK(cudaStreamWaitEvent(sl.lo, sl.ev_done, 0));
+            IBlock ib[1] = {iblock_of(root, b0)};
+            const int *ipm[1] = {root.iperm_all + (size_t)b * block};
+            j.nloc = n; j.out_f = sl.res_f; j.out_list = sl.res_list;
+            run_job(j, ib, ipm, q, true, false);
+            L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)n * root.nj_total;
+            nlaunch++; last = n; L.last_slot = q;
+        }
+        for (int q = 0; q < nslot && q < nblocks; q++) CUDA_CHECK(cudaStreamWaitEvent(root.st, root.slots[q].ev_done, 0));
+    } else {
+        for (int b0 = i0; b0 < i0 + ni; b0 += block) {
+            const int n = (i0 + ni - b0 < block) ? i0 + ni - b0 : block;
+            IBlock ib[MAX_RANKS];
+            const int *ipm[MAX_RANKS];
+            cudaEvent_t *tl = timeline ? &tlev[(size_t)5 * nlaunch] : nullptr;
+            if (tl) CUDA_CHECK(cudaEventRecord(tl[0], root.st));
+            for (int g = 0; g < G; g++) {
+                Dev &d = L.devs[g];
+                set_dev(d);
+                ib[g] = iblock_of(d, b0);
+                launch_isort(d, d.st, n, n, ib[g].xi, d.iperm, nullptr);
+                ipm[g] = d.iperm;
+            }
+            set_dev(root);
+            if (tl) CUDA_CHECK(cudaEventRecord(tl[1], root.st));
+            j.nloc = n; j.out_f = root.slots[0].res_f; j.out_list = root.slots[0].res_list;
+            run_job(j, ib, ipm, 0, false, false, tl);
+            L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)n * root.nj_total;
+            nlaunch++; last = n; L.last_slot = 0;
+        }
     }
     set_dev(root);
     CUDA_CHECK(cudaEventRecord(root.evs1, root.st));
@@ -1731,7 +1967,7 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
         L.ctr[GPUNB_B200_CTR_TL_BLOCKS] += nlaunch;
     }
     L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += nlaunch;
-    L.last_ni = last; L.last_lmax = *lmaxp;
+    L.last_ni = last; L.last_lmax = *lmaxp; L.last_on_host = false;
     return ms;
 }
 
@@ -1740,7 +1976,22 @@ void gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double
     const int ni = L.last_ni, lmax = L.last_lmax;
     *n_last = ni; *lmaxp = lmax;
     if (ni <= 0) return;
-    fetch_results(ni, lmax, &acc[0][0], &jrk[0][0], pot, list);
+    if (!L.last_on_host) {         // a resident sweep leaves its last block in the slot's device buffers
+        Dev &root = L.devs[0];
+        set_dev(root);
+        Slot &sl = root.slots[L.last_slot];
+        CUDA_CHECK(cudaMemcpyAsync(L.h_f, sl.res_f, sizeof(double) * 7 * ni, cudaMemcpyDeviceToHost, root.st));
+        CUDA_CHECK(cudaMemcpyAsync(L.h_list, sl.res_list, sizeof(int) * (size_t)ni * lmax, cudaMemcpyDeviceToHost, root.st));
+        CUDA_CHECK(cudaStreamSynchronize(root.st));
+        L.last_on_host = true;
+    }
+    scatter_rows(nullptr, 0, ni, lmax, &acc[0][0], &jrk[0][0], pot, list);
+}
+
+void gpunb_b200_set_tuning(int nslot, int nsub)
+{
+    if (nslot >= 1 && nslot <= MAX_SLOTS) L.nslot = nslot;
+    if (nsub >= 1 && nsub <= MAX_SLOTS) L.nsub = nsub;
 }
 
 // tuning aid: per-work-item start/end timestamps (ns) of the LAST regf_kernel launch (GPUNB_B200_STATS=2)
@@ -1782,6 +2033,7 @@ int gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128])
     int rc = sh.init(&sh.comm, nranks, id, rank);
     if (rc != 0) FATAL("ncclCommInitRank failed: %s", sh.errstr ? sh.errstr(rc) : "?");
     sh.rank = rank; sh.R = nranks; sh.seq = 0;
+    for (Slot &sl : d.slots) if (sl.done_ctr) CUDA_CHECK(cudaMemsetAsync(sl.done_ctr, 0, 2 * sizeof(unsigned), d.st));
     CUDA_CHECK(cudaMalloc((void **)&sh.xbuf, XB_BYTES));
     CUDA_CHECK(cudaMemsetAsync(sh.xbuf, 0, XB_BYTES, d.st));
     // exchange cudaIpc handles of the exchange buffers with an all-gather (bootstrap only), then map every peer's

@@ -88,6 +88,8 @@ class ForceLib:
             L.gpunb_b200_nccl_init.restype = C.c_int
             L.gpunb_b200_nccl_finalize.argtypes = []
             L.gpunb_b200_nccl_finalize.restype = None
+            L.gpunb_b200_set_tuning.argtypes = [C.c_int, C.c_int]
+            L.gpunb_b200_set_tuning.restype = None
         self.nj = 0
 
     # ---- the reference interface -------------------------------------------------------------
@@ -245,6 +247,11 @@ class ForceLib:
     def nccl_finalize(self):
         self._need_b200()
         self.lib.gpunb_b200_nccl_finalize()
+
+    def set_tuning(self, nslot: int = 0, nsub: int = 0):
+        """Pipeline depth: slots of a resident sweep / sub-blocks of one gpunb_regf_ call (0 = leave unchanged)."""
+        self._need_b200()
+        self.lib.gpunb_b200_set_tuning(nslot, nsub)
 
     def fp32_microbench(self, mode: int, iters: int = 4096) -> float:
         self._need_b200()

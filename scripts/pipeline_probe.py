@@ -1,0 +1,46 @@
+"""Pipeline depth probe on one GPU (or one rank per GPU under torchrun): device-resident sweep rate for
+nslot = 1..4 pipeline slots, and microseconds per gpunb_regf_ call (host arrays) for nsub = 1..4 sub-blocks.
+Usage: python scripts/pipeline_probe.py [N] [blocks]"""
+import os, sys, time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+import numpy as np
+import torch
+os.environ["GPU_LIST"] = str(local)
+torch.cuda.set_device(local)
+dist = None
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+from nbody6ppgpu_b200 import load, snapshots as S
+lib = load(); lib.devinit(rank)
+if dist:
+    from nbody6ppgpu_b200.sharding import nccl_bootstrap
+    nccl_bootstrap(lib, rank, world)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+nblk = int(sys.argv[2]) if len(sys.argv) > 2 else 192
+m, x, v = S.plummer(n, 1, "kroupa"); h2, dtr = S.radii_nnb(x, m, 200.0)
+lib.open(n + 10, rank); lib.send(m, x, v); lib.set_radii(h2, dtr)
+for nslot in (1, 2, 3, 4, 3):
+    lib.set_tuning(nslot, 0)
+    lib.sweep_resident(0, 1024 * 16, 1024, 600, 550, 0)
+    if dist: dist.barrier()
+    ms = min(lib.sweep_resident(0, 1024 * nblk, 1024, 600, 550, 0) for _ in range(2))
+    print(f"rank {rank}/{world} nslot {nslot}: {ms / nblk * 1e3:7.1f} us per block  {1024.0 * nblk * n / ms * 1e-6:8.1f} Gint/s", flush=True)
+out = lib.caller_arrays(1024, 600)
+for nsub in (1, 2, 3, 4, 2):
+    lib.set_tuning(0, nsub)
+    for rep in range(2):
+        if dist: dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for b in range(48):
+            i0 = b * 1024
+            lib.regf_into(out, h2[i0:i0 + 1024], dtr[i0:i0 + 1024], x[i0:i0 + 1024], v[i0:i0 + 1024], 600, 550, 0)
+        t = time.perf_counter() - t0
+    print(f"rank {rank}/{world} nsub {nsub}: {t / 48 * 1e6:7.1f} us per gpunb_regf_ call  {1024.0 * 48 * n / t * 1e-9:8.1f} Gint/s", flush=True)
+lib.close()
+if dist:
+    dist.barrier(); lib.nccl_finalize(); dist.destroy_process_group()

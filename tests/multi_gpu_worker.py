@@ -32,9 +32,12 @@ def check(lib, tag, rank=0):
             assert max(ea, ej, ep) <= 1e-6, (tag, ea, ej, ep)
         # resident sweep path uses the same exchange step, launched back to back
         lib.set_radii(h2, dtr)
-        lib.sweep_resident(0, 4096, 1024, lmax, nnbmax, m_flag)
+        # 12 blocks: more than the XSLOTS = 8 exchange slots, so slot reuse (acks) is exercised
+        lib.sweep_resident(0, 12 * 1024, 1024, lmax, nnbmax, m_flag)
         a, j, p, l = lib.fetch_last(lmax)
-        a2, j2, p2, l2 = lib.regf(h2[3072:4096], dtr[3072:4096], x[3072:4096], v[3072:4096], lmax, nnbmax, m_flag)
+        lib.set_tuning(0, 1)                        # one pair-kernel launch per call: same summation order as the sweep
+        a2, j2, p2, l2 = lib.regf(h2[11264:12288], dtr[11264:12288], x[11264:12288], v[11264:12288], lmax, nnbmax, m_flag)
+        lib.set_tuning(0, 2)
         assert np.array_equal(a, a2) and np.array_equal(p, p2) and not oracle_lib.list_rows_equal(l, l2)
         lib.close()
     print(f"{tag} rank {rank}: ok", flush=True)

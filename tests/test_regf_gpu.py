@@ -193,19 +193,51 @@ def test_against_reference_avx_library(b200, ref_avx):
     assert oracle_lib.relerr(out["b200"][2], out["avx"][2]) < 3e-5
 
 
-def test_resident_sweep_matches_abi(b200):
-    n = 8192
+@pytest.mark.parametrize("nslot", [1, 2, 3, 4])
+def test_resident_sweep_matches_abi(b200, nslot):
+    """Pipelined sweeps (blocks cycling through `nslot` pipeline slots, one batched isort) give bit-for-bit what a
+    single gpunb_regf_ launch of the same block gives."""
+    n = 8192 + 300                # ragged last block
     m, x, v = S.plummer(n, 9, "kroupa")
     h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 100.0))
     b200.open(n + 10, 0)
     b200.send(m, x, v)
     try:
+        b200.set_tuning(nslot, 1)
         b200.set_radii(h2, dtr)
-        ms = b200.sweep_resident(0, n, 1024, 400, 350, 0)
-        assert ms > 0
-        a, j, p, l = b200.fetch_last(400)
-        a2, j2, p2, l2 = b200.regf(h2[n - 1024:], dtr[n - 1024:], x[n - 1024:], v[n - 1024:], 400, 350, 0)
-        assert np.array_equal(a, a2) and np.array_equal(j, j2) and np.array_equal(p, p2)
-        assert not oracle_lib.list_rows_equal(l, l2)
+        for n_sweep in (n, 5 * 1024):          # the last block lands in different slots
+            ms = b200.sweep_resident(0, n_sweep, 1024, 400, 350, 0)
+            assert ms > 0
+            i0 = ((n_sweep - 1) // 1024) * 1024
+            a, j, p, l = b200.fetch_last(400)
+            assert a.shape[0] == n_sweep - i0
+            a2, j2, p2, l2 = b200.regf(h2[i0:n_sweep], dtr[i0:n_sweep], x[i0:n_sweep], v[i0:n_sweep], 400, 350, 0)
+            assert np.array_equal(a, a2) and np.array_equal(j, j2) and np.array_equal(p, p2)
+            assert not oracle_lib.list_rows_equal(l, l2)
     finally:
+        b200.set_tuning(3, 2)
+        b200.close()
+
+
+@pytest.mark.parametrize("ni", [512, 513, 700, 1024, 2048])
+def test_subblock_pipeline_matches_single_launch(b200, ni):
+    """gpunb_regf_ split into sub-blocks on pipeline slots (zero-copy result rows, host copy overlapped with the next
+    pair kernel): lists identical to the single-launch path, sums equal up to fp64 summation order."""
+    n = 6000
+    m, x, v = S.plummer(n, 4, "kroupa")
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 80.0))
+    b200.open(n + 10, 0)
+    b200.send(m, x, v)
+    try:
+        out = {}
+        for nsub in (1, 2, 4):
+            b200.set_tuning(0, nsub)
+            for rep in range(2):      # twice: slot buffers are reused
+                out[nsub] = [a.copy() for a in b200.regf(h2[:ni], dtr[:ni], x[:ni], v[:ni], 400, 350, 0)]
+        for nsub in (2, 4):
+            assert not oracle_lib.list_rows_equal(out[nsub][3], out[1][3])
+            for q in range(3):
+                assert oracle_lib.relerr(out[nsub][q], out[1][q]) < 1e-12
+    finally:
+        b200.set_tuning(3, 2)
         b200.close()
