@@ -44,7 +44,7 @@ LMAX, NNBMAX, BLOCK = 600, 550, 1024          # --with-par=1m: LMAX=600 (configu
 NNB_TARGET = 200.0
 FLOP_PER_INT = 60.0                           # reference convention, gpunb.velocity.cu:894
 NSLOT = int(os.environ.get("GPUNB_B200_NSLOT", "3"))     # pipeline slots of the resident sweep
-NSUB = int(os.environ.get("GPUNB_B200_NSUB", "2"))       # sub-blocks of one gpunb_regf_ call
+NSUB = int(os.environ.get("GPUNB_B200_NSUB", "4"))       # sub-blocks of one gpunb_regf_ call
 
 
 def parse():
@@ -138,13 +138,13 @@ def load_reference_avx():
 def time_reference(ref, m, x, v, h2, dtr, blocks, m_flag, first_block=0):
     """One bounded sample: send + `blocks` regf calls of 1024 on the AVX library.  Returns (s, interactions)."""
     n = m.shape[0]
-    out = ref.caller_arrays(BLOCK, LMAX)          # caller-owned arrays allocated once, as for the b200 arm
+    call = ref.block_caller(h2, dtr, x, v, BLOCK, LMAX, NNBMAX, m_flag)   # static caller arrays, as for the b200 arm
     t0 = time.perf_counter()
     ref.send(m, x, v)
     inter = 0
     for b in range(blocks):
         i0 = ((first_block + b) * BLOCK) % max(n - BLOCK - 8, 1)      # the AVX library reads 3 rows past ni
-        ref.regf_into(out, h2[i0:i0 + BLOCK], dtr[i0:i0 + BLOCK], x[i0:i0 + BLOCK], v[i0:i0 + BLOCK], LMAX, NNBMAX, m_flag)
+        call(i0, BLOCK)
         inter += BLOCK * n
     return time.perf_counter() - t0, inter
 
@@ -281,15 +281,15 @@ def main():
     int_per_launch = float(BLOCK) * n * interactions_scale
 
     # ---------------- end-to-end leg through the C-ABI with host buffers: `e2e` ----------------
-    out_arrays = lib.caller_arrays(BLOCK, LMAX)      # caller-owned, allocated once (the Fortran caller's static arrays)
+    # caller-owned arrays and by-reference scalars set up once (the Fortran caller's static arrays)
+    regf_call = lib.block_caller(h2, dtr, x, v, BLOCK, LMAX, NNBMAX, args.m_flag)
 
     def abi_step():
         lib.send(m, x, v)
         nnb_sum = 0
         for i0 in range(0, ni_total, BLOCK):
-            i1 = min(i0 + BLOCK, ni_total)
-            acc, jrk, pot, lst = lib.regf_into(out_arrays, h2[i0:i1], dtr[i0:i1], x[i0:i1], v[i0:i1], LMAX, NNBMAX, args.m_flag)
-            nnb_sum += int(lst[:, 0].sum())
+            acc, jrk, pot, lst = regf_call(i0, min(BLOCK, ni_total - i0))
+            nnb_sum += int(lst[:, 0].sum())          # the step's result is read on the host
         return nnb_sum
 
     e2e_warm = max(1, min(args.warmup, 1)) if ni_total >= 500_000 else args.warmup

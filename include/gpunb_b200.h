@@ -77,6 +77,12 @@ enum {
     GPUNB_B200_CTR_TL_REGF_MS,      /* regf_kernel                                             */
     GPUNB_B200_CTR_TL_MERGE_MS,     /* merge_kernel                                            */
     GPUNB_B200_CTR_TL_EXCH_MS,      /* signal_kernel + combine_kernel (multi-GPU; includes waiting for the slowest shard) */
+    /* host-side wall-clock buckets of gpunb_regf_ (ms): pack + NaN check of the i-block, enqueueing copies and
+     * kernels, waiting for the device, copying result rows into the caller's arrays */
+    GPUNB_B200_CTR_HOST_PACK_MS,
+    GPUNB_B200_CTR_HOST_ENQUEUE_MS,
+    GPUNB_B200_CTR_HOST_WAIT_MS,
+    GPUNB_B200_CTR_HOST_SCATTER_MS,
     GPUNB_B200_CTR_COUNT
 };
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);

@@ -1076,7 +1076,7 @@ constexpr int ROWS_LMAX_CAP = 1024;    // row stride capacity of the IPC-exporte
 // priority stream `hi`, latency-bound kernels) run beside it.
 constexpr int MAX_SLOTS = 4;
 constexpr int DEFAULT_NSLOT = 3;       // slots a resident sweep cycles through (GPUNB_B200_NSLOT)
-constexpr int DEFAULT_NSUB  = 2;       // sub-blocks of one gpunb_regf_ call (GPUNB_B200_NSUB)
+constexpr int DEFAULT_NSUB  = 4;       // sub-blocks of one gpunb_regf_ call (GPUNB_B200_NSUB)
 struct Slot {
     cudaStream_t lo = nullptr, hi = nullptr;
     cudaEvent_t ev_regf = nullptr, ev_done = nullptr;
@@ -1158,7 +1158,7 @@ struct Lib {
     int *h_list = nullptr, *h_list_dev = nullptr; size_t h_list_n = 0;
     int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
-    int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB;
+    int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
     int last_slot = 0; bool last_on_host = false;
     double time_send = 0, time_grav = 0, time_reduce = 0, time_out = 0;      // reference: gpunb.velocity.cu:557-559
     long long numInter = 0; int icall = 0, ini = 0, isend = 0;
@@ -1257,6 +1257,7 @@ void lib_devinit(int irank)
     memset(L.h_flag, 0, 16 * sizeof(int));
     { const char *e = getenv("GPUNB_B200_NSLOT"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nslot = atoi(e); }
     { const char *e = getenv("GPUNB_B200_NSUB");  if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nsub = atoi(e); }
+    { const char *e = getenv("GPUNB_B200_HOST_THREADS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) L.host_threads = atoi(e); }
     L.devinit = true;
 }
 
@@ -1635,8 +1636,10 @@ void run_job(const Job &j, const IBlock *ib, const int *const *iperm, int q, boo
 // Host side of gpunb_regf_: rows [k0, k1) of the sorted order from the mapped staging buffers (indexed by i) to the
 // caller's arrays.  order == NULL: identity.
 void scatter_rows(const int *order, int k0, int k1, int lmax, double *acc, double *jrk, double *pot, int *list)
-{
+{   // the rows were just written by the device, so they are cold for the CPU: a few host threads hide the DRAM latency
+    // (the reference's host side is OpenMP as well, gpunb.velocity.cu:607-613,756)
     double bytes = 0;
+#pragma omp parallel for num_threads(L.host_threads) schedule(static) reduction(+ : bytes) if (L.host_threads > 1 && k1 - k0 >= 64)
     for (int k = k0; k < k1; k++) {
         const int i = order ? order[k] : k;
         const double *f = L.h_f + 7 * (size_t)i;
@@ -1672,6 +1675,8 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     memcpy(h + 2 * (size_t)ni, xi, sizeof(double) * 3 * ni);
     memcpy(h + 5 * (size_t)ni, vi, sizeof(double) * 3 * ni);
     for (int k = 0; k < 8 * ni; k++) if (h[k] != h[k]) FATAL("gpunb_regf: NaN in i-particle data");
+    const double wt_packed = wtime();
+    double t_wait = 0.0;
     const int G = (int)L.devs.size();
     Dev &root = L.devs[0];
     // One call = nsub sub-blocks of the Morton-sorted i-block, each in its own pipeline slot: the pair kernel of
@@ -1699,8 +1704,11 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     if (nsub == 1) {
         j.slot0 = 0; j.nloc = ni;
         run_job(j, ib, ipm, 0, false, true);
+        const double tw = wtime();
         CUDA_CHECK(cudaStreamSynchronize(root.st));
         const double t0 = wtime();
+        t_wait = t0 - tw;
+        L.ctr[GPUNB_B200_CTR_HOST_ENQUEUE_MS] += (tw - wt_packed) * 1e3;
         scatter_rows(L.h_iperm, 0, ni, lmax, acc, jrk, pot, list);
         t_scatter = wtime() - t0;
     } else {
@@ -1716,9 +1724,12 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         }
         CUDA_CHECK(cudaEventRecord(root.ev1, root.slots[nq - 1].lo));       // ... to the end of the last one
         CUDA_CHECK(cudaEventRecord(root.ev3, root.slots[nq - 1].hi));
+        L.ctr[GPUNB_B200_CTR_HOST_ENQUEUE_MS] += (wtime() - wt_packed) * 1e3;
         for (int q = 0; q < nq; q++) {
+            const double tw = wtime();
             CUDA_CHECK(cudaEventSynchronize(root.slots[q].ev_done));
             const double t0 = wtime();
+            t_wait += t0 - tw;
             const int k0 = q * per, k1 = (k0 + per < ni) ? k0 + per : ni;
             scatter_rows(L.h_iperm, k0, k1, lmax, acc, jrk, pot, list);
             t_scatter += wtime() - t0;
@@ -1732,6 +1743,9 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += 1;
     const double wt = wtime();
     L.time_grav += (wt - wt_in) - t_scatter; L.time_reduce += t_scatter;      // reference buckets: grav(s), nb(s)
+    L.ctr[GPUNB_B200_CTR_HOST_PACK_MS] += (wt_packed - wt_in) * 1e3;
+    L.ctr[GPUNB_B200_CTR_HOST_WAIT_MS] += t_wait * 1e3;
+    L.ctr[GPUNB_B200_CTR_HOST_SCATTER_MS] += t_scatter * 1e3;
     L.last_ni = ni; L.last_lmax = lmax; L.last_on_host = true;
 }
 

@@ -23,10 +23,11 @@ _HERE = Path(__file__).resolve().parent
 _c_int_p = C.POINTER(C.c_int)
 _c_dbl_p = C.POINTER(C.c_double)
 
-N_COUNTERS = 15
+N_COUNTERS = 19
 CTR = dict(grav_ms=0, grav_launches=1, launches=2, h2d_bytes=3, d2h_bytes=4, interactions=5,
            merge_ms=6, pot_ms=7, near_tiles=8, all_tiles=9,
-           tl_blocks=10, tl_isort_ms=11, tl_regf_ms=12, tl_merge_ms=13, tl_exch_ms=14)
+           tl_blocks=10, tl_isort_ms=11, tl_regf_ms=12, tl_merge_ms=13, tl_exch_ms=14,
+           host_pack_ms=15, host_enqueue_ms=16, host_wait_ms=17, host_scatter_ms=18)
 
 
 class LibraryMissing(RuntimeError):
@@ -156,6 +157,32 @@ class ForceLib:
                              C.byref(C.c_int(lmax)), C.byref(C.c_int(nnbmax)),
                              lst.ctypes.data_as(_c_int_p), C.byref(C.c_int(m_flag)))
         return acc[:ni], jrk[:ni], pot[:ni], lst[:ni]
+
+    def block_caller(self, h2, dtr, x, v, nimax: int, lmax: int, nnbmax: int, m_flag: int = 0, pad: int = 8):
+        """What the Fortran caller is (fpoly0.F:72-125, util_gpu.F:33-60): static input/output arrays and by-reference
+        scalars set up ONCE, then one bare ``gpunb_regf_`` call per i-block [i0, i0+ni) of the arrays -- no per-call
+        Python marshalling beyond four address additions.  Returns ``call(i0, ni) -> (acc, jrk, pot, list)`` (views
+        of the caller-owned output arrays, rows [:ni])."""
+        for a in (h2, dtr, x, v):
+            if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("block_caller needs C-contiguous float64 arrays")
+        n = h2.shape[0]
+        acc, jrk, pot, lst = self.caller_arrays(nimax, lmax, pad)
+        c_ni, c_lmax, c_nnbmax, c_mflag = C.c_int(0), C.c_int(lmax), C.c_int(nnbmax), C.c_int(m_flag)
+        fn = C.CFUNCTYPE(None, *([C.c_void_p] * 12))(("gpunb_regf_", self.lib))
+        a_h2, a_dtr, a_x, a_v = h2.ctypes.data, dtr.ctypes.data, x.ctypes.data, v.ctypes.data
+        fixed = (acc.ctypes.data, jrk.ctypes.data, pot.ctypes.data, C.addressof(c_lmax), C.addressof(c_nnbmax),
+                 lst.ctypes.data, C.addressof(c_mflag))
+        p_ni = C.addressof(c_ni)
+        keep = (h2, dtr, x, v, acc, jrk, pot, lst, c_ni, c_lmax, c_nnbmax, c_mflag)
+
+        def call(i0: int, ni: int, _keep=keep):
+            if ni > nimax or i0 < 0 or i0 + ni > n:
+                raise ValueError("i-block outside the arrays")
+            c_ni.value = ni
+            fn(p_ni, a_h2 + 8 * i0, a_dtr + 8 * i0, a_x + 24 * i0, a_v + 24 * i0, *fixed)
+            return acc[:ni], jrk[:ni], pot[:ni], lst[:ni]
+        return call
 
     def profile(self, irank: int = 0):
         self.lib.gpunb_profile_(C.byref(C.c_int(irank)))

@@ -29,18 +29,21 @@ for nslot in (1, 2, 3, 4, 3):
     if dist: dist.barrier()
     ms = min(lib.sweep_resident(0, 1024 * nblk, 1024, 600, 550, 0) for _ in range(2))
     print(f"rank {rank}/{world} nslot {nslot}: {ms / nblk * 1e3:7.1f} us per block  {1024.0 * nblk * n / ms * 1e-6:8.1f} Gint/s", flush=True)
-out = lib.caller_arrays(1024, 600)
+call = lib.block_caller(h2, dtr, x, v, 1024, 600, 550, 0)
 for nsub in (1, 2, 3, 4, 2):
     lib.set_tuning(0, nsub)
     for rep in range(2):
         if dist: dist.barrier()
         torch.cuda.synchronize()
+        lib.reset_counters()
         t0 = time.perf_counter()
         for b in range(48):
-            i0 = b * 1024
-            lib.regf_into(out, h2[i0:i0 + 1024], dtr[i0:i0 + 1024], x[i0:i0 + 1024], v[i0:i0 + 1024], 600, 550, 0)
+            call(b * 1024, 1024)
         t = time.perf_counter() - t0
-    print(f"rank {rank}/{world} nsub {nsub}: {t / 48 * 1e6:7.1f} us per gpunb_regf_ call  {1024.0 * 48 * n / t * 1e-9:8.1f} Gint/s", flush=True)
+    c = lib.counters()
+    print(f"rank {rank}/{world} nsub {nsub}: {t / 48 * 1e6:7.1f} us per gpunb_regf_ call  {1024.0 * 48 * n / t * 1e-9:8.1f} Gint/s | host us/call: "
+          f"pack {c['host_pack_ms'] / 48 * 1e3:5.1f} enqueue {c['host_enqueue_ms'] / 48 * 1e3:5.1f} wait {c['host_wait_ms'] / 48 * 1e3:6.1f} "
+          f"scatter {c['host_scatter_ms'] / 48 * 1e3:5.1f} | device us/call: pair kernels {c['grav_ms'] / 48 * 1e3:6.1f} tail {c['merge_ms'] / 48 * 1e3:5.1f}", flush=True)
 lib.close()
 if dist:
     dist.barrier(); lib.nccl_finalize(); dist.destroy_process_group()

@@ -37,7 +37,7 @@ def check(lib, tag, rank=0):
         a, j, p, l = lib.fetch_last(lmax)
         lib.set_tuning(0, 1)                        # one pair-kernel launch per call: same summation order as the sweep
         a2, j2, p2, l2 = lib.regf(h2[11264:12288], dtr[11264:12288], x[11264:12288], v[11264:12288], lmax, nnbmax, m_flag)
-        lib.set_tuning(0, 2)
+        lib.set_tuning(0, 4)
         assert np.array_equal(a, a2) and np.array_equal(p, p2) and not oracle_lib.list_rows_equal(l, l2)
         lib.close()
     print(f"{tag} rank {rank}: ok", flush=True)

@@ -1,0 +1,44 @@
+"""Ahmad-Cohen driver (nbody6ppgpu_b200/hermite_ac.py): energy conservation over the regular-force ABI.
+
+CPU: the driver itself is exercised with the reference's AVX library behind the ABI (the checker; tests only).
+GPU: the north-star's drift criterion -- the energy error over one N-body time unit with libgpunb_b200.so is laid
+beside the reference library's on the identical snapshot and integrator settings."""
+import numpy as np
+import pytest
+
+from nbody6ppgpu_b200 import hermite_ac as H
+from nbody6ppgpu_b200 import snapshots as S
+
+
+def test_ac_driver_conserves_energy_with_reference_library(ref_avx):
+    if ref_avx is None:
+        pytest.skip("oracle/_ref not built")
+    m, x, v = S.plummer(256, 5, "equal")
+    ac = H.AhmadCohen(ref_avx, m, x, v, nnbopt=30)
+    try:
+        st = ac.run(0.25)
+    finally:
+        ac.close()
+    e0, e1 = st.energies[0][1], st.energies[-1][1]
+    assert abs(e0 + 0.25) < 0.05                      # Plummer sphere in N-body units: E = -1/4
+    assert abs((e1 - e0) / e0) < 1e-4, (e0, e1)
+    assert st.t == 0.25 and st.reg_steps > 256 and st.irr_steps > st.reg_steps
+    assert np.all(ac.t0 == 0.25)                      # block steps re-synchronise at multiples of dtmax
+    assert 0.3 * 30 < ac.nnb.mean() < 3.0 * 30        # RS control keeps the lists near NNBOPT
+    # lists are ascending, self-free and irregular steps never exceed regular ones
+    for i in range(0, 256, 17):
+        row = ac.nb[i, :ac.nnb[i]]
+        assert np.all(np.diff(row) > 0) and i not in row
+    assert np.all(ac.dt <= ac.dtr)
+
+
+@pytest.mark.gpu
+def test_energy_drift_matches_reference_library(b200, ref_avx):
+    """Energy error over one N-body time unit: this library vs the reference's behind the same driver."""
+    out = {}
+    for name, lib in (("b200", b200), ("avx", ref_avx)):
+        de, st = H.energy_drift(lib, n=1024, seed=5, t_end=1.0, nnbopt=40)
+        out[name] = de
+        print(f"{name}: dE/E = {de:+.3e} over t=1 ({st.irr_steps} irregular, {st.reg_steps} regular steps, "
+              f"{st.regf_calls} gpunb_regf_ calls, {st.overflow_retries} overflow retries, {st.wall_total:.1f} s)")
+    assert abs(out["b200"]) <= 3.0 * abs(out["avx"]) + 1e-5, out

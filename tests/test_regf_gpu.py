@@ -215,7 +215,7 @@ def test_resident_sweep_matches_abi(b200, nslot):
             assert np.array_equal(a, a2) and np.array_equal(j, j2) and np.array_equal(p, p2)
             assert not oracle_lib.list_rows_equal(l, l2)
     finally:
-        b200.set_tuning(3, 2)
+        b200.set_tuning(3, 4)
         b200.close()
 
 
@@ -239,5 +239,5 @@ def test_subblock_pipeline_matches_single_launch(b200, ni):
             for q in range(3):
                 assert oracle_lib.relerr(out[nsub][q], out[1][q]) < 1e-12
     finally:
-        b200.set_tuning(3, 2)
+        b200.set_tuning(3, 4)
         b200.close()
