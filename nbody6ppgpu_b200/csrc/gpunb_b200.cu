@@ -1212,8 +1212,13 @@ void lib_devinit(int irank)
         CUDA_CHECK(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
         int prio_least = 0, prio_greatest = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-        for (Slot &sl : d.slots) {
-            CUDA_CHECK(cudaStreamCreateWithPriority(&sl.lo, cudaStreamNonBlocking, prio_least));
+        // hi streams: highest priority.  lo streams: descending priority with the slot number, so that when the pair
+        // kernels of several slots are pending at once (sub-blocks of one call) they take the SMs in slot order.
+        for (int q = 0; q < MAX_SLOTS; q++) {
+            Slot &sl = d.slots[q];
+            int plo = prio_greatest + 1 + q;
+            if (plo > prio_least) plo = prio_least;
+            CUDA_CHECK(cudaStreamCreateWithPriority(&sl.lo, cudaStreamNonBlocking, plo));
             CUDA_CHECK(cudaStreamCreateWithPriority(&sl.hi, cudaStreamNonBlocking, prio_greatest));
             CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_regf, cudaEventDisableTiming));
             CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
