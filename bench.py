@@ -157,7 +157,7 @@ def run_reference(args, rank, world):
     os.environ["OMP_NUM_THREADS"] = str(threads)
     ref = load_reference_avx()
     if ref is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgpunb_ref_avx.so not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libgpunb_ref_avx.so not built"})
         return
     m, x, v, h2, dtr, rs0 = make_snapshot(args.n, args.m_flag)
     ref.open(args.n + 10, 0)
@@ -171,7 +171,7 @@ def run_reference(args, rank, world):
     ref.close()
     val = inter_tot / t_tot * 1e-9
     sample = f"send + {blocks} regf calls of {BLOCK} i-particles against all {args.n} j per step"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_tot / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -180,7 +180,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def measured_peaks():
@@ -193,8 +193,31 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Native libraries (NCCL's version banner, the force libraries' '# Open ...' lines) write to fd 1; the driver wants
+    ONE JSON line on stdout.  Everything but emit() goes to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, line)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     # before torch/numpy pull in libgomp: the reference AVX library asserts threads <= 32 (reg.avx.cpp:7,103)
     os.environ["OMP_NUM_THREADS"] = str(cpu_threads())
     rank = int(os.environ.get("RANK", "0"))
@@ -384,7 +407,7 @@ def main():
                                    "sample": f"reference reg.avx.cpp (oracle/_ref): send + {args.cpu_blocks} regf calls of {BLOCK} i against all {n} j, {t:.1f} s"}
         else:
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "oracle/_ref not built"}
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":
