@@ -83,6 +83,12 @@ enum {
     GPUNB_B200_CTR_HOST_ENQUEUE_MS,
     GPUNB_B200_CTR_HOST_WAIT_MS,
     GPUNB_B200_CTR_HOST_SCATTER_MS,
+    /* gpunb_send_: calls, wall-clock ms in total / in the chunked pinned staging + upload loop, and device ms of the
+     * tile construction (keys, radix sort, tilepack) */
+    GPUNB_B200_CTR_SENDS,
+    GPUNB_B200_CTR_SEND_MS,
+    GPUNB_B200_CTR_SEND_STAGE_MS,
+    GPUNB_B200_CTR_SEND_TILES_MS,
     GPUNB_B200_CTR_COUNT
 };
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);
@@ -101,7 +107,9 @@ void  gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], doubl
 
 /* Pipeline depth: nslot = pipeline slots a resident sweep cycles through (1 = one block after the other on one
  * stream), nsub = sub-blocks one gpunb_regf_ call is split into (1 = the whole i-block in one pair-kernel launch).
- * Values outside 1..4 leave the setting unchanged.  Environment: GPUNB_B200_NSLOT / GPUNB_B200_NSUB. */
+ * A call is split only while every sub-block keeps >= 256 i-particles and ~1.5e8 pairs (the pair kernel must outlast
+ * the fixed costs of a launch); nsub = -k forces k sub-blocks of any size (tests).  Other values leave the setting
+ * unchanged.  Environment: GPUNB_B200_NSLOT / GPUNB_B200_NSUB. */
 void  gpunb_b200_set_tuning(int nslot, int nsub);
 
 /* FP32 pipe microbenchmark: returns achieved scalar/packed FFMA TFLOP/s on device 0

@@ -1159,6 +1159,7 @@ struct Lib {
     int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
+    bool nsub_forced = false;      // tests: split even when the pair kernels would be too short to be worth it
     int last_slot = 0; bool last_on_host = false;
     double time_send = 0, time_grav = 0, time_reduce = 0, time_out = 0;      // reference: gpunb.velocity.cu:557-559
     long long numInter = 0; int icall = 0, ini = 0, isend = 0;
@@ -1442,32 +1443,60 @@ void lib_close()
     L.nbmax = 0;
 }
 
-// The snapshot is staged once in pinned memory (m | x | v), copied to every local device asynchronously and
-// converted there; each device tiles only its own j-shard.  The reference converts fp64->fp32 on ONE host
-// thread per GPU (gpunb.velocity.cu:721-724) and uses a blocking copy (:726).
+// The snapshot is staged in pinned memory (m | x | v) in chunks: a few host threads copy chunk c+1 while the copy
+// engine uploads chunk c to every local device, then each device converts and tiles its own j-shard.  The reference
+// converts fp64->fp32 on ONE host thread per GPU (gpunb.velocity.cu:721-724) and uses a blocking copy (:726).
+void threaded_copy(double *dst, const double *src, size_t n)
+{
+    const int T = L.host_threads;
+    if (T <= 1 || n < 65536) { memcpy(dst, src, sizeof(double) * n); return; }
+#pragma omp parallel for num_threads(T) schedule(static)
+    for (int t = 0; t < T; t++) {
+        const size_t lo = n * t / T, hi = n * (t + 1) / T;
+        memcpy(dst + lo, src + lo, sizeof(double) * (hi - lo));
+    }
+}
+
 void lib_send(int nj, const double *mj, const double *xj, const double *vj)
 {
     if (!L.is_open) FATAL("gpunb_send called while the library is closed");
     if (nj > L.nbmax) FATAL("gpunb_send: nj=%d exceeds nbmax=%d given to gpunb_open", nj, L.nbmax);
-    L.time_send -= wtime();
+    const double wt0 = wtime();
+    L.time_send -= wt0;
     L.isend++;
     L.nbody = nj;
     double *h = L.h_j;
-    memcpy(h, mj, sizeof(double) * nj);
-    memcpy(h + nj, xj, sizeof(double) * 3 * nj);
-    memcpy(h + 4 * (size_t)nj, vj, sizeof(double) * 3 * nj);
     const int R = total_ranks();
     for (size_t g = 0; g < L.devs.size(); g++) {
         Dev &d = L.devs[g];
         set_dev(d);
-        const int r = L.sh.on ? L.sh.rank : (int)g;
         int nloc;
-        shard_tiles(r, R, nj, nloc);
+        shard_tiles(L.sh.on ? L.sh.rank : (int)g, R, nj, nloc);
         ensure_j_capacity(d, nj, nloc * TJ);
         d.nj_total = nj; d.ntiles = nloc; d.nj = nloc * TJ;
-        CUDA_CHECK(cudaMemcpyAsync(d.jraw, h, sizeof(double) * 7 * nj, cudaMemcpyHostToDevice, d.st));
+    }
+    constexpr int CHUNK = 1 << 17;                    // particles per chunk (7 MB)
+    for (int c0 = 0; c0 < nj; c0 += CHUNK) {
+        const size_t c = (size_t)c0, n = (size_t)((nj - c0 < CHUNK) ? nj - c0 : CHUNK);
+        threaded_copy(h + c, mj + c, n);
+        threaded_copy(h + nj + 3 * c, xj + 3 * c, 3 * n);
+        threaded_copy(h + 4 * (size_t)nj + 3 * c, vj + 3 * c, 3 * n);
+        for (Dev &d : L.devs) {
+            set_dev(d);
+            CUDA_CHECK(cudaMemcpyAsync(d.jraw + c, h + c, sizeof(double) * n, cudaMemcpyHostToDevice, d.st));
+            CUDA_CHECK(cudaMemcpyAsync(d.jraw + nj + 3 * c, h + nj + 3 * c, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, d.st));
+            CUDA_CHECK(cudaMemcpyAsync(d.jraw + 4 * (size_t)nj + 3 * c, h + 4 * (size_t)nj + 3 * c, sizeof(double) * 3 * n,
+                                       cudaMemcpyHostToDevice, d.st));
+        }
+    }
+    const double wt1 = wtime();
+    for (size_t g = 0; g < L.devs.size(); g++) {
+        Dev &d = L.devs[g];
+        set_dev(d);
         L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * nj;
-        build_tiles(d, nj, d.jraw, d.jraw + nj, d.jraw + 4 * (size_t)nj, d.jtile, d.jidx, r, R, nloc);
+        CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
+        build_tiles(d, nj, d.jraw, d.jraw + nj, d.jraw + 4 * (size_t)nj, d.jtile, d.jidx, L.sh.on ? L.sh.rank : (int)g, R, d.ntiles);
+        CUDA_CHECK(cudaEventRecord(d.evs1, d.st));
         CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, d.nanflag, sizeof(int), cudaMemcpyDeviceToHost, d.st));
     }
     for (size_t g = 0; g < L.devs.size(); g++) {
@@ -1475,7 +1504,14 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
         CUDA_CHECK(cudaStreamSynchronize(L.devs[g].st));
         if (L.h_flag[g]) FATAL("gpunb_send: NaN in j-particle data (reference asserts here, gpunb.velocity.cu:72-78)");
     }
-    L.time_send += wtime();
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, L.devs[0].evs0, L.devs[0].evs1));
+    const double wt2 = wtime();
+    L.ctr[GPUNB_B200_CTR_SEND_TILES_MS] += ms;
+    L.ctr[GPUNB_B200_CTR_SEND_STAGE_MS] += (wt1 - wt0) * 1e3;
+    L.ctr[GPUNB_B200_CTR_SEND_MS] += (wt2 - wt0) * 1e3;
+    L.ctr[GPUNB_B200_CTR_SENDS] += 1;
+    L.time_send += wt2;
 }
 
 struct Plan { int n_itiles, S, n_items; };
@@ -1687,8 +1723,11 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     // One call = nsub sub-blocks of the Morton-sorted i-block, each in its own pipeline slot: the pair kernel of
     // sub-block q+1 fills the SMs as the CTAs of sub-block q retire, and merge, the PCIe writes of the result rows
     // and the host-side copy into the caller's arrays of sub-block q all run beside it.
+    // A sub-block must keep the pair kernel busy for >~150 us, or its fixed costs (launch, merge, exchange step) show.
     int nsub = (G == 1) ? L.nsub : 1;
     if (nsub > ni / 256) nsub = ni / 256;
+    const double pairs = (double)ni * root.nj;
+    if (!L.nsub_forced && nsub > (int)(pairs / 1.5e8)) nsub = (int)(pairs / 1.5e8);
     if (nsub < 1) nsub = 1;
     IBlock ib[MAX_RANKS];
     const int *ipm[MAX_RANKS];
@@ -2010,7 +2049,8 @@ void gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double
 void gpunb_b200_set_tuning(int nslot, int nsub)
 {
     if (nslot >= 1 && nslot <= MAX_SLOTS) L.nslot = nslot;
-    if (nsub >= 1 && nsub <= MAX_SLOTS) L.nsub = nsub;
+    if (nsub >= 1 && nsub <= MAX_SLOTS) { L.nsub = nsub; L.nsub_forced = false; }
+    if (nsub <= -1 && nsub >= -MAX_SLOTS) { L.nsub = -nsub; L.nsub_forced = true; }
 }
 
 // tuning aid: per-work-item start/end timestamps (ns) of the LAST regf_kernel launch (GPUNB_B200_STATS=2)

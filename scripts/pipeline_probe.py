@@ -23,6 +23,12 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 nblk = int(sys.argv[2]) if len(sys.argv) > 2 else 192
 m, x, v = S.plummer(n, 1, "kroupa"); h2, dtr = S.radii_nnb(x, m, 200.0)
 lib.open(n + 10, rank); lib.send(m, x, v); lib.set_radii(h2, dtr)
+lib.reset_counters()
+for _ in range(5):
+    lib.send(m, x, v)
+c = lib.counters()
+print(f"rank {rank}/{world} gpunb_send_ N={n}: {c['send_ms'] / c['sends']:6.2f} ms per call (pinned staging + upload loop {c['send_stage_ms'] / c['sends']:6.2f} ms, "
+      f"tile construction on the device {c['send_tiles_ms'] / c['sends']:6.2f} ms)", flush=True)
 for nslot in (1, 2, 3, 4, 3):
     lib.set_tuning(nslot, 0)
     lib.sweep_resident(0, 1024 * 16, 1024, 600, 550, 0)

@@ -23,6 +23,7 @@ def check(lib, tag, rank=0):
         lib.open(n + 10, rank)
         lib.send(m, x, v)
         for isel in (slice(0, 1024), slice(n - 700, n), slice(5000, 5003)):
+            lib.set_tuning(0, -2 if isel.start == 0 else 4)      # first block: forced sub-blocks (two exchange steps per call)
             acc, jrk, pot, lst = lib.regf(h2[isel], dtr[isel], x[isel], v[isel], lmax, nnbmax, m_flag)
             a64, j64, p64, l64, band, _ = o.regf_f64(m, x, v, h2[isel], dtr[isel], x[isel], v[isel], lmax, nnbmax, m_flag, 4.0)
             bad = [i for i in oracle_lib.list_rows_equal(lst, l64) if band[i] > 4.0]

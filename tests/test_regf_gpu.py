@@ -231,7 +231,7 @@ def test_subblock_pipeline_matches_single_launch(b200, ni):
     try:
         out = {}
         for nsub in (1, 2, 4):
-            b200.set_tuning(0, nsub)
+            b200.set_tuning(0, -nsub)             # forced: these blocks are too small to be split on their own
             for rep in range(2):      # twice: slot buffers are reused
                 out[nsub] = [a.copy() for a in b200.regf(h2[:ni], dtr[:ni], x[:ni], v[:ni], 400, 350, 0)]
         for nsub in (2, 4):
