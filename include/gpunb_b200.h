@@ -105,6 +105,26 @@ float gpunb_b200_sweep_resident(int *i0, int *ni, int *block, int *lmax, int *nn
 void  gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double pot[],
                             int *lmax, int *list);
 
+/* Device-resident predictor: replaces the host predictor xbpredall (src/Main/xbpredall.f:15-26,
+ * called at intgrt.F:516-520) AND the gpunb_send_ upload that follows it before every regular block (intgrt.F:912-918).
+ * Fortran-callable like the reference entries (scalars by reference, REAL*8, X(3,N) == x[N][3]); strictly additive:
+ * a caller that never uses them keeps the reference behaviour.
+ *   state_all     BODY, X0, X0DOT, F, FDOT, T0 of all nj j-particles (arrays start at IFIRST) in the integrator's own
+ *                 conventions: F is half the force, FDOT one sixth of its derivative (xbpredall.f:20-25).  Call once,
+ *                 and again whenever the particle table is re-ordered (KS creation / termination, escapers).
+ *   state_update  the same six quantities for the n particles idx[k] (0-based, relative to the j array, like the
+ *                 returned neighbour indices) the integrator has just advanced; entry k belongs to particle idx[k].
+ *   predict_send  X = ((FDOT*S + F)*S + X0DOT)*S + X0, XDOT = (FDOT*1.5S + F)*2S + X0DOT with S = time - T0 for the
+ *                 first nj particles, on the device, in fp64 without FMA contraction (bit-for-bit an unfused host
+ *                 build), followed by the tile construction of gpunb_send_.  gpunb_regf_ then works as usual.
+ *   get_predicted predicted x / xdot of the particles idx[k] from that snapshot. */
+void gpunb_b200_state_all_(int *nj, double body[], double x0[][3], double x0dot[][3], double f[][3], double fdot[][3],
+                           double t0[]);
+void gpunb_b200_state_update_(int *n, int idx[], double body[], double x0[][3], double x0dot[][3], double f[][3],
+                              double fdot[][3], double t0[]);
+void gpunb_b200_predict_send_(int *nj, double *time);
+void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3]);
+
 /* Pipeline depth: nslot = pipeline slots a resident sweep cycles through (1 = one block after the other on one
  * stream), nsub = sub-blocks one gpunb_regf_ call is split into (1 = the whole i-block in one pair-kernel launch).
  * A call is split only while every sub-block keeps >= 256 i-particles and ~1.5e8 pairs (the pair kernel must outlast

@@ -1050,6 +1050,53 @@ __global__ void pot_merge_kernel(const double *__restrict__ part, int S, int ni,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device-resident predictor.  The state of the j-set -- BODY, X0, X0DOT, F (= force / 2), FDOT
+// (= derivative / 6) and T0 in the integrator's own conventions -- lives on the device; predict_kernel restates
+// xbpredall.f:17-26 in fp64,
+//     S = TIME - T0;  X = ((FDOT*S + F)*S + X0DOT)*S + X0;  XDOT = (FDOT*(1.5 S) + F)*(2 S) + X0DOT,
+// and writes the m | x | v snapshot gpunb_send_ would have uploaded.  Products and sums are rounded separately
+// (__dmul_rn / __dadd_rn: no FMA contraction), i.e. the arithmetic of an unfused host build, so that the
+// predicted snapshot is bit-for-bit the one a host predictor followed by gpunb_send_ produces.
+// State layout: body[cap] | x0[3 cap] | x0dot[3 cap] | f[3 cap] | fdot[3 cap] | t0[cap].
+// ---------------------------------------------------------------------------------------------
+__global__ void predict_kernel(int n, int cap, const double *__restrict__ st, double time, double *__restrict__ jraw)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double *x0 = st + cap, *v0 = st + 4 * (size_t)cap, *f = st + 7 * (size_t)cap, *fd = st + 10 * (size_t)cap;
+    const double s = __dsub_rn(time, st[13 * (size_t)cap + j]);
+    const double s1 = __dmul_rn(1.5, s), s2 = __dmul_rn(2.0, s);
+    jraw[j] = st[j];
+    double *x = jraw + n, *v = jraw + 4 * (size_t)n;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const size_t q = 3 * (size_t)j + c;
+        const double F = f[q], FD = fd[q], V0 = v0[q];
+        x[q] = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(FD, s), F), s), V0), s), x0[q]);
+        v[q] = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(FD, s1), F), s2), V0);
+    }
+}
+// rec: n records of 14 doubles (body, x0[3], x0dot[3], f[3], fdot[3], t0) for the particles idx[k] (0-based)
+__global__ void state_scatter_kernel(int n, int cap, int nj, const int *__restrict__ idx, const double *__restrict__ rec,
+                                     double *__restrict__ st, int *__restrict__ bad)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int j = idx[k];
+    if (j < 0 || j >= nj) { atomicExch(bad, 1); return; }
+    const double *r = rec + 14 * (size_t)k;
+    st[j] = r[0];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        st[cap + 3 * (size_t)j + c] = r[1 + c];
+        st[4 * (size_t)cap + 3 * (size_t)j + c] = r[4 + c];
+        st[7 * (size_t)cap + 3 * (size_t)j + c] = r[7 + c];
+        st[10 * (size_t)cap + 3 * (size_t)j + c] = r[10 + c];
+    }
+    st[13 * (size_t)cap + j] = r[13];
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
 double wtime() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + 1e-6 * tv.tv_usec; }
@@ -1094,6 +1141,8 @@ struct Dev {
     Slot slots[MAX_SLOTS];
     cudaEvent_t ev_fork = nullptr;
     int *iperm_all = nullptr; size_t iperm_all_n = 0;   // Morton order of every block of a resident sweep
+    double *state = nullptr; int state_cap = 0, state_n = 0;   // device-resident predictor state (14 doubles per particle)
+    double *upd_rec = nullptr; int *upd_idx = nullptr; int upd_cap = 0; int *upd_bad = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs0 = nullptr, evs1 = nullptr, evdone = nullptr;
     int nsm = 0, warps_resident = 0, variant = DEFAULT_VARIANT, itile = 32, oversub = OVERSUB;
     // j: full fp64 snapshot (m | x | v, packed for the current nj_total) and the tiles of this device's shard
@@ -1151,6 +1200,7 @@ struct Lib {
     Shard sh;
     int nbmax = 0, nbody = 0;
     double *h_j = nullptr; size_t h_j_n = 0;          // pinned staging: 7*nj doubles
+    double *h_upd = nullptr; int *h_upd_idx = nullptr; int h_upd_cap = 0;    // pinned staging of state updates
     double *h_i = nullptr;                            // 8*NIMAX doubles (pinned staging of the i-block)
     // results of gpunb_regf_: MAPPED pinned host memory that merge / combine write straight over PCIe (zero copy),
     // and the device-side aliases of those buffers
@@ -1213,13 +1263,11 @@ void lib_devinit(int irank)
         CUDA_CHECK(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
         int prio_least = 0, prio_greatest = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-        // hi streams: highest priority.  lo streams: descending priority with the slot number, so that when the pair
-        // kernels of several slots are pending at once (sub-blocks of one call) they take the SMs in slot order.
+        // hi streams: highest priority; lo streams: lowest, all equal (descending priorities by slot were measured:
+        // they do not fix the start order of sub-blocks and cost 2 % in 3-slot sweeps, profiles/r01p_pipeline_probe_1gpu.txt)
         for (int q = 0; q < MAX_SLOTS; q++) {
             Slot &sl = d.slots[q];
-            int plo = prio_greatest + 1 + q;
-            if (plo > prio_least) plo = prio_least;
-            CUDA_CHECK(cudaStreamCreateWithPriority(&sl.lo, cudaStreamNonBlocking, plo));
+            CUDA_CHECK(cudaStreamCreateWithPriority(&sl.lo, cudaStreamNonBlocking, prio_least));
             CUDA_CHECK(cudaStreamCreateWithPriority(&sl.hi, cudaStreamNonBlocking, prio_greatest));
             CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_regf, cudaEventDisableTiming));
             CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
@@ -1434,18 +1482,32 @@ void lib_close()
             dev_free(sl.done_ctr); sl.used = false;
         }
         dev_free(d.iperm_all); d.iperm_all_n = 0;
+        dev_free(d.state); d.state_cap = d.state_n = 0; dev_free(d.upd_rec); dev_free(d.upd_idx); dev_free(d.upd_bad); d.upd_cap = 0;
         dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.stats); dev_free(d.wtime);
         dev_free(d.jidx);
         dev_free(d.nanflag);
     }
     host_free(L.h_j); L.h_j_n = 0; host_free(L.h_i); host_free(L.h_f); host_free(L.h_list); L.h_list_n = 0;
-    host_free(L.h_iperm);
+    host_free(L.h_iperm); host_free(L.h_upd); host_free(L.h_upd_idx); L.h_upd_cap = 0;
     L.nbmax = 0;
 }
 
 // The snapshot is staged in pinned memory (m | x | v) in chunks: a few host threads copy chunk c+1 while the copy
 // engine uploads chunk c to every local device, then each device converts and tiles its own j-shard.  The reference
 // converts fp64->fp32 on ONE host thread per GPU (gpunb.velocity.cu:721-724) and uses a blocking copy (:726).
+void finish_send(int nj, double wt0, const char *who);
+void set_shards(int nj)
+{
+    const int R = total_ranks();
+    for (size_t g = 0; g < L.devs.size(); g++) {
+        Dev &d = L.devs[g];
+        set_dev(d);
+        int nloc;
+        shard_tiles(L.sh.on ? L.sh.rank : (int)g, R, nj, nloc);
+        ensure_j_capacity(d, nj, nloc * TJ);
+        d.nj_total = nj; d.ntiles = nloc; d.nj = nloc * TJ;
+    }
+}
 void threaded_copy(double *dst, const double *src, size_t n)
 {
     const int T = L.host_threads;
@@ -1466,15 +1528,7 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
     L.isend++;
     L.nbody = nj;
     double *h = L.h_j;
-    const int R = total_ranks();
-    for (size_t g = 0; g < L.devs.size(); g++) {
-        Dev &d = L.devs[g];
-        set_dev(d);
-        int nloc;
-        shard_tiles(L.sh.on ? L.sh.rank : (int)g, R, nj, nloc);
-        ensure_j_capacity(d, nj, nloc * TJ);
-        d.nj_total = nj; d.ntiles = nloc; d.nj = nloc * TJ;
-    }
+    set_shards(nj);
     constexpr int CHUNK = 1 << 17;                    // particles per chunk (7 MB)
     for (int c0 = 0; c0 < nj; c0 += CHUNK) {
         const size_t c = (size_t)c0, n = (size_t)((nj - c0 < CHUNK) ? nj - c0 : CHUNK);
@@ -1489,11 +1543,18 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
                                        cudaMemcpyHostToDevice, d.st));
         }
     }
+    L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * nj * L.devs.size();
+    finish_send(nj, wt0, "gpunb_send");
+}
+
+// Tiles of every device's j-shard from the m | x | v snapshot already in d.jraw (uploaded or predicted on the device).
+void finish_send(int nj, double wt0, const char *who)
+{
+    const int R = total_ranks();
     const double wt1 = wtime();
     for (size_t g = 0; g < L.devs.size(); g++) {
         Dev &d = L.devs[g];
         set_dev(d);
-        L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * nj;
         CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
         build_tiles(d, nj, d.jraw, d.jraw + nj, d.jraw + 4 * (size_t)nj, d.jtile, d.jidx, L.sh.on ? L.sh.rank : (int)g, R, d.ntiles);
         CUDA_CHECK(cudaEventRecord(d.evs1, d.st));
@@ -1502,7 +1563,7 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
     for (size_t g = 0; g < L.devs.size(); g++) {
         set_dev(L.devs[g]);
         CUDA_CHECK(cudaStreamSynchronize(L.devs[g].st));
-        if (L.h_flag[g]) FATAL("gpunb_send: NaN in j-particle data (reference asserts here, gpunb.velocity.cu:72-78)");
+        if (L.h_flag[g]) FATAL("%s: NaN in j-particle data (reference asserts here, gpunb.velocity.cu:72-78)", who);
     }
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, L.devs[0].evs0, L.devs[0].evs1));
@@ -1512,6 +1573,144 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
     L.ctr[GPUNB_B200_CTR_SEND_MS] += (wt2 - wt0) * 1e3;
     L.ctr[GPUNB_B200_CTR_SENDS] += 1;
     L.time_send += wt2;
+}
+
+// ---- device-resident predictor: host side ------------------------------------------------------
+void ensure_state(Dev &d, int nj)
+{
+    set_dev(d);
+    if (nj > d.state_cap) {
+        if (d.state_n > 0) FATAL("gpunb_b200_state: nj=%d exceeds the state capacity %d (call gpunb_b200_state_all_ with the new set)", nj, d.state_cap);
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        dev_free(d.state);
+        d.state_cap = (nj > L.nbmax ? nj : L.nbmax) + 64;
+        dev_alloc(d.state, (size_t)14 * d.state_cap);
+    }
+    if (!d.upd_bad) { dev_alloc(d.upd_bad, 1); CUDA_CHECK(cudaMemsetAsync(d.upd_bad, 0, sizeof(int), d.st)); }
+}
+
+// Full state of the j-set (once, and again whenever the caller's particle table is re-ordered: KS creation /
+// termination, escapers).  Arrays start at the first j-particle (IFIRST), like the arguments of gpunb_send_.
+void lib_state_all(int nj, const double *body, const double *x0, const double *x0dot, const double *f, const double *fdot,
+                   const double *t0)
+{
+    if (!L.is_open) FATAL("gpunb_b200_state_all called while the library is closed");
+    if (nj > L.nbmax) FATAL("gpunb_b200_state_all: nj=%d exceeds nbmax=%d given to gpunb_open", nj, L.nbmax);
+    const double *src[6] = {body, x0, x0dot, f, fdot, t0};
+    const int width[6] = {1, 3, 3, 3, 3, 1};
+    for (Dev &d : L.devs) { d.state_n = 0; ensure_state(d, nj); }
+    // staged through the pinned snapshot buffer (7 (nbmax+64) doubles) in two halves: {body, x0, x0dot} then {f, fdot, t0}
+    for (int half = 0; half < 2; half++) {
+        double *h = L.h_j;
+        size_t off = 0;
+        for (int q = 3 * half; q < 3 * half + 3; q++) {
+            threaded_copy(h + off, src[q], (size_t)width[q] * nj);
+            off += (size_t)width[q] * nj;
+        }
+        for (Dev &d : L.devs) {
+            set_dev(d);
+            size_t o = 0;
+            const size_t dst_off[6] = {0, (size_t)d.state_cap, 4 * (size_t)d.state_cap, 7 * (size_t)d.state_cap,
+                                       10 * (size_t)d.state_cap, 13 * (size_t)d.state_cap};
+            for (int q = 3 * half; q < 3 * half + 3; q++) {
+                CUDA_CHECK(cudaMemcpyAsync(d.state + dst_off[q], h + o, sizeof(double) * width[q] * nj, cudaMemcpyHostToDevice, d.st));
+                o += (size_t)width[q] * nj;
+            }
+        }
+        for (Dev &d : L.devs) { set_dev(d); CUDA_CHECK(cudaStreamSynchronize(d.st)); }     // h is reused
+    }
+    for (Dev &d : L.devs) d.state_n = nj;
+    L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 14.0 * nj * L.devs.size();
+}
+
+// State of the n particles idx[k] (0-based, relative to the j array like the neighbour indices) that the integrator
+// has just advanced: entry k of every array belongs to particle idx[k].
+void lib_state_update(int n, const int *idx, const double *body, const double *x0, const double *x0dot, const double *f,
+                      const double *fdot, const double *t0)
+{
+    if (!L.is_open) FATAL("gpunb_b200_state_update called while the library is closed");
+    if (n <= 0) return;
+    if (L.devs[0].state_n <= 0) FATAL("gpunb_b200_state_update before gpunb_b200_state_all_");
+    if (n > L.h_upd_cap) {
+        for (Dev &d : L.devs) { set_dev(d); CUDA_CHECK(cudaStreamSynchronize(d.st)); }
+        host_free(L.h_upd); host_free(L.h_upd_idx);
+        L.h_upd_cap = n + 4096;
+        host_alloc(L.h_upd, (size_t)14 * L.h_upd_cap);
+        host_alloc(L.h_upd_idx, (size_t)L.h_upd_cap);
+    }
+    for (int k = 0; k < n; k++) {
+        double *r = L.h_upd + 14 * (size_t)k;
+        r[0] = body[k];
+        for (int c = 0; c < 3; c++) {
+            r[1 + c] = x0[3 * (size_t)k + c]; r[4 + c] = x0dot[3 * (size_t)k + c];
+            r[7 + c] = f[3 * (size_t)k + c];  r[10 + c] = fdot[3 * (size_t)k + c];
+        }
+        r[13] = t0[k];
+        L.h_upd_idx[k] = idx[k];
+    }
+    for (size_t g = 0; g < L.devs.size(); g++) {
+        Dev &d = L.devs[g];
+        set_dev(d);
+        if (n > d.upd_cap) {
+            CUDA_CHECK(cudaStreamSynchronize(d.st));
+            dev_free(d.upd_rec); dev_free(d.upd_idx);
+            d.upd_cap = L.h_upd_cap;
+            dev_alloc(d.upd_rec, (size_t)14 * d.upd_cap); dev_alloc(d.upd_idx, (size_t)d.upd_cap);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(d.upd_rec, L.h_upd, sizeof(double) * 14 * n, cudaMemcpyHostToDevice, d.st));
+        CUDA_CHECK(cudaMemcpyAsync(d.upd_idx, L.h_upd_idx, sizeof(int) * n, cudaMemcpyHostToDevice, d.st));
+        state_scatter_kernel<<<(n + 127) / 128, 128, 0, d.st>>>(n, d.state_cap, d.state_n, d.upd_idx, d.upd_rec, d.state, d.upd_bad);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, d.upd_bad, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+    }
+    for (size_t g = 0; g < L.devs.size(); g++) {      // the pinned staging is reused by the next update
+        set_dev(L.devs[g]);
+        CUDA_CHECK(cudaStreamSynchronize(L.devs[g].st));
+        if (L.h_flag[g]) FATAL("gpunb_b200_state_update: particle index outside [0, %d)", L.devs[g].state_n);
+    }
+    L.ctr[GPUNB_B200_CTR_H2D_BYTES] += (sizeof(double) * 14.0 + sizeof(int)) * n * L.devs.size();
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += (double)L.devs.size();
+}
+
+// xbpredall + gpunb_send_ in one call, without the PCIe upload: predict every j-particle to `time` on the device and
+// rebuild the tiles.  nj may be smaller than the state (the caller's NTOT shrinks); it cannot exceed it.
+void lib_predict_send(int nj, double time)
+{
+    if (!L.is_open) FATAL("gpunb_b200_predict_send called while the library is closed");
+    const double wt0 = wtime();
+    L.time_send -= wt0;
+    L.isend++;
+    L.nbody = nj;
+    set_shards(nj);
+    for (Dev &d : L.devs) {
+        if (nj > d.state_n) FATAL("gpunb_b200_predict_send: nj=%d but the device state holds %d particles", nj, d.state_n);
+        set_dev(d);
+        predict_kernel<<<(nj + 255) / 256, 256, 0, d.st>>>(nj, d.state_cap, d.state, time, d.jraw);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += (double)L.devs.size();
+    finish_send(nj, wt0, "gpunb_b200_predict_send");
+}
+
+// Predicted x / xdot of the particles idx[k] from the snapshot built by the last predict_send (the caller needs them
+// for the i-block it passes to gpunb_regf_ when it does not run its own full predictor).
+void lib_get_predicted(int n, const int *idx, double *x, double *xdot)
+{
+    if (!L.is_open) FATAL("gpunb_b200_get_predicted called while the library is closed");
+    Dev &d = L.devs[0];
+    set_dev(d);
+    const int nj = d.nj_total;
+    // small n: gather on the host from two strided copies would need n round trips; copy the two arrays once instead
+    static std::vector<double> hx;
+    hx.resize((size_t)6 * nj);
+    CUDA_CHECK(cudaMemcpyAsync(hx.data(), d.jraw + nj, sizeof(double) * 6 * nj, cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    for (int k = 0; k < n; k++) {
+        const int j = idx[k];
+        if (j < 0 || j >= nj) FATAL("gpunb_b200_get_predicted: index %d outside [0, %d)", j, nj);
+        for (int c = 0; c < 3; c++) { x[3 * (size_t)k + c] = hx[3 * (size_t)j + c]; xdot[3 * (size_t)k + c] = hx[3 * (size_t)nj + 3 * (size_t)j + c]; }
+    }
+    L.ctr[GPUNB_B200_CTR_D2H_BYTES] += sizeof(double) * 6.0 * nj;
 }
 
 struct Plan { int n_itiles, S, n_items; };
@@ -2045,6 +2244,18 @@ void gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double
     }
     scatter_rows(nullptr, 0, ni, lmax, &acc[0][0], &jrk[0][0], pot, list);
 }
+
+void gpunb_b200_state_all_(int *nj, double body[], double x0[][3], double x0dot[][3], double f[][3], double fdot[][3], double t0[])
+{
+    lib_state_all(*nj, body, &x0[0][0], &x0dot[0][0], &f[0][0], &fdot[0][0], t0);
+}
+void gpunb_b200_state_update_(int *n, int idx[], double body[], double x0[][3], double x0dot[][3], double f[][3],
+                              double fdot[][3], double t0[])
+{
+    lib_state_update(*n, idx, body, &x0[0][0], &x0dot[0][0], &f[0][0], &fdot[0][0], t0);
+}
+void gpunb_b200_predict_send_(int *nj, double *time) { lib_predict_send(*nj, *time); }
+void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3]) { lib_get_predicted(*n, idx, &x[0][0], &xdot[0][0]); }
 
 void gpunb_b200_set_tuning(int nslot, int nsub)
 {

@@ -92,6 +92,12 @@ class ForceLib:
             L.gpunb_b200_nccl_finalize.restype = None
             L.gpunb_b200_set_tuning.argtypes = [C.c_int, C.c_int]
             L.gpunb_b200_set_tuning.restype = None
+            L.gpunb_b200_state_all_.argtypes = [_c_int_p] + [_c_dbl_p] * 6
+            L.gpunb_b200_state_update_.argtypes = [_c_int_p, _c_int_p] + [_c_dbl_p] * 6
+            L.gpunb_b200_predict_send_.argtypes = [_c_int_p, _c_dbl_p]
+            L.gpunb_b200_get_predicted_.argtypes = [_c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p]
+            for f in (L.gpunb_b200_state_all_, L.gpunb_b200_state_update_, L.gpunb_b200_predict_send_, L.gpunb_b200_get_predicted_):
+                f.restype = None
         self.nj = 0
 
     # ---- the reference interface -------------------------------------------------------------
@@ -275,6 +281,32 @@ class ForceLib:
     def nccl_finalize(self):
         self._need_b200()
         self.lib.gpunb_b200_nccl_finalize()
+
+    # device-resident predictor (xbpredall.f + gpunb_send_ without the upload); F = force/2, FDOT = derivative/6
+    def state_all(self, body, x0, x0dot, f, fdot, t0):
+        self._need_b200()
+        body = _f64(body); nj = body.shape[0]
+        a = [_f64(x0, (nj, 3)), _f64(x0dot, (nj, 3)), _f64(f, (nj, 3)), _f64(fdot, (nj, 3)), _f64(t0, (nj,))]
+        self.nj = nj
+        self.lib.gpunb_b200_state_all_(C.byref(C.c_int(nj)), _dp(body), *[_dp(q) for q in a])
+
+    def state_update(self, idx, body, x0, x0dot, f, fdot, t0):
+        self._need_b200()
+        idx = np.ascontiguousarray(idx, dtype=np.int32); n = idx.shape[0]
+        a = [_f64(body, (n,)), _f64(x0, (n, 3)), _f64(x0dot, (n, 3)), _f64(f, (n, 3)), _f64(fdot, (n, 3)), _f64(t0, (n,))]
+        self.lib.gpunb_b200_state_update_(C.byref(C.c_int(n)), idx.ctypes.data_as(_c_int_p), *[_dp(q) for q in a])
+
+    def predict_send(self, nj: int, time: float):
+        self._need_b200()
+        self.nj = nj
+        self.lib.gpunb_b200_predict_send_(C.byref(C.c_int(nj)), C.byref(C.c_double(time)))
+
+    def get_predicted(self, idx):
+        self._need_b200()
+        idx = np.ascontiguousarray(idx, dtype=np.int32); n = idx.shape[0]
+        x = np.zeros((n, 3)); v = np.zeros((n, 3))
+        self.lib.gpunb_b200_get_predicted_(C.byref(C.c_int(n)), idx.ctypes.data_as(_c_int_p), _dp(x), _dp(v))
+        return x, v
 
     def set_tuning(self, nslot: int = 0, nsub: int = 0):
         """Pipeline depth: slots of a resident sweep / sub-blocks of one gpunb_regf_ call (0 = leave unchanged)."""

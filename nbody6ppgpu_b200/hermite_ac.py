@@ -54,8 +54,12 @@ def _pow2_floor(dt, dtmax):
 
 class AhmadCohen:
     def __init__(self, lib, m, x, v, *, nnbopt=40, lmax=128, eta_i=0.02, eta_r=0.02, dtmax=0.125, dtmin=2.0 ** -22,
-                 m_flag=0, rs0=None):
+                 m_flag=0, rs0=None, device_predictor=False):
         self.lib = lib
+        # device_predictor: regular blocks call gpunb_b200_predict_send_ (state kept on the device, updated with the
+        # particles advanced since the last regular block) instead of uploading the host-predicted snapshot
+        self.device_predictor = bool(device_predictor)
+        self._dirty = None
         self.n = n = m.shape[0]
         self.m = np.ascontiguousarray(m, dtype=np.float64)
         self.x0 = np.array(x, dtype=np.float64)
@@ -84,10 +88,20 @@ class AhmadCohen:
 
     # ---- force pieces ------------------------------------------------------------------------
     def _predict(self, t):
-        d = (t - self.t0)[:, None]
-        xp = self.x0 + d * (self.v0 + d * (0.5 * self.f + d * (1.0 / 6.0) * self.fd))
-        vp = self.v0 + d * (self.f + d * 0.5 * self.fd)
+        """xbpredall.f:17-26, in the integrator's conventions (F2 = F/2, FD6 = FDOT/6), fp64 without fusion."""
+        s = (t - self.t0)[:, None]
+        f2, fd6 = 0.5 * self.f, self.fd * (1.0 / 6.0)
+        xp = ((fd6 * s + f2) * s + self.v0) * s + self.x0
+        vp = (fd6 * (1.5 * s) + f2) * (2.0 * s) + self.v0
         return xp, vp
+
+    def _push_state(self, idx=None):
+        """Device-resident predictor: full state, or the particles just advanced (gpunb_b200_state_all_/_update_)."""
+        if idx is None:
+            self.lib.state_all(self.m, self.x0, self.v0, 0.5 * self.f, self.fd * (1.0 / 6.0), self.t0)
+        else:
+            self.lib.state_update(idx, self.m[idx], self.x0[idx], self.v0[idx], 0.5 * self.f[idx],
+                                  self.fd[idx] * (1.0 / 6.0), self.t0[idx])
 
     def _irregular(self, idx, xp, vp, lists, counts):
         """fp64 force and derivative on particles idx from their neighbour lists (rows of -1 padded indices)."""
@@ -109,11 +123,18 @@ class AhmadCohen:
         fd = (mr3[:, :, None] * (dv - rv[:, :, None] * dx)).sum(1)
         return fi, fd
 
-    def _regular(self, idx, xp, vp):
+    def _regular(self, idx, xp, vp, t=0.0):
         """gpunb_send_ + gpunb_regf_ over the block idx; returns (fr, frd, lists[-1 padded], counts)."""
         st = self.stats
         t0 = time.perf_counter()
-        self.lib.send(self.m, xp, vp)
+        if self.device_predictor and self._dirty is not None:
+            dirty = np.nonzero(self._dirty)[0]
+            if dirty.size:
+                self._push_state(dirty)
+                self._dirty[:] = False
+            self.lib.predict_send(self.n, t)
+        else:
+            self.lib.send(self.m, xp, vp)
         st.wall_send += time.perf_counter() - t0
         nreg = idx.size
         fr = np.zeros((nreg, 3)); frd = np.zeros((nreg, 3))
@@ -159,6 +180,9 @@ class AhmadCohen:
         self.dt = np.maximum(_pow2_floor(dt_i, self.dtmax), self.dtmin)
         self.dtr = np.maximum(_pow2_floor(np.maximum(dt_r, self.dt), self.dtmax), self.dt)
         self._adjust_rs(idx, counts)
+        if self.device_predictor:
+            self._push_state()
+            self._dirty = np.zeros(self.n, dtype=bool)
 
     def _adjust_rs(self, idx, counts):
         """Volume rule towards NNBOPT members with a stabilising factor (regcor_gpu.F:623-760, simplified)."""
@@ -197,7 +221,7 @@ class AhmadCohen:
             st.reg_blocks += 1; st.reg_steps += reg.size
             # regular polynomial over the OLD list at both ends (list changes corrected, regcor_gpu.F:510-552)
             fi_old, fid_old = self._irregular(reg, xp, vp, self.nb[reg], self.nnb[reg])
-            frn, frdn, lnew, cnew = self._regular(reg, xp, vp)
+            frn, frdn, lnew, cnew = self._regular(reg, xp, vp, tn)
             fin, fidn = self._irregular(reg, xp, vp, lnew, cnew)
             ftot, fdtot = fin + frn, fidn + frdn
             fr_oldlist, frd_oldlist = ftot - fi_old, fdtot - fid_old
@@ -217,6 +241,8 @@ class AhmadCohen:
         self.fi[act], self.fid[act] = fi_new, fid_new
         self.f[act], self.fd[act] = f1, fd1
         st.irr_steps += act.size
+        if self._dirty is not None:
+            self._dirty[act] = True
 
         # new irregular steps: block quantised, at most doubled, doubled only on even block boundaries
         dt_new = self._aarseth(self.eta_i, f1, fd1, a2, a3, dti)

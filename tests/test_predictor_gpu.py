@@ -1,0 +1,66 @@
+"""Device-resident predictor (gpunb_b200_state_all_/_state_update_/_predict_send_): the snapshot predicted
+on the device must be BIT-FOR-BIT the one an (unfused fp64) host predictor restating xbpredall.f:17-26 uploads with
+gpunb_send_, so every downstream result is identical."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from nbody6ppgpu_b200 import hermite_ac as H
+from nbody6ppgpu_b200 import snapshots as S
+
+pytestmark = pytest.mark.gpu
+
+
+def host_predict(x0, v0, f2, fd6, t0, time):
+    s = (time - t0)[:, None]
+    return ((fd6 * s + f2) * s + v0) * s + x0, (fd6 * (1.5 * s) + f2) * (2.0 * s) + v0
+
+
+def test_predict_send_equals_host_predict_plus_send(b200):
+    n = 5003
+    rng = np.random.default_rng(11)
+    m, x0, v0 = S.plummer(n, 7, "kroupa")
+    f2 = 0.5 * rng.normal(size=(n, 3)); fd6 = rng.normal(size=(n, 3)) * 3.0
+    t0 = rng.integers(0, 64, size=n) * 2.0 ** -10
+    time = 0.0703125
+    h2, dtr = S.radii(x0, m, S.rs0_for_nnb(n, 60.0))
+    isel = slice(100, 100 + 777)
+    b200.open(n + 10, 0)
+    try:
+        def both(nj, t):
+            xp, vp = host_predict(x0[:nj], v0[:nj], f2[:nj], fd6[:nj], t0[:nj], t)
+            b200.send(m[:nj], xp, vp)
+            a = [q.copy() for q in b200.regf(h2[isel], dtr[isel], xp[isel], vp[isel], 400, 350, 0)]
+            b200.predict_send(nj, t)
+            gx, gv = b200.get_predicted(np.arange(isel.start, isel.stop))
+            assert np.array_equal(gx, xp[isel]) and np.array_equal(gv, vp[isel])
+            b = b200.regf(h2[isel], dtr[isel], xp[isel], vp[isel], 400, 350, 0)
+            for q in range(3):
+                assert np.array_equal(a[q], b[q])
+            assert not oracle_lib.list_rows_equal(a[3], b[3])
+
+        b200.state_all(m, x0, v0, f2, fd6, t0)
+        both(n, time)
+        # the integrator advances a few particles: only they are pushed
+        idx = rng.choice(n, size=300, replace=False).astype(np.int32)
+        x0[idx] += 1e-3 * rng.normal(size=(300, 3)); v0[idx] += 1e-3 * rng.normal(size=(300, 3))
+        f2[idx] *= 1.01; fd6[idx] *= 0.99; t0[idx] = time; m[idx] *= 1.0 + 1e-6
+        b200.state_update(idx, m[idx], x0[idx], v0[idx], f2[idx], fd6[idx], t0[idx])
+        both(n, time + 2.0 ** -7)
+        both(n - 131, time + 2.0 ** -6)           # NTOT shrinks: the first nj particles of the state
+    finally:
+        b200.close()
+
+
+def test_ac_driver_with_device_predictor_is_bitwise_the_host_path(b200):
+    m, x, v = S.plummer(512, 3, "equal")
+    res = {}
+    for dev in (False, True):
+        ac = H.AhmadCohen(b200, m, x, v, nnbopt=30, device_predictor=dev)
+        try:
+            st = ac.run(0.25)
+        finally:
+            ac.close()
+        res[dev] = (ac.x0.copy(), ac.v0.copy(), st.energies[-1][1], st.regf_calls)
+    assert np.array_equal(res[False][0], res[True][0]) and np.array_equal(res[False][1], res[True][1])
+    assert res[False][2] == res[True][2] and res[False][3] == res[True][3]
