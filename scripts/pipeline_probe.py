@@ -29,6 +29,22 @@ for _ in range(5):
 c = lib.counters()
 print(f"rank {rank}/{world} gpunb_send_ N={n}: {c['send_ms'] / c['sends']:6.2f} ms per call (pinned staging + upload loop {c['send_stage_ms'] / c['sends']:6.2f} ms, "
       f"tile construction on the device {c['send_tiles_ms'] / c['sends']:6.2f} ms)", flush=True)
+z3 = np.zeros((n, 3))
+lib.state_all(m, x, v, z3, z3, np.zeros(n))
+lib.reset_counters()
+t0 = time.perf_counter()
+for k in range(5):
+    lib.predict_send(n, 1e-3 * (k + 1))
+tp = (time.perf_counter() - t0) / 5
+idx = np.arange(0, n, n // 2000, dtype=np.int32)[:2000]
+t0 = time.perf_counter()
+for k in range(5):
+    lib.state_update(idx, m[idx], x[idx], v[idx], z3[idx], z3[idx], np.zeros(idx.size))
+tu = (time.perf_counter() - t0) / 5
+c = lib.counters()
+print(f"rank {rank}/{world} gpunb_b200_predict_send_ N={n}: {tp * 1e3:6.2f} ms per call (device tile construction {c['send_tiles_ms'] / c['sends']:6.2f} ms); "
+      f"state_update of {idx.size} particles {tu * 1e3:6.3f} ms", flush=True)
+lib.send(m, x, v)
 for nslot in (1, 2, 3, 4, 3):
     lib.set_tuning(nslot, 0)
     lib.sweep_resident(0, 1024 * 16, 1024, 600, 550, 0)
