@@ -1049,6 +1049,18 @@ __global__ void pot_merge_kernel(const double *__restrict__ part, int S, int ni,
     out[ii] = p;
 }
 
+// gpupot over j-shards: phi_i = sum over shards, in rank order (deterministic), of the shard partials.  parts[r] may
+// be peer pointers (one process driving several GPUs) or rows of an all-gathered buffer (one process per GPU).
+struct PotParts { const double *p[MAX_RANKS]; };
+__global__ void pot_sum_kernel(const PotParts parts, int R, int ni, double *__restrict__ out)
+{
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii >= ni) return;
+    double p = 0.0;
+    for (int r = 0; r < R; r++) p += parts.p[r][ii];
+    out[ii] = p;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Device-resident predictor.  The state of the j-set -- BODY, X0, X0DOT, F (= force / 2), FDOT
 // (= derivative / 6) and T0 in the integrator's own conventions -- lives on the device; predict_kernel restates
@@ -1166,6 +1178,9 @@ struct Dev {
     int *rows = nullptr; size_t rows_ints = 0;                                     // shard rows (in-process multi-GPU)
     int *nanflag = nullptr;
     double *pot_part = nullptr, *pot_out = nullptr; size_t pot_part_n = 0, pot_out_n = 0;
+    // gpupot's own snapshot (m | x) and tiles of this device's shard, so that gpupot never disturbs the regf j-set
+    double *pot_jraw = nullptr; float *pot_jtile = nullptr; int *pot_jidx = nullptr; int pot_cap = 0;
+    double *pot_gather = nullptr; size_t pot_gather_n = 0;      // [R][ni] partial potentials of all ranks (NCCL mode)
 };
 
 // NCCL types / entry points, resolved with dlopen so that the library has no link-time NCCL dependency
@@ -2004,48 +2019,91 @@ void lib_profile(int irank)
 }
 
 // gpupot: may be called with the library closed (reference: gpupot.gpu.cu:69 only needs devinit).
+// Multi-GPU: the j-set is sharded like regf's -- every device tiles and sums over every R-th Hilbert tile
+// for the whole i-range -- and the partial potentials are added in rank order: over P2P by a kernel on the first
+// device (one process, several GPUs) or after ONE ncclAllGather of the ni partials (one process per GPU; this is the
+// path's real exchange step for gpupot, 8 B per i and rank).
 void lib_pot(int irank, int istart, int ni, int n, const double *m, const double *x, double *pot)
 {
     lib_devinit(irank);
     const double t0 = wtime();
     if (ni <= 0) return;
     if (istart < 1 || istart - 1 + ni > n) FATAL("gpupot: istart=%d ni=%d outside 1..n=%d", istart, ni, n);
-    Dev &d = L.devs[0];
-    set_dev(d);
-    // private buffers so that gpupot never disturbs the regf j-snapshot
-    static double *jraw = nullptr; static float *jtile = nullptr; static int *jidx = nullptr; static int cap = 0;
     static double *hpin = nullptr; static size_t hpin_n = 0;
-    const int ntiles = (n + TJ - 1) / TJ;
-    if (ntiles * TJ > cap) {
-        dev_free(jraw); dev_free(jtile); dev_free(jidx);
-        cap = ntiles * TJ;
-        dev_alloc(jraw, (size_t)4 * cap); dev_alloc(jtile, (size_t)ntiles * TILE_FLOATS); dev_alloc(jidx, (size_t)cap);
-    }
     if ((size_t)4 * n + ni > hpin_n) { host_free(hpin); hpin_n = (size_t)4 * n + ni + 1024; host_alloc(hpin, hpin_n); }
-    if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
-    memcpy(hpin, m, sizeof(double) * n);
-    memcpy(hpin + n, x, sizeof(double) * 3 * n);
-    CUDA_CHECK(cudaMemcpyAsync(jraw, hpin, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, d.st));
-    build_tiles(d, n, jraw, jraw + n, nullptr, jtile, jidx, 0, 1, ntiles);
+    threaded_copy(hpin, m, (size_t)n);
+    threaded_copy(hpin + n, x, (size_t)3 * n);
+    const int G = (int)L.devs.size(), R = total_ranks();
     const int n_it = (ni + 31) / 32;
-    int S = (d.nsm * 16 * 4) / n_it; if (S < 1) S = 1; if (S > ntiles) S = ntiles;
-    if ((size_t)S * ni > d.pot_part_n) { dev_free(d.pot_part); d.pot_part_n = (size_t)S * ni; dev_alloc(d.pot_part, d.pot_part_n); }
-    if ((size_t)ni > d.pot_out_n) { dev_free(d.pot_out); d.pot_out_n = ni; dev_alloc(d.pot_out, d.pot_out_n); }
-    CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
-    pot_kernel<<<(n_it * S + 3) / 4, 128, 0, d.st>>>(jtile, ntiles, S, jraw + n, istart - 1, ni, d.pot_part);
-    CUDA_CHECK(cudaGetLastError());
-    pot_merge_kernel<<<(ni + 127) / 128, 128, 0, d.st>>>(d.pot_part, S, ni, d.pot_out);
-    CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaEventRecord(d.evs1, d.st));
+    Dev &root = L.devs[0];
+    for (int g = 0; g < G; g++) {
+        Dev &d = L.devs[g];
+        set_dev(d);
+        int nloc;
+        shard_tiles(L.sh.on ? L.sh.rank : g, R, n, nloc);
+        const int ntiles_all = (n + TJ - 1) / TJ;
+        if (ntiles_all * TJ > d.pot_cap) {
+            CUDA_CHECK(cudaStreamSynchronize(d.st));
+            dev_free(d.pot_jraw); dev_free(d.pot_jtile); dev_free(d.pot_jidx);
+            d.pot_cap = ntiles_all * TJ;
+            dev_alloc(d.pot_jraw, (size_t)4 * d.pot_cap); dev_alloc(d.pot_jtile, (size_t)(ntiles_all + 2) * TILE_FLOATS);
+            dev_alloc(d.pot_jidx, (size_t)(ntiles_all + 2) * TJ);        // sized for R = 1: R may change between calls
+        }
+        if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
+        CUDA_CHECK(cudaMemcpyAsync(d.pot_jraw, hpin, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, d.st));
+        build_tiles(d, n, d.pot_jraw, d.pot_jraw + n, nullptr, d.pot_jtile, d.pot_jidx, L.sh.on ? L.sh.rank : g, R, nloc);
+        int S = (d.nsm * 16 * 4) / n_it; if (S < 1) S = 1; if (S > nloc) S = nloc > 0 ? nloc : 1;
+        if ((size_t)S * ni > d.pot_part_n) { CUDA_CHECK(cudaStreamSynchronize(d.st)); dev_free(d.pot_part); d.pot_part_n = (size_t)S * ni; dev_alloc(d.pot_part, d.pot_part_n); }
+        if ((size_t)ni > d.pot_out_n) { CUDA_CHECK(cudaStreamSynchronize(d.st)); dev_free(d.pot_out); d.pot_out_n = ni; dev_alloc(d.pot_out, d.pot_out_n); }
+        if (g == 0) CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
+        if (g > 0) CUDA_CHECK(cudaStreamWaitEvent(d.st, root.evdone, 0));        // the root has consumed d.pot_out of the previous call
+        pot_kernel<<<(n_it * S + 3) / 4, 128, 0, d.st>>>(d.pot_jtile, nloc, S, d.pot_jraw + n, istart - 1, ni, d.pot_part);
+        CUDA_CHECK(cudaGetLastError());
+        pot_merge_kernel<<<(ni + 127) / 128, 128, 0, d.st>>>(d.pot_part, S, ni, d.pot_out);
+        CUDA_CHECK(cudaGetLastError());
+        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
+        L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 4.0 * n;
+        if (g > 0) {
+            CUDA_CHECK(cudaEventRecord(d.evdone, d.st));
+            CUDA_CHECK(cudaStreamWaitEvent(root.st, d.evdone, 0));
+        }
+    }
+    set_dev(root);
+    const double *result = root.pot_out;
+    if (R > 1) {
+        if ((size_t)(R + 1) * ni > root.pot_gather_n) {
+            CUDA_CHECK(cudaStreamSynchronize(root.st));
+            dev_free(root.pot_gather); root.pot_gather_n = (size_t)(R + 1) * ni; dev_alloc(root.pot_gather, root.pot_gather_n);
+        }
+        PotParts pp;
+        if (L.sh.on) {
+            const int rc = L.sh.allgather(root.pot_out, root.pot_gather, (size_t)ni, NCCL_FLOAT64, L.sh.comm, root.st);
+            if (rc != 0) FATAL("gpupot: ncclAllGather failed: %s", L.sh.errstr ? L.sh.errstr(rc) : "?");
+            for (int r = 0; r < R; r++) pp.p[r] = root.pot_gather + (size_t)r * ni;
+        } else {
+            for (int g = 0; g < G; g++) pp.p[g] = L.devs[g].pot_out;
+        }
+        double *sum = root.pot_gather + (size_t)R * ni;
+        pot_sum_kernel<<<(ni + 127) / 128, 128, 0, root.st>>>(pp, R, ni, sum);
+        CUDA_CHECK(cudaGetLastError());
+        if (!L.sh.on) CUDA_CHECK(cudaEventRecord(root.evdone, root.st));
+        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+        result = sum;
+    }
+    CUDA_CHECK(cudaEventRecord(root.evs1, root.st));
     double *hout = hpin + 4 * (size_t)n;
-    CUDA_CHECK(cudaMemcpyAsync(hout, d.pot_out, sizeof(double) * ni, cudaMemcpyDeviceToHost, d.st));
-    CUDA_CHECK(cudaMemcpyAsync(L.h_flag, d.nanflag, sizeof(int), cudaMemcpyDeviceToHost, d.st));
-    CUDA_CHECK(cudaStreamSynchronize(d.st));
-    if (L.h_flag[0]) FATAL("gpupot: NaN in particle data");
-    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, d.evs0, d.evs1));
+    CUDA_CHECK(cudaMemcpyAsync(hout, result, sizeof(double) * ni, cudaMemcpyDeviceToHost, root.st));
+    for (int g = 0; g < G; g++) {
+        set_dev(L.devs[g]);
+        CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, L.devs[g].nanflag, sizeof(int), cudaMemcpyDeviceToHost, L.devs[g].st));
+    }
+    for (int g = G - 1; g >= 0; g--) {
+        set_dev(L.devs[g]);
+        CUDA_CHECK(cudaStreamSynchronize(L.devs[g].st));
+        if (L.h_flag[g]) FATAL("gpupot: NaN in particle data");
+    }
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, root.evs0, root.evs1));
     L.ctr[GPUNB_B200_CTR_POT_MS] += ms;
-    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
-    L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 4.0 * n;
     L.ctr[GPUNB_B200_CTR_D2H_BYTES] += sizeof(double) * (double)ni;
     memcpy(pot, hout, sizeof(double) * ni);
     const double t1 = wtime();

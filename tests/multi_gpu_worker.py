@@ -41,6 +41,11 @@ def check(lib, tag, rank=0):
         lib.set_tuning(0, 4)
         assert np.array_equal(a, a2) and np.array_equal(p, p2) and not oracle_lib.list_rows_equal(l, l2)
         lib.close()
+    # gpupot over the same j-shards (partials summed in rank order)
+    for istart, ni in ((1, n), (4097, 3001)):
+        phi = lib.gpupot(istart, ni, m, x)
+        ref = o.pot_f64(istart, ni, m, x)
+        assert float(np.max(np.abs(phi - ref) / ref)) <= 1e-6, (tag, istart, ni)
     print(f"{tag} rank {rank}: ok", flush=True)
 
 

@@ -35,10 +35,17 @@ def test_ac_driver_conserves_energy_with_reference_library(ref_avx):
 @pytest.mark.gpu
 def test_energy_drift_matches_reference_library(b200, ref_avx):
     """Energy error over one N-body time unit: this library vs the reference's behind the same driver."""
-    out = {}
+    out, stats = {}, {}
     for name, lib in (("b200", b200), ("avx", ref_avx)):
         de, st = H.energy_drift(lib, n=1024, seed=5, t_end=1.0, nnbopt=40)
         out[name] = de
+        stats[name] = {"irr_steps": st.irr_steps, "reg_steps": st.reg_steps, "regf_calls": st.regf_calls,
+                       "overflow_retries": st.overflow_retries, "wall_s": st.wall_total, "wall_regf_s": st.wall_regf,
+                       "wall_send_s": st.wall_send}
         print(f"{name}: dE/E = {de:+.3e} over t=1 ({st.irr_steps} irregular, {st.reg_steps} regular steps, "
               f"{st.regf_calls} gpunb_regf_ calls, {st.overflow_retries} overflow retries, {st.wall_total:.1f} s)")
+    import json, os
+    if os.environ.get("GPUNB_DRIFT_OUT"):         # GPU sessions keep the two numbers (profiles/)
+        with open(os.environ["GPUNB_DRIFT_OUT"], "w") as fh:
+            json.dump({"n": 1024, "t_end": 1.0, "nnbopt": 40, "dE_over_E": out, "stats": stats}, fh)
     assert abs(out["b200"]) <= 3.0 * abs(out["avx"]) + 1e-5, out

@@ -241,3 +241,41 @@ def test_subblock_pipeline_matches_single_launch(b200, ni):
     finally:
         b200.set_tuning(3, 4)
         b200.close()
+
+
+def test_full_size_parity_1M(b200, oracle):
+    """BASELINE.json's headline configuration (synthetic Plummer N=1M, Kroupa IMF, <nnb> ~ 200, lmax 600): blocks from
+    the core, the halo and a scattered gather against the oracle over ALL 10^6 j, plus the size-independent properties
+    (ascending self-including rows, determinism of a repeated call, sub-block split = single launch)."""
+    n = 1_000_000
+    m, x, v = S.plummer(n, 1, "kroupa")
+    h2, dtr = S.radii_nnb(x, m, 200.0)
+    r = np.sqrt((x ** 2).sum(1))
+    order = np.argsort(r)
+    rng = np.random.default_rng(3)
+    blocks = {"core": np.sort(order[:256]), "halo": np.sort(order[-256:]), "gather": np.sort(rng.choice(n, 256, replace=False))}
+    b200.open(n + 10, 0)
+    b200.send(m, x, v)
+    try:
+        for name, idx in blocks.items():
+            res = check_block(b200, oracle, m, x, v, h2, dtr, idx, 600, 550, 0)
+            print("N=1M", name, res)
+            acc, jrk, pot, lst = [a.copy() for a in b200.regf(h2[idx], dtr[idx], x[idx], v[idx], 600, 550, 0)]
+            ok = lst[:, 0] >= 0
+            for k in np.nonzero(ok)[0][::16]:
+                assert idx[k] in lst[k, 1:1 + lst[k, 0]]          # self is a member (the caller removes it, util_gpu.F:102-111)
+            a2 = b200.regf(h2[idx], dtr[idx], x[idx], v[idx], 600, 550, 0)
+            assert np.array_equal(acc, a2[0]) and np.array_equal(jrk, a2[1]) and not oracle_lib.list_rows_equal(lst, a2[3])
+        # a full 1024 block: 4 sub-blocks (the default at this size) against one launch
+        i0 = 300_000
+        sel = slice(i0, i0 + 1024)
+        b200.set_tuning(0, 4)
+        a4 = [a.copy() for a in b200.regf(h2[sel], dtr[sel], x[sel], v[sel], 600, 550, 0)]
+        b200.set_tuning(0, 1)
+        a1 = b200.regf(h2[sel], dtr[sel], x[sel], v[sel], 600, 550, 0)
+        assert not oracle_lib.list_rows_equal(a4[3], a1[3])
+        for q in range(3):
+            assert oracle_lib.relerr(a4[q], a1[q]) < 1e-12
+    finally:
+        b200.set_tuning(3, 4)
+        b200.close()
