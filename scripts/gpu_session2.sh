@@ -2,7 +2,7 @@
 # Session: tests (verbose tail incl. energy drift), probe, bench, ncu launch list + full capture.  Usage: scripts/gpu_session2.sh <tag>
 TAG=${1:-r01p}
 mkdir -p gpurun_out
-GPUNB_DRIFT_OUT=gpurun_out/energy_drift_$TAG.json timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | grep -v "^#\|^\[R" | tail -40 > gpurun_out/pytest_$TAG.log; tail -12 gpurun_out/pytest_$TAG.log
+GPUNB_DRIFT_OUT=gpurun_out/energy_drift_$TAG.json GPUNB_REFCUDA_OUT=gpurun_out/ref_cuda_$TAG.json timeout 900 python -m pytest tests -m gpu -q -s 2>&1 | grep -v "^#\|^\[R" | tail -40 > gpurun_out/pytest_$TAG.log; tail -12 gpurun_out/pytest_$TAG.log
 timeout 300 python scripts/pipeline_probe.py 1000000 192 > gpurun_out/probe_$TAG.log 2>&1; grep -v "^#\|^\[R" gpurun_out/probe_$TAG.log | tail -12
 timeout 400 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>/dev/null; cat gpurun_out/bench_ref_$TAG.json

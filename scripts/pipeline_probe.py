@@ -66,6 +66,12 @@ for nsub in (1, 2, 3, 4, 2):
     print(f"rank {rank}/{world} nsub {nsub}: {t / 48 * 1e6:7.1f} us per gpunb_regf_ call  {1024.0 * 48 * n / t * 1e-9:8.1f} Gint/s | host us/call: "
           f"pack {c['host_pack_ms'] / 48 * 1e3:5.1f} enqueue {c['host_enqueue_ms'] / 48 * 1e3:5.1f} wait {c['host_wait_ms'] / 48 * 1e3:6.1f} "
           f"scatter {c['host_scatter_ms'] / 48 * 1e3:5.1f} | device us/call: pair kernels {c['grav_ms'] / 48 * 1e3:6.1f} tail {c['merge_ms'] / 48 * 1e3:5.1f}", flush=True)
+lib.reset_counters()
+t0 = time.perf_counter()
+phi = lib.gpupot(1, n, m, x)
+tp = time.perf_counter() - t0
+c = lib.counters()
+print(f"rank {rank}/{world} gpupot_ N={n}: {tp * 1e3:7.1f} ms per call, kernels {c['pot_ms']:7.1f} ms = {float(n) * n / world / c['pot_ms'] * 1e-6:7.1f} Gpair/s per GPU", flush=True)
 lib.close()
 if dist:
     dist.barrier(); lib.nccl_finalize(); dist.destroy_process_group()

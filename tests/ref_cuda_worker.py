@@ -1,0 +1,72 @@
+"""Worker for tests/test_reference_cuda_gpu.py (own process: the reference's CUDA library asserts / aborts on its own
+errors).  Runs the reference's gpunb.velocity.cu + gpupot.gpu.cu, built UNMODIFIED for sm_100 into
+oracle/_ref/libgpunb_ref_gpu.so, and this repo's library on identical snapshots through the identical C-ABI on the
+same GPU: parity at N=16384 and the regular-force rate of both at N=1M ("the kernel to beat").  Prints one JSON line."""
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+os.environ.setdefault("OMP_NUM_THREADS", "8")
+os.environ.setdefault("GPU_LIST", "0")
+import numpy as np  # noqa: E402
+
+import oracle_lib  # noqa: E402
+from nbody6ppgpu_b200 import load, snapshots as S  # noqa: E402
+
+
+def main():
+    ref = oracle_lib.ref_gpu()
+    b200 = load()
+    ref.devinit(0); b200.devinit(0)
+    out = {}
+    # ---- parity, N = 16384, both neighbour criteria
+    n = 16384
+    m, x, v = S.plummer(n, 8, "kroupa")
+    for m_flag in (0, 1):
+        h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 100.0), 0.125, m_flag)
+        res = {}
+        for name, lib in (("b200", b200), ("ref", ref)):
+            lib.open(n + 10, 0)
+            lib.send(m, x, v)
+            res[name] = [a.copy() for a in lib.regf(h2[:1024], dtr[:1024], x[:1024], v[:1024], 400, 350, m_flag)]
+            lib.close()
+        bad = oracle_lib.list_rows_equal(res["b200"][3], res["ref"][3])
+        out[f"parity_mflag{m_flag}"] = {
+            "rows_differing": len(bad), "mean_nnb": float(res["ref"][3][:, 0].mean()),
+            "acc_relerr": oracle_lib.relerr(res["b200"][0], res["ref"][0]),
+            "jrk_relerr": oracle_lib.relerr(res["b200"][1], res["ref"][1]),
+            "pot_relerr": oracle_lib.relerr(res["b200"][2], res["ref"][2])}
+    phi_b = b200.gpupot(1, n, m, x); phi_r = ref.gpupot(1, n, m, x)
+    out["gpupot_relerr"] = float(np.max(np.abs(phi_b - phi_r) / np.abs(phi_r)))
+    # ---- rate at N = 1M, 1024 i per call, host arrays (both through the same caller)
+    n = int(os.environ.get("REFCUDA_N", "1000000"))
+    calls = 24
+    m, x, v = S.plummer(n, 1, "kroupa")
+    h2, dtr = S.radii_nnb(x, m, 200.0)
+    for name, lib in (("ref", ref), ("b200", b200)):
+        lib.open(n + 10, 0)
+        lib.send(m, x, v)
+        call = lib.block_caller(h2, dtr, x, v, 1024, 600, 550, 0)
+        for b in range(4):
+            call(b * 1024, 1024)
+        t0 = time.perf_counter()
+        nnb = 0
+        for b in range(calls):
+            lst = call((4 + b) * 1024, 1024)[3]
+            nnb += int(lst[:, 0].sum())
+        t = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        lib.send(m, x, v)
+        ts = time.perf_counter() - t0
+        lib.close()
+        out[f"rate_{name}"] = {"gint_per_s": 1024.0 * calls * n / t * 1e-9, "us_per_call": t / calls * 1e6,
+                               "send_ms": ts * 1e3, "mean_nnb": nnb / (1024.0 * calls), "n": n}
+    print("REFCUDA " + json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
