@@ -89,6 +89,7 @@ enum {
     GPUNB_B200_CTR_SEND_MS,
     GPUNB_B200_CTR_SEND_STAGE_MS,
     GPUNB_B200_CTR_SEND_TILES_MS,
+    GPUNB_B200_CTR_EXACT_QUADS,     /* quads (4 j) of NEAR tiles redone by the exact scalar body (GPUNB_B200_STATS=1) */
     GPUNB_B200_CTR_COUNT
 };
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);
@@ -131,6 +132,10 @@ void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3
  * the fixed costs of a launch); nsub = -k forces k sub-blocks of any size (tests).  Other values leave the setting
  * unchanged.  Environment: GPUNB_B200_NSLOT / GPUNB_B200_NSUB. */
 void  gpunb_b200_set_tuning(int nslot, int nsub);
+
+/* Tuning / A-B measurement: 1 = every quad of a NEAR tile through the exact scalar body (the kernel before the
+ * two-pass NEAR tiles), 0 = two-pass, -1 = follow GPUNB_B200_NEAR_EXACT. */
+void  gpunb_b200_set_near_exact(int on);
 
 /* FP32 pipe microbenchmark: returns achieved scalar/packed FFMA TFLOP/s on device 0
  * (mode 0: FFMA, 1: FFMA2 (f32x2), 2: FADD2, 3: FMUL2, 4: MUFU.RSQ Gop/s, 5: FFMA2+ALU mix). */

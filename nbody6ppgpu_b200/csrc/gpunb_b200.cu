@@ -370,7 +370,8 @@ struct RegfArgs {
     int          *seg;       // [nloc][S][segcap]
     int           segcap;
     int           force_near;  // debugging/tuning: classify every tile as NEAR
-    unsigned long long *stats; // optional: [0] near tiles, [1] all tiles (per warp-tile visit)
+    int           near_exact;  // debugging/tuning: every quad of a NEAR tile through the exact scalar body
+    unsigned long long *stats; // optional: [0] near tiles, [1] all tiles (per warp-tile visit), [2] exact quads of NEAR tiles
     unsigned long long *wtime; // optional: per work item start/end %globaltimer (tuning)
 };
 
@@ -416,13 +417,12 @@ __device__ __forceinline__ void accumulate(Acc &A, float rinv, float m, float rv
 // FAR tile: the bounding boxes prove that no pair of (this warp's i-particles, this tile) can satisfy the
 // neighbour criterion, so the body is the force alone: 27 FP32 ops + 1 MUFU per pair, two pairs per instruction.
 // Order of the accumulating FFMA2s: the triples share their first operand (reuse cache -> 2 distinct pairs).
-__device__ __forceinline__ void interact_far2(const float2 cx, const float2 cy, const float2 cz,
-                                              const float2 nvx, const float2 nvy, const float2 nvz, Acc2 &A,
-                                              float2 DX, float2 DY, float2 DZ, float2 VX, float2 VY, float2 VZ, float2 M)
+// far_force2: the part after the separation (dx, dy, dz) and r2 of two pairs are known.
+__device__ __forceinline__ void far_force2(const float2 dx, const float2 dy, const float2 dz, const float2 r2,
+                                           const float2 nvx, const float2 nvy, const float2 nvz, Acc2 &A,
+                                           float2 VX, float2 VY, float2 VZ, float2 M)
 {
-    const float2 dx = add2(DX, cx), dy = add2(DY, cy), dz = add2(DZ, cz);
     const float2 dvx = add2(VX, nvx), dvy = add2(VY, nvy), dvz = add2(VZ, nvz);
-    const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
     const float2 rv = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
     const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
     const float2 rinv2  = mul2(rinv, rinv);
@@ -433,6 +433,14 @@ __device__ __forceinline__ void interact_far2(const float2 cx, const float2 cy, 
     const float2 ix = fma2(rv3, dx, dvx), iy = fma2(rv3, dy, dvy), iz = fma2(rv3, dz, dvz);
     A.ax = fma2(mrinv3, dx, A.ax);   A.ay = fma2(mrinv3, dy, A.ay);   A.az = fma2(mrinv3, dz, A.az);
     A.jx = fma2(mrinv3, ix, A.jx);   A.jy = fma2(mrinv3, iy, A.jy);   A.jz = fma2(mrinv3, iz, A.jz);
+}
+__device__ __forceinline__ void interact_far2(const float2 cx, const float2 cy, const float2 cz,
+                                              const float2 nvx, const float2 nvy, const float2 nvz, Acc2 &A,
+                                              float2 DX, float2 DY, float2 DZ, float2 VX, float2 VY, float2 VZ, float2 M)
+{
+    const float2 dx = add2(DX, cx), dy = add2(DY, cy), dz = add2(DZ, cz);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    far_force2(dx, dy, dz, r2, nvx, nvy, nvz, A, VX, VY, VZ, M);
 }
 
 // NEAR tile: full body.
@@ -546,7 +554,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         }
     };
 
-    unsigned n_near = 0, n_all = 0;
+    unsigned n_near = 0, n_all = 0, n_exact = 0;
     int n = 0;
     for (int t = s; t < a.ntiles; t += a.S, n++) {
         const int st = n % NSTAGE;
@@ -571,6 +579,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         // with margins that dominate every fp32 rounding (positions/velocities rounded to fp32 by the predicate,
         // this arithmetic itself, the approximate sqrt).
         bool lane_far = true;
+        float cut2[IT];        // NEAR tiles: pairs with r2 >= cut2 can neither be neighbours nor need float-float separations
         {
             const float jh[3] = {h1.z, h1.w, h2v.x};
             const float jvc[3] = {h2v.y, h2v.z, h2v.w};
@@ -594,18 +603,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 // ~1e-7 of the smallest separation by sending tiles closer than half their own reach NEAR
                 const bool f = (d2 > rr * rr) && (d2 > 0.25f * sreach * sreach);
                 lane_far &= (f || iidx[k] < 0);
+                // per-PAIR version of the same two conditions, on the fp32 separation the FAR body computes: the
+                // predicate sees positions rounded to fp32 (|error| <= slack per particle), the separation itself
+                // carries ~2^-23 (|c| + h)
+                const float rc = rr + 4.f * (I[k].slack + 1.2e-7f * sreach);
+                cut2[k] = iidx[k] < 0 ? 0.f : fmaxf(rc * rc, 0.25f * sreach * sreach) * 1.00001f;
             }
         }
         const bool far = __all_sync(0xffffffffu, lane_far) && !a.force_near;
         n_all++;
         const float4 *c = reinterpret_cast<const float4 *>(tb + HDR);
-        if (far) {
-            float2 cx2[IT], cy2[IT], cz2[IT], nvx2[IT], nvy2[IT], nvz2[IT];
+        float2 cx2[IT], cy2[IT], cz2[IT], nvx2[IT], nvy2[IT], nvz2[IT];
 #pragma unroll
-            for (int k = 0; k < IT; k++) {
-                cx2[k] = dup2(I[k].cx); cy2[k] = dup2(I[k].cy); cz2[k] = dup2(I[k].cz);
-                nvx2[k] = dup2(I[k].nvx); nvy2[k] = dup2(I[k].nvy); nvz2[k] = dup2(I[k].nvz);
-            }
+        for (int k = 0; k < IT; k++) {
+            cx2[k] = dup2(I[k].cx); cy2[k] = dup2(I[k].cy); cz2[k] = dup2(I[k].cz);
+            nvx2[k] = dup2(I[k].nvx); nvy2[k] = dup2(I[k].nvy); nvz2[k] = dup2(I[k].nvz);
+        }
+        if (far) {
 #pragma unroll FAR_UNROLL_Q
             for (int q = 0; q < TJ / 4; q++) {
                 const float4 DX = c[C_DX * 16 + q], DY = c[C_DY * 16 + q], DZ = c[C_DZ * 16 + q];
@@ -622,27 +636,56 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 }
             }
         } else {
+            // NEAR tile.  Most of its pairs are still far from every lane's neighbour sphere: per quad of j the packed
+            // body computes the separations and r2 first, and only if ANY lane has a pair below its cut (cut2: the
+            // per-pair form of the FAR conditions) the quad is redone by the exact scalar body -- reference predicate
+            // on the fp32-rounded positions, float-float separation, Newton-refined rsqrt.  At N=1M the 32 spheres of
+            // a warp cover ~1-2 % of the j of its NEAR tiles, so a NEAR tile costs little more than a FAR one.
             n_near++;
-            Acc A[IT][2];
-#pragma unroll
-            for (int k = 0; k < IT; k++) {
-                A[k][0] = Acc{P[k].ax.x, P[k].ay.x, P[k].az.x, P[k].p.x, P[k].jx.x, P[k].jy.x, P[k].jz.x};
-                A[k][1] = Acc{P[k].ax.y, P[k].ay.y, P[k].az.y, P[k].p.y, P[k].jx.y, P[k].jy.y, P[k].jz.y};
-            }
 #pragma unroll 1
             for (int q = 0; q < TJ / 4; q++) {
+                const float4 DX = c[C_DX * 16 + q], DY = c[C_DY * 16 + q], DZ = c[C_DZ * 16 + q];
+                float2 dxa[IT], dya[IT], dza[IT], r2a[IT], dxb[IT], dyb[IT], dzb[IT], r2b[IT];
+                bool flag = a.near_exact != 0;
+#pragma unroll
+                for (int k = 0; k < IT; k++) {
+                    dxa[k] = add2(make_float2(DX.x, DX.y), cx2[k]); dya[k] = add2(make_float2(DY.x, DY.y), cy2[k]);
+                    dza[k] = add2(make_float2(DZ.x, DZ.y), cz2[k]);
+                    dxb[k] = add2(make_float2(DX.z, DX.w), cx2[k]); dyb[k] = add2(make_float2(DY.z, DY.w), cy2[k]);
+                    dzb[k] = add2(make_float2(DZ.z, DZ.w), cz2[k]);
+                    r2a[k] = fma2(dza[k], dza[k], fma2(dya[k], dya[k], mul2(dxa[k], dxa[k])));
+                    r2b[k] = fma2(dzb[k], dzb[k], fma2(dyb[k], dyb[k], mul2(dxb[k], dxb[k])));
+                    flag |= fminf(fminf(r2a[k].x, r2a[k].y), fminf(r2b[k].x, r2b[k].y)) < cut2[k];
+                }
                 const float4 VX = c[C_VX * 16 + q], VY = c[C_VY * 16 + q], VZ = c[C_VZ * 16 + q];
                 const float4 M  = c[C_M * 16 + q];
+                if (!__any_sync(0xffffffffu, flag)) {
+#pragma unroll
+                    for (int k = 0; k < IT; k++) {
+                        far_force2(dxa[k], dya[k], dza[k], r2a[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(VX.x, VX.y),
+                                   make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), make_float2(M.x, M.y));
+                        far_force2(dxb[k], dyb[k], dzb[k], r2b[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(VX.z, VX.w),
+                                   make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), make_float2(M.z, M.w));
+                    }
+                    continue;
+                }
+                n_exact++;
                 const float4 XH = c[C_XH * 16 + q], YH = c[C_YH * 16 + q], ZH = c[C_ZH * 16 + q];
                 const float4 XL = c[C_XL * 16 + q], YL = c[C_YL * 16 + q], ZL = c[C_ZL * 16 + q];
                 unsigned hit = 0;
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
-                    const bool h0 = interact_near<MFLAG>(I[k], A[k][0], VX.x, VY.x, VZ.x, M.x, XH.x, YH.x, ZH.x, XL.x, YL.x, ZL.x);
-                    const bool h1b = interact_near<MFLAG>(I[k], A[k][1], VX.y, VY.y, VZ.y, M.y, XH.y, YH.y, ZH.y, XL.y, YL.y, ZL.y);
-                    const bool h2b = interact_near<MFLAG>(I[k], A[k][0], VX.z, VY.z, VZ.z, M.z, XH.z, YH.z, ZH.z, XL.z, YL.z, ZL.z);
-                    const bool h3b = interact_near<MFLAG>(I[k], A[k][1], VX.w, VY.w, VZ.w, M.w, XH.w, YH.w, ZH.w, XL.w, YL.w, ZL.w);
+                    Acc A0 = Acc{P[k].ax.x, P[k].ay.x, P[k].az.x, P[k].p.x, P[k].jx.x, P[k].jy.x, P[k].jz.x};
+                    Acc A1 = Acc{P[k].ax.y, P[k].ay.y, P[k].az.y, P[k].p.y, P[k].jx.y, P[k].jy.y, P[k].jz.y};
+                    const bool h0 = interact_near<MFLAG>(I[k], A0, VX.x, VY.x, VZ.x, M.x, XH.x, YH.x, ZH.x, XL.x, YL.x, ZL.x);
+                    const bool h1b = interact_near<MFLAG>(I[k], A1, VX.y, VY.y, VZ.y, M.y, XH.y, YH.y, ZH.y, XL.y, YL.y, ZL.y);
+                    const bool h2b = interact_near<MFLAG>(I[k], A0, VX.z, VY.z, VZ.z, M.z, XH.z, YH.z, ZH.z, XL.z, YL.z, ZL.z);
+                    const bool h3b = interact_near<MFLAG>(I[k], A1, VX.w, VY.w, VZ.w, M.w, XH.w, YH.w, ZH.w, XL.w, YL.w, ZL.w);
                     hit |= ((h0 ? 1u : 0u) | (h1b ? 2u : 0u) | (h2b ? 4u : 0u) | (h3b ? 8u : 0u)) << (4 * k);
+                    P[k].ax = make_float2(A0.ax, A1.ax); P[k].ay = make_float2(A0.ay, A1.ay);
+                    P[k].az = make_float2(A0.az, A1.az); P[k].p  = make_float2(A0.p,  A1.p);
+                    P[k].jx = make_float2(A0.jx, A1.jx); P[k].jy = make_float2(A0.jy, A1.jy);
+                    P[k].jz = make_float2(A0.jz, A1.jz);
                 }
                 if (hit) {                             // rare: ~2e-4 of pairs are neighbours
                     const int pb = t * TJ + q * 4;
@@ -660,13 +703,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                         }
                     }
                 }
-            }
-#pragma unroll
-            for (int k = 0; k < IT; k++) {
-                P[k].ax = make_float2(A[k][0].ax, A[k][1].ax); P[k].ay = make_float2(A[k][0].ay, A[k][1].ay);
-                P[k].az = make_float2(A[k][0].az, A[k][1].az); P[k].p  = make_float2(A[k][0].p,  A[k][1].p);
-                P[k].jx = make_float2(A[k][0].jx, A[k][1].jx); P[k].jy = make_float2(A[k][0].jy, A[k][1].jy);
-                P[k].jz = make_float2(A[k][0].jz, A[k][1].jz);
             }
         }
         __syncwarp();                                  // every lane is done reading stage st
@@ -687,7 +723,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             a.cnt[(size_t)s * a.nloc + kl] = cnt[k];
         }
     }
-    if (a.stats && lane == 0) { atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all); }
+    if (a.stats && lane == 0) {
+        atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all);
+        atomicAdd(&a.stats[2], (unsigned long long)n_exact);
+    }
     if (a.wtime && lane == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); a.wtime[3 * w + 1] = t1; a.wtime[3 * w + 2] = n_near; }
 }
 
@@ -1001,6 +1040,9 @@ __global__ void __launch_bounds__(128) pot_kernel(const float *__restrict__ tile
     const int ii = it * 32 + lane;
     const int i = i0 + (ii < ni ? ii : ni - 1);
     const double xd = x[3 * (size_t)i], yd = x[3 * (size_t)i + 1], zd = x[3 * (size_t)i + 2];
+    // two-float position of i: tiles closer than half their own reach use float-float separations (below)
+    const float xh = (float)xd, yh = (float)yd, zh = (float)zd;
+    const float xl = (float)(xd - (double)xh), yl = (float)(yd - (double)yh), zl = (float)(zd - (double)zh);
     double phi = 0.0;
     float *b = sb[warp];
     for (int t = s; t < ntiles; t += S) {
@@ -1021,6 +1063,36 @@ __global__ void __launch_bounds__(128) pot_kernel(const float *__restrict__ tile
                     cz = (float)(((double)b[2] + (double)b[5]) - zd);
         const float4 *c = reinterpret_cast<const float4 *>(b + HDR);
         float acc = 0.f;
+        // dx = c + offset carries an absolute error of ~2^-23 (|c| + h): fine while the pair distance is comparable to
+        // the tile's reach (same rule as regf_kernel's FAR tiles).  Tiles closer than that -- the lane's own tile and
+        // its neighbours, where a close pair can carry most of phi_i -- take the separation from the two-float
+        // positions, (xh_j - xh_i) + (xl_j - xl_i), exact to ~2^-48 (the reference keeps float2 positions for the
+        // same reason, gpupot.gpu.cu:15-30).
+        float d2 = 0.f, sreach = 0.f;
+        {
+            const float cf[3] = {cx, cy, cz};
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const float g = fmaxf(fabsf(cf[q]) - b[6 + q], 0.f);
+                d2 = fmaf(g, g, d2);
+                sreach = fmaxf(sreach, fabsf(cf[q]) + b[6 + q]);
+            }
+        }
+        if (!__all_sync(0xffffffffu, d2 > 0.25f * sreach * sreach)) {
+            const float *g = tp + HDR;
+#pragma unroll 4
+            for (int j = 0; j < TJ; j++) {
+                const float dx = (g[C_XH * TJ + j] - xh) + (g[C_XL * TJ + j] - xl);
+                const float dy = (g[C_YH * TJ + j] - yh) + (g[C_YL * TJ + j] - yl);
+                const float dz = (g[C_ZH * TJ + j] - zh) + (g[C_ZL * TJ + j] - zl);
+                const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                float y = rsqrt_approx(r2);
+                y = y * fmaf(-0.5f * r2 * y, y, 1.5f);
+                acc += (r2 > 0.f) ? b[HDR + 3 * TJ + j] * y : 0.f;
+            }
+            phi += (double)acc;
+            continue;
+        }
 #pragma unroll 4
         for (int q = 0; q < TJ / 4; q++) {
             const float4 DX = c[q], DY = c[16 + q], DZ = c[32 + q], M = c[48 + q];
@@ -1224,6 +1296,7 @@ struct Lib {
     int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
+    int near_exact = -1;           // >= 0: overrides GPUNB_B200_NEAR_EXACT (gpunb_b200_set_near_exact)
     bool nsub_forced = false;      // tests: split even when the pair kernels would be too short to be worth it
     int last_slot = 0; bool last_on_host = false;
     double time_send = 0, time_grav = 0, time_reduce = 0, time_out = 0;      // reference: gpunb.velocity.cu:557-559
@@ -1470,7 +1543,7 @@ void lib_open(int nbmax, int irank)
         if (!d.ibuf)    dev_alloc(d.ibuf, (size_t)8 * NIMAX);
         if (!d.fr)      dev_alloc(d.fr, (size_t)8 * NIMAX);
         if (!d.iperm)   dev_alloc(d.iperm, (size_t)NIMAX);
-        if (!d.stats && getenv("GPUNB_B200_STATS")) { dev_alloc(d.stats, 2); CUDA_CHECK(cudaMemsetAsync(d.stats, 0, 16, d.st)); }
+        if (!d.stats && getenv("GPUNB_B200_STATS")) { dev_alloc(d.stats, 4); CUDA_CHECK(cudaMemsetAsync(d.stats, 0, 32, d.st)); }
         if (!d.wtime && getenv("GPUNB_B200_STATS") && atoi(getenv("GPUNB_B200_STATS")) >= 2) dev_alloc(d.wtime, (size_t)3 * 65536);
         if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
     }
@@ -1784,6 +1857,7 @@ void launch_regf(Dev &d, Slot &sl, cudaStream_t lo, cudaStream_t hi, const Job &
     RegfArgs a;
     a.tiles = d.jtile; a.jidx = d.jidx; a.ntiles = d.ntiles; a.iperm = iperm;
     { static int fn = -1; if (fn < 0) { const char *e = getenv("GPUNB_B200_FORCE_NEAR"); fn = e ? atoi(e) : 0; } a.force_near = fn; }
+    { static int ne = -1; if (ne < 0) { const char *e = getenv("GPUNB_B200_NEAR_EXACT"); ne = e ? atoi(e) : 0; } a.near_exact = L.near_exact >= 0 ? L.near_exact : ne; }
     a.stats = d.stats; a.wtime = d.wtime;
     a.h2 = ib.h2; a.dtr = ib.dtr; a.xi = ib.xi; a.vi = ib.vi;
     a.slot0 = j.slot0; a.nloc = j.nloc; a.n_itiles = p.n_itiles; a.S = p.S; a.n_items = p.n_items;
@@ -2160,11 +2234,12 @@ void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT])
     if (L.devinit && !L.devs.empty() && L.devs[0].stats) {
         Dev &d = L.devs[0];
         set_dev(d);
-        unsigned long long h[2];
-        CUDA_CHECK(cudaMemcpyAsync(h, d.stats, 16, cudaMemcpyDeviceToHost, d.st));
+        unsigned long long h[4];
+        CUDA_CHECK(cudaMemcpyAsync(h, d.stats, 32, cudaMemcpyDeviceToHost, d.st));
         CUDA_CHECK(cudaStreamSynchronize(d.st));
         L.ctr[GPUNB_B200_CTR_NEAR_TILES] = (double)h[0];
         L.ctr[GPUNB_B200_CTR_ALL_TILES] = (double)h[1];
+        L.ctr[GPUNB_B200_CTR_EXACT_QUADS] = (double)h[2];
     }
     for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) out[k] = L.ctr[k];
 }
@@ -2173,7 +2248,7 @@ void gpunb_b200_reset_counters(void)
     for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) L.ctr[k] = 0;
     if (L.devinit && !L.devs.empty() && L.devs[0].stats) {
         set_dev(L.devs[0]);
-        CUDA_CHECK(cudaMemsetAsync(L.devs[0].stats, 0, 16, L.devs[0].st));
+        CUDA_CHECK(cudaMemsetAsync(L.devs[0].stats, 0, 32, L.devs[0].st));
     }
 }
 
@@ -2314,6 +2389,8 @@ void gpunb_b200_state_update_(int *n, int idx[], double body[], double x0[][3], 
 }
 void gpunb_b200_predict_send_(int *nj, double *time) { lib_predict_send(*nj, *time); }
 void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3]) { lib_get_predicted(*n, idx, &x[0][0], &xdot[0][0]); }
+
+void gpunb_b200_set_near_exact(int on) { L.near_exact = on; }
 
 void gpunb_b200_set_tuning(int nslot, int nsub)
 {

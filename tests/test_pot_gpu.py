@@ -24,3 +24,23 @@ def test_gpupot_while_closed_and_matches_avx(b200, ref_avx):
     a = b200.gpupot(1, n, m, x)
     b = ref_avx.gpupot(1, n, m, x)
     assert np.max(np.abs(a - b) / b) < 2e-6
+
+
+def test_gpupot_close_pairs(b200, oracle):
+    """Hard binaries: pairs 1e-3 ... 1e-7 apart far from the origin, where a tile-local fp32 offset difference loses
+    the separation; their mutual term dominates phi_i.  (Found by the multi-GPU test: Plummer N=20011, seed 31 has a
+    pair that left 1.5e-6 before close tiles used two-float separations.)"""
+    n = 20011
+    m, x, v = S.plummer(n, 31, "kroupa")
+    ref = oracle.pot_f64(1, n, m, x)
+    pot = b200.gpupot(1, n, m, x)
+    assert np.max(np.abs(pot - ref) / ref) <= 1.0e-6
+    rng = np.random.default_rng(5)
+    for k, sep in enumerate((1e-3, 1e-4, 1e-5, 1e-6, 1e-7)):
+        i, j = 100 + 2 * k, 9000 + 2 * k
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        x[j] = x[i] + sep * d
+    x += np.array([3.0, -2.0, 1.0])                    # away from the origin: absolute fp32 resolution is ~2e-7
+    ref = oracle.pot_f64(1, n, m, x)
+    pot = b200.gpupot(1, n, m, x)
+    assert np.max(np.abs(pot - ref) / ref) <= 1.0e-6

@@ -279,3 +279,28 @@ def test_full_size_parity_1M(b200, oracle):
     finally:
         b200.set_tuning(3, 4)
         b200.close()
+
+
+def test_shifted_cluster_with_hard_binaries(b200, oracle):
+    """The cluster centre away from the origin (fp32 resolution of the coordinates ~2e-7) and pairs down to 1e-6 apart:
+    the neighbour predicate must still be the reference's bit for bit on the fp32-rounded positions, and the regular
+    force must hold 1e-6 (tile-local offsets + two-float separations)."""
+    n = 8192
+    m, x, v = S.plummer(n, 21, "kroupa")
+    rng = np.random.default_rng(9)
+    for k, sep in enumerate((1e-2, 1e-3, 1e-4, 1e-5, 1e-6)):
+        i, j = 10 + 3 * k, 4000 + 5 * k
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        x[j] = x[i] + sep * d
+        v[j] = v[i] + 0.3 * rng.normal(size=3)
+    x += np.array([3.0, -2.0, 1.0]); v += np.array([0.1, 0.2, -0.3])
+    for m_flag in (0, 1):
+        h2, dtr = S.radii(x - np.array([3.0, -2.0, 1.0]), m, S.rs0_for_nnb(n, 60.0), 0.125, m_flag)
+        b200.open(n + 10, 0)
+        b200.send(m, x, v)
+        try:
+            for isel in (slice(0, 1024), slice(3600, 4400)):
+                r = check_block(b200, oracle, m, x, v, h2, dtr, isel, 400, 350, m_flag)
+                print("shifted", m_flag, r)
+        finally:
+            b200.close()
