@@ -603,11 +603,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 // ~1e-7 of the smallest separation by sending tiles closer than half their own reach NEAR
                 const bool f = (d2 > rr * rr) && (d2 > 0.25f * sreach * sreach);
                 lane_far &= (f || iidx[k] < 0);
-                // per-PAIR version of the same two conditions, on the fp32 separation the FAR body computes: the
-                // predicate sees positions rounded to fp32 (|error| <= slack per particle), the separation itself
-                // carries ~2^-23 (|c| + h)
+                // per-PAIR version of the neighbour condition, on the two-float separation the first pass of a NEAR
+                // tile computes: the predicate sees positions rounded to fp32 (|error| <= slack per particle)
                 const float rc = rr + 4.f * (I[k].slack + 1.2e-7f * sreach);
-                cut2[k] = iidx[k] < 0 ? 0.f : fmaxf(rc * rc, 0.25f * sreach * sreach) * 1.00001f;
+                cut2[k] = iidx[k] < 0 ? 0.f : rc * rc * 1.00001f;
             }
         }
         const bool far = __all_sync(0xffffffffu, lane_far) && !a.force_near;
@@ -636,23 +635,32 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 }
             }
         } else {
-            // NEAR tile.  Most of its pairs are still far from every lane's neighbour sphere: per quad of j the packed
-            // body computes the separations and r2 first, and only if ANY lane has a pair below its cut (cut2: the
-            // per-pair form of the FAR conditions) the quad is redone by the exact scalar body -- reference predicate
-            // on the fp32-rounded positions, float-float separation, Newton-refined rsqrt.  At N=1M the 32 spheres of
-            // a warp cover ~1-2 % of the j of its NEAR tiles, so a NEAR tile costs little more than a FAR one.
+            // NEAR tile.  Most of its pairs are still outside every lane's neighbour sphere: per quad of j a packed
+            // first pass computes the separations -- from the TWO-FLOAT positions, (xh_j - xh_i) + (xl_j - xl_i), so
+            // that no pair of a close tile loses precision -- and r2, and only if ANY lane has a pair below its cut
+            // (cut2: the per-pair neighbour bound) the quad is redone by the exact scalar body: reference predicate on
+            // the fp32-rounded positions, Newton-refined rsqrt, list append.  Otherwise the packed far body finishes it.
             n_near++;
+            float2 nxh2[IT], nyh2[IT], nzh2[IT], nxl2[IT], nyl2[IT], nzl2[IT];
+#pragma unroll
+            for (int k = 0; k < IT; k++) {
+                nxh2[k] = dup2(I[k].nxh); nyh2[k] = dup2(I[k].nyh); nzh2[k] = dup2(I[k].nzh);
+                nxl2[k] = dup2(I[k].nxl); nyl2[k] = dup2(I[k].nyl); nzl2[k] = dup2(I[k].nzl);
+            }
 #pragma unroll 1
             for (int q = 0; q < TJ / 4; q++) {
-                const float4 DX = c[C_DX * 16 + q], DY = c[C_DY * 16 + q], DZ = c[C_DZ * 16 + q];
+                const float4 XH = c[C_XH * 16 + q], YH = c[C_YH * 16 + q], ZH = c[C_ZH * 16 + q];
+                const float4 XL = c[C_XL * 16 + q], YL = c[C_YL * 16 + q], ZL = c[C_ZL * 16 + q];
                 float2 dxa[IT], dya[IT], dza[IT], r2a[IT], dxb[IT], dyb[IT], dzb[IT], r2b[IT];
                 bool flag = a.near_exact != 0;
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
-                    dxa[k] = add2(make_float2(DX.x, DX.y), cx2[k]); dya[k] = add2(make_float2(DY.x, DY.y), cy2[k]);
-                    dza[k] = add2(make_float2(DZ.x, DZ.y), cz2[k]);
-                    dxb[k] = add2(make_float2(DX.z, DX.w), cx2[k]); dyb[k] = add2(make_float2(DY.z, DY.w), cy2[k]);
-                    dzb[k] = add2(make_float2(DZ.z, DZ.w), cz2[k]);
+                    dxa[k] = add2(add2(make_float2(XH.x, XH.y), nxh2[k]), add2(make_float2(XL.x, XL.y), nxl2[k]));
+                    dya[k] = add2(add2(make_float2(YH.x, YH.y), nyh2[k]), add2(make_float2(YL.x, YL.y), nyl2[k]));
+                    dza[k] = add2(add2(make_float2(ZH.x, ZH.y), nzh2[k]), add2(make_float2(ZL.x, ZL.y), nzl2[k]));
+                    dxb[k] = add2(add2(make_float2(XH.z, XH.w), nxh2[k]), add2(make_float2(XL.z, XL.w), nxl2[k]));
+                    dyb[k] = add2(add2(make_float2(YH.z, YH.w), nyh2[k]), add2(make_float2(YL.z, YL.w), nyl2[k]));
+                    dzb[k] = add2(add2(make_float2(ZH.z, ZH.w), nzh2[k]), add2(make_float2(ZL.z, ZL.w), nzl2[k]));
                     r2a[k] = fma2(dza[k], dza[k], fma2(dya[k], dya[k], mul2(dxa[k], dxa[k])));
                     r2b[k] = fma2(dzb[k], dzb[k], fma2(dyb[k], dyb[k], mul2(dxb[k], dxb[k])));
                     flag |= fminf(fminf(r2a[k].x, r2a[k].y), fminf(r2b[k].x, r2b[k].y)) < cut2[k];
@@ -670,8 +678,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                     continue;
                 }
                 n_exact++;
-                const float4 XH = c[C_XH * 16 + q], YH = c[C_YH * 16 + q], ZH = c[C_ZH * 16 + q];
-                const float4 XL = c[C_XL * 16 + q], YL = c[C_YL * 16 + q], ZL = c[C_ZL * 16 + q];
                 unsigned hit = 0;
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
