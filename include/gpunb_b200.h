@@ -89,7 +89,6 @@ enum {
     GPUNB_B200_CTR_SEND_MS,
     GPUNB_B200_CTR_SEND_STAGE_MS,
     GPUNB_B200_CTR_SEND_TILES_MS,
-    GPUNB_B200_CTR_EXACT_QUADS,     /* quads (4 j) of NEAR tiles redone by the exact scalar body (GPUNB_B200_STATS=1) */
     GPUNB_B200_CTR_COUNT
 };
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);
@@ -133,8 +132,8 @@ void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3
  * unchanged.  Environment: GPUNB_B200_NSLOT / GPUNB_B200_NSUB. */
 void  gpunb_b200_set_tuning(int nslot, int nsub);
 
-/* Tuning / A-B measurement: 1 = every quad of a NEAR tile through the exact scalar body (the kernel before the
- * two-pass NEAR tiles), 0 = two-pass, -1 = follow GPUNB_B200_NEAR_EXACT. */
+/* Tuning / A-B measurement: 1 = NEAR tiles through the scalar pair body, 0 = through the packed (f32x2) pair body
+ * (default; bit-for-bit the same results), -1 = follow the environment variable GPUNB_B200_NEAR_EXACT. */
 void  gpunb_b200_set_near_exact(int on);
 
 /* FP32 pipe microbenchmark: returns achieved scalar/packed FFMA TFLOP/s on device 0

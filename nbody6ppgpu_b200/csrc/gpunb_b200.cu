@@ -370,7 +370,7 @@ struct RegfArgs {
     int          *seg;       // [nloc][S][segcap]
     int           segcap;
     int           force_near;  // debugging/tuning: classify every tile as NEAR
-    int           near_exact;  // debugging/tuning: every quad of a NEAR tile through the exact scalar body
+    int           near_scalar; // tuning / A-B: NEAR tiles through the scalar body (the kernel before the packed NEAR body)
     unsigned long long *stats; // optional: [0] near tiles, [1] all tiles (per warp-tile visit), [2] exact quads of NEAR tiles
     unsigned long long *wtime; // optional: per work item start/end %globaltimer (tuning)
 };
@@ -476,6 +476,46 @@ __device__ __forceinline__ bool interact_near(const IState &I, Acc &A,
     return nb;
 }
 
+// The same body PACKED over two j (f32x2): every operation is the component-wise IEEE operation of the scalar body
+// above, in the same order, so predicate and sums are bit-for-bit those of interact_near on the pair's two chains --
+// at ~26 issue slots per pair instead of ~50.  Returns bit 0 / bit 1: neighbour hit of the .x / .y pair.
+template <bool MFLAG>
+__device__ __forceinline__ unsigned interact_near2(const IState &I, Acc2 &A, float2 VX, float2 VY, float2 VZ, float2 M,
+                                                   float2 XH, float2 YH, float2 ZH, float2 XL, float2 YL, float2 ZL)
+{
+    const float2 dxr = add2(XH, dup2(I.nxh)), dyr = add2(YH, dup2(I.nyh)), dzr = add2(ZH, dup2(I.nzh));
+    const float2 dx = add2(dxr, add2(XL, dup2(I.nxl))), dy = add2(dyr, add2(YL, dup2(I.nyl))),
+                 dz = add2(dzr, add2(ZL, dup2(I.nzl)));
+    const float2 dvx = add2(VX, dup2(I.nvx)), dvy = add2(VY, dup2(I.nvy)), dvz = add2(VZ, dup2(I.nvz));
+
+    const float2 r2r = fma2(dzr, dzr, fma2(dyr, dyr, mul2(dxr, dxr)));
+    const float2 dtr = dup2(I.dtr);
+    const float2 dxp = fma2(dtr, dvx, dxr), dyp = fma2(dtr, dvy, dyr), dzp = fma2(dtr, dvz, dzr);
+    const float2 r2p = fma2(dzp, dzp, fma2(dyp, dyp, mul2(dxp, dxp)));
+    const float2 r2  = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    const float2 rv  = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
+
+    const float2 lim = MFLAG ? mul2(M, dup2(I.h2)) : dup2(I.h2);
+    const bool nb0 = fminf(r2r.x, r2p.x) < lim.x, nb1 = fminf(r2r.y, r2p.y) < lim.y;
+    float2 rinv;
+    rinv.x = (nb0 || !(r2.x > 0.f)) ? 0.f : rsqrt_approx(r2.x);
+    rinv.y = (nb1 || !(r2.y > 0.f)) ? 0.f : rsqrt_approx(r2.y);
+    // one Newton step: y <- y - y/2 (r2 y^2 - 1)
+    const float2 e = fma2(mul2(r2, rinv), rinv, dup2(-1.f));
+    rinv = fma2(mul2(rinv, e), dup2(-0.5f), rinv);
+    // accumulate(): gpunb.velocity.cu:192-207
+    const float2 rinv2  = mul2(rinv, rinv);
+    const float2 mrinv  = mul2(M, rinv);
+    const float2 mrinv3 = mul2(mrinv, rinv2);
+    const float2 rv3    = mul2(rv, mul2(rinv2, dup2(-3.f)));
+    A.p = add2(A.p, mrinv);
+    A.ax = fma2(mrinv3, dx, A.ax);   A.ay = fma2(mrinv3, dy, A.ay);   A.az = fma2(mrinv3, dz, A.az);
+    A.jx = fma2(mrinv3, fma2(rv3, dx, dvx), A.jx);
+    A.jy = fma2(mrinv3, fma2(rv3, dy, dvy), A.jy);
+    A.jz = fma2(mrinv3, fma2(rv3, dz, dvz), A.jz);
+    return (nb0 ? 1u : 0u) | (nb1 ? 2u : 0u);
+}
+
 template <int IT, bool MFLAG, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a)
 {
@@ -554,7 +594,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         }
     };
 
-    unsigned n_near = 0, n_all = 0, n_exact = 0;
+    unsigned n_near = 0, n_all = 0;
     int n = 0;
     for (int t = s; t < a.ntiles; t += a.S, n++) {
         const int st = n % NSTAGE;
@@ -579,7 +619,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         // with margins that dominate every fp32 rounding (positions/velocities rounded to fp32 by the predicate,
         // this arithmetic itself, the approximate sqrt).
         bool lane_far = true;
-        float cut2[IT];        // NEAR tiles: pairs with r2 >= cut2 can neither be neighbours nor need float-float separations
         {
             const float jh[3] = {h1.z, h1.w, h2v.x};
             const float jvc[3] = {h2v.y, h2v.z, h2v.w};
@@ -603,10 +642,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 // ~1e-7 of the smallest separation by sending tiles closer than half their own reach NEAR
                 const bool f = (d2 > rr * rr) && (d2 > 0.25f * sreach * sreach);
                 lane_far &= (f || iidx[k] < 0);
-                // per-PAIR version of the neighbour condition, on the two-float separation the first pass of a NEAR
-                // tile computes: the predicate sees positions rounded to fp32 (|error| <= slack per particle)
-                const float rc = rr + 4.f * (I[k].slack + 1.2e-7f * sreach);
-                cut2[k] = iidx[k] < 0 ? 0.f : rc * rc * 1.00001f;
             }
         }
         const bool far = __all_sync(0xffffffffu, lane_far) && !a.force_near;
@@ -635,63 +670,44 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 }
             }
         } else {
-            // NEAR tile.  Most of its pairs are still outside every lane's neighbour sphere: per quad of j a packed
-            // first pass computes the separations -- from the TWO-FLOAT positions, (xh_j - xh_i) + (xl_j - xl_i), so
-            // that no pair of a close tile loses precision -- and r2, and only if ANY lane has a pair below its cut
-            // (cut2: the per-pair neighbour bound) the quad is redone by the exact scalar body: reference predicate on
-            // the fp32-rounded positions, Newton-refined rsqrt, list append.  Otherwise the packed far body finishes it.
+            // NEAR tile: the full body (reference predicate on the fp32-rounded positions, two-float separation,
+            // Newton-refined rsqrt), packed over j like the FAR body.  A two-pass variant (packed far body first, exact
+            // fix-up of the quads in which any lane has a pair inside its neighbour bound) was measured and dropped:
+            // 45 % of the quads of NEAR tiles need the fix-up, because a tile is smaller than a neighbour sphere
+            // (profiles/r01t_pipeline_probe_1gpu.txt).
             n_near++;
-            float2 nxh2[IT], nyh2[IT], nzh2[IT], nxl2[IT], nyl2[IT], nzl2[IT];
-#pragma unroll
-            for (int k = 0; k < IT; k++) {
-                nxh2[k] = dup2(I[k].nxh); nyh2[k] = dup2(I[k].nyh); nzh2[k] = dup2(I[k].nzh);
-                nxl2[k] = dup2(I[k].nxl); nyl2[k] = dup2(I[k].nyl); nzl2[k] = dup2(I[k].nzl);
-            }
 #pragma unroll 1
             for (int q = 0; q < TJ / 4; q++) {
-                const float4 XH = c[C_XH * 16 + q], YH = c[C_YH * 16 + q], ZH = c[C_ZH * 16 + q];
-                const float4 XL = c[C_XL * 16 + q], YL = c[C_YL * 16 + q], ZL = c[C_ZL * 16 + q];
-                float2 dxa[IT], dya[IT], dza[IT], r2a[IT], dxb[IT], dyb[IT], dzb[IT], r2b[IT];
-                bool flag = a.near_exact != 0;
-#pragma unroll
-                for (int k = 0; k < IT; k++) {
-                    dxa[k] = add2(add2(make_float2(XH.x, XH.y), nxh2[k]), add2(make_float2(XL.x, XL.y), nxl2[k]));
-                    dya[k] = add2(add2(make_float2(YH.x, YH.y), nyh2[k]), add2(make_float2(YL.x, YL.y), nyl2[k]));
-                    dza[k] = add2(add2(make_float2(ZH.x, ZH.y), nzh2[k]), add2(make_float2(ZL.x, ZL.y), nzl2[k]));
-                    dxb[k] = add2(add2(make_float2(XH.z, XH.w), nxh2[k]), add2(make_float2(XL.z, XL.w), nxl2[k]));
-                    dyb[k] = add2(add2(make_float2(YH.z, YH.w), nyh2[k]), add2(make_float2(YL.z, YL.w), nyl2[k]));
-                    dzb[k] = add2(add2(make_float2(ZH.z, ZH.w), nzh2[k]), add2(make_float2(ZL.z, ZL.w), nzl2[k]));
-                    r2a[k] = fma2(dza[k], dza[k], fma2(dya[k], dya[k], mul2(dxa[k], dxa[k])));
-                    r2b[k] = fma2(dzb[k], dzb[k], fma2(dyb[k], dyb[k], mul2(dxb[k], dxb[k])));
-                    flag |= fminf(fminf(r2a[k].x, r2a[k].y), fminf(r2b[k].x, r2b[k].y)) < cut2[k];
-                }
                 const float4 VX = c[C_VX * 16 + q], VY = c[C_VY * 16 + q], VZ = c[C_VZ * 16 + q];
                 const float4 M  = c[C_M * 16 + q];
-                if (!__any_sync(0xffffffffu, flag)) {
+                const float4 XH = c[C_XH * 16 + q], YH = c[C_YH * 16 + q], ZH = c[C_ZH * 16 + q];
+                const float4 XL = c[C_XL * 16 + q], YL = c[C_YL * 16 + q], ZL = c[C_ZL * 16 + q];
+                unsigned hit = 0;
+                if (a.near_scalar) {                   // A/B: the scalar body, bit-for-bit the same results
 #pragma unroll
                     for (int k = 0; k < IT; k++) {
-                        far_force2(dxa[k], dya[k], dza[k], r2a[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(VX.x, VX.y),
-                                   make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), make_float2(M.x, M.y));
-                        far_force2(dxb[k], dyb[k], dzb[k], r2b[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(VX.z, VX.w),
-                                   make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), make_float2(M.z, M.w));
+                        Acc A0 = Acc{P[k].ax.x, P[k].ay.x, P[k].az.x, P[k].p.x, P[k].jx.x, P[k].jy.x, P[k].jz.x};
+                        Acc A1 = Acc{P[k].ax.y, P[k].ay.y, P[k].az.y, P[k].p.y, P[k].jx.y, P[k].jy.y, P[k].jz.y};
+                        const bool h0 = interact_near<MFLAG>(I[k], A0, VX.x, VY.x, VZ.x, M.x, XH.x, YH.x, ZH.x, XL.x, YL.x, ZL.x);
+                        const bool h1b = interact_near<MFLAG>(I[k], A1, VX.y, VY.y, VZ.y, M.y, XH.y, YH.y, ZH.y, XL.y, YL.y, ZL.y);
+                        const bool h2b = interact_near<MFLAG>(I[k], A0, VX.z, VY.z, VZ.z, M.z, XH.z, YH.z, ZH.z, XL.z, YL.z, ZL.z);
+                        const bool h3b = interact_near<MFLAG>(I[k], A1, VX.w, VY.w, VZ.w, M.w, XH.w, YH.w, ZH.w, XL.w, YL.w, ZL.w);
+                        hit |= ((h0 ? 1u : 0u) | (h1b ? 2u : 0u) | (h2b ? 4u : 0u) | (h3b ? 8u : 0u)) << (4 * k);
+                        P[k].ax = make_float2(A0.ax, A1.ax); P[k].ay = make_float2(A0.ay, A1.ay);
+                        P[k].az = make_float2(A0.az, A1.az); P[k].p  = make_float2(A0.p,  A1.p);
+                        P[k].jx = make_float2(A0.jx, A1.jx); P[k].jy = make_float2(A0.jy, A1.jy);
+                        P[k].jz = make_float2(A0.jz, A1.jz);
                     }
-                    continue;
-                }
-                n_exact++;
-                unsigned hit = 0;
+                } else
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
-                    Acc A0 = Acc{P[k].ax.x, P[k].ay.x, P[k].az.x, P[k].p.x, P[k].jx.x, P[k].jy.x, P[k].jz.x};
-                    Acc A1 = Acc{P[k].ax.y, P[k].ay.y, P[k].az.y, P[k].p.y, P[k].jx.y, P[k].jy.y, P[k].jz.y};
-                    const bool h0 = interact_near<MFLAG>(I[k], A0, VX.x, VY.x, VZ.x, M.x, XH.x, YH.x, ZH.x, XL.x, YL.x, ZL.x);
-                    const bool h1b = interact_near<MFLAG>(I[k], A1, VX.y, VY.y, VZ.y, M.y, XH.y, YH.y, ZH.y, XL.y, YL.y, ZL.y);
-                    const bool h2b = interact_near<MFLAG>(I[k], A0, VX.z, VY.z, VZ.z, M.z, XH.z, YH.z, ZH.z, XL.z, YL.z, ZL.z);
-                    const bool h3b = interact_near<MFLAG>(I[k], A1, VX.w, VY.w, VZ.w, M.w, XH.w, YH.w, ZH.w, XL.w, YL.w, ZL.w);
-                    hit |= ((h0 ? 1u : 0u) | (h1b ? 2u : 0u) | (h2b ? 4u : 0u) | (h3b ? 8u : 0u)) << (4 * k);
-                    P[k].ax = make_float2(A0.ax, A1.ax); P[k].ay = make_float2(A0.ay, A1.ay);
-                    P[k].az = make_float2(A0.az, A1.az); P[k].p  = make_float2(A0.p,  A1.p);
-                    P[k].jx = make_float2(A0.jx, A1.jx); P[k].jy = make_float2(A0.jy, A1.jy);
-                    P[k].jz = make_float2(A0.jz, A1.jz);
+                    const unsigned ha = interact_near2<MFLAG>(I[k], P[k], make_float2(VX.x, VX.y), make_float2(VY.x, VY.y),
+                        make_float2(VZ.x, VZ.y), make_float2(M.x, M.y), make_float2(XH.x, XH.y), make_float2(YH.x, YH.y),
+                        make_float2(ZH.x, ZH.y), make_float2(XL.x, XL.y), make_float2(YL.x, YL.y), make_float2(ZL.x, ZL.y));
+                    const unsigned hb = interact_near2<MFLAG>(I[k], P[k], make_float2(VX.z, VX.w), make_float2(VY.z, VY.w),
+                        make_float2(VZ.z, VZ.w), make_float2(M.z, M.w), make_float2(XH.z, XH.w), make_float2(YH.z, YH.w),
+                        make_float2(ZH.z, ZH.w), make_float2(XL.z, XL.w), make_float2(YL.z, YL.w), make_float2(ZL.z, ZL.w));
+                    hit |= (ha | (hb << 2)) << (4 * k);
                 }
                 if (hit) {                             // rare: ~2e-4 of pairs are neighbours
                     const int pb = t * TJ + q * 4;
@@ -729,10 +745,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             a.cnt[(size_t)s * a.nloc + kl] = cnt[k];
         }
     }
-    if (a.stats && lane == 0) {
-        atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all);
-        atomicAdd(&a.stats[2], (unsigned long long)n_exact);
-    }
+    if (a.stats && lane == 0) { atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all); }
     if (a.wtime && lane == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); a.wtime[3 * w + 1] = t1; a.wtime[3 * w + 2] = n_near; }
 }
 
@@ -1863,7 +1876,7 @@ void launch_regf(Dev &d, Slot &sl, cudaStream_t lo, cudaStream_t hi, const Job &
     RegfArgs a;
     a.tiles = d.jtile; a.jidx = d.jidx; a.ntiles = d.ntiles; a.iperm = iperm;
     { static int fn = -1; if (fn < 0) { const char *e = getenv("GPUNB_B200_FORCE_NEAR"); fn = e ? atoi(e) : 0; } a.force_near = fn; }
-    { static int ne = -1; if (ne < 0) { const char *e = getenv("GPUNB_B200_NEAR_EXACT"); ne = e ? atoi(e) : 0; } a.near_exact = L.near_exact >= 0 ? L.near_exact : ne; }
+    { static int ne = -1; if (ne < 0) { const char *e = getenv("GPUNB_B200_NEAR_EXACT"); ne = e ? atoi(e) : 0; } a.near_scalar = L.near_exact >= 0 ? L.near_exact : ne; }
     a.stats = d.stats; a.wtime = d.wtime;
     a.h2 = ib.h2; a.dtr = ib.dtr; a.xi = ib.xi; a.vi = ib.vi;
     a.slot0 = j.slot0; a.nloc = j.nloc; a.n_itiles = p.n_itiles; a.S = p.S; a.n_items = p.n_items;
@@ -2245,7 +2258,7 @@ void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT])
         CUDA_CHECK(cudaStreamSynchronize(d.st));
         L.ctr[GPUNB_B200_CTR_NEAR_TILES] = (double)h[0];
         L.ctr[GPUNB_B200_CTR_ALL_TILES] = (double)h[1];
-        L.ctr[GPUNB_B200_CTR_EXACT_QUADS] = (double)h[2];
+
     }
     for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) out[k] = L.ctr[k];
 }

@@ -55,13 +55,13 @@ for ne in (1, 0):
     lib.set_near_exact(ne)
     lib.sweep_resident(0, 1024 * 16, 1024, 600, 550, 0)
     ms = min(lib.sweep_resident(0, 1024 * nblk, 1024, 600, 550, 0) for _ in range(2))
-    print(f"rank {rank}/{world} NEAR tiles {'exact scalar body only' if ne else 'two-pass (packed + exact fix-up)'}: {ms / nblk * 1e3:7.1f} us per block  {1024.0 * nblk * n / ms * 1e-6:8.1f} Gint/s", flush=True)
+    print(f"rank {rank}/{world} NEAR tiles {'scalar pair body' if ne else 'packed f32x2 pair body'}: {ms / nblk * 1e3:7.1f} us per block  {1024.0 * nblk * n / ms * 1e-6:8.1f} Gint/s", flush=True)
 lib.set_near_exact(-1)
 if os.environ.get("GPUNB_B200_STATS"):
     lib.reset_counters()
     lib.sweep_resident(0, 1024 * 64, 1024, 600, 550, 0)
     c = lib.counters()
-    print(f"rank {rank}/{world} tile visits: NEAR {c['near_tiles'] / c['all_tiles'] * 100:5.2f} %, exact quads {c['exact_quads'] / (16 * max(c['near_tiles'], 1)) * 100:5.2f} % of the quads of NEAR tiles", flush=True)
+    print(f"rank {rank}/{world} tile visits: NEAR {c['near_tiles'] / c['all_tiles'] * 100:5.2f} %", flush=True)
 call = lib.block_caller(h2, dtr, x, v, 1024, 600, 550, 0)
 for nsub in (1, 2, 3, 4, 2):
     lib.set_tuning(0, nsub)

@@ -304,3 +304,24 @@ def test_shifted_cluster_with_hard_binaries(b200, oracle):
                 print("shifted", m_flag, r)
         finally:
             b200.close()
+
+
+def test_packed_near_body_is_bitwise_the_scalar_body(b200):
+    """NEAR tiles run the full pair body packed over two j (f32x2): every operation is the component-wise IEEE
+    operation of the scalar body in the same order, so lists AND sums are bit-for-bit identical."""
+    n = 16384
+    m, x, v = S.plummer(n, 13, "kroupa")
+    b200.open(n + 10, 0)
+    b200.send(m, x, v)
+    try:
+        for m_flag in (0, 1):
+            h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 120.0), 0.125, m_flag)
+            out = {}
+            for scalar in (1, 0):
+                b200.set_near_exact(scalar)
+                out[scalar] = [a.copy() for a in b200.regf(h2[:2048], dtr[:2048], x[:2048], v[:2048], 400, 350, m_flag)]
+            for q in range(4):
+                assert np.array_equal(out[0][q], out[1][q])
+    finally:
+        b200.set_near_exact(-1)
+        b200.close()
