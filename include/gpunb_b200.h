@@ -132,9 +132,11 @@ void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3
  * unchanged.  Environment: GPUNB_B200_NSLOT / GPUNB_B200_NSUB. */
 void  gpunb_b200_set_tuning(int nslot, int nsub);
 
-/* Tuning / A-B measurement: 1 = NEAR tiles through the scalar pair body, 0 = through the packed (f32x2) pair body
- * (default; bit-for-bit the same results), -1 = follow the environment variable GPUNB_B200_NEAR_EXACT. */
+/* A-B builds only (make EXTRA=-DNEAR_SCALAR_AB; gpunb_b200_has_near_scalar_ab() == 1): 1 = NEAR tiles through the
+ * scalar pair body, 0 = through the packed (f32x2) pair body (bit-for-bit the same results), -1 = follow the
+ * environment variable GPUNB_B200_NEAR_EXACT.  No effect in the default build (packed body only). */
 void  gpunb_b200_set_near_exact(int on);
+int   gpunb_b200_has_near_scalar_ab(void);
 
 /* FP32 pipe microbenchmark: returns achieved scalar/packed FFMA TFLOP/s on device 0
  * (mode 0: FFMA, 1: FFMA2 (f32x2), 2: FADD2, 3: FMUL2, 4: MUFU.RSQ Gop/s, 5: FFMA2+ALU mix). */

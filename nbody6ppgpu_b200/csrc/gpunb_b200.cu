@@ -683,7 +683,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 const float4 XH = c[C_XH * 16 + q], YH = c[C_YH * 16 + q], ZH = c[C_ZH * 16 + q];
                 const float4 XL = c[C_XL * 16 + q], YL = c[C_YL * 16 + q], ZL = c[C_ZL * 16 + q];
                 unsigned hit = 0;
-                if (a.near_scalar) {                   // A/B: the scalar body, bit-for-bit the same results
+#ifdef NEAR_SCALAR_AB
+                if (a.near_scalar) {                   // A/B build: the scalar body, bit-for-bit the same results
 #pragma unroll
                     for (int k = 0; k < IT; k++) {
                         Acc A0 = Acc{P[k].ax.x, P[k].ay.x, P[k].az.x, P[k].p.x, P[k].jx.x, P[k].jy.x, P[k].jz.x};
@@ -699,6 +700,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                         P[k].jz = make_float2(A0.jz, A1.jz);
                     }
                 } else
+#endif
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
                     const unsigned ha = interact_near2<MFLAG>(I[k], P[k], make_float2(VX.x, VX.y), make_float2(VY.x, VY.y),
@@ -2242,7 +2244,15 @@ void gpupot_(int *irank, int *istart, int *ni, int *n, double m[], double x[][3]
     lib_pot(*irank, *istart, *ni, *n, m, &x[0][0], pot);
 }
 
-int gpunb_b200_version(void) { return 102; }
+int gpunb_b200_version(void) { return 103; }
+int gpunb_b200_has_near_scalar_ab(void)
+{
+#ifdef NEAR_SCALAR_AB
+    return 1;
+#else
+    return 0;
+#endif
+}
 const char *gpunb_b200_build_info(void)
 {
     return "gpunb_b200 sm_100a: regf_kernel<TMA bulk Hilbert tiles TJ=64, packed f32x2 FAR body, scalar float-float NEAR body>, isort, merge (register bitonic), combine (NVLink peer pulls + flags), pot, tilepack";

@@ -90,6 +90,7 @@ class ForceLib:
             L.gpunb_b200_nccl_init.restype = C.c_int
             L.gpunb_b200_nccl_finalize.argtypes = []
             L.gpunb_b200_nccl_finalize.restype = None
+            L.gpunb_b200_has_near_scalar_ab.restype = C.c_int
             L.gpunb_b200_set_near_exact.argtypes = [C.c_int]
             L.gpunb_b200_set_near_exact.restype = None
             L.gpunb_b200_set_tuning.argtypes = [C.c_int, C.c_int]

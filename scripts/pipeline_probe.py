@@ -51,7 +51,7 @@ for nslot in (1, 2, 3, 4, 3):
     if dist: dist.barrier()
     ms = min(lib.sweep_resident(0, 1024 * nblk, 1024, 600, 550, 0) for _ in range(2))
     print(f"rank {rank}/{world} nslot {nslot}: {ms / nblk * 1e3:7.1f} us per block  {1024.0 * nblk * n / ms * 1e-6:8.1f} Gint/s", flush=True)
-for ne in (1, 0):
+for ne in ((1, 0) if lib.lib.gpunb_b200_has_near_scalar_ab() else (0,)):
     lib.set_near_exact(ne)
     lib.sweep_resident(0, 1024 * 16, 1024, 600, 550, 0)
     ms = min(lib.sweep_resident(0, 1024 * nblk, 1024, 600, 550, 0) for _ in range(2))
