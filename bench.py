@@ -8,8 +8,9 @@ j-particles, then gpunb_regf over i-blocks of 1024 until `--ni-total` i-particle
 all N -> 977 calls, 1e12 interactions).  interactions = sum ni*nj exactly as the reference counts
 (gpunb.velocity.cu:747), self and neighbour pairs included.
 
-  value   device-resident leg: the j snapshot, radii and i-blocks already in HBM, kernels launched back to
-          back on the library's stream, timed with CUDA events on that stream (gpunb_b200_sweep_resident).
+  value   device-resident leg: the j snapshot, radii and i-blocks already in HBM; the blocks cycle through the
+          library's pipeline slots (pair kernel of block b+1 beside merge/exchange of block b), timed with CUDA
+          events on the library's main stream around the whole sweep (gpunb_b200_sweep_resident).
   e2e     the same sweep through the reference-facing C-ABI (gpunb_send_ + gpunb_regf_) with HOST
           (pageable numpy) buffers: H2D of the snapshot and of every i-block, D2H of forces and
           neighbour lists inside the timed region.
@@ -22,7 +23,9 @@ all N -> 977 calls, 1e12 interactions).  interactions = sum ni*nj exactly as the
           bounded sample of the same workload.
 
 `--impl reference` times that AVX library alone (same metric/config), each step a bounded sample.
-Under torchrun (N>1) the j-set is sharded over ranks and partial results are combined with NCCL.
+Under torchrun (N>1) the j-set is sharded over ranks (every R-th Hilbert tile); partial sums and neighbour rows are
+exchanged by the library's own kernels over NVLink peer memory (flags + peer pulls); NCCL only
+bootstraps the cudaIpc handles.
 """
 from __future__ import annotations
 
@@ -371,6 +374,9 @@ def main():
         "gint_per_s_kernel": int_per_launch / (kern_ms * 1e-3) * 1e-9,
         "roofline_gint_per_s": fp32_nominal * 1e12 / FLOP_PER_INT * 1e-9,
         "traffic": traffic,
+        # the same 60 flop/interaction over the WHOLE pipelined sweep (`value`), where the tail of every launch is
+        # filled by the next block's CTAs -- per GPU
+        "frac_of_sweep": value / world / (fp32_nominal * 1e12 / FLOP_PER_INT * 1e-9),
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms * 1e-3) * 1e-9,
                 "peak_gbs": hbm_peak, "peak_source": peak_src, "frac": alg_bytes / (kern_ms * 1e-3) * 1e-9 / hbm_peak},
         "merge_kernel_ms": merge_ms,
