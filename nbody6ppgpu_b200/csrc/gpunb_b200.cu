@@ -1114,21 +1114,27 @@ __global__ void __launch_bounds__(128) pot_kernel(const float *__restrict__ tile
             phi += (double)acc;
             continue;
         }
+        // packed f32x2 over j: 11 packed FP32 ops + 2 MUFU.RSQ per two pairs, two chains of 32 terms
+        const float2 cx2 = dup2(cx), cy2 = dup2(cy), cz2 = dup2(cz);
+        float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll 4
         for (int q = 0; q < TJ / 4; q++) {
             const float4 DX = c[q], DY = c[16 + q], DZ = c[32 + q], M = c[48 + q];
-            const float dxs[4] = {DX.x, DX.y, DX.z, DX.w}, dys[4] = {DY.x, DY.y, DY.z, DY.w};
-            const float dzs[4] = {DZ.x, DZ.y, DZ.z, DZ.w}, ms[4] = {M.x, M.y, M.z, M.w};
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const float dx = dxs[e] + cx, dy = dys[e] + cy, dz = dzs[e] + cz;
-                const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                float y = rsqrt_approx(r2);
-                y = y * fmaf(-0.5f * r2 * y, y, 1.5f);      // one Newton step
-                acc += (r2 > 0.f) ? ms[e] * y : 0.f;
+            for (int h = 0; h < 2; h++) {
+                const float2 dx = add2(h ? make_float2(DX.z, DX.w) : make_float2(DX.x, DX.y), cx2);
+                const float2 dy = add2(h ? make_float2(DY.z, DY.w) : make_float2(DY.x, DY.y), cy2);
+                const float2 dz = add2(h ? make_float2(DZ.z, DZ.w) : make_float2(DZ.x, DZ.y), cz2);
+                const float2 m2 = h ? make_float2(M.z, M.w) : make_float2(M.x, M.y);
+                const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                float2 y;                                  // a self pair (r2 == 0) contributes nothing (:52)
+                y.x = (r2.x > 0.f) ? rsqrt_approx(r2.x) : 0.f;
+                y.y = (r2.y > 0.f) ? rsqrt_approx(r2.y) : 0.f;
+                y = mul2(y, fma2(mul2(mul2(r2, dup2(-0.5f)), y), y, dup2(1.5f)));      // one Newton step
+                acc2 = fma2(m2, y, acc2);
             }
         }
-        phi += (double)acc;
+        phi += (double)(acc2.x + acc2.y);
     }
     if (ii < ni) part[(size_t)s * ni + ii] = phi;
 }
