@@ -46,7 +46,7 @@ UNIT = "Gint/s"
 LMAX, NNBMAX, BLOCK = 600, 550, 1024          # --with-par=1m: LMAX=600 (configure.ac:390-394); NNBMAX=min(N/2,LMAX-50)
 NNB_TARGET = 200.0
 FLOP_PER_INT = 60.0                           # reference convention, gpunb.velocity.cu:894
-NSLOT = int(os.environ.get("GPUNB_B200_NSLOT", "3"))     # pipeline slots of the resident sweep
+NSLOT = int(os.environ.get("GPUNB_B200_NSLOT", "0"))     # pipeline slots of the resident sweep (0: library default, 2 on one GPU / 3 sharded)
 NSUB = int(os.environ.get("GPUNB_B200_NSUB", "4"))       # sub-blocks of one gpunb_regf_ call
 
 
@@ -390,7 +390,7 @@ def main():
                    "block": BLOCK, "lmax": LMAX, "nnbmax": NNBMAX, "m_flag": args.m_flag, "rs_min": rs0, "mean_nnb": mean_nnb,
                    "interactions_per_step": inter_step, "l2": "flushed between timed steps (256 MB fill)",
                    "parallelism": f"j-shard x{world}",
-                   "pipeline": {"sweep_slots": NSLOT, "regf_subblocks": NSUB}},
+                   "pipeline": {"sweep_slots": NSLOT if NSLOT else (2 if world == 1 else 3), "regf_subblocks": NSUB}},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": c_e2e["h2d_bytes"] / e2e_steps,
                 "d2h_bytes_per_step": c_e2e["d2h_bytes"] / e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,

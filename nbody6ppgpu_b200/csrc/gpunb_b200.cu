@@ -1233,7 +1233,7 @@ constexpr int ROWS_LMAX_CAP = 1024;    // row stride capacity of the IPC-exporte
 // priority stream `lo`) fills the SMs as the CTAs of block b retire, while merge / exchange of block b (high
 // priority stream `hi`, latency-bound kernels) run beside it.
 constexpr int MAX_SLOTS = 4;
-constexpr int DEFAULT_NSLOT = 3;       // slots a resident sweep cycles through (GPUNB_B200_NSLOT)
+constexpr int DEFAULT_NSLOT = 3;       // slots a sharded resident sweep cycles through (GPUNB_B200_NSLOT); one GPU: 2
 constexpr int DEFAULT_NSUB  = 4;       // sub-blocks of one gpunb_regf_ call (GPUNB_B200_NSUB)
 struct Slot {
     cudaStream_t lo = nullptr, hi = nullptr;
@@ -1323,6 +1323,7 @@ struct Lib {
     int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
+    bool nslot_auto = true;        // nslot not chosen by the caller (environment / gpunb_b200_set_tuning)
     int near_exact = -1;           // >= 0: overrides GPUNB_B200_NEAR_EXACT (gpunb_b200_set_near_exact)
     bool nsub_forced = false;      // tests: split even when the pair kernels would be too short to be worth it
     int last_slot = 0; bool last_on_host = false;
@@ -1424,7 +1425,7 @@ void lib_devinit(int irank)
     CUDA_CHECK(cudaSetDevice(L.devs[0].id));
     host_alloc(L.h_flag, 16);
     memset(L.h_flag, 0, 16 * sizeof(int));
-    { const char *e = getenv("GPUNB_B200_NSLOT"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nslot = atoi(e); }
+    { const char *e = getenv("GPUNB_B200_NSLOT"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) { L.nslot = atoi(e); L.nslot_auto = false; } }
     { const char *e = getenv("GPUNB_B200_NSUB");  if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nsub = atoi(e); }
     { const char *e = getenv("GPUNB_B200_HOST_THREADS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) L.host_threads = atoi(e); }
     L.devinit = true;
@@ -2312,7 +2313,8 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
     // Pipelined (default, one GPU per process): every block's Morton order comes from ONE batched isort launch, then
     // the blocks cycle through nslot pipeline slots (see Slot).  Sequential (GPUNB_B200_NSLOT=1, the per-kernel
     // timeline, or one process driving several GPUs): one block after the other on the main stream.
-    const int nslot = (G == 1 && !timeline) ? L.nslot : 1;
+    // measured: 2 slots are best on one GPU (1024.6 vs 1019.7 Gint/s with 3), 3-4 once an exchange step has to be hidden
+    const int nslot = (G == 1 && !timeline) ? ((L.nslot_auto && !L.sh.on) ? 2 : L.nslot) : 1;
     const bool pipelined = nslot > 1;
     for (int g = 0; g < G; g++) ensure_work_buffers(L.devs[g], *lmaxp, *nnbmaxp, g == 0, nslot, true);
     set_dev(root);
@@ -2429,7 +2431,7 @@ void gpunb_b200_set_near_exact(int on) { L.near_exact = on; }
 
 void gpunb_b200_set_tuning(int nslot, int nsub)
 {
-    if (nslot >= 1 && nslot <= MAX_SLOTS) L.nslot = nslot;
+    if (nslot >= 1 && nslot <= MAX_SLOTS) { L.nslot = nslot; L.nslot_auto = false; }
     if (nsub >= 1 && nsub <= MAX_SLOTS) { L.nsub = nsub; L.nsub_forced = false; }
     if (nsub <= -1 && nsub >= -MAX_SLOTS) { L.nsub = -nsub; L.nsub_forced = true; }
 }
