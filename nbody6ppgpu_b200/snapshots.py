@@ -111,8 +111,14 @@ def radii_nnb(x: np.ndarray, m: np.ndarray, nnb: float, smax: float = 0.125, m_f
     a = 3.0 * np.pi / 16.0
     ri2 = (x * x).sum(1)
     rs = a * (nnb / n) ** (1.0 / 3.0) * (1.0 + ri2 / (a * a)) ** (5.0 / 6.0)
+    # the integrator never lets a halo sphere reach back into the core (RS limits in regcor_gpu.F); without a bound the
+    # r^(5/3) growth does exactly that at small N.  Not binding for r <= 10 at N = 10^6.
+    rs = np.minimum(rs, 0.4 * np.sqrt(ri2 + a * a))
     dtr = np.minimum(smax / 8.0 * np.sqrt(1.0 + ri2), smax)
     h2 = rs * rs
     if m_flag:
-        h2 = h2 / m.mean()
+        # criterion r^2 < h2 * m_j: a sphere of radius rs sqrt(m_j / <m>) per j, so the count scales with
+        # <(m/<m>)^1.5>; RS is taken smaller by that factor^(1/3) to keep ~nnb members with an IMF
+        w = float(((m / m.mean()) ** 1.5).mean())
+        h2 = h2 / w ** (2.0 / 3.0) / m.mean()
     return h2, dtr

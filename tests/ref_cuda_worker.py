@@ -47,7 +47,9 @@ def main():
     calls = 24
     m, x, v = S.plummer(n, 1, "kroupa")
     h2, dtr = S.radii_nnb(x, m, 200.0)
+    lists = {}
     for name, lib in (("ref", ref), ("b200", b200)):
+        lists[name] = []
         lib.open(n + 10, 0)
         lib.send(m, x, v)
         call = lib.block_caller(h2, dtr, x, v, 1024, 600, 550, 0)
@@ -58,6 +60,7 @@ def main():
         for b in range(calls):
             lst = call((4 + b) * 1024, 1024)[3]
             nnb += int(lst[:, 0].sum())
+            lists[name].append(lst.copy())
         t = time.perf_counter() - t0
         t0 = time.perf_counter()
         lib.send(m, x, v)
@@ -65,6 +68,22 @@ def main():
         lib.close()
         out[f"rate_{name}"] = {"gint_per_s": 1024.0 * calls * n / t * 1e-9, "us_per_call": t / calls * 1e6,
                                "send_ms": ts * 1e3, "mean_nnb": nnb / (1024.0 * calls), "n": n}
+    # list parity at N = 1M over the timed calls; every differing pair is reported with its distance from the boundary
+    diffs = []
+    for b in range(calls):
+        for r in oracle_lib.list_rows_equal(lists["b200"][b], lists["ref"][b]):
+            i = (4 + b) * 1024 + r
+            la, lb = lists["b200"][b][r], lists["ref"][b][r]
+            sa, sb = set(la[1:1 + la[0]].tolist()), set(lb[1:1 + lb[0]].tolist())
+            for j in sorted(sa ^ sb):
+                xi32, xj32 = x[i].astype(np.float32).astype(np.float64), x[j].astype(np.float32).astype(np.float64)
+                dv = v[j].astype(np.float32).astype(np.float64) - v[i].astype(np.float32).astype(np.float64)
+                d = xj32 - xi32
+                dp = d + float(np.float32(dtr[i])) * dv
+                lim = float(np.float32(h2[i]))
+                diffs.append({"i": int(i), "j": int(j), "in": "b200" if j in sa else "ref",
+                              "min_r2_over_h2_minus_1": float(min((d * d).sum(), (dp * dp).sum()) / lim - 1.0)})
+    out["lists_1M"] = {"rows_compared": 1024 * calls, "pairs_differing": len(diffs), "detail": diffs[:8]}
     print("REFCUDA " + json.dumps(out), flush=True)
 
 
