@@ -68,6 +68,31 @@ def main():
         lib.close()
         out[f"rate_{name}"] = {"gint_per_s": 1024.0 * calls * n / t * 1e-9, "us_per_call": t / calls * 1e6,
                                "send_ms": ts * 1e3, "mean_nnb": nnb / (1024.0 * calls), "n": n}
+    # ---- small active blocks (config samples/N10k_B1k.input: N = 10k, KS-heavy, <Ni> small): microseconds per
+    # gpunb_regf_ call against a fixed j-set, same caller for both libraries
+    n = 10000
+    m2, x2, v2 = S.plummer(n, 4, "kroupa")
+    h22, dtr2 = S.radii_nnb(x2, m2, 100.0)
+    small = {}
+    for name, lib in (("ref", ref), ("b200", b200)):
+        lib.open(n + 10, 0)
+        lib.send(m2, x2, v2)
+        call = lib.block_caller(h22, dtr2, x2, v2, 1024, 400, 350, 0)
+        small[name] = {}
+        for ni in (1, 8, 32, 64, 256, 1024):
+            for b in range(10):
+                call((37 * b) % (n - ni), ni)
+            reps = 200
+            t0 = time.perf_counter()
+            for b in range(reps):
+                call((97 * b) % (n - ni), ni)
+            small[name][str(ni)] = (time.perf_counter() - t0) / reps * 1e6
+        t0 = time.perf_counter()
+        for b in range(20):
+            lib.send(m2, x2, v2)
+        small[name]["send"] = (time.perf_counter() - t0) / 20 * 1e6
+        lib.close()
+    out["small_blocks_N10k_us_per_call"] = small
     # list parity at N = 1M over the timed calls; every differing pair is reported with its distance from the boundary
     diffs = []
     for b in range(calls):
