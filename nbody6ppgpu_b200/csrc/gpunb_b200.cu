@@ -445,7 +445,9 @@ __device__ __forceinline__ void interact_far2(const float2 cx, const float2 cy, 
 
 // NEAR tile: full body.
 //   Predicate: the reference's, bit for bit, on the fp32-rounded inputs (gpunb.velocity.cu:168-187,
-//   :235 for m_flag): r2 = fma(dz,dz,fma(dy,dy,dx*dx)), dxp = fma(dtr,dvx,dx), min(r2,r2p) < h2 [*mj].
+//   :235 for m_flag), in the operation order nvcc gives the reference kernel (read off its SASS:
+//   FMUL dy*dy; FFMA dx,dx; FFMA dz,dz): r2 = fma(dz,dz,fma(dx,dx,dy*dy)), dxp = fma(dtr,dvx,dx), r2p likewise,
+//   min(r2,r2p) < h2 [*mj].
 //   Force: from the float-float separation (xh_j - xh_i) + (xl_j - xl_i) -- exact to ~2^-48 whatever the tile
 //   extent -- with a Newton-refined rsqrt (a close massive perturber can dominate the sum, so the single
 //   term must hold ~1e-7).  Pairs at r2 == 0 (self) never contribute
@@ -460,9 +462,9 @@ __device__ __forceinline__ bool interact_near(const IState &I, Acc &A,
     const float dx = dxr + (XL + I.nxl), dy = dyr + (YL + I.nyl), dz = dzr + (ZL + I.nzl);
     const float dvx = VX + I.nvx, dvy = VY + I.nvy, dvz = VZ + I.nvz;
 
-    const float r2r = fmaf(dzr, dzr, fmaf(dyr, dyr, dxr * dxr));
+    const float r2r = fmaf(dzr, dzr, fmaf(dxr, dxr, dyr * dyr));
     const float dxp = fmaf(I.dtr, dvx, dxr), dyp = fmaf(I.dtr, dvy, dyr), dzp = fmaf(I.dtr, dvz, dzr);
-    const float r2p = fmaf(dzp, dzp, fmaf(dyp, dyp, dxp * dxp));
+    const float r2p = fmaf(dzp, dzp, fmaf(dxp, dxp, dyp * dyp));
     const float r2  = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     const float rv  = fmaf(dz, dvz, fmaf(dy, dvy, dx * dvx));
 
@@ -488,10 +490,10 @@ __device__ __forceinline__ unsigned interact_near2(const IState &I, Acc2 &A, flo
                  dz = add2(dzr, add2(ZL, dup2(I.nzl)));
     const float2 dvx = add2(VX, dup2(I.nvx)), dvy = add2(VY, dup2(I.nvy)), dvz = add2(VZ, dup2(I.nvz));
 
-    const float2 r2r = fma2(dzr, dzr, fma2(dyr, dyr, mul2(dxr, dxr)));
+    const float2 r2r = fma2(dzr, dzr, fma2(dxr, dxr, mul2(dyr, dyr)));
     const float2 dtr = dup2(I.dtr);
     const float2 dxp = fma2(dtr, dvx, dxr), dyp = fma2(dtr, dvy, dyr), dzp = fma2(dtr, dvz, dzr);
-    const float2 r2p = fma2(dzp, dzp, fma2(dyp, dyp, mul2(dxp, dxp)));
+    const float2 r2p = fma2(dzp, dzp, fma2(dxp, dxp, mul2(dyp, dyp)));
     const float2 r2  = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
     const float2 rv  = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
 
