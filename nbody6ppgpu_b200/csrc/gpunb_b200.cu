@@ -1271,6 +1271,7 @@ struct Dev {
     int *vals_in = nullptr, *perm = nullptr; int sort_cap = 0;
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     int *iperm = nullptr;         // Morton order of the current i-block
+    int *iperm_identity = nullptr;   // 0, 1, 2, ... (blocks of a single i-tile are not sorted)
     unsigned long long *stats = nullptr;   // [0] near (warp,tile) visits, [1] all visits (GPUNB_B200_STATS=1)
     unsigned long long *wtime = nullptr;   // per work item start/end timestamps (GPUNB_B200_STATS=2)
     double *ibuf = nullptr;       // 8*NIMAX doubles: h2 | dtr | x | v
@@ -1466,6 +1467,14 @@ void ensure_j_capacity(Dev &d, int nj_total, int shard_n)
     }
 }
 
+int hilbert_bits(int n)
+{
+    int lg = 0;
+    while ((1ll << lg) < n) lg++;
+    int b = (lg + 2) / 3 + 5;
+    return b < 8 ? 8 : (b > 21 ? 21 : b);
+}
+
 void ensure_sort_capacity(Dev &d, int n)
 {
     set_dev(d);
@@ -1495,7 +1504,11 @@ void build_tiles(Dev &d, int n, const double *m, const double *x, const double *
     absmax_kernel<<<(n + 255) / 256, 256, 0, d.st>>>(n, m, x, v, d.hbits, d.nanflag);
     mortonkey_kernel<<<(n + 255) / 256, 256, 0, d.st>>>(n, x, d.hbits, d.keys_in, d.vals_in);
     size_t bytes = d.cub_tmp_bytes;
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d.cub_tmp, bytes, d.keys_in, d.keys_out, d.vals_in, d.perm, n, 0, 63, d.st));
+    // Only the leading 3*b bits of the 63-bit keys are sorted (b = bits per axis for ~32 cells per particle along the
+    // curve); ties keep their index order (stable).  5 radix passes at N = 10^6 and 4 at N = 10^4 instead of 8: at
+    // small N the sort is nothing but launch latency.  Mirror: sharding.hilbert_order().
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d.cub_tmp, bytes, d.keys_in, d.keys_out, d.vals_in, d.perm, n,
+                                               63 - 3 * hilbert_bits(n), 63, d.st));
     if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx);
     CUDA_CHECK(cudaGetLastError());
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 4;       // + the CUB sort passes (library code, not counted)
@@ -1573,6 +1586,11 @@ void lib_open(int nbmax, int irank)
         if (!d.ibuf)    dev_alloc(d.ibuf, (size_t)8 * NIMAX);
         if (!d.fr)      dev_alloc(d.fr, (size_t)8 * NIMAX);
         if (!d.iperm)   dev_alloc(d.iperm, (size_t)NIMAX);
+        if (!d.iperm_identity) {
+            dev_alloc(d.iperm_identity, (size_t)NIMAX);
+            iota_kernel<<<(NIMAX + 255) / 256, 256, 0, d.st>>>(NIMAX, NIMAX, d.iperm_identity, nullptr);
+            CUDA_CHECK(cudaGetLastError());
+        }
         if (!d.stats && getenv("GPUNB_B200_STATS")) { dev_alloc(d.stats, 4); CUDA_CHECK(cudaMemsetAsync(d.stats, 0, 32, d.st)); }
         if (!d.wtime && getenv("GPUNB_B200_STATS") && atoi(getenv("GPUNB_B200_STATS")) >= 2) dev_alloc(d.wtime, (size_t)3 * 65536);
         if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
@@ -1601,7 +1619,7 @@ void lib_close()
         }
         dev_free(d.iperm_all); d.iperm_all_n = 0;
         dev_free(d.state); d.state_cap = d.state_n = 0; dev_free(d.upd_rec); dev_free(d.upd_idx); dev_free(d.upd_bad); d.upd_cap = 0;
-        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.stats); dev_free(d.wtime);
+        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.iperm_identity); dev_free(d.stats); dev_free(d.wtime);
         dev_free(d.jidx);
         dev_free(d.nanflag);
     }
@@ -2056,8 +2074,12 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         CUDA_CHECK(cudaMemcpyAsync(d.ibuf, h, sizeof(double) * 8 * ni, cudaMemcpyHostToDevice, d.st));
         L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 8.0 * ni;
         ib[g] = IBlock{d.ibuf, d.ibuf + ni, d.ibuf + 2 * (size_t)ni, d.ibuf + 5 * (size_t)ni};
-        launch_isort(d, d.st, ni, ni, ib[g].xi, d.iperm, g == 0 ? L.h_iperm_dev : nullptr);
-        ipm[g] = d.iperm;
+        if (ni <= d.itile) {               // one i-tile: the order does not matter, skip the sort
+            ipm[g] = d.iperm_identity;
+        } else {
+            launch_isort(d, d.st, ni, ni, ib[g].xi, d.iperm, g == 0 ? L.h_iperm_dev : nullptr);
+            ipm[g] = d.iperm;
+        }
     }
     set_dev(root);
     Job j;
@@ -2071,7 +2093,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         const double t0 = wtime();
         t_wait = t0 - tw;
         L.ctr[GPUNB_B200_CTR_HOST_ENQUEUE_MS] += (tw - wt_packed) * 1e3;
-        scatter_rows(L.h_iperm, 0, ni, lmax, acc, jrk, pot, list);
+        scatter_rows(ni <= root.itile ? nullptr : L.h_iperm, 0, ni, lmax, acc, jrk, pot, list);
         t_scatter = wtime() - t0;
     } else {
         const int per = (((ni + nsub - 1) / nsub) + 31) & ~31;       // whole i-tiles per sub-block

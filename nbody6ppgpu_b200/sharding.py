@@ -64,10 +64,24 @@ def hilbert_keys(x: np.ndarray) -> np.ndarray:
     return (spread(X[0]) << np.uint64(2)) | (spread(X[1]) << np.uint64(1)) | spread(X[2])
 
 
+def hilbert_bits(n: int) -> int:
+    """Bits per axis the library sorts on (mirror of hilbert_bits() in gpunb_b200.cu)."""
+    lg = 0
+    while (1 << lg) < n:
+        lg += 1
+    return min(max((lg + 2) // 3 + 5, 8), 21)
+
+
+def hilbert_order(x: np.ndarray) -> np.ndarray:
+    """The library's j order: stable sort on the leading 3*hilbert_bits(n) bits of the 63-bit Hilbert keys."""
+    shift = np.uint64(63 - 3 * hilbert_bits(x.shape[0]))
+    return np.argsort(hilbert_keys(x) >> shift, kind="stable")
+
+
 def shard_members(x: np.ndarray, rank: int, nranks: int) -> np.ndarray:
     """Global j indices (ascending) of the particles in shard `rank`."""
     nj = x.shape[0]
-    order = np.argsort(hilbert_keys(x), kind="stable")
+    order = hilbert_order(x)
     parts = [order[t * TJ:min((t + 1) * TJ, nj)] for t in shard_tiles(rank, nranks, nj)]
     return np.sort(np.concatenate(parts)) if parts else np.zeros(0, dtype=np.int64)
 
