@@ -1239,7 +1239,7 @@ constexpr int DEFAULT_NSLOT = 3;       // slots a sharded resident sweep cycles 
 constexpr int DEFAULT_NSUB  = 4;       // sub-blocks of one gpunb_regf_ call (GPUNB_B200_NSUB)
 struct Slot {
     cudaStream_t lo = nullptr, hi = nullptr;
-    cudaEvent_t ev_regf = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_regf = nullptr, ev_done = nullptr, ev_start = nullptr;
     bool used = false;                 // ev_done has been recorded at least once
     int items_cap = 0;
     double *part = nullptr; int *cnt = nullptr;
@@ -1326,6 +1326,7 @@ struct Lib {
     int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
+    bool taper = true;             // tapering sub-block sizes (GPUNB_B200_TAPER=0: equal sizes)
     bool nslot_auto = true;        // nslot not chosen by the caller (environment / gpunb_b200_set_tuning)
     int near_exact = -1;           // >= 0: overrides GPUNB_B200_NEAR_EXACT (gpunb_b200_set_near_exact)
     bool nsub_forced = false;      // tests: split even when the pair kernels would be too short to be worth it
@@ -1390,6 +1391,7 @@ void lib_devinit(int irank)
             CUDA_CHECK(cudaStreamCreateWithPriority(&sl.hi, cudaStreamNonBlocking, prio_greatest));
             CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_regf, cudaEventDisableTiming));
             CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&sl.ev_start, cudaEventDisableTiming));
         }
         const int smem = WARPS * NSTAGE * TILE_BYTES + WARPS * NSTAGE * 8;
         const char *vn = getenv("GPUNB_B200_VARIANT");
@@ -1430,6 +1432,7 @@ void lib_devinit(int irank)
     memset(L.h_flag, 0, 16 * sizeof(int));
     { const char *e = getenv("GPUNB_B200_NSLOT"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) { L.nslot = atoi(e); L.nslot_auto = false; } }
     { const char *e = getenv("GPUNB_B200_NSUB");  if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nsub = atoi(e); }
+    { const char *e = getenv("GPUNB_B200_TAPER"); if (e) L.taper = atoi(e) != 0; }
     { const char *e = getenv("GPUNB_B200_HOST_THREADS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) L.host_threads = atoi(e); }
     L.devinit = true;
 }
@@ -2096,13 +2099,29 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         scatter_rows(ni <= root.itile ? nullptr : L.h_iperm, 0, ni, lmax, acc, jrk, pot, list);
         t_scatter = wtime() - t0;
     } else {
-        const int per = (((ni + nsub - 1) / nsub) + 31) & ~31;       // whole i-tiles per sub-block
-        CUDA_CHECK(cudaEventRecord(root.ev_fork, root.st));
+        // Sub-block sizes taper off (weights 7:5:3:1 for four): what stays exposed at the end of the call -- the
+        // unfilled tail of the last pair kernel, its merge and the host copy of its rows -- shrinks with the last
+        // sub-block.  Whole i-tiles per sub-block; the streams are released in slot order (each waits for the start
+        // marker of the previous one), so the pair kernels are submitted largest first.
+        int off[MAX_SLOTS + 1] = {0};
         int nq = 0;
-        for (int q = 0; q < nsub && q * per < ni; q++, nq++) {
+        {
+            const int wsum = nsub * nsub;                       // sum of 2(nsub-q)-1
+            for (int q = 0; q < nsub && off[nq] < ni; q++) {
+                int sz = L.taper ? (int)((long long)ni * (2 * (nsub - q) - 1) / wsum) : (ni + nsub - 1) / nsub;
+                sz = (sz + 31) & ~31;
+                if (sz < 32) sz = 32;
+                if (q == nsub - 1 || off[nq] + sz > ni) sz = ni - off[nq];
+                off[nq + 1] = off[nq] + sz;
+                nq++;
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(root.ev_fork, root.st));
+        for (int q = 0; q < nq; q++) {
             Slot &sl = root.slots[q];
-            CUDA_CHECK(cudaStreamWaitEvent(sl.lo, root.ev_fork, 0));
-            j.slot0 = q * per; j.nloc = (ni - j.slot0 < per) ? ni - j.slot0 : per;
+            CUDA_CHECK(cudaStreamWaitEvent(sl.lo, q == 0 ? root.ev_fork : root.slots[q - 1].ev_start, 0));
+            CUDA_CHECK(cudaEventRecord(sl.ev_start, sl.lo));
+            j.slot0 = off[q]; j.nloc = off[q + 1] - off[q];
             if (q == 0) CUDA_CHECK(cudaEventRecord(root.ev0, sl.lo));       // "grav" span: start of the first pair kernel ...
             run_job(j, ib, ipm, q, true, false);
         }
@@ -2114,8 +2133,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
             CUDA_CHECK(cudaEventSynchronize(root.slots[q].ev_done));
             const double t0 = wtime();
             t_wait += t0 - tw;
-            const int k0 = q * per, k1 = (k0 + per < ni) ? k0 + per : ni;
-            scatter_rows(L.h_iperm, k0, k1, lmax, acc, jrk, pot, list);
+            scatter_rows(L.h_iperm, off[q], off[q + 1], lmax, acc, jrk, pot, list);
             t_scatter += wtime() - t0;
         }
         for (int q = 0; q < nq; q++) CUDA_CHECK(cudaStreamWaitEvent(root.st, root.slots[q].ev_done, 0));
@@ -2452,6 +2470,7 @@ void gpunb_b200_predict_send_(int *nj, double *time) { lib_predict_send(*nj, *ti
 void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3]) { lib_get_predicted(*n, idx, &x[0][0], &xdot[0][0]); }
 
 void gpunb_b200_set_near_exact(int on) { L.near_exact = on; }
+void gpunb_b200_set_taper(int on) { L.taper = on != 0; }
 
 void gpunb_b200_set_tuning(int nslot, int nsub)
 {

@@ -93,6 +93,8 @@ class ForceLib:
             L.gpunb_b200_has_near_scalar_ab.restype = C.c_int
             L.gpunb_b200_set_near_exact.argtypes = [C.c_int]
             L.gpunb_b200_set_near_exact.restype = None
+            L.gpunb_b200_set_taper.argtypes = [C.c_int]
+            L.gpunb_b200_set_taper.restype = None
             L.gpunb_b200_set_tuning.argtypes = [C.c_int, C.c_int]
             L.gpunb_b200_set_tuning.restype = None
             L.gpunb_b200_state_all_.argtypes = [_c_int_p] + [_c_dbl_p] * 6
@@ -315,6 +317,11 @@ class ForceLib:
         """Pipeline depth: slots of a resident sweep / sub-blocks of one gpunb_regf_ call (0 = leave unchanged)."""
         self._need_b200()
         self.lib.gpunb_b200_set_tuning(nslot, nsub)
+
+    def set_taper(self, on: int):
+        """Sub-block sizes of one gpunb_regf_ call: tapering (1, default) or equal (0)."""
+        self._need_b200()
+        self.lib.gpunb_b200_set_taper(on)
 
     def set_near_exact(self, on: int):
         """A/B: 1 = NEAR tiles through the scalar pair body, 0 = the packed body (same bits), -1 = environment."""

@@ -63,8 +63,8 @@ if os.environ.get("GPUNB_B200_STATS"):
     c = lib.counters()
     print(f"rank {rank}/{world} tile visits: NEAR {c['near_tiles'] / c['all_tiles'] * 100:5.2f} %", flush=True)
 call = lib.block_caller(h2, dtr, x, v, 1024, 600, 550, 0)
-for nsub in (1, 2, 3, 4, 2):
-    lib.set_tuning(0, nsub)
+for nsub, taper in ((1, 1), (2, 0), (2, 1), (3, 0), (3, 1), (4, 0), (4, 1)):
+    lib.set_tuning(0, nsub); lib.set_taper(taper)
     for rep in range(2):
         if dist: dist.barrier()
         torch.cuda.synchronize()
@@ -74,7 +74,7 @@ for nsub in (1, 2, 3, 4, 2):
             call(b * 1024, 1024)
         t = time.perf_counter() - t0
     c = lib.counters()
-    print(f"rank {rank}/{world} nsub {nsub}: {t / 48 * 1e6:7.1f} us per gpunb_regf_ call  {1024.0 * 48 * n / t * 1e-9:8.1f} Gint/s | host us/call: "
+    print(f"rank {rank}/{world} nsub {nsub} {'tapering' if taper else 'equal   '}: {t / 48 * 1e6:7.1f} us per gpunb_regf_ call  {1024.0 * 48 * n / t * 1e-9:8.1f} Gint/s | host us/call: "
           f"pack {c['host_pack_ms'] / 48 * 1e3:5.1f} enqueue {c['host_enqueue_ms'] / 48 * 1e3:5.1f} wait {c['host_wait_ms'] / 48 * 1e3:6.1f} "
           f"scatter {c['host_scatter_ms'] / 48 * 1e3:5.1f} | device us/call: pair kernels {c['grav_ms'] / 48 * 1e3:6.1f} tail {c['merge_ms'] / 48 * 1e3:5.1f}", flush=True)
 lib.reset_counters()
