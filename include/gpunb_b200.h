@@ -131,8 +131,8 @@ void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3
  * the fixed costs of a launch); nsub = -k forces k sub-blocks of any size (tests).  Other values leave the setting
  * unchanged.  Environment: GPUNB_B200_NSLOT / GPUNB_B200_NSUB. */
 void  gpunb_b200_set_tuning(int nslot, int nsub);
-/* Sub-block sizes of one gpunb_regf_ call: 1 = tapering (weights 7:5:3:1 for four sub-blocks; default), 0 = equal.
- * Environment: GPUNB_B200_TAPER. */
+/* Sub-block sizes of one gpunb_regf_ call: 0 = equal (default), 1 = tapering (weights 7:5:3:1 for four sub-blocks;
+ * measured, no gain).  Environment: GPUNB_B200_TAPER. */
 void  gpunb_b200_set_taper(int on);
 
 /* A-B builds only (make EXTRA=-DNEAR_SCALAR_AB; gpunb_b200_has_near_scalar_ab() == 1): 1 = NEAR tiles through the

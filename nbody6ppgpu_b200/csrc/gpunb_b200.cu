@@ -1326,7 +1326,7 @@ struct Lib {
     int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
-    bool taper = true;             // tapering sub-block sizes (GPUNB_B200_TAPER=0: equal sizes)
+    bool taper = false;            // tapering sub-block sizes (GPUNB_B200_TAPER=1); measured: no gain at 4 sub-blocks
     bool nslot_auto = true;        // nslot not chosen by the caller (environment / gpunb_b200_set_tuning)
     int near_exact = -1;           // >= 0: overrides GPUNB_B200_NEAR_EXACT (gpunb_b200_set_near_exact)
     bool nsub_forced = false;      // tests: split even when the pair kernels would be too short to be worth it
@@ -2099,10 +2099,11 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         scatter_rows(ni <= root.itile ? nullptr : L.h_iperm, 0, ni, lmax, acc, jrk, pot, list);
         t_scatter = wtime() - t0;
     } else {
-        // Sub-block sizes taper off (weights 7:5:3:1 for four): what stays exposed at the end of the call -- the
-        // unfilled tail of the last pair kernel, its merge and the host copy of its rows -- shrinks with the last
-        // sub-block.  Whole i-tiles per sub-block; the streams are released in slot order (each waits for the start
-        // marker of the previous one), so the pair kernels are submitted largest first.
+        // Whole i-tiles per sub-block, equal sizes by default.  Tapering sizes (weights 7:5:3:1 for four, so that what
+        // stays exposed at the end of the call -- the unfilled tail of the last pair kernel, its merge and the host copy
+        // of its rows -- shrinks with the last sub-block) were measured: 1206 us per call either way at 4 sub-blocks,
+        // because the hardware does not start the pair kernels of equal-priority streams in submission order (with two
+        // sub-blocks the SMALL one ran first).  The streams are still released in slot order.
         int off[MAX_SLOTS + 1] = {0};
         int nq = 0;
         {

@@ -319,7 +319,7 @@ class ForceLib:
         self.lib.gpunb_b200_set_tuning(nslot, nsub)
 
     def set_taper(self, on: int):
-        """Sub-block sizes of one gpunb_regf_ call: tapering (1, default) or equal (0)."""
+        """Sub-block sizes of one gpunb_regf_ call: equal (0, default) or tapering (1)."""
         self._need_b200()
         self.lib.gpunb_b200_set_taper(on)
 
