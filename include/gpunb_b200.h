@@ -76,7 +76,7 @@ enum {
     GPUNB_B200_CTR_TL_ISORT_MS,     /* isort_kernel                                            */
     GPUNB_B200_CTR_TL_REGF_MS,      /* regf_kernel                                             */
     GPUNB_B200_CTR_TL_MERGE_MS,     /* merge_kernel                                            */
-    GPUNB_B200_CTR_TL_EXCH_MS,      /* signal_kernel + combine_kernel (multi-GPU; includes waiting for the slowest shard) */
+    GPUNB_B200_CTR_TL_EXCH_MS,      /* combine_kernel (multi-GPU; includes waiting for the slowest shard's flag) */
     /* host-side wall-clock buckets of gpunb_regf_ (ms): pack + NaN check of the i-block, enqueueing copies and
      * kernels, waiting for the device, copying result rows into the caller's arrays */
     GPUNB_B200_CTR_HOST_PACK_MS,
@@ -161,9 +161,11 @@ int gpunb_b200_debug_wtimes(unsigned long long *out, int max_items);
  *  (B) one process per GPU (MPI / torchrun): rank 0 creates a 128-byte ncclUniqueId with
  *      gpunb_b200_nccl_unique_id, the caller broadcasts it, every rank calls gpunb_b200_nccl_init after
  *      gpunb_devinit_ and before gpunb_open_.  From then on EVERY rank makes identical calls (same snapshot,
- *      same i-blocks) and every rank receives the complete result; rank r sums over j in
- *      [r*nj/R, (r+1)*nj/R).  Partials (64 B per i) travel by ncclAllGather, neighbour rows are pulled from
- *      cudaIpc-mapped peer memory by the combine kernel.
+ *      same i-blocks) and every rank receives the complete result; rank r sums over every R-th tile of the
+ *      Hilbert-sorted j-set.  NCCL only bootstraps (cudaIpc handles, barriers): per call, each rank's merge kernel
+ *      raises a flag in every peer's exchange buffer over NVLink and the combine kernel pulls the 64 B per i of
+ *      partial sums and the valid part of the neighbour rows from the peers' memory.  gpupot_ uses one
+ *      ncclAllGather of the partial potentials.
  * Return 0 on success. */
 int  gpunb_b200_nccl_unique_id(unsigned char id128[128]);
 int  gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128]);

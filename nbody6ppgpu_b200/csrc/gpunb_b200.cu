@@ -21,25 +21,33 @@
 //                       xl,yl,zl = (float)(x - xh)  low words: NEAR pairs use the float-float separation.
 //            A tile is contiguous: ONE 1-D TMA bulk copy brings header and data.
 //   jidx   : sorted slot -> global j index (ghost slots of the last tile: -1)
-//   part   : per (j-slice s, i) partial sums, 7 doubles, + count                            [S][ni]
-//   seg    : per (i, s) neighbour-index segment, capacity segcap ints
-//   res_f  : per i  acc[3] jrk[3] pot  (fp64)   ; res_list : [ni][lmax] int32 (the ABI layout)
+//   per pipeline slot (struct Slot: the buffers one i-block or sub-block needs, and a lo/hi stream pair)
+//     part   : per (j-slice s, local i-slot) partial sums, 7 doubles, + count                  [S][nloc]
+//     seg    : per (local i-slot, s) neighbour-index segment, capacity segcap ints
+//     res_f  : per i  acc[3] jrk[3] pot  (fp64)   ; res_list : [ni][lmax] int32 (the ABI layout); gpunb_regf_ results
+//              go to MAPPED pinned host buffers of the same layout instead (written by the kernels over PCIe)
+//   state  : device-resident predictor (body | x0 | x0dot | f | fdot | t0)
 //
 // Kernels
 //   absmax/mortonkey/tilepack   fp64 snapshot -> sorted tiles (radix sort of the keys: CUB, plumbing)
 //   isort_kernel   Morton order of the i-block, so that the 32 i-particles of a warp are close in space
 //   regf_kernel    the O(ni*nj) pair kernel.  One WARP = one work item (32*IT i-particles, every S-th
 //                  j-tile).  Tiles stream through warp-private shared memory by TMA bulk copies
-//                  (cp.async.bulk + mbarrier, double buffered); lanes own i-particles, j is broadcast
-//                  from smem; scalar FP32 FMA stream (see the note above accumulate()).
+//                  (cp.async.bulk + mbarrier, 3 stages); lanes own i-particles, j is broadcast from smem;
+//                  packed f32x2 over j (see the note above accumulate()).
 //                  Per (warp, tile) the bounding boxes decide: FAR tiles (no pair can satisfy the
 //                  neighbour criterion, with margin) run a 27-op force-only body; NEAR tiles run the
 //                  full body with the reference predicate.  FP32 chains are 32 terms, then fp64.
 //   merge_kernel   per i: fp64 sum of the S partials in fixed order, gather of the S segments, sort
 //                  ascending (lists must be strictly ascending: regcor_gpu.F:299-336), overflow
 //                  encoding -(count) (reg.avx.cpp:320-321).
-//   combine_kernel multi-GPU exchange step over NVLink peer pointers.
-//   pot_kernel     gpupot: tile-local dx, rsqrt + one Newton step, fp64 flush.
+//                  Its last CTA publishes the shard result to the peers (flags over NVLink) when sharded.
+//   combine_kernel multi-GPU exchange step over NVLink peer pointers (flags, peer pulls, acks).
+//   pot_kernel     gpupot: tile-local dx (two-float separations for close tiles), packed f32x2, rsqrt + one
+//                  Newton step, fp64 flush; pot_sum_kernel adds the shards' partials in rank order.
+//   predict_kernel device-resident predictor (xbpredall.f restated, unfused fp64).
+// Host side: resident sweeps cycle the i-blocks through pipeline slots; gpunb_regf_ splits its block into sub-blocks
+// on the same slots.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cstdio>
