@@ -1197,6 +1197,20 @@ __global__ void predict_kernel(int n, int cap, const double *__restrict__ st, do
         v[q] = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(FD, s1), F), s2), V0);
     }
 }
+// out[k] = x[idx[k]] | v[idx[k]] (6 doubles) from the m | x | v snapshot
+__global__ void snapshot_gather_kernel(int n, int nj, const int *__restrict__ idx, const double *__restrict__ jraw,
+                                       double *__restrict__ out, int *__restrict__ bad)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int j = idx[k];
+    if (j < 0 || j >= nj) { atomicExch(bad, 1); return; }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        out[6 * (size_t)k + c] = jraw[nj + 3 * (size_t)j + c];
+        out[6 * (size_t)k + 3 + c] = jraw[4 * (size_t)nj + 3 * (size_t)j + c];
+    }
+}
 // rec: n records of 14 doubles (body, x0[3], x0dot[3], f[3], fdot[3], t0) for the particles idx[k] (0-based)
 __global__ void state_scatter_kernel(int n, int cap, int nj, const int *__restrict__ idx, const double *__restrict__ rec,
                                      double *__restrict__ st, int *__restrict__ bad)
@@ -1844,20 +1858,38 @@ void lib_predict_send(int nj, double time)
 void lib_get_predicted(int n, const int *idx, double *x, double *xdot)
 {
     if (!L.is_open) FATAL("gpunb_b200_get_predicted called while the library is closed");
+    if (n <= 0) return;
     Dev &d = L.devs[0];
     set_dev(d);
     const int nj = d.nj_total;
-    // small n: gather on the host from two strided copies would need n round trips; copy the two arrays once instead
-    static std::vector<double> hx;
-    hx.resize((size_t)6 * nj);
-    CUDA_CHECK(cudaMemcpyAsync(hx.data(), d.jraw + nj, sizeof(double) * 6 * nj, cudaMemcpyDeviceToHost, d.st));
-    CUDA_CHECK(cudaStreamSynchronize(d.st));
-    for (int k = 0; k < n; k++) {
-        const int j = idx[k];
-        if (j < 0 || j >= nj) FATAL("gpunb_b200_get_predicted: index %d outside [0, %d)", j, nj);
-        for (int c = 0; c < 3; c++) { x[3 * (size_t)k + c] = hx[3 * (size_t)j + c]; xdot[3 * (size_t)k + c] = hx[3 * (size_t)nj + 3 * (size_t)j + c]; }
+    // reuses the staging buffers of state_update: idx up, 6 doubles per particle down
+    if (n > L.h_upd_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        host_free(L.h_upd); host_free(L.h_upd_idx);
+        L.h_upd_cap = n + 4096;
+        host_alloc(L.h_upd, (size_t)14 * L.h_upd_cap);
+        host_alloc(L.h_upd_idx, (size_t)L.h_upd_cap);
     }
-    L.ctr[GPUNB_B200_CTR_D2H_BYTES] += sizeof(double) * 6.0 * nj;
+    if (n > d.upd_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(d.st));
+        dev_free(d.upd_rec); dev_free(d.upd_idx);
+        d.upd_cap = L.h_upd_cap;
+        dev_alloc(d.upd_rec, (size_t)14 * d.upd_cap); dev_alloc(d.upd_idx, (size_t)d.upd_cap);
+    }
+    if (!d.upd_bad) { dev_alloc(d.upd_bad, 1); CUDA_CHECK(cudaMemsetAsync(d.upd_bad, 0, sizeof(int), d.st)); }
+    memcpy(L.h_upd_idx, idx, sizeof(int) * n);
+    CUDA_CHECK(cudaMemcpyAsync(d.upd_idx, L.h_upd_idx, sizeof(int) * n, cudaMemcpyHostToDevice, d.st));
+    snapshot_gather_kernel<<<(n + 127) / 128, 128, 0, d.st>>>(n, nj, d.upd_idx, d.jraw, d.upd_rec, d.upd_bad);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(L.h_upd, d.upd_rec, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaMemcpyAsync(L.h_flag, d.upd_bad, sizeof(int), cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    if (L.h_flag[0]) FATAL("gpunb_b200_get_predicted: particle index outside [0, %d)", nj);
+    for (int k = 0; k < n; k++)
+        for (int c = 0; c < 3; c++) { x[3 * (size_t)k + c] = L.h_upd[6 * (size_t)k + c]; xdot[3 * (size_t)k + c] = L.h_upd[6 * (size_t)k + 3 + c]; }
+    L.ctr[GPUNB_B200_CTR_D2H_BYTES] += sizeof(double) * 6.0 * n;
+    L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(int) * (double)n;
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
 }
 
 struct Plan { int n_itiles, S, n_items; };
