@@ -66,6 +66,24 @@ def main():
         t0 = time.perf_counter()
         lib.send(m, x, v)
         ts = time.perf_counter() - t0
+        # a steady-state regular block (intgrt.F:912-974): upload the predicted snapshot, then ONE call with few i
+        blockcost = {}
+        for ni in (64, 256):
+            t0 = time.perf_counter()
+            for b in range(5):
+                lib.send(m, x, v)
+                call((30 + b) * 1024, ni)
+            blockcost[f"send+regf_ni{ni}_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+        if lib.is_b200:                            # the same block with the device-resident predictor
+            z3 = np.zeros((n, 3))
+            lib.state_all(m, x, v, z3, z3, np.zeros(n))
+            for ni in (64, 256):
+                t0 = time.perf_counter()
+                for b in range(5):
+                    lib.predict_send(n, 0.0)
+                    call((30 + b) * 1024, ni)
+                blockcost[f"predict_send+regf_ni{ni}_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+        out[f"regular_block_1M_{name}"] = blockcost
         lib.close()
         out[f"rate_{name}"] = {"gint_per_s": 1024.0 * calls * n / t * 1e-9, "us_per_call": t / calls * 1e6,
                                "send_ms": ts * 1e3, "mean_nnb": nnb / (1024.0 * calls), "n": n}
