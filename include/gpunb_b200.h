@@ -131,6 +131,13 @@ void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3
  * the fixed costs of a launch); nsub = -k forces k sub-blocks of any size (tests).  Other values leave the setting
  * unchanged.  Environment: GPUNB_B200_NSLOT / GPUNB_B200_NSUB. */
 void  gpunb_b200_set_tuning(int nslot, int nsub);
+/* Hilbert order of the j-tiles refreshed only every k-th snapshot (gpunb_send_ / gpunb_b200_predict_send_); in between
+ * the previous permutation is kept and the tiles are re-packed from the current positions: results stay exact (boxes and
+ * offsets are recomputed), a snapshot costs one launch instead of nine, and the summation order -- hence the last bits
+ * of the sums -- then depends on the call history.  Default 1 (always sort: results are a function of the snapshot
+ * alone).  Environment: GPUNB_B200_RESORT_EVERY. */
+void  gpunb_b200_set_resort_every(int k);
+
 /* Sub-block sizes of one gpunb_regf_ call: 0 = equal (default), 1 = tapering (weights 7:5:3:1 for four sub-blocks;
  * measured, no gain).  Environment: GPUNB_B200_TAPER. */
 void  gpunb_b200_set_taper(int on);

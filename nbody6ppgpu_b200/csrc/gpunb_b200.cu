@@ -222,7 +222,7 @@ __global__ void mortonkey_kernel(int n, const double *__restrict__ x, const unsi
 __global__ void __launch_bounds__(128) tilepack_kernel(int n, int t0, int tstride, int nloc, const double *__restrict__ m,
                                                         const double *__restrict__ x, const double *__restrict__ v,
                                                         const int *__restrict__ perm, float *__restrict__ tiles,
-                                                        int *__restrict__ jidx)
+                                                        int *__restrict__ jidx, int *__restrict__ nanflag)
 {   // packs tiles t = t0 + l * tstride (l < nloc) of the sorted order into tiles[l], jidx[l * TJ ..]
     const int lane = threadIdx.x & 31;
     const int l = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(128) tilepack_kernel(int n, int t0, int tstrid
             vmn[c] = fminf(vmn[c], pv[h][c]); vmx[c] = fmaxf(vmx[c], pv[h][c]);
         }
         pm[h] = real ? (float)m[src] : 0.f;
+        if (pm[h] != pm[h] || px[h][0] != px[h][0] || px[h][1] != px[h][1] || px[h][2] != px[h][2] ||
+            pv[h][0] != pv[h][0] || pv[h][1] != pv[h][1] || pv[h][2] != pv[h][2]) atomicExch(nanflag, 1);
         mmax = fmaxf(mmax, pm[h]);
         jidx[l * TJ + h * 32 + lane] = real ? src : -1;
     }
@@ -1291,6 +1293,7 @@ struct Dev {
     unsigned *hbits = nullptr;    // largest |coordinate| of the shard (float bits)
     unsigned long long *keys_in = nullptr, *keys_out = nullptr;
     int *vals_in = nullptr, *perm = nullptr; int sort_cap = 0;
+    int perm_n = 0;               // perm holds the order of the regf snapshot of this many particles (0: invalid)
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     int *iperm = nullptr;         // Morton order of the current i-block
     int *iperm_identity = nullptr;   // 0, 1, 2, ... (blocks of a single i-tile are not sorted)
@@ -1348,6 +1351,8 @@ struct Lib {
     int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
+    int resort_every = 1;          // Hilbert order refreshed every k-th snapshot (GPUNB_B200_RESORT_EVERY); 1 = always
+    int snapshots_since_sort = 0;
     bool taper = false;            // tapering sub-block sizes (GPUNB_B200_TAPER=1); measured: no gain at 4 sub-blocks
     bool nslot_auto = true;        // nslot not chosen by the caller (environment / gpunb_b200_set_tuning)
     int near_exact = -1;           // >= 0: overrides GPUNB_B200_NEAR_EXACT (gpunb_b200_set_near_exact)
@@ -1455,6 +1460,7 @@ void lib_devinit(int irank)
     { const char *e = getenv("GPUNB_B200_NSLOT"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) { L.nslot = atoi(e); L.nslot_auto = false; } }
     { const char *e = getenv("GPUNB_B200_NSUB");  if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nsub = atoi(e); }
     { const char *e = getenv("GPUNB_B200_TAPER"); if (e) L.taper = atoi(e) != 0; }
+    { const char *e = getenv("GPUNB_B200_RESORT_EVERY"); if (e && atoi(e) >= 1) L.resort_every = atoi(e); }
     { const char *e = getenv("GPUNB_B200_HOST_THREADS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) L.host_threads = atoi(e); }
     L.devinit = true;
 }
@@ -1507,6 +1513,7 @@ void ensure_sort_capacity(Dev &d, int n)
     if (n <= d.sort_cap) return;
     CUDA_CHECK(cudaStreamSynchronize(d.st));
     dev_free(d.keys_in); dev_free(d.keys_out); dev_free(d.vals_in); dev_free(d.perm);
+    d.perm_n = 0;
     if (d.cub_tmp) CUDA_CHECK(cudaFree(d.cub_tmp)); d.cub_tmp = nullptr;
     d.sort_cap = n + 1024;
     dev_alloc(d.keys_in, d.sort_cap); dev_alloc(d.keys_out, d.sort_cap);
@@ -1520,21 +1527,31 @@ void ensure_sort_capacity(Dev &d, int n)
 // fp64 particles (m, x, v or NULL; n of them, device pointers) -> Hilbert-sorted tiles + slot->index map.
 // ALL n particles are sorted; tiles t0, t0 + tstride, ... (nloc of them) of the sorted order are packed (the tiles
 // of one j-shard, see shard_tiles).  The radix sort of the 63-bit keys is CUB (plumbing, not the hot path).
+// reuse_order: keep the permutation of the previous snapshot of the same n (GPUNB_B200_RESORT_EVERY > 1); the tiles are
+// re-packed from the current positions, so boxes, offsets and results stay exact -- only the compactness of the tiles
+// ages with the particles' motion.
 void build_tiles(Dev &d, int n, const double *m, const double *x, const double *v, float *tiles, int *jidx,
-                 int t0, int tstride, int nloc)
+                 int t0, int tstride, int nloc, bool reuse_order = false)
 {
     if (n <= 0) return;
     ensure_sort_capacity(d, n);
+    if (reuse_order && d.perm_n == n) {
+        if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag);
+        CUDA_CHECK(cudaGetLastError());
+        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+        return;
+    }
     CUDA_CHECK(cudaMemsetAsync(d.hbits, 0, sizeof(unsigned), d.st));
     absmax_kernel<<<(n + 255) / 256, 256, 0, d.st>>>(n, m, x, v, d.hbits, d.nanflag);
     mortonkey_kernel<<<(n + 255) / 256, 256, 0, d.st>>>(n, x, d.hbits, d.keys_in, d.vals_in);
+    d.perm_n = n;
     size_t bytes = d.cub_tmp_bytes;
     // Only the leading 3*b bits of the 63-bit keys are sorted (b = bits per axis for ~32 cells per particle along the
     // curve); ties keep their index order (stable).  5 radix passes at N = 10^6 and 4 at N = 10^4 instead of 8: at
     // small N the sort is nothing but launch latency.  Mirror: sharding.hilbert_order().
     CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d.cub_tmp, bytes, d.keys_in, d.keys_out, d.vals_in, d.perm, n,
                                                63 - 3 * hilbert_bits(n), 63, d.st));
-    if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx);
+    if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag);
     CUDA_CHECK(cudaGetLastError());
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 4;       // + the CUB sort passes (library code, not counted)
 }
@@ -1713,11 +1730,13 @@ void finish_send(int nj, double wt0, const char *who)
 {
     const int R = total_ranks();
     const double wt1 = wtime();
+    const bool reuse = L.resort_every > 1 && (L.snapshots_since_sort % L.resort_every) != 0;
+    L.snapshots_since_sort = reuse ? L.snapshots_since_sort + 1 : 1;
     for (size_t g = 0; g < L.devs.size(); g++) {
         Dev &d = L.devs[g];
         set_dev(d);
         CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
-        build_tiles(d, nj, d.jraw, d.jraw + nj, d.jraw + 4 * (size_t)nj, d.jtile, d.jidx, L.sh.on ? L.sh.rank : (int)g, R, d.ntiles);
+        build_tiles(d, nj, d.jraw, d.jraw + nj, d.jraw + 4 * (size_t)nj, d.jtile, d.jidx, L.sh.on ? L.sh.rank : (int)g, R, d.ntiles, reuse);
         CUDA_CHECK(cudaEventRecord(d.evs1, d.st));
         CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, d.nanflag, sizeof(int), cudaMemcpyDeviceToHost, d.st));
     }
@@ -2237,6 +2256,7 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
         if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
         CUDA_CHECK(cudaMemcpyAsync(d.pot_jraw, hpin, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, d.st));
         build_tiles(d, n, d.pot_jraw, d.pot_jraw + n, nullptr, d.pot_jtile, d.pot_jidx, L.sh.on ? L.sh.rank : g, R, nloc);
+        d.perm_n = 0;                              // the sort scratch now holds gpupot's order
         int S = (d.nsm * 16 * 4) / n_it; if (S < 1) S = 1; if (S > nloc) S = nloc > 0 ? nloc : 1;
         if ((size_t)S * ni > d.pot_part_n) { CUDA_CHECK(cudaStreamSynchronize(d.st)); dev_free(d.pot_part); d.pot_part_n = (size_t)S * ni; dev_alloc(d.pot_part, d.pot_part_n); }
         if ((size_t)ni > d.pot_out_n) { CUDA_CHECK(cudaStreamSynchronize(d.st)); dev_free(d.pot_out); d.pot_out_n = ni; dev_alloc(d.pot_out, d.pot_out_n); }
@@ -2512,6 +2532,7 @@ void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3
 
 void gpunb_b200_set_near_exact(int on) { L.near_exact = on; }
 void gpunb_b200_set_taper(int on) { L.taper = on != 0; }
+void gpunb_b200_set_resort_every(int k) { if (k >= 1) { L.resort_every = k; L.snapshots_since_sort = 0; } }
 
 void gpunb_b200_set_tuning(int nslot, int nsub)
 {

@@ -93,6 +93,8 @@ class ForceLib:
             L.gpunb_b200_has_near_scalar_ab.restype = C.c_int
             L.gpunb_b200_set_near_exact.argtypes = [C.c_int]
             L.gpunb_b200_set_near_exact.restype = None
+            L.gpunb_b200_set_resort_every.argtypes = [C.c_int]
+            L.gpunb_b200_set_resort_every.restype = None
             L.gpunb_b200_set_taper.argtypes = [C.c_int]
             L.gpunb_b200_set_taper.restype = None
             L.gpunb_b200_set_tuning.argtypes = [C.c_int, C.c_int]
@@ -317,6 +319,11 @@ class ForceLib:
         """Pipeline depth: slots of a resident sweep / sub-blocks of one gpunb_regf_ call (0 = leave unchanged)."""
         self._need_b200()
         self.lib.gpunb_b200_set_tuning(nslot, nsub)
+
+    def set_resort_every(self, k: int):
+        """Hilbert order refreshed every k-th snapshot only (1 = always, the default)."""
+        self._need_b200()
+        self.lib.gpunb_b200_set_resort_every(k)
 
     def set_taper(self, on: int):
         """Sub-block sizes of one gpunb_regf_ call: equal (0, default) or tapering (1)."""

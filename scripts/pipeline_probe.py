@@ -44,7 +44,21 @@ tu = (time.perf_counter() - t0) / 5
 c = lib.counters()
 print(f"rank {rank}/{world} gpunb_b200_predict_send_ N={n}: {tp * 1e3:6.2f} ms per call (device tile construction {c['send_tiles_ms'] / c['sends']:6.2f} ms); "
       f"state_update of {idx.size} particles {tu * 1e3:6.3f} ms", flush=True)
+lib.set_resort_every(8)
+lib.predict_send(n, 0.0)
+lib.reset_counters()
+t0 = time.perf_counter()
+for k in range(7):
+    lib.predict_send(n, 1e-3 * (k + 1))
+tp = (time.perf_counter() - t0) / 7
+c = lib.counters()
+print(f"rank {rank}/{world} gpunb_b200_predict_send_ with the Hilbert order kept (GPUNB_B200_RESORT_EVERY=8): {tp * 1e3:6.2f} ms per call "
+      f"(device tile construction {c['send_tiles_ms'] / c['sends']:6.2f} ms)", flush=True)
+lib.set_resort_every(1)
 lib.send(m, x, v)
+if os.environ.get("PROBE_ONLY_SEND"):
+    lib.close()
+    sys.exit(0)
 for nslot in (1, 2, 3, 4, 3):
     lib.set_tuning(nslot, 0)
     lib.sweep_resident(0, 1024 * 16, 1024, 600, 550, 0)
