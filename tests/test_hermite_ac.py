@@ -49,3 +49,20 @@ def test_energy_drift_matches_reference_library(b200, ref_avx):
         with open(os.environ["GPUNB_DRIFT_OUT"], "w") as fh:
             json.dump({"n": 1024, "t_end": 1.0, "nnbopt": 40, "dE_over_E": out, "stats": stats}, fh)
     assert abs(out["b200"]) <= 3.0 * abs(out["avx"]) + 1e-5, out
+
+
+def test_ac_driver_with_imf_and_mass_weighted_criterion(ref_avx):
+    """Kroupa IMF + m_flag = 1 (neighbour criterion r^2 < h2 * m_j, KZ(39) = 2 as in samples/N16k.input): the RS control,
+    the overflow retry loop and the energy bookkeeping of the driver hold with the reference library behind it."""
+    if ref_avx is None:
+        pytest.skip("oracle/_ref not built")
+    m, x, v = S.plummer(384, 8, "kroupa")
+    ac = H.AhmadCohen(ref_avx, m, x, v, nnbopt=24, lmax=128, m_flag=1)
+    try:
+        st = ac.run(0.125)
+    finally:
+        ac.close()
+    e0, e1 = st.energies[0][1], st.energies[-1][1]
+    assert abs((e1 - e0) / e0) < 5e-4, (e0, e1)
+    assert st.reg_steps > 384 and np.all(ac.t0 == 0.125)
+    assert ac.nnb.max() <= ac.nnbmax
