@@ -131,6 +131,16 @@ void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3
  * the fixed costs of a launch); nsub = -k forces k sub-blocks of any size (tests).  Other values leave the setting
  * unchanged.  Environment: GPUNB_B200_NSLOT / GPUNB_B200_NSUB. */
 void  gpunb_b200_set_tuning(int nslot, int nsub);
+/* Caller-pinned arrays (optional).  The reference ABI hands the library pageable arrays, so gpunb_send_ stages the
+ * snapshot through pinned memory and gpunb_regf_ copies result rows into the caller's arrays on the host.  A caller
+ * whose arrays live for the whole run (the Fortran COMMON blocks / static GPUACC, GPUJRK, GPUPHI, LISTGP of
+ * util_gpu.F:14) can pin them ONCE: gpunb_send_ then DMAs straight from them and the kernels write acc / jrk / pot and
+ * the list rows straight into them over PCIe.  Detection is per call and per array range; results are identical.
+ * pin_host returns 0 on success (non-zero: the range stays pageable and the staged path is used).  Unpin before the
+ * memory is freed. */
+int   gpunb_b200_pin_host_(void *ptr, long long *bytes);
+void  gpunb_b200_unpin_host_(void *ptr);
+
 /* Hilbert order of the j-tiles refreshed only every k-th snapshot (gpunb_send_ / gpunb_b200_predict_send_); in between
  * the previous permutation is kept and the tiles are re-packed from the current positions: results stay exact (boxes and
  * offsets are recomputed), a snapshot costs one launch instead of nine, and the summation order -- hence the last bits

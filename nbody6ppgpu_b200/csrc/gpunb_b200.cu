@@ -899,6 +899,8 @@ struct MergeArgs {
     int nloc, S, segcap, lmax, nnbmax;
     const int *iperm;   // output row of local slot kl: i = iperm[kl] (the caller passes iperm + slot0); NULL: i = kl
     double *res_f;      // [.][f_stride]; f_stride = 8 stores the (signed) count in slot 7 for the shard combine
+    double *abi_acc, *abi_jrk, *abi_pot;   // non-NULL: final sums go straight to the caller's acc[.][3] / jrk[.][3] / pot[.]
+                                           // (host arrays the caller has pinned, gpunb_b200_pin_host_) instead of res_f
     int     f_stride;
     int    *res_list;   // [.][lmax]
     int     sort;       // 0: leave the row in arrival order (a shard row: combine_kernel sorts the union)
@@ -926,7 +928,11 @@ __device__ __forceinline__ void merge_row(const MergeArgs &a, int kl, int lane, 
         total += __shfl_xor_sync(0xffffffffu, total, o);
     }
     const int i = a.iperm ? a.iperm[kl] : kl;
-    if (lane < 7) a.res_f[(size_t)i * a.f_stride + lane] = f[lane];   // f[] is uniform after the butterfly
+    if (a.abi_acc) {
+        if (lane < 3) a.abi_acc[3 * (size_t)i + lane] = f[lane];
+        else if (lane < 6) a.abi_jrk[3 * (size_t)i + lane - 3] = f[lane];
+        else if (lane == 6) a.abi_pot[i] = f[6];
+    } else if (lane < 7) a.res_f[(size_t)i * a.f_stride + lane] = f[lane];   // f[] is uniform after the butterfly
     if (a.f_stride == 8 && lane == 7) a.res_f[(size_t)i * 8 + 7] = (double)(total > a.nnbmax ? -total : total);
     int *row = a.res_list + (size_t)i * a.lmax;
     if (total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
@@ -987,6 +993,7 @@ struct CombineArgs {
     const int    *rows[MAX_RANKS];   // [nloc][lmax]
     const int    *iperm;             // output row of kl (NULL: kl)
     double *res_f;                   // [.][7]
+    double *abi_acc, *abi_jrk, *abi_pot;   // non-NULL: the caller's own (pinned) arrays instead of res_f
     int    *res_list;                // [.][lmax]
     // one process per GPU: flags[r] (in THIS rank's exchange buffer) is set to `seq` by rank r, over NVLink, once
     // its fr/rows of this call are complete (last CTA of its merge_kernel).  NULL: ordering is done with stream events.
@@ -1019,7 +1026,11 @@ __device__ __forceinline__ void combine_row(const CombineArgs &a, int kl, int la
         }
     }
     const int i = a.iperm ? a.iperm[kl] : kl;
-    if (lane < 7) a.res_f[(size_t)i * 7 + lane] = f;
+    if (a.abi_acc) {
+        if (lane < 3) a.abi_acc[3 * (size_t)i + lane] = f;
+        else if (lane < 6) a.abi_jrk[3 * (size_t)i + lane - 3] = f;
+        else if (lane == 6) a.abi_pot[i] = f;
+    } else if (lane < 7) a.res_f[(size_t)i * 7 + lane] = f;
     int *row = a.res_list + (size_t)i * a.lmax;
     if (over || total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
     if (lane == 0) row[0] = total;
@@ -1556,6 +1567,22 @@ void build_tiles(Dev &d, int n, const double *m, const double *x, const double *
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 4;       // + the CUB sort passes (library code, not counted)
 }
 
+// Host ranges the caller has pinned with gpunb_b200_pin_host_ (cudaHostRegister, mapped): gpunb_send_ uploads from them
+// without the staging copy, and gpunb_regf_ lets the kernels write results straight into them.
+struct PinnedRange { const char *base; size_t bytes; };
+std::vector<PinnedRange> g_pinned;
+template <class T> T *pinned_alias(const T *p, size_t n)
+{   // device-side alias of p[0..n) when the whole range lies inside one pinned range, else NULL
+    const char *b = reinterpret_cast<const char *>(p);
+    for (const PinnedRange &r : g_pinned)
+        if (b >= r.base && b + n * sizeof(T) <= r.base + r.bytes) {
+            void *d = nullptr;
+            if (cudaHostGetDevicePointer(&d, const_cast<char *>(b), 0) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+            return reinterpret_cast<T *>(d);
+        }
+    return nullptr;
+}
+
 template <class T> void host_alloc_mapped(T *&h, T *&dptr, size_t n)
 {
     CUDA_CHECK(cudaHostAlloc((void **)&h, n * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable));
@@ -1708,7 +1735,16 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
     double *h = L.h_j;
     set_shards(nj);
     constexpr int CHUNK = 1 << 17;                    // particles per chunk (7 MB)
-    for (int c0 = 0; c0 < nj; c0 += CHUNK) {
+    const bool direct = pinned_alias(mj, (size_t)nj) && pinned_alias(xj, (size_t)3 * nj) && pinned_alias(vj, (size_t)3 * nj);
+    if (direct) {                                     // the caller's arrays are pinned: DMA from them, no staging copy
+        for (Dev &d : L.devs) {
+            set_dev(d);
+            CUDA_CHECK(cudaMemcpyAsync(d.jraw, mj, sizeof(double) * nj, cudaMemcpyHostToDevice, d.st));
+            CUDA_CHECK(cudaMemcpyAsync(d.jraw + nj, xj, sizeof(double) * 3 * nj, cudaMemcpyHostToDevice, d.st));
+            CUDA_CHECK(cudaMemcpyAsync(d.jraw + 4 * (size_t)nj, vj, sizeof(double) * 3 * nj, cudaMemcpyHostToDevice, d.st));
+        }
+    }
+    for (int c0 = 0; c0 < nj && !direct; c0 += CHUNK) {
         const size_t c = (size_t)c0, n = (size_t)((nj - c0 < CHUNK) ? nj - c0 : CHUNK);
         threaded_copy(h + c, mj + c, n);
         threaded_copy(h + nj + 3 * c, xj + 3 * c, 3 * n);
@@ -1957,6 +1993,7 @@ struct Job {
     int slot0, nloc;
     int lmax, nnbmax, m_flag;
     double *out_f; int *out_list;      // final results, row i = iperm[slot] (device memory or mapped host memory)
+    double *abi_acc = nullptr, *abi_jrk = nullptr, *abi_pot = nullptr;   // or the caller's pinned arrays (with out_list)
 };
 
 // Pair kernel (stream lo) + shard-local merge (stream hi) of one job on device d, pipeline slot sl.
@@ -2014,12 +2051,14 @@ void run_job(const Job &j, const IBlock *ib, const int *const *iperm, int q, boo
     if (!L.sh.on && G == 1) {          // single GPU: the shard-local merge IS the final result
         MergeArgs m = merge_defaults();
         m.iperm = iperm[0] + j.slot0; m.res_f = j.out_f; m.f_stride = 7; m.res_list = j.out_list; m.sort = 1;
+        m.abi_acc = j.abi_acc; m.abi_jrk = j.abi_jrk; m.abi_pot = j.abi_pot;
         launch_regf(root, sl, lo, hi, j, ib[0], iperm[0], m, time_it, tl);
     } else {
         CombineArgs c;
         memset(&c, 0, sizeof(c));
         c.nloc = j.nloc; c.lmax = j.lmax; c.nnbmax = j.nnbmax; c.res_f = j.out_f; c.res_list = j.out_list;
         c.iperm = iperm[0] + j.slot0;
+        c.abi_acc = j.abi_acc; c.abi_jrk = j.abi_jrk; c.abi_pot = j.abi_pot;
         if (L.sh.on) {
             // One process per GPU.  No collective call in the data path: merge_kernel writes the shard result into
             // this rank's exchange slot and its last CTA raises this rank's flag in every peer's buffer over NVLink;
@@ -2146,6 +2185,25 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     set_dev(root);
     Job j;
     j.lmax = lmax; j.nnbmax = nnbmax; j.m_flag = m_flag; j.out_f = L.h_f_dev; j.out_list = L.h_list_dev;
+    // Output arrays the caller has pinned (gpunb_b200_pin_host_): merge / combine write the ABI layout straight into
+    // them over PCIe and the host-side copy of the rows disappears.
+    bool direct_out = false;
+    {
+        double *a_acc = pinned_alias(acc, (size_t)3 * ni), *a_jrk = pinned_alias(jrk, (size_t)3 * ni), *a_pot = pinned_alias(pot, (size_t)ni);
+        int *a_list = pinned_alias(list, (size_t)ni * lmax);
+        if (a_acc && a_jrk && a_pot && a_list) {
+            direct_out = true;
+            j.abi_acc = a_acc; j.abi_jrk = a_jrk; j.abi_pot = a_pot; j.out_list = a_list; j.out_f = nullptr;
+        }
+    }
+    auto deliver = [&](int k0, int k1) {
+        if (!direct_out) { scatter_rows(ni <= root.itile ? nullptr : L.h_iperm, k0, k1, lmax, acc, jrk, pot, list); return; }
+        if (k0 == 0) {                 // bytes the kernels wrote over PCIe (counted once per call)
+            double bytes = 0;
+            for (int i = 0; i < ni; i++) { const int c = list[(size_t)i * lmax]; bytes += 56.0 + 4.0 * (1 + (c > 0 ? c : 0)); }
+            L.ctr[GPUNB_B200_CTR_D2H_BYTES] += bytes;
+        }
+    };
     double t_scatter = 0.0;
     if (nsub == 1) {
         j.slot0 = 0; j.nloc = ni;
@@ -2155,7 +2213,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         const double t0 = wtime();
         t_wait = t0 - tw;
         L.ctr[GPUNB_B200_CTR_HOST_ENQUEUE_MS] += (tw - wt_packed) * 1e3;
-        scatter_rows(ni <= root.itile ? nullptr : L.h_iperm, 0, ni, lmax, acc, jrk, pot, list);
+        deliver(0, ni);
         t_scatter = wtime() - t0;
     } else {
         // Whole i-tiles per sub-block, equal sizes by default.  Tapering sizes (weights 7:5:3:1 for four, so that what
@@ -2193,7 +2251,8 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
             CUDA_CHECK(cudaEventSynchronize(root.slots[q].ev_done));
             const double t0 = wtime();
             t_wait += t0 - tw;
-            scatter_rows(L.h_iperm, off[q], off[q + 1], lmax, acc, jrk, pot, list);
+            if (!direct_out) deliver(off[q], off[q + 1]);
+            else if (q == nq - 1) deliver(0, ni);
             t_scatter += wtime() - t0;
         }
         for (int q = 0; q < nq; q++) CUDA_CHECK(cudaStreamWaitEvent(root.st, root.slots[q].ev_done, 0));
@@ -2531,6 +2590,30 @@ void gpunb_b200_predict_send_(int *nj, double *time) { lib_predict_send(*nj, *ti
 void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3]) { lib_get_predicted(*n, idx, &x[0][0], &xdot[0][0]); }
 
 void gpunb_b200_set_near_exact(int on) { L.near_exact = on; }
+int gpunb_b200_pin_host_(void *ptr, long long *bytes)
+{
+    if (!L.devinit) FATAL("gpunb_b200_pin_host_ before gpunb_devinit_");
+    if (!ptr || *bytes <= 0) return 1;
+    set_dev(L.devs[0]);
+    const cudaError_t e = cudaHostRegister(ptr, (size_t)*bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        fprintf(stderr, "gpunb_b200: cannot pin %lld bytes at %p (%s); the staged path stays in use\n", *bytes, ptr, cudaGetErrorString(e));
+        return 2;
+    }
+    g_pinned.push_back(PinnedRange{reinterpret_cast<const char *>(ptr), (size_t)*bytes});
+    return 0;
+}
+void gpunb_b200_unpin_host_(void *ptr)
+{
+    for (size_t k = 0; k < g_pinned.size(); k++)
+        if (g_pinned[k].base == reinterpret_cast<const char *>(ptr)) {
+            for (Dev &d : L.devs) { set_dev(d); CUDA_CHECK(cudaDeviceSynchronize()); }
+            CUDA_CHECK(cudaHostUnregister(ptr));
+            g_pinned.erase(g_pinned.begin() + (long)k);
+            return;
+        }
+}
 void gpunb_b200_set_taper(int on) { L.taper = on != 0; }
 void gpunb_b200_set_resort_every(int k) { if (k >= 1) { L.resort_every = k; L.snapshots_since_sort = 0; } }
 

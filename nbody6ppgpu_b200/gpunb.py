@@ -93,6 +93,10 @@ class ForceLib:
             L.gpunb_b200_has_near_scalar_ab.restype = C.c_int
             L.gpunb_b200_set_near_exact.argtypes = [C.c_int]
             L.gpunb_b200_set_near_exact.restype = None
+            L.gpunb_b200_pin_host_.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+            L.gpunb_b200_pin_host_.restype = C.c_int
+            L.gpunb_b200_unpin_host_.argtypes = [C.c_void_p]
+            L.gpunb_b200_unpin_host_.restype = None
             L.gpunb_b200_set_resort_every.argtypes = [C.c_int]
             L.gpunb_b200_set_resort_every.restype = None
             L.gpunb_b200_set_taper.argtypes = [C.c_int]
@@ -196,6 +200,7 @@ class ForceLib:
             c_ni.value = ni
             fn(p_ni, a_h2 + 8 * i0, a_dtr + 8 * i0, a_x + 24 * i0, a_v + 24 * i0, *fixed)
             return acc[:ni], jrk[:ni], pot[:ni], lst[:ni]
+        call.outputs = (acc, jrk, pot, lst)            # the caller-owned result arrays (e.g. for pin_host)
         return call
 
     def profile(self, irank: int = 0):
@@ -319,6 +324,21 @@ class ForceLib:
         """Pipeline depth: slots of a resident sweep / sub-blocks of one gpunb_regf_ call (0 = leave unchanged)."""
         self._need_b200()
         self.lib.gpunb_b200_set_tuning(nslot, nsub)
+
+    def pin_host(self, *arrays) -> bool:
+        """Pin caller-owned numpy arrays (what a Fortran caller does once for its static arrays): gpunb_send_ then
+        uploads without the staging copy and gpunb_regf_ results are written straight into them.  Returns True when
+        every array was pinned.  Call unpin_host before the arrays are released."""
+        self._need_b200()
+        ok = True
+        for a in arrays:
+            ok &= self.lib.gpunb_b200_pin_host_(C.c_void_p(a.ctypes.data), C.byref(C.c_longlong(a.nbytes))) == 0
+        return ok
+
+    def unpin_host(self, *arrays):
+        self._need_b200()
+        for a in arrays:
+            self.lib.gpunb_b200_unpin_host_(C.c_void_p(a.ctypes.data))
 
     def set_resort_every(self, k: int):
         """Hilbert order refreshed every k-th snapshot only (1 = always, the default)."""

@@ -328,3 +328,39 @@ def test_packed_near_body_is_bitwise_the_scalar_body(b200):
     finally:
         b200.set_near_exact(-1)
         b200.close()
+
+
+def test_pinned_caller_arrays_match_staged_path(b200):
+    """gpunb_b200_pin_host_: with the caller's arrays pinned, gpunb_send_ uploads without the staging copy and the kernels
+    write acc / jrk / pot / list rows straight into the caller's arrays -- bit for bit the results of the staged path,
+    for single launches, sub-blocks and overflow rows."""
+    n = 9000
+    m, x, v = S.plummer(n, 23, "kroupa")
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 70.0))
+    h2[100:110] = 1e6                                  # overflow rows: -(count), no entries
+    b200.open(n + 10, 0)
+    staged = {}
+    pinned = []
+    try:
+        for mode in ("staged", "pinned"):
+            call = b200.block_caller(h2, dtr, x, v, 2048, 400, 350, 0)
+            if mode == "pinned":
+                pinned = [m, x, v, *call.outputs]
+                assert b200.pin_host(*pinned)
+            b200.send(m, x, v)
+            for nsub, i0, ni in ((1, 0, 1024), (-2, 50, 2048), (1, 7000, 33), (-4, 3000, 1500)):
+                b200.set_tuning(0, nsub)
+                for a in call.outputs:
+                    a[...] = 0
+                res = [a.copy() for a in call(i0, ni)]
+                if mode == "staged":
+                    staged[(nsub, i0, ni)] = res
+                else:
+                    for q in range(4):
+                        assert np.array_equal(res[q], staged[(nsub, i0, ni)][q]), (nsub, i0, ni, q)
+                    assert (res[3][:, 0] < 0).any() == (i0 < 110)
+    finally:
+        if pinned:
+            b200.unpin_host(*pinned)
+        b200.set_tuning(3, 4)
+        b200.close()
