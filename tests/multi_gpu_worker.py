@@ -12,6 +12,38 @@ os.environ.setdefault("OMP_NUM_THREADS", "8")
 import numpy as np  # noqa: E402
 
 
+def check_pinned(lib, tag, rank=0):
+    """Caller-pinned arrays (gpunb_b200_pin_host_) through the exchange step: combine_kernel writes the ABI layout straight
+    into the caller's arrays; bit for bit the staged path."""
+    from nbody6ppgpu_b200 import snapshots as S
+    n = 20011
+    m, x, v = S.plummer(n, 31, "kroupa")
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 150.0))
+    lib.open(n + 10, rank)
+    staged, pinned = {}, []
+    try:
+        for mode in ("staged", "pinned"):
+            call = lib.block_caller(h2, dtr, x, v, 2048, 400, 350, 0)
+            if mode == "pinned":
+                pinned = [m, x, v, *call.outputs]
+                assert lib.pin_host(*pinned)
+            lib.send(m, x, v)
+            for nsub, i0, ni in ((1, 0, 1024), (-2, 5000, 2048), (1, 300, 20)):
+                lib.set_tuning(0, nsub)
+                res = [a.copy() for a in call(i0, ni)]
+                if mode == "staged":
+                    staged[(nsub, i0, ni)] = res
+                else:
+                    for q in range(4):
+                        assert np.array_equal(res[q], staged[(nsub, i0, ni)][q]), (tag, nsub, i0, ni, q)
+    finally:
+        if pinned:
+            lib.unpin_host(*pinned)
+        lib.set_tuning(0, 4)
+        lib.close()
+    print(f"{tag} rank {rank}: pinned ok", flush=True)
+
+
 def check(lib, tag, rank=0):
     import oracle_lib
     from nbody6ppgpu_b200 import snapshots as S
@@ -58,7 +90,9 @@ def main():
         from nbody6ppgpu_b200 import load
         lib = load(); lib.devinit(0)
         assert lib.num_devices() == G
-        check(lib, f"inproc x{G}")
+        check_pinned(lib, f"inproc x{G}")
+        if not os.environ.get("WORKER_ONLY_PINNED"):
+            check(lib, f"inproc x{G}")
     elif mode == "nccl":
         import torch
         import torch.distributed as dist
@@ -70,7 +104,9 @@ def main():
         from nbody6ppgpu_b200.sharding import nccl_bootstrap
         lib = load(); lib.devinit(rank)
         nccl_bootstrap(lib, rank, world)
-        check(lib, f"nccl x{world}", rank)          # every rank checks: results are replicated
+        check_pinned(lib, f"nccl x{world}", rank)
+        if not os.environ.get("WORKER_ONLY_PINNED"):
+            check(lib, f"nccl x{world}", rank)      # every rank checks: results are replicated
         dist.barrier()
         lib.nccl_finalize()
         dist.destroy_process_group()
