@@ -1,0 +1,35 @@
+/*
+ * irr_b200.h -- C-ABI of libirr_b200.so: the reference's irregular-force interface (irr_simd_*).
+ *
+ * DRAFT: the library compiles for sm_100a and its fp64 statement is pinned against the reference's AVX library on the
+ * CPU, but it has not been validated on a GPU yet (tests gated behind IRR_B200_VALIDATE=1).  The regular-force library
+ * (gpunb_b200.h) does not depend on it.
+ *
+ * Fortran-callable like the reference (trailing underscore, scalars by reference, 1-based particle addresses).
+ */
+#ifndef IRR_B200_H
+#define IRR_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference: src/Main/irr.avx.cpp:365-402, :567-569.  nmax particles, lists of at most lmax entries. */
+void irr_simd_open_(int *nmax, int *lmax, int *rank);
+/* reference: irr.avx.cpp:421-435, :570-572 */
+void irr_simd_close_(int *rank);
+/* reference: irr.avx.cpp:404-419, :573-575 (stderr line, counters reset) */
+void irr_simd_profile_(int *rank);
+/* reference: irr.avx.cpp:437-447, :576-586.  X0, X0DOT, F/2, FDOT/6, BODY, T0 of particle addr. */
+void irr_simd_set_jp_(int *addr, double pos[3], double vel[3], double acc2[3], double jrk6[3], double *mass, double *time);
+/* reference: irr.avx.cpp:449-494, :587-592.  nblist = [nnb, j1, ..., j_nnb], 1-based addresses. */
+void irr_simd_set_list_(int *addr, int *nblist);
+/* reference: irr.avx.cpp:539-563, :593-602.  Force / derivative over each active particle's list at time ti (every
+ * involved particle predicted to ti) and the address of its nearest neighbour. */
+void irr_simd_firr_vec_(double *ti, int *ni, int addr[], double acc[][3], double jrk[][3], int nnbid[]);
+
+int irr_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
