@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--ni-total", type=int, default=0, help="i-particles swept per step (0 = all N)")
-    ap.add_argument("--cpu-blocks", type=int, default=64, help="i-blocks of 1024 in the CPU baseline sample")
+    ap.add_argument("--cpu-blocks", type=int, default=256, help="i-blocks of 1024 in the CPU baseline sample (~12 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--m-flag", type=int, default=0)
     ap.add_argument("--pageable", action="store_true", help="e2e leg with pageable caller arrays (default: the caller pins "
@@ -166,7 +166,7 @@ def run_reference(args, rank, world):
         return
     m, x, v, h2, dtr, rs0 = make_snapshot(args.n, args.m_flag)
     ref.open(args.n + 10, 0)
-    blocks = max(1, min(args.cpu_blocks // 4, 16))
+    blocks = max(1, min(args.cpu_blocks // 4, 64))
     for w in range(args.warmup):
         time_reference(ref, m, x, v, h2, dtr, 1, args.m_flag)
     t_tot, inter_tot = 0.0, 0
