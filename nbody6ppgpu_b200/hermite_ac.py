@@ -59,6 +59,8 @@ class AhmadCohen:
         # device_predictor: regular blocks call gpunb_b200_predict_send_ (state kept on the device, updated with the
         # particles advanced since the last regular block) instead of uploading the host-predicted snapshot
         self.device_predictor = bool(device_predictor)
+        if self.device_predictor and not getattr(lib, "is_b200", False):
+            raise ValueError("device_predictor needs libgpunb_b200.so (gpunb_b200_state_all_/_update_/_predict_send_)")
         self._dirty = None
         self.n = n = m.shape[0]
         self.m = np.ascontiguousarray(m, dtype=np.float64)
