@@ -89,6 +89,7 @@ enum {
     GPUNB_B200_CTR_SEND_MS,
     GPUNB_B200_CTR_SEND_STAGE_MS,
     GPUNB_B200_CTR_SEND_TILES_MS,
+    GPUNB_B200_CTR_TRANSPOSED_TILES, /* NEAR (warp, j-tile) visits handled by the transposed path (GPUNB_B200_STATS=1) */
     GPUNB_B200_CTR_COUNT
 };
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);

@@ -428,13 +428,18 @@ __device__ __forceinline__ void accumulate(Acc &A, float rinv, float m, float rv
 // neighbour criterion, so the body is the force alone: 27 FP32 ops + 1 MUFU per pair, two pairs per instruction.
 // Order of the accumulating FFMA2s: the triples share their first operand (reuse cache -> 2 distinct pairs).
 // far_force2: the part after the separation (dx, dy, dz) and r2 of two pairs are known.
+template <bool NEWTON>
 __device__ __forceinline__ void far_force2(const float2 dx, const float2 dy, const float2 dz, const float2 r2,
                                            const float2 nvx, const float2 nvy, const float2 nvz, Acc2 &A,
                                            float2 VX, float2 VY, float2 VZ, float2 M)
 {
     const float2 dvx = add2(VX, nvx), dvy = add2(VY, nvy), dvz = add2(VZ, nvz);
     const float2 rv = fma2(dz, dvz, fma2(dy, dvy, mul2(dx, dvx)));
-    const float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+    float2 rinv = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+    if (NEWTON) {        // precision option (variant suffix "n"): one Newton step, y <- y - y/2 (r2 y^2 - 1), 4 packed ops
+        const float2 e = fma2(mul2(r2, rinv), rinv, dup2(-1.f));
+        rinv = fma2(mul2(rinv, e), dup2(-0.5f), rinv);
+    }
     const float2 rinv2  = mul2(rinv, rinv);
     const float2 mrinv  = mul2(M, rinv);
     const float2 mrinv3 = mul2(mrinv, rinv2);
@@ -444,13 +449,14 @@ __device__ __forceinline__ void far_force2(const float2 dx, const float2 dy, con
     A.ax = fma2(mrinv3, dx, A.ax);   A.ay = fma2(mrinv3, dy, A.ay);   A.az = fma2(mrinv3, dz, A.az);
     A.jx = fma2(mrinv3, ix, A.jx);   A.jy = fma2(mrinv3, iy, A.jy);   A.jz = fma2(mrinv3, iz, A.jz);
 }
+template <bool NEWTON>
 __device__ __forceinline__ void interact_far2(const float2 cx, const float2 cy, const float2 cz,
                                               const float2 nvx, const float2 nvy, const float2 nvz, Acc2 &A,
                                               float2 DX, float2 DY, float2 DZ, float2 VX, float2 VY, float2 VZ, float2 M)
 {
     const float2 dx = add2(DX, cx), dy = add2(DY, cy), dz = add2(DZ, cz);
     const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-    far_force2(dx, dy, dz, r2, nvx, nvy, nvz, A, VX, VY, VZ, M);
+    far_force2<NEWTON>(dx, dy, dz, r2, nvx, nvy, nvz, A, VX, VY, VZ, M);
 }
 
 // NEAR tile: full body.
@@ -528,10 +534,20 @@ __device__ __forceinline__ unsigned interact_near2(const IState &I, Acc2 &A, flo
     return (nb0 ? 1u : 0u) | (nb1 ? 2u : 0u);
 }
 
-template <int IT, bool MFLAG, int MINB>
+// OPT bit 0 (variant suffix "n"): Newton step in the FAR body (jerk-precision option, +4 packed ops per two pairs).
+// OPT bit 1 (variant suffix "t", IT = 1): NEAR tiles in which only a few lanes fail the FAR test are TRANSPOSED -- every
+//   lane runs the cheap FAR body, the failing lanes throw their tile sums away and get them back from the whole warp:
+//   their i-state is broadcast by shuffles, the 32 lanes take two j of the tile each through the exact NEAR body, the
+//   seven sums are reduced by a butterfly and neighbour hits are appended by the hitting lanes.  When the i-particles of a
+//   warp are far apart (the rule for an i-block picked by time step, not by position) a NEAR tile holds neighbours of one or
+//   two lanes only, and the other ~30 lanes no longer pay the exact body for nothing.
+template <int IT, bool MFLAG, int MINB, int OPT>
 __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a)
 {
     constexpr int ITILE = 32 * IT;
+    constexpr bool NEWTON = (OPT & 1) != 0;
+    constexpr bool TRANSPOSE = (OPT & 2) != 0 && IT == 1;
+    constexpr int  TRANSPOSE_MAX = 8;                 // more failing lanes than this: the whole warp runs the NEAR body
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * WARPS + warp;
@@ -606,7 +622,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         }
     };
 
-    unsigned n_near = 0, n_all = 0;
+    unsigned n_near = 0, n_all = 0, n_tr = 0;
     int n = 0;
     for (int t = s; t < a.ntiles; t += a.S, n++) {
         const int st = n % NSTAGE;
@@ -656,7 +672,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 lane_far &= (f || iidx[k] < 0);
             }
         }
-        const bool far = __all_sync(0xffffffffu, lane_far) && !a.force_near;
+        const unsigned nearmask = __ballot_sync(0xffffffffu, !lane_far);
+        const bool transposed = TRANSPOSE && nearmask != 0u && __popc(nearmask) <= TRANSPOSE_MAX && !a.force_near;
+        const bool far = (nearmask == 0u && !a.force_near) || transposed;
         n_all++;
         const float4 *c = reinterpret_cast<const float4 *>(tb + HDR);
         float2 cx2[IT], cy2[IT], cz2[IT], nvx2[IT], nvy2[IT], nvz2[IT];
@@ -673,12 +691,64 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
                 const float4 M  = c[C_M * 16 + q];
 #pragma unroll
                 for (int k = 0; k < IT; k++) {
-                    interact_far2(cx2[k], cy2[k], cz2[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(DX.x, DX.y),
+                    interact_far2<NEWTON>(cx2[k], cy2[k], cz2[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(DX.x, DX.y),
                                   make_float2(DY.x, DY.y), make_float2(DZ.x, DZ.y), make_float2(VX.x, VX.y),
                                   make_float2(VY.x, VY.y), make_float2(VZ.x, VZ.y), make_float2(M.x, M.y));
-                    interact_far2(cx2[k], cy2[k], cz2[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(DX.z, DX.w),
+                    interact_far2<NEWTON>(cx2[k], cy2[k], cz2[k], nvx2[k], nvy2[k], nvz2[k], P[k], make_float2(DX.z, DX.w),
                                   make_float2(DY.z, DY.w), make_float2(DZ.z, DZ.w), make_float2(VX.z, VX.w),
                                   make_float2(VY.z, VY.w), make_float2(VZ.z, VZ.w), make_float2(M.z, M.w));
+                }
+            }
+            if (TRANSPOSE && transposed) {
+                // The failing lanes' FAR sums of this tile are void (neighbours inside, or the tile too close for the
+                // tile-local separations): cleared here, recomputed exactly by the whole warp below.
+                n_near++; n_tr++;
+                if (!lane_far) P[0].clear();
+                const float2 *c2 = reinterpret_cast<const float2 *>(tb + HDR);      // this lane's two j: 2 lane, 2 lane + 1
+                const float2 jVX = c2[C_VX * 32 + lane], jVY = c2[C_VY * 32 + lane], jVZ = c2[C_VZ * 32 + lane], jM = c2[C_M * 32 + lane];
+                const float2 jXH = c2[C_XH * 32 + lane], jYH = c2[C_YH * 32 + lane], jZH = c2[C_ZH * 32 + lane];
+                const float2 jXL = c2[C_XL * 32 + lane], jYL = c2[C_YL * 32 + lane], jZL = c2[C_ZL * 32 + lane];
+                for (unsigned rest = nearmask; rest; rest &= rest - 1u) {
+                    const int L = __ffs(rest) - 1;
+                    IState B;                          // i-state of lane L (only the fields the NEAR body reads)
+                    B.nxh = __shfl_sync(0xffffffffu, I[0].nxh, L); B.nyh = __shfl_sync(0xffffffffu, I[0].nyh, L);
+                    B.nzh = __shfl_sync(0xffffffffu, I[0].nzh, L); B.nxl = __shfl_sync(0xffffffffu, I[0].nxl, L);
+                    B.nyl = __shfl_sync(0xffffffffu, I[0].nyl, L); B.nzl = __shfl_sync(0xffffffffu, I[0].nzl, L);
+                    B.nvx = __shfl_sync(0xffffffffu, I[0].nvx, L); B.nvy = __shfl_sync(0xffffffffu, I[0].nvy, L);
+                    B.nvz = __shfl_sync(0xffffffffu, I[0].nvz, L); B.dtr = __shfl_sync(0xffffffffu, I[0].dtr, L);
+                    B.h2  = __shfl_sync(0xffffffffu, I[0].h2, L);
+                    Acc2 Q; Q.clear();
+                    const unsigned hit = interact_near2<MFLAG>(B, Q, jVX, jVY, jVZ, jM, jXH, jYH, jZH, jXL, jYL, jZL);
+                    // neighbour hits: appended by the hitting lanes at positions handed out by ballots (ghost slots of the
+                    // last tile are never neighbours); lane L keeps the count
+                    bool v0 = false, v1 = false;
+                    int jg0 = -1, jg1 = -1;
+                    if (hit) {
+                        const int2 jg = reinterpret_cast<const int2 *>(a.jidx + (size_t)t * TJ)[lane];
+                        jg0 = jg.x; jg1 = jg.y;
+                        v0 = (hit & 1u) && jg0 >= 0; v1 = (hit & 2u) && jg1 >= 0;
+                    }
+                    const unsigned b0 = __ballot_sync(0xffffffffu, v0), b1 = __ballot_sync(0xffffffffu, v1);
+                    if (b0 | b1) {
+                        const int cntL = __shfl_sync(0xffffffffu, cnt[0], L);
+                        const unsigned lt = (1u << lane) - 1u;
+                        int pos = cntL + __popc(b0 & lt) + __popc(b1 & lt);
+                        int *sp = a.seg + ((size_t)(it * ITILE + L) * a.S + s) * a.segcap;
+                        if (v0) { if (pos < a.segcap) sp[pos] = jg0; pos++; }
+                        if (v1) { if (pos < a.segcap) sp[pos] = jg1; }
+                        if (lane == L) cnt[0] = cntL + __popc(b0) + __popc(b1);
+                    }
+                    float r[7] = {Q.ax.x + Q.ax.y, Q.ay.x + Q.ay.y, Q.az.x + Q.az.y, Q.p.x + Q.p.y,
+                                  Q.jx.x + Q.jx.y, Q.jy.x + Q.jy.y, Q.jz.x + Q.jz.y};
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int q = 0; q < 7; q++) r[q] += __shfl_xor_sync(0xffffffffu, r[q], o);
+                    }
+                    if (lane == L) {
+                        P[0].ax.x = r[0]; P[0].ay.x = r[1]; P[0].az.x = r[2]; P[0].p.x = r[3];
+                        P[0].jx.x = r[4]; P[0].jy.x = r[5]; P[0].jz.x = r[6];
+                    }
                 }
             }
         } else {
@@ -759,7 +829,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             a.cnt[(size_t)s * a.nloc + kl] = cnt[k];
         }
     }
-    if (a.stats && lane == 0) { atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all); }
+    if (a.stats && lane == 0) { atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all); atomicAdd(&a.stats[2], (unsigned long long)n_tr); }
     if (a.wtime && lane == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); a.wtime[3 * w + 1] = t1; a.wtime[3 * w + 2] = n_near; }
 }
 
@@ -888,9 +958,27 @@ __device__ __forceinline__ void publish_when_last(const ExchSignal &g)
         st_release_sys(g.peer[threadIdx.x], g.seq);
     }
 }
+// Bounded: a peer that died or fell out of step (different calls on different ranks) must not wedge the other ranks inside
+// a kernel for ever.  After g_spin_timeout_ns (default 60 s, GPUNB_B200_SPIN_TIMEOUT_S) the waiting kernel reports which
+// rank's flag is stuck and traps; the host side then aborts with the CUDA error like for any other device fault.
+__device__ unsigned long long g_spin_timeout_ns = 60000000000ull;
 __device__ __forceinline__ void wait_all_ranks(const unsigned long long *flags, int R, long long need, int lane)
 {   // every warp for itself: lanes < R spin on the R entries of a flag array in LOCAL memory (written by the peers)
-    if (lane < R) while ((long long)ld_acquire_sys(flags + lane) < need) { }
+    if (lane < R) {
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        while ((long long)ld_acquire_sys(flags + lane) < need) {
+            if ((++spins & 0xfffu) == 0u) {
+                unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > g_spin_timeout_ns) {
+                    printf("gpunb_b200: exchange step %lld: the flag of rank %d is stuck at %lld -- a peer rank died or the ranks "
+                           "do not make identical calls\n", need, lane, (long long)ld_acquire_sys(flags + lane));
+                    __trap();
+                }
+            }
+        }
+    }
     __syncwarp();
 }
 
@@ -1254,12 +1342,15 @@ double wtime() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec
 typedef void (*RegfKernel)(const RegfArgs);
 struct Variant { const char *name; int it; RegfKernel k[2]; };
 const Variant VARIANTS[] = {
-    {"it2",   2, {regf_kernel<2, false, 1>, regf_kernel<2, true, 1>}},
-    {"it2b3", 2, {regf_kernel<2, false, 3>, regf_kernel<2, true, 3>}},
-    {"it1",   1, {regf_kernel<1, false, 1>, regf_kernel<1, true, 1>}},
-    {"it1b5", 1, {regf_kernel<1, false, 5>, regf_kernel<1, true, 5>}},
-    {"it1b4", 1, {regf_kernel<1, false, 4>, regf_kernel<1, true, 4>}},
-    {"it1b3", 1, {regf_kernel<1, false, 3>, regf_kernel<1, true, 3>}},
+    {"it2",    2, {regf_kernel<2, false, 1, 0>, regf_kernel<2, true, 1, 0>}},
+    {"it2b3",  2, {regf_kernel<2, false, 3, 0>, regf_kernel<2, true, 3, 0>}},
+    {"it1",    1, {regf_kernel<1, false, 1, 0>, regf_kernel<1, true, 1, 0>}},
+    {"it1b5",  1, {regf_kernel<1, false, 5, 0>, regf_kernel<1, true, 5, 0>}},
+    {"it1b4",  1, {regf_kernel<1, false, 4, 0>, regf_kernel<1, true, 4, 0>}},
+    {"it1b3",  1, {regf_kernel<1, false, 3, 0>, regf_kernel<1, true, 3, 0>}},
+    {"it1b4n", 1, {regf_kernel<1, false, 4, 1>, regf_kernel<1, true, 4, 1>}},      // + Newton step in the FAR body
+    {"it1b4t", 1, {regf_kernel<1, false, 4, 2>, regf_kernel<1, true, 4, 2>}},      // + transposed NEAR lanes
+    {"it1b4nt", 1, {regf_kernel<1, false, 4, 3>, regf_kernel<1, true, 4, 3>}},
 };
 constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
 constexpr int DEFAULT_VARIANT = 4;     // it1b4: 4 CTAs/SM (<= 128 registers), fastest at every ni (profiles/r01e_variants.txt)
@@ -2163,7 +2254,9 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     // A sub-block must keep the pair kernel busy for >~150 us, or its fixed costs (launch, merge, exchange step) show.
     int nsub = (G == 1) ? L.nsub : 1;
     if (nsub > ni / 256) nsub = ni / 256;
-    const double pairs = (double)ni * root.nj;
+    // decided from rank-invariant quantities only: every rank of a sharded run must cut the call into the same
+    // sub-blocks (each is one exchange step), and shard sizes differ by a tile between ranks
+    const double pairs = (double)ni * L.nbody / total_ranks();
     if (!L.nsub_forced && nsub > (int)(pairs / 1.5e8)) nsub = (int)(pairs / 1.5e8);
     if (nsub < 1) nsub = 1;
     IBlock ib[MAX_RANKS];
@@ -2257,6 +2350,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         }
         for (int q = 0; q < nq; q++) CUDA_CHECK(cudaStreamWaitEvent(root.st, root.slots[q].ev_done, 0));
         CUDA_CHECK(cudaEventSynchronize(root.ev3));
+        CUDA_CHECK(cudaEventSynchronize(root.ev1));      // recorded on a lo stream: not implied by ev3 / ev_done
     }
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, root.ev0, root.ev1)); L.ctr[GPUNB_B200_CTR_GRAV_MS] += ms;
@@ -2437,6 +2531,7 @@ void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT])
         CUDA_CHECK(cudaStreamSynchronize(d.st));
         L.ctr[GPUNB_B200_CTR_NEAR_TILES] = (double)h[0];
         L.ctr[GPUNB_B200_CTR_ALL_TILES] = (double)h[1];
+        L.ctr[GPUNB_B200_CTR_TRANSPOSED_TILES] = (double)h[2];
 
     }
     for (int k = 0; k < GPUNB_B200_CTR_COUNT; k++) out[k] = L.ctr[k];
@@ -2648,7 +2743,7 @@ int gpunb_b200_nccl_unique_id(unsigned char id128[128])
 
 // Join `nranks` processes (one GPU each) into one j-sharded force library.  Call after gpunb_devinit_
 // and before gpunb_open_.  Every rank then makes IDENTICAL calls (same snapshot, same i-blocks) and every
-// rank receives the complete result; rank r sums over j in [r*nj/R, (r+1)*nj/R).
+// rank receives the complete result; rank r sums over the tiles r, r+R, r+2R, ... of the Hilbert-sorted j-set (shard_tiles).
 int gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128])
 {
     if (!L.devinit) FATAL("gpunb_b200_nccl_init before gpunb_devinit_");
@@ -2663,6 +2758,8 @@ int gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128])
     int rc = sh.init(&sh.comm, nranks, id, rank);
     if (rc != 0) FATAL("ncclCommInitRank failed: %s", sh.errstr ? sh.errstr(rc) : "?");
     sh.rank = rank; sh.R = nranks; sh.seq = 0;
+    { const char *e = getenv("GPUNB_B200_SPIN_TIMEOUT_S");
+      if (e && atof(e) > 0) { const unsigned long long ns = (unsigned long long)(atof(e) * 1e9); CUDA_CHECK(cudaMemcpyToSymbol(g_spin_timeout_ns, &ns, sizeof(ns))); } }
     for (Slot &sl : d.slots) if (sl.done_ctr) CUDA_CHECK(cudaMemsetAsync(sl.done_ctr, 0, 2 * sizeof(unsigned), d.st));
     CUDA_CHECK(cudaMalloc((void **)&sh.xbuf, XB_BYTES));
     CUDA_CHECK(cudaMemsetAsync(sh.xbuf, 0, XB_BYTES, d.st));

@@ -23,12 +23,12 @@ _HERE = Path(__file__).resolve().parent
 _c_int_p = C.POINTER(C.c_int)
 _c_dbl_p = C.POINTER(C.c_double)
 
-N_COUNTERS = 23
+N_COUNTERS = 24
 CTR = dict(grav_ms=0, grav_launches=1, launches=2, h2d_bytes=3, d2h_bytes=4, interactions=5,
            merge_ms=6, pot_ms=7, near_tiles=8, all_tiles=9,
            tl_blocks=10, tl_isort_ms=11, tl_regf_ms=12, tl_merge_ms=13, tl_exch_ms=14,
            host_pack_ms=15, host_enqueue_ms=16, host_wait_ms=17, host_scatter_ms=18,
-           sends=19, send_ms=20, send_stage_ms=21, send_tiles_ms=22)
+           sends=19, send_ms=20, send_stage_ms=21, send_tiles_ms=22, transposed_tiles=23)
 
 
 class LibraryMissing(RuntimeError):

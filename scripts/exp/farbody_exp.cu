@@ -265,11 +265,153 @@ template <int SHAPE, int UNROLL> void run_farp(const char *name, int nsm, int ct
     cudaFree(out);
 }
 
-int main()
+
+// ---- round 2: packed shapes that avoid FFMA2s with three DISTINCT register-pair operands (4.5-4.8 cycles instead of 2) ----
+// SHAPE bits (packed variants, farq_kernel):
+//   1  rv chain as FMUL2 + FADD2 (no 3-operand FFMA2 in the dot product)
+//   2  rv chain as scalar FFMAs (4 scalar instead of 2 packed)
+//   4  jerk as two sums  JA += mrinv3*dv,  JB += (mrinv3*rv*rinv2)*dx  (J = JA - 3 JB at the flush): the six
+//      accumulating FFMA2s of acc and JA share mrinv3 in the first operand slot
+//   8  one Newton step on rsqrt.approx (4 packed ops): cost of the jerk-precision option
+//  16  Newton folded into the products (e = 1 - r2 y^2; mrinv3 *= 1 + 1.5 e; rinv2 *= 1 + e): 4 ops, shorter chain
+//  32  ix/iy/iz as FMUL2 + FADD2
+struct QAcc { float2 ax, ay, az, p, jx, jy, jz, bx, by, bz; };
+template <int SHAPE>
+__device__ __forceinline__ void far_q(QAcc &A, float2 cx, float2 cy, float2 cz, float2 nvx, float2 nvy, float2 nvz,
+                                      float2 DX, float2 DY, float2 DZ, float2 VX, float2 VY, float2 VZ, float2 M)
+{
+    const float2 dx = __fadd2_rn(DX, cx), dy = __fadd2_rn(DY, cy), dz = __fadd2_rn(DZ, cz);
+    const float2 dvx = __fadd2_rn(VX, nvx), dvy = __fadd2_rn(VY, nvy), dvz = __fadd2_rn(VZ, nvz);
+    const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+    float2 rv;
+    if (SHAPE & 1) {
+        rv = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dvx), __fmul2_rn(dy, dvy)), __fmul2_rn(dz, dvz));
+    } else if (SHAPE & 2) {
+        rv = __fmul2_rn(dx, dvx);
+        rv.x = fmaf(dy.x, dvy.x, rv.x); rv.y = fmaf(dy.y, dvy.y, rv.y);
+        rv.x = fmaf(dz.x, dvz.x, rv.x); rv.y = fmaf(dz.y, dvz.y, rv.y);
+    } else {
+        rv = __ffma2_rn(dz, dvz, __ffma2_rn(dy, dvy, __fmul2_rn(dx, dvx)));
+    }
+    float2 rinv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.x) : "f"(r2.x));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.y) : "f"(r2.y));
+    if (SHAPE & 8) {
+        const float2 e = __ffma2_rn(__fmul2_rn(r2, rinv), rinv, make_float2(-1.f, -1.f));
+        rinv = __ffma2_rn(__fmul2_rn(rinv, e), make_float2(-0.5f, -0.5f), rinv);
+    }
+    float2 rinv2 = __fmul2_rn(rinv, rinv);
+    const float2 mrinv = __fmul2_rn(M, rinv);
+    float2 mrinv3;
+    if (SHAPE & 16) {
+        const float2 e = __ffma2_rn(r2, __fmul2_rn(rinv2, make_float2(-1.f, -1.f)), make_float2(1.f, 1.f));   // 1 - r2 y^2
+        const float2 g = __ffma2_rn(e, make_float2(1.5f, 1.5f), make_float2(1.f, 1.f));
+        mrinv3 = __fmul2_rn(mrinv, __fmul2_rn(rinv2, g));
+        rinv2 = __ffma2_rn(rinv2, e, rinv2);
+    } else {
+        mrinv3 = __fmul2_rn(mrinv, rinv2);
+    }
+    A.p = __fadd2_rn(A.p, mrinv);
+    if (SHAPE & 4) {
+        const float2 w = __fmul2_rn(mrinv3, __fmul2_rn(rv, rinv2));
+        A.ax = __ffma2_rn(mrinv3, dx, A.ax); A.ay = __ffma2_rn(mrinv3, dy, A.ay); A.az = __ffma2_rn(mrinv3, dz, A.az);
+        A.jx = __ffma2_rn(mrinv3, dvx, A.jx); A.jy = __ffma2_rn(mrinv3, dvy, A.jy); A.jz = __ffma2_rn(mrinv3, dvz, A.jz);
+        A.bx = __ffma2_rn(w, dx, A.bx); A.by = __ffma2_rn(w, dy, A.by); A.bz = __ffma2_rn(w, dz, A.bz);
+    } else {
+        const float2 rv3 = __fmul2_rn(rv, __fmul2_rn(rinv2, make_float2(-3.f, -3.f)));
+        A.ax = __ffma2_rn(mrinv3, dx, A.ax); A.ay = __ffma2_rn(mrinv3, dy, A.ay); A.az = __ffma2_rn(mrinv3, dz, A.az);
+        float2 ix, iy, iz;
+        if (SHAPE & 32) {
+            ix = __fadd2_rn(__fmul2_rn(rv3, dx), dvx); iy = __fadd2_rn(__fmul2_rn(rv3, dy), dvy); iz = __fadd2_rn(__fmul2_rn(rv3, dz), dvz);
+        } else {
+            ix = __ffma2_rn(rv3, dx, dvx); iy = __ffma2_rn(rv3, dy, dvy); iz = __ffma2_rn(rv3, dz, dvz);
+        }
+        A.jx = __ffma2_rn(mrinv3, ix, A.jx); A.jy = __ffma2_rn(mrinv3, iy, A.jy); A.jz = __ffma2_rn(mrinv3, iz, A.jz);
+    }
+}
+
+template <int SHAPE, int UNROLL>
+__global__ void __launch_bounds__(128) farq_kernel(int ntile_iters, float seed, float *out)
+{
+    __shared__ __align__(16) float tile[4][7 * 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *tb = tile[warp];
+    for (int k = lane; k < 7 * 64; k += 32) tb[k] = seed * (1.f + 0.001f * k) + 0.01f * warp;
+    __syncwarp();
+    QAcc P[2];
+    for (int h = 0; h < 2; h++) P[h] = QAcc{{0,0},{0,0},{0,0},{0,0},{0,0},{0,0},{0,0},{0,0},{0,0},{0,0}};
+    float cxs = seed + lane, cys = seed - lane, czs = 0.5f * seed;
+    const float2 nvx = make_float2(0.1f * lane, 0.1f * lane), nvy = make_float2(-0.2f * lane, -0.2f * lane), nvz = make_float2(0.3f, 0.3f);
+    const float4 *c = reinterpret_cast<const float4 *>(tb);
+    double D[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < ntile_iters; t++) {
+        const float2 cx = make_float2(cxs, cxs), cy = make_float2(cys, cys), cz = make_float2(czs, czs);
+#pragma unroll UNROLL
+        for (int q = 0; q < 16; q++) {
+            const float4 DX = c[q], DY = c[16 + q], DZ = c[32 + q], VX = c[48 + q], VY = c[64 + q], VZ = c[80 + q], M = c[96 + q];
+            far_q<SHAPE>(P[0], cx, cy, cz, nvx, nvy, nvz, LO(DX), LO(DY), LO(DZ), LO(VX), LO(VY), LO(VZ), LO(M));
+            far_q<SHAPE>(P[1], cx, cy, cz, nvx, nvy, nvz, HI(DX), HI(DY), HI(DZ), HI(VX), HI(VY), HI(VZ), HI(M));
+        }
+        cxs += 1e-3f;
+    }
+    float s = 0.f;
+    for (int h = 0; h < 2; h++) {
+        s += P[h].ax.x + P[h].ay.x + P[h].az.x + P[h].p.x + P[h].jx.x + P[h].jy.x + P[h].jz.x + P[h].bx.x + P[h].by.x + P[h].bz.x;
+        s += P[h].ax.y + P[h].ay.y + P[h].az.y + P[h].p.y + P[h].jx.y + P[h].jy.y + P[h].jz.y + P[h].bx.y + P[h].by.y + P[h].bz.y;
+    }
+    if (s == 12345.678f) out[0] = s + (float)D[0];
+}
+
+template <int SHAPE, int UNROLL> void run_farq(const char *name, int nsm, int ctas)
+{
+    float *out; CK(cudaMalloc(&out, 4));
+    const int iters = 2000, blocks = nsm * ctas;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 4; r++) {
+        cudaEventRecord(e0);
+        farq_kernel<SHAPE, UNROLL><<<blocks, 128>>>(iters, 1.0001f, out);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    const double pairs = (double)blocks * 128 * iters * 64;
+    printf("farq shape %2d unroll %d  %-52s %d CTAs/SM: %7.1f Gint/s\n", SHAPE, UNROLL, name, ctas, pairs / (best * 1e-3) * 1e-9);
+    cudaFree(out);
+}
+
+int main(int argc, char **argv)
 {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     const int nsm = prop.multiProcessorCount;
     printf("%s, %d SMs\n", prop.name, nsm);
+
+    if (argc > 1) {          // round 2: packed shapes only
+        for (int ctas = 3; ctas <= 4; ctas++) {
+            run_farq<0, 2>("reference packed body (27 ops)", nsm, ctas);
+            run_farq<0, 4>("reference packed body (27 ops)", nsm, ctas);
+            run_farq<1, 2>("rv = FMUL2+FADD2", nsm, ctas);
+            run_farq<1, 4>("rv = FMUL2+FADD2", nsm, ctas);
+            run_farq<2, 2>("rv = scalar FFMA", nsm, ctas);
+            run_farq<2, 4>("rv = scalar FFMA", nsm, ctas);
+            run_farq<4, 2>("split jerk sums", nsm, ctas);
+            run_farq<4, 4>("split jerk sums", nsm, ctas);
+            run_farq<5, 2>("split jerk sums + rv FMUL2/FADD2", nsm, ctas);
+            run_farq<5, 4>("split jerk sums + rv FMUL2/FADD2", nsm, ctas);
+            run_farq<6, 2>("split jerk sums + rv scalar", nsm, ctas);
+            run_farq<6, 4>("split jerk sums + rv scalar", nsm, ctas);
+            run_farq<33, 2>("rv and ix as FMUL2+FADD2 (no 3-operand but accum)", nsm, ctas);
+            run_farq<33, 4>("rv and ix as FMUL2+FADD2 (no 3-operand but accum)", nsm, ctas);
+            run_farq<8, 2>("Newton step (4 ops)", nsm, ctas);
+            run_farq<8, 4>("Newton step (4 ops)", nsm, ctas);
+            run_farq<16, 2>("Newton folded into products (4 ops)", nsm, ctas);
+            run_farq<16, 4>("Newton folded into products (4 ops)", nsm, ctas);
+            run_farq<13, 4>("split jerk + rv FMUL2/FADD2 + Newton", nsm, ctas);
+            run_farq<21, 4>("split jerk + rv FMUL2/FADD2 + folded Newton", nsm, ctas);
+        }
+        return 0;
+    }
     run_mix<0>("FFMA", nsm); run_mix<1>("FMUL", nsm); run_mix<2>("FADD", nsm);
     run_mix<3>("FMUL,FFMA alternating", nsm); run_mix<4>("FADD,FFMA alternating", nsm); run_mix<5>("FADD,FMUL alternating", nsm);
     run_mix<6>("FMUL,FFMA,FFMA", nsm); run_mix<7>("FADD,FMUL,FFMA,FFMA", nsm); run_mix<8>("FMUL imm,FFMA alternating", nsm);
