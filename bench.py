@@ -11,9 +11,17 @@ all N -> 977 calls, 1e12 interactions).  interactions = sum ni*nj exactly as the
   value   device-resident leg: the j snapshot, radii and i-blocks already in HBM; the blocks cycle through the
           library's pipeline slots (pair kernel of block b+1 beside merge/exchange of block b), timed with CUDA
           events on the library's main stream around the whole sweep (gpunb_b200_sweep_resident).
-  e2e     the same sweep through the reference-facing C-ABI (gpunb_send_ + gpunb_regf_) with HOST
-          (pageable numpy) buffers: H2D of the snapshot and of every i-block, D2H of forces and
-          neighbour lists inside the timed region.
+  e2e     the same sweep through the reference-facing C-ABI (gpunb_send_ + gpunb_regf_) with HOST buffers:
+          H2D of the snapshot and of every i-block, D2H of forces and neighbour lists inside the timed
+          region.  Default: caller-owned arrays pinned ONCE with gpunb_b200_pin_host_ (what a Fortran
+          caller does for its COMMON blocks); the same leg with plain pageable arrays is reported beside
+          it (`e2e.pageable`).  Under torchrun the ranks use the library's i-slice mode (the calling
+          pattern of NBODY6++'s MPI build, intgrt.F:982-1231): every rank passes its own blocks of 1024
+          and receives its own rows.
+  parity_check  one block of 1024 i-particles through gpunb_regf_ against the oracle (oracle/, the checker)
+          BEFORE the timed region: lists exact outside the 4-ulp band, acc / pot <= 1e-6, strict and scaled
+          jerk error reported; at world > 1 also bitwise equality of the replicated results across ranks and
+          the i-slice mode against the oracle.  A failure exits non-zero.
   roofline  FP32-FMA bound (no tensor cores: pairwise sum, not a contraction).  achieved = 60 flop x
           interactions of one launch / mean launch duration of regf_kernel (CUDA events around each
           launch, on its stream); peak = 2*128*148*sm_max_mhz nominal AND the FFMA rate measured by the
@@ -61,8 +69,10 @@ def parse():
     ap.add_argument("--cpu-blocks", type=int, default=256, help="i-blocks of 1024 in the CPU baseline sample (~12 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--m-flag", type=int, default=0)
-    ap.add_argument("--pageable", action="store_true", help="e2e leg with pageable caller arrays (default: the caller pins "
-                    "its static arrays once with gpunb_b200_pin_host_)")
+    ap.add_argument("--pageable", action="store_true", help="headline e2e leg with pageable caller arrays (default: the caller pins "
+                    "its static arrays once with gpunb_b200_pin_host_; the other kind is reported beside it)")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary legs (pageable e2e, other configs, reference CUDA library)")
+    ap.add_argument("--ref-cuda-probe", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -73,6 +83,16 @@ def make_snapshot(n, m_flag):
     # neighbour spheres with <nnb> ~ NNBOPT = 200 everywhere (the state the RS control converges to)
     h2, dtr = S.radii_nnb(x, m, NNB_TARGET, 0.125, m_flag)
     return m, x, v, h2, dtr, float(np.sqrt(h2.min() * (m.mean() if m_flag else 1.0)))
+
+
+def bench_config(n, m_flag, rs0, world):
+    """The workload, identical for both arms (`--impl b200` and `--impl reference`): what is computed, not how much of it a
+    step samples (that is the top-level `sample` / `run`)."""
+    return {"workload": f"synthetic Plummer N={n} Kroupa IMF, regular-force sweep", "nj": n, "block": BLOCK, "lmax": LMAX,
+            "nnbmax": NNBMAX, "m_flag": m_flag, "rs_min": rs0, "nnb_target": NNB_TARGET,
+            "radii": "RS_i from the local Plummer density for <nnb> ~ 200 (snapshots.radii_nnb), dtr as fpoly0.F:53-56",
+            "l2": "flushed between timed steps (256 MB fill) on the GPU arm; the j-set (56 MB fp64) exceeds the host caches on the CPU arm",
+            "parallelism": f"j-shard x{world}"}
 
 
 class ClockSampler:
@@ -180,8 +200,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_tot / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic Plummer N={args.n} Kroupa IMF, regular-force sweep", "nj": args.n, "block": BLOCK,
-                   "lmax": LMAX, "nnbmax": NNBMAX, "m_flag": args.m_flag, "rs_min": rs0, "sample": sample},
+        "config": bench_config(args.n, args.m_flag, rs0, args.gpus), "sample": sample,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -220,6 +239,134 @@ def emit(obj):
         os.write(_JSON_FD, line)
 
 
+def sweep_block(lib, world):
+    """i-particles per launch group of the resident sweep: 1024 on one GPU.  With the j-set sharded over R ranks the block
+    grows with R, so that one launch keeps about the same number of pairs and its fixed costs stay amortised:
+    32 * (W / S) with W the resident warps and S the largest integer <= W / (32 R) that divides W (2048 / 4736 / 9472
+    at R = 2 / 4 / 8 on a B200) -- every resident warp gets a work item."""
+    if world == 1:
+        return BLOCK
+    W = lib.resident_warps()
+    S = max(1, W // (32 * world))
+    while S > 1 and W % S:
+        S -= 1
+    return min(32 * (W // S), 16384)
+
+
+def valid_rows_bytes(lst):
+    import numpy as np
+    return b"".join(lst[i, :max(int(lst[i, 0]), 0) + 1].tobytes() for i in range(lst.shape[0]))
+
+
+def parity_check(lib, dist, rank, world, m, x, v, h2, dtr, m_flag):
+    """One block of 1024 i-particles through gpunb_regf_ BEFORE the timed region, against the oracle (the checker under
+    oracle/, on rank 0): lists exact outside the 4-ulp band of the RS boundary, acc / pot <= 1e-6, jerk reported strictly
+    and under the cancellation-aware norm of tests/test_regf_gpu.py.  world > 1: the replicated results must be bitwise
+    equal on every rank, and the i-slice mode (rank r passes rows [r ni / R, (r+1) ni / R) of the same block) must give
+    the same lists and forces within the same bars."""
+    import hashlib
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib
+    i0, ni = 4096, BLOCK
+    sel = slice(i0, i0 + ni)
+    lib.set_tuning(0, NSUB)
+    rep = [a.copy() for a in lib.regf(h2[sel], dtr[sel], x[sel], v[sel], LMAX, NNBMAX, m_flag)]
+    out = {"block_i0": i0, "ni": ni, "tolerance": 1e-6, "band_ulp": 4.0}
+    gathered = None
+    if world > 1:
+        import torch
+        dig = hashlib.sha256(rep[0].tobytes() + rep[1].tobytes() + rep[2].tobytes() + valid_rows_bytes(rep[3])).digest()
+        t = torch.tensor(list(dig[:16]), dtype=torch.int64, device="cuda")
+        alld = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(alld, t)
+        out["replicated_bitwise_equal_across_ranks"] = bool(all(torch.equal(alld[0], q) for q in alld))
+        lo, hi = i0 + rank * ni // world, i0 + (rank + 1) * ni // world
+        lib.set_islice(1)
+        mine = [a.copy() for a in lib.regf(h2[lo:hi], dtr[lo:hi], x[lo:hi], v[lo:hi], LMAX, NNBMAX, m_flag)]
+        lib.set_islice(0)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+    ok = True
+    if rank == 0:
+        o = oracle_lib.Oracle()
+        a64, j64, p64, l64, band, nband = o.regf_f64(m, x, v, h2[sel], dtr[sel], x[sel], v[sel], LMAX, NNBMAX, m_flag, 4.0)
+        scale = o.scale[:, 1].copy()
+
+        def judge(res, tag):
+            acc, jrk, pot, lst = res
+            bad = oracle_lib.list_rows_equal(lst, l64)
+            outside = [i for i in bad if band[i] > 4.0]
+            a, j, pp = a64, j64, p64
+            if bad:
+                okrow = lst[:, 0] >= 0
+                a, j, pp = o.regf_f64_given_list(m, x, v, x[sel], v[sel], np.where(okrow[:, None], lst, l64))
+            dj = np.linalg.norm(jrk - j, axis=1) / np.linalg.norm(j, axis=1)
+            r = {"list_rows_differing_in_band": len(bad), "list_rows_differing_outside_band": len(outside),
+                 "acc_relerr": oracle_lib.relerr(acc, a), "pot_relerr": oracle_lib.relerr(pot, pp),
+                 "jerk_scaled_relerr": float(np.max(np.linalg.norm(jrk - j, axis=1) / np.maximum(np.linalg.norm(j, axis=1), scale))),
+                 "jerk_strict_relerr_max": float(dj.max()), "jerk_strict_relerr_p99": float(np.quantile(dj, 0.99)),
+                 "jerk_strict_relerr_median": float(np.median(dj))}
+            r["ok"] = (not outside) and max(r["acc_relerr"], r["pot_relerr"], r["jerk_scaled_relerr"]) <= 1e-6 and r["jerk_strict_relerr_max"] <= 1e-5
+            out[tag] = r
+            return r["ok"]
+        ok = judge(rep, "regf_vs_oracle")
+        if gathered is not None:
+            ok &= out["replicated_bitwise_equal_across_ranks"]
+            isl = [np.concatenate([g[q] for g in gathered]) for q in range(4)]
+            ok &= judge(isl, "islice_vs_oracle")
+            out["islice_lists_equal_replicated"] = not oracle_lib.list_rows_equal(isl[3], rep[3])
+            ok &= out["islice_lists_equal_replicated"]
+        out["oracle"] = "oracle/regf_oracle.c: fp64 statement of regint.f:39-79 with the reference FP32 membership"
+        out["jerk_note"] = ("jerk bar: 1e-6 of max(|J_i|, R_i), R_i the quadrature sum of the pair terms; the strict |dJ|/|J| is reported, "
+                            "bounded at 1e-5 (cancellation outliers; the reference's FP32 path leaves 5e-6..2e-5)")
+    if world > 1:
+        import torch
+        t = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+    out["ok"] = ok
+    return out
+
+
+def ref_cuda_probe(args):
+    """(subprocess) the reference's own CUDA library (gpunb.velocity.cu built unmodified for sm_100, oracle/_ref) on the
+    same workload through the same caller: 32 gpunb_regf_ calls of 1024 i with host arrays."""
+    from nbody6ppgpu_b200.gpunb import ForceLib
+    so = ROOT / "oracle" / "_ref" / "libgpunb_ref_gpu.so"
+    if not so.exists():
+        emit({"unavailable": "oracle/_ref/libgpunb_ref_gpu.so not built"})
+        return
+    ref = ForceLib(so)
+    ref.devinit(0)
+    n = args.n
+    m, x, v, h2, dtr, rs0 = make_snapshot(n, args.m_flag)
+    ref.open(n + 10, 0)
+    t0 = time.perf_counter(); ref.send(m, x, v); ts = time.perf_counter() - t0
+    call = ref.block_caller(h2, dtr, x, v, BLOCK, LMAX, NNBMAX, args.m_flag)
+    nb = max(1, min(32, n // BLOCK - 1))
+    for b in range(min(4, nb)):
+        call(b * BLOCK, BLOCK)
+    t0 = time.perf_counter()
+    for b in range(nb):
+        call(b * BLOCK, BLOCK)
+    t = time.perf_counter() - t0
+    ref.close()
+    emit({"gint_per_s": float(BLOCK) * nb * n / t * 1e-9, "us_per_call": t / nb * 1e6, "send_ms": ts * 1e3, "calls": nb, "n": n,
+          "library": "reference gpunb.velocity.cu, sm_100, same gpunb_regf_ calls with host arrays"})
+
+
+def run_ref_cuda_probe(n, m_flag, local):
+    try:
+        env = dict(os.environ, GPU_LIST=str(local), OMP_NUM_THREADS="8")
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--ref-cuda-probe", "--n", str(n), "--m-flag", str(m_flag)],
+                           capture_output=True, text=True, timeout=300, env=env)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"unavailable": (r.stderr or "no output")[-200:]}
+    except Exception as e:                                   # never fatal for the bench line
+        return {"unavailable": repr(e)[:200]}
+
+
 def main():
     args = parse()
     quiet_stdout()
@@ -228,6 +375,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.ref_cuda_probe:
+        ref_cuda_probe(args)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -245,7 +395,7 @@ def main():
     from nbody6ppgpu_b200 import load
     lib = load()
     lib.devinit(rank)
-    if world > 1:                                    # j sharded over ranks, every rank makes identical calls
+    if world > 1:                                    # j sharded over ranks
         from nbody6ppgpu_b200.sharding import nccl_bootstrap
         nccl_bootstrap(lib, rank, world)
 
@@ -262,6 +412,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(val):
+        if dist is None:
+            return val
+        t = torch.tensor([val], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     n = args.n
     ni_total = args.ni_total if args.ni_total > 0 else n
     m, x, v, h2, dtr, rs0 = make_snapshot(n, args.m_flag)
@@ -274,18 +431,26 @@ def main():
         flush.fill_(rank + 1)
         torch.cuda.synchronize()
 
-    # ---------------- device-resident leg: `value` ----------------
     lib.send(m, x, v)
+    # ---------------- parity before anything is timed ----------------
+    parity = parity_check(lib, dist, rank, world, m, x, v, h2, dtr, args.m_flag) if n > 4096 + BLOCK else {"ok": True, "skipped": "n too small"}
+    if not parity["ok"]:
+        if rank == 0:
+            emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity_check": parity, "error": "parity check failed"})
+        raise SystemExit(3)
+
+    # ---------------- device-resident leg: `value` ----------------
+    sblock = sweep_block(lib, world)
     lib.set_radii(h2, dtr)
     for _ in range(args.warmup):
-        lib.sweep_resident(0, ni_total, BLOCK, LMAX, NNBMAX, args.m_flag)
+        lib.sweep_resident(0, ni_total, sblock, LMAX, NNBMAX, args.m_flag)
     lib.reset_counters()
     sampler = ClockSampler(local)
     ms_steps = []
     for _ in range(args.steps):
         flush_l2()
         barrier()
-        ms_steps.append(max_over_ranks(lib.sweep_resident(0, ni_total, BLOCK, LMAX, NNBMAX, args.m_flag)))
+        ms_steps.append(max_over_ranks(lib.sweep_resident(0, ni_total, sblock, LMAX, NNBMAX, args.m_flag)))
         barrier()
     clocks = sampler.stop()
     c_res = lib.counters()
@@ -293,6 +458,7 @@ def main():
     ms_per_step = sum(ms_steps) / len(ms_steps)
     value = inter_step / (ms_per_step * 1e-3) * 1e-9
     launches_res = c_res["launches"]
+    sweep_blocks = (ni_total + sblock - 1) // sblock
 
     # per-launch duration of the dominant kernel (regf_kernel): CUDA events around each launch on its stream,
     # taken from a timed pass of ABI calls (the resident sweep does not break the stream to read events)
@@ -311,39 +477,61 @@ def main():
     # ---------------- end-to-end leg through the C-ABI with host buffers: `e2e` ----------------
     # caller-owned arrays and by-reference scalars set up once (the Fortran caller's static arrays)
     regf_call = lib.block_caller(h2, dtr, x, v, BLOCK, LMAX, NNBMAX, args.m_flag)
-    # ... and pinned once, like COMMON blocks that live for the whole run (gpunb_b200_pin_host_): the snapshot is then
-    # uploaded without a staging copy and result rows land straight in the caller's arrays.  --pageable: plain arrays.
-    pinned_arrays = [] if args.pageable else [m, x, v, *regf_call.outputs]
-    host_kind = "pinned" if (pinned_arrays and lib.pin_host(*pinned_arrays)) else "pageable"
+    nblk = (ni_total + BLOCK - 1) // BLOCK
 
     def abi_step():
         lib.send(m, x, v)
         nnb_sum = 0
-        for i0 in range(0, ni_total, BLOCK):
-            acc, jrk, pot, lst = regf_call(i0, min(BLOCK, ni_total - i0))
-            nnb_sum += int(lst[:, 0].sum())          # the step's result is read on the host
+        if world == 1:
+            for i0 in range(0, ni_total, BLOCK):
+                acc, jrk, pot, lst = regf_call(i0, min(BLOCK, ni_total - i0))
+                nnb_sum += int(lst[:, 0].sum())      # the step's result is read on the host
+        else:
+            # i-slice mode: block b belongs to rank b mod R (NBODY6++'s MPI build slices the i-block the same way,
+            # intgrt.F:982-1231); every collective call takes one block of 1024 from every rank
+            for c in range((nblk + world - 1) // world):
+                b = c * world + rank
+                if b < nblk:
+                    acc, jrk, pot, lst = regf_call(b * BLOCK, min(BLOCK, ni_total - b * BLOCK))
+                    nnb_sum += int(lst[:, 0].sum())
+                else:
+                    regf_call(0, 0)                  # nothing left for this rank: it still joins the collective call
         return nnb_sum
 
-    e2e_warm = max(1, min(args.warmup, 1)) if ni_total >= 500_000 else args.warmup
-    for _ in range(e2e_warm):
-        abi_step()
-    lib.reset_counters()
-    torch.cuda.synchronize()
-    t_e2e = 0.0
-    e2e_steps = args.steps
-    nnb_sum = 0
-    for _ in range(e2e_steps):
-        flush_l2()
-        barrier()
-        t0 = time.perf_counter()
-        nnb_sum = abi_step()
+    def abi_leg(pin):
+        """Returns (Gint/s, seconds per step, counters, host kind, sum of neighbour counts over all ranks)."""
+        pinned_arrays = [m, x, v, *regf_call.outputs] if pin else []
+        kind = "pinned" if (pinned_arrays and lib.pin_host(*pinned_arrays)) else "pageable"
+        if world > 1:
+            lib.set_islice(1)
+        e2e_warm = max(1, min(args.warmup, 1)) if ni_total >= 500_000 else args.warmup
+        for _ in range(e2e_warm):
+            abi_step()
+        lib.reset_counters()
         torch.cuda.synchronize()
-        t_e2e += max_over_ranks(time.perf_counter() - t0)
-        barrier()
-    c_e2e = lib.counters()
-    if pinned_arrays:
-        lib.unpin_host(*pinned_arrays)
-    e2e_val = inter_step * e2e_steps / t_e2e * 1e-9
+        t_tot, nnb = 0.0, 0
+        for _ in range(args.steps):
+            flush_l2()
+            barrier()
+            t0 = time.perf_counter()
+            nnb = abi_step()
+            torch.cuda.synchronize()
+            t_tot += max_over_ranks(time.perf_counter() - t0)
+            barrier()
+        c = lib.counters()
+        if world > 1:
+            lib.set_islice(0)
+        if pinned_arrays:
+            lib.unpin_host(*pinned_arrays)
+        return inter_step * args.steps / t_tot * 1e-9, t_tot / args.steps, c, kind, sum_over_ranks(float(nnb))
+
+    e2e_val, e2e_s, c_e2e, host_kind, nnb_sum = abi_leg(not args.pageable)
+    e2e_other = None
+    if not args.quick:
+        ov, os_, oc, ok_, _ = abi_leg(args.pageable)
+        e2e_other = {"value": ov, "unit": UNIT, "ms_per_step": os_ * 1e3, "host_arrays": ok_}
+    h2d_step = sum_over_ranks(c_e2e["h2d_bytes"]) / args.steps
+    d2h_step = sum_over_ranks(c_e2e["d2h_bytes"]) / args.steps
     lib.profile(rank)
 
     # ---------------- FP32 pipe microbenchmark (roofline denominator measured in the same run) ----------------
@@ -351,6 +539,42 @@ def main():
     # operand; a scalar FFMA with three distinct registers only reaches ~70 % of the lane rate on this part)
     ffma_tflops = max(lib.fp32_microbench(mode, 8192) for mode in (1, 8, 10) for _ in range(2))
     lib.close()
+
+    # ---------------- the smaller BASELINE configs, quick (one GPU only) ----------------
+    def quick_config(n2, m_flag2):
+        m2, x2, v2, h22, dtr2, _ = make_snapshot(n2, m_flag2)
+        lib.open(n2 + 10, rank)
+        lib.send(m2, x2, v2)
+        lib.set_radii(h22, dtr2)
+        for _ in range(2):
+            lib.sweep_resident(0, n2, BLOCK, LMAX, NNBMAX, m_flag2)
+        ms = min(lib.sweep_resident(0, n2, BLOCK, LMAX, NNBMAX, m_flag2) for _ in range(3))
+        call2 = lib.block_caller(h22, dtr2, x2, v2, BLOCK, LMAX, NNBMAX, m_flag2)
+        pinned2 = [m2, x2, v2, *call2.outputs]
+        kind2 = "pinned" if lib.pin_host(*pinned2) else "pageable"
+
+        def step2():
+            lib.send(m2, x2, v2)
+            for i0 in range(0, n2, BLOCK):
+                call2(i0, min(BLOCK, n2 - i0))
+        step2()
+        reps = 3 if n2 > 100_000 else 10
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step2()
+        te = (time.perf_counter() - t0) / reps
+        lib.unpin_host(*pinned2)
+        lib.close()
+        val2 = float(n2) * n2 / (ms * 1e-3) * 1e-9
+        return {"n": n2, "m_flag": m_flag2, "value": val2, "e2e": float(n2) * n2 / te * 1e-9, "unit": UNIT, "ms_per_sweep": ms,
+                "frac_of_sweep": val2 / (2.0 * 128 * 148 * 1965e6 / FLOP_PER_INT * 1e-9), "host_arrays": kind2}
+
+    configs = None
+    ref_cuda = None
+    if world == 1 and not args.quick and n >= 500_000:
+        configs = {"N256k_mflag0": quick_config(262144, 0), "N16k_mflag1": quick_config(16000, 1)}
+        ref_cuda = run_ref_cuda_probe(n, args.m_flag, local)
+
     if world > 1:
         barrier()
         lib.nccl_finalize()
@@ -361,52 +585,78 @@ def main():
     peaks, peak_src = measured_peaks()
     sm_max = clocks.get("sm_max_mhz") or 1965.0
     fp32_nominal = 2.0 * 128 * 148 * sm_max * 1e6 * 1e-12
+    roof_gint = fp32_nominal * 1e12 / FLOP_PER_INT * 1e-9
     achieved_tflops = FLOP_PER_INT * int_per_launch / (kern_ms * 1e-3) * 1e-12
     mean_nnb = nnb_sum / float(ni_total)
     # j tiles once (3392 B per 64 j) + i-block in + partial sums/lists out
     alg_bytes = n * interactions_scale * (3392.0 / 64.0) + BLOCK * (64.0 + 56.0 + 4.0 * (1 + mean_nnb))
-    traffic = None                                   # dram bytes of one regf_kernel launch from the committed ncu capture
+    traffic, traffic_src = None, None                # dram bytes of one regf_kernel launch from the committed ncu capture
     try:
         prof = json.loads((ROOT / "profiles" / "regf_kernel_ncu_latest.json").read_text())
         if world == 1 and prof.get("nj") == n:
             traffic = float(prof["dram_bytes_read"]) + float(prof["dram_bytes_write"])
+            traffic_src = f"profiles/regf_kernel_ncu_latest.json (ncu --set full capture {prof.get('tag')}, kernel {prof.get('kernel')})"
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    gint_kernel = int_per_launch / (kern_ms * 1e-3) * 1e-9
+    in_sweep_ms = ms_per_step / sweep_blocks
+    in_sweep_gint = float(sblock) * n * interactions_scale / (in_sweep_ms * 1e-3) * 1e-9 if sweep_blocks > 1 else value / world
+    lane_peak = 128.0 * 148 * sm_max * 1e6           # FP32 lane-instructions per second
     roofline = {
         "bound": "fp32", "kernel": "regf_kernel", "achieved": achieved_tflops, "peak": fp32_nominal, "unit": "TFLOP/s",
         "frac": achieved_tflops / fp32_nominal,
+        "convention": "60 flop per interaction, the reference's own (gpunb.velocity.cu:894); see fp32_pipe_slot_frac for the executed work",
         "peak_source": f"nominal 2*128 lanes*148 SM*{sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 entry)",
         "peak_measured_ffma": ffma_tflops, "peak_measured_ffma_how": "library microbenchmark, packed FFMA2 with <= 2 distinct register operands", "frac_of_measured_ffma": achieved_tflops / ffma_tflops,
-        "flop_per_interaction": FLOP_PER_INT, "interactions_per_launch": int_per_launch, "launch_ms": kern_ms,
-        "gint_per_s_kernel": int_per_launch / (kern_ms * 1e-3) * 1e-9,
-        "roofline_gint_per_s": fp32_nominal * 1e12 / FLOP_PER_INT * 1e-9,
-        "traffic": traffic,
+        "flop_per_interaction": FLOP_PER_INT, "interactions_per_launch": int_per_launch,
+        "launch_ms": kern_ms, "launch_ms_how": "isolated launches (one gpunb_regf_ call = one pair-kernel launch), CUDA events on the launching stream",
+        "gint_per_s_kernel": gint_kernel, "roofline_gint_per_s": roof_gint,
+        # what the FAR body (94 % of the tile visits) executes per pair: 27 FP32 lane-operations (13.5 packed f32x2
+        # instructions) + 1 MUFU.RSQ -- the fraction of the FP32 pipe's lane-operation slots the kernel fills
+        "fp32_lane_ops_per_interaction": 27.0, "fp32_pipe_slot_frac": 27.0 * gint_kernel * 1e9 / lane_peak,
+        "in_sweep_block_ms": in_sweep_ms, "in_sweep_block_i": sblock, "in_sweep_gint_per_s_per_gpu": in_sweep_gint,
+        "in_sweep_how": "ms_per_step / blocks of the pipelined resident sweep: consecutive launches overlap their tails",
+        "traffic": traffic, "traffic_source": traffic_src,
         # the same 60 flop/interaction over the WHOLE pipelined sweep (`value`), where the tail of every launch is
         # filled by the next block's CTAs -- per GPU
-        "frac_of_sweep": value / world / (fp32_nominal * 1e12 / FLOP_PER_INT * 1e-9),
+        "frac_of_sweep": value / world / roof_gint,
+        "fp32_pipe_slot_frac_of_sweep": 27.0 * value / world * 1e9 / lane_peak,
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms * 1e-3) * 1e-9,
                 "peak_gbs": hbm_peak, "peak_source": peak_src, "frac": alg_bytes / (kern_ms * 1e-3) * 1e-9 / hbm_peak},
         "merge_kernel_ms": merge_ms,
     }
 
+    if world == 1:
+        e2e_api = (f"gpunb_send_ + {nblk} gpunb_regf_ calls of {BLOCK} i (ctypes, {host_kind} caller-owned host arrays allocated once; result rows "
+                   "written by the kernels over PCIe, d2h = bytes of valid rows)")
+    else:
+        e2e_api = (f"every rank: gpunb_send_ + {(nblk + world - 1) // world} collective gpunb_regf_ calls in i-slice mode (rank r passes block c R + r of "
+                   f"{BLOCK} i and receives its own rows; ctypes, {host_kind} caller-owned host arrays); bytes summed over ranks")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic Plummer N={n} Kroupa IMF, regular-force sweep", "nj": n, "ni_per_step": ni_total,
-                   "block": BLOCK, "lmax": LMAX, "nnbmax": NNBMAX, "m_flag": args.m_flag, "rs_min": rs0, "mean_nnb": mean_nnb,
-                   "interactions_per_step": inter_step, "l2": "flushed between timed steps (256 MB fill)",
-                   "parallelism": f"j-shard x{world}",
-                   "pipeline": {"sweep_slots": NSLOT if NSLOT else (2 if world == 1 else 3), "regf_subblocks": NSUB}},
+        "config": bench_config(n, args.m_flag, rs0, world),
+        "sample": f"send + every i-block of the sweep ({nblk} blocks of {BLOCK}) against all {n} j per step",
+        "run": {"ni_per_step": ni_total, "sweep_block": sblock, "mean_nnb": mean_nnb, "interactions_per_step": inter_step,
+                "pipeline": {"sweep_slots": NSLOT if NSLOT else (2 if world == 1 else 3), "regf_subblocks": NSUB}},
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": c_e2e["h2d_bytes"] / e2e_steps,
-                "d2h_bytes_per_step": c_e2e["d2h_bytes"] / e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
-                "api": f"gpunb_send_ + gpunb_regf_ (ctypes, {host_kind} caller-owned host arrays allocated once; result rows "
-                       "written by the kernels over PCIe, d2h = bytes of valid rows)", "host_arrays": host_kind},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                "ms_per_step": e2e_s * 1e3, "api": e2e_api, "host_arrays": host_kind, "mode": "single process" if world == 1 else "i-slice (collective calls)"},
         "gpu_launches": int(launches_res),
         "roofline": roofline,
+        "parity_check": parity,
+        "jerk_strict": {"relerr_max": parity.get("regf_vs_oracle", {}).get("jerk_strict_relerr_max"), "tolerance_used": 1e-5,
+                        "north_star_tolerance": 1e-6, "scaled_relerr": parity.get("regf_vs_oracle", {}).get("jerk_scaled_relerr"),
+                        "note": "strict per-particle |dJ|/|J| at N=1M on the parity block; the 1e-6 bar is met under the cancellation-aware norm only"},
     }
+    if e2e_other is not None:
+        out["e2e"]["pageable" if e2e_other["host_arrays"] == "pageable" else "pinned"] = e2e_other
+    if configs is not None:
+        out["configs"] = configs
+    if ref_cuda is not None:
+        out["ref_cuda"] = ref_cuda
 
     if not args.no_cpu_baseline and rank == 0:
         threads = cpu_threads()

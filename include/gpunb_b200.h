@@ -57,6 +57,9 @@ const char *gpunb_b200_build_info(void);
 
 /* Number of GPUs this process drives (after devinit). */
 int gpunb_b200_num_devices(void);
+/* Resident warps of the pair kernel on device 0 (SMs x CTAs per SM x 4): a block of 32 * (resident_warps / S) i-particles
+ * with integer S fills the machine exactly (1024 at S = 74 on a B200; 2048 / 4736 / 9472 at S = 37 / 16 / 8). */
+int gpunb_b200_resident_warps(void);
 
 /* Counters since the last reset (doubles, see GPUNB_B200_CTR_*): device time of the pair kernel
  * measured with CUDA events on its launching stream, launches, bytes moved, interactions. */
@@ -90,6 +93,7 @@ enum {
     GPUNB_B200_CTR_SEND_STAGE_MS,
     GPUNB_B200_CTR_SEND_TILES_MS,
     GPUNB_B200_CTR_TRANSPOSED_TILES, /* NEAR (warp, j-tile) visits handled by the transposed path (GPUNB_B200_STATS=1) */
+    GPUNB_B200_CTR_HOST_RENDEZVOUS_MS, /* i-slice mode: publishing this rank's slice and waiting for the other ranks' (ms) */
     GPUNB_B200_CTR_COUNT
 };
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);
@@ -148,6 +152,19 @@ void  gpunb_b200_unpin_host_(void *ptr);
  * of the sums -- then depends on the call history.  Default 1 (always sort: results are a function of the snapshot
  * alone).  Environment: GPUNB_B200_RESORT_EVERY. */
 void  gpunb_b200_set_resort_every(int k);
+
+/* i-slice mode (one process per GPU, after gpunb_b200_nccl_init; environment GPUNB_B200_ISLICE=1).  Off (default): every
+ * rank passes the SAME i-block to gpunb_regf_ and receives the complete result (replicated data).  On: gpunb_regf_ is a
+ * collective call in which every rank passes ITS OWN i-slice -- ni may differ between ranks and may be 0, lmax / nnbmax /
+ * m_flag must agree -- and receives the results of that slice only.  This is the calling pattern of NBODY6++'s MPI build,
+ * where every rank integrates its share of the regular block (intgrt.F:982-1231): the ranks' slices meet in a shared-
+ * memory segment of the node, every GPU runs ONE pair-kernel launch on the union of the slices against its j-shard, and
+ * each rank's combine kernel pulls only its own rows from the peers over NVLink.  Every rank must make the same number
+ * of gpunb_regf_ calls (pad with ni = 0). */
+void  gpunb_b200_set_islice(int on);
+
+/* Pairs (i x local j) a sub-block of gpunb_regf_ must keep for the call to be split (default 1.5e8; tests lower it). */
+void  gpunb_b200_set_sub_pairs(double pairs);
 
 /* Sub-block sizes of one gpunb_regf_ call: 0 = equal (default), 1 = tapering (weights 7:5:3:1 for four sub-blocks;
  * measured, no gain).  Environment: GPUNB_B200_TAPER. */

@@ -60,6 +60,9 @@
 #include <sys/time.h>
 #include <unistd.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
 #include "../../include/gpunb_b200.h"
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -78,6 +81,8 @@ enum { C_DX = 0, C_DY, C_DZ, C_VX, C_VY, C_VZ, C_M, C_XH, C_YH, C_ZH, C_XL, C_YL
 constexpr int NSTAGE      = 3;                    // smem stages per warp
 constexpr int WARPS       = 4;                    // warps per CTA (warp-autonomous: no CTA-wide sync)
 constexpr int NIMAX       = 2048;                 // capacity per call (reference: gpunb.velocity.cu:24)
+constexpr int JOBCAP      = 16384;                // i-particles of one launch group: the union of all ranks' i-slices of a
+                                                  // collective gpunb_regf_ (i-slice mode), or one block of a resident sweep
 constexpr int PART_STRIDE = 8;                    // doubles per partial record (7 used)
 constexpr int OVERSUB     = 1;                    // work items per resident warp (GPUNB_B200_OVERSUB; >1 measured no gain)
 constexpr int SORT_CAP    = 1024;
@@ -324,16 +329,29 @@ __device__ __forceinline__ unsigned long long bitonic_pick(unsigned long long v,
     const bool up = (e & size) == 0, lower = (e & stride) == 0;
     return (lower == up) ? (v < o ? v : o) : (v < o ? o : v);
 }
-__global__ void __launch_bounds__(1024) isort_kernel(int ni_total, int block, const double *__restrict__ xi_all,
-                                                      const unsigned *__restrict__ hbits, int *__restrict__ iperm_all,
-                                                      int *__restrict__ iperm_host)
-{   // CTA b sorts the i-block [b*block, b*block + ni): one launch orders every block of a resident sweep.
-    // iperm holds indices LOCAL to the block.  iperm_host (optional, mapped pinned memory): the same order for the
+__global__ void __launch_bounds__(1024) isort_kernel(int ni_total, int block, int sortblk, const int *__restrict__ blk_off,
+                                                      const double *__restrict__ xi_all, const unsigned *__restrict__ hbits,
+                                                      int *__restrict__ iperm_all, int *__restrict__ iperm_host)
+{   // One CTA sorts one SORT BLOCK (<= NIMAX particles); one launch orders every block of a resident sweep.
+    //   blk_off == NULL: the i-set is cut into job blocks of `block` particles (one launch group each), every job block into
+    //                    sort blocks of `sortblk`; CTA b = job * ceil(block / sortblk) + sub.
+    //   blk_off != NULL: ONE job; sort block b covers [blk_off[b], blk_off[b+1]) (the ranks' i-slices of a collective call).
+    // iperm holds indices LOCAL to the job block.  iperm_host (optional, mapped pinned memory): the same order for the
     // host side of gpunb_regf_, which receives its result rows in sorted order.
     __shared__ unsigned long long key[NIMAX];
     const int t = threadIdx.x;
-    const int off = blockIdx.x * block;
-    const int ni = min(block, ni_total - off);
+    int off, ni, in_job;
+    if (blk_off) {
+        off = blk_off[blockIdx.x]; ni = blk_off[blockIdx.x + 1] - off; in_job = off;
+    } else {
+        const int spj = (block + sortblk - 1) / sortblk;
+        const int job = blockIdx.x / spj, sub = blockIdx.x - job * spj;
+        const int job_ni = min(block, ni_total - job * block);
+        in_job = sub * sortblk;
+        ni = min(sortblk, job_ni - in_job);
+        off = job * block + in_job;
+    }
+    if (ni <= 0) return;
     const double *xi = xi_all + 3 * (size_t)off;
     int *iperm = iperm_all + off;
     const float sc = 511.5f / fmaxf(__uint_as_float(*hbits), 1e-30f);
@@ -358,8 +376,8 @@ __global__ void __launch_bounds__(1024) isort_kernel(int ni_total, int block, co
             }
         }
     }
-    if (t < ni) { iperm[t] = (int)(v0 & 2047ull); if (iperm_host) iperm_host[off + t] = (int)(v0 & 2047ull); }
-    if (two && t + 1024 < ni) { iperm[t + 1024] = (int)(v1 & 2047ull); if (iperm_host) iperm_host[off + t + 1024] = (int)(v1 & 2047ull); }
+    if (t < ni) { const int i = in_job + (int)(v0 & 2047ull); iperm[t] = i; if (iperm_host) iperm_host[off + t] = i; }
+    if (two && t + 1024 < ni) { const int i = in_job + (int)(v1 & 2047ull); iperm[t + 1024] = i; if (iperm_host) iperm_host[off + t + 1024] = i; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1077,6 +1095,9 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
 // ---------------------------------------------------------------------------------------------
 struct CombineArgs {
     int nloc, R, lmax, nnbmax;
+    int kl0, kl1;                    // this launch combines the local slots [kl0, kl1) of the job: everything (replicated
+                                     // results) or the slots of this rank's own i-slice (i-slice mode)
+    int row_base;                    // output row of slot kl: iperm[kl] - row_base
     const double *fr[MAX_RANKS];     // [nloc][8]
     const int    *rows[MAX_RANKS];   // [nloc][lmax]
     const int    *iperm;             // output row of kl (NULL: kl)
@@ -1113,7 +1134,7 @@ __device__ __forceinline__ void combine_row(const CombineArgs &a, int kl, int la
             }
         }
     }
-    const int i = a.iperm ? a.iperm[kl] : kl;
+    const int i = (a.iperm ? a.iperm[kl] : kl) - a.row_base;
     if (a.abi_acc) {
         if (lane < 3) a.abi_acc[3 * (size_t)i + lane] = f;
         else if (lane < 6) a.abi_jrk[3 * (size_t)i + lane - 3] = f;
@@ -1145,8 +1166,8 @@ __global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
     __shared__ int sbuf[4][SORT_CAP];
     __shared__ int soff[4][MAX_RANKS], scnt[4][MAX_RANKS];
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int kl = blockIdx.x * 4 + wq;
-    if (kl < a.nloc) {
+    const int kl = a.kl0 + blockIdx.x * 4 + wq;
+    if (kl < a.kl1) {
         if (a.flags) wait_all_ranks(a.flags, a.R, (long long)a.seq, lane);    // every shard has published this call
         combine_row(a, kl, lane, sbuf[wq], soff[wq], scnt[wq]);
     }
@@ -1353,7 +1374,9 @@ const Variant VARIANTS[] = {
     {"it1b4nt", 1, {regf_kernel<1, false, 4, 3>, regf_kernel<1, true, 4, 3>}},
 };
 constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
-constexpr int DEFAULT_VARIANT = 4;     // it1b4: 4 CTAs/SM (<= 128 registers), fastest at every ni (profiles/r01e_variants.txt)
+constexpr int DEFAULT_VARIANT = 7;     // it1b4t: 4 CTAs/SM (<= 128 registers) + transposed NEAR lanes: +2 % at ni = 1024, +8 % at 256,
+                                       // +18 % at 32 over it1b4 at N = 1M (profiles/r2a_variant_probe.txt); the Newton step in the
+                                       // FAR body ("n") costs 10 % and leaves the strict jerk error where it is (2.9e-6 vs 3.1e-6)
 constexpr int ROWS_LMAX_CAP = 1024;    // row stride capacity of the IPC-exported shard rows (NCCL mode)
 
 // Pipeline slot: the work buffers one i-block (or sub-block) needs from the pair kernel to the merged result, and the
@@ -1401,7 +1424,7 @@ struct Dev {
     int *iperm_identity = nullptr;   // 0, 1, 2, ... (blocks of a single i-tile are not sorted)
     unsigned long long *stats = nullptr;   // [0] near (warp,tile) visits, [1] all visits (GPUNB_B200_STATS=1)
     unsigned long long *wtime = nullptr;   // per work item start/end timestamps (GPUNB_B200_STATS=2)
-    double *ibuf = nullptr;       // 8*NIMAX doubles: h2 | dtr | x | v
+    double *ibuf = nullptr;       // 8*JOBCAP doubles: h2 | dtr | x | v (+ 64: slice offsets of a collective call)
     int segcap = 0;
     double *fr = nullptr;         // [NIMAX][8] shard partial + count (multi-GPU)
     int *rows = nullptr; size_t rows_ints = 0;                                     // shard rows (in-process multi-GPU)
@@ -1430,12 +1453,23 @@ struct Shard {                     // one process per GPU, j sharded over ranks
     pfn_ncclCommDestroy destroy = nullptr; pfn_ncclGetErrorString errstr = nullptr;
     ncclComm_t comm = nullptr;
     // Exchange buffer of this rank (one allocation, exported with cudaIpc, mapped by every peer):
-    //   [XSLOTS] x { fr[NIMAX][8] doubles | rows[NIMAX][ROWS_LMAX_CAP] ints }  |  flags[XSLOTS][MAX_RANKS] u64
+    //   [XSLOTS] x { fr[JOBCAP][8] doubles | rows[JOBCAP][ROWS_LMAX_CAP] ints }  |  flags[XSLOTS][MAX_RANKS] u64
     //   | acks[XSLOTS][MAX_RANKS] u64
     unsigned char *xbuf = nullptr;
     unsigned char *xbuf_peer[MAX_RANKS] = {nullptr};
     unsigned long long seq = 0;    // exchange steps so far (every rank makes the same calls)
     double *scratch = nullptr;     // bootstrap / finalize all-gathers
+    // i-slice mode (gpunb_b200_set_islice): gpunb_regf_ is a COLLECTIVE call in which every rank passes its OWN i-slice
+    // (what NBODY6++'s MPI build does: each rank integrates its share of the block, intgrt.F:982-1231) and receives the
+    // results of that slice only.  The slices (<= 64 B x 2048 per rank) meet in a POSIX shared-memory segment of the node.
+    bool islice = false;
+    struct ShmSeg *shm = nullptr;
+    unsigned long long icall = 0;  // collective calls so far
+};
+struct ShmSlice { int ni, lmax, nnbmax, m_flag; int pad[12]; double data[8 * NIMAX]; };     // h2 | dtr | x | v of one rank
+struct ShmSeg {
+    unsigned long long seq[2][MAX_RANKS];      // call number whose slice sits in slice[parity][rank]
+    ShmSlice slice[2][MAX_RANKS];
 };
 
 struct Lib {
@@ -1445,7 +1479,7 @@ struct Lib {
     int nbmax = 0, nbody = 0;
     double *h_j = nullptr; size_t h_j_n = 0;          // pinned staging: 7*nj doubles
     double *h_upd = nullptr; int *h_upd_idx = nullptr; int h_upd_cap = 0;    // pinned staging of state updates
-    double *h_i = nullptr;                            // 8*NIMAX doubles (pinned staging of the i-block)
+    double *h_i = nullptr;                            // 8*JOBCAP + 64 doubles (pinned staging of the i-block)
     // results of gpunb_regf_: MAPPED pinned host memory that merge / combine write straight over PCIe (zero copy),
     // and the device-side aliases of those buffers
     double *h_f = nullptr, *h_f_dev = nullptr;        // [NIMAX][7]
@@ -1454,6 +1488,7 @@ struct Lib {
     int *h_flag = nullptr;
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
     int resort_every = 1;          // Hilbert order refreshed every k-th snapshot (GPUNB_B200_RESORT_EVERY); 1 = always
+    double sub_pairs = 1.5e8;      // pairs a sub-block of gpunb_regf_ must keep (GPUNB_B200_SUB_PAIRS)
     int snapshots_since_sort = 0;
     bool taper = false;            // tapering sub-block sizes (GPUNB_B200_TAPER=1); measured: no gain at 4 sub-blocks
     bool nslot_auto = true;        // nslot not chosen by the caller (environment / gpunb_b200_set_tuning)
@@ -1562,6 +1597,7 @@ void lib_devinit(int irank)
     { const char *e = getenv("GPUNB_B200_NSLOT"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) { L.nslot = atoi(e); L.nslot_auto = false; } }
     { const char *e = getenv("GPUNB_B200_NSUB");  if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nsub = atoi(e); }
     { const char *e = getenv("GPUNB_B200_TAPER"); if (e) L.taper = atoi(e) != 0; }
+    { const char *e = getenv("GPUNB_B200_SUB_PAIRS"); if (e && atof(e) >= 1.0) L.sub_pairs = atof(e); }
     { const char *e = getenv("GPUNB_B200_RESORT_EVERY"); if (e && atoi(e) >= 1) L.resort_every = atoi(e); }
     { const char *e = getenv("GPUNB_B200_HOST_THREADS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) L.host_threads = atoi(e); }
     L.devinit = true;
@@ -1681,13 +1717,14 @@ template <class T> void host_alloc_mapped(T *&h, T *&dptr, size_t n)
 }
 
 // Work buffers of the first `nslots` pipeline slots of device d, and (root) the mapped host result buffers.
-void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root, int nslots, bool device_results)
+void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root, int nslots, bool device_results, int job_rows = NIMAX)
 {
     set_dev(d);
     // n_itiles * S never exceeds warps_resident (+ n_itiles when S = 1)
-    const int items = d.warps_resident * d.oversub + NIMAX / d.itile;
+    const int items = d.warps_resident * d.oversub + JOBCAP / d.itile;
     const int segcap = ((nnbmax > 0 ? nnbmax : 1) + 3) & ~3;
-    const size_t rl = (size_t)NIMAX * lmax;
+    const size_t rl = (size_t)NIMAX * lmax;                  // host-side results: one rank's call
+    const size_t rl_job = (size_t)(job_rows > NIMAX ? job_rows : NIMAX) * lmax;      // device-side results of a sweep block
     for (int q = 0; q < nslots; q++) {
         Slot &sl = d.slots[q];
         if (items > sl.items_cap) {
@@ -1706,12 +1743,12 @@ void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root, int nslots,
         }
         if (!sl.done_ctr) { dev_alloc(sl.done_ctr, 2); CUDA_CHECK(cudaMemset(sl.done_ctr, 0, 2 * sizeof(unsigned))); }
         if (is_root && device_results) {
-            if (!sl.res_f) dev_alloc(sl.res_f, (size_t)7 * NIMAX);
-            if (rl > sl.res_list_ints) {
+            if (!sl.res_f) dev_alloc(sl.res_f, (size_t)7 * JOBCAP);
+            if (rl_job > sl.res_list_ints) {
                 CUDA_CHECK(cudaDeviceSynchronize());
                 dev_free(sl.res_list);
-                sl.res_list_ints = rl;
-                dev_alloc(sl.res_list, rl);
+                sl.res_list_ints = rl_job;
+                dev_alloc(sl.res_list, rl_job);
             }
         }
     }
@@ -1743,12 +1780,12 @@ void lib_open(int nbmax, int irank)
     for (Dev &d : L.devs) {
         set_dev(d);
         ensure_j_capacity(d, nbmax, nbmax / R + TJ);
-        if (!d.ibuf)    dev_alloc(d.ibuf, (size_t)8 * NIMAX);
+        if (!d.ibuf)    dev_alloc(d.ibuf, (size_t)8 * JOBCAP + 64);          // + the slice offsets of a collective call
         if (!d.fr)      dev_alloc(d.fr, (size_t)8 * NIMAX);
-        if (!d.iperm)   dev_alloc(d.iperm, (size_t)NIMAX);
+        if (!d.iperm)   dev_alloc(d.iperm, (size_t)JOBCAP);
         if (!d.iperm_identity) {
-            dev_alloc(d.iperm_identity, (size_t)NIMAX);
-            iota_kernel<<<(NIMAX + 255) / 256, 256, 0, d.st>>>(NIMAX, NIMAX, d.iperm_identity, nullptr);
+            dev_alloc(d.iperm_identity, (size_t)JOBCAP);
+            iota_kernel<<<(JOBCAP + 255) / 256, 256, 0, d.st>>>(JOBCAP, JOBCAP, d.iperm_identity, nullptr);
             CUDA_CHECK(cudaGetLastError());
         }
         if (!d.stats && getenv("GPUNB_B200_STATS")) { dev_alloc(d.stats, 4); CUDA_CHECK(cudaMemsetAsync(d.stats, 0, 32, d.st)); }
@@ -1757,7 +1794,7 @@ void lib_open(int nbmax, int irank)
     }
     const size_t hj = (size_t)7 * ((size_t)nbmax + 64);
     if (hj > L.h_j_n) { host_free(L.h_j); L.h_j_n = hj; host_alloc(L.h_j, hj); }
-    if (!L.h_i) host_alloc(L.h_i, (size_t)8 * NIMAX);
+    if (!L.h_i) host_alloc(L.h_i, (size_t)8 * JOBCAP + 64);
     if (!L.h_f) host_alloc_mapped(L.h_f, L.h_f_dev, (size_t)7 * NIMAX);
     if (!L.h_iperm) host_alloc_mapped(L.h_iperm, L.h_iperm_dev, (size_t)NIMAX);
     fprintf(stderr, "# Open GPU regular force - rank: %d; nbmax: %d\n", irank, nbmax);
@@ -2057,8 +2094,8 @@ struct IBlock { const double *h2, *dtr, *xi, *vi; };
 // several i-blocks can be in flight (pipelined sweeps); a slot is overwritten only after every peer has acknowledged
 // reading its previous contents (acks, checked inside merge_kernel).
 constexpr int    XSLOTS        = 8;
-constexpr size_t XB_FR_BYTES   = (size_t)NIMAX * 8 * sizeof(double);
-constexpr size_t XB_ROWS_BYTES = (size_t)NIMAX * 1024 /*ROWS_LMAX_CAP*/ * sizeof(int);
+constexpr size_t XB_FR_BYTES   = (size_t)JOBCAP * 8 * sizeof(double);
+constexpr size_t XB_ROWS_BYTES = (size_t)JOBCAP * 1024 /*ROWS_LMAX_CAP*/ * sizeof(int);
 constexpr size_t XB_SLOT       = XB_FR_BYTES + XB_ROWS_BYTES;
 constexpr size_t XB_FLAGS_OFF  = XSLOTS * XB_SLOT;
 constexpr size_t XB_ACKS_OFF   = XB_FLAGS_OFF + (size_t)XSLOTS * 16 /*MAX_RANKS*/ * sizeof(unsigned long long);
@@ -2068,13 +2105,17 @@ inline int    *xb_rows(unsigned char *b, int xs) { return reinterpret_cast<int *
 inline unsigned long long *xb_flags(unsigned char *b, int xs) { return reinterpret_cast<unsigned long long *>(b + XB_FLAGS_OFF) + xs * 16; }
 inline unsigned long long *xb_acks(unsigned char *b, int xs)  { return reinterpret_cast<unsigned long long *>(b + XB_ACKS_OFF) + xs * 16; }
 
-void launch_isort(Dev &d, cudaStream_t st, int ni_total, int block, const double *xi, int *iperm, int *iperm_host)
-{
+void launch_isort(Dev &d, cudaStream_t st, int ni_total, int block, const double *xi, int *iperm, int *iperm_host,
+                  const int *blk_off = nullptr, int nblk_off = 0)
+{   // blk_off (device, nblk_off + 1 entries): one job whose sort blocks are the ranks' i-slices; else uniform job blocks
     static int noisort = -1;
     if (noisort < 0) { const char *e = getenv("GPUNB_B200_NOISORT"); noisort = (e && atoi(e) > 0) ? 1 : 0; }
-    const int nblocks = (ni_total + block - 1) / block;
+    const int sortblk = block <= NIMAX ? block : 1024;
+    const int spj = (block + sortblk - 1) / sortblk;
+    const int njobs = (ni_total + block - 1) / block;
     if (noisort) iota_kernel<<<(ni_total + 255) / 256, 256, 0, st>>>(ni_total, block, iperm, iperm_host);
-    else isort_kernel<<<nblocks, 1024, 0, st>>>(ni_total, block, xi, d.hbits, iperm, iperm_host);
+    else if (blk_off) isort_kernel<<<nblk_off, 1024, 0, st>>>(ni_total, ni_total, NIMAX, blk_off, xi, d.hbits, iperm, iperm_host);
+    else isort_kernel<<<njobs * spj, 1024, 0, st>>>(ni_total, block, sortblk, nullptr, xi, d.hbits, iperm, iperm_host);
     CUDA_CHECK(cudaGetLastError());
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
 }
@@ -2085,6 +2126,9 @@ struct Job {
     int lmax, nnbmax, m_flag;
     double *out_f; int *out_list;      // final results, row i = iperm[slot] (device memory or mapped host memory)
     double *abi_acc = nullptr, *abi_jrk = nullptr, *abi_pot = nullptr;   // or the caller's pinned arrays (with out_list)
+    // i-slice mode (collective gpunb_regf_, one process per GPU): this rank combines and receives only the sorted slots
+    // [own0, own1) of the block -- its own i-slice -- and its result rows are numbered from row_base
+    int own0 = 0, own1 = INT_MAX, row_base = 0;
 };
 
 // Pair kernel (stream lo) + shard-local merge (stream hi) of one job on device d, pipeline slot sl.
@@ -2149,6 +2193,10 @@ void run_job(const Job &j, const IBlock *ib, const int *const *iperm, int q, boo
         memset(&c, 0, sizeof(c));
         c.nloc = j.nloc; c.lmax = j.lmax; c.nnbmax = j.nnbmax; c.res_f = j.out_f; c.res_list = j.out_list;
         c.iperm = iperm[0] + j.slot0;
+        c.kl0 = j.own0 > j.slot0 ? j.own0 - j.slot0 : 0;
+        c.kl1 = j.own1 - j.slot0 < j.nloc ? j.own1 - j.slot0 : j.nloc;
+        if (c.kl1 < c.kl0) c.kl1 = c.kl0;          // nothing of this rank in the job: the launch still acknowledges
+        c.row_base = j.row_base;
         c.abi_acc = j.abi_acc; c.abi_jrk = j.abi_jrk; c.abi_pot = j.abi_pot;
         if (L.sh.on) {
             // One process per GPU.  No collective call in the data path: merge_kernel writes the shard result into
@@ -2192,7 +2240,8 @@ void run_job(const Job &j, const IBlock *ib, const int *const *iperm, int q, boo
             c.R = G;
             set_dev(root);
         }
-        combine_kernel<<<(j.nloc + 3) / 4, 128, 0, hi>>>(c);      // 4 warps per CTA: one i each
+        const int ncomb = c.kl1 - c.kl0;
+        combine_kernel<<<ncomb > 0 ? (ncomb + 3) / 4 : 1, 128, 0, hi>>>(c);      // 4 warps per CTA: one i each
         CUDA_CHECK(cudaGetLastError());
         L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
         if (!L.sh.on) CUDA_CHECK(cudaEventRecord(root.evdone, root.st));
@@ -2225,10 +2274,14 @@ void scatter_rows(const int *order, int k0, int k1, int lmax, double *acc, doubl
     L.ctr[GPUNB_B200_CTR_D2H_BYTES] += bytes;      // what the kernels wrote over PCIe into the mapped buffers
 }
 
+void lib_regf_islice(int ni, const double *h2, const double *dtr, const double *xi, const double *vi,
+                     double *acc, double *jrk, double *pot, int lmax, int nnbmax, int *list, int m_flag);
+
 void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, const double *vi,
               double *acc, double *jrk, double *pot, int lmax, int nnbmax, int *list, int m_flag)
 {
     if (!L.is_open) FATAL("gpunb_regf called while the library is closed");
+    if (L.sh.on && L.sh.islice) { lib_regf_islice(ni, h2, dtr, xi, vi, acc, jrk, pot, lmax, nnbmax, list, m_flag); return; }
     if (!(0 < ni && ni <= NIMAX)) FATAL("gpunb_regf: ni=%d out of range (0, %d]", ni, NIMAX);
     if (nnbmax + 1 > lmax) FATAL("gpunb_regf: nnbmax=%d does not fit rows of lmax=%d", nnbmax, lmax);
     if (nnbmax > SORT_CAP) FATAL("gpunb_regf: nnbmax=%d exceeds the list capacity %d of this build", nnbmax, SORT_CAP);
@@ -2257,7 +2310,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     // decided from rank-invariant quantities only: every rank of a sharded run must cut the call into the same
     // sub-blocks (each is one exchange step), and shard sizes differ by a tile between ranks
     const double pairs = (double)ni * L.nbody / total_ranks();
-    if (!L.nsub_forced && nsub > (int)(pairs / 1.5e8)) nsub = (int)(pairs / 1.5e8);
+    if (!L.nsub_forced && nsub > (int)(pairs / L.sub_pairs)) nsub = (int)(pairs / L.sub_pairs);
     if (nsub < 1) nsub = 1;
     IBlock ib[MAX_RANKS];
     const int *ipm[MAX_RANKS];
@@ -2361,6 +2414,149 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     L.ctr[GPUNB_B200_CTR_HOST_PACK_MS] += (wt_packed - wt_in) * 1e3;
     L.ctr[GPUNB_B200_CTR_HOST_WAIT_MS] += t_wait * 1e3;
     L.ctr[GPUNB_B200_CTR_HOST_SCATTER_MS] += t_scatter * 1e3;
+    L.last_ni = ni; L.last_lmax = lmax; L.last_on_host = true;
+}
+
+// gpunb_regf_ in i-slice mode (one process per GPU, gpunb_b200_set_islice): a collective call.  Every rank passes its own
+// i-slice (ni may differ between ranks and may be 0); the slices meet in shared memory, every rank computes the UNION
+// against its j-shard in one launch group (the pair kernel runs on ni_total x nj/R pairs, so its fixed costs are paid
+// once per R slices), merge publishes the shard rows of the whole union, and combine_kernel on rank r pulls and delivers
+// only the rows of rank r's own slice: result traffic over NVLink and PCIe is partitioned, not replicated.
+void lib_regf_islice(int ni, const double *h2, const double *dtr, const double *xi, const double *vi,
+                     double *acc, double *jrk, double *pot, int lmax, int nnbmax, int *list, int m_flag)
+{
+    Shard &sh = L.sh;
+    Dev &root = L.devs[0];
+    const int R = sh.R, me = sh.rank;
+    if (!(0 <= ni && ni <= NIMAX)) FATAL("gpunb_regf (i-slice mode): ni=%d out of range [0, %d]", ni, NIMAX);
+    if (nnbmax + 1 > lmax) FATAL("gpunb_regf: nnbmax=%d does not fit rows of lmax=%d", nnbmax, lmax);
+    if (nnbmax > SORT_CAP) FATAL("gpunb_regf: nnbmax=%d exceeds the list capacity %d of this build", nnbmax, SORT_CAP);
+    const double wt_in = wtime();
+    L.numInter += (long long)ni * L.nbody;
+    L.ctr[GPUNB_B200_CTR_INTERACTIONS] += (double)ni * L.nbody;
+    L.ini += ni; L.icall++;
+    // ---- rendezvous: publish this rank's slice, wait for everybody's
+    const unsigned long long c = ++sh.icall;
+    const int p = (int)(c & 1ull);
+    {
+        ShmSlice &mine = sh.shm->slice[p][me];
+        mine.ni = ni; mine.lmax = lmax; mine.nnbmax = nnbmax; mine.m_flag = m_flag;
+        double *h = mine.data;
+        memcpy(h, h2, sizeof(double) * ni);
+        memcpy(h + ni, dtr, sizeof(double) * ni);
+        memcpy(h + 2 * (size_t)ni, xi, sizeof(double) * 3 * ni);
+        memcpy(h + 5 * (size_t)ni, vi, sizeof(double) * 3 * ni);
+        for (int k = 0; k < 8 * ni; k++) if (h[k] != h[k]) FATAL("gpunb_regf: NaN in i-particle data");
+        __atomic_store_n(&sh.shm->seq[p][me], c, __ATOMIC_RELEASE);
+    }
+    int off[MAX_RANKS + 1];
+    off[0] = 0;
+    for (int q = 0; q < R; q++) {
+        const double tw = wtime();
+        unsigned spins = 0;
+        while (__atomic_load_n(&sh.shm->seq[p][q], __ATOMIC_ACQUIRE) < c) {
+            if ((++spins & 0x3ffu) == 0u) {
+                if (wtime() - tw > 120.0) FATAL("gpunb_regf (i-slice mode): rank %d has not joined collective call %llu after 120 s", q, c);
+                sched_yield();
+            }
+        }
+        const ShmSlice &sl = sh.shm->slice[p][q];
+        if (sl.lmax != lmax || sl.nnbmax != nnbmax || sl.m_flag != m_flag)
+            FATAL("gpunb_regf (i-slice mode): rank %d passed lmax/nnbmax/m_flag = %d/%d/%d, this rank %d/%d/%d", q, sl.lmax, sl.nnbmax, sl.m_flag, lmax, nnbmax, m_flag);
+        off[q + 1] = off[q] + sl.ni;
+    }
+    const int tot = off[R];
+    const double wt_packed0 = wtime();
+    if (tot == 0) return;
+    if (tot > JOBCAP) FATAL("gpunb_regf (i-slice mode): %d i-particles in one collective call exceed the capacity %d", tot, JOBCAP);
+    // ---- union of the slices: [slice offsets | h2 | dtr | x | v] in pinned staging, one upload
+    int *hoff = reinterpret_cast<int *>(L.h_i);
+    for (int q = 0; q <= R; q++) hoff[q] = off[q];
+    double *h = L.h_i + 64;
+    for (int q = 0; q < R; q++) {
+        const ShmSlice &sl = sh.shm->slice[p][q];
+        const int n = sl.ni;
+        memcpy(h + off[q], sl.data, sizeof(double) * n);
+        memcpy(h + tot + off[q], sl.data + n, sizeof(double) * n);
+        memcpy(h + 2 * (size_t)tot + 3 * (size_t)off[q], sl.data + 2 * (size_t)n, sizeof(double) * 3 * n);
+        memcpy(h + 5 * (size_t)tot + 3 * (size_t)off[q], sl.data + 5 * (size_t)n, sizeof(double) * 3 * n);
+    }
+    const double wt_packed = wtime();
+    int nsub = L.nsub;
+    if (nsub > tot / 256) nsub = tot / 256;
+    const double pairs = (double)tot * L.nbody / R;          // rank-invariant: every rank cuts the same sub-blocks
+    if (!L.nsub_forced && nsub > (int)(pairs / L.sub_pairs)) nsub = (int)(pairs / L.sub_pairs);
+    if (nsub < 1) nsub = 1;
+    set_dev(root);
+    ensure_work_buffers(root, lmax, nnbmax, true, nsub, false);
+    CUDA_CHECK(cudaMemcpyAsync(root.ibuf, L.h_i, sizeof(double) * (64 + 8 * (size_t)tot), cudaMemcpyHostToDevice, root.st));
+    L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * (64.0 + 8.0 * tot);
+    const double *ib0 = root.ibuf + 64;
+    IBlock ib[1] = {IBlock{ib0, ib0 + tot, ib0 + 2 * (size_t)tot, ib0 + 5 * (size_t)tot}};
+    const int *ipm[1];
+    if (tot <= root.itile) {
+        ipm[0] = root.iperm_identity;
+    } else {
+        launch_isort(root, root.st, tot, tot, ib[0].xi, root.iperm, nullptr, reinterpret_cast<const int *>(root.ibuf), R);
+        ipm[0] = root.iperm;
+    }
+    Job j;
+    j.lmax = lmax; j.nnbmax = nnbmax; j.m_flag = m_flag; j.out_f = L.h_f_dev; j.out_list = L.h_list_dev;
+    j.own0 = off[me]; j.own1 = off[me + 1]; j.row_base = off[me];
+    bool direct_out = false;
+    if (ni > 0) {
+        double *a_acc = pinned_alias(acc, (size_t)3 * ni), *a_jrk = pinned_alias(jrk, (size_t)3 * ni), *a_pot = pinned_alias(pot, (size_t)ni);
+        int *a_list = pinned_alias(list, (size_t)ni * lmax);
+        if (a_acc && a_jrk && a_pot && a_list) {
+            direct_out = true;
+            j.abi_acc = a_acc; j.abi_jrk = a_jrk; j.abi_pot = a_pot; j.out_list = a_list; j.out_f = nullptr;
+        }
+    }
+    int soff[MAX_SLOTS + 1] = {0};
+    int nq = 0;
+    for (int q = 0; q < nsub && soff[nq] < tot; q++) {
+        int sz = (tot + nsub - 1) / nsub;
+        sz = (sz + 31) & ~31;
+        if (q == nsub - 1 || soff[nq] + sz > tot) sz = tot - soff[nq];
+        soff[nq + 1] = soff[nq] + sz;
+        nq++;
+    }
+    CUDA_CHECK(cudaEventRecord(root.ev_fork, root.st));
+    for (int q = 0; q < nq; q++) {
+        Slot &sl = root.slots[q];
+        CUDA_CHECK(cudaStreamWaitEvent(sl.lo, q == 0 ? root.ev_fork : root.slots[q - 1].ev_start, 0));
+        CUDA_CHECK(cudaEventRecord(sl.ev_start, sl.lo));
+        j.slot0 = soff[q]; j.nloc = soff[q + 1] - soff[q];
+        if (q == 0) CUDA_CHECK(cudaEventRecord(root.ev0, sl.lo));
+        run_job(j, ib, ipm, q, true, false);
+    }
+    CUDA_CHECK(cudaEventRecord(root.ev1, root.slots[nq - 1].lo));
+    CUDA_CHECK(cudaEventRecord(root.ev3, root.slots[nq - 1].hi));
+    L.ctr[GPUNB_B200_CTR_HOST_ENQUEUE_MS] += (wtime() - wt_packed) * 1e3;
+    const double tw = wtime();
+    for (int q = 0; q < nq; q++) CUDA_CHECK(cudaEventSynchronize(root.slots[q].ev_done));
+    for (int q = 0; q < nq; q++) CUDA_CHECK(cudaStreamWaitEvent(root.st, root.slots[q].ev_done, 0));
+    CUDA_CHECK(cudaEventSynchronize(root.ev3));
+    CUDA_CHECK(cudaEventSynchronize(root.ev1));
+    const double t0 = wtime();
+    if (ni > 0) {
+        if (!direct_out) scatter_rows(nullptr, 0, ni, lmax, acc, jrk, pot, list);
+        else {
+            double bytes = 0;
+            for (int i = 0; i < ni; i++) { const int cnt = list[(size_t)i * lmax]; bytes += 56.0 + 4.0 * (1 + (cnt > 0 ? cnt : 0)); }
+            L.ctr[GPUNB_B200_CTR_D2H_BYTES] += bytes;
+        }
+    }
+    const double wt = wtime();
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, root.ev0, root.ev1)); L.ctr[GPUNB_B200_CTR_GRAV_MS] += ms;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, root.ev1, root.ev3)); L.ctr[GPUNB_B200_CTR_MERGE_MS] += ms;
+    L.ctr[GPUNB_B200_CTR_GRAV_LAUNCHES] += 1;
+    L.time_grav += (wt - wt_in) - (wt - t0); L.time_reduce += wt - t0;
+    L.ctr[GPUNB_B200_CTR_HOST_PACK_MS] += (wt_packed - wt_in) * 1e3;
+    L.ctr[GPUNB_B200_CTR_HOST_RENDEZVOUS_MS] += (wt_packed0 - wt_in) * 1e3;
+    L.ctr[GPUNB_B200_CTR_HOST_WAIT_MS] += (t0 - tw) * 1e3;
+    L.ctr[GPUNB_B200_CTR_HOST_SCATTER_MS] += (wt - t0) * 1e3;
     L.last_ni = ni; L.last_lmax = lmax; L.last_on_host = true;
 }
 
@@ -2507,7 +2703,7 @@ void gpupot_(int *irank, int *istart, int *ni, int *n, double m[], double x[][3]
     lib_pot(*irank, *istart, *ni, *n, m, &x[0][0], pot);
 }
 
-int gpunb_b200_version(void) { return 103; }
+int gpunb_b200_version(void) { return 200; }
 int gpunb_b200_has_near_scalar_ab(void)
 {
 #ifdef NEAR_SCALAR_AB
@@ -2521,6 +2717,7 @@ const char *gpunb_b200_build_info(void)
     return "gpunb_b200 sm_100a: regf_kernel<TMA bulk Hilbert tiles TJ=64, packed f32x2 FAR body, scalar float-float NEAR body>, isort, merge (register bitonic), combine (NVLink peer pulls + flags), pot, tilepack";
 }
 int gpunb_b200_num_devices(void) { return (int)L.devs.size(); }
+int gpunb_b200_resident_warps(void) { return L.devs.empty() ? 0 : L.devs[0].warps_resident; }
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT])
 {
     if (L.devinit && !L.devs.empty() && L.devs[0].stats) {
@@ -2564,7 +2761,8 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
     Dev &root = L.devs[0];
     const int G = (int)L.devs.size();
     const int i0 = *i0p, ni = *nip, block = *blockp;
-    if (i0 < 0 || i0 + ni > root.nj_total || block < 1 || block > NIMAX) FATAL("gpunb_b200_sweep_resident: bad range");
+    if (i0 < 0 || i0 + ni > root.nj_total || block < 1 || block > JOBCAP) FATAL("gpunb_b200_sweep_resident: bad range");
+    if (block > NIMAX && G > 1) FATAL("gpunb_b200_sweep_resident: blocks of more than %d i-particles need one process per GPU", NIMAX);
     static int timeline = -1;
     if (timeline < 0) { const char *e = getenv("GPUNB_B200_TIMELINE"); timeline = (e && atoi(e) > 0 && L.devs.size() == 1) ? 1 : 0; }
     // Pipelined (default, one GPU per process): every block's Morton order comes from ONE batched isort launch, then
@@ -2573,7 +2771,7 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
     // measured: 2 slots are best on one GPU (1024.6 vs 1019.7 Gint/s with 3), 3-4 once an exchange step has to be hidden
     const int nslot = (G == 1 && !timeline) ? ((L.nslot_auto && !L.sh.on) ? 2 : L.nslot) : 1;
     const bool pipelined = nslot > 1;
-    for (int g = 0; g < G; g++) ensure_work_buffers(L.devs[g], *lmaxp, *nnbmaxp, g == 0, nslot, true);
+    for (int g = 0; g < G; g++) ensure_work_buffers(L.devs[g], *lmaxp, *nnbmaxp, g == 0, nslot, true, block);
     set_dev(root);
     const int nblocks = (ni + block - 1) / block;
     static std::vector<cudaEvent_t> tlev;
@@ -2660,6 +2858,7 @@ void gpunb_b200_fetch_last(int *n_last, double acc[][3], double jrk[][3], double
     const int ni = L.last_ni, lmax = L.last_lmax;
     *n_last = ni; *lmaxp = lmax;
     if (ni <= 0) return;
+    if (ni > NIMAX) FATAL("gpunb_b200_fetch_last: the last block holds %d rows, the host buffers %d", ni, NIMAX);
     if (!L.last_on_host) {         // a resident sweep leaves its last block in the slot's device buffers
         Dev &root = L.devs[0];
         set_dev(root);
@@ -2710,6 +2909,12 @@ void gpunb_b200_unpin_host_(void *ptr)
         }
 }
 void gpunb_b200_set_taper(int on) { L.taper = on != 0; }
+void gpunb_b200_set_sub_pairs(double pairs) { if (pairs >= 1.0) L.sub_pairs = pairs; }
+void gpunb_b200_set_islice(int on)
+{
+    if (on && !L.sh.on) FATAL("gpunb_b200_set_islice: the i-slice mode needs one process per GPU (gpunb_b200_nccl_init)");
+    L.sh.islice = on != 0;
+}
 void gpunb_b200_set_resort_every(int k) { if (k >= 1) { L.resort_every = k; L.snapshots_since_sort = 0; } }
 
 void gpunb_b200_set_tuning(int nslot, int nsub)
@@ -2781,11 +2986,29 @@ int gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128])
         if (e != cudaSuccess) FATAL("cudaIpcOpenMemHandle(rank %d) failed: %s (NVLink P2P between ranks is required)", r, cudaGetErrorString(e));
         sh.xbuf_peer[r] = (unsigned char *)p;
     }
+    // shared-memory segment of the node for the i-slice rendezvous (named after the unique id; unlinked once every
+    // rank has mapped it, so nothing is left behind if a rank dies)
+    char shm_name[64];
+    {
+        unsigned long long hsh = 1469598103934665603ull;
+        for (int k = 0; k < 128; k++) hsh = (hsh ^ id128[k]) * 1099511628211ull;
+        snprintf(shm_name, sizeof(shm_name), "/gpunb_b200_%016llx", hsh);
+        const int fd = shm_open(shm_name, O_CREAT | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t)sizeof(ShmSeg)) != 0) FATAL("cannot create the shared-memory segment %s of the i-slice mode", shm_name);
+        void *m = mmap(nullptr, sizeof(ShmSeg), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (m == MAP_FAILED) FATAL("cannot map the shared-memory segment %s", shm_name);
+        sh.shm = reinterpret_cast<ShmSeg *>(m);
+        sh.icall = 0;
+        const char *e = getenv("GPUNB_B200_ISLICE");
+        sh.islice = e && atoi(e) > 0;
+    }
     // every rank has zeroed its flags and mapped its peers before anybody can signal: one more all-gather as barrier
     dev_alloc(sh.scratch, 2 * (size_t)MAX_RANKS);
     rc = sh.allgather(sh.scratch + MAX_RANKS, sh.scratch, 1, NCCL_FLOAT64, sh.comm, d.st);
     if (rc != 0) FATAL("ncclAllGather(barrier) failed: %s", sh.errstr ? sh.errstr(rc) : "?");
     CUDA_CHECK(cudaStreamSynchronize(d.st));
+    if (rank == 0) shm_unlink(shm_name);
     sh.on = true;
     return 0;
 }
@@ -2807,6 +3030,8 @@ void gpunb_b200_nccl_finalize(void)
     dev_free(sh.scratch);
     CUDA_CHECK(cudaFree(sh.xbuf)); sh.xbuf = nullptr;
     sh.destroy(sh.comm);
+    if (sh.shm) { munmap(sh.shm, sizeof(ShmSeg)); sh.shm = nullptr; }
+    sh.islice = false;
     sh.comm = nullptr; sh.on = false; sh.R = 1; sh.rank = 0;
 }
 

@@ -23,12 +23,12 @@ _HERE = Path(__file__).resolve().parent
 _c_int_p = C.POINTER(C.c_int)
 _c_dbl_p = C.POINTER(C.c_double)
 
-N_COUNTERS = 24
+N_COUNTERS = 25
 CTR = dict(grav_ms=0, grav_launches=1, launches=2, h2d_bytes=3, d2h_bytes=4, interactions=5,
            merge_ms=6, pot_ms=7, near_tiles=8, all_tiles=9,
            tl_blocks=10, tl_isort_ms=11, tl_regf_ms=12, tl_merge_ms=13, tl_exch_ms=14,
            host_pack_ms=15, host_enqueue_ms=16, host_wait_ms=17, host_scatter_ms=18,
-           sends=19, send_ms=20, send_stage_ms=21, send_tiles_ms=22, transposed_tiles=23)
+           sends=19, send_ms=20, send_stage_ms=21, send_tiles_ms=22, transposed_tiles=23, host_rendezvous_ms=24)
 
 
 class LibraryMissing(RuntimeError):
@@ -77,6 +77,7 @@ class ForceLib:
             L.gpunb_b200_version.restype = C.c_int
             L.gpunb_b200_build_info.restype = C.c_char_p
             L.gpunb_b200_num_devices.restype = C.c_int
+            L.gpunb_b200_resident_warps.restype = C.c_int
             L.gpunb_b200_get_counters.argtypes = [_c_dbl_p]
             L.gpunb_b200_set_radii.argtypes = [_c_int_p, _c_dbl_p, _c_dbl_p]
             L.gpunb_b200_sweep_resident.argtypes = [_c_int_p] * 6
@@ -101,6 +102,10 @@ class ForceLib:
             L.gpunb_b200_set_resort_every.restype = None
             L.gpunb_b200_set_taper.argtypes = [C.c_int]
             L.gpunb_b200_set_taper.restype = None
+            L.gpunb_b200_set_islice.argtypes = [C.c_int]
+            L.gpunb_b200_set_islice.restype = None
+            L.gpunb_b200_set_sub_pairs.argtypes = [C.c_double]
+            L.gpunb_b200_set_sub_pairs.restype = None
             L.gpunb_b200_set_tuning.argtypes = [C.c_int, C.c_int]
             L.gpunb_b200_set_tuning.restype = None
             L.gpunb_b200_state_all_.argtypes = [_c_int_p] + [_c_dbl_p] * 6
@@ -240,6 +245,10 @@ class ForceLib:
         self._need_b200()
         return int(self.lib.gpunb_b200_num_devices())
 
+    def resident_warps(self) -> int:
+        self._need_b200()
+        return int(self.lib.gpunb_b200_resident_warps())
+
     def counters(self) -> dict:
         self._need_b200()
         buf = np.zeros(N_COUNTERS)
@@ -344,6 +353,17 @@ class ForceLib:
         """Hilbert order refreshed every k-th snapshot only (1 = always, the default)."""
         self._need_b200()
         self.lib.gpunb_b200_set_resort_every(k)
+
+    def set_islice(self, on: int):
+        """i-slice mode of the multi-process library: gpunb_regf_ becomes a collective call, every rank passes its own
+        i-slice (possibly empty) and receives the results of that slice only."""
+        self._need_b200()
+        self.lib.gpunb_b200_set_islice(int(on))
+
+    def set_sub_pairs(self, pairs: float):
+        """Pairs a sub-block of gpunb_regf_ must keep for the call to be split (default 1.5e8)."""
+        self._need_b200()
+        self.lib.gpunb_b200_set_sub_pairs(float(pairs))
 
     def set_taper(self, on: int):
         """Sub-block sizes of one gpunb_regf_ call: equal (0, default) or tapering (1)."""

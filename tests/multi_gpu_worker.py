@@ -81,6 +81,93 @@ def check(lib, tag, rank=0):
     print(f"{tag} rank {rank}: ok", flush=True)
 
 
+def check_auto_subblocks(lib, tag, rank, world):
+    """the number of sub-blocks (= exchange steps) of one gpunb_regf_ call must be the same on every rank even
+    though the shards differ by a tile.  n = 20011 gives 313 tiles (157 / 156 at two ranks); with the threshold lowered to
+    3e6 pairs, ni = 600 put the rank-local pair counts on either side of a multiple of the threshold (the old rule cut the
+    call into 2 sub-blocks on rank 0 and 1 on rank 1: wrong rows or a hang)."""
+    import oracle_lib
+    from nbody6ppgpu_b200 import snapshots as S
+    o = oracle_lib.Oracle()
+    n = 20011
+    m, x, v = S.plummer(n, 31, "kroupa")
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 150.0))
+    lib.open(n + 10, rank)
+    lib.send(m, x, v)
+    lib.set_tuning(0, 4)
+    try:
+        for thr, ni in ((3.0e6, 600), (1.5e6 * 4 / world, 600), (2.0e6, 900), (1.0e6, 1200)):
+            lib.set_sub_pairs(thr)
+            isel = slice(100, 100 + ni)
+            acc, jrk, pot, lst = lib.regf(h2[isel], dtr[isel], x[isel], v[isel], 400, 350, 0)
+            a64, j64, p64, l64, band, _ = o.regf_f64(m, x, v, h2[isel], dtr[isel], x[isel], v[isel], 400, 350, 0, 4.0)
+            bad = [i for i in oracle_lib.list_rows_equal(lst, l64) if band[i] > 4.0]
+            assert not bad, (tag, thr, ni, bad[:5])
+            assert max(oracle_lib.relerr(acc, a64), oracle_lib.relerr(pot, p64)) <= 1e-6, (tag, thr, ni)
+    finally:
+        lib.set_sub_pairs(1.5e8)
+        lib.close()
+    print(f"{tag} rank {rank}: auto sub-blocks ok", flush=True)
+
+
+def check_islice(lib, tag, rank, world):
+    """i-slice mode: gpunb_regf_ as a collective call -- every rank passes ITS OWN i-slice (ragged sizes, one rank empty)
+    and receives its own rows; checked against the oracle on the rank's slice, staged and with pinned caller arrays, with
+    one and several sub-blocks (exchange steps), for both neighbour criteria."""
+    import oracle_lib
+    from nbody6ppgpu_b200 import snapshots as S
+    o = oracle_lib.Oracle()
+    n = 20011
+    m, x, v = S.plummer(n, 37, "kroupa")
+    sizes_all = [[1024] * world, [1 + (311 * (r + 1)) % 1000 for r in range(world)], [0 if r == world - 1 else 700 + r for r in range(world)],
+                 [2048 if r == 0 else 5 for r in range(world)], [3 if r == 1 % world else 0 for r in range(world)], [0] * world]
+    for m_flag, lmax, nnbmax in ((0, 400, 350), (1, 128, 60)):
+        h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 150.0), 0.125, m_flag)
+        lib.open(n + 10, rank)
+        lib.set_islice(1)
+        lib.send(m, x, v)
+        try:
+            for case, sizes in enumerate(sizes_all):
+                start = 17 * case + sum(sizes[:rank]) + 50 * rank           # disjoint slices, different on every rank
+                ni = sizes[rank]
+                idx = (start + 3 * np.arange(ni)) % n                          # a strided gather
+                for nsub in (1, -3):
+                    lib.set_tuning(0, nsub)
+                    acc, jrk, pot, lst = lib.regf(h2[idx], dtr[idx], x[idx], v[idx], lmax, nnbmax, m_flag)
+                    if ni == 0:
+                        continue
+                    a64, j64, p64, l64, band, _ = o.regf_f64(m, x, v, h2[idx], dtr[idx], x[idx], v[idx], lmax, nnbmax, m_flag, 4.0)
+                    bad = [i for i in oracle_lib.list_rows_equal(lst, l64) if band[i] > 4.0]
+                    assert not bad, (tag, "islice", case, nsub, m_flag, bad[:5])
+                    ok = lst[:, 0] >= 0
+                    if oracle_lib.list_rows_equal(lst, l64):
+                        a64, j64, p64 = o.regf_f64_given_list(m, x, v, x[idx], v[idx], np.where(ok[:, None], lst, l64))
+                    ea, ep = oracle_lib.relerr(acc, a64), oracle_lib.relerr(pot, p64)
+                    ej = oracle_lib.relerr_scaled(jrk, j64, o.scale[:, 1])
+                    assert max(ea, ej, ep) <= 1e-6, (tag, "islice", case, nsub, ea, ej, ep)
+            # pinned caller arrays: bit for bit the staged rows
+            ni = 300 + 100 * rank
+            i0 = 4000 + 1000 * rank
+            call = lib.block_caller(h2, dtr, x, v, 2048, lmax, nnbmax, m_flag)
+            lib.set_tuning(0, 1)
+            staged = [a.copy() for a in call(i0, ni)]
+            pinned = list(call.outputs)
+            assert lib.pin_host(*pinned)
+            try:
+                for a in call.outputs:
+                    a[...] = 0
+                res = [a.copy() for a in call(i0, ni)]
+            finally:
+                lib.unpin_host(*pinned)
+            for q in range(4):
+                assert np.array_equal(res[q], staged[q]), (tag, "islice pinned", q)
+        finally:
+            lib.set_islice(0)
+            lib.set_tuning(0, 4)
+            lib.close()
+    print(f"{tag} rank {rank}: i-slice mode ok", flush=True)
+
+
 def main():
     mode = sys.argv[1]
     if mode == "inproc":
@@ -107,6 +194,8 @@ def main():
         check_pinned(lib, f"nccl x{world}", rank)
         if not os.environ.get("WORKER_ONLY_PINNED"):
             check(lib, f"nccl x{world}", rank)      # every rank checks: results are replicated
+            check_auto_subblocks(lib, f"nccl x{world}", rank, world)
+            check_islice(lib, f"nccl x{world}", rank, world)
         dist.barrier()
         lib.nccl_finalize()
         dist.destroy_process_group()
