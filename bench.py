@@ -54,7 +54,7 @@ UNIT = "Gint/s"
 LMAX, NNBMAX, BLOCK = 600, 550, 1024          # --with-par=1m: LMAX=600 (configure.ac:390-394); NNBMAX=min(N/2,LMAX-50)
 NNB_TARGET = 200.0
 FLOP_PER_INT = 60.0                           # reference convention, gpunb.velocity.cu:894
-NSLOT = int(os.environ.get("GPUNB_B200_NSLOT", "0"))     # pipeline slots of the resident sweep (0: library default, 2 on one GPU / 3 sharded)
+NSLOT = int(os.environ.get("GPUNB_B200_NSLOT", "0"))     # pipeline slots of the resident sweep (0: library default, 3)
 NSUB = int(os.environ.get("GPUNB_B200_NSUB", "4"))       # sub-blocks of one gpunb_regf_ call
 
 
@@ -546,9 +546,11 @@ def main():
         lib.open(n2 + 10, rank)
         lib.send(m2, x2, v2)
         lib.set_radii(h22, dtr2)
+        # small j-sets: fewer, larger launch groups (the block of a resident sweep is free; 4736 = 32 x 148 i-tiles)
+        sb2 = BLOCK if n2 > 65536 else 4736
         for _ in range(2):
-            lib.sweep_resident(0, n2, BLOCK, LMAX, NNBMAX, m_flag2)
-        ms = min(lib.sweep_resident(0, n2, BLOCK, LMAX, NNBMAX, m_flag2) for _ in range(3))
+            lib.sweep_resident(0, n2, sb2, LMAX, NNBMAX, m_flag2)
+        ms = min(lib.sweep_resident(0, n2, sb2, LMAX, NNBMAX, m_flag2) for _ in range(3))
         call2 = lib.block_caller(h22, dtr2, x2, v2, BLOCK, LMAX, NNBMAX, m_flag2)
         pinned2 = [m2, x2, v2, *call2.outputs]
         kind2 = "pinned" if lib.pin_host(*pinned2) else "pageable"
@@ -566,7 +568,7 @@ def main():
         lib.unpin_host(*pinned2)
         lib.close()
         val2 = float(n2) * n2 / (ms * 1e-3) * 1e-9
-        return {"n": n2, "m_flag": m_flag2, "value": val2, "e2e": float(n2) * n2 / te * 1e-9, "unit": UNIT, "ms_per_sweep": ms,
+        return {"n": n2, "m_flag": m_flag2, "sweep_block": sb2, "value": val2, "e2e": float(n2) * n2 / te * 1e-9, "unit": UNIT, "ms_per_sweep": ms,
                 "frac_of_sweep": val2 / (2.0 * 128 * 148 * 1965e6 / FLOP_PER_INT * 1e-9), "host_arrays": kind2}
 
     configs = None
@@ -640,7 +642,7 @@ def main():
         "config": bench_config(n, args.m_flag, rs0, world),
         "sample": f"send + every i-block of the sweep ({nblk} blocks of {BLOCK}) against all {n} j per step",
         "run": {"ni_per_step": ni_total, "sweep_block": sblock, "mean_nnb": mean_nnb, "interactions_per_step": inter_step,
-                "pipeline": {"sweep_slots": NSLOT if NSLOT else (2 if world == 1 else 3), "regf_subblocks": NSUB}},
+                "pipeline": {"sweep_slots": NSLOT if NSLOT else 3, "regf_subblocks": NSUB}},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                 "ms_per_step": e2e_s * 1e3, "api": e2e_api, "host_arrays": host_kind, "mode": "single process" if world == 1 else "i-slice (collective calls)"},

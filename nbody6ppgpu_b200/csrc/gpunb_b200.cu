@@ -173,7 +173,7 @@ __global__ void absmax_kernel(int n, const double *__restrict__ m, const double 
     }
     a = warp_max(a);
     if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(out, __float_as_uint(a));
-    if (bad) atomicExch(nanflag, 1);
+    if (bad) *(volatile int *)nanflag = 1;            // mapped host memory: the host reads it after the stream sync
 }
 
 __device__ __forceinline__ unsigned long long spread21(unsigned v)
@@ -221,6 +221,60 @@ __global__ void mortonkey_kernel(int n, const double *__restrict__ x, const unsi
     vals[j] = j;
 }
 
+// Small j-sets (n <= SMALLSORT_MAX): |x|max, NaN check, Hilbert keys and the sort in ONE launch of ONE CTA.  At N = 10^4 the
+// nine launches of the general path (memset, absmax, keys, CUB histogram / scan / 4-5 onesweep passes) are nothing but
+// launch latency: 72 us of the 150 us of a gpunb_send_, against 68 us for the reference's whole call
+// (profiles/r2c_small_n.txt).  Composite key = (leading 3 b bits of the Hilbert key) << 14 | index, sorted by a bitonic
+// network in shared memory: the index in the low bits reproduces the STABLE order of the radix sort, so the tile order
+// -- and with it every sum -- is the same function of the snapshot on both paths.
+constexpr int SMALLSORT_MAX = 16384;
+__global__ void __launch_bounds__(1024) smallsort_kernel(int n, int n2, int keybits, const double *__restrict__ m,
+                                                          const double *__restrict__ x, const double *__restrict__ v,
+                                                          unsigned *__restrict__ hbits, int *__restrict__ perm, int *__restrict__ nanflag)
+{
+    extern __shared__ unsigned long long skey[];       // n2 composite keys
+    __shared__ float wmax[32];
+    const int t = threadIdx.x;
+    float a = 0.f;
+    bool bad = false;
+    for (int j = t; j < n; j += 1024) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double xd = x[3 * (size_t)j + k];
+            a = fmaxf(a, fabsf((float)xd));
+            bad |= (xd != xd);
+            if (v) { const double vd = v[3 * (size_t)j + k]; bad |= (vd != vd); }
+        }
+        const double md = m[j];
+        bad |= (md != md);
+    }
+    if (bad) *(volatile int *)nanflag = 1;
+    a = warp_max(a);
+    if ((t & 31) == 0) wmax[t >> 5] = a;
+    __syncthreads();
+    a = warp_max(wmax[t & 31]);
+    if (t == 0) *hbits = __float_as_uint(a);           // isort_kernel scales the i-block with the same extent
+    const float H = fmaxf(a, 1e-30f);
+    for (int j = t; j < n2; j += 1024) {
+        unsigned long long k = ~0ull;
+        if (j < n) k = ((morton_key(x[3 * (size_t)j], x[3 * (size_t)j + 1], x[3 * (size_t)j + 2], H) >> (63 - keybits)) << 14) | (unsigned)j;
+        skey[j] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = t; k < (n2 >> 1); k += 1024) {
+                const int lo = 2 * k - (k & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long p = skey[lo], q = skey[hi];
+                if ((p > q) == up) { skey[lo] = q; skey[hi] = p; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = t; j < n; j += 1024) perm[j] = (int)(skey[j] & 0x3fffull);
+}
+
 // One warp per tile: gathers its 64 particles through the sort permutation, finds the bounding boxes,
 // writes header + arrays.  Ghost slots of the last tile replicate the tile's first particle with mass 0
 // and index -1 (never listed, no force).  v may be NULL (gpupot tiles).
@@ -251,7 +305,7 @@ __global__ void __launch_bounds__(128) tilepack_kernel(int n, int t0, int tstrid
         }
         pm[h] = real ? (float)m[src] : 0.f;
         if (pm[h] != pm[h] || px[h][0] != px[h][0] || px[h][1] != px[h][1] || px[h][2] != px[h][2] ||
-            pv[h][0] != pv[h][0] || pv[h][1] != pv[h][1] || pv[h][2] != pv[h][2]) atomicExch(nanflag, 1);
+            pv[h][0] != pv[h][0] || pv[h][1] != pv[h][1] || pv[h][2] != pv[h][2]) *(volatile int *)nanflag = 1;
         mmax = fmaxf(mmax, pm[h]);
         jidx[l * TJ + h * 32 + lane] = real ? src : -1;
     }
@@ -1003,6 +1057,7 @@ __device__ __forceinline__ void wait_all_ranks(const unsigned long long *flags, 
 struct MergeArgs {
     const double *part; const int *cnt; const int *seg;
     int nloc, S, segcap, lmax, nnbmax;
+    int kl0, kl1;       // this launch merges the local slots [kl0, kl1) (the whole job unless the delivery is cut into parts)
     const int *iperm;   // output row of local slot kl: i = iperm[kl] (the caller passes iperm + slot0); NULL: i = kl
     double *res_f;      // [.][f_stride]; f_stride = 8 stores the (signed) count in slot 7 for the shard combine
     double *abi_acc, *abi_jrk, *abi_pot;   // non-NULL: final sums go straight to the caller's acc[.][3] / jrk[.][3] / pot[.]
@@ -1071,8 +1126,8 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
 {
     __shared__ int sbuf[4][SORT_CAP];
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int kl = blockIdx.x * 4 + wq;
-    if (kl < a.nloc) {
+    const int kl = a.kl0 + blockIdx.x * 4 + wq;
+    if (kl < a.kl1) {
         if (a.acks) wait_all_ranks(a.acks, a.R, a.ack_need, lane);
         merge_row(a, kl, lane, sbuf[wq]);
     }
@@ -1428,7 +1483,7 @@ struct Dev {
     int segcap = 0;
     double *fr = nullptr;         // [NIMAX][8] shard partial + count (multi-GPU)
     int *rows = nullptr; size_t rows_ints = 0;                                     // shard rows (in-process multi-GPU)
-    int *nanflag = nullptr;
+    int *nanflag = nullptr;       // device alias of this device's entry of L.h_nan (mapped pinned host memory)
     double *pot_part = nullptr, *pot_out = nullptr; size_t pot_part_n = 0, pot_out_n = 0;
     // gpupot's own snapshot (m | x) and tiles of this device's shard, so that gpupot never disturbs the regf j-set
     double *pot_jraw = nullptr; float *pot_jtile = nullptr; int *pot_jidx = nullptr; int pot_cap = 0;
@@ -1486,6 +1541,7 @@ struct Lib {
     int *h_list = nullptr, *h_list_dev = nullptr; size_t h_list_n = 0;
     int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
+    int *h_nan = nullptr;          // [MAX_RANKS] NaN flags written by the tile kernels straight into host memory
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
     int resort_every = 1;          // Hilbert order refreshed every k-th snapshot (GPUNB_B200_RESORT_EVERY); 1 = always
     double sub_pairs = 1.5e8;      // pairs a sub-block of gpunb_regf_ must keep (GPUNB_B200_SUB_PAIRS)
@@ -1594,6 +1650,13 @@ void lib_devinit(int irank)
     CUDA_CHECK(cudaSetDevice(L.devs[0].id));
     host_alloc(L.h_flag, 16);
     memset(L.h_flag, 0, 16 * sizeof(int));
+    CUDA_CHECK(cudaHostAlloc((void **)&L.h_nan, MAX_RANKS * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(L.h_nan, 0, MAX_RANKS * sizeof(int));
+    for (size_t g = 0; g < L.devs.size(); g++) {
+        CUDA_CHECK(cudaSetDevice(L.devs[g].id));
+        CUDA_CHECK(cudaHostGetDevicePointer((void **)&L.devs[g].nanflag, (void *)(L.h_nan + g), 0));
+    }
+    CUDA_CHECK(cudaSetDevice(L.devs[0].id));
     { const char *e = getenv("GPUNB_B200_NSLOT"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) { L.nslot = atoi(e); L.nslot_auto = false; } }
     { const char *e = getenv("GPUNB_B200_NSUB");  if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nsub = atoi(e); }
     { const char *e = getenv("GPUNB_B200_TAPER"); if (e) L.taper = atoi(e) != 0; }
@@ -1677,6 +1740,22 @@ void build_tiles(Dev &d, int n, const double *m, const double *x, const double *
         if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag);
         CUDA_CHECK(cudaGetLastError());
         L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+        return;
+    }
+    static int smallsort = -1;
+    if (smallsort < 0) {
+        const char *e = getenv("GPUNB_B200_SMALLSORT");
+        smallsort = (e && atoi(e) == 0) ? 0 : 1;
+        CUDA_CHECK(cudaFuncSetAttribute(smallsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALLSORT_MAX * 8));
+    }
+    if (smallsort && n <= SMALLSORT_MAX) {          // one launch instead of eight (same order: stable on the leading key bits)
+        int n2 = 2048;
+        while (n2 < n) n2 <<= 1;
+        smallsort_kernel<<<1, 1024, (size_t)n2 * 8, d.st>>>(n, n2, 3 * hilbert_bits(n), m, x, v, d.hbits, d.perm, d.nanflag);
+        d.perm_n = n;
+        if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag);
+        CUDA_CHECK(cudaGetLastError());
+        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
         return;
     }
     CUDA_CHECK(cudaMemsetAsync(d.hbits, 0, sizeof(unsigned), d.st));
@@ -1790,7 +1869,6 @@ void lib_open(int nbmax, int irank)
         }
         if (!d.stats && getenv("GPUNB_B200_STATS")) { dev_alloc(d.stats, 4); CUDA_CHECK(cudaMemsetAsync(d.stats, 0, 32, d.st)); }
         if (!d.wtime && getenv("GPUNB_B200_STATS") && atoi(getenv("GPUNB_B200_STATS")) >= 2) dev_alloc(d.wtime, (size_t)3 * 65536);
-        if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
     }
     const size_t hj = (size_t)7 * ((size_t)nbmax + 64);
     if (hj > L.h_j_n) { host_free(L.h_j); L.h_j_n = hj; host_alloc(L.h_j, hj); }
@@ -1818,7 +1896,6 @@ void lib_close()
         dev_free(d.state); d.state_cap = d.state_n = 0; dev_free(d.upd_rec); dev_free(d.upd_idx); dev_free(d.upd_bad); d.upd_cap = 0;
         dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.iperm_identity); dev_free(d.stats); dev_free(d.wtime);
         dev_free(d.jidx);
-        dev_free(d.nanflag);
     }
     host_free(L.h_j); L.h_j_n = 0; host_free(L.h_i); host_free(L.h_f); host_free(L.h_list); L.h_list_n = 0;
     host_free(L.h_iperm); host_free(L.h_upd); host_free(L.h_upd_idx); L.h_upd_cap = 0;
@@ -1872,7 +1949,17 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
             CUDA_CHECK(cudaMemcpyAsync(d.jraw + 4 * (size_t)nj, vj, sizeof(double) * 3 * nj, cudaMemcpyHostToDevice, d.st));
         }
     }
-    for (int c0 = 0; c0 < nj && !direct; c0 += CHUNK) {
+    if (!direct && nj <= CHUNK) {
+        // small snapshot: one chunk, whose staging layout (m | x | v) IS the device layout -- two uploads, the first in
+        // flight while the velocities are staged
+        const size_t n4 = 4 * (size_t)nj, n3 = 3 * (size_t)nj;
+        memcpy(h, mj, sizeof(double) * nj);
+        memcpy(h + nj, xj, sizeof(double) * n3);
+        for (Dev &d : L.devs) { set_dev(d); CUDA_CHECK(cudaMemcpyAsync(d.jraw, h, sizeof(double) * n4, cudaMemcpyHostToDevice, d.st)); }
+        memcpy(h + n4, vj, sizeof(double) * n3);
+        for (Dev &d : L.devs) { set_dev(d); CUDA_CHECK(cudaMemcpyAsync(d.jraw + n4, h + n4, sizeof(double) * n3, cudaMemcpyHostToDevice, d.st)); }
+    }
+    for (int c0 = 0; c0 < nj && !direct && nj > CHUNK; c0 += CHUNK) {
         const size_t c = (size_t)c0, n = (size_t)((nj - c0 < CHUNK) ? nj - c0 : CHUNK);
         threaded_copy(h + c, mj + c, n);
         threaded_copy(h + nj + 3 * c, xj + 3 * c, 3 * n);
@@ -1902,12 +1989,11 @@ void finish_send(int nj, double wt0, const char *who)
         CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
         build_tiles(d, nj, d.jraw, d.jraw + nj, d.jraw + 4 * (size_t)nj, d.jtile, d.jidx, L.sh.on ? L.sh.rank : (int)g, R, d.ntiles, reuse);
         CUDA_CHECK(cudaEventRecord(d.evs1, d.st));
-        CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, d.nanflag, sizeof(int), cudaMemcpyDeviceToHost, d.st));
     }
     for (size_t g = 0; g < L.devs.size(); g++) {
         set_dev(L.devs[g]);
         CUDA_CHECK(cudaStreamSynchronize(L.devs[g].st));
-        if (L.h_flag[g]) FATAL("%s: NaN in j-particle data (reference asserts here, gpunb.velocity.cu:72-78)", who);
+        if (L.h_nan[g]) FATAL("%s: NaN in j-particle data (reference asserts here, gpunb.velocity.cu:72-78)", who);
     }
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, L.devs[0].evs0, L.devs[0].evs1));
@@ -2129,6 +2215,7 @@ struct Job {
     // i-slice mode (collective gpunb_regf_, one process per GPU): this rank combines and receives only the sorted slots
     // [own0, own1) of the block -- its own i-slice -- and its result rows are numbered from row_base
     int own0 = 0, own1 = INT_MAX, row_base = 0;
+    int merge_parts = 1;               // single GPU: merge launches (delivery parts) of this job
 };
 
 // Pair kernel (stream lo) + shard-local merge (stream hi) of one job on device d, pipeline slot sl.
@@ -2157,8 +2244,17 @@ void launch_regf(Dev &d, Slot &sl, cudaStream_t lo, cudaStream_t hi, const Job &
     }
     m.part = sl.part; m.cnt = sl.cnt; m.seg = sl.seg; m.nloc = j.nloc; m.S = p.S; m.segcap = d.segcap;
     m.lmax = j.lmax; m.nnbmax = j.nnbmax;
-    merge_kernel<<<(j.nloc + 3) / 4, 128, 0, hi>>>(m);
+    // delivery in parts (single GPU, staged results): one merge launch per part, an event behind each, so that the host
+    // copies the rows of part p into the caller's arrays while part p+1 is being merged
+    const int parts = (j.merge_parts > 1 && !m.sig.done_ctr) ? j.merge_parts : 1;
+    for (int q = 0; q < parts; q++) {
+        m.kl0 = (int)((long long)j.nloc * q / parts) & ~3;
+        m.kl1 = q == parts - 1 ? j.nloc : (int)((long long)j.nloc * (q + 1) / parts) & ~3;
+        if (m.kl1 > m.kl0) merge_kernel<<<(m.kl1 - m.kl0 + 3) / 4, 128, 0, hi>>>(m);
+        if (parts > 1) CUDA_CHECK(cudaEventRecord(d.slots[q].ev_start, hi));        // idle events of the unused pipeline slots
+    }
     CUDA_CHECK(cudaGetLastError());
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += parts - 1;
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev2, hi));
     if (tl) CUDA_CHECK(cudaEventRecord(tl[3], hi));
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
@@ -2353,14 +2449,31 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     double t_scatter = 0.0;
     if (nsub == 1) {
         j.slot0 = 0; j.nloc = ni;
+        // staged results of a large block on one GPU: delivered in parts, the host copy of part p beside the merge of p+1
+        const int parts = (G == 1 && !L.sh.on && !direct_out && ni >= 512) ? (ni >= 1024 ? 4 : 2) : 1;
+        j.merge_parts = parts;
         run_job(j, ib, ipm, 0, false, true);
-        const double tw = wtime();
-        CUDA_CHECK(cudaStreamSynchronize(root.st));
-        const double t0 = wtime();
-        t_wait = t0 - tw;
-        L.ctr[GPUNB_B200_CTR_HOST_ENQUEUE_MS] += (tw - wt_packed) * 1e3;
-        deliver(0, ni);
-        t_scatter = wtime() - t0;
+        L.ctr[GPUNB_B200_CTR_HOST_ENQUEUE_MS] += (wtime() - wt_packed) * 1e3;
+        if (parts > 1) {
+            for (int q = 0; q < parts; q++) {
+                const int k0 = (int)((long long)ni * q / parts) & ~3;
+                const int k1 = q == parts - 1 ? ni : (int)((long long)ni * (q + 1) / parts) & ~3;
+                const double tw = wtime();
+                CUDA_CHECK(cudaEventSynchronize(root.slots[q].ev_start));
+                const double t0 = wtime();
+                t_wait += t0 - tw;
+                if (k1 > k0) deliver(k0, k1);
+                t_scatter += wtime() - t0;
+            }
+            CUDA_CHECK(cudaStreamSynchronize(root.st));
+        } else {
+            const double tw = wtime();
+            CUDA_CHECK(cudaStreamSynchronize(root.st));
+            const double t0 = wtime();
+            t_wait = t0 - tw;
+            deliver(0, ni);
+            t_scatter = wtime() - t0;
+        }
     } else {
         // Whole i-tiles per sub-block, equal sizes by default.  Tapering sizes (weights 7:5:3:1 for four, so that what
         // stays exposed at the end of the call -- the unfilled tail of the last pair kernel, its merge and the host copy
@@ -2602,7 +2715,6 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
             dev_alloc(d.pot_jraw, (size_t)4 * d.pot_cap); dev_alloc(d.pot_jtile, (size_t)(ntiles_all + 2) * TILE_FLOATS);
             dev_alloc(d.pot_jidx, (size_t)(ntiles_all + 2) * TJ);        // sized for R = 1: R may change between calls
         }
-        if (!d.nanflag) { dev_alloc(d.nanflag, 1); CUDA_CHECK(cudaMemsetAsync(d.nanflag, 0, sizeof(int), d.st)); }
         CUDA_CHECK(cudaMemcpyAsync(d.pot_jraw, hpin, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, d.st));
         build_tiles(d, n, d.pot_jraw, d.pot_jraw + n, nullptr, d.pot_jtile, d.pot_jidx, L.sh.on ? L.sh.rank : g, R, nloc);
         d.perm_n = 0;                              // the sort scratch now holds gpupot's order
@@ -2647,14 +2759,10 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
     CUDA_CHECK(cudaEventRecord(root.evs1, root.st));
     double *hout = hpin + 4 * (size_t)n;
     CUDA_CHECK(cudaMemcpyAsync(hout, result, sizeof(double) * ni, cudaMemcpyDeviceToHost, root.st));
-    for (int g = 0; g < G; g++) {
-        set_dev(L.devs[g]);
-        CUDA_CHECK(cudaMemcpyAsync(L.h_flag + g, L.devs[g].nanflag, sizeof(int), cudaMemcpyDeviceToHost, L.devs[g].st));
-    }
     for (int g = G - 1; g >= 0; g--) {
         set_dev(L.devs[g]);
         CUDA_CHECK(cudaStreamSynchronize(L.devs[g].st));
-        if (L.h_flag[g]) FATAL("gpupot: NaN in particle data");
+        if (L.h_nan[g]) FATAL("gpupot: NaN in particle data");
     }
     float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, root.evs0, root.evs1));
     L.ctr[GPUNB_B200_CTR_POT_MS] += ms;
@@ -2768,8 +2876,9 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
     // Pipelined (default, one GPU per process): every block's Morton order comes from ONE batched isort launch, then
     // the blocks cycle through nslot pipeline slots (see Slot).  Sequential (GPUNB_B200_NSLOT=1, the per-kernel
     // timeline, or one process driving several GPUs): one block after the other on the main stream.
-    // measured: 2 slots are best on one GPU (1024.6 vs 1019.7 Gint/s with 3), 3-4 once an exchange step has to be hidden
-    const int nslot = (G == 1 && !timeline) ? ((L.nslot_auto && !L.sh.on) ? 2 : L.nslot) : 1;
+    // measured (profiles/r2c_sweep_probe.txt): with 2 slots the stagger of consecutive launches can collapse (945 ... 1042
+    // Gint/s between runs of the same sweep), 3 and 4 slots hold 1035-1039 on one GPU and hide the exchange step when sharded
+    const int nslot = (G == 1 && !timeline) ? L.nslot : 1;
     const bool pipelined = nslot > 1;
     for (int g = 0; g < G; g++) ensure_work_buffers(L.devs[g], *lmaxp, *nnbmaxp, g == 0, nslot, true, block);
     set_dev(root);

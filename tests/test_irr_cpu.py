@@ -1,7 +1,7 @@
-"""Irregular-force interface (DRAFT).  CPU: the fp64 statement nbody6ppgpu_b200/irr.py:firr_f64 is
-pinned against the reference's own AVX library (oracle/_ref/libirr_ref_avx.so, compiled from src/Main/irr.avx.cpp), and
-the draft CUDA library exports the reference's six symbols.  GPU: gated behind IRR_B200_VALIDATE=1 until the kernel has
-been validated on hardware (no GPU budget was left for it in round 1)."""
+"""Irregular-force interface.  CPU: the fp64 statement nbody6ppgpu_b200/irr.py:firr_f64 is pinned
+against the reference's own AVX library (oracle/_ref/libirr_ref_avx.so, compiled from src/Main/irr.avx.cpp), and the CUDA
+library exports the reference's six symbols.  GPU: the CUDA library against the fp64 statement (validated on B200 in
+session r2a: forces to 2e-14, nearest-neighbour addresses identical)."""
 import ctypes
 import os
 import re
@@ -60,7 +60,7 @@ def test_fp64_statement_is_pinned_against_the_reference_library():
     assert np.array_equal(nn, n64)
 
 
-def test_draft_cuda_library_exports_the_reference_symbols():
+def test_cuda_library_exports_the_reference_symbols():
     so = irr.lib_path()
     assert so.exists(), "libirr_b200.so not built: run __graft_entry__.build()"
     hdr = (ROOT / "include" / "irr_b200.h").read_text()
@@ -73,7 +73,6 @@ def test_draft_cuda_library_exports_the_reference_symbols():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("IRR_B200_VALIDATE") != "1", reason="draft kernel: validation on a GPU pending (IRR_B200_VALIDATE=1)")
 def test_cuda_library_against_the_fp64_statement():
     case = make_case()
     acc, jrk, nn = run(irr.IrrLib(irr.lib_path()), case)
