@@ -165,6 +165,9 @@ void  gpunb_b200_set_islice(int on);
 
 /* Pairs (i x local j) a sub-block of gpunb_regf_ must keep for the call to be split (default 1.5e8; tests lower it). */
 void  gpunb_b200_set_sub_pairs(double pairs);
+/* gpunb_regf_ calls with fewer than `pairs` (ni x nj) pairs keep the caller's order of the i-block instead of Morton-sorting
+ * it (default 2.5e7: the sort would add more latency than it saves; 0 = always sort).  Environment: GPUNB_B200_ISORT_PAIRS. */
+void  gpunb_b200_set_isort_pairs(double pairs);
 
 /* Sub-block sizes of one gpunb_regf_ call: 0 = equal (default), 1 = tapering (weights 7:5:3:1 for four sub-blocks;
  * measured, no gain).  Environment: GPUNB_B200_TAPER. */

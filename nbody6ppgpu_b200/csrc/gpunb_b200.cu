@@ -50,6 +50,7 @@
 // on the same slots.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/block/block_radix_sort.cuh>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -224,15 +225,20 @@ __global__ void mortonkey_kernel(int n, const double *__restrict__ x, const unsi
 // Small j-sets (n <= SMALLSORT_MAX): |x|max, NaN check, Hilbert keys and the sort in ONE launch of ONE CTA.  At N = 10^4 the
 // nine launches of the general path (memset, absmax, keys, CUB histogram / scan / 4-5 onesweep passes) are nothing but
 // launch latency: 72 us of the 150 us of a gpunb_send_, against 68 us for the reference's whole call
-// (profiles/r2c_small_n.txt).  Composite key = (leading 3 b bits of the Hilbert key) << 14 | index, sorted by a bitonic
-// network in shared memory: the index in the low bits reproduces the STABLE order of the radix sort, so the tile order
-// -- and with it every sum -- is the same function of the snapshot on both paths.
+// (profiles/r2c_small_n.txt).  The leading 3 b <= 30 bits of the Hilbert key fit a 32-bit word; the block-wide radix sort
+// (cub::BlockRadixSort: plumbing, like the device-wide sort of the general path) is stable and the keys are dealt to the
+// threads in index order, so ties keep their index order exactly as on the general path: the tile order -- and with it
+// every sum -- is the same function of the snapshot on both paths.  (A bitonic network in shared memory was tried first:
+// 105 stages x 256 KB through the shared memory of ONE SM = 200 us.)
 constexpr int SMALLSORT_MAX = 16384;
-__global__ void __launch_bounds__(1024) smallsort_kernel(int n, int n2, int keybits, const double *__restrict__ m,
+template <int IPT>
+__global__ void __launch_bounds__(1024) smallsort_kernel(int n, int keybits, const double *__restrict__ m,
                                                           const double *__restrict__ x, const double *__restrict__ v,
                                                           unsigned *__restrict__ hbits, int *__restrict__ perm, int *__restrict__ nanflag)
 {
-    extern __shared__ unsigned long long skey[];       // n2 composite keys
+    typedef cub::BlockRadixSort<unsigned, 1024, IPT, int> Sort;
+    extern __shared__ __align__(16) unsigned char ssort_raw[];
+    typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(ssort_raw);
     __shared__ float wmax[32];
     const int t = threadIdx.x;
     float a = 0.f;
@@ -255,24 +261,28 @@ __global__ void __launch_bounds__(1024) smallsort_kernel(int n, int n2, int keyb
     a = warp_max(wmax[t & 31]);
     if (t == 0) *hbits = __float_as_uint(a);           // isort_kernel scales the i-block with the same extent
     const float H = fmaxf(a, 1e-30f);
-    for (int j = t; j < n2; j += 1024) {
-        unsigned long long k = ~0ull;
-        if (j < n) k = ((morton_key(x[3 * (size_t)j], x[3 * (size_t)j + 1], x[3 * (size_t)j + 2], H) >> (63 - keybits)) << 14) | (unsigned)j;
-        skey[j] = k;
+    unsigned key[IPT];
+    int val[IPT];
+#pragma unroll
+    for (int u = 0; u < IPT; u++) {                    // blocked arrangement: thread t owns the particles [t IPT, (t+1) IPT)
+        const int j = t * IPT + u;
+        key[u] = j < n ? (unsigned)(morton_key(x[3 * (size_t)j], x[3 * (size_t)j + 1], x[3 * (size_t)j + 2], H) >> (63 - keybits)) : 0xffffffffu;
+        val[u] = j;
     }
-    __syncthreads();
-    for (int size = 2; size <= n2; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int k = t; k < (n2 >> 1); k += 1024) {
-                const int lo = 2 * k - (k & (stride - 1)), hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const unsigned long long p = skey[lo], q = skey[hi];
-                if ((p > q) == up) { skey[lo] = q; skey[hi] = p; }
-            }
-            __syncthreads();
-        }
+    Sort(tmp).Sort(key, val, 0, 32);                   // all 32 bits: the padding keys (0xffffffff) must end up last
+#pragma unroll
+    for (int u = 0; u < IPT; u++) {
+        const int p = t * IPT + u;
+        if (p < n) perm[p] = val[u];
     }
-    for (int j = t; j < n; j += 1024) perm[j] = (int)(skey[j] & 0x3fffull);
+}
+template <int IPT> void launch_smallsort(cudaStream_t st, int n, int keybits, const double *m, const double *x, const double *v,
+                                         unsigned *hbits, int *perm, int *nanflag)
+{
+    typedef cub::BlockRadixSort<unsigned, 1024, IPT, int> Sort;
+    static bool attr = false;
+    if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(smallsort_kernel<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename Sort::TempStorage))); attr = true; }
+    smallsort_kernel<IPT><<<1, 1024, sizeof(typename Sort::TempStorage), st>>>(n, keybits, m, x, v, hbits, perm, nanflag);
 }
 
 // One warp per tile: gathers its 64 particles through the sort permutation, finds the bounding boxes,
@@ -1545,6 +1555,7 @@ struct Lib {
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
     int resort_every = 1;          // Hilbert order refreshed every k-th snapshot (GPUNB_B200_RESORT_EVERY); 1 = always
     double sub_pairs = 1.5e8;      // pairs a sub-block of gpunb_regf_ must keep (GPUNB_B200_SUB_PAIRS)
+    double isort_pairs = 2.5e7;    // gpunb_regf_ calls with fewer pairs skip the Morton sort of the i-block (GPUNB_B200_ISORT_PAIRS)
     int snapshots_since_sort = 0;
     bool taper = false;            // tapering sub-block sizes (GPUNB_B200_TAPER=1); measured: no gain at 4 sub-blocks
     bool nslot_auto = true;        // nslot not chosen by the caller (environment / gpunb_b200_set_tuning)
@@ -1661,6 +1672,7 @@ void lib_devinit(int irank)
     { const char *e = getenv("GPUNB_B200_NSUB");  if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nsub = atoi(e); }
     { const char *e = getenv("GPUNB_B200_TAPER"); if (e) L.taper = atoi(e) != 0; }
     { const char *e = getenv("GPUNB_B200_SUB_PAIRS"); if (e && atof(e) >= 1.0) L.sub_pairs = atof(e); }
+    { const char *e = getenv("GPUNB_B200_ISORT_PAIRS"); if (e && atof(e) >= 0.0) L.isort_pairs = atof(e); }
     { const char *e = getenv("GPUNB_B200_RESORT_EVERY"); if (e && atoi(e) >= 1) L.resort_every = atoi(e); }
     { const char *e = getenv("GPUNB_B200_HOST_THREADS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) L.host_threads = atoi(e); }
     L.devinit = true;
@@ -1743,15 +1755,12 @@ void build_tiles(Dev &d, int n, const double *m, const double *x, const double *
         return;
     }
     static int smallsort = -1;
-    if (smallsort < 0) {
-        const char *e = getenv("GPUNB_B200_SMALLSORT");
-        smallsort = (e && atoi(e) == 0) ? 0 : 1;
-        CUDA_CHECK(cudaFuncSetAttribute(smallsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALLSORT_MAX * 8));
-    }
-    if (smallsort && n <= SMALLSORT_MAX) {          // one launch instead of eight (same order: stable on the leading key bits)
-        int n2 = 2048;
-        while (n2 < n) n2 <<= 1;
-        smallsort_kernel<<<1, 1024, (size_t)n2 * 8, d.st>>>(n, n2, 3 * hilbert_bits(n), m, x, v, d.hbits, d.perm, d.nanflag);
+    if (smallsort < 0) { const char *e = getenv("GPUNB_B200_SMALLSORT"); smallsort = (e && atoi(e) == 0) ? 0 : 1; }
+    if (smallsort && n <= SMALLSORT_MAX && 3 * hilbert_bits(n) <= 30) {      // one launch instead of eight, same order
+        const int kb = 3 * hilbert_bits(n);
+        if (n <= 4096)      launch_smallsort<4>(d.st, n, kb, m, x, v, d.hbits, d.perm, d.nanflag);
+        else if (n <= 8192) launch_smallsort<8>(d.st, n, kb, m, x, v, d.hbits, d.perm, d.nanflag);
+        else                launch_smallsort<16>(d.st, n, kb, m, x, v, d.hbits, d.perm, d.nanflag);
         d.perm_n = n;
         if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag);
         CUDA_CHECK(cudaGetLastError());
@@ -2410,6 +2419,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     if (nsub < 1) nsub = 1;
     IBlock ib[MAX_RANKS];
     const int *ipm[MAX_RANKS];
+    const bool i_sorted = !(ni <= root.itile || (double)ni * L.nbody < L.isort_pairs);
     for (int g = 0; g < G; g++) {
         Dev &d = L.devs[g];
         set_dev(d);
@@ -2417,7 +2427,11 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         CUDA_CHECK(cudaMemcpyAsync(d.ibuf, h, sizeof(double) * 8 * ni, cudaMemcpyHostToDevice, d.st));
         L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 8.0 * ni;
         ib[g] = IBlock{d.ibuf, d.ibuf + ni, d.ibuf + 2 * (size_t)ni, d.ibuf + 5 * (size_t)ni};
-        if (ni <= d.itile) {               // one i-tile: the order does not matter, skip the sort
+        // one i-tile: the order does not matter.  Small calls (ni x nj below ~2.5e7 pairs: the pair kernel is shorter
+        // than the 12 us the sort adds to the critical path of a synchronous call) keep the caller's order too:
+        // measured at N = 10^4, 76 vs 89 us per call at ni = 256, 118 vs 126 us at ni = 1024 (profiles/r2d_small_n.txt).
+        // Rank-invariant (ni and the global nj), like every decision that shapes the exchange.
+        if (!i_sorted) {
             ipm[g] = d.iperm_identity;
         } else {
             launch_isort(d, d.st, ni, ni, ib[g].xi, d.iperm, g == 0 ? L.h_iperm_dev : nullptr);
@@ -2439,7 +2453,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
         }
     }
     auto deliver = [&](int k0, int k1) {
-        if (!direct_out) { scatter_rows(ni <= root.itile ? nullptr : L.h_iperm, k0, k1, lmax, acc, jrk, pot, list); return; }
+        if (!direct_out) { scatter_rows(i_sorted ? L.h_iperm : nullptr, k0, k1, lmax, acc, jrk, pot, list); return; }
         if (k0 == 0) {                 // bytes the kernels wrote over PCIe (counted once per call)
             double bytes = 0;
             for (int i = 0; i < ni; i++) { const int c = list[(size_t)i * lmax]; bytes += 56.0 + 4.0 * (1 + (c > 0 ? c : 0)); }
@@ -2450,7 +2464,11 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     if (nsub == 1) {
         j.slot0 = 0; j.nloc = ni;
         // staged results of a large block on one GPU: delivered in parts, the host copy of part p beside the merge of p+1
-        const int parts = (G == 1 && !L.sh.on && !direct_out && ni >= 512) ? (ni >= 1024 ? 4 : 2) : 1;
+        // (measured at N = 10^4, ni = 1024: 162 us per call with 4 parts against 152 us with one merge launch -- the extra
+        // launches and event waits cost more than the overlapped host copy saves; kept for tuning: GPUNB_B200_MERGE_PARTS)
+        static int mp = -1;
+        if (mp < 0) { const char *e = getenv("GPUNB_B200_MERGE_PARTS"); mp = (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) ? atoi(e) : 1; }
+        const int parts = (G == 1 && !L.sh.on && !direct_out && ni >= 512) ? mp : 1;
         j.merge_parts = parts;
         run_job(j, ib, ipm, 0, false, true);
         L.ctr[GPUNB_B200_CTR_HOST_ENQUEUE_MS] += (wtime() - wt_packed) * 1e3;
@@ -3019,6 +3037,7 @@ void gpunb_b200_unpin_host_(void *ptr)
 }
 void gpunb_b200_set_taper(int on) { L.taper = on != 0; }
 void gpunb_b200_set_sub_pairs(double pairs) { if (pairs >= 1.0) L.sub_pairs = pairs; }
+void gpunb_b200_set_isort_pairs(double pairs) { if (pairs >= 0.0) L.isort_pairs = pairs; }
 void gpunb_b200_set_islice(int on)
 {
     if (on && !L.sh.on) FATAL("gpunb_b200_set_islice: the i-slice mode needs one process per GPU (gpunb_b200_nccl_init)");

@@ -106,6 +106,8 @@ class ForceLib:
             L.gpunb_b200_set_islice.restype = None
             L.gpunb_b200_set_sub_pairs.argtypes = [C.c_double]
             L.gpunb_b200_set_sub_pairs.restype = None
+            L.gpunb_b200_set_isort_pairs.argtypes = [C.c_double]
+            L.gpunb_b200_set_isort_pairs.restype = None
             L.gpunb_b200_set_tuning.argtypes = [C.c_int, C.c_int]
             L.gpunb_b200_set_tuning.restype = None
             L.gpunb_b200_state_all_.argtypes = [_c_int_p] + [_c_dbl_p] * 6
@@ -364,6 +366,11 @@ class ForceLib:
         """Pairs a sub-block of gpunb_regf_ must keep for the call to be split (default 1.5e8)."""
         self._need_b200()
         self.lib.gpunb_b200_set_sub_pairs(float(pairs))
+
+    def set_isort_pairs(self, pairs: float):
+        """gpunb_regf_ calls below this many pairs skip the Morton sort of the i-block (default 2.5e7; 0 = always sort)."""
+        self._need_b200()
+        self.lib.gpunb_b200_set_isort_pairs(float(pairs))
 
     def set_taper(self, on: int):
         """Sub-block sizes of one gpunb_regf_ call: equal (0, default) or tapering (1)."""

@@ -69,8 +69,10 @@ def check(lib, tag, rank=0):
         lib.sweep_resident(0, 12 * 1024, 1024, lmax, nnbmax, m_flag)
         a, j, p, l = lib.fetch_last(lmax)
         lib.set_tuning(0, 1)                        # one pair-kernel launch per call: same summation order as the sweep
+        lib.set_isort_pairs(0.0)                    # ... and the same Morton order of the i-block (small calls skip the sort)
         a2, j2, p2, l2 = lib.regf(h2[11264:12288], dtr[11264:12288], x[11264:12288], v[11264:12288], lmax, nnbmax, m_flag)
         lib.set_tuning(0, 4)
+        lib.set_isort_pairs(2.5e7)
         assert np.array_equal(a, a2) and np.array_equal(p, p2) and not oracle_lib.list_rows_equal(l, l2)
         lib.close()
     # gpupot over the same j-shards (partials summed in rank order)

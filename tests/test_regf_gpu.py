@@ -204,6 +204,7 @@ def test_resident_sweep_matches_abi(b200, nslot):
     b200.send(m, x, v)
     try:
         b200.set_tuning(nslot, 1)
+        b200.set_isort_pairs(0.0)         # the ABI call sorts its i-block like the sweep does (small calls skip the sort)
         b200.set_radii(h2, dtr)
         for n_sweep in (n, 5 * 1024):          # the last block lands in different slots
             ms = b200.sweep_resident(0, n_sweep, 1024, 400, 350, 0)
@@ -216,6 +217,7 @@ def test_resident_sweep_matches_abi(b200, nslot):
             assert not oracle_lib.list_rows_equal(l, l2)
     finally:
         b200.set_tuning(3, 4)
+        b200.set_isort_pairs(2.5e7)
         b200.close()
 
 
