@@ -50,7 +50,6 @@
 // on the same slots.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/block/block_radix_sort.cuh>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -222,77 +221,19 @@ __global__ void mortonkey_kernel(int n, const double *__restrict__ x, const unsi
     vals[j] = j;
 }
 
-// Small j-sets (n <= SMALLSORT_MAX): |x|max, NaN check, Hilbert keys and the sort in ONE launch of ONE CTA.  At N = 10^4 the
-// nine launches of the general path (memset, absmax, keys, CUB histogram / scan / 4-5 onesweep passes) are nothing but
-// launch latency: 72 us of the 150 us of a gpunb_send_, against 68 us for the reference's whole call
-// (profiles/r2c_small_n.txt).  The leading 3 b <= 30 bits of the Hilbert key fit a 32-bit word; the block-wide radix sort
-// (cub::BlockRadixSort: plumbing, like the device-wide sort of the general path) is stable and the keys are dealt to the
-// threads in index order, so ties keep their index order exactly as on the general path: the tile order -- and with it
-// every sum -- is the same function of the snapshot on both paths.  (A bitonic network in shared memory was tried first:
-// 105 stages x 256 KB through the shared memory of ONE SM = 200 us.)
-constexpr int SMALLSORT_MAX = 16384;
-template <int IPT>
-__global__ void __launch_bounds__(1024) smallsort_kernel(int n, int keybits, const double *__restrict__ m,
-                                                          const double *__restrict__ x, const double *__restrict__ v,
-                                                          unsigned *__restrict__ hbits, int *__restrict__ perm, int *__restrict__ nanflag)
-{
-    typedef cub::BlockRadixSort<unsigned, 1024, IPT, int> Sort;
-    extern __shared__ __align__(16) unsigned char ssort_raw[];
-    typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(ssort_raw);
-    __shared__ float wmax[32];
-    const int t = threadIdx.x;
-    float a = 0.f;
-    bool bad = false;
-    for (int j = t; j < n; j += 1024) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const double xd = x[3 * (size_t)j + k];
-            a = fmaxf(a, fabsf((float)xd));
-            bad |= (xd != xd);
-            if (v) { const double vd = v[3 * (size_t)j + k]; bad |= (vd != vd); }
-        }
-        const double md = m[j];
-        bad |= (md != md);
-    }
-    if (bad) *(volatile int *)nanflag = 1;
-    a = warp_max(a);
-    if ((t & 31) == 0) wmax[t >> 5] = a;
-    __syncthreads();
-    a = warp_max(wmax[t & 31]);
-    if (t == 0) *hbits = __float_as_uint(a);           // isort_kernel scales the i-block with the same extent
-    const float H = fmaxf(a, 1e-30f);
-    unsigned key[IPT];
-    int val[IPT];
-#pragma unroll
-    for (int u = 0; u < IPT; u++) {                    // blocked arrangement: thread t owns the particles [t IPT, (t+1) IPT)
-        const int j = t * IPT + u;
-        key[u] = j < n ? (unsigned)(morton_key(x[3 * (size_t)j], x[3 * (size_t)j + 1], x[3 * (size_t)j + 2], H) >> (63 - keybits)) : 0xffffffffu;
-        val[u] = j;
-    }
-    Sort(tmp).Sort(key, val, 0, 32);                   // all 32 bits: the padding keys (0xffffffff) must end up last
-#pragma unroll
-    for (int u = 0; u < IPT; u++) {
-        const int p = t * IPT + u;
-        if (p < n) perm[p] = val[u];
-    }
-}
-template <int IPT> void launch_smallsort(cudaStream_t st, int n, int keybits, const double *m, const double *x, const double *v,
-                                         unsigned *hbits, int *perm, int *nanflag)
-{
-    typedef cub::BlockRadixSort<unsigned, 1024, IPT, int> Sort;
-    static bool attr = false;
-    if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(smallsort_kernel<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(typename Sort::TempStorage))); attr = true; }
-    smallsort_kernel<IPT><<<1, 1024, sizeof(typename Sort::TempStorage), st>>>(n, keybits, m, x, v, hbits, perm, nanflag);
-}
-
 // One warp per tile: gathers its 64 particles through the sort permutation, finds the bounding boxes,
 // writes header + arrays.  Ghost slots of the last tile replicate the tile's first particle with mass 0
 // and index -1 (never listed, no force).  v may be NULL (gpupot tiles).
 __global__ void __launch_bounds__(128) tilepack_kernel(int n, int t0, int tstride, int nloc, const double *__restrict__ m,
                                                         const double *__restrict__ x, const double *__restrict__ v,
                                                         const int *__restrict__ perm, float *__restrict__ tiles,
-                                                        int *__restrict__ jidx, int *__restrict__ nanflag)
+                                                        int *__restrict__ jidx, int *__restrict__ nanflag,
+                                                        const unsigned *__restrict__ hbits, unsigned long long *__restrict__ qsum,
+                                                        unsigned long long *__restrict__ q_host)
 {   // packs tiles t = t0 + l * tstride (l < nloc) of the sorted order into tiles[l], jidx[l * TJ ..]
+    // qsum (optional): [0] sum over the tiles of (hx + hy + hz) / |x|max in fixed point -- an ORDER-INDEPENDENT integer
+    // sum, so that the decision it feeds (keep the Hilbert order for the next snapshot or sort again) is deterministic --,
+    // [1] tiles done; the last tile to finish hands the sum to the host (mapped memory) and clears both.
     const int lane = threadIdx.x & 31;
     const int l = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (l >= nloc) return;
@@ -334,15 +275,30 @@ __global__ void __launch_bounds__(128) tilepack_kernel(int n, int t0, int tstrid
     }
     mmax = warp_max(mmax);
     if (lane == 0) {
+        float hsum = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             tb[c] = Oh[c]; tb[3 + c] = Ol[c];
             // half-extents rounded up (conservative): fp32-rounded coordinates may sit 1 ulp outside
-            tb[6 + c]  = (float)fmax(mx[c] - O[c], O[c] - mn[c]) * 1.000002f + 1.2e-7f * (float)fmax(fabs(mn[c]), fabs(mx[c])) + 1e-30f;
+            const float hc = (float)fmax(mx[c] - O[c], O[c] - mn[c]) * 1.000002f + 1.2e-7f * (float)fmax(fabs(mn[c]), fabs(mx[c])) + 1e-30f;
+            tb[6 + c]  = hc;
+            hsum += hc;
             tb[9 + c]  = 0.5f * (vmn[c] + vmx[c]);
             tb[12 + c] = 0.5f * (vmx[c] - vmn[c]) * 1.000001f + 1.2e-7f * fmaxf(fabsf(vmn[c]), fabsf(vmx[c])) + 1e-30f;
         }
         tb[15] = sqrtf(mmax) * 1.000001f;          // sqrt of the largest mass (m_flag criterion h2*mj), rounded up
+        if (qsum) {
+            const float H = fmaxf(__uint_as_float(*hbits), 1e-30f);
+            const float e = fminf(hsum / H, 8.f);
+            atomicAdd(&qsum[0], (unsigned long long)(e * 1048576.f));
+            __threadfence();
+            if (atomicAdd(&qsum[1], 1ull) == (unsigned long long)(nloc - 1)) {
+                __threadfence();
+                *q_host = atomicAdd(&qsum[0], 0ull);
+                qsum[0] = 0ull; qsum[1] = 0ull;
+                __threadfence();
+            }
+        }
     }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -1484,6 +1440,7 @@ struct Dev {
     unsigned long long *keys_in = nullptr, *keys_out = nullptr;
     int *vals_in = nullptr, *perm = nullptr; int sort_cap = 0;
     int perm_n = 0;               // perm holds the order of the regf snapshot of this many particles (0: invalid)
+    unsigned long long *qsum = nullptr;   // [2] tile-extent sum / tiles done of the running tilepack (adaptive re-sort)
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     int *iperm = nullptr;         // Morton order of the current i-block
     int *iperm_identity = nullptr;   // 0, 1, 2, ... (blocks of a single i-tile are not sorted)
@@ -1553,7 +1510,10 @@ struct Lib {
     int *h_flag = nullptr;
     int *h_nan = nullptr;          // [MAX_RANKS] NaN flags written by the tile kernels straight into host memory
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
-    int resort_every = 1;          // Hilbert order refreshed every k-th snapshot (GPUNB_B200_RESORT_EVERY); 1 = always
+    int resort_every = 0;          // Hilbert order refreshed every k-th snapshot (GPUNB_B200_RESORT_EVERY); 1 = always;
+                                   // 0 (default) = adaptive: kept while the tiles stay compact (one GPU; sharded runs always sort)
+    unsigned long long *h_q = nullptr;                 // mapped: tile-extent sum of the last tilepack (device 0)
+    double q_ref = 0.0, q_last = 0.0;                  // ... right after the last sort / of the last snapshot
     double sub_pairs = 1.5e8;      // pairs a sub-block of gpunb_regf_ must keep (GPUNB_B200_SUB_PAIRS)
     double isort_pairs = 2.5e7;    // gpunb_regf_ calls with fewer pairs skip the Morton sort of the i-block (GPUNB_B200_ISORT_PAIRS)
     int snapshots_since_sort = 0;
@@ -1673,7 +1633,9 @@ void lib_devinit(int irank)
     { const char *e = getenv("GPUNB_B200_TAPER"); if (e) L.taper = atoi(e) != 0; }
     { const char *e = getenv("GPUNB_B200_SUB_PAIRS"); if (e && atof(e) >= 1.0) L.sub_pairs = atof(e); }
     { const char *e = getenv("GPUNB_B200_ISORT_PAIRS"); if (e && atof(e) >= 0.0) L.isort_pairs = atof(e); }
-    { const char *e = getenv("GPUNB_B200_RESORT_EVERY"); if (e && atoi(e) >= 1) L.resort_every = atoi(e); }
+    { const char *e = getenv("GPUNB_B200_RESORT_EVERY"); if (e && atoi(e) >= 0) L.resort_every = atoi(e); }
+    CUDA_CHECK(cudaHostAlloc((void **)&L.h_q, sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+    *L.h_q = 0ull;
     { const char *e = getenv("GPUNB_B200_HOST_THREADS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) L.host_threads = atoi(e); }
     L.devinit = true;
 }
@@ -1744,27 +1706,15 @@ void ensure_sort_capacity(Dev &d, int n)
 // re-packed from the current positions, so boxes, offsets and results stay exact -- only the compactness of the tiles
 // ages with the particles' motion.
 void build_tiles(Dev &d, int n, const double *m, const double *x, const double *v, float *tiles, int *jidx,
-                 int t0, int tstride, int nloc, bool reuse_order = false)
+                 int t0, int tstride, int nloc, bool reuse_order = false, unsigned long long *qsum = nullptr,
+                 unsigned long long *q_host = nullptr)
 {
     if (n <= 0) return;
     ensure_sort_capacity(d, n);
     if (reuse_order && d.perm_n == n) {
-        if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag);
+        if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag, d.hbits, qsum, q_host);
         CUDA_CHECK(cudaGetLastError());
         L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
-        return;
-    }
-    static int smallsort = -1;
-    if (smallsort < 0) { const char *e = getenv("GPUNB_B200_SMALLSORT"); smallsort = (e && atoi(e) == 0) ? 0 : 1; }
-    if (smallsort && n <= SMALLSORT_MAX && 3 * hilbert_bits(n) <= 30) {      // one launch instead of eight, same order
-        const int kb = 3 * hilbert_bits(n);
-        if (n <= 4096)      launch_smallsort<4>(d.st, n, kb, m, x, v, d.hbits, d.perm, d.nanflag);
-        else if (n <= 8192) launch_smallsort<8>(d.st, n, kb, m, x, v, d.hbits, d.perm, d.nanflag);
-        else                launch_smallsort<16>(d.st, n, kb, m, x, v, d.hbits, d.perm, d.nanflag);
-        d.perm_n = n;
-        if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag);
-        CUDA_CHECK(cudaGetLastError());
-        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
         return;
     }
     CUDA_CHECK(cudaMemsetAsync(d.hbits, 0, sizeof(unsigned), d.st));
@@ -1777,7 +1727,7 @@ void build_tiles(Dev &d, int n, const double *m, const double *x, const double *
     // small N the sort is nothing but launch latency.  Mirror: sharding.hilbert_order().
     CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d.cub_tmp, bytes, d.keys_in, d.keys_out, d.vals_in, d.perm, n,
                                                63 - 3 * hilbert_bits(n), 63, d.st));
-    if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag);
+    if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag, d.hbits, qsum, q_host);
     CUDA_CHECK(cudaGetLastError());
     L.ctr[GPUNB_B200_CTR_LAUNCHES] += 4;       // + the CUB sort passes (library code, not counted)
 }
@@ -1905,10 +1855,11 @@ void lib_close()
         dev_free(d.state); d.state_cap = d.state_n = 0; dev_free(d.upd_rec); dev_free(d.upd_idx); dev_free(d.upd_bad); d.upd_cap = 0;
         dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.iperm_identity); dev_free(d.stats); dev_free(d.wtime);
         dev_free(d.jidx);
+        dev_free(d.qsum); d.perm_n = 0;
     }
     host_free(L.h_j); L.h_j_n = 0; host_free(L.h_i); host_free(L.h_f); host_free(L.h_list); L.h_list_n = 0;
     host_free(L.h_iperm); host_free(L.h_upd); host_free(L.h_upd_idx); L.h_upd_cap = 0;
-    L.nbmax = 0;
+    L.nbmax = 0; L.q_ref = L.q_last = 0.0; L.snapshots_since_sort = 0;
 }
 
 // The snapshot is staged in pinned memory (m | x | v) in chunks: a few host threads copy chunk c+1 while the copy
@@ -1990,13 +1941,26 @@ void finish_send(int nj, double wt0, const char *who)
 {
     const int R = total_ranks();
     const double wt1 = wtime();
-    const bool reuse = L.resort_every > 1 && (L.snapshots_since_sort % L.resort_every) != 0;
+    // Keep the Hilbert order of the previous snapshot?  k > 1: for k-1 of k snapshots.  Adaptive (default, one GPU): while
+    // the tiles are still about as compact as right after the last sort -- the sum of their half-extents (an exact integer
+    // sum, so the decision is reproducible) has grown by less than 10 % -- and for at most 64 snapshots.  The tiles are
+    // re-packed from the current positions either way: lists stay bit-exact, forces within the same bars; only the
+    // summation order follows the kept permutation.  Sharded runs always sort: every rank must cut the same tiles.
+    const bool adaptive = L.resort_every == 0 && R == 1;
+    bool reuse = false;
+    if (L.resort_every > 1) reuse = (L.snapshots_since_sort % L.resort_every) != 0;
+    else if (adaptive) reuse = L.devs[0].perm_n == nj && L.q_ref > 0.0 && L.q_last <= 1.10 * L.q_ref && L.snapshots_since_sort < 64;
+    if (reuse && L.devs[0].perm_n != nj) reuse = false;
     L.snapshots_since_sort = reuse ? L.snapshots_since_sort + 1 : 1;
     for (size_t g = 0; g < L.devs.size(); g++) {
         Dev &d = L.devs[g];
         set_dev(d);
+        if (adaptive && !d.qsum) { dev_alloc(d.qsum, 2); CUDA_CHECK(cudaMemsetAsync(d.qsum, 0, 2 * sizeof(unsigned long long), d.st)); }
+        unsigned long long *q_dev = nullptr;
+        if (adaptive) CUDA_CHECK(cudaHostGetDevicePointer((void **)&q_dev, (void *)L.h_q, 0));
         CUDA_CHECK(cudaEventRecord(d.evs0, d.st));
-        build_tiles(d, nj, d.jraw, d.jraw + nj, d.jraw + 4 * (size_t)nj, d.jtile, d.jidx, L.sh.on ? L.sh.rank : (int)g, R, d.ntiles, reuse);
+        build_tiles(d, nj, d.jraw, d.jraw + nj, d.jraw + 4 * (size_t)nj, d.jtile, d.jidx, L.sh.on ? L.sh.rank : (int)g, R, d.ntiles, reuse,
+                    adaptive ? d.qsum : nullptr, q_dev);
         CUDA_CHECK(cudaEventRecord(d.evs1, d.st));
     }
     for (size_t g = 0; g < L.devs.size(); g++) {
@@ -2004,6 +1968,11 @@ void finish_send(int nj, double wt0, const char *who)
         CUDA_CHECK(cudaStreamSynchronize(L.devs[g].st));
         if (L.h_nan[g]) FATAL("%s: NaN in j-particle data (reference asserts here, gpunb.velocity.cu:72-78)", who);
     }
+    if (adaptive) {
+        L.q_last = (double)*L.h_q;
+        if (!reuse) L.q_ref = L.q_last;
+    }
+    if (reuse) L.ctr[GPUNB_B200_CTR_SENDS_ORDER_KEPT] += 1;
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, L.devs[0].evs0, L.devs[0].evs1));
     const double wt2 = wtime();
@@ -3043,7 +3012,7 @@ void gpunb_b200_set_islice(int on)
     if (on && !L.sh.on) FATAL("gpunb_b200_set_islice: the i-slice mode needs one process per GPU (gpunb_b200_nccl_init)");
     L.sh.islice = on != 0;
 }
-void gpunb_b200_set_resort_every(int k) { if (k >= 1) { L.resort_every = k; L.snapshots_since_sort = 0; } }
+void gpunb_b200_set_resort_every(int k) { if (k >= 0) { L.resort_every = k; L.snapshots_since_sort = 0; L.q_ref = 0.0; } }
 
 void gpunb_b200_set_tuning(int nslot, int nsub)
 {

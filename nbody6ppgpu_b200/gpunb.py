@@ -23,12 +23,12 @@ _HERE = Path(__file__).resolve().parent
 _c_int_p = C.POINTER(C.c_int)
 _c_dbl_p = C.POINTER(C.c_double)
 
-N_COUNTERS = 25
+N_COUNTERS = 26
 CTR = dict(grav_ms=0, grav_launches=1, launches=2, h2d_bytes=3, d2h_bytes=4, interactions=5,
            merge_ms=6, pot_ms=7, near_tiles=8, all_tiles=9,
            tl_blocks=10, tl_isort_ms=11, tl_regf_ms=12, tl_merge_ms=13, tl_exch_ms=14,
            host_pack_ms=15, host_enqueue_ms=16, host_wait_ms=17, host_scatter_ms=18,
-           sends=19, send_ms=20, send_stage_ms=21, send_tiles_ms=22, transposed_tiles=23, host_rendezvous_ms=24)
+           sends=19, send_ms=20, send_stage_ms=21, send_tiles_ms=22, transposed_tiles=23, sends_order_kept=24, host_rendezvous_ms=25)
 
 
 class LibraryMissing(RuntimeError):
@@ -352,7 +352,7 @@ class ForceLib:
             self.lib.gpunb_b200_unpin_host_(C.c_void_p(a.ctypes.data))
 
     def set_resort_every(self, k: int):
-        """Hilbert order refreshed every k-th snapshot only (1 = always, the default)."""
+        """Hilbert order across snapshots: 0 = adaptive (default), 1 = always sort, k > 1 = sort every k-th snapshot."""
         self._need_b200()
         self.lib.gpunb_b200_set_resort_every(k)
 

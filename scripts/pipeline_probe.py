@@ -54,7 +54,7 @@ tp = (time.perf_counter() - t0) / 7
 c = lib.counters()
 print(f"rank {rank}/{world} gpunb_b200_predict_send_ with the Hilbert order kept (GPUNB_B200_RESORT_EVERY=8): {tp * 1e3:6.2f} ms per call "
       f"(device tile construction {c['send_tiles_ms'] / c['sends']:6.2f} ms)", flush=True)
-lib.set_resort_every(1)
+lib.set_resort_every(0)
 lib.send(m, x, v)
 if os.environ.get("PROBE_ONLY_SEND"):
     lib.close()

@@ -93,5 +93,40 @@ def test_reused_tile_order_stays_exact(b200, oracle):
             assert oracle_lib.relerr_scaled(jrk, j64, oracle.scale[:, 1]) <= 1e-6
             phi = b200.gpupot(1, n, m, xs) if step == 3 else None      # gpupot in between invalidates the kept order
     finally:
-        b200.set_resort_every(1)
+        b200.set_resort_every(0)
         b200.close()
+
+
+def test_adaptive_tile_order(b200, oracle):
+    """Default mode (GPUNB_B200_RESORT_EVERY = 0): the Hilbert order of the previous snapshot is kept while the tiles stay
+    compact (summed half-extents within 10 % of their value after the last sort) and refreshed once the particles have
+    drifted.  Small drifts keep the order, a large one triggers a sort; lists stay bit-exact and forces within 1e-6 on
+    every snapshot, and the decision sequence is reproducible."""
+    n = 12000
+    m, x, v = S.plummer(n, 19, "kroupa")
+    h2, dtr = S.radii(x, m, S.rs0_for_nnb(n, 80.0))
+    isel = slice(3000, 3000 + 512)
+    drifts = [0.0, 1e-4, 2e-4, 3e-4, 0.05, 0.0501, 0.0502, 0.2]
+    kept_runs = []
+    for rep in range(2):
+        b200.open(n + 10, 0)
+        try:
+            b200.set_resort_every(0)
+            kept = []
+            for dt in drifts:
+                xs = x + v * dt
+                b200.reset_counters()
+                b200.send(m, xs, v)
+                kept.append(int(b200.counters()["sends_order_kept"]))
+                acc, jrk, pot, lst = b200.regf(h2[isel], dtr[isel], xs[isel], v[isel], 400, 350, 0)
+                a64, j64, p64, l64, band, _ = oracle.regf_f64(m, xs, v, h2[isel], dtr[isel], xs[isel], v[isel], 400, 350, 0, 4.0)
+                assert not [i for i in oracle_lib.list_rows_equal(lst, l64) if band[i] > 4.0], dt
+                assert oracle_lib.relerr(acc, a64) <= 1e-6 and oracle_lib.relerr(pot, p64) <= 1e-6
+                assert oracle_lib.relerr_scaled(jrk, j64, oracle.scale[:, 1]) <= 1e-6
+            kept_runs.append(kept)
+        finally:
+            b200.close()
+    assert kept_runs[0] == kept_runs[1]                    # reproducible decisions
+    assert kept_runs[0][0] == 0                            # the first snapshot after open is always sorted
+    assert kept_runs[0][1:4] == [1, 1, 1]                  # tiny drifts keep the order
+    assert 0 in kept_runs[0][4:], kept_runs[0]             # the large drifts trigger a fresh sort (one snapshot later)
