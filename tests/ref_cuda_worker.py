@@ -112,6 +112,18 @@ def main():
         small[name]["send"] = (time.perf_counter() - t0) / 20 * 1e6
         lib.close()
     out["small_blocks_N10k_us_per_call"] = small
+    # BASELINE config 2 (samples/N16k.input: N = 16000, m_flag = 1): device-resident sweep of this library as a fraction of
+    # the FP32 roofline (the block of a resident sweep is free: 4736 = 32 x 148 i-tiles, four launch groups)
+    n = 16000
+    m3, x3, v3 = S.plummer(n, 6, "kroupa")
+    h23, dtr3 = S.radii_nnb(x3, m3, 100.0, 0.125, 1)
+    b200.open(n + 10, 0)
+    b200.send(m3, x3, v3); b200.set_radii(h23, dtr3)
+    for _ in range(3):
+        b200.sweep_resident(0, n, 4736, 400, 350, 1)
+    ms = min(b200.sweep_resident(0, n, 4736, 400, 350, 1) for _ in range(5))
+    b200.close()
+    out["sweep_N16k_mflag1"] = {"ms": ms, "gint_per_s": float(n) * n / ms * 1e-6, "frac_of_fp32_roofline": float(n) * n / ms * 1e-6 / 1240.8}
     # list parity at N = 1M over the timed calls; every differing pair is reported with its distance from the boundary
     diffs = []
     for b in range(calls):

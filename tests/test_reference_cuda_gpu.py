@@ -36,3 +36,10 @@ def test_parity_and_rate_against_reference_cuda_library():
     assert out["lists_1M"]["pairs_differing"] <= 8, out["lists_1M"]
     assert out["gpupot_relerr"] < 1e-6
     assert out["rate_b200"]["gint_per_s"] > out["rate_ref"]["gint_per_s"]
+    # latency-bound regime (BASELINE config N10k_B1k): every column of the small-block table -- gpunb_regf_ for 1 ... 1024
+    # i-particles and gpunb_send_, pageable caller arrays, the same caller for both libraries -- must not be slower than the
+    # reference's own CUDA library on the same GPU (10 % allowance for timing noise on a shared host)
+    small = out["small_blocks_N10k_us_per_call"]
+    for col, t_ref in small["ref"].items():
+        assert small["b200"][col] <= 1.10 * t_ref, (col, small["b200"][col], t_ref)
+    assert out["sweep_N16k_mflag1"]["frac_of_fp32_roofline"] >= 0.40, out["sweep_N16k_mflag1"]
