@@ -1092,10 +1092,11 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
 {
     __shared__ int sbuf[4][SORT_CAP];
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int kl = a.kl0 + blockIdx.x * 4 + wq;
-    if (kl < a.kl1) {
-        if (a.acks) wait_all_ranks(a.acks, a.R, a.ack_need, lane);
+    int kl = a.kl0 + blockIdx.x * 4 + wq;              // grid-stride over the rows (the grid is capped when the kernel may spin)
+    if (kl < a.kl1 && a.acks) wait_all_ranks(a.acks, a.R, a.ack_need, lane);
+    for (; kl < a.kl1; kl += gridDim.x * 4) {
         merge_row(a, kl, lane, sbuf[wq]);
+        __syncwarp();
     }
     publish_when_last(a.sig);
 }
@@ -1187,10 +1188,11 @@ __global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
     __shared__ int sbuf[4][SORT_CAP];
     __shared__ int soff[4][MAX_RANKS], scnt[4][MAX_RANKS];
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int kl = a.kl0 + blockIdx.x * 4 + wq;
-    if (kl < a.kl1) {
-        if (a.flags) wait_all_ranks(a.flags, a.R, (long long)a.seq, lane);    // every shard has published this call
+    int kl = a.kl0 + blockIdx.x * 4 + wq;              // grid-stride over the rows
+    if (kl < a.kl1 && a.flags) wait_all_ranks(a.flags, a.R, (long long)a.seq, lane);    // every shard has published this call
+    for (; kl < a.kl1; kl += gridDim.x * 4) {
         combine_row(a, kl, lane, sbuf[wq], soff[wq], scnt[wq]);
+        __syncwarp();
     }
     publish_when_last(a.ack);
 }
@@ -2228,7 +2230,12 @@ void launch_regf(Dev &d, Slot &sl, cudaStream_t lo, cudaStream_t hi, const Job &
     for (int q = 0; q < parts; q++) {
         m.kl0 = (int)((long long)j.nloc * q / parts) & ~3;
         m.kl1 = q == parts - 1 ? j.nloc : (int)((long long)j.nloc * (q + 1) / parts) & ~3;
-        if (m.kl1 > m.kl0) merge_kernel<<<(m.kl1 - m.kl0 + 3) / 4, 128, 0, hi>>>(m);
+        // A kernel that may SPIN on peer flags never gets more than a few CTAs per SM: pair kernels of equal-priority
+        // streams do not start in submission order, and a machine full of spinning CTAs of block b+1 would starve the
+        // pair kernel of block b whose merge the peers are waiting for (seen at 8 ranks with 9472-row blocks).
+        int mgrid = (m.kl1 - m.kl0 + 3) / 4;
+        if (m.acks && mgrid > 2 * d.nsm) mgrid = 2 * d.nsm;
+        if (m.kl1 > m.kl0) merge_kernel<<<mgrid, 128, 0, hi>>>(m);
         if (parts > 1) CUDA_CHECK(cudaEventRecord(d.slots[q].ev_start, hi));        // idle events of the unused pipeline slots
     }
     CUDA_CHECK(cudaGetLastError());
@@ -2315,7 +2322,9 @@ void run_job(const Job &j, const IBlock *ib, const int *const *iperm, int q, boo
             set_dev(root);
         }
         const int ncomb = c.kl1 - c.kl0;
-        combine_kernel<<<ncomb > 0 ? (ncomb + 3) / 4 : 1, 128, 0, hi>>>(c);      // 4 warps per CTA: one i each
+        int cgrid = ncomb > 0 ? (ncomb + 3) / 4 : 1;                             // 4 warps per CTA: one i each
+        if (c.flags && cgrid > root.nsm) cgrid = root.nsm;                       // spins on peer flags: see launch_regf (one CTA per SM and pipeline slot)
+        combine_kernel<<<cgrid, 128, 0, hi>>>(c);
         CUDA_CHECK(cudaGetLastError());
         L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
         if (!L.sh.on) CUDA_CHECK(cudaEventRecord(root.evdone, root.st));
