@@ -95,6 +95,8 @@ enum {
     GPUNB_B200_CTR_TRANSPOSED_TILES, /* NEAR (warp, j-tile) visits handled by the transposed path (GPUNB_B200_STATS=1) */
     GPUNB_B200_CTR_SENDS_ORDER_KEPT,  /* snapshots whose tiles were re-packed in the kept Hilbert order (no sort) */
     GPUNB_B200_CTR_HOST_RENDEZVOUS_MS, /* i-slice mode: publishing this rank's slice and waiting for the other ranks' (ms) */
+    GPUNB_B200_CTR_REGCOR_MS,         /* gpunb_b200_regcor_: wall-clock ms inside the calls (pack, upload, kernel, results) */
+    GPUNB_B200_CTR_REGCOR_ROWS,       /* ... rows handled */
     GPUNB_B200_CTR_COUNT
 };
 void gpunb_b200_get_counters(double out[GPUNB_B200_CTR_COUNT]);
@@ -211,6 +213,43 @@ int gpunb_b200_debug_wtimes(unsigned long long *out, int max_items);
 int  gpunb_b200_nccl_unique_id(unsigned char id128[128]);
 int  gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128]);
 void gpunb_b200_nccl_finalize(void);
+
+/* ---------------- Part 3: neighbour-list bookkeeping after gpunb_regf_ ----------------
+ * Replaces, for the ni rows of one regular block in ONE call, what the Fortran caller does per particle on the host:
+ *   src/Main/util_gpu.F:102-111     row of gpunb_regf_ -> NLIST: + IFIRST, self dropped
+ *   src/Main/regcor_gpu.F:267-336   NBLOSS / NBGAIN / JJLIST: old list LIST(:,I) against NLIST
+ *   src/Main/regcor_gpu.F:338-420   lost members with STEP(J) <= SMIN inside 2 RS are put back (NBSMIN, FREG / FDR corrected)
+ *   src/Main/regcor_gpu.F:425-470   DFIRR / DFD: - pair terms of the lost members + pair terms of the gained ones, fp64
+ * X, XDOT, BODY of those lines are the predicted values of the block = the snapshot the last gpunb_send_ /
+ * gpunb_b200_predict_send_ left on the device: particle J sits at index J - IFIRST, nothing is uploaded again.
+ * Fortran-callable (scalars by reference, INTEGER*4 / REAL*8).  All particle numbers are the Fortran program's (1-based).
+ *   index_i[ni]        particle I of each row
+ *   new_list[ni][lmax] in: rows exactly as gpunb_regf_ returned them ([count, 0-based j ascending, self included]; rows with
+ *                      a negative count are passed through untouched -- the overflow retry of util_gpu.F:71-97 comes first);
+ *                      out: NLIST = [NNB, members ascending] after self removal and retention
+ *   old_list[ni][lmax] LIST(1:LMAX, I) = [NNB0, members ascending], or NULL: the rows of the device-resident list store
+ *                      (gpunb_b200_lists_put_; once the store exists every call commits the final NLIST of its rows to it,
+ *                      so a caller that changes lists nowhere else never uploads a list)
+ *   rs2[ni]            RS(I)**2 as regcor sees it at entry (regcor_gpu.F:41)
+ *   step               STEP(IFIRST:NTOT) on the host (uploaded by this call), or NULL: the resident copy kept by
+ *                      gpunb_b200_steps_all_ / _update_; without either no lost member is ever retained (JMIN stays 0)
+ *   freg, fdr          in/out [ni][3]: FREG, FDR (retention subtracts the retained members' terms)
+ *   dfirr, dfd         in/out [ni][3]: the caller passes zeros (regcor_gpu.F:262-263) or its NNB = 0 values (:121-130)
+ *   nbloss, nbgain     out [ni]
+ *   jjlist             out [ni][2*lmax]: JJLIST(1..NBLOSS) lost, JJLIST(NNB0+1..NNB0+NBGAIN) gained (JJLIST(k) = jjlist[k-1])
+ *   nbsmin             out: members retained in this call (the caller adds it to NBSMIN, regcor_gpu.F:363-365)
+ * Every fp64 operation is the single IEEE operation the Fortran names, in its order: results are bit for bit those of an
+ * unfused host build (tests/test_regcor_gpu.py against oracle/regcor_oracle.c). */
+void gpunb_b200_regcor_(int *ni, int index_i[], int *ifirst, int *n, int *ntot, int *lmax, int new_list[], int old_list[],
+                        double rs2[], double step[], double *smin, int *nnbmax, double freg[][3], double fdr[][3],
+                        double dfirr[][3], double dfd[][3], int nbloss[], int nbgain[], int jjlist[], int *nbsmin);
+/* Device-resident list store (one row of lmax entries per particle number): lists[k] = LIST(1:LMAX, index_i[k]).
+ * put after FPOLY0 and whenever the caller edits a list itself (KS, CHECKL, ...); get reads rows back. */
+void gpunb_b200_lists_put_(int *n, int index_i[], int *lmax, int lists[]);
+void gpunb_b200_lists_get_(int *n, int index_i[], int *lmax, int lists[]);
+/* Resident STEP of the snapshot particles (idx 0-based relative to the j array, like gpunb_b200_state_update_). */
+void gpunb_b200_steps_all_(int *nj, double step[]);
+void gpunb_b200_steps_update_(int *n, int idx[], double step[]);
 
 #ifdef __cplusplus
 }

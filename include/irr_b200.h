@@ -1,9 +1,10 @@
 /*
  * irr_b200.h -- C-ABI of libirr_b200.so: the reference's irregular-force interface (irr_simd_*).
  *
- * DRAFT: the library compiles for sm_100a and its fp64 statement is pinned against the reference's AVX library on the
- * CPU, but it has not been validated on a GPU yet (tests gated behind IRR_B200_VALIDATE=1).  The regular-force library
- * (gpunb_b200.h) does not depend on it.
+ * The fp64 statement it implements is pinned against the reference's AVX library on the CPU (tests/test_irr_cpu.py) and
+ * the CUDA library reproduces it to 2e-14 on a B200 (tests/test_irr_gpu.py).  The regular-force library (gpunb_b200.h)
+ * does not depend on it.  Semantics that differ from the AVX library, both invisible to a conforming caller: set_jp /
+ * set_list are buffered on the host and reach the device with the next force call; an empty list returns nnbid = 0.
  *
  * Fortran-callable like the reference (trailing underscore, scalars by reference, 1-based particle addresses).
  */
@@ -28,6 +29,15 @@ void irr_simd_set_list_(int *addr, int *nblist);
 void irr_simd_firr_vec_(double *ti, int *ni, int addr[], double acc[][3], double jrk[][3], int nnbid[]);
 
 int irr_b200_version(void);
+
+/* Additive batch forms: the n particles a block step has just advanced / the n lists a regular block has just renewed in
+ * ONE call (entry k belongs to particle addr[k]; lists[k] has stride *lstride ints and holds [nnb, j1, ...], 1-based). */
+void irr_b200_set_jp_batch_(int *n, int addr[], double pos[][3], double vel[][3], double acc2[][3], double jrk6[][3],
+                            double mass[], double time[]);
+void irr_b200_set_list_batch_(int *n, int addr[], int *lstride, int lists[]);
+/* out[0] = device ms of the force kernel since the last call of this function (CUDA events on the library's stream),
+ * out[1] = force calls, out[2] = pair interactions since open / the last irr_simd_profile_. */
+void irr_b200_counters(double out[3]);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,7 @@
 #include <sched.h>
 #include <sys/mman.h>
 #include "../../include/gpunb_b200.h"
+#include "internal.h"
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
     fprintf(stderr, "gpunb_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, \
@@ -1843,6 +1844,7 @@ void lib_close()
 {
     if (!L.is_open) { fprintf(stderr, "gpunb: it is already close\n"); return; }   // reference: :669-672
     L.is_open = false;
+    if (!L.devs.empty()) { set_dev(L.devs[0]); CUDA_CHECK(cudaDeviceSynchronize()); gpunb_b200_internal_regcor_close(); }
     for (Dev &d : L.devs) {
         set_dev(d);
         CUDA_CHECK(cudaDeviceSynchronize());
@@ -2769,6 +2771,21 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
 }
 
 // ---- NCCL mode -------------------------------------------------------------------------------
+}  // namespace
+
+// regcor_b200.cu works on the snapshot the last send left on the root device
+bool gpunb_b200_internal_snapshot(GpunbSnapshotView *out)
+{
+    if (!L.is_open || L.devs.empty() || L.devs[0].nj_total <= 0 || !L.devs[0].jraw) return false;
+    const Dev &d = L.devs[0];
+    out->device = d.id; out->stream = d.st; out->nj = d.nj_total; out->nbmax = L.nbmax;
+    out->m = d.jraw; out->x = d.jraw + d.nj_total; out->v = d.jraw + 4 * (size_t)d.nj_total;
+    out->counters = L.ctr;
+    return true;
+}
+
+namespace {
+
 void nccl_load()
 {
     Shard &sh = L.sh;

@@ -1,0 +1,18 @@
+// internal.h -- what the translation units of libgpunb_b200.so share besides the public C-ABI (not installed, not exported).
+#pragma once
+#include <cuda_runtime.h>
+
+#define GPUNB_HIDDEN __attribute__((visibility("hidden")))
+
+// The snapshot of the last gpunb_send_ / gpunb_b200_predict_send_ as it sits on the root device: the caller's fp64 arrays
+// m[nj], x[nj][3], v[nj][3] (particle J of the Fortran program at index J - IFIRST), and the stream every call of the
+// library is ordered on.
+struct GpunbSnapshotView {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    int nj = 0, nbmax = 0;
+    const double *m = nullptr, *x = nullptr, *v = nullptr;
+    double *counters = nullptr;          // GPUNB_B200_CTR_* array of the library
+};
+GPUNB_HIDDEN bool gpunb_b200_internal_snapshot(GpunbSnapshotView *out);      // false: library closed or nothing sent yet
+GPUNB_HIDDEN void gpunb_b200_internal_regcor_close();                        // frees the buffers of regcor_b200.cu (gpunb_close_)

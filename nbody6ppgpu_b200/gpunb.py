@@ -23,12 +23,13 @@ _HERE = Path(__file__).resolve().parent
 _c_int_p = C.POINTER(C.c_int)
 _c_dbl_p = C.POINTER(C.c_double)
 
-N_COUNTERS = 26
+N_COUNTERS = 28
 CTR = dict(grav_ms=0, grav_launches=1, launches=2, h2d_bytes=3, d2h_bytes=4, interactions=5,
            merge_ms=6, pot_ms=7, near_tiles=8, all_tiles=9,
            tl_blocks=10, tl_isort_ms=11, tl_regf_ms=12, tl_merge_ms=13, tl_exch_ms=14,
            host_pack_ms=15, host_enqueue_ms=16, host_wait_ms=17, host_scatter_ms=18,
-           sends=19, send_ms=20, send_stage_ms=21, send_tiles_ms=22, transposed_tiles=23, sends_order_kept=24, host_rendezvous_ms=25)
+           sends=19, send_ms=20, send_stage_ms=21, send_tiles_ms=22, transposed_tiles=23, sends_order_kept=24, host_rendezvous_ms=25,
+           regcor_ms=26, regcor_rows=27)
 
 
 class LibraryMissing(RuntimeError):
@@ -115,6 +116,15 @@ class ForceLib:
             L.gpunb_b200_predict_send_.argtypes = [_c_int_p, _c_dbl_p]
             L.gpunb_b200_get_predicted_.argtypes = [_c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p]
             for f in (L.gpunb_b200_state_all_, L.gpunb_b200_state_update_, L.gpunb_b200_predict_send_, L.gpunb_b200_get_predicted_):
+                f.restype = None
+            L.gpunb_b200_regcor_.argtypes = ([_c_int_p] * 8 + [_c_dbl_p, _c_dbl_p, _c_dbl_p, _c_int_p] + [_c_dbl_p] * 4
+                                             + [_c_int_p] * 4)
+            L.gpunb_b200_lists_put_.argtypes = [_c_int_p] * 4
+            L.gpunb_b200_lists_get_.argtypes = [_c_int_p] * 4
+            L.gpunb_b200_steps_all_.argtypes = [_c_int_p, _c_dbl_p]
+            L.gpunb_b200_steps_update_.argtypes = [_c_int_p, _c_int_p, _c_dbl_p]
+            for f in (L.gpunb_b200_regcor_, L.gpunb_b200_lists_put_, L.gpunb_b200_lists_get_, L.gpunb_b200_steps_all_,
+                      L.gpunb_b200_steps_update_):
                 f.restype = None
         self.nj = 0
 
@@ -330,6 +340,58 @@ class ForceLib:
         x = np.zeros((n, 3)); v = np.zeros((n, 3))
         self.lib.gpunb_b200_get_predicted_(C.byref(C.c_int(n)), idx.ctypes.data_as(_c_int_p), _dp(x), _dp(v))
         return x, v
+
+    # neighbour-list bookkeeping after gpunb_regf_ (util_gpu.F:102-111 + regcor_gpu.F:267-470), batched on the device
+    def regcor(self, index_i, ifirst: int, n: int, ntot: int, new_list, old_list, rs2, step, smin: float, nnbmax: int,
+               freg, fdr, dfirr=None, dfd=None):
+        """Returns dict(nlist, nbloss, nbgain, jjlist, freg, fdr, dfirr, dfd, nbsmin); argument meaning as
+        include/gpunb_b200.h part 3 (old_list None: resident list store; step None: resident steps or no retention)."""
+        self._need_b200()
+        index_i = np.ascontiguousarray(index_i, dtype=np.int32); ni = index_i.shape[0]
+        nl = np.array(new_list, dtype=np.int32, order="C"); lmax = nl.shape[1]
+        ol = None if old_list is None else np.ascontiguousarray(old_list, dtype=np.int32)
+        if ol is not None and ol.shape != nl.shape:
+            raise ValueError("old_list and new_list differ in shape")
+        st = None if step is None else _f64(step)
+        rs2 = _f64(rs2, (ni,))
+        fr = np.array(freg, dtype=np.float64, order="C"); fd = np.array(fdr, dtype=np.float64, order="C")
+        di = np.zeros((ni, 3)) if dfirr is None else np.array(dfirr, dtype=np.float64, order="C")
+        dd = np.zeros((ni, 3)) if dfd is None else np.array(dfd, dtype=np.float64, order="C")
+        nbloss = np.zeros(ni, dtype=np.int32); nbgain = np.zeros(ni, dtype=np.int32)
+        jj = np.zeros((ni, 2 * lmax), dtype=np.int32)
+        nbsmin = C.c_int(0)
+        ip = lambda a: a.ctypes.data_as(_c_int_p)
+        self.lib.gpunb_b200_regcor_(C.byref(C.c_int(ni)), ip(index_i), C.byref(C.c_int(ifirst)), C.byref(C.c_int(n)),
+                                    C.byref(C.c_int(ntot)), C.byref(C.c_int(lmax)), ip(nl), None if ol is None else ip(ol),
+                                    _dp(rs2), None if st is None else _dp(st), C.byref(C.c_double(smin)),
+                                    C.byref(C.c_int(nnbmax)), _dp(fr), _dp(fd), _dp(di), _dp(dd), ip(nbloss), ip(nbgain),
+                                    ip(jj), C.byref(nbsmin))
+        return dict(nlist=nl, nbloss=nbloss, nbgain=nbgain, jjlist=jj, freg=fr, fdr=fd, dfirr=di, dfd=dd,
+                    nbsmin=int(nbsmin.value))
+
+    def lists_put(self, index_i, lists):
+        self._need_b200()
+        index_i = np.ascontiguousarray(index_i, dtype=np.int32); lists = np.ascontiguousarray(lists, dtype=np.int32)
+        self.lib.gpunb_b200_lists_put_(C.byref(C.c_int(index_i.shape[0])), index_i.ctypes.data_as(_c_int_p),
+                                       C.byref(C.c_int(lists.shape[1])), lists.ctypes.data_as(_c_int_p))
+
+    def lists_get(self, index_i, lmax: int):
+        self._need_b200()
+        index_i = np.ascontiguousarray(index_i, dtype=np.int32)
+        out = np.zeros((index_i.shape[0], lmax), dtype=np.int32)
+        self.lib.gpunb_b200_lists_get_(C.byref(C.c_int(index_i.shape[0])), index_i.ctypes.data_as(_c_int_p),
+                                       C.byref(C.c_int(lmax)), out.ctypes.data_as(_c_int_p))
+        return out
+
+    def steps_all(self, step):
+        self._need_b200()
+        step = _f64(step)
+        self.lib.gpunb_b200_steps_all_(C.byref(C.c_int(step.shape[0])), _dp(step))
+
+    def steps_update(self, idx, step):
+        self._need_b200()
+        idx = np.ascontiguousarray(idx, dtype=np.int32); step = _f64(step, (idx.shape[0],))
+        self.lib.gpunb_b200_steps_update_(C.byref(C.c_int(idx.shape[0])), idx.ctypes.data_as(_c_int_p), _dp(step))
 
     def set_tuning(self, nslot: int = 0, nsub: int = 0):
         """Pipeline depth: slots of a resident sweep / sub-blocks of one gpunb_regf_ call (0 = leave unchanged)."""

@@ -4,8 +4,7 @@
 (src/Main/irr.avx.cpp:565-603): ``irr_simd_open_ / close_ / profile_ / set_jp_ / set_list_ / firr_vec_`` --
 
 * ``oracle/_ref/libirr_ref_avx.so``          the reference's own AVX library (tests only),
-* ``nbody6ppgpu_b200/libirr_b200.so``         this repo's CUDA library (DRAFT: compiled and linked, not yet validated
-                                              on a GPU -- the round's GPU budget was spent on the regular-force path).
+* ``nbody6ppgpu_b200/libirr_b200.so``         this repo's CUDA library.
 
 Argument meaning follows the reference: particle addresses are 1-based; ``set_jp`` stores X0, X0DOT, F/2, FDOT/6, BODY,
 T0 of one particle (irr.avx.cpp:437-447); ``set_list`` takes the NBODY6 list ``[nnb, j1, j2, ...]`` with 1-based
@@ -45,6 +44,13 @@ class IrrLib:
         for f in (L.irr_simd_open_, L.irr_simd_close_, L.irr_simd_profile_, L.irr_simd_set_jp_, L.irr_simd_set_list_,
                   L.irr_simd_firr_vec_):
             f.restype = None
+        self.is_b200 = hasattr(L, "irr_b200_version")
+        if self.is_b200:
+            L.irr_b200_set_jp_batch_.argtypes = [_ip, _ip] + [_dp] * 6
+            L.irr_b200_set_list_batch_.argtypes = [_ip, _ip, _ip, _ip]
+            L.irr_b200_counters.argtypes = [_dp]
+            for f in (L.irr_b200_set_jp_batch_, L.irr_b200_set_list_batch_, L.irr_b200_counters):
+                f.restype = None
 
     def open(self, nmax: int, lmax: int, rank: int = 0):
         self.lib.irr_simd_open_(C.byref(C.c_int(nmax)), C.byref(C.c_int(lmax)), C.byref(C.c_int(rank)))
@@ -73,6 +79,32 @@ class IrrLib:
         self.lib.irr_simd_firr_vec_(C.byref(C.c_double(ti)), C.byref(C.c_int(ni)), addr.ctypes.data_as(_ip),
                                     acc.ctypes.data_as(_dp), jrk.ctypes.data_as(_dp), nnbid.ctypes.data_as(_ip))
         return acc, jrk, nnbid
+
+
+    # batch forms (libirr_b200.so only; the reference library takes the same data one particle per call)
+    def set_jp_batch(self, addr, pos, vel, acc2, jrk6, mass, time):
+        addr = np.ascontiguousarray(addr, dtype=np.int32); n = addr.shape[0]
+        a = [np.ascontiguousarray(q, dtype=np.float64) for q in (pos, vel, acc2, jrk6, mass, time)]
+        if self.is_b200:
+            self.lib.irr_b200_set_jp_batch_(C.byref(C.c_int(n)), addr.ctypes.data_as(_ip), *[q.ctypes.data_as(_dp) for q in a])
+        else:
+            for k in range(n):
+                self.set_jp(int(addr[k]), a[0][k], a[1][k], a[2][k], a[3][k], float(a[4][k]), float(a[5][k]))
+
+    def set_list_batch(self, addr, lists):
+        """lists[k] = [nnb, j1, ...] (1-based), rows of equal stride with >= 8 spare entries behind the longest list."""
+        addr = np.ascontiguousarray(addr, dtype=np.int32); lists = np.ascontiguousarray(lists, dtype=np.int32)
+        if self.is_b200:
+            self.lib.irr_b200_set_list_batch_(C.byref(C.c_int(addr.shape[0])), addr.ctypes.data_as(_ip),
+                                              C.byref(C.c_int(lists.shape[1])), lists.ctypes.data_as(_ip))
+        else:
+            for k in range(addr.shape[0]):
+                self.lib.irr_simd_set_list_(C.byref(C.c_int(int(addr[k]))), lists[k].ctypes.data_as(_ip))
+
+    def counters(self):
+        out = np.zeros(3)
+        self.lib.irr_b200_counters(out.ctypes.data_as(_dp))
+        return dict(kernel_ms=float(out[0]), calls=float(out[1]), interactions=float(out[2]))
 
 
 def pad_list(neigh_1based) -> np.ndarray:

@@ -74,6 +74,34 @@ class Oracle:
                                             _d(acc), _d(jrk), _d(pot), C.c_int(lmax), lst.ctypes.data_as(_ip), _d(self.scale))
         return acc, jrk, pot
 
+    def regcor(self, index_i, ifirst, n, ntot, new_list, old_list, m, x, v, rs2, step, smin, nnbmax, freg, fdr,
+               dfirr=None, dfd=None):
+        """oracle/regcor_oracle.c: util_gpu.F:102-111 + regcor_gpu.F:267-470 for a batch of rows; same argument meaning
+        and return dict as ForceLib.regcor (the snapshot is passed explicitly)."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        index_i = np.ascontiguousarray(index_i, dtype=np.int32); ni = index_i.shape[0]
+        nl = np.array(new_list, dtype=np.int32, order="C"); lmax = nl.shape[1]
+        ol = np.ascontiguousarray(old_list, dtype=np.int32)
+        m, x, v, rs2 = f(m), f(x), f(v), f(rs2)
+        st = None if step is None else f(step)
+        fr = np.array(freg, dtype=np.float64, order="C"); fd = np.array(fdr, dtype=np.float64, order="C")
+        di = np.zeros((ni, 3)) if dfirr is None else np.array(dfirr, dtype=np.float64, order="C")
+        dd = np.zeros((ni, 3)) if dfd is None else np.array(dfd, dtype=np.float64, order="C")
+        nbloss = np.zeros(ni, dtype=np.int32); nbgain = np.zeros(ni, dtype=np.int32)
+        jj = np.zeros((ni, 2 * lmax), dtype=np.int32)
+        nbsmin = C.c_int(0)
+        ip = lambda a: a.ctypes.data_as(_ip)
+        self.lib.oracle_regcor.restype = None
+        import time as _t
+        _t0 = _t.perf_counter()
+        self.lib.oracle_regcor(C.c_int(ni), ip(index_i), C.c_int(ifirst), C.c_int(n), C.c_int(ntot), C.c_int(lmax), ip(nl),
+                               ip(ol), _d(m), _d(x), _d(v), _d(rs2), None if st is None else _d(st), C.c_double(smin),
+                               C.c_int(nnbmax), _d(fr), _d(fd), _d(di), _d(dd), ip(nbloss), ip(nbgain), ip(jj),
+                               C.byref(nbsmin))
+        self.last_regcor_s = _t.perf_counter() - _t0          # the C call alone
+        return dict(nlist=nl, nbloss=nbloss, nbgain=nbgain, jjlist=jj, freg=fr, fdr=fd, dfirr=di, dfd=dd,
+                    nbsmin=int(nbsmin.value))
+
     def pot_f64(self, istart, ni, m, x):
         m = np.ascontiguousarray(m, dtype=np.float64); x = np.ascontiguousarray(x, dtype=np.float64)
         pot = np.zeros(ni)

@@ -1,0 +1,114 @@
+"""libirr_b200.so on the GPU: batch entry points against the fp64 statement, and the latency / gather-rate table against the
+reference's own AVX library (oracle/_ref/libirr_ref_avx.so, all host threads) at the block sizes of intgrt.F:545."""
+import json
+import os
+import time
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from nbody6ppgpu_b200 import irr
+from nbody6ppgpu_b200 import snapshots as S
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+REF = ROOT / "oracle" / "_ref" / "libirr_ref_avx.so"
+
+
+def make(n, nnb, seed=1):
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    m, x, v = S.plummer(n, seed, "kroupa")
+    a2 = 0.5 * rng.normal(size=(n, 3)); j6 = rng.normal(size=(n, 3)) / 6.0
+    t0 = rng.integers(0, 16, size=n) * 2.0 ** -10
+    idx = np.sort(cKDTree(x).query(x, k=nnb + 1)[1][:, 1:], axis=1) + 1            # 1-based, ascending, self excluded
+    stride = 1 + 8 * ((nnb + 7) // 8) + 8
+    lists = np.zeros((n, stride), dtype=np.int32)
+    lists[:, 0] = nnb; lists[:, 1:1 + nnb] = idx
+    return m, x, v, a2, j6, t0, lists
+
+
+def fill(lib, case, batch):
+    m, x, v, a2, j6, t0, lists = case
+    n = m.shape[0]
+    addr = np.arange(1, n + 1, dtype=np.int32)
+    if batch:
+        lib.set_jp_batch(addr, x, v, a2, j6, m, t0)
+        lib.set_list_batch(addr, lists)
+    else:
+        for i in range(n):
+            lib.set_jp(i + 1, x[i], v[i], a2[i], j6[i], m[i], t0[i])
+            lib.lib.irr_simd_set_list_(irr.C.byref(irr.C.c_int(i + 1)), lists[i].ctypes.data_as(irr._ip))
+
+
+def test_batch_entry_points_and_large_block():
+    case = make(20000, 48, seed=3)
+    m, x, v, a2, j6, t0, lists = case
+    n = m.shape[0]
+    lib = irr.IrrLib(irr.lib_path())
+    lib.open(n, lists.shape[1], 0)
+    try:
+        fill(lib, case, batch=True)
+        # some particles advance: their records change before the next force call (the later values win)
+        adv = np.arange(5, n, 97, dtype=np.int32)
+        x2 = x.copy(); x2[adv] += 1e-3
+        t2 = t0.copy(); t2[adv] = 2.0 ** -6
+        lib.set_jp_batch(adv + 1, x2[adv], v[adv], a2[adv], j6[adv], m[adv], t2[adv])
+        addr = np.arange(1, n + 1, dtype=np.int32)                                   # the whole system in one call (> 1024: device copy path)
+        acc, jrk, nn = lib.firr_vec(0.02, addr)
+        small = addr[:700]                                                           # <= 1024: mapped address path
+        acc_s, jrk_s, nn_s = lib.firr_vec(0.02, small)
+    finally:
+        lib.close(0)
+    a64, j64, n64 = irr.firr_f64(0.02, addr, [r[1:1 + r[0]] for r in lists], x2, v, a2, j6, m, t2)
+    rel = lambda a, b: float(np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)))
+    assert rel(acc, a64) < 1e-11 and rel(jrk, j64) < 1e-10
+    assert np.array_equal(nn, n64)
+    assert np.array_equal(acc_s, acc[:700]) and np.array_equal(jrk_s, jrk[:700]) and np.array_equal(nn_s, nn[:700])
+
+
+def test_latency_table_against_the_reference_avx_library():
+    if not REF.exists():
+        pytest.skip("oracle/_ref/libirr_ref_avx.so not built")
+    n, nnb = int(os.environ.get("IRR_TABLE_N", "100000")), 64
+    case = make(n, nnb)
+    rng = np.random.default_rng(5)
+    blocks = {ni: np.sort(rng.choice(n, ni, replace=False)).astype(np.int32) + 1 for ni in (1, 32, 1024, 16384)}
+    table = {}
+    results = {}
+    for name, path, batch in (("b200", irr.lib_path(), True), ("ref_avx", REF, False)):
+        lib = irr.IrrLib(path)
+        lib.open(n, case[6].shape[1], 0)
+        try:
+            fill(lib, case, batch)
+            row = {}
+            for ni, addr in blocks.items():
+                lib.firr_vec(0.003, addr)
+                if name == "b200":
+                    lib.counters()
+                reps = 200 if ni <= 1024 else 30
+                t = time.perf_counter()
+                for _ in range(reps):
+                    out = lib.firr_vec(0.003, addr)
+                dt = (time.perf_counter() - t) / reps
+                row[ni] = {"us_per_call": dt * 1e6, "gint_per_s": ni * nnb / dt * 1e-9}
+                if name == "b200":
+                    ms = lib.counters()["kernel_ms"] / reps
+                    row[ni]["kernel_us"] = ms * 1e3
+                    row[ni]["gathered_gb_per_s_kernel"] = ni * (nnb + 1) * 128 / (ms * 1e-3) * 1e-9
+                results[(name, ni)] = out
+            table[name] = row
+        finally:
+            lib.close(0)
+    for ni in blocks:                      # the two libraries agree to the reference's FP32 accuracy, same nearest neighbours
+        (ab, jb, nb_), (ar, jr, nr) = results[("b200", ni)], results[("ref_avx", ni)]
+        rel = lambda a, b: float(np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)))
+        assert rel(ar, ab) < 1e-5 and rel(jr, jb) < 1e-4, ni
+        assert np.mean(nb_ == nr) > 0.999, ni
+    out = {"n": n, "nnb": nnb, "host_threads": int(os.environ.get("OMP_NUM_THREADS", "0")), "table": table,
+           "note": "us per irr_simd_firr_vec_ call through the same ctypes caller; record = 128 B per gathered neighbour"}
+    print(json.dumps(out, indent=1))
+    if os.environ.get("GPUNB_IRR_OUT"):
+        Path(os.environ["GPUNB_IRR_OUT"]).write_text(json.dumps(out, indent=1))
+    # recorded, not asserted: which library wins depends on the block size (launch latency vs host cores) -- DESIGN.md section 7
