@@ -73,6 +73,12 @@ def parse():
                     "its static arrays once with gpunb_b200_pin_host_; the other kind is reported beside it)")
     ap.add_argument("--quick", action="store_true", help="skip the secondary legs (pageable e2e, other configs, reference CUDA library)")
     ap.add_argument("--ref-cuda-probe", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--time-unit", action="store_true", help="second half of the metric alone: wall s per N-body time unit of the "
+                    "Ahmad-Cohen driver at N=16k (samples/N16k.input: NNBOPT=100, KZ(39)=2) behind this library, the reference CUDA "
+                    "library and the reference AVX library, with dE/E for each; prints one JSON line")
+    ap.add_argument("--time-unit-probe", default="", help=argparse.SUPPRESS)      # (subprocess) one library: b200 | b200_host | ref_cuda | ref_avx
+    ap.add_argument("--tu-n", type=int, default=16000)
+    ap.add_argument("--tu-t", type=float, default=1.0, help="N-body time units integrated by --time-unit (multiple of 0.125)")
     return ap.parse_args()
 
 
@@ -367,6 +373,57 @@ def run_ref_cuda_probe(n, m_flag, local):
         return {"unavailable": repr(e)[:200]}
 
 
+TU_WORKLOAD = ("Plummer N={n} Kroupa IMF, NNBOPT=100, LMAX=400, mass-weighted neighbour criterion (m_flag=1, KZ(39)=2), SMAX=0.125, "
+               "ETAI=ETAR=0.02 as samples/N16k.input; Ahmad-Cohen block-step driver nbody6ppgpu_b200/hermite_ac.py (no KS, no stellar evolution)")
+
+
+def time_unit_probe(args):
+    """(subprocess) integrate --tu-t N-body time units behind ONE regular-force library.  The irregular force always goes
+    through this repo's libirr_b200.so (the same for every arm, so the arms differ in the regular-force library only);
+    `b200` also uses the device-resident predictor and gpunb_b200_regcor_, `b200_host` keeps those on the host like the
+    reference arms do."""
+    from nbody6ppgpu_b200 import hermite_ac as H, irr, snapshots as S
+    from nbody6ppgpu_b200.gpunb import ForceLib, load
+    kind = args.time_unit_probe
+    so = {"ref_cuda": ROOT / "oracle" / "_ref" / "libgpunb_ref_gpu.so", "ref_avx": ROOT / "oracle" / "_ref" / "libgpunb_ref_avx.so"}.get(kind)
+    if so is not None and not so.exists():
+        emit({"unavailable": f"{so.name} not built"})
+        return
+    lib = load() if so is None else ForceLib(so)
+    lib.devinit(0)
+    n, T = args.tu_n, args.tu_t
+    m, x, v = S.plummer(n, 5, "kroupa")
+    dev = kind == "b200"
+    t0 = time.perf_counter()
+    ac = H.AhmadCohen(lib, m, x, v, nnbopt=100, lmax=400, m_flag=1, dtmax=0.125, irr_lib=irr.IrrLib(irr.lib_path()),
+                      device_predictor=dev, use_regcor=dev)
+    t_init = time.perf_counter() - t0
+    try:
+        st = ac.run(T)
+    finally:
+        ac.close()
+    e0, e1 = st.energies[0][1], st.energies[-1][1]
+    emit({"library": {"b200": "libgpunb_b200.so + device-resident predictor + gpunb_b200_regcor_", "b200_host": "libgpunb_b200.so (reference ABI only)",
+                      "ref_cuda": "reference gpunb.velocity.cu + gpupot.gpu.cu (sm_100, oracle/_ref)",
+                      "ref_avx": f"reference reg.avx.cpp + pot.avx.cpp (oracle/_ref, {os.environ.get('OMP_NUM_THREADS')} threads)"}[kind],
+          "wall_s_per_time_unit": st.wall_total / T, "t_integrated": T, "dE_over_E": (e1 - e0) / abs(e0), "E0": e0,
+          "block_steps": st.block_steps, "irr_steps": st.irr_steps, "reg_steps": st.reg_steps, "reg_blocks": st.reg_blocks,
+          "regf_calls": st.regf_calls, "overflow_retries": st.overflow_retries, "init_s": t_init,
+          "wall_breakdown_s": {"gpunb_send_or_predict_send": st.wall_send, "gpunb_regf": st.wall_regf, "regcor": st.wall_regcor,
+                               "irr_firr_vec": st.wall_irr, "driver_numpy": st.wall_total - st.wall_send - st.wall_regf - st.wall_regcor - st.wall_irr}})
+
+
+def run_time_unit_probe(kind, n, T, local, timeout=1500):
+    try:
+        env = dict(os.environ, GPU_LIST=str(local), OMP_NUM_THREADS=str(cpu_threads()))
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--time-unit-probe", kind, "--tu-n", str(n), "--tu-t", str(T)],
+                           capture_output=True, text=True, timeout=timeout, env=env)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"unavailable": (r.stderr or "no output")[-300:]}
+    except Exception as e:                                   # never fatal for the bench line
+        return {"unavailable": repr(e)[:200]}
+
+
 def main():
     args = parse()
     quiet_stdout()
@@ -377,6 +434,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.ref_cuda_probe:
         ref_cuda_probe(args)
+        return
+    if args.time_unit_probe:
+        time_unit_probe(args)
+        return
+    if args.time_unit:
+        if rank == 0:
+            arms = {k: run_time_unit_probe(k, args.tu_n, args.tu_t, local) for k in ("b200", "b200_host", "ref_cuda", "ref_avx")}
+            emit({"metric": "wall s per N-body time unit", "unit": "s", "higher_is_better": False, "n_gpus": 1,
+                  "config": {"workload": TU_WORKLOAD.format(n=args.tu_n)}, "value": arms["b200"].get("wall_s_per_time_unit"), "arms": arms})
         return
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -573,9 +639,14 @@ def main():
 
     configs = None
     ref_cuda = None
+    time_unit = None
     if world == 1 and not args.quick and n >= 500_000:
         configs = {"N256k_mflag0": quick_config(262144, 0), "N16k_mflag1": quick_config(16000, 1)}
         ref_cuda = run_ref_cuda_probe(n, args.m_flag, local)
+        # second half of BASELINE.json's metric, on a bounded sample: 1/8 time unit at N=16k behind this library
+        # (`python bench.py --time-unit` integrates a whole unit behind this and both reference libraries)
+        time_unit = run_time_unit_probe("b200", 16000, 0.125, local, timeout=300)
+        time_unit["workload"] = TU_WORKLOAD.format(n=16000)
 
     if world > 1:
         barrier()
@@ -659,6 +730,9 @@ def main():
         out["configs"] = configs
     if ref_cuda is not None:
         out["ref_cuda"] = ref_cuda
+    if time_unit is not None:
+        out["time_unit"] = time_unit
+        out["wall_s_per_time_unit"] = time_unit.get("wall_s_per_time_unit")
 
     if not args.no_cpu_baseline and rank == 0:
         threads = cpu_threads()

@@ -19,8 +19,19 @@ identical snapshots, and the energy errors laid side by side:
                        volume rule with a stabilising factor);
   * energy          -- kinetic energy + potential from ``gpupot_`` (energy.F / gpupot.gpu.cu).
 
-What it deliberately leaves out: KS / chain regularisation, stellar evolution, external tides, the full RS control logic.
-Host arithmetic is numpy fp64; the driver is a measurement harness, not a production integrator.
+Optional device paths (this repo's libraries only; the reference libraries run the host statements of the same steps):
+
+  * ``irr_lib``     -- an ``irr.IrrLib`` (libirr_b200.so, or the reference's AVX library) takes the irregular force
+                       (``irr_simd_firr_vec_``: the library predicts the neighbours itself, so the host predicts only the
+                       active particles); the driver feeds it ``set_jp`` after every corrector and ``set_list`` after every
+                       regular step, batched (intgrt.F:199-207,545);
+  * ``use_regcor``  -- ``gpunb_b200_regcor_`` does the list bookkeeping of a regular block on the device: NLIST, and the force
+                       swap DFIRR / DFD that turns the irregular force over the old list into the one over the new list
+                       (regcor_gpu.F:267-470) -- the host neither diffs lists nor sums the changed members.
+
+What it deliberately leaves out: KS / chain regularisation, stellar evolution, external tides, the full RS control logic,
+retention of small-step neighbours (SMIN is not used).  Host arithmetic is numpy fp64; the driver is a measurement harness,
+not a production integrator.
 """
 from __future__ import annotations
 
@@ -43,6 +54,9 @@ class ACStats:
     wall_regf: float = 0.0
     wall_send: float = 0.0
     wall_total: float = 0.0
+    wall_irr: float = 0.0
+    wall_regcor: float = 0.0
+    block_steps: int = 0
     energies: list = field(default_factory=list)      # (t, E)
 
 
@@ -54,8 +68,12 @@ def _pow2_floor(dt, dtmax):
 
 class AhmadCohen:
     def __init__(self, lib, m, x, v, *, nnbopt=40, lmax=128, eta_i=0.02, eta_r=0.02, dtmax=0.125, dtmin=2.0 ** -22,
-                 m_flag=0, rs0=None, device_predictor=False):
+                 m_flag=0, rs0=None, device_predictor=False, irr_lib=None, use_regcor=False):
         self.lib = lib
+        self.irr = irr_lib
+        self.use_regcor = bool(use_regcor)
+        if self.use_regcor and not getattr(lib, "is_b200", False):
+            raise ValueError("use_regcor needs libgpunb_b200.so (gpunb_b200_regcor_)")
         # device_predictor: regular blocks call gpunb_b200_predict_send_ (state kept on the device, updated with the
         # particles advanced since the last regular block) instead of uploading the host-predicted snapshot
         self.device_predictor = bool(device_predictor)
@@ -83,10 +101,34 @@ class AhmadCohen:
         self.nnb = np.zeros(n, dtype=np.int64)
         self.stats = ACStats()
         lib.open(n + 10, 0)
+        if self.irr is not None:
+            self.lstride = 1 + 8 * ((self.nnbmax + 8) // 8) + 8
+            self.irr.open(n, self.lstride, 0)
         self._initial_forces()
 
     def close(self):
         self.lib.close()
+        if self.irr is not None:
+            self.irr.close(0)
+
+    # ---- irregular-force library feeds (intgrt.F:199-207: set_jp after the corrector, set_list after a regular step) ----
+    def _irr_push_particles(self, idx):
+        self.irr.set_jp_batch(idx.astype(np.int32) + 1, self.x0[idx], self.v0[idx], 0.5 * self.f[idx],
+                              self.fd[idx] * (1.0 / 6.0), self.m[idx], self.t0[idx])
+
+    def _irr_push_lists(self, idx):
+        rows = np.zeros((idx.size, self.lstride), dtype=np.int32)
+        rows[:, 0] = self.nnb[idx]
+        k = self.nb.shape[1]
+        rows[:, 1:1 + k] = np.where(self.nb[idx] >= 0, self.nb[idx] + 1, 0)
+        self.irr.set_list_batch(idx.astype(np.int32) + 1, rows)
+
+    def _predict_idx(self, idx, t):
+        s = (t - self.t0[idx])[:, None]
+        f2, fd6 = 0.5 * self.f[idx], self.fd[idx] * (1.0 / 6.0)
+        xp = ((fd6 * s + f2) * s + self.v0[idx]) * s + self.x0[idx]
+        vp = (fd6 * (1.5 * s) + f2) * (2.0 * s) + self.v0[idx]
+        return xp, vp
 
     # ---- force pieces ------------------------------------------------------------------------
     def _predict(self, t):
@@ -125,8 +167,10 @@ class AhmadCohen:
         fd = (mr3[:, :, None] * (dv - rv[:, :, None] * dx)).sum(1)
         return fi, fd
 
-    def _regular(self, idx, xp, vp, t=0.0):
-        """gpunb_send_ + gpunb_regf_ over the block idx; returns (fr, frd, lists[-1 padded], counts)."""
+    def _regular(self, idx, xp, vp, t=0.0, xi=None, vi=None, raw=False):
+        """gpunb_send_ + gpunb_regf_ over the block idx; returns (fr, frd, lists[-1 padded], counts).
+        xp, vp: predicted snapshot of all particles (None with the device predictor: nothing is uploaded); xi, vi: the
+        block's own predicted positions when xp is None.  raw: also return the untouched gpunb_regf_ rows."""
         st = self.stats
         t0 = time.perf_counter()
         if self.device_predictor and self._dirty is not None:
@@ -138,6 +182,9 @@ class AhmadCohen:
         else:
             self.lib.send(self.m, xp, vp)
         st.wall_send += time.perf_counter() - t0
+        if xi is None:
+            xi, vi = xp[idx], vp[idx]
+        raw_rows = []
         nreg = idx.size
         fr = np.zeros((nreg, 3)); frd = np.zeros((nreg, 3))
         lists = np.full((nreg, self.nnbmax + 1), -1, dtype=np.int64)
@@ -147,7 +194,8 @@ class AhmadCohen:
             while True:
                 h2 = self.rs[sel] ** 2 / (self.bodym if self.m_flag else 1.0)
                 t0 = time.perf_counter()
-                acc, jrk, pot, lst = self.lib.regf(h2, self.dtr[sel], xp[sel], vp[sel], self.lmax, self.nnbmax, self.m_flag)
+                acc, jrk, pot, lst = self.lib.regf(h2, self.dtr[sel], xi[c0:c0 + MAXTHR], vi[c0:c0 + MAXTHR], self.lmax,
+                                                   self.nnbmax, self.m_flag)
                 st.wall_regf += time.perf_counter() - t0
                 st.regf_calls += 1
                 over = lst[:, 0] < 0
@@ -159,19 +207,55 @@ class AhmadCohen:
                 self.rs[sel[over]] *= scale
                 st.overflow_retries += 1
             fr[c0:c0 + sel.size] = acc; frd[c0:c0 + sel.size] = jrk
-            for r in range(sel.size):          # util_gpu.F:102-111: drop self, keep ascending order
-                row = lst[r, 1:1 + lst[r, 0]]
-                row = row[row != sel[r]]
-                lists[c0 + r, :row.size] = row
-                counts[c0 + r] = row.size
+            if raw:                            # the rows go to gpunb_b200_regcor_ as they are
+                raw_rows.append(lst.copy())
+                continue
+            # util_gpu.F:102-111: drop self, keep ascending order (all rows at once)
+            body = lst[:, 1:]
+            keep = (np.arange(body.shape[1])[None, :] < lst[:, :1]) & (body != sel[:, None])
+            pos = np.cumsum(keep, axis=1) - 1
+            rr, cc = np.nonzero(keep)
+            lists[c0 + rr, pos[rr, cc]] = body[rr, cc]
+            counts[c0:c0 + sel.size] = keep.sum(1)
+        if raw:
+            return fr, frd, np.concatenate(raw_rows), None
         return fr, frd, lists, counts
+
+    def _regcor(self, idx, rows):
+        """gpunb_b200_regcor_ on the rows gpunb_regf_ just returned for the block idx: (lists[-1 padded], counts, dfirr, dfd)."""
+        t0 = time.perf_counter()
+        old = np.zeros((idx.size, self.lmax), dtype=np.int32)
+        old[:, 0] = self.nnb[idx]
+        k = min(self.nb.shape[1], self.lmax - 1)
+        old[:, 1:1 + k] = np.where(self.nb[idx, :k] >= 0, self.nb[idx, :k] + 1, 0)
+        z = np.zeros((idx.size, 3))
+        out = self.lib.regcor(idx.astype(np.int32) + 1, 1, self.n, self.n, rows, old, self.rs[idx] ** 2, None, 0.0,
+                              self.nnbmax, z, z)
+        nl = out["nlist"]
+        counts = nl[:, 0].astype(np.int64)
+        lists = np.full((idx.size, self.nnbmax + 1), -1, dtype=np.int64)
+        kk = min(lists.shape[1], self.lmax - 1)
+        ar = np.arange(kk)[None, :]
+        lists[:, :kk] = np.where(ar < counts[:, None], nl[:, 1:1 + kk].astype(np.int64) - 1, -1)
+        self.stats.wall_regcor += time.perf_counter() - t0
+        return lists, counts, out["dfirr"], out["dfd"]
+
+    def _firr(self, idx, t):
+        t0 = time.perf_counter()
+        acc, jrk, _ = self.irr.firr_vec(t, idx.astype(np.int32) + 1)
+        self.stats.wall_irr += time.perf_counter() - t0
+        return acc, jrk
 
     def _initial_forces(self):
         idx = np.arange(self.n)
         fr, frd, lists, counts = self._regular(idx, self.x0, self.v0)
-        fi, fid = self._irregular(idx, self.x0, self.v0, lists, counts)
-        self.fr, self.frd, self.fi, self.fid = fr, frd, fi, fid
         self.nb[:, :lists.shape[1]] = lists; self.nnb = counts
+        if self.irr is not None:               # records without F / FDOT yet: at t = t0 the prediction does not use them
+            self._irr_push_particles(idx); self._irr_push_lists(idx)
+            fi, fid = self._firr(idx, 0.0)
+        else:
+            fi, fid = self._irregular(idx, self.x0, self.v0, lists, counts)
+        self.fr, self.frd, self.fi, self.fid = fr, frd, fi, fid
         self.f = fi + fr; self.fd = fid + frd
         # starting steps from F and FDOT only (no higher derivatives yet)
         fa = np.linalg.norm(self.f, axis=1); fda = np.linalg.norm(self.fd, axis=1) + 1e-300
@@ -182,6 +266,8 @@ class AhmadCohen:
         self.dt = np.maximum(_pow2_floor(dt_i, self.dtmax), self.dtmin)
         self.dtr = np.maximum(_pow2_floor(np.maximum(dt_r, self.dt), self.dtmax), self.dt)
         self._adjust_rs(idx, counts)
+        if self.irr is not None:
+            self._irr_push_particles(idx)
         if self.device_predictor:
             self._push_state()
             self._dirty = np.zeros(self.n, dtype=bool)
@@ -211,7 +297,14 @@ class AhmadCohen:
         st = self.stats
         tn = float((self.t0 + self.dt).min())
         act = np.nonzero(self.t0 + self.dt == tn)[0]
-        xp, vp = self._predict(tn)
+        use_irr = self.irr is not None
+        st.block_steps += 1
+        if use_irr:                                # the library predicts the neighbours itself: the host predicts the actives only
+            xa, va = self._predict_idx(act, tn)
+            xp = vp = None
+        else:
+            xp, vp = self._predict(tn)
+            xa, va = xp[act], vp[act]
         isreg = self.t0r[act] + self.dtr[act] <= tn
         reg = act[isreg]
         dti = tn - self.t0[act]
@@ -219,12 +312,31 @@ class AhmadCohen:
         fr_new = self.fr[act] + self.frd[act] * (tn - self.t0r[act])[:, None]        # intgrt.F:284-293
         frd_new = self.frd[act].copy()
         lists = self.nb[act]; counts = self.nnb[act]
+        fi_act = None
+        if use_irr:                                # irregular force of every active particle over the list it holds (old lists)
+            fi_act, fid_act = self._firr(act, tn)
         if reg.size:
             st.reg_blocks += 1; st.reg_steps += reg.size
             # regular polynomial over the OLD list at both ends (list changes corrected, regcor_gpu.F:510-552)
-            fi_old, fid_old = self._irregular(reg, xp, vp, self.nb[reg], self.nnb[reg])
-            frn, frdn, lnew, cnew = self._regular(reg, xp, vp, tn)
-            fin, fidn = self._irregular(reg, xp, vp, lnew, cnew)
+            if use_irr:
+                fi_old, fid_old = fi_act[isreg], fid_act[isreg]
+                if not self.device_predictor:
+                    xp, vp = self._predict(tn)     # the snapshot gpunb_send_ uploads
+            else:
+                fi_old, fid_old = self._irregular(reg, xp, vp, self.nb[reg], self.nnb[reg])
+            if self.use_regcor:
+                # the device diffs the lists and returns the force swap: F_irr(new list) = F_irr(old list) + DFIRR
+                frn, frdn, rows, _ = self._regular(reg, xp, vp, tn, xi=xa[isreg], vi=va[isreg], raw=True)
+                lnew, cnew, dfi, dfd = self._regcor(reg, rows)
+                fin, fidn = fi_old + dfi, fid_old + dfd
+            else:
+                frn, frdn, lnew, cnew = self._regular(reg, xp, vp, tn, xi=xa[isreg], vi=va[isreg])
+                if use_irr:
+                    self.nb[reg] = lnew; self.nnb[reg] = cnew
+                    self._irr_push_lists(reg)
+                    fin, fidn = self._firr(reg, tn)
+                else:
+                    fin, fidn = self._irregular(reg, xp, vp, lnew, cnew)
             ftot, fdtot = fin + frn, fidn + frdn
             fr_oldlist, frd_oldlist = ftot - fi_old, fdtot - fid_old
             dtr = tn - self.t0r[reg]
@@ -233,12 +345,19 @@ class AhmadCohen:
             fr_new[isreg] = frn; frd_new[isreg] = frdn
             lists = lists.copy(); counts = counts.copy()
             lists[isreg] = lnew; counts[isreg] = cnew
-        fi_new, fid_new = self._irregular(act, xp, vp, lists, counts)
+        if use_irr or self.use_regcor:
+            if fi_act is None:
+                fi_act, fid_act = self._irregular(act, xp, vp, self.nb[act], self.nnb[act])
+            fi_new, fid_new = fi_act.copy(), fid_act.copy()
+            if reg.size:
+                fi_new[isreg] = fin; fid_new[isreg] = fidn
+        else:
+            fi_new, fid_new = self._irregular(act, xp, vp, lists, counts)
         f1, fd1 = fi_new + fr_new, fid_new + frd_new
         a2, a3 = self._hermite_coeffs(self.f[act], self.fd[act], f1, fd1, dti)
         d = dti[:, None]
-        self.x0[act] = xp[act] + d ** 4 / 24.0 * a2 + d ** 5 / 120.0 * a3
-        self.v0[act] = vp[act] + d ** 3 / 6.0 * a2 + d ** 4 / 24.0 * a3
+        self.x0[act] = xa + d ** 4 / 24.0 * a2 + d ** 5 / 120.0 * a3
+        self.v0[act] = va + d ** 3 / 6.0 * a2 + d ** 4 / 24.0 * a3
         self.t0[act] = tn
         self.fi[act], self.fid[act] = fi_new, fid_new
         self.f[act], self.fd[act] = f1, fd1
@@ -263,12 +382,16 @@ class AhmadCohen:
             qr = np.where(dbl, 2.0 * oldr, qr)
             self.dtr[reg] = np.maximum(qr, self.dt[reg])
             self._adjust_rs(reg, cnew)
+            if use_irr:
+                self._irr_push_lists(reg)
         else:
             # the regular force of non-regular actives stays a linear extrapolation from t0r
             pass
         # an irregular step never exceeds the distance to the particle's next regular time
         nxt = self.t0r[act] + self.dtr[act] - tn
         self.dt[act] = np.where(nxt > 0, np.minimum(self.dt[act], _pow2_floor(nxt, self.dtmax)), self.dt[act])
+        if use_irr:
+            self._irr_push_particles(act)
         self.t = tn
         st.t = tn
 

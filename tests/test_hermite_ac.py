@@ -66,3 +66,52 @@ def test_ac_driver_with_imf_and_mass_weighted_criterion(ref_avx):
     assert abs((e1 - e0) / e0) < 5e-4, (e0, e1)
     assert st.reg_steps > 384 and np.all(ac.t0 == 0.125)
     assert ac.nnb.max() <= ac.nnbmax
+
+
+def test_ac_driver_with_the_irregular_force_library(ref_avx):
+    """The driver's library path for the irregular force (set_jp / set_list / firr_vec, intgrt.F:199-207,545) with the
+    reference's own AVX libraries on both sides: same block structure as the numpy path, energy conserved."""
+    from pathlib import Path
+    from nbody6ppgpu_b200 import irr
+    so = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "libirr_ref_avx.so"
+    if ref_avx is None or not so.exists():
+        pytest.skip("oracle/_ref not built")
+    m, x, v = S.plummer(256, 5, "equal")
+    ac = H.AhmadCohen(ref_avx, m, x, v, nnbopt=30, irr_lib=irr.IrrLib(so))
+    try:
+        st = ac.run(0.25)
+    finally:
+        ac.close()
+    e0, e1 = st.energies[0][1], st.energies[-1][1]
+    assert abs((e1 - e0) / e0) < 2e-4, (e0, e1)          # the AVX library predicts and sums in FP32
+    assert st.t == 0.25 and st.irr_steps > st.reg_steps > 256 and st.wall_irr > 0
+    for i in range(0, 256, 17):
+        row = ac.nb[i, :ac.nnb[i]]
+        assert np.all(np.diff(row) > 0) and i not in row
+
+
+@pytest.mark.gpu
+def test_device_paths_of_the_driver(b200):
+    """Irregular force through libirr_b200.so, list bookkeeping through gpunb_b200_regcor_, snapshot from the device-resident
+    predictor: the same integration as the host statements of those steps (numpy), to rounding."""
+    from nbody6ppgpu_b200 import irr
+    m, x, v = S.plummer(1024, 5, "kroupa")
+    out = {}
+    for name, kw in (("host", {}),
+                     ("irr", dict(irr_lib=irr.IrrLib(irr.lib_path()))),
+                     ("device", dict(irr_lib=irr.IrrLib(irr.lib_path()), use_regcor=True, device_predictor=True))):
+        ac = H.AhmadCohen(b200, m, x, v, nnbopt=40, m_flag=1, **kw)
+        try:
+            st = ac.run(0.25)
+        finally:
+            ac.close()
+        e0, e1 = st.energies[0][1], st.energies[-1][1]
+        out[name] = dict(de=(e1 - e0) / abs(e0), irr=st.irr_steps, reg=st.reg_steps, blocks=st.block_steps, wall=st.wall_total,
+                         x=ac.x0.copy(), nnb=float(ac.nnb.mean()))
+        print(name, {k: out[name][k] for k in ("de", "irr", "reg", "blocks", "wall", "nnb")})
+    for name in ("irr", "device"):
+        assert abs(out[name]["de"]) < 1e-4
+        # same block structure up to the few steps a last-bit difference in a force can shift
+        assert abs(out[name]["irr"] - out["host"]["irr"]) < 0.02 * out["host"]["irr"]
+        assert abs(out[name]["reg"] - out["host"]["reg"]) < 0.02 * out["host"]["reg"]
+        assert np.median(np.linalg.norm(out[name]["x"] - out["host"]["x"], axis=1)) < 1e-6
