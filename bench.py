@@ -374,43 +374,35 @@ def run_ref_cuda_probe(n, m_flag, local):
 
 
 TU_WORKLOAD = ("Plummer N={n} Kroupa IMF, NNBOPT=100, LMAX=400, mass-weighted neighbour criterion (m_flag=1, KZ(39)=2), SMAX=0.125, "
-               "ETAI=ETAR=0.02 as samples/N16k.input; Ahmad-Cohen block-step driver nbody6ppgpu_b200/hermite_ac.py (no KS, no stellar evolution)")
+               "ETAI=ETAR=0.02 as samples/N16k.input; Ahmad-Cohen block-step driver nbody6ppgpu_b200/csrc/ac_driver.cpp (no KS, no stellar evolution)")
 
 
 def time_unit_probe(args):
-    """(subprocess) integrate --tu-t N-body time units behind ONE regular-force library.  The irregular force always goes
+    """(subprocess) integrate --tu-t N-body time units behind ONE regular-force library with the native driver
+    (csrc/ac_driver.cpp; its Python twin hermite_ac.py gives the same integration bit for bit).  The irregular force always goes
     through this repo's libirr_b200.so (the same for every arm, so the arms differ in the regular-force library only);
     `b200` also uses the device-resident predictor and gpunb_b200_regcor_, `b200_host` keeps those on the host like the
     reference arms do."""
-    from nbody6ppgpu_b200 import hermite_ac as H, irr, snapshots as S
-    from nbody6ppgpu_b200.gpunb import ForceLib, load
+    from nbody6ppgpu_b200 import ac_native, irr, lib_path, snapshots as S
     kind = args.time_unit_probe
-    so = {"ref_cuda": ROOT / "oracle" / "_ref" / "libgpunb_ref_gpu.so", "ref_avx": ROOT / "oracle" / "_ref" / "libgpunb_ref_avx.so"}.get(kind)
-    if so is not None and not so.exists():
+    so = {"ref_cuda": ROOT / "oracle" / "_ref" / "libgpunb_ref_gpu.so", "ref_avx": ROOT / "oracle" / "_ref" / "libgpunb_ref_avx.so"}.get(kind, lib_path())
+    if not so.exists():
         emit({"unavailable": f"{so.name} not built"})
         return
-    lib = load() if so is None else ForceLib(so)
-    lib.devinit(0)
     n, T = args.tu_n, args.tu_t
     m, x, v = S.plummer(n, 5, "kroupa")
     dev = kind == "b200"
-    t0 = time.perf_counter()
-    ac = H.AhmadCohen(lib, m, x, v, nnbopt=100, lmax=400, m_flag=1, dtmax=0.125, irr_lib=irr.IrrLib(irr.lib_path()),
-                      device_predictor=dev, use_regcor=dev)
-    t_init = time.perf_counter() - t0
-    try:
-        st = ac.run(T)
-    finally:
-        ac.close()
-    e0, e1 = st.energies[0][1], st.energies[-1][1]
+    st, _, _ = ac_native.run(so, irr.lib_path(), m, x, v, T, nnbopt=100, lmax=400, m_flag=1, dtmax=0.125, use_predictor=dev, use_regcor=dev)
+    libs = st["wall_send"] + st["wall_regf"] + st["wall_regcor"] + st["wall_irr"]
     emit({"library": {"b200": "libgpunb_b200.so + device-resident predictor + gpunb_b200_regcor_", "b200_host": "libgpunb_b200.so (reference ABI only)",
                       "ref_cuda": "reference gpunb.velocity.cu + gpupot.gpu.cu (sm_100, oracle/_ref)",
                       "ref_avx": f"reference reg.avx.cpp + pot.avx.cpp (oracle/_ref, {os.environ.get('OMP_NUM_THREADS')} threads)"}[kind],
-          "wall_s_per_time_unit": st.wall_total / T, "t_integrated": T, "dE_over_E": (e1 - e0) / abs(e0), "E0": e0,
-          "block_steps": st.block_steps, "irr_steps": st.irr_steps, "reg_steps": st.reg_steps, "reg_blocks": st.reg_blocks,
-          "regf_calls": st.regf_calls, "overflow_retries": st.overflow_retries, "init_s": t_init,
-          "wall_breakdown_s": {"gpunb_send_or_predict_send": st.wall_send, "gpunb_regf": st.wall_regf, "regcor": st.wall_regcor,
-                               "irr_firr_vec": st.wall_irr, "driver_numpy": st.wall_total - st.wall_send - st.wall_regf - st.wall_regcor - st.wall_irr}})
+          "driver": "native (nbody6ppgpu_b200/csrc/ac_driver.cpp); irregular force through libirr_b200.so for every arm",
+          "wall_s_per_time_unit": st["wall_total"] / T, "t_integrated": T, "dE_over_E": st["dE_over_E"], "E0": st["e0"],
+          "block_steps": st["block_steps"], "irr_steps": st["irr_steps"], "reg_steps": st["reg_steps"], "reg_blocks": st["reg_blocks"],
+          "regf_calls": st["regf_calls"], "overflow_retries": st["overflow_retries"], "mean_nnb": st["mean_nnb"], "init_s": st["wall_init"],
+          "wall_breakdown_s": {"gpunb_send_or_predict_send": st["wall_send"], "gpunb_regf": st["wall_regf"], "regcor": st["wall_regcor"],
+                               "irr_firr_vec": st["wall_irr"], "driver_host": st["wall_total"] - libs}})
 
 
 def run_time_unit_probe(kind, n, T, local, timeout=1500):
@@ -661,8 +653,8 @@ def main():
     roof_gint = fp32_nominal * 1e12 / FLOP_PER_INT * 1e-9
     achieved_tflops = FLOP_PER_INT * int_per_launch / (kern_ms * 1e-3) * 1e-12
     mean_nnb = nnb_sum / float(ni_total)
-    # j tiles once (3392 B per 64 j) + i-block in + partial sums/lists out
-    alg_bytes = n * interactions_scale * (3392.0 / 64.0) + BLOCK * (64.0 + 56.0 + 4.0 * (1 + mean_nnb))
+    # j tiles once (3408 B per 64 j) + i-block in + partial sums/lists out
+    alg_bytes = n * interactions_scale * (3408.0 / 64.0) + BLOCK * (64.0 + 56.0 + 4.0 * (1 + mean_nnb))
     traffic, traffic_src = None, None                # dram bytes of one regf_kernel launch from the committed ncu capture
     try:
         prof = json.loads((ROOT / "profiles" / "regf_kernel_ncu_latest.json").read_text())

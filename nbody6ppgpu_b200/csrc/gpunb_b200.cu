@@ -74,10 +74,10 @@
 namespace {
 
 constexpr int TJ          = 64;                   // j-particles per tile
-constexpr int HDR         = 16;                   // header floats
+constexpr int HDR         = 20;                   // header floats (16-17: bounding-sphere radius, |velocity half-extents|; 18-19 spare)
 constexpr int NCOMP       = 13;                   // float arrays per tile
-constexpr int TILE_FLOATS = HDR + TJ * NCOMP;     // 848
-constexpr int TILE_BYTES  = TILE_FLOATS * 4;      // 3392 (multiple of 16: one TMA bulk copy)
+constexpr int TILE_FLOATS = HDR + TJ * NCOMP;     // 852
+constexpr int TILE_BYTES  = TILE_FLOATS * 4;      // 3408 (multiple of 16: one TMA bulk copy)
 enum { C_DX = 0, C_DY, C_DZ, C_VX, C_VY, C_VZ, C_M, C_XH, C_YH, C_ZH, C_XL, C_YL, C_ZL };
 constexpr int NSTAGE      = 3;                    // smem stages per warp
 constexpr int WARPS       = 4;                    // warps per CTA (warp-autonomous: no CTA-wide sync)
@@ -288,6 +288,10 @@ __global__ void __launch_bounds__(128) tilepack_kernel(int n, int t0, int tstrid
             tb[12 + c] = 0.5f * (vmx[c] - vmn[c]) * 1.000001f + 1.2e-7f * fmaxf(fabsf(vmn[c]), fabsf(vmx[c])) + 1e-30f;
         }
         tb[15] = sqrtf(mmax) * 1.000001f;          // sqrt of the largest mass (m_flag criterion h2*mj), rounded up
+        // bounding sphere of the position box and length of the velocity half-extents, rounded up (quick FAR test)
+        tb[16] = sqrtf(tb[6] * tb[6] + tb[7] * tb[7] + tb[8] * tb[8]) * 1.000001f;
+        tb[17] = sqrtf(tb[12] * tb[12] + tb[13] * tb[13] + tb[14] * tb[14]) * 1.000001f;
+        tb[18] = 0.f; tb[19] = 0.f;
         if (qsum) {
             const float H = fmaxf(__uint_as_float(*hbits), 1e-30f);
             const float e = fminf(hsum / H, 8.f);
@@ -419,6 +423,7 @@ struct RegfArgs {
     int          *seg;       // [nloc][S][segcap]
     int           segcap;
     int           force_near;  // debugging/tuning: classify every tile as NEAR
+    int           itmap;       // tuning (GPUNB_B200_ITMAP=1): work item w -> (i-tile w % n_itiles, slice w / n_itiles)
     int           near_scalar; // tuning / A-B: NEAR tiles through the scalar body (the kernel before the packed NEAR body)
     unsigned long long *stats; // optional: [0] near tiles, [1] all tiles (per warp-tile visit), [2] exact quads of NEAR tiles
     unsigned long long *wtime; // optional: per work item start/end %globaltimer (tuning)
@@ -586,6 +591,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
     constexpr int ITILE = 32 * IT;
     constexpr bool NEWTON = (OPT & 1) != 0;
     constexpr bool TRANSPOSE = (OPT & 2) != 0 && IT == 1;
+    constexpr bool QUICK  = (OPT & 4) != 0 && IT == 1;   // "q": bounding-sphere FAR test first, the box test only when a lane fails it
+    constexpr bool FLUSH2 = (OPT & 8) != 0;              // "f": FP32 chains of 64 terms (flush every second tile)
+    constexpr int  UQ     = (OPT & 16) ? 4 : FAR_UNROLL_Q;   // "u": four quads of j per iteration of the FAR loop
     constexpr int  TRANSPOSE_MAX = 8;                 // more failing lanes than this: the whole warp runs the NEAR body
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -594,7 +602,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
     float    *buf  = reinterpret_cast<float *>(smem_raw) + warp * NSTAGE * TILE_FLOATS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + WARPS * NSTAGE * TILE_BYTES) + warp * NSTAGE;
 
-    const int it = w / a.S, s = w - it * a.S;         // this warp visits tiles s, s+S, s+2S, ...
+    // this warp visits tiles s, s+S, s+2S, ... for i-tile it; itmap: the warps of a CTA take DIFFERENT i-tiles and the same s
+    const int it = a.itmap ? w % a.n_itiles : w / a.S, s = a.itmap ? w / a.n_itiles : w - (w / a.S) * a.S;
+    if (it >= a.n_itiles || s >= a.S) return;
     if (a.wtime && lane == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); a.wtime[3 * w] = t0; }
 
     if (lane == 0) {
@@ -686,7 +696,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         // with margins that dominate every fp32 rounding (positions/velocities rounded to fp32 by the predicate,
         // this arithmetic itself, the approximate sqrt).
         bool lane_far = true;
-        {
+        bool need_box = true;
+        if (QUICK) {
+            // Bounding-sphere version of the test below (a proof of FAR by the same argument with coarser bounds: gap to the
+            // sphere <= gap to the box, |dv| <= |v_tile centre - v_i| + |velocity half-extents|): ~17 instructions instead of
+            // ~35; the box test runs only for the (warp, tile) visits in which some lane fails it.
+            const float4 h4 = reinterpret_cast<const float4 *>(tb)[4];      // R | VR | - | -
+            const float c2 = fmaf(I[0].cz, I[0].cz, fmaf(I[0].cy, I[0].cy, I[0].cx * I[0].cx));
+            float dist; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(dist) : "f"(c2));
+            const float g = fmaf(dist, 0.999999f, -(h4.x + 2.f * I[0].slack));
+            const float wx = h2v.y + I[0].nvx, wy = h2v.z + I[0].nvy, wz = h2v.w + I[0].nvz;
+            float wn; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(wn) : "f"(fmaf(wz, wz, fmaf(wy, wy, wx * wx))));
+            const float reach = fmaf(I[0].adtr, fmaf(wn, 1.000001f, h4.y), MFLAG ? I[0].rs * h3.w : I[0].rs);
+            const bool qf = (g > reach) && (g > 0.5f * fmaf(dist, 1.000001f, h4.x));
+            need_box = __any_sync(0xffffffffu, !(qf || iidx[0] < 0));
+        }
+        if (need_box) {
             const float jh[3] = {h1.z, h1.w, h2v.x};
             const float jvc[3] = {h2v.y, h2v.z, h2v.w};
             const float jvh[3] = {h3.x, h3.y, h3.z};
@@ -722,8 +747,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             cx2[k] = dup2(I[k].cx); cy2[k] = dup2(I[k].cy); cz2[k] = dup2(I[k].cz);
             nvx2[k] = dup2(I[k].nvx); nvy2[k] = dup2(I[k].nvy); nvz2[k] = dup2(I[k].nvz);
         }
+        if (FLUSH2 && TRANSPOSE && transposed) flush();   // the transposed path replaces this tile's sums of the failing lanes
         if (far) {
-#pragma unroll FAR_UNROLL_Q
+#pragma unroll UQ
             for (int q = 0; q < TJ / 4; q++) {
                 const float4 DX = c[C_DX * 16 + q], DY = c[C_DY * 16 + q], DZ = c[C_DZ * 16 + q];
                 const float4 VX = c[C_VX * 16 + q], VY = c[C_VY * 16 + q], VZ = c[C_VZ * 16 + q];
@@ -855,8 +881,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
             mbar_expect_tx(&bars[st], TILE_BYTES);
             tma_bulk_g2s(buf + st * TILE_FLOATS, a.tiles + (size_t)(t + NSTAGE * a.S) * TILE_FLOATS, TILE_BYTES, &bars[st]);
         }
-        flush();                                       // FP32 chains of 32 terms -> fp64
+        if (!FLUSH2 || (n & 1)) flush();               // FP32 chains of 32 (64) terms -> fp64
     }
+    if (FLUSH2) flush();
 
 #pragma unroll
     for (int k = 0; k < IT; k++) {
@@ -869,7 +896,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) regf_kernel(const RegfArgs a
         }
     }
     if (a.stats && lane == 0) { atomicAdd(&a.stats[0], (unsigned long long)n_near); atomicAdd(&a.stats[1], (unsigned long long)n_all); atomicAdd(&a.stats[2], (unsigned long long)n_tr); }
-    if (a.wtime && lane == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); a.wtime[3 * w + 1] = t1; a.wtime[3 * w + 2] = n_near; }
+    if (a.wtime && lane == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); a.wtime[3 * w + 1] = t1;
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.wtime[3 * w + 2] = (unsigned long long)n_near | ((unsigned long long)smid << 32); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1396,9 +1425,14 @@ const Variant VARIANTS[] = {
     {"it1b4n", 1, {regf_kernel<1, false, 4, 1>, regf_kernel<1, true, 4, 1>}},      // + Newton step in the FAR body
     {"it1b4t", 1, {regf_kernel<1, false, 4, 2>, regf_kernel<1, true, 4, 2>}},      // + transposed NEAR lanes
     {"it1b4nt", 1, {regf_kernel<1, false, 4, 3>, regf_kernel<1, true, 4, 3>}},
+    {"it1b4tq", 1, {regf_kernel<1, false, 4, 2 + 4>, regf_kernel<1, true, 4, 2 + 4>}},         // + bounding-sphere FAR test first
+    {"it1b4tf", 1, {regf_kernel<1, false, 4, 2 + 8>, regf_kernel<1, true, 4, 2 + 8>}},         // + FP32 chains of 64 terms
+    {"it1b4tu", 1, {regf_kernel<1, false, 4, 2 + 16>, regf_kernel<1, true, 4, 2 + 16>}},       // + FAR loop unrolled 4 quads
+    {"it1b4tqf", 1, {regf_kernel<1, false, 4, 2 + 4 + 8>, regf_kernel<1, true, 4, 2 + 4 + 8>}},
+    {"it1b4tqu", 1, {regf_kernel<1, false, 4, 2 + 4 + 16>, regf_kernel<1, true, 4, 2 + 4 + 16>}},
 };
 constexpr int NVARIANTS = sizeof(VARIANTS) / sizeof(VARIANTS[0]);
-constexpr int DEFAULT_VARIANT = 7;     // it1b4t: 4 CTAs/SM (<= 128 registers) + transposed NEAR lanes: +2 % at ni = 1024, +8 % at 256,
+constexpr int DEFAULT_VARIANT = 9;     // it1b4tq (it1b4t + the bounding-sphere FAR test first: +0.7 %, identical results, profiles/r2r_variant_probe.txt); it1b4t: 4 CTAs/SM (<= 128 registers) + transposed NEAR lanes: +2 % at ni = 1024, +8 % at 256,
                                        // +18 % at 32 over it1b4 at N = 1M (profiles/r2a_variant_probe.txt); the Newton step in the
                                        // FAR body ("n") costs 10 % and leaves the strict jerk error where it is (2.9e-6 vs 3.1e-6)
 constexpr int ROWS_LMAX_CAP = 1024;    // row stride capacity of the IPC-exported shard rows (NCCL mode)
@@ -2208,6 +2242,7 @@ void launch_regf(Dev &d, Slot &sl, cudaStream_t lo, cudaStream_t hi, const Job &
     RegfArgs a;
     a.tiles = d.jtile; a.jidx = d.jidx; a.ntiles = d.ntiles; a.iperm = iperm;
     { static int fn = -1; if (fn < 0) { const char *e = getenv("GPUNB_B200_FORCE_NEAR"); fn = e ? atoi(e) : 0; } a.force_near = fn; }
+    { static int im = -1; if (im < 0) { const char *e = getenv("GPUNB_B200_ITMAP"); im = e ? atoi(e) : 0; } a.itmap = im; }
     { static int ne = -1; if (ne < 0) { const char *e = getenv("GPUNB_B200_NEAR_EXACT"); ne = e ? atoi(e) : 0; } a.near_scalar = L.near_exact >= 0 ? L.near_exact : ne; }
     a.stats = d.stats; a.wtime = d.wtime;
     a.h2 = ib.h2; a.dtr = ib.dtr; a.xi = ib.xi; a.vi = ib.vi;

@@ -89,13 +89,16 @@ if __name__ == "__main__":
         outp = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/variant_probe2.json"
         res = []
         for var in sys.argv[2:] or ["it1b4", "it1b4n", "it1b4t", "it1b4nt"]:
-            env = dict(os.environ, GPUNB_B200_VARIANT=var)
+            env = dict(os.environ, GPUNB_B200_VARIANT=var.split("+")[0])
+            if var.endswith("+x"):                 # work items mapped so that the warps of a CTA take different i-tiles
+                env["GPUNB_B200_ITMAP"] = "1"
             r = subprocess.run([sys.executable, __file__, "--child"], env=env, capture_output=True, text=True)
             lines = [l for l in r.stdout.splitlines() if l.startswith("VARIANT ")]
             if not lines:
                 print("FAILED", var, r.stdout[-1500:], r.stderr[-3000:], flush=True)
                 continue
             d = json.loads(lines[-1][8:])
+            d["variant"] = var
             res.append(d)
             worst = {k: max(e[k] for e in d["errors"].values()) for k in ("acc", "pot", "jrk_strict", "jrk_scaled")}
             print(var, {k: f"{v:.2e}" for k, v in worst.items()},

@@ -115,3 +115,51 @@ def test_device_paths_of_the_driver(b200):
         assert abs(out[name]["irr"] - out["host"]["irr"]) < 0.02 * out["host"]["irr"]
         assert abs(out[name]["reg"] - out["host"]["reg"]) < 0.02 * out["host"]["reg"]
         assert np.median(np.linalg.norm(out[name]["x"] - out["host"]["x"], axis=1)) < 1e-6
+
+
+def test_native_driver_is_the_python_driver_bit_for_bit(ref_avx):
+    """csrc/ac_driver.cpp (libac_driver.so) restates hermite_ac.py statement by statement: behind the same (reference)
+    libraries the two integrations agree in every step count and in every bit of the final positions."""
+    from pathlib import Path
+    from nbody6ppgpu_b200 import ac_native, irr
+    ref = Path(__file__).resolve().parent.parent / "oracle" / "_ref"
+    if ref_avx is None or not (ref / "libirr_ref_avx.so").exists():
+        pytest.skip("oracle/_ref not built")
+    assert ac_native.lib_path().exists(), "libac_driver.so not built: run __graft_entry__.build()"
+    m, x, v = S.plummer(512, 7, "kroupa")
+    for irr_so, m_flag in ((None, 0), (ref / "libirr_ref_avx.so", 1)):
+        kw = dict(nnbopt=30, lmax=128, m_flag=m_flag)
+        ac = H.AhmadCohen(ref_avx, m, x, v, irr_lib=irr.IrrLib(irr_so) if irr_so else None, **kw)
+        try:
+            st = ac.run(0.25)
+        finally:
+            ac.close()
+        out, xo, vo = ac_native.run(ref / "libgpunb_ref_avx.so", irr_so, m, x, v, 0.25, **kw)
+        assert (out["block_steps"], out["irr_steps"], out["reg_steps"], out["regf_calls"], out["overflow_retries"]) == \
+               (st.block_steps, st.irr_steps, st.reg_steps, st.regf_calls, st.overflow_retries)
+        assert np.array_equal(xo, ac.x0) and np.array_equal(vo, ac.v0)
+        assert abs(out["e0"] - st.energies[0][1]) < 1e-13 and abs(out["e1"] - st.energies[-1][1]) < 1e-13    # summation order of E only
+        assert abs(out["dE_over_E"]) < 2e-4
+
+
+@pytest.mark.gpu
+def test_native_driver_on_the_device_paths(b200):
+    """The native driver behind this repo's three device paths (libgpunb_b200.so with the device-resident predictor and
+    gpunb_b200_regcor_, libirr_b200.so): the same integration as the Python driver on the same paths."""
+    from nbody6ppgpu_b200 import ac_native, irr, lib_path
+    m, x, v = S.plummer(2048, 5, "kroupa")
+    kw = dict(nnbopt=40, lmax=128, m_flag=1)
+    ac = H.AhmadCohen(b200, m, x, v, irr_lib=irr.IrrLib(irr.lib_path()), use_regcor=True, device_predictor=True, **kw)
+    try:
+        st = ac.run(0.25)
+    finally:
+        ac.close()
+    out, xo, vo = ac_native.run(lib_path(), irr.lib_path(), m, x, v, 0.25, use_predictor=True, use_regcor=True, **kw)
+    print({k: out[k] for k in ("wall_total", "wall_send", "wall_regf", "wall_irr", "wall_regcor", "block_steps", "irr_steps", "dE_over_E")},
+          "python wall", st.wall_total)
+    assert (out["block_steps"], out["irr_steps"], out["reg_steps"]) == (st.block_steps, st.irr_steps, st.reg_steps)
+    assert np.array_equal(xo, ac.x0) and np.array_equal(vo, ac.v0)
+    assert abs(out["dE_over_E"]) < 1e-4
+    host, xh, _ = ac_native.run(lib_path(), irr.lib_path(), m, x, v, 0.25, **kw)         # reference ABI only: host predictor, host lists
+    assert abs(host["irr_steps"] - out["irr_steps"]) < 0.02 * out["irr_steps"]
+    assert np.median(np.linalg.norm(xh - xo, axis=1)) < 1e-6
