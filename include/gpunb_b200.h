@@ -243,6 +243,12 @@ void gpunb_b200_nccl_finalize(void);
 void gpunb_b200_regcor_(int *ni, int index_i[], int *ifirst, int *n, int *ntot, int *lmax, int new_list[], int old_list[],
                         double rs2[], double step[], double *smin, int *nnbmax, double freg[][3], double fdr[][3],
                         double dfirr[][3], double dfd[][3], int nbloss[], int nbgain[], int jjlist[], int *nbsmin);
+/* The same bookkeeping for the rows of the LAST gpunb_regf_ call, taken from the copy that call left on the device (ni and
+ * lmax must be that call's; index_i[k] names the particle of its row k; not available in i-slice mode): new_list is output
+ * only.  With old_list = NULL (resident list store) and step = NULL (resident steps) no list crosses PCIe on the way in. */
+void gpunb_b200_regcor_last_(int *ni, int index_i[], int *ifirst, int *n, int *ntot, int *lmax, int new_list[], int old_list[],
+                             double rs2[], double step[], double *smin, int *nnbmax, double freg[][3], double fdr[][3],
+                             double dfirr[][3], double dfd[][3], int nbloss[], int nbgain[], int jjlist[], int *nbsmin);
 /* Device-resident list store (one row of lmax entries per particle number): lists[k] = LIST(1:LMAX, index_i[k]).
  * put after FPOLY0 and whenever the caller edits a list itself (KS, CHECKL, ...); get reads rows back. */
 void gpunb_b200_lists_put_(int *n, int index_i[], int *lmax, int lists[]);

@@ -38,6 +38,8 @@ void irr_b200_set_list_batch_(int *n, int addr[], int *lstride, int lists[]);
 /* out[0] = device ms of the force kernel since the last call of this function (CUDA events on the library's stream),
  * out[1] = force calls, out[2] = pair interactions since open / the last irr_simd_profile_. */
 void irr_b200_counters(double out[3]);
+/* Kernel timing (two event records and one query per force call) is off by default; on: IRR_B200_TIMING=1 or this call. */
+void irr_b200_set_timing(int on);
 
 #ifdef __cplusplus
 }

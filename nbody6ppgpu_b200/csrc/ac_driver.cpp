@@ -40,6 +40,7 @@ struct Abi {
     void (*predict_send)(int *, double *) = nullptr;
     void (*regcor)(int *, int *, int *, int *, int *, int *, int *, int *, double *, double *, double *, int *, d3 *, d3 *, d3 *,
                    d3 *, int *, int *, int *, int *) = nullptr;
+    decltype(regcor) regcor_last = nullptr;
     // irregular-force library
     void (*iopen)(int *, int *, int *) = nullptr;
     void (*iclose)(int *) = nullptr;
@@ -76,7 +77,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
     if (!sym(A.h, "gpunb_open_", A.open) || !sym(A.h, "gpunb_close_", A.close) || !sym(A.h, "gpunb_send_", A.send) ||
         !sym(A.h, "gpunb_regf_", A.regf) || !sym(A.h, "gpupot_", A.pot)) { fprintf(stderr, "ac_driver: %s lacks the reference ABI\n", gpunb_so); return 2; }
     const bool b200 = sym(A.h, "gpunb_b200_state_all_", A.state_all);
-    if (b200) { sym(A.h, "gpunb_b200_state_update_", A.state_update); sym(A.h, "gpunb_b200_predict_send_", A.predict_send); sym(A.h, "gpunb_b200_regcor_", A.regcor); }
+    if (b200) { sym(A.h, "gpunb_b200_state_update_", A.state_update); sym(A.h, "gpunb_b200_predict_send_", A.predict_send); sym(A.h, "gpunb_b200_regcor_", A.regcor); sym(A.h, "gpunb_b200_regcor_last_", A.regcor_last); }
     const bool predictor = p->use_predictor && b200, use_regcor = p->use_regcor && b200 && A.regcor;
     if ((p->use_predictor || p->use_regcor) && !b200) { fprintf(stderr, "ac_driver: device paths need libgpunb_b200.so\n"); return 3; }
     const bool use_irr = irr_so && *irr_so;
@@ -350,8 +351,10 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                     for (int l = 0; l < nnb[i]; l++) o[1 + l] = nb[(size_t)i * (nnbmax + 1) + l] + 1;
                 }
                 int kk = nr, ifirst = 1, nn = n, lm = lmax, nm = nnbmax, nbsmin = 0; double smin = 0.0;
-                A.regcor(&kk, idx1.data(), &ifirst, &nn, &nn, &lm, rows_raw.data(), old_rows.data(), rs2.data(), nullptr, &smin, &nm,
-                         (d3 *)zf.data(), (d3 *)zd.data(), (d3 *)dfi.data(), (d3 *)dfd.data(), nbl.data(), nbg.data(), jj.data(), &nbsmin);
+                // a block that went through ONE gpunb_regf_ call still has its rows on the device: nothing is uploaded but the old lists
+                (nr <= MAXTHR && A.regcor_last ? A.regcor_last : A.regcor)(
+                    &kk, idx1.data(), &ifirst, &nn, &nn, &lm, rows_raw.data(), old_rows.data(), rs2.data(), nullptr, &smin, &nm,
+                    (d3 *)zf.data(), (d3 *)zd.data(), (d3 *)dfi.data(), (d3 *)dfd.data(), nbl.data(), nbg.data(), jj.data(), &nbsmin);
                 lnew.assign((size_t)nr * (nnbmax + 1), -1); cnew.assign(nr, 0);
                 fin.resize((size_t)3 * nr); fidn.resize((size_t)3 * nr);
                 for (int q = 0; q < nr; q++) {

@@ -1060,6 +1060,7 @@ struct MergeArgs {
                                            // (host arrays the caller has pinned, gpunb_b200_pin_host_) instead of res_f
     int     f_stride;
     int    *res_list;   // [.][lmax]
+    int    *res_list2;  // optional second copy of the final rows in DEVICE memory (gpunb_b200_regcor_last_ reads it); NULL: none
     int     sort;       // 0: leave the row in arrival order (a shard row: combine_kernel sorts the union)
     // exchange slot reuse (one process per GPU): wait until every peer has acknowledged reading the previous
     // contents (acks[r] >= ack_need) before overwriting res_f / res_list.  NULL: no wait.
@@ -1092,8 +1093,9 @@ __device__ __forceinline__ void merge_row(const MergeArgs &a, int kl, int lane, 
     } else if (lane < 7) a.res_f[(size_t)i * a.f_stride + lane] = f[lane];   // f[] is uniform after the butterfly
     if (a.f_stride == 8 && lane == 7) a.res_f[(size_t)i * 8 + 7] = (double)(total > a.nnbmax ? -total : total);
     int *row = a.res_list + (size_t)i * a.lmax;
-    if (total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
-    if (lane == 0) row[0] = total;
+    int *row2 = a.res_list2 ? a.res_list2 + (size_t)i * a.lmax : nullptr;
+    if (total > a.nnbmax) { if (lane == 0) { row[0] = -total; if (row2) row2[0] = -total; } return; }
+    if (lane == 0) { row[0] = total; if (row2) row2[0] = total; }
     if (total == 0) return;
     int base = 0;
     for (int s0 = 0; s0 < a.S; s0 += 32) {
@@ -1116,6 +1118,7 @@ __device__ __forceinline__ void merge_row(const MergeArgs &a, int kl, int lane, 
         __syncwarp();
     }
     for (int k = lane; k < total; k += 32) row[1 + k] = sb[k];
+    if (row2) for (int k = lane; k < total; k += 32) row2[1 + k] = sb[k];
 }
 
 __global__ void __launch_bounds__(128) merge_kernel(const MergeArgs a)
@@ -1156,6 +1159,7 @@ struct CombineArgs {
     double *res_f;                   // [.][7]
     double *abi_acc, *abi_jrk, *abi_pot;   // non-NULL: the caller's own (pinned) arrays instead of res_f
     int    *res_list;                // [.][lmax]
+    int    *res_list2;               // optional device copy of the final rows (see MergeArgs)
     // one process per GPU: flags[r] (in THIS rank's exchange buffer) is set to `seq` by rank r, over NVLink, once
     // its fr/rows of this call are complete (last CTA of its merge_kernel).  NULL: ordering is done with stream events.
     const unsigned long long *flags;
@@ -1193,8 +1197,9 @@ __device__ __forceinline__ void combine_row(const CombineArgs &a, int kl, int la
         else if (lane == 6) a.abi_pot[i] = f;
     } else if (lane < 7) a.res_f[(size_t)i * 7 + lane] = f;
     int *row = a.res_list + (size_t)i * a.lmax;
-    if (over || total > a.nnbmax) { if (lane == 0) row[0] = -total; return; }
-    if (lane == 0) row[0] = total;
+    int *row2 = a.res_list2 ? a.res_list2 + (size_t)i * a.lmax : nullptr;
+    if (over || total > a.nnbmax) { if (lane == 0) { row[0] = -total; if (row2) row2[0] = -total; } return; }
+    if (lane == 0) { row[0] = total; if (row2) row2[0] = total; }
     if (total == 0) return;
     __syncwarp();
     // flat gather: entry e of the union comes from the shard whose [off, off + cnt) contains it
@@ -1211,6 +1216,7 @@ __device__ __forceinline__ void combine_row(const CombineArgs &a, int kl, int la
     for (int k = total + lane; k < n2; k += 32) sb[k] = INT_MAX;
     warp_sort_smem(sb, n2, lane);
     for (int k = lane; k < total; k += 32) row[1 + k] = sb[k];
+    if (row2) for (int k = lane; k < total; k += 32) row2[1 + k] = sb[k];
 }
 
 __global__ void __launch_bounds__(128) combine_kernel(const CombineArgs a)
@@ -1487,6 +1493,7 @@ struct Dev {
     int segcap = 0;
     double *fr = nullptr;         // [NIMAX][8] shard partial + count (multi-GPU)
     int *rows = nullptr; size_t rows_ints = 0;                                     // shard rows (in-process multi-GPU)
+    int *last_rows = nullptr; size_t last_rows_ints = 0;                           // root: device copy of the rows of the last gpunb_regf_
     int *nanflag = nullptr;       // device alias of this device's entry of L.h_nan (mapped pinned host memory)
     double *pot_part = nullptr, *pot_out = nullptr; size_t pot_part_n = 0, pot_out_n = 0;
     // gpupot's own snapshot (m | x) and tiles of this device's shard, so that gpupot never disturbs the regf j-set
@@ -1563,6 +1570,7 @@ struct Lib {
     long long numInter = 0; int icall = 0, ini = 0, isend = 0;
     double ctr[GPUNB_B200_CTR_COUNT] = {0};
     int last_ni = 0, last_lmax = 0;
+    int last_rows_ni = 0, last_rows_lmax = 0;      // rows of the last gpunb_regf_ held in devs[0].last_rows (0: none)
 } L;
 
 template <class T> void dev_alloc(T *&p, size_t n) { CUDA_CHECK(cudaMalloc((void **)&p, n * sizeof(T))); }
@@ -1834,6 +1842,12 @@ void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root, int nslots,
         d.rows_ints = rl;
         dev_alloc(d.rows, rl);
     }
+    if (is_root && !device_results && rl > d.last_rows_ints) {
+        CUDA_CHECK(cudaDeviceSynchronize());
+        dev_free(d.last_rows);
+        d.last_rows_ints = rl;
+        dev_alloc(d.last_rows, rl);
+    }
     if (is_root && rl > L.h_list_n) {
         CUDA_CHECK(cudaDeviceSynchronize());
         host_free(L.h_list);
@@ -1891,7 +1905,7 @@ void lib_close()
         }
         dev_free(d.iperm_all); d.iperm_all_n = 0;
         dev_free(d.state); d.state_cap = d.state_n = 0; dev_free(d.upd_rec); dev_free(d.upd_idx); dev_free(d.upd_bad); d.upd_cap = 0;
-        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.iperm); dev_free(d.iperm_identity); dev_free(d.stats); dev_free(d.wtime);
+        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.last_rows); d.last_rows_ints = 0; dev_free(d.iperm); dev_free(d.iperm_identity); dev_free(d.stats); dev_free(d.wtime);
         dev_free(d.jidx);
         dev_free(d.qsum); d.perm_n = 0;
     }
@@ -2227,6 +2241,7 @@ struct Job {
     int slot0, nloc;
     int lmax, nnbmax, m_flag;
     double *out_f; int *out_list;      // final results, row i = iperm[slot] (device memory or mapped host memory)
+    int *out_list2 = nullptr;          // device copy of the final rows (gpunb_regf_: kept for gpunb_b200_regcor_last_)
     double *abi_acc = nullptr, *abi_jrk = nullptr, *abi_pot = nullptr;   // or the caller's pinned arrays (with out_list)
     // i-slice mode (collective gpunb_regf_, one process per GPU): this rank combines and receives only the sorted slots
     // [own0, own1) of the block -- its own i-slice -- and its result rows are numbered from row_base
@@ -2303,13 +2318,13 @@ void run_job(const Job &j, const IBlock *ib, const int *const *iperm, int q, boo
     cudaStream_t lo = own_streams ? sl.lo : root.st, hi = own_streams ? sl.hi : root.st;
     if (!L.sh.on && G == 1) {          // single GPU: the shard-local merge IS the final result
         MergeArgs m = merge_defaults();
-        m.iperm = iperm[0] + j.slot0; m.res_f = j.out_f; m.f_stride = 7; m.res_list = j.out_list; m.sort = 1;
+        m.iperm = iperm[0] + j.slot0; m.res_f = j.out_f; m.f_stride = 7; m.res_list = j.out_list; m.res_list2 = j.out_list2; m.sort = 1;
         m.abi_acc = j.abi_acc; m.abi_jrk = j.abi_jrk; m.abi_pot = j.abi_pot;
         launch_regf(root, sl, lo, hi, j, ib[0], iperm[0], m, time_it, tl);
     } else {
         CombineArgs c;
         memset(&c, 0, sizeof(c));
-        c.nloc = j.nloc; c.lmax = j.lmax; c.nnbmax = j.nnbmax; c.res_f = j.out_f; c.res_list = j.out_list;
+        c.nloc = j.nloc; c.lmax = j.lmax; c.nnbmax = j.nnbmax; c.res_f = j.out_f; c.res_list = j.out_list; c.res_list2 = j.out_list2;
         c.iperm = iperm[0] + j.slot0;
         c.kl0 = j.own0 > j.slot0 ? j.own0 - j.slot0 : 0;
         c.kl1 = j.own1 - j.slot0 < j.nloc ? j.own1 - j.slot0 : j.nloc;
@@ -2456,6 +2471,8 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     set_dev(root);
     Job j;
     j.lmax = lmax; j.nnbmax = nnbmax; j.m_flag = m_flag; j.out_f = L.h_f_dev; j.out_list = L.h_list_dev;
+    j.out_list2 = root.last_rows;      // the rows also stay on the device, for the list bookkeeping that follows (regcor_b200.cu)
+    L.last_rows_ni = 0;
     // Output arrays the caller has pinned (gpunb_b200_pin_host_): merge / combine write the ABI layout straight into
     // them over PCIe and the host-side copy of the rows disappears.
     bool direct_out = false;
@@ -2561,6 +2578,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     L.ctr[GPUNB_B200_CTR_HOST_WAIT_MS] += t_wait * 1e3;
     L.ctr[GPUNB_B200_CTR_HOST_SCATTER_MS] += t_scatter * 1e3;
     L.last_ni = ni; L.last_lmax = lmax; L.last_on_host = true;
+    L.last_rows_ni = ni; L.last_rows_lmax = lmax;
 }
 
 // gpunb_regf_ in i-slice mode (one process per GPU, gpunb_b200_set_islice): a collective call.  Every rank passes its own
@@ -2574,6 +2592,7 @@ void lib_regf_islice(int ni, const double *h2, const double *dtr, const double *
     Shard &sh = L.sh;
     Dev &root = L.devs[0];
     const int R = sh.R, me = sh.rank;
+    L.last_rows_ni = 0;
     if (!(0 <= ni && ni <= NIMAX)) FATAL("gpunb_regf (i-slice mode): ni=%d out of range [0, %d]", ni, NIMAX);
     if (nnbmax + 1 > lmax) FATAL("gpunb_regf: nnbmax=%d does not fit rows of lmax=%d", nnbmax, lmax);
     if (nnbmax > SORT_CAP) FATAL("gpunb_regf: nnbmax=%d exceeds the list capacity %d of this build", nnbmax, SORT_CAP);
@@ -2816,6 +2835,8 @@ bool gpunb_b200_internal_snapshot(GpunbSnapshotView *out)
     out->device = d.id; out->stream = d.st; out->nj = d.nj_total; out->nbmax = L.nbmax;
     out->m = d.jraw; out->x = d.jraw + d.nj_total; out->v = d.jraw + 4 * (size_t)d.nj_total;
     out->counters = L.ctr;
+    out->last_rows = L.last_rows_ni > 0 ? d.last_rows : nullptr; out->last_rows_ni = L.last_rows_ni; out->last_rows_lmax = L.last_rows_lmax;
+    out->pinned_alias = [](const void *p, size_t bytes) -> void * { return pinned_alias(reinterpret_cast<const char *>(p), bytes); };
     return true;
 }
 

@@ -13,6 +13,9 @@ struct GpunbSnapshotView {
     int nj = 0, nbmax = 0;
     const double *m = nullptr, *x = nullptr, *v = nullptr;
     double *counters = nullptr;          // GPUNB_B200_CTR_* array of the library
+    // rows of the last gpunb_regf_ call as they were delivered ([ni][lmax], row i of the call), still on the device
+    const int *last_rows = nullptr; int last_rows_ni = 0, last_rows_lmax = 0;
+    void *(*pinned_alias)(const void *p, size_t bytes) = nullptr;     // device alias of caller-pinned host memory, or NULL
 };
 GPUNB_HIDDEN bool gpunb_b200_internal_snapshot(GpunbSnapshotView *out);      // false: library closed or nothing sent yet
 GPUNB_HIDDEN void gpunb_b200_internal_regcor_close();                        // frees the buffers of regcor_b200.cu (gpunb_close_)

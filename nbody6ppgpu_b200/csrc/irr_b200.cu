@@ -121,6 +121,7 @@ struct Irr {
     std::vector<int> pslot, lslot;                                        // address -> pending slot (-1: none)
     std::vector<int> nnb_host;                                            // list lengths (profile line only)
     int *h_addr = nullptr, *d_addr = nullptr, *h_addr_dev = nullptr;      // active list: mapped pinned (small blocks read it over PCIe) / device copy
+    bool timing = false;                                                  // IRR_B200_TIMING=1 or irr_b200_set_timing: events around the kernel
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; double kernel_ms = 0;       // device time of firr_kernel (CUDA events on S.st)
     double *h_res = nullptr, *d_res = nullptr; int *h_nn = nullptr, *d_nn = nullptr;   // mapped pinned results
     double time_grav = 0; unsigned long long num_inter = 0, num_fcall = 0, num_steps = 0;
@@ -128,7 +129,9 @@ struct Irr {
 
 double wtime() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + 1e-6 * tv.tv_usec; }
 
-void flush_particles()
+// sync = false (from the force call): the copies, the scatter and the force kernel are ordered on S.st and the force call
+// synchronises once at its end, before the pinned staging buffers can be refilled
+void flush_particles(bool sync = true)
 {
     if (!S.np) return;
     CUDA_CHECK(cudaMemcpyAsync(S.d_rec, S.h_rec, sizeof(double) * REC * S.np, cudaMemcpyHostToDevice, S.st));
@@ -136,18 +139,18 @@ void flush_particles()
     const int threads = S.np * (REC / 2);
     scatter_particles_kernel<<<(threads + 255) / 256, 256, 0, S.st>>>(S.np, S.d_paddr, S.d_rec, S.ptcl);
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaStreamSynchronize(S.st));                  // the pinned buffers are refilled right away
+    if (sync) CUDA_CHECK(cudaStreamSynchronize(S.st));        // the pinned buffers are refilled right away
     for (int k = 0; k < S.np; k++) S.pslot[S.h_paddr[k]] = -1;
     S.np = 0;
 }
 
-void flush_lists()
+void flush_lists(bool sync = true)
 {
     if (!S.nl) return;
     CUDA_CHECK(cudaMemcpyAsync(S.d_slots, S.h_slots, sizeof(int) * (size_t)S.slot_ints * S.nl, cudaMemcpyHostToDevice, S.st));
     scatter_lists_kernel<<<(S.nl * 32 + 127) / 128, 128, 0, S.st>>>(S.nl, S.slot_ints, S.lstride, S.d_slots, S.list, S.nnb);
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaStreamSynchronize(S.st));
+    if (sync) CUDA_CHECK(cudaStreamSynchronize(S.st));
     for (int k = 0; k < S.nl; k++) S.lslot[S.h_slots[(size_t)k * S.slot_ints]] = -1;
     S.nl = 0;
 }
@@ -192,6 +195,7 @@ void irr_simd_open_(int *nmaxp, int *lmaxp, int *rank)
     S.pslot.assign((size_t)S.nmax + 1, -1); S.lslot.assign((size_t)S.nmax + 1, -1);
     S.nnb_host.assign((size_t)S.nmax + 1, 0);
     S.np = S.nl = 0;
+    { const char *e = getenv("IRR_B200_TIMING"); S.timing = e && atoi(e) > 0; }
     S.time_grav = 0; S.num_inter = S.num_fcall = S.num_steps = 0;
     CUDA_CHECK(cudaStreamSynchronize(S.st));
     fprintf(stderr, "# Opening IRR lib. B200 ver. - rank: %d; nmax: %d, lmax: %d\n", *rank, S.nmax, S.lmax);
@@ -267,9 +271,10 @@ void irr_simd_firr_vec_(double *ti, int *nip, int addr[], double acc[][3], doubl
     if (!S.is_open) FATAL("irr_simd_firr_vec called while the library is closed");
     const double t0 = wtime();
     CUDA_CHECK(cudaSetDevice(S.dev));
-    flush_particles();
-    flush_lists();
+    flush_particles(false);
+    flush_lists(false);
     const int ni = *nip;
+    if (ni <= 0) CUDA_CHECK(cudaStreamSynchronize(S.st));
     for (int i0 = 0; i0 < ni; i0 += ICAP) {
         const int n = ni - i0 < ICAP ? ni - i0 : ICAP;
         memcpy(S.h_addr, addr + i0, sizeof(int) * n);
@@ -279,12 +284,12 @@ void irr_simd_firr_vec_(double *ti, int *nip, int addr[], double acc[][3], doubl
         // pinned buffer -- one enqueue less on a call that is all latency; large blocks get a device copy first
         const int *addr_dev = S.h_addr_dev;
         if (n > 1024) { CUDA_CHECK(cudaMemcpyAsync(S.d_addr, S.h_addr, sizeof(int) * n, cudaMemcpyHostToDevice, S.st)); addr_dev = S.d_addr; }
-        CUDA_CHECK(cudaEventRecord(S.ev0, S.st));
+        if (S.timing) CUDA_CHECK(cudaEventRecord(S.ev0, S.st));
         firr_kernel<<<(n + 3) / 4, 128, 0, S.st>>>(n, *ti, addr_dev, S.ptcl, S.list, S.nnb, S.lstride, S.d_res, S.d_nn);
         CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaEventRecord(S.ev1, S.st));
+        if (S.timing) CUDA_CHECK(cudaEventRecord(S.ev1, S.st));
         CUDA_CHECK(cudaStreamSynchronize(S.st));
-        { float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, S.ev0, S.ev1)); S.kernel_ms += ms; }
+        if (S.timing) { float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, S.ev0, S.ev1)); S.kernel_ms += ms; }
         for (int k = 0; k < n; k++) {
             const double *r = S.h_res + (size_t)k * 6;
             acc[i0 + k][0] = r[0]; acc[i0 + k][1] = r[1]; acc[i0 + k][2] = r[2];
@@ -314,6 +319,7 @@ void irr_b200_set_list_batch_(int *n, int addr[], int *lstride, int lists[])
 }
 // out[0] = device ms of the force kernel since open / the last call of this function, out[1] = force calls,
 // out[2] = pair interactions (CUDA events on the library's stream)
+void irr_b200_set_timing(int on) { S.timing = on != 0; }
 void irr_b200_counters(double out[3])
 {
     out[0] = S.kernel_ms; out[1] = (double)S.num_fcall; out[2] = (double)S.num_inter;

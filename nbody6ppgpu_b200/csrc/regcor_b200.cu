@@ -38,7 +38,8 @@ constexpr int RC_WARPS = 4;        // warps (rows) per CTA
 struct RegcorArgs {
     int ni, ifirst, n, ntot, lmax, nnbmax, nj;
     const int *index_i;                 // [ni] particle number I of each row (Fortran numbering)
-    const int *new_rows, *new_off;      // packed rows of gpunb_regf_: row r at new_rows + new_off[r] = [count, 0-based j ...]
+    const int *new_rows, *new_off;      // rows of gpunb_regf_ = [count, 0-based j ...]: packed, row r at new_rows + new_off[r]; or
+                                        // (new_off == NULL) at new_rows + r lmax: the device copy the last gpunb_regf_ left
     const int *old_rows, *old_off;      // packed old lists [NNB0, members ...] (Fortran numbering), or NULL: list store
     int       *store; int store_stride; // resident list store: row I - 1 (NULL: none); the final NLIST is committed to it
     const double *m, *x, *v;            // snapshot: particle J at index J - ifirst
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) regcor_kernel(const RegcorArgs 
     int *JJ = OL + a.lmax + 2;                                    // JJLIST(k) = JJ[k-1]
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
     const int I = a.index_i[r];
-    const int *nrow = a.new_rows + a.new_off[r];
+    const int *nrow = a.new_off ? a.new_rows + a.new_off[r] : a.new_rows + (size_t)r * a.lmax;
     int *onl = a.out_nlist + (size_t)r * a.lmax;
     int *ocnt = a.out_cnt + 4 * (size_t)r;
     double *fo = a.fio_out + 12 * (size_t)r;
@@ -337,14 +338,15 @@ size_t pack_rows(int n, int lmax, const int *rows, int *dst, int *off, int base)
 {
     size_t used = 0;
     for (int r = 0; r < n; r++) {
-        const int *row = rows + (size_t)r * lmax;
-        const int c = row[0] < 0 ? 0 : row[0];
+        const int c0 = rows[(size_t)r * lmax], c = c0 < 0 ? 0 : c0;
         if (c + 1 > lmax) FATAL("list row %d holds %d members, lmax = %d", r, c, lmax);
         off[r] = base + (int)used;
-        memcpy(dst + used, row, sizeof(int) * (size_t)(c + 1));
         used += (size_t)c + 1;
     }
     off[n] = base + (int)used;
+#pragma omp parallel for num_threads(4) schedule(static) if (n >= 256)
+    for (int r = 0; r < n; r++)
+        memcpy(dst + (off[r] - base), rows + (size_t)r * lmax, sizeof(int) * (size_t)(off[r + 1] - off[r]));
     return used;
 }
 
@@ -360,11 +362,14 @@ void gpunb_b200_internal_regcor_close()
 
 extern "C" {
 
-void gpunb_b200_regcor_(int *nip, int index_i[], int *ifirstp, int *np, int *ntotp, int *lmaxp, int new_list[], int old_list[],
+static void regcor_impl(bool last, int *nip, int index_i[], int *ifirstp, int *np, int *ntotp, int *lmaxp, int new_list[], int old_list[],
                         double rs2[], double step[], double *sminp, int *nnbmaxp, double freg[][3], double fdr[][3],
                         double dfirr[][3], double dfd[][3], int nbloss[], int nbgain[], int jjlist[], int *nbsmin)
 {
-    const GpunbSnapshotView S = snapshot_or_die("gpunb_b200_regcor_");
+    const GpunbSnapshotView S = snapshot_or_die(last ? "gpunb_b200_regcor_last_" : "gpunb_b200_regcor_");
+    if (last && (S.last_rows == nullptr || S.last_rows_ni != *nip || S.last_rows_lmax != *lmaxp))
+        FATAL("gpunb_b200_regcor_last_: the last gpunb_regf_ call left %d rows of lmax %d on the device, this call names %d rows of lmax %d "
+              "(i-slice mode keeps none)", S.last_rows_ni, S.last_rows_lmax, *nip, *lmaxp);
     struct timeval tv0; gettimeofday(&tv0, nullptr);
     const int ni = *nip, ifirst = *ifirstp, lmax = *lmaxp;
     if (lmax < 4) FATAL("gpunb_b200_regcor_: lmax = %d", lmax);
@@ -399,7 +404,7 @@ void gpunb_b200_regcor_(int *nip, int index_i[], int *ifirstp, int *np, int *nto
         int *h_index = hi, *h_noff = hi + RC_ROWS, *h_ooff = h_noff + RC_ROWS + 1, *h_pack = h_ooff + RC_ROWS + 1;
         const int pack_base = (int)(h_pack - hi);
         memcpy(h_index, index_i + r0, sizeof(int) * (size_t)nr);
-        size_t used = pack_rows(nr, lmax, new_list + (size_t)r0 * lmax, h_pack, h_noff, pack_base);
+        size_t used = last ? 0 : pack_rows(nr, lmax, new_list + (size_t)r0 * lmax, h_pack, h_noff, pack_base);
         // overflow rows keep their negative count in the packed copy (pack_rows copies row[0] as it is)
         if (old_list) used += pack_rows(nr, lmax, old_list + (size_t)(r0) * lmax, h_pack + used, h_ooff, pack_base + (int)used);
         double *hd = RC.h_dbl;
@@ -415,7 +420,7 @@ void gpunb_b200_regcor_(int *nip, int index_i[], int *ifirstp, int *np, int *nto
         CUDA_CHECK(cudaMemcpyAsync(RC.d_dbl, hd, sizeof(double) * ((size_t)RC_ROWS + 12 * (size_t)nr), cudaMemcpyHostToDevice, S.stream));
         RegcorArgs a;
         a.ni = nr; a.ifirst = ifirst; a.n = *np; a.ntot = *ntotp; a.lmax = lmax; a.nnbmax = *nnbmaxp; a.nj = S.nj;
-        a.index_i = RC.d_int; a.new_rows = RC.d_int; a.new_off = RC.d_int + RC_ROWS;
+        a.index_i = RC.d_int; a.new_rows = last ? S.last_rows : RC.d_int; a.new_off = last ? nullptr : RC.d_int + RC_ROWS;
         a.old_rows = old_list ? RC.d_int : nullptr; a.old_off = RC.d_int + 2 * RC_ROWS + 1;
         a.store = RC.store; a.store_stride = RC.store_stride;
         a.m = S.m; a.x = S.x; a.v = S.v;
@@ -427,12 +432,14 @@ void gpunb_b200_regcor_(int *nip, int index_i[], int *ifirstp, int *np, int *nto
         CUDA_CHECK(cudaStreamSynchronize(S.stream));
         // ---- results: only the entries in use cross PCIe (the kernel wrote them into mapped pinned memory) ----------
         size_t out_ints = 0;
+#pragma omp parallel for num_threads(4) schedule(static) reduction(+ : out_ints, total_smin) if (nr >= 256)
         for (int r = 0; r < nr; r++) {
             const int *oc = RC.o_cnt + 4 * (size_t)r;
             const int *onl = RC.o_nlist + (size_t)r * lmax;
             int *nl = new_list + (size_t)(r0 + r) * lmax;
             const int nnb = onl[0];
             if (nnb >= 0) memcpy(nl, onl, sizeof(int) * (size_t)(nnb + 1));
+            else nl[0] = nnb;
             nbloss[r0 + r] = oc[0]; nbgain[r0 + r] = oc[1]; total_smin += oc[2];
             const int *ojj = RC.o_jj + 2 * (size_t)r * lmax;
             int *jj = jjlist + 2 * (size_t)(r0 + r) * lmax;
@@ -452,6 +459,21 @@ void gpunb_b200_regcor_(int *nip, int index_i[], int *ifirstp, int *np, int *nto
     struct timeval tv1; gettimeofday(&tv1, nullptr);
     S.counters[GPUNB_B200_CTR_REGCOR_MS] += 1e3 * (tv1.tv_sec - tv0.tv_sec) + 1e-3 * (tv1.tv_usec - tv0.tv_usec);
     S.counters[GPUNB_B200_CTR_REGCOR_ROWS] += ni;
+}
+
+void gpunb_b200_regcor_(int *ni, int index_i[], int *ifirst, int *n, int *ntot, int *lmax, int new_list[], int old_list[],
+                        double rs2[], double step[], double *smin, int *nnbmax, double freg[][3], double fdr[][3],
+                        double dfirr[][3], double dfd[][3], int nbloss[], int nbgain[], int jjlist[], int *nbsmin)
+{
+    regcor_impl(false, ni, index_i, ifirst, n, ntot, lmax, new_list, old_list, rs2, step, smin, nnbmax, freg, fdr, dfirr, dfd, nbloss, nbgain, jjlist, nbsmin);
+}
+// The same for the rows of the LAST gpunb_regf_ call, which are still on the device: new_list is output only (NLIST) and no
+// list is uploaded -- none at all when the old lists come from the resident store.
+void gpunb_b200_regcor_last_(int *ni, int index_i[], int *ifirst, int *n, int *ntot, int *lmax, int new_list[], int old_list[],
+                             double rs2[], double step[], double *smin, int *nnbmax, double freg[][3], double fdr[][3],
+                             double dfirr[][3], double dfd[][3], int nbloss[], int nbgain[], int jjlist[], int *nbsmin)
+{
+    regcor_impl(true, ni, index_i, ifirst, n, ntot, lmax, new_list, old_list, rs2, step, smin, nnbmax, freg, fdr, dfirr, dfd, nbloss, nbgain, jjlist, nbsmin);
 }
 
 // Rows of the resident list store: lists[k] (stride lmax) = LIST(1:LMAX, index_i[k]) = [NNB, members ...], Fortran numbering.

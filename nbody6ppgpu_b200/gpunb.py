@@ -119,6 +119,8 @@ class ForceLib:
                 f.restype = None
             L.gpunb_b200_regcor_.argtypes = ([_c_int_p] * 8 + [_c_dbl_p, _c_dbl_p, _c_dbl_p, _c_int_p] + [_c_dbl_p] * 4
                                              + [_c_int_p] * 4)
+            L.gpunb_b200_regcor_last_.argtypes = L.gpunb_b200_regcor_.argtypes
+            L.gpunb_b200_regcor_last_.restype = None
             L.gpunb_b200_lists_put_.argtypes = [_c_int_p] * 4
             L.gpunb_b200_lists_get_.argtypes = [_c_int_p] * 4
             L.gpunb_b200_steps_all_.argtypes = [_c_int_p, _c_dbl_p]
@@ -343,12 +345,15 @@ class ForceLib:
 
     # neighbour-list bookkeeping after gpunb_regf_ (util_gpu.F:102-111 + regcor_gpu.F:267-470), batched on the device
     def regcor(self, index_i, ifirst: int, n: int, ntot: int, new_list, old_list, rs2, step, smin: float, nnbmax: int,
-               freg, fdr, dfirr=None, dfd=None):
+               freg, fdr, dfirr=None, dfd=None, last_lmax: int = 0):
         """Returns dict(nlist, nbloss, nbgain, jjlist, freg, fdr, dfirr, dfd, nbsmin); argument meaning as
-        include/gpunb_b200.h part 3 (old_list None: resident list store; step None: resident steps or no retention)."""
+        include/gpunb_b200.h part 3 (old_list None: resident list store; step None: resident steps or no retention).
+        new_list None + last_lmax: gpunb_b200_regcor_last_ (the rows of the last gpunb_regf_ call, still on the device)."""
         self._need_b200()
         index_i = np.ascontiguousarray(index_i, dtype=np.int32); ni = index_i.shape[0]
-        nl = np.array(new_list, dtype=np.int32, order="C"); lmax = nl.shape[1]
+        last = new_list is None
+        nl = np.zeros((ni, last_lmax), dtype=np.int32) if last else np.array(new_list, dtype=np.int32, order="C")
+        lmax = nl.shape[1]
         ol = None if old_list is None else np.ascontiguousarray(old_list, dtype=np.int32)
         if ol is not None and ol.shape != nl.shape:
             raise ValueError("old_list and new_list differ in shape")
@@ -361,7 +366,8 @@ class ForceLib:
         jj = np.zeros((ni, 2 * lmax), dtype=np.int32)
         nbsmin = C.c_int(0)
         ip = lambda a: a.ctypes.data_as(_c_int_p)
-        self.lib.gpunb_b200_regcor_(C.byref(C.c_int(ni)), ip(index_i), C.byref(C.c_int(ifirst)), C.byref(C.c_int(n)),
+        fn = self.lib.gpunb_b200_regcor_last_ if last else self.lib.gpunb_b200_regcor_
+        fn(C.byref(C.c_int(ni)), ip(index_i), C.byref(C.c_int(ifirst)), C.byref(C.c_int(n)),
                                     C.byref(C.c_int(ntot)), C.byref(C.c_int(lmax)), ip(nl), None if ol is None else ip(ol),
                                     _dp(rs2), None if st is None else _dp(st), C.byref(C.c_double(smin)),
                                     C.byref(C.c_int(nnbmax)), _dp(fr), _dp(fd), _dp(di), _dp(dd), ip(nbloss), ip(nbgain),

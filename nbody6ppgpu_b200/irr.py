@@ -101,6 +101,9 @@ class IrrLib:
             for k in range(addr.shape[0]):
                 self.lib.irr_simd_set_list_(C.byref(C.c_int(int(addr[k]))), lists[k].ctypes.data_as(_ip))
 
+    def set_timing(self, on: bool):
+        self.lib.irr_b200_set_timing(int(on))
+
     def counters(self):
         out = np.zeros(3)
         self.lib.irr_b200_counters(out.ctypes.data_as(_dp))

@@ -90,8 +90,11 @@ if __name__ == "__main__":
         res = []
         for var in sys.argv[2:] or ["it1b4", "it1b4n", "it1b4t", "it1b4nt"]:
             env = dict(os.environ, GPUNB_B200_VARIANT=var.split("+")[0])
-            if var.endswith("+x"):                 # work items mapped so that the warps of a CTA take different i-tiles
-                env["GPUNB_B200_ITMAP"] = "1"
+            for opt in var.split("+")[1:]:
+                if opt == "x":                     # work items mapped so that the warps of a CTA take different i-tiles
+                    env["GPUNB_B200_ITMAP"] = "1"
+                if opt.startswith("o"):            # grid oversubscription: o2 = two work items per resident warp slot
+                    env["GPUNB_B200_OVERSUB"] = opt[1:]
             r = subprocess.run([sys.executable, __file__, "--child"], env=env, capture_output=True, text=True)
             lines = [l for l in r.stdout.splitlines() if l.startswith("VARIANT ")]
             if not lines:

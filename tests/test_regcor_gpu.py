@@ -164,3 +164,44 @@ def test_rows_of_gpunb_regf_at_lmax_600_in_batches(b200, oracle):
                            "first_batch_2500_rows_s": {"device": t_dev, "oracle": t_ora}}, f, indent=1)
     finally:
         b200.close()
+
+
+def test_rows_still_on_the_device(b200, oracle):
+    """gpunb_b200_regcor_last_: the rows of the last gpunb_regf_ call are taken from the copy that call left on the device
+    (nothing is uploaded but index_i, rs2 and the four force vectors); with the resident list store and resident steps no
+    list crosses PCIe on the way in.  Same results as the oracle on the rows the call returned to the host."""
+    from nbody6ppgpu_b200 import snapshots as S
+    n, lmax, nnbmax, ifirst = 30000, 400, 350, 11
+    m, x, v = S.plummer(n, 6, "kroupa")
+    h2, dtr = S.radii_nnb(x, m, 90.0)
+    rng = np.random.default_rng(4)
+    step = 2.0 ** -rng.integers(3, 12, size=n).astype(np.float64)
+    smin = float(np.quantile(step, 0.2))
+    b200.open(n + 10, 0)
+    try:
+        for ni, sub in ((1024, 1), (777, -3), (40, 1)):                        # one launch, forced sub-blocks, a small unsorted block
+            rows_j = np.sort(rng.choice(n, ni, replace=False))
+            index_i = (rows_j + ifirst).astype(np.int32)
+            b200.set_tuning(0, sub)
+            b200.send(m, x + 0.002 * rng.normal(size=x.shape), v)
+            old_raw = b200.regf(h2[rows_j] * 1.05, dtr[rows_j], x[rows_j], v[rows_j], lmax, nnbmax, 0)[3].copy()
+            old = np.zeros_like(old_raw)
+            for r in range(ni):
+                row = old_raw[r, 1:1 + old_raw[r, 0]]
+                row = row[row != rows_j[r]] + ifirst
+                old[r, 0] = row.size; old[r, 1:1 + row.size] = row
+            b200.send(m, x, v)
+            new = b200.regf(h2[rows_j], dtr[rows_j], x[rows_j], v[rows_j], lmax, nnbmax, 0)[3].copy()
+            freg = rng.normal(size=(ni, 3)); fdr = rng.normal(size=(ni, 3))
+            b200.lists_put(index_i, old); b200.steps_all(step)
+            b200.reset_counters()
+            dev = b200.regcor(index_i, ifirst, n + ifirst - 1, n + ifirst - 1, None, None, h2[rows_j], None, smin, nnbmax, freg, fdr, last_lmax=lmax)
+            c = b200.counters()
+            ora = oracle.regcor(index_i, ifirst, n + ifirst - 1, n + ifirst - 1, new, old, m, x, v, h2[rows_j], step, smin, nnbmax, freg, fdr)
+            same(dev, ora, old)
+            assert ora["nbloss"].sum() > 0 and ora["nbgain"].sum() > 0
+            assert c["h2d_bytes"] < 200.0 * ni, c["h2d_bytes"]                  # index, rs2, four vectors per row: no list went up
+            print(f"regcor_last ni {ni}: {c['regcor_ms'] * 1e3:.1f} us inside the call, oracle {oracle.last_regcor_s * 1e6:.1f} us")
+        b200.set_tuning(0, 4)
+    finally:
+        b200.close()
