@@ -57,6 +57,7 @@
 #include <cmath>
 #include <climits>
 #include <vector>
+#include <algorithm>
 #include <sys/time.h>
 #include <unistd.h>
 #include <dlfcn.h>
@@ -85,7 +86,15 @@ constexpr int NIMAX       = 2048;                 // capacity per call (referenc
 constexpr int JOBCAP      = 16384;                // i-particles of one launch group: the union of all ranks' i-slices of a
                                                   // collective gpunb_regf_ (i-slice mode), or one block of a resident sweep
 constexpr int PART_STRIDE = 8;                    // doubles per partial record (7 used)
-constexpr int OVERSUB     = 1;                    // work items per resident warp (GPUNB_B200_OVERSUB; >1 measured no gain)
+constexpr int OVERSUB     = 1;                    // work items per resident warp slot of a resident SWEEP (GPUNB_B200_OVERSUB): 1 --
+                                                  // consecutive launches fill each other's tails, finer items only add fixed costs
+constexpr int REGF_OVERSUB = 4;                   // ... of a gpunb_regf_ call (GPUNB_B200_REGF_OVERSUB).  A launch that runs ALONE is one wave
+                                                  // of 16 warps per SM which the warp scheduler does not serve evenly: work items end between
+                                                  // 0.40 and 1.08 ms (profiles/r2s_tail_probe_per_sm.txt) and the last quarter of the kernel has
+                                                  // one warp per sub-partition.  Four times as many, four times shorter work items keep the
+                                                  // sub-partitions full until the last wave: 946 -> 1001 Gint/s per launch at ni = 1024,
+                                                  // 906 -> 953 at ni = 256 (profiles/r2t_variant_probe.txt)
+constexpr int MIN_TILES_PER_ITEM = 12;            // ... as long as a work item keeps this many j-tiles
 constexpr int SORT_CAP    = 1024;
 #ifndef FAR_UNROLL
 #define FAR_UNROLL 2
@@ -1305,7 +1314,12 @@ __global__ void __launch_bounds__(128) pot_kernel(const float *__restrict__ tile
             phi += (double)acc;
             continue;
         }
-        // packed f32x2 over j: 11 packed FP32 ops + 2 MUFU.RSQ per two pairs, two chains of 32 terms
+        // packed f32x2 over j: 7 packed FP32 ops + 2 MUFU.RSQ per two pairs, two chains of 32 terms.  No pair of a tile
+        // that passed the test above is a self pair or a coincident pair (their tiles' boxes contain x_i: d2 = 0), so
+        // r2 > 0 needs no guard here; and the raw MUFU.RSQ (relative error 2^-22.9 per term, a random walk over the
+        // sum) is enough for the 1e-6 bar of a FAR term -- the Newton step of pot.avx.cpp:22-25 stays in the exact path
+        // above, where one close pair can carry most of phi_i.  The body is then bound by the MUFU pipe (16 lanes per
+        // clock and SM), not by the FMA pipe.
         const float2 cx2 = dup2(cx), cy2 = dup2(cy), cz2 = dup2(cz);
         float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll 4
@@ -1318,10 +1332,7 @@ __global__ void __launch_bounds__(128) pot_kernel(const float *__restrict__ tile
                 const float2 dz = add2(h ? make_float2(DZ.z, DZ.w) : make_float2(DZ.x, DZ.y), cz2);
                 const float2 m2 = h ? make_float2(M.z, M.w) : make_float2(M.x, M.y);
                 const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-                float2 y;                                  // a self pair (r2 == 0) contributes nothing (:52)
-                y.x = (r2.x > 0.f) ? rsqrt_approx(r2.x) : 0.f;
-                y.y = (r2.y > 0.f) ? rsqrt_approx(r2.y) : 0.f;
-                y = mul2(y, fma2(mul2(mul2(r2, dup2(-0.5f)), y), y, dup2(1.5f)));      // one Newton step
+                const float2 y = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
                 acc2 = fma2(m2, y, acc2);
             }
         }
@@ -1554,6 +1565,7 @@ struct Lib {
     int *h_flag = nullptr;
     int *h_nan = nullptr;          // [MAX_RANKS] NaN flags written by the tile kernels straight into host memory
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
+    int regf_oversub = REGF_OVERSUB;
     int resort_every = 0;          // Hilbert order refreshed every k-th snapshot (GPUNB_B200_RESORT_EVERY); 1 = always;
                                    // 0 (default) = adaptive: kept while the tiles stay compact (one GPU; sharded runs always sort)
     unsigned long long *h_q = nullptr;                 // mapped: tile-extent sum of the last tilepack (device 0)
@@ -1649,6 +1661,7 @@ void lib_devinit(int irank)
         if (nb < 1) FATAL("regf_kernel does not fit on an SM");
         d.warps_resident = d.nsm * nb * WARPS;
         { const char *e = getenv("GPUNB_B200_OVERSUB"); if (e && atoi(e) >= 1 && atoi(e) <= 32) d.oversub = atoi(e); }
+        { const char *e = getenv("GPUNB_B200_REGF_OVERSUB"); if (e && atoi(e) >= 1 && atoi(e) <= 32) L.regf_oversub = atoi(e); }
         fprintf(stderr, "# GPU initialization - rank: %d; HOST %s; NGPU %d; device: %d %s; B200-native regf[%s]: %d SMs x %d CTAs x %d warps\n",
                 irank, host, (int)ids.size(), d.id, prop.name, V.name, d.nsm, nb, WARPS);
         L.devs.push_back(d);
@@ -1804,7 +1817,7 @@ void ensure_work_buffers(Dev &d, int lmax, int nnbmax, bool is_root, int nslots,
 {
     set_dev(d);
     // n_itiles * S never exceeds warps_resident (+ n_itiles when S = 1)
-    const int items = d.warps_resident * d.oversub + JOBCAP / d.itile;
+    const int items = d.warps_resident * std::max(d.oversub, L.regf_oversub) + JOBCAP / d.itile;
     const int segcap = ((nnbmax > 0 ? nnbmax : 1) + 3) & ~3;
     const size_t rl = (size_t)NIMAX * lmax;                  // host-side results: one rank's call
     const size_t rl_job = (size_t)(job_rows > NIMAX ? job_rows : NIMAX) * lmax;      // device-side results of a sweep block
@@ -2192,11 +2205,13 @@ void lib_get_predicted(int n, const int *idx, double *x, double *xdot)
 }
 
 struct Plan { int n_itiles, S, n_items; };
-Plan make_plan(const Dev &d, int nloc)
+Plan make_plan(const Dev &d, int nloc, int oversub)
 {
     Plan p;
     p.n_itiles = (nloc + d.itile - 1) / d.itile;
-    int S = (d.warps_resident * d.oversub) / p.n_itiles;
+    const int S1 = std::max(1, d.warps_resident / p.n_itiles);
+    while (oversub > 1 && d.ntiles < (long long)MIN_TILES_PER_ITEM * S1 * oversub) oversub--;
+    int S = (d.warps_resident * oversub) / p.n_itiles;
     if (S < 1) S = 1;
     if (S > d.ntiles) S = d.ntiles > 0 ? d.ntiles : 1;
     p.S = S;
@@ -2247,13 +2262,14 @@ struct Job {
     // [own0, own1) of the block -- its own i-slice -- and its result rows are numbered from row_base
     int own0 = 0, own1 = INT_MAX, row_base = 0;
     int merge_parts = 1;               // single GPU: merge launches (delivery parts) of this job
+    int oversub = 1;                   // work items per resident warp slot (see OVERSUB / REGF_OVERSUB)
 };
 
 // Pair kernel (stream lo) + shard-local merge (stream hi) of one job on device d, pipeline slot sl.
 void launch_regf(Dev &d, Slot &sl, cudaStream_t lo, cudaStream_t hi, const Job &j, const IBlock &ib, const int *iperm,
                  MergeArgs m, bool time_it, cudaEvent_t *tl)
 {   // tl (optional): [2] after regf, [3] after merge.  m arrives with its outputs / exchange fields set.
-    const Plan p = make_plan(d, j.nloc);
+    const Plan p = make_plan(d, j.nloc, j.oversub);
     RegfArgs a;
     a.tiles = d.jtile; a.jidx = d.jidx; a.ntiles = d.ntiles; a.iperm = iperm;
     { static int fn = -1; if (fn < 0) { const char *e = getenv("GPUNB_B200_FORCE_NEAR"); fn = e ? atoi(e) : 0; } a.force_near = fn; }
@@ -2471,6 +2487,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     set_dev(root);
     Job j;
     j.lmax = lmax; j.nnbmax = nnbmax; j.m_flag = m_flag; j.out_f = L.h_f_dev; j.out_list = L.h_list_dev;
+    j.oversub = L.regf_oversub;
     j.out_list2 = root.last_rows;      // the rows also stay on the device, for the list bookkeeping that follows (regcor_b200.cu)
     L.last_rows_ni = 0;
     // Output arrays the caller has pinned (gpunb_b200_pin_host_): merge / combine write the ABI layout straight into
@@ -2668,6 +2685,7 @@ void lib_regf_islice(int ni, const double *h2, const double *dtr, const double *
     Job j;
     j.lmax = lmax; j.nnbmax = nnbmax; j.m_flag = m_flag; j.out_f = L.h_f_dev; j.out_list = L.h_list_dev;
     j.own0 = off[me]; j.own1 = off[me + 1]; j.row_base = off[me];
+    j.oversub = L.regf_oversub;
     bool direct_out = false;
     if (ni > 0) {
         double *a_acc = pinned_alias(acc, (size_t)3 * ni), *a_jrk = pinned_alias(jrk, (size_t)3 * ni), *a_pot = pinned_alias(pot, (size_t)ni);
@@ -2747,8 +2765,15 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
     const double t0 = wtime();
     if (ni <= 0) return;
     if (istart < 1 || istart - 1 + ni > n) FATAL("gpupot: istart=%d ni=%d outside 1..n=%d", istart, ni, n);
-    static double *hpin = nullptr; static size_t hpin_n = 0;
-    if ((size_t)4 * n + ni > hpin_n) { host_free(hpin); hpin_n = (size_t)4 * n + ni + 1024; host_alloc(hpin, hpin_n); }
+    // pinned staging: the snapshot buffer of gpunb_send_ when the library is open and large enough (ADJUST calls gpupot_ in
+    // the middle of a run: no 32 MB pinned allocation on the first energy check), else a buffer of its own
+    static double *hpin_own = nullptr; static size_t hpin_own_n = 0;
+    double *hpin = nullptr;
+    if (L.is_open && L.h_j && (size_t)4 * n + ni <= L.h_j_n) hpin = L.h_j;
+    else {
+        if ((size_t)4 * n + ni > hpin_own_n) { host_free(hpin_own); hpin_own_n = (size_t)4 * n + ni + 1024; host_alloc(hpin_own, hpin_own_n); }
+        hpin = hpin_own;
+    }
     threaded_copy(hpin, m, (size_t)n);
     threaded_copy(hpin + n, x, (size_t)3 * n);
     const int G = (int)L.devs.size(), R = total_ranks();
@@ -2960,6 +2985,7 @@ float gpunb_b200_sweep_resident(int *i0p, int *nip, int *blockp, int *lmaxp, int
     }
     Job j;
     j.lmax = *lmaxp; j.nnbmax = *nnbmaxp; j.m_flag = *m_flagp; j.slot0 = 0;
+    j.oversub = root.oversub;
     auto iblock_of = [&](Dev &d, int b0) {
         const double *x = d.jraw + d.nj_total, *v = d.jraw + 4 * (size_t)d.nj_total;
         return IBlock{d.radii + b0, d.radii + d.raw_cap + b0, x + 3 * (size_t)b0, v + 3 * (size_t)b0};

@@ -261,7 +261,12 @@ struct Regcor {
     double *d_step = nullptr; int step_cap = 0; bool step_resident = false;
     int *store = nullptr; int store_rows = 0, store_stride = 0;
     bool smem_attr = false;
+    // GPUNB_B200_REGCOR_PROFILE=1: host buckets and kernel time per call (us), printed by gpunb_close_
+    bool profile = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double t_pack = 0, t_enqueue = 0, t_wait = 0, t_unpack = 0, t_kernel = 0; long long n_prof = 0;
 } RC;
+
+double now_us() { struct timeval tv; gettimeofday(&tv, nullptr); return 1e6 * tv.tv_sec + tv.tv_usec; }
 
 template <class T> void pinned(T *&p, size_t n) { CUDA_CHECK(cudaMallocHost((void **)&p, n * sizeof(T))); }
 template <class T> void mapped(T *&h, T *&d, size_t n)
@@ -354,6 +359,10 @@ size_t pack_rows(int n, int lmax, const int *rows, int *dst, int *off, int base)
 
 void gpunb_b200_internal_regcor_close()
 {
+    if (RC.profile && RC.n_prof)
+        fprintf(stderr, "gpunb_b200_regcor: %lld launches, us per launch: pack %.1f enqueue %.1f wait %.1f (kernel %.1f) unpack %.1f\n", RC.n_prof,
+                RC.t_pack / RC.n_prof, RC.t_enqueue / RC.n_prof, RC.t_wait / RC.n_prof, RC.t_kernel / RC.n_prof, RC.t_unpack / RC.n_prof);
+    if (RC.ev0) { cudaEventDestroy(RC.ev0); cudaEventDestroy(RC.ev1); }
     free_buffers();
     if (RC.d_step) cudaFree(RC.d_step);
     if (RC.store) cudaFree(RC.store);
@@ -377,6 +386,9 @@ static void regcor_impl(bool last, int *nip, int index_i[], int *ifirstp, int *n
     if (!RC.smem_attr) {
         CUDA_CHECK(cudaFuncSetAttribute(regcor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         RC.smem_attr = true;
+        const char *e = getenv("GPUNB_B200_REGCOR_PROFILE");
+        RC.profile = e && atoi(e) > 0;
+        if (RC.profile) { CUDA_CHECK(cudaEventCreate(&RC.ev0)); CUDA_CHECK(cudaEventCreate(&RC.ev1)); }
     }
     const size_t smem = sizeof(int) * (size_t)RC_WARPS * (4 * (size_t)lmax + 8);
     if (smem > 200 * 1024) FATAL("gpunb_b200_regcor_: lmax = %d needs %zu bytes of shared memory per CTA", lmax, smem);
@@ -401,8 +413,10 @@ static void regcor_impl(bool last, int *nip, int index_i[], int *ifirstp, int *n
         if (!old_list && !RC.store) FATAL("gpunb_b200_regcor_: no old lists passed and no resident list store (gpunb_b200_lists_put_)");
         // ---- pack and upload -------------------------------------------------------------------------------------
         int *hi = RC.h_int;
-        int *h_index = hi, *h_noff = hi + RC_ROWS, *h_ooff = h_noff + RC_ROWS + 1, *h_pack = h_ooff + RC_ROWS + 1;
+        // layout sized by this call's rows: index | new_off | old_off | packed new | packed old
+        int *h_index = hi, *h_noff = hi + nr, *h_ooff = h_noff + nr + 1, *h_pack = h_ooff + nr + 1;
         const int pack_base = (int)(h_pack - hi);
+        const double tp0 = now_us();
         memcpy(h_index, index_i + r0, sizeof(int) * (size_t)nr);
         size_t used = last ? 0 : pack_rows(nr, lmax, new_list + (size_t)r0 * lmax, h_pack, h_noff, pack_base);
         // overflow rows keep their negative count in the packed copy (pack_rows copies row[0] as it is)
@@ -410,26 +424,31 @@ static void regcor_impl(bool last, int *nip, int index_i[], int *ifirstp, int *n
         double *hd = RC.h_dbl;
         for (int r = 0; r < nr; r++) {
             hd[r] = rs2[r0 + r];
-            double *f = hd + RC_ROWS + 12 * (size_t)r;
+            double *f = hd + nr + 12 * (size_t)r;
             for (int c = 0; c < 3; c++) {
                 f[c] = freg[r0 + r][c]; f[3 + c] = fdr[r0 + r][c]; f[6 + c] = dfirr[r0 + r][c]; f[9 + c] = dfd[r0 + r][c];
             }
         }
         const size_t nint = (size_t)pack_base + used;
         CUDA_CHECK(cudaMemcpyAsync(RC.d_int, hi, sizeof(int) * nint, cudaMemcpyHostToDevice, S.stream));
-        CUDA_CHECK(cudaMemcpyAsync(RC.d_dbl, hd, sizeof(double) * ((size_t)RC_ROWS + 12 * (size_t)nr), cudaMemcpyHostToDevice, S.stream));
+        const double tp1 = now_us();
+        CUDA_CHECK(cudaMemcpyAsync(RC.d_dbl, hd, sizeof(double) * 13 * (size_t)nr, cudaMemcpyHostToDevice, S.stream));
         RegcorArgs a;
         a.ni = nr; a.ifirst = ifirst; a.n = *np; a.ntot = *ntotp; a.lmax = lmax; a.nnbmax = *nnbmaxp; a.nj = S.nj;
-        a.index_i = RC.d_int; a.new_rows = last ? S.last_rows : RC.d_int; a.new_off = last ? nullptr : RC.d_int + RC_ROWS;
-        a.old_rows = old_list ? RC.d_int : nullptr; a.old_off = RC.d_int + 2 * RC_ROWS + 1;
+        a.index_i = RC.d_int; a.new_rows = last ? S.last_rows : RC.d_int; a.new_off = last ? nullptr : RC.d_int + nr;
+        a.old_rows = old_list ? RC.d_int : nullptr; a.old_off = RC.d_int + 2 * nr + 1;
         a.store = RC.store; a.store_stride = RC.store_stride;
         a.m = S.m; a.x = S.x; a.v = S.v;
         a.step = d_step; a.smin = *sminp;
-        a.rs2 = RC.d_dbl; a.fio_in = RC.d_dbl + RC_ROWS; a.fio_out = RC.o_f_d;
+        a.rs2 = RC.d_dbl; a.fio_in = RC.d_dbl + nr; a.fio_out = RC.o_f_d;
         a.out_nlist = RC.o_nlist_d; a.out_jj = RC.o_jj_d; a.out_cnt = RC.o_cnt_d;
+        if (RC.profile) CUDA_CHECK(cudaEventRecord(RC.ev0, S.stream));
         regcor_kernel<<<(nr + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, smem, S.stream>>>(a);
         CUDA_CHECK(cudaGetLastError());
+        if (RC.profile) CUDA_CHECK(cudaEventRecord(RC.ev1, S.stream));
+        const double tp2 = now_us();
         CUDA_CHECK(cudaStreamSynchronize(S.stream));
+        const double tp3 = now_us();
         // ---- results: only the entries in use cross PCIe (the kernel wrote them into mapped pinned memory) ----------
         size_t out_ints = 0;
 #pragma omp parallel for num_threads(4) schedule(static) reduction(+ : out_ints, total_smin) if (nr >= 256)
@@ -451,7 +470,11 @@ static void regcor_impl(bool last, int *nip, int index_i[], int *ifirstp, int *n
             }
             out_ints += (size_t)(nnb > 0 ? nnb : 0) + 1 + oc[0] + oc[1] + 4;
         }
-        S.counters[GPUNB_B200_CTR_H2D_BYTES] += sizeof(int) * (double)nint + sizeof(double) * (RC_ROWS + 12.0 * nr);
+        if (RC.profile) {
+            float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, RC.ev0, RC.ev1));
+            RC.t_pack += tp1 - tp0; RC.t_enqueue += tp2 - tp1; RC.t_wait += tp3 - tp2; RC.t_unpack += now_us() - tp3; RC.t_kernel += 1e3 * ms; RC.n_prof++;
+        }
+        S.counters[GPUNB_B200_CTR_H2D_BYTES] += sizeof(int) * (double)nint + sizeof(double) * 13.0 * nr;
         S.counters[GPUNB_B200_CTR_D2H_BYTES] += sizeof(int) * (double)out_ints + sizeof(double) * 12.0 * nr;
         S.counters[GPUNB_B200_CTR_LAUNCHES] += 1;
     }

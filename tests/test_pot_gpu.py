@@ -44,3 +44,34 @@ def test_gpupot_close_pairs(b200, oracle):
     ref = oracle.pot_f64(1, n, m, x)
     pot = b200.gpupot(1, n, m, x)
     assert np.max(np.abs(pot - ref) / ref) <= 1.0e-6
+
+
+def test_gpupot_full_size_1M(b200, oracle):
+    """BASELINE's size: N = 1M, every i (1e12 pairs).  Parity on two windows of 256 particles (core / halo order of the
+    snapshot) against the fp64 statement; wall-clock against the kernels' own time (no allocation or re-upload overhead
+    beyond the 32 MB snapshot)."""
+    import json, os, time
+    n = 1_000_000
+    m, x, v = S.plummer(n, 1, "kroupa")
+    b200.open(n + 10, 0)
+    try:
+        b200.gpupot(1, 4096, m, x)                    # buffers and tiles exist from here on
+        b200.reset_counters()
+        t0 = time.perf_counter()
+        pot = b200.gpupot(1, n, m, x)
+        wall = time.perf_counter() - t0
+        c = b200.counters()
+    finally:
+        b200.close()
+    r = np.sqrt((x ** 2).sum(1))
+    for istart in (1, int(np.argmax(r)) + 1 - 128, 500_001):
+        istart = max(1, min(istart, n - 255))
+        ref = oracle.pot_f64(istart, 256, m, x)
+        err = float(np.max(np.abs(pot[istart - 1:istart + 255] - ref) / ref))
+        assert err <= 1.0e-6, (istart, err)
+    out = {"n": n, "wall_ms": wall * 1e3, "kernel_ms": c["pot_ms"], "gpair_per_s": float(n) * n / c["pot_ms"] * 1e-6, "max_relerr_sampled": err}
+    print("gpupot 1M:", json.dumps(out))
+    if os.environ.get("GPUNB_POT_OUT"):
+        with open(os.environ["GPUNB_POT_OUT"], "w") as f:
+            json.dump(out, f)
+    assert wall * 1e3 <= 1.05 * c["pot_ms"] + 5.0, out

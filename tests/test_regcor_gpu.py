@@ -200,7 +200,7 @@ def test_rows_still_on_the_device(b200, oracle):
             ora = oracle.regcor(index_i, ifirst, n + ifirst - 1, n + ifirst - 1, new, old, m, x, v, h2[rows_j], step, smin, nnbmax, freg, fdr)
             same(dev, ora, old)
             assert ora["nbloss"].sum() > 0 and ora["nbgain"].sum() > 0
-            assert c["h2d_bytes"] < 200.0 * ni, c["h2d_bytes"]                  # index, rs2, four vectors per row: no list went up
+            assert c["h2d_bytes"] < 200.0 * ni + 64, c["h2d_bytes"]             # index, rs2, four vectors per row: no list went up
             print(f"regcor_last ni {ni}: {c['regcor_ms'] * 1e3:.1f} us inside the call, oracle {oracle.last_regcor_s * 1e6:.1f} us")
         b200.set_tuning(0, 4)
     finally:
