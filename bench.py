@@ -392,9 +392,10 @@ def time_unit_probe(args):
     n, T = args.tu_n, args.tu_t
     m, x, v = S.plummer(n, 5, "kroupa")
     dev = kind == "b200"
-    st, _, _ = ac_native.run(so, irr.lib_path(), m, x, v, T, nnbopt=100, lmax=400, m_flag=1, dtmax=0.125, use_predictor=dev, use_regcor=dev)
+    st, _, _ = ac_native.run(so, irr.lib_path(), m, x, v, T, nnbopt=100, lmax=400, m_flag=1, dtmax=0.125, use_predictor=2 if dev else 0,
+                             use_regcor=2 if dev else 0)
     libs = st["wall_send"] + st["wall_regf"] + st["wall_regcor"] + st["wall_irr"]
-    emit({"library": {"b200": "libgpunb_b200.so + device-resident predictor + gpunb_b200_regcor_", "b200_host": "libgpunb_b200.so (reference ABI only)",
+    emit({"library": {"b200": "libgpunb_b200.so + device-resident predictor on the irr library's particle table + gpunb_b200_regcor_ on the device-resident list store", "b200_host": "libgpunb_b200.so (reference ABI only)",
                       "ref_cuda": "reference gpunb.velocity.cu + gpupot.gpu.cu (sm_100, oracle/_ref)",
                       "ref_avx": f"reference reg.avx.cpp + pot.avx.cpp (oracle/_ref, {os.environ.get('OMP_NUM_THREADS')} threads)"}[kind],
           "driver": "native (nbody6ppgpu_b200/csrc/ac_driver.cpp); irregular force through libirr_b200.so for every arm",

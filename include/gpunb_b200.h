@@ -132,6 +132,13 @@ void gpunb_b200_state_update_(int *n, int idx[], double body[], double x0[][3], 
                               double fdot[][3], double t0[]);
 void gpunb_b200_predict_send_(int *nj, double *time);
 void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3]);
+/* predict_send from particle records that ANOTHER library keeps on the same device: records_dev is a DEVICE pointer to the
+ * record of the first j-particle, *stride doubles apart (>= 16, even), laid out x0[3] m | v0[3] t0 | f[3] . | fdot[3] . with
+ * F = force/2, FDOT = derivative/6 -- the table of libirr_b200.so (irr_b200_particle_records_, include/irr_b200.h), which the
+ * integrator refreshes with irr_simd_set_jp_ after every corrector.  One copy of the state then serves the irregular force
+ * AND the predictor of the regular force: no gpunb_b200_state_update_, no upload before a regular block.  The caller makes
+ * the records complete first (irr_b200_flush_).  One process, one GPU.  Same arithmetic as predict_send. */
+void gpunb_b200_predict_send_records_(int *nj, double *time, const double *records_dev, int *stride);
 
 /* Pipeline depth: nslot = pipeline slots a resident sweep cycles through (1 = one block after the other on one
  * stream), nsub = sub-blocks one gpunb_regf_ call is split into (1 = the whole i-block in one pair-kernel launch).

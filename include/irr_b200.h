@@ -38,6 +38,12 @@ void irr_b200_set_list_batch_(int *n, int addr[], int *lstride, int lists[]);
 /* out[0] = device ms of the force kernel since the last call of this function (CUDA events on the library's stream),
  * out[1] = force calls, out[2] = pair interactions since open / the last irr_simd_profile_. */
 void irr_b200_counters(double out[3]);
+/* The particle table on the device, for a consumer on the same device: returns a DEVICE pointer to the record of address 1;
+ * *stride = doubles per record (16: x0[3] m | v0[3] t0 | F/2 [3] . | FDOT/6 [3] .).  irr_b200_flush_ sends the pending
+ * set_jp / set_list to the device and drains the stream: afterwards the table is what the integrator last set.
+ * gpunb_b200_predict_send_records_ (include/gpunb_b200.h) predicts the regular-force snapshot from it. */
+const double *irr_b200_particle_records_(int *stride);
+void irr_b200_flush_(void);
 /* Kernel timing (two event records and one query per force call) is off by default; on: IRR_B200_TIMING=1 or this call. */
 void irr_b200_set_timing(int on);
 

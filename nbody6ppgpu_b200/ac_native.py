@@ -30,7 +30,11 @@ def lib_path() -> Path:
 
 def run(gpunb_so, irr_so, m, x, v, t_end, *, nnbopt=40, lmax=128, eta_i=0.02, eta_r=0.02, dtmax=0.125, dtmin=2.0 ** -22, m_flag=0,
         rs0=0.0, use_predictor=False, use_regcor=False):
-    """Integrate t_end N-body time units; returns (stats dict, x, v).  irr_so None: irregular sums on the host in fp64."""
+    """Integrate t_end N-body time units; returns (stats dict, x, v).  irr_so None: irregular sums on the host in fp64.
+    use_predictor: 0 host predictor + gpunb_send_, 1 device-resident predictor with its own state (gpunb_b200_state_*),
+    2 device-resident predictor reading the irregular-force library's particle table (one copy of the state on the device).
+    use_regcor: 0 host list bookkeeping, 1 gpunb_b200_regcor_ with the old lists passed by the driver, 2 with the old lists in
+    the library's device-resident list store."""
     so = lib_path()
     if not so.exists():
         raise RuntimeError(f"{so} not found -- build it first (python -c 'import __graft_entry__ as g; g.build()')")

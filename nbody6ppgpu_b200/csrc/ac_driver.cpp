@@ -41,6 +41,10 @@ struct Abi {
     void (*regcor)(int *, int *, int *, int *, int *, int *, int *, int *, double *, double *, double *, int *, d3 *, d3 *, d3 *,
                    d3 *, int *, int *, int *, int *) = nullptr;
     decltype(regcor) regcor_last = nullptr;
+    void (*predict_send_records)(int *, double *, const double *, int *) = nullptr;
+    void (*lists_put)(int *, int *, int *, int *) = nullptr;
+    const double *(*irr_records)(int *) = nullptr;
+    void (*irr_flush)() = nullptr;
     // irregular-force library
     void (*iopen)(int *, int *, int *) = nullptr;
     void (*iclose)(int *) = nullptr;
@@ -77,7 +81,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
     if (!sym(A.h, "gpunb_open_", A.open) || !sym(A.h, "gpunb_close_", A.close) || !sym(A.h, "gpunb_send_", A.send) ||
         !sym(A.h, "gpunb_regf_", A.regf) || !sym(A.h, "gpupot_", A.pot)) { fprintf(stderr, "ac_driver: %s lacks the reference ABI\n", gpunb_so); return 2; }
     const bool b200 = sym(A.h, "gpunb_b200_state_all_", A.state_all);
-    if (b200) { sym(A.h, "gpunb_b200_state_update_", A.state_update); sym(A.h, "gpunb_b200_predict_send_", A.predict_send); sym(A.h, "gpunb_b200_regcor_", A.regcor); sym(A.h, "gpunb_b200_regcor_last_", A.regcor_last); }
+    if (b200) { sym(A.h, "gpunb_b200_state_update_", A.state_update); sym(A.h, "gpunb_b200_predict_send_", A.predict_send); sym(A.h, "gpunb_b200_regcor_", A.regcor); sym(A.h, "gpunb_b200_regcor_last_", A.regcor_last); sym(A.h, "gpunb_b200_predict_send_records_", A.predict_send_records); sym(A.h, "gpunb_b200_lists_put_", A.lists_put); }
     const bool predictor = p->use_predictor && b200, use_regcor = p->use_regcor && b200 && A.regcor;
     if ((p->use_predictor || p->use_regcor) && !b200) { fprintf(stderr, "ac_driver: device paths need libgpunb_b200.so\n"); return 3; }
     const bool use_irr = irr_so && *irr_so;
@@ -87,7 +91,15 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
         if (!sym(A.hi, "irr_simd_open_", A.iopen) || !sym(A.hi, "irr_simd_close_", A.iclose) || !sym(A.hi, "irr_simd_set_jp_", A.set_jp) ||
             !sym(A.hi, "irr_simd_set_list_", A.set_list) || !sym(A.hi, "irr_simd_firr_vec_", A.firr)) { fprintf(stderr, "ac_driver: %s lacks irr_simd_*\n", irr_so); return 2; }
         sym(A.hi, "irr_b200_set_jp_batch_", A.set_jp_batch); sym(A.hi, "irr_b200_set_list_batch_", A.set_list_batch);
+        sym(A.hi, "irr_b200_particle_records_", A.irr_records); sym(A.hi, "irr_b200_flush_", A.irr_flush);
     }
+    // use_predictor = 2: ONE copy of the particle state on the device -- the irregular-force library's table, which set_jp keeps
+    // current -- also feeds the regular-force predictor (gpunb_b200_predict_send_records_): no state upload of its own
+    const bool shared_state = p->use_predictor == 2;
+    // use_regcor = 2: the old lists come from the library's device-resident list store (put once after the initial forces,
+    // committed by every regcor call since): no list is uploaded in steady state
+    const bool resident_lists = p->use_regcor == 2 && use_regcor && A.lists_put;
+    if (shared_state && !(A.predict_send_records && A.irr_records && A.irr_flush)) { fprintf(stderr, "ac_driver: shared predictor state needs libgpunb_b200.so and libirr_b200.so\n"); return 3; }
     memset(st, 0, sizeof(*st));
     const double w_init = wtime();
     const int nnbopt = p->nnbopt, lmax = p->lmax, m_flag = p->m_flag;
@@ -191,7 +203,12 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
         const int k = (int)idx.size();
         double w0 = wtime();
         int nj = n;
-        if (predictor && !snapshot_is_x0) {
+        if (shared_state && !snapshot_is_x0) {
+            A.irr_flush();
+            int stride = 0; const double *rec = A.irr_records(&stride);
+            double tt = t;
+            A.predict_send_records(&nj, &tt, rec, &stride);
+        } else if (predictor && !snapshot_is_x0) {
             std::vector<int> d;
             for (int i = 0; i < n; i++) if (dirty[i]) { d.push_back(i); dirty[i] = 0; }
             if (!d.empty()) {
@@ -295,7 +312,21 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
     }
     adjust_rs(all, cnew);
     if (use_irr) irr_push_particles(all);
-    if (predictor) {
+    if (resident_lists) {
+        std::vector<int> rows((size_t)MAXTHR * lmax), idx(MAXTHR);
+        for (int i0 = 0; i0 < n; i0 += MAXTHR) {
+            int k = std::min(MAXTHR, n - i0), lm = lmax;
+            for (int q = 0; q < k; q++) {
+                const int i = i0 + q;
+                idx[q] = i + 1;
+                int *o = &rows[(size_t)q * lmax];
+                o[0] = nnb[i];
+                for (int l = 0; l < nnb[i]; l++) o[1 + l] = nb[(size_t)i * (nnbmax + 1) + l] + 1;
+            }
+            A.lists_put(&k, idx.data(), &lm, rows.data());
+        }
+    }
+    if (predictor && !shared_state) {
         std::vector<double> f2(3 * N), fd6(3 * N);
         for (int k = 0; k < 3 * n; k++) { f2[k] = 0.5 * f[k]; fd6[k] = fd[k] * (1.0 / 6.0); }
         int nj = n;
@@ -346,6 +377,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 for (int q = 0; q < nr; q++) {
                     const int i = reg[q];
                     idx1[q] = i + 1; rs2[q] = rs[i] * rs[i];
+                    if (resident_lists) continue;
                     int *o = &old_rows[(size_t)q * lmax];
                     o[0] = nnb[i];
                     for (int l = 0; l < nnb[i]; l++) o[1 + l] = nb[(size_t)i * (nnbmax + 1) + l] + 1;
@@ -353,7 +385,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 int kk = nr, ifirst = 1, nn = n, lm = lmax, nm = nnbmax, nbsmin = 0; double smin = 0.0;
                 // a block that went through ONE gpunb_regf_ call still has its rows on the device: nothing is uploaded but the old lists
                 (nr <= MAXTHR && A.regcor_last ? A.regcor_last : A.regcor)(
-                    &kk, idx1.data(), &ifirst, &nn, &nn, &lm, rows_raw.data(), old_rows.data(), rs2.data(), nullptr, &smin, &nm,
+                    &kk, idx1.data(), &ifirst, &nn, &nn, &lm, rows_raw.data(), resident_lists ? nullptr : old_rows.data(), rs2.data(), nullptr, &smin, &nm,
                     (d3 *)zf.data(), (d3 *)zd.data(), (d3 *)dfi.data(), (d3 *)dfd.data(), nbl.data(), nbg.data(), jj.data(), &nbsmin);
                 lnew.assign((size_t)nr * (nnbmax + 1), -1); cnew.assign(nr, 0);
                 fin.resize((size_t)3 * nr); fidn.resize((size_t)3 * nr);
@@ -398,7 +430,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 fi[3 * i + c] = fia[3 * q + c]; fid[3 * i + c] = fida[3 * q + c]; f[3 * i + c] = f1[c]; fd[3 * i + c] = fd1[c];
             }
             t0[i] = tn;
-            dirty[i] = 1;
+            if (!shared_state) dirty[i] = 1;
             const double dt_new = aarseth(p->eta_i, f1, fd1, a2, a3, d), old = dt[i];
             double qd = dt_new < old ? std::max(pow2_floor(dt_new), dtmin) : old;
             if (dt_new >= 2.0 * old && fmod(tn, 2.0 * old) == 0.0 && 2.0 * old <= dtmax) qd = 2.0 * old;

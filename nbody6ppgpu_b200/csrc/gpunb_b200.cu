@@ -1390,6 +1390,32 @@ __global__ void predict_kernel(int n, int cap, const double *__restrict__ st, do
     }
 }
 // out[k] = x[idx[k]] | v[idx[k]] (6 doubles) from the m | x | v snapshot
+// The same predictor from particle RECORDS owned by somebody else on this device -- the irregular-force library's table
+// (irr_b200.cu: 16 doubles per particle, x0[3] m | v0[3] t0 | a2[3] . | j6[3] ., a2 = F/2, j6 = FDOT/6), which the
+// integrator refreshes after every corrector anyway: one copy of the state serves both libraries and nothing is uploaded
+// twice.  Same unfused operations as predict_kernel.
+__global__ void predict_records_kernel(int n, const double *__restrict__ rec, int stride, double time, double *__restrict__ jraw)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double *r = rec + (size_t)j * stride;
+    const double2 a = reinterpret_cast<const double2 *>(r)[0], b = reinterpret_cast<const double2 *>(r)[1];
+    const double2 c2 = reinterpret_cast<const double2 *>(r)[2], d = reinterpret_cast<const double2 *>(r)[3];
+    const double2 e = reinterpret_cast<const double2 *>(r)[4], f2 = reinterpret_cast<const double2 *>(r)[5];
+    const double2 g = reinterpret_cast<const double2 *>(r)[6], h = reinterpret_cast<const double2 *>(r)[7];
+    const double X0[3] = {a.x, a.y, b.x}, V0[3] = {c2.x, c2.y, d.x}, F[3] = {e.x, e.y, f2.x}, FD[3] = {g.x, g.y, h.x};
+    const double s = __dsub_rn(time, d.y);
+    const double s1 = __dmul_rn(1.5, s), s2 = __dmul_rn(2.0, s);
+    jraw[j] = b.y;
+    double *x = jraw + n, *v = jraw + 4 * (size_t)n;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const size_t q = 3 * (size_t)j + c;
+        x[q] = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(FD[c], s), F[c]), s), V0[c]), s), X0[c]);
+        v[q] = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(FD[c], s1), F[c]), s2), V0[c]);
+    }
+}
+
 __global__ void snapshot_gather_kernel(int n, int nj, const int *__restrict__ idx, const double *__restrict__ jraw,
                                        double *__restrict__ out, int *__restrict__ bad)
 {
@@ -2165,6 +2191,30 @@ void lib_predict_send(int nj, double time)
     finish_send(nj, wt0, "gpunb_b200_predict_send");
 }
 
+// predict_send from particle records another library keeps on this device (see predict_records_kernel).  The caller
+// guarantees that the records are complete (irr_b200_flush_) and stay untouched during the call.
+void lib_predict_send_records(int nj, double time, const double *records_dev, int stride)
+{
+    if (!L.is_open) FATAL("gpunb_b200_predict_send_records called while the library is closed");
+    if (nj > L.nbmax) FATAL("gpunb_b200_predict_send_records: nj=%d exceeds nbmax=%d given to gpunb_open", nj, L.nbmax);
+    if (L.devs.size() != 1 || L.sh.on) FATAL("gpunb_b200_predict_send_records: one process, one GPU (the records live on one device)");
+    if (stride < 16 || (stride & 1) || ((uintptr_t)records_dev & 15)) FATAL("gpunb_b200_predict_send_records: records of %d doubles at %p", stride, (const void *)records_dev);
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, records_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice || attr.device != L.devs[0].id)
+        FATAL("gpunb_b200_predict_send_records: %p is not memory of device %d", (const void *)records_dev, L.devs[0].id);
+    const double wt0 = wtime();
+    L.time_send -= wt0;
+    L.isend++;
+    L.nbody = nj;
+    set_shards(nj);
+    Dev &d = L.devs[0];
+    set_dev(d);
+    predict_records_kernel<<<(nj + 255) / 256, 256, 0, d.st>>>(nj, records_dev, stride, time, d.jraw);
+    CUDA_CHECK(cudaGetLastError());
+    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+    finish_send(nj, wt0, "gpunb_b200_predict_send_records");
+}
+
 // Predicted x / xdot of the particles idx[k] from the snapshot built by the last predict_send (the caller needs them
 // for the i-block it passes to gpunb_regf_ when it does not run its own full predictor).
 void lib_get_predicted(int n, const int *idx, double *x, double *xdot)
@@ -2566,6 +2616,9 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
             CUDA_CHECK(cudaStreamWaitEvent(sl.lo, q == 0 ? root.ev_fork : root.slots[q - 1].ev_start, 0));
             CUDA_CHECK(cudaEventRecord(sl.ev_start, sl.lo));
             j.slot0 = off[q]; j.nloc = off[q + 1] - off[q];
+            // only the LAST sub-block's pair kernel runs into an empty machine: the others are followed by the next one, and
+            // finer work items would only add their fixed costs (measured: e2e 918 -> 882 Gint/s with every sub-block at 4x)
+            j.oversub = q == nq - 1 ? L.regf_oversub : 1;
             if (q == 0) CUDA_CHECK(cudaEventRecord(root.ev0, sl.lo));       // "grav" span: start of the first pair kernel ...
             run_job(j, ib, ipm, q, true, false);
         }
@@ -3085,6 +3138,7 @@ void gpunb_b200_state_update_(int *n, int idx[], double body[], double x0[][3], 
     lib_state_update(*n, idx, body, &x0[0][0], &x0dot[0][0], &f[0][0], &fdot[0][0], t0);
 }
 void gpunb_b200_predict_send_(int *nj, double *time) { lib_predict_send(*nj, *time); }
+void gpunb_b200_predict_send_records_(int *nj, double *time, const double *records_dev, int *stride) { lib_predict_send_records(*nj, *time, records_dev, *stride); }
 void gpunb_b200_get_predicted_(int *n, int idx[], double x[][3], double xdot[][3]) { lib_get_predicted(*n, idx, &x[0][0], &xdot[0][0]); }
 
 void gpunb_b200_set_near_exact(int on) { L.near_exact = on; }

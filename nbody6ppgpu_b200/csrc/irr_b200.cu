@@ -69,10 +69,11 @@ __device__ __forceinline__ void predict(const double *__restrict__ r, double ti,
     }
 }
 
-// One warp per active particle.  res[i] = acc[3] jrk[3]; nn[i] = 1-based address of the nearest neighbour (0: empty list).
+// One warp per active particle.  res = acc[ni][3] | jrk[ni][3] (the caller's layouts: plain copies on the host side);
+// nn[i] = 1-based address of the nearest neighbour (0: empty list); inter: pair interactions (profile line).
 __global__ void __launch_bounds__(128) firr_kernel(int ni, double ti, const int *__restrict__ addr, const double *__restrict__ ptcl,
                                                     const int *__restrict__ list, const int *__restrict__ nnb, int lstride,
-                                                    double *__restrict__ res, int *__restrict__ nn)
+                                                    double *__restrict__ res, int *__restrict__ nn, unsigned long long *__restrict__ inter)
 {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= ni) return;
@@ -106,8 +107,9 @@ __global__ void __launch_bounds__(128) firr_kernel(int ni, double ti, const int 
         const int jo = __shfl_xor_sync(0xffffffffu, jmin, o);
         if (r2o < r2min || (r2o == r2min && jo < jmin)) { r2min = r2o; jmin = jo; }
     }
-    if (lane < 6) res[(size_t)w * 6 + lane] = f[lane];
-    if (lane == 0) nn[w] = c > 0 ? jmin + 1 : 0;
+    if (lane < 3) res[(size_t)w * 3 + lane] = f[lane];
+    else if (lane < 6) res[3 * (size_t)ni + (size_t)w * 3 + lane - 3] = f[lane];
+    if (lane == 0) { nn[w] = c > 0 ? jmin + 1 : 0; if (c > 0) atomicAdd(inter, (unsigned long long)c); }
 }
 
 struct Irr {
@@ -119,7 +121,7 @@ struct Irr {
     double *h_rec = nullptr, *d_rec = nullptr; int *h_paddr = nullptr, *d_paddr = nullptr; int np = 0;
     int *h_slots = nullptr, *d_slots = nullptr; int nl = 0;
     std::vector<int> pslot, lslot;                                        // address -> pending slot (-1: none)
-    std::vector<int> nnb_host;                                            // list lengths (profile line only)
+    unsigned long long *d_inter = nullptr;                                // pair interactions since the last profile line (device counter)
     int *h_addr = nullptr, *d_addr = nullptr, *h_addr_dev = nullptr;      // active list: mapped pinned (small blocks read it over PCIe) / device copy
     bool timing = false;                                                  // IRR_B200_TIMING=1 or irr_b200_set_timing: events around the kernel
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; double kernel_ms = 0;       // device time of firr_kernel (CUDA events on S.st)
@@ -193,7 +195,8 @@ void irr_simd_open_(int *nmaxp, int *lmaxp, int *rank)
     CUDA_CHECK(cudaHostAlloc((void **)&S.h_nn, sizeof(int) * ICAP, cudaHostAllocMapped));
     CUDA_CHECK(cudaHostGetDevicePointer((void **)&S.d_nn, S.h_nn, 0));
     S.pslot.assign((size_t)S.nmax + 1, -1); S.lslot.assign((size_t)S.nmax + 1, -1);
-    S.nnb_host.assign((size_t)S.nmax + 1, 0);
+    CUDA_CHECK(cudaMalloc((void **)&S.d_inter, sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemsetAsync(S.d_inter, 0, sizeof(unsigned long long), S.st));
     S.np = S.nl = 0;
     { const char *e = getenv("IRR_B200_TIMING"); S.timing = e && atoi(e) > 0; }
     S.time_grav = 0; S.num_inter = S.num_fcall = S.num_steps = 0;
@@ -208,7 +211,7 @@ void irr_simd_close_(int *rank)
     if (!S.is_open) { fprintf(stderr, "irr_simd: it is already close\n"); return; }
     CUDA_CHECK(cudaSetDevice(S.dev));
     CUDA_CHECK(cudaStreamSynchronize(S.st));
-    cudaFree(S.ptcl); cudaFree(S.list); cudaFree(S.nnb); cudaFree(S.d_rec); cudaFree(S.d_paddr); cudaFree(S.d_slots); cudaFree(S.d_addr);
+    cudaFree(S.d_inter); cudaFree(S.ptcl); cudaFree(S.list); cudaFree(S.nnb); cudaFree(S.d_rec); cudaFree(S.d_paddr); cudaFree(S.d_slots); cudaFree(S.d_addr);
     cudaFreeHost(S.h_rec); cudaFreeHost(S.h_paddr); cudaFreeHost(S.h_slots); cudaFreeHost(S.h_addr); cudaFreeHost(S.h_res); cudaFreeHost(S.h_nn);
     CUDA_CHECK(cudaStreamDestroy(S.st));
     cudaEventDestroy(S.ev0); cudaEventDestroy(S.ev1);
@@ -220,6 +223,9 @@ void irr_simd_close_(int *rank)
 void irr_simd_profile_(int *rank)
 {
     if (!S.is_open || !S.num_fcall) return;
+    CUDA_CHECK(cudaSetDevice(S.dev));
+    CUDA_CHECK(cudaMemcpy(&S.num_inter, S.d_inter, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemset(S.d_inter, 0, sizeof(unsigned long long)));
     fprintf(stderr, "[R.%d B200 Irr.F ] Ncall: %llu <NI>: %d <NB>: %f grav: %f s, %f Gflops, %f usec\n", *rank, S.num_fcall,
             (int)(S.num_inter / S.num_fcall), (double)S.num_inter / (double)S.num_steps, S.time_grav,
             60.0 * (double)S.num_inter * 1e-9 / S.time_grav, 1e6 * S.time_grav / S.num_fcall);
@@ -262,7 +268,6 @@ void irr_simd_set_list_(int *addr, int *nblist)
     int *s = S.h_slots + (size_t)k * S.slot_ints;
     s[0] = a; s[1] = c;
     memcpy(s + 2, nblist + 1, sizeof(int) * c);
-    S.nnb_host[a] = c;
 }
 
 // reference: irr.avx.cpp:539-563, :593-602
@@ -285,18 +290,14 @@ void irr_simd_firr_vec_(double *ti, int *nip, int addr[], double acc[][3], doubl
         const int *addr_dev = S.h_addr_dev;
         if (n > 1024) { CUDA_CHECK(cudaMemcpyAsync(S.d_addr, S.h_addr, sizeof(int) * n, cudaMemcpyHostToDevice, S.st)); addr_dev = S.d_addr; }
         if (S.timing) CUDA_CHECK(cudaEventRecord(S.ev0, S.st));
-        firr_kernel<<<(n + 3) / 4, 128, 0, S.st>>>(n, *ti, addr_dev, S.ptcl, S.list, S.nnb, S.lstride, S.d_res, S.d_nn);
+        firr_kernel<<<(n + 3) / 4, 128, 0, S.st>>>(n, *ti, addr_dev, S.ptcl, S.list, S.nnb, S.lstride, S.d_res, S.d_nn, S.d_inter);
         CUDA_CHECK(cudaGetLastError());
         if (S.timing) CUDA_CHECK(cudaEventRecord(S.ev1, S.st));
         CUDA_CHECK(cudaStreamSynchronize(S.st));
         if (S.timing) { float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, S.ev0, S.ev1)); S.kernel_ms += ms; }
-        for (int k = 0; k < n; k++) {
-            const double *r = S.h_res + (size_t)k * 6;
-            acc[i0 + k][0] = r[0]; acc[i0 + k][1] = r[1]; acc[i0 + k][2] = r[2];
-            jrk[i0 + k][0] = r[3]; jrk[i0 + k][1] = r[4]; jrk[i0 + k][2] = r[5];
-            nnbid[i0 + k] = S.h_nn[k];
-            S.num_inter += (unsigned long long)S.nnb_host[S.h_addr[k] - 1];
-        }
+        memcpy(&acc[i0][0], S.h_res, sizeof(double) * 3 * (size_t)n);
+        memcpy(&jrk[i0][0], S.h_res + 3 * (size_t)n, sizeof(double) * 3 * (size_t)n);
+        memcpy(nnbid + i0, S.h_nn, sizeof(int) * (size_t)n);
     }
     S.time_grav += wtime() - t0;
     S.num_fcall++;
@@ -320,9 +321,28 @@ void irr_b200_set_list_batch_(int *n, int addr[], int *lstride, int lists[])
 // out[0] = device ms of the force kernel since open / the last call of this function, out[1] = force calls,
 // out[2] = pair interactions (CUDA events on the library's stream)
 void irr_b200_set_timing(int on) { S.timing = on != 0; }
+// The particle table on the device (record of address 1; REC = 16 doubles per particle: x0[3] m | v0[3] t0 | a2[3] . | j6[3] .)
+// for a consumer on the same device (gpunb_b200_predict_send_records_), and the call that makes it complete: pending
+// set_jp / set_list reach the device and the stream is drained.
+const double *irr_b200_particle_records_(int *stride)
+{
+    if (!S.is_open) FATAL("irr_b200_particle_records called while the library is closed");
+    if (stride) *stride = REC;
+    return S.ptcl;
+}
+void irr_b200_flush_(void)
+{
+    if (!S.is_open) FATAL("irr_b200_flush called while the library is closed");
+    CUDA_CHECK(cudaSetDevice(S.dev));
+    flush_particles(false);
+    flush_lists(false);
+    CUDA_CHECK(cudaStreamSynchronize(S.st));
+}
 void irr_b200_counters(double out[3])
 {
-    out[0] = S.kernel_ms; out[1] = (double)S.num_fcall; out[2] = (double)S.num_inter;
+    unsigned long long inter = 0;
+    if (S.is_open) { CUDA_CHECK(cudaSetDevice(S.dev)); CUDA_CHECK(cudaMemcpy(&inter, S.d_inter, sizeof(inter), cudaMemcpyDeviceToHost)); }
+    out[0] = S.kernel_ms; out[1] = (double)S.num_fcall; out[2] = (double)inter;
     S.kernel_ms = 0;
 }
 

@@ -160,6 +160,10 @@ def test_native_driver_on_the_device_paths(b200):
     assert (out["block_steps"], out["irr_steps"], out["reg_steps"]) == (st.block_steps, st.irr_steps, st.reg_steps)
     assert np.array_equal(xo, ac.x0) and np.array_equal(vo, ac.v0)
     assert abs(out["dE_over_E"]) < 1e-4
+    # one copy of the state on the device: the predictor reads the irr library's particle table -- the same snapshots, bit for bit
+    shared, xs, vs = ac_native.run(lib_path(), irr.lib_path(), m, x, v, 0.25, use_predictor=2, use_regcor=2, **kw)
+    assert np.array_equal(xs, xo) and np.array_equal(vs, vo)
+    print("shared state:", {k: shared[k] for k in ("wall_total", "wall_send", "wall_regf", "wall_irr", "wall_regcor")})
     host, xh, _ = ac_native.run(lib_path(), irr.lib_path(), m, x, v, 0.25, **kw)         # reference ABI only: host predictor, host lists
     assert abs(host["irr_steps"] - out["irr_steps"]) < 0.02 * out["irr_steps"]
     assert np.median(np.linalg.norm(xh - xo, axis=1)) < 1e-6
