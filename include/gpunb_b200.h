@@ -181,6 +181,12 @@ void  gpunb_b200_set_sub_pairs(double pairs);
  * it (default 2.5e7: the sort would add more latency than it saves; 0 = always sort).  Environment: GPUNB_B200_ISORT_PAIRS. */
 void  gpunb_b200_set_isort_pairs(double pairs);
 
+/* Work items per resident warp slot of a gpunb_regf_ call that is ONE pair-kernel launch (1 ... 4, default 4: four times
+ * shorter work items against the tail of a launch that runs alone -- DESIGN.md section 3; calls split into sub-blocks
+ * are not affected).  Lists are identical for every setting, sums differ in the last bits (more fp64 partials per i).
+ * Environment: GPUNB_B200_REGF_OVERSUB. */
+void  gpunb_b200_set_regf_oversub(int k);
+
 /* Sub-block sizes of one gpunb_regf_ call: 0 = equal (default), 1 = tapering (weights 7:5:3:1 for four sub-blocks;
  * measured, no gain).  Environment: GPUNB_B200_TAPER. */
 void  gpunb_b200_set_taper(int on);

@@ -157,13 +157,15 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
     auto irr_push_lists = [&](const std::vector<int> &idx) {
         const int k = (int)idx.size();
         if (!k) return;
-        addr.resize(k); irows.assign((size_t)k * lstride, 0);
+        addr.resize(k);
+        if (irows.size() < (size_t)k * lstride) irows.resize((size_t)k * lstride);
         for (int q = 0; q < k; q++) {
             const int i = idx[q];
             addr[q] = i + 1;
             int *r = &irows[(size_t)q * lstride];
             r[0] = nnb[i];
             for (int l = 0; l < nnb[i]; l++) r[1 + l] = nb[(size_t)i * (nnbmax + 1) + l] + 1;
+            for (int l = nnb[i]; l < std::min(lstride - 1, nnb[i] + 8); l++) r[1 + l] = 0;     // the AVX library reads the list 8 at a time
         }
         if (A.set_list_batch) { int kk = k, ls = lstride; A.set_list_batch(&kk, addr.data(), &ls, irows.data()); }
         else for (int q = 0; q < k; q++) A.set_list(&addr[q], &irows[(size_t)q * lstride]);
@@ -229,8 +231,8 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
         else A.send(&nj, m.data(), (d3 *)xp.data(), (d3 *)vp.data());
         st->wall_send += wtime() - w0;
         frn_.assign((size_t)3 * k, 0.0); frdn_.assign((size_t)3 * k, 0.0);
-        if (raw) rows_raw.assign((size_t)k * lmax, 0);
-        else { lnew.assign((size_t)k * (nnbmax + 1), -1); cnew.assign(k, 0); }
+        if (raw) { if (rows_raw.size() < (size_t)k * lmax) rows_raw.resize((size_t)k * lmax); }
+        else { if (lnew.size() < (size_t)k * (nnbmax + 1)) lnew.resize((size_t)k * (nnbmax + 1)); cnew.assign(k, 0); }
         for (int c0 = 0; c0 < k; c0 += MAXTHR) {
             int ni = std::min(MAXTHR, k - c0);
             memcpy(xi.data(), bx + 3 * (size_t)c0, sizeof(double) * 3 * ni); memcpy(vi.data(), bv + 3 * (size_t)c0, sizeof(double) * 3 * ni);
@@ -295,7 +297,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
     std::vector<int> all(n);
     for (int i = 0; i < n; i++) all[i] = i;
     regular(all, x0.data(), v0.data(), 0.0, true, false);
-    for (int i = 0; i < n; i++) { nnb[i] = cnew[i]; memcpy(&nb[(size_t)i * (nnbmax + 1)], &lnew[(size_t)i * (nnbmax + 1)], sizeof(int) * (nnbmax + 1)); }
+    for (int i = 0; i < n; i++) { nnb[i] = cnew[i]; memcpy(&nb[(size_t)i * (nnbmax + 1)], &lnew[(size_t)i * (nnbmax + 1)], sizeof(int) * cnew[i]); }
     if (use_irr) { irr_push_particles(all); irr_push_lists(all); }
     memcpy(xp.data(), x0.data(), sizeof(double) * 3 * n); memcpy(vp.data(), v0.data(), sizeof(double) * 3 * n);
     irregular(all, 0.0, fia, fida, true);
@@ -371,9 +373,12 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
             if (use_regcor) {
                 // the device diffs the lists and returns the force swap: F_irr(new list) = F_irr(old list) + DFIRR
                 const double w0 = wtime();
-                old_rows.assign((size_t)nr * lmax, 0); idx1.resize(nr); rs2.resize(nr);
+                // scratch grows monotonically and is never cleared: only the entries in use are written and read
+                if (!resident_lists && old_rows.size() < (size_t)nr * lmax) old_rows.resize((size_t)nr * lmax);
+                idx1.resize(nr); rs2.resize(nr);
                 zf.assign((size_t)3 * nr, 0.0); zd.assign((size_t)3 * nr, 0.0); dfi.assign((size_t)3 * nr, 0.0); dfd.assign((size_t)3 * nr, 0.0);
-                nbl.resize(nr); nbg.resize(nr); jj.resize((size_t)2 * nr * lmax);
+                nbl.resize(nr); nbg.resize(nr);
+                if (jj.size() < (size_t)2 * nr * lmax) jj.resize((size_t)2 * nr * lmax);
                 for (int q = 0; q < nr; q++) {
                     const int i = reg[q];
                     idx1[q] = i + 1; rs2[q] = rs[i] * rs[i];
@@ -387,7 +392,8 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 (nr <= MAXTHR && A.regcor_last ? A.regcor_last : A.regcor)(
                     &kk, idx1.data(), &ifirst, &nn, &nn, &lm, rows_raw.data(), resident_lists ? nullptr : old_rows.data(), rs2.data(), nullptr, &smin, &nm,
                     (d3 *)zf.data(), (d3 *)zd.data(), (d3 *)dfi.data(), (d3 *)dfd.data(), nbl.data(), nbg.data(), jj.data(), &nbsmin);
-                lnew.assign((size_t)nr * (nnbmax + 1), -1); cnew.assign(nr, 0);
+                if (lnew.size() < (size_t)nr * (nnbmax + 1)) lnew.resize((size_t)nr * (nnbmax + 1));
+                cnew.assign(nr, 0);
                 fin.resize((size_t)3 * nr); fidn.resize((size_t)3 * nr);
                 for (int q = 0; q < nr; q++) {
                     const int *row = &rows_raw[(size_t)q * lmax];
@@ -397,7 +403,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 }
                 st->wall_regcor += wtime() - w0;
             } else {
-                for (int q = 0; q < nr; q++) { const int i = reg[q]; nnb[i] = cnew[q]; memcpy(&nb[(size_t)i * (nnbmax + 1)], &lnew[(size_t)q * (nnbmax + 1)], sizeof(int) * (nnbmax + 1)); }
+                for (int q = 0; q < nr; q++) { const int i = reg[q]; nnb[i] = cnew[q]; memcpy(&nb[(size_t)i * (nnbmax + 1)], &lnew[(size_t)q * (nnbmax + 1)], sizeof(int) * cnew[q]); }
                 if (use_irr) irr_push_lists(reg);
                 irregular(reg, tn, fin, fidn, have_snapshot);
             }
@@ -442,7 +448,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 const int i = reg[q];
                 for (int c = 0; c < 3; c++) { fr[3 * i + c] = frn_[3 * q + c]; frd[3 * i + c] = frdn_[3 * q + c]; }
                 t0r[i] = tn;
-                nnb[i] = cnew[q]; memcpy(&nb[(size_t)i * (nnbmax + 1)], &lnew[(size_t)q * (nnbmax + 1)], sizeof(int) * (nnbmax + 1));
+                nnb[i] = cnew[q]; memcpy(&nb[(size_t)i * (nnbmax + 1)], &lnew[(size_t)q * (nnbmax + 1)], sizeof(int) * cnew[q]);
                 const double oldr = dtr[i];
                 double qr = dtr_new[q] < oldr ? pow2_floor(dtr_new[q]) : oldr;
                 if (dtr_new[q] >= 2.0 * oldr && fmod(tn, 2.0 * oldr) == 0.0 && 2.0 * oldr <= dtmax) qr = 2.0 * oldr;

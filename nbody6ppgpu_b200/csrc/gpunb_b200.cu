@@ -94,7 +94,7 @@ constexpr int REGF_OVERSUB = 4;                   // ... of a gpunb_regf_ call (
                                                   // one warp per sub-partition.  Four times as many, four times shorter work items keep the
                                                   // sub-partitions full until the last wave: 946 -> 1001 Gint/s per launch at ni = 1024,
                                                   // 906 -> 953 at ni = 256 (profiles/r2t_variant_probe.txt)
-constexpr int MIN_TILES_PER_ITEM = 12;            // ... as long as a work item keeps this many j-tiles
+constexpr int MIN_TILES_PER_ITEM = 24;            // ... as long as a work item keeps this many j-tiles
 constexpr int SORT_CAP    = 1024;
 #ifndef FAR_UNROLL
 #define FAR_UNROLL 2
@@ -2537,7 +2537,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     set_dev(root);
     Job j;
     j.lmax = lmax; j.nnbmax = nnbmax; j.m_flag = m_flag; j.out_f = L.h_f_dev; j.out_list = L.h_list_dev;
-    j.oversub = L.regf_oversub;
+    j.oversub = 1;                     // set below: only a call that is ONE launch is oversubscribed
     j.out_list2 = root.last_rows;      // the rows also stay on the device, for the list bookkeeping that follows (regcor_b200.cu)
     L.last_rows_ni = 0;
     // Output arrays the caller has pinned (gpunb_b200_pin_host_): merge / combine write the ABI layout straight into
@@ -2562,6 +2562,7 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     double t_scatter = 0.0;
     if (nsub == 1) {
         j.slot0 = 0; j.nloc = ni;
+        j.oversub = L.regf_oversub;
         // staged results of a large block on one GPU: delivered in parts, the host copy of part p beside the merge of p+1
         // (measured at N = 10^4, ni = 1024: 162 us per call with 4 parts against 152 us with one merge launch -- the extra
         // launches and event waits cost more than the overlapped host copy saves; kept for tuning: GPUNB_B200_MERGE_PARTS)
@@ -2616,9 +2617,9 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
             CUDA_CHECK(cudaStreamWaitEvent(sl.lo, q == 0 ? root.ev_fork : root.slots[q - 1].ev_start, 0));
             CUDA_CHECK(cudaEventRecord(sl.ev_start, sl.lo));
             j.slot0 = off[q]; j.nloc = off[q + 1] - off[q];
-            // only the LAST sub-block's pair kernel runs into an empty machine: the others are followed by the next one, and
-            // finer work items would only add their fixed costs (measured: e2e 918 -> 882 Gint/s with every sub-block at 4x)
-            j.oversub = q == nq - 1 ? L.regf_oversub : 1;
+            // sub-blocks are not oversubscribed: each pair kernel is followed by the next one, and for the last one the longer
+            // merge (4x the partial records, on the critical path of the call) costs more than the shorter tail saves
+            // (measured on one box: 1123 us per call without, 1152 us with the last sub-block at 4x, 1180 us with all)
             if (q == 0) CUDA_CHECK(cudaEventRecord(root.ev0, sl.lo));       // "grav" span: start of the first pair kernel ...
             run_job(j, ib, ipm, q, true, false);
         }
@@ -3167,6 +3168,7 @@ void gpunb_b200_unpin_host_(void *ptr)
         }
 }
 void gpunb_b200_set_taper(int on) { L.taper = on != 0; }
+void gpunb_b200_set_regf_oversub(int k) { if (k >= 1 && k <= REGF_OVERSUB) L.regf_oversub = k; }
 void gpunb_b200_set_sub_pairs(double pairs) { if (pairs >= 1.0) L.sub_pairs = pairs; }
 void gpunb_b200_set_isort_pairs(double pairs) { if (pairs >= 0.0) L.isort_pairs = pairs; }
 void gpunb_b200_set_islice(int on)

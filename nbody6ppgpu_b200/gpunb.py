@@ -101,6 +101,8 @@ class ForceLib:
             L.gpunb_b200_unpin_host_.restype = None
             L.gpunb_b200_set_resort_every.argtypes = [C.c_int]
             L.gpunb_b200_set_resort_every.restype = None
+            L.gpunb_b200_set_regf_oversub.argtypes = [C.c_int]
+            L.gpunb_b200_set_regf_oversub.restype = None
             L.gpunb_b200_set_taper.argtypes = [C.c_int]
             L.gpunb_b200_set_taper.restype = None
             L.gpunb_b200_set_islice.argtypes = [C.c_int]
@@ -439,6 +441,11 @@ class ForceLib:
         """gpunb_regf_ calls below this many pairs skip the Morton sort of the i-block (default 2.5e7; 0 = always sort)."""
         self._need_b200()
         self.lib.gpunb_b200_set_isort_pairs(float(pairs))
+
+    def set_regf_oversub(self, k: int):
+        """Work items per resident warp slot of an unsplit gpunb_regf_ call (1 ... 4, default 4)."""
+        self._need_b200()
+        self.lib.gpunb_b200_set_regf_oversub(int(k))
 
     def set_taper(self, on: int):
         """Sub-block sizes of one gpunb_regf_ call: equal (0, default) or tapering (1)."""

@@ -245,6 +245,31 @@ def test_subblock_pipeline_matches_single_launch(b200, ni):
         b200.close()
 
 
+@pytest.mark.parametrize("n,ni", [(200_000, 1024), (200_000, 96), (20_000, 700)])
+def test_oversubscribed_launch_matches_plain_launch(b200, n, ni):
+    """An unsplit gpunb_regf_ call runs up to four work items per resident warp slot (while an item keeps >= 24 j-tiles):
+    lists identical to the one-item-per-warp launch, sums equal up to the fp64 summation order of the extra partials."""
+    m, x, v = S.plummer(n, 9, "kroupa")
+    h2, dtr = S.radii_nnb(x, m, 120.0)
+    b200.open(n + 10, 0)
+    b200.send(m, x, v)
+    try:
+        b200.set_tuning(0, 1)
+        out = {}
+        for k in (1, 2, 4):
+            b200.set_regf_oversub(k)
+            for rep in range(2):
+                out[k] = [a.copy() for a in b200.regf(h2[:ni], dtr[:ni], x[:ni], v[:ni], 600, 550, 0)]
+        for k in (2, 4):
+            assert not oracle_lib.list_rows_equal(out[k][3], out[1][3])
+            for q in range(3):
+                assert oracle_lib.relerr(out[k][q], out[1][q]) < 1e-12
+    finally:
+        b200.set_regf_oversub(4)
+        b200.set_tuning(3, 4)
+        b200.close()
+
+
 def test_full_size_parity_1M(b200, oracle):
     """BASELINE.json's headline configuration (synthetic Plummer N=1M, Kroupa IMF, <nnb> ~ 200, lmax 600): blocks from
     the core, the halo and a scattered gather against the oracle over ALL 10^6 j, plus the size-independent properties
