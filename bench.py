@@ -29,6 +29,10 @@ all N -> 977 calls, 1e12 interactions).  interactions = sum ni*nj exactly as the
           from memory bound.
   cpu_baseline  the reference's own AVX library (oracle/_ref, kind "reference") on the host cores, on a
           bounded sample of the same workload.
+  time_unit / wall_s_per_time_unit  the second half of BASELINE.json's metric on a bounded sample: 1/8 N-body time unit at
+          N = 16 000 (samples/N16k.input settings) behind this library with the native Ahmad-Cohen driver
+          (csrc/ac_driver.cpp), wall seconds per time unit, buckets per library call, dE/E.  `--time-unit` integrates
+          a whole time unit behind this library (device paths / reference ABI only) and both reference libraries.
 
 `--impl reference` times that AVX library alone (same metric/config), each step a bounded sample.
 Under torchrun (N>1) the j-set is sharded over ranks (every R-th Hilbert tile); partial sums and neighbour rows are

@@ -170,6 +170,38 @@ def check_islice(lib, tag, rank, world):
     print(f"{tag} rank {rank}: i-slice mode ok", flush=True)
 
 
+def check_regcor(lib, tag, rank=0):
+    """The list bookkeeping after a SHARDED gpunb_regf_: combine_kernel leaves the device copy of the rows that
+    gpunb_b200_regcor_last_ reads; same results as the call that uploads the rows, and as the CPU restatement."""
+    import oracle_lib
+    import regcor_cases as RC
+    c = RC.make_case(n_tot=20011, ni=900, ifirst=5, lmax=400, nnb_mean=60.0, seed=13)
+    o = oracle_lib.Oracle()
+    rows_j = c["index_i"] - c["ifirst"]
+    h2 = c["rs2"].copy()
+    lib.open(c["m"].shape[0] + 10, rank)
+    try:
+        lib.send(c["m"], c["x"], c["v"])
+        for nsub in (1, -2):
+            lib.set_tuning(0, nsub)
+            new = lib.regf(h2, np.full(900, 0.01), c["x"][rows_j], c["v"][rows_j], 400, 350, 0)[3].copy()
+            assert (new[:, 0] >= 0).all()
+            args = (c["index_i"], c["ifirst"], c["n"], c["ntot"])
+            tail = (c["rs2"], c["step"], c["smin"], c["nnbmax"], c["freg"], c["fdr"])
+            last = lib.regcor(*args, None, c["old"], *tail, last_lmax=400)
+            up = lib.regcor(*args, new, c["old"], *tail)
+            ora = o.regcor(*args, new, c["old"], c["m"], c["x"], c["v"], *tail)
+            for k in ("nbloss", "nbgain", "freg", "fdr", "dfirr", "dfd"):
+                assert np.array_equal(last[k], up[k]) and np.array_equal(last[k], ora[k]), (tag, nsub, k)
+            for r in range(900):
+                assert np.array_equal(last["nlist"][r, :last["nlist"][r, 0] + 1], ora["nlist"][r, :ora["nlist"][r, 0] + 1]), (tag, nsub, r)
+            assert last["nbsmin"] == ora["nbsmin"] and ora["nbloss"].sum() > 0 and ora["nbgain"].sum() > 0
+    finally:
+        lib.set_tuning(0, 4)
+        lib.close()
+    print(f"{tag} rank {rank}: regcor after a sharded regf ok", flush=True)
+
+
 def main():
     mode = sys.argv[1]
     if mode == "inproc":
@@ -182,6 +214,7 @@ def main():
         check_pinned(lib, f"inproc x{G}")
         if not os.environ.get("WORKER_ONLY_PINNED"):
             check(lib, f"inproc x{G}")
+            check_regcor(lib, f"inproc x{G}")
     elif mode == "nccl":
         import torch
         import torch.distributed as dist
@@ -198,6 +231,7 @@ def main():
             check(lib, f"nccl x{world}", rank)      # every rank checks: results are replicated
             check_auto_subblocks(lib, f"nccl x{world}", rank, world)
             check_islice(lib, f"nccl x{world}", rank, world)
+            check_regcor(lib, f"nccl x{world}", rank)
         dist.barrier()
         lib.nccl_finalize()
         dist.destroy_process_group()
