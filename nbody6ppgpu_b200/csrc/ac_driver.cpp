@@ -342,10 +342,14 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
     const double w_run = wtime();
     std::vector<double> frnew, frdnew, fr_old, frd_old, dtr_new;
     while (t < p->t_end) {
+        // next block time and its particles in ONE pass over the N next-step times (the same set as min + equality scan)
         double tn = 1e300;
-        for (int i = 0; i < n; i++) tn = std::min(tn, t0[i] + dt[i]);
         act.clear(); reg.clear(); regpos.clear();
-        for (int i = 0; i < n; i++) if (t0[i] + dt[i] == tn) act.push_back(i);
+        for (int i = 0; i < n; i++) {
+            const double ti = t0[i] + dt[i];
+            if (ti < tn) { tn = ti; act.clear(); act.push_back(i); }
+            else if (ti == tn) act.push_back(i);
+        }
         const int na = (int)act.size();
         st->block_steps++;
         xa.resize((size_t)3 * na); va.resize((size_t)3 * na);

@@ -31,6 +31,7 @@ constexpr int REC = 16;            // doubles per particle record: x0[3] m | v0[
 constexpr int PCAP = 1 << 16;      // pending particle records before an early flush
 constexpr int LCAP = 1 << 14;      // pending neighbour lists before an early flush
 constexpr int ICAP = 1 << 16;      // active particles per launch
+constexpr int SMALL_FLUSH = 2048;  // pending records up to which the scatter kernels read the mapped host buffers directly
 
 __global__ void scatter_particles_kernel(int n, const int *__restrict__ addr, const double *__restrict__ rec,
                                          double *__restrict__ ptcl)
@@ -120,6 +121,7 @@ struct Irr {
     // pending updates (pinned host) and their device copies
     double *h_rec = nullptr, *d_rec = nullptr; int *h_paddr = nullptr, *d_paddr = nullptr; int np = 0;
     int *h_slots = nullptr, *d_slots = nullptr; int nl = 0;
+    double *h_rec_dev = nullptr; int *h_paddr_dev = nullptr, *h_slots_dev = nullptr;     // device aliases of the (mapped) pending buffers
     std::vector<int> pslot, lslot;                                        // address -> pending slot (-1: none)
     unsigned long long *d_inter = nullptr;                                // pair interactions since the last profile line (device counter)
     int *h_addr = nullptr, *d_addr = nullptr, *h_addr_dev = nullptr;      // active list: mapped pinned (small blocks read it over PCIe) / device copy
@@ -136,10 +138,16 @@ double wtime() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec
 void flush_particles(bool sync = true)
 {
     if (!S.np) return;
-    CUDA_CHECK(cudaMemcpyAsync(S.d_rec, S.h_rec, sizeof(double) * REC * S.np, cudaMemcpyHostToDevice, S.st));
-    CUDA_CHECK(cudaMemcpyAsync(S.d_paddr, S.h_paddr, sizeof(int) * S.np, cudaMemcpyHostToDevice, S.st));
+    // a block step's worth of records (a few hundred) is read by the scatter kernel straight from the mapped pinned buffer:
+    // one enqueue instead of three on a call that is all latency; large batches go through the copy engine first
+    const double *rec = S.h_rec_dev; const int *paddr = S.h_paddr_dev;
+    if (S.np > SMALL_FLUSH) {
+        CUDA_CHECK(cudaMemcpyAsync(S.d_rec, S.h_rec, sizeof(double) * REC * S.np, cudaMemcpyHostToDevice, S.st));
+        CUDA_CHECK(cudaMemcpyAsync(S.d_paddr, S.h_paddr, sizeof(int) * S.np, cudaMemcpyHostToDevice, S.st));
+        rec = S.d_rec; paddr = S.d_paddr;
+    }
     const int threads = S.np * (REC / 2);
-    scatter_particles_kernel<<<(threads + 255) / 256, 256, 0, S.st>>>(S.np, S.d_paddr, S.d_rec, S.ptcl);
+    scatter_particles_kernel<<<(threads + 255) / 256, 256, 0, S.st>>>(S.np, paddr, rec, S.ptcl);
     CUDA_CHECK(cudaGetLastError());
     if (sync) CUDA_CHECK(cudaStreamSynchronize(S.st));        // the pinned buffers are refilled right away
     for (int k = 0; k < S.np; k++) S.pslot[S.h_paddr[k]] = -1;
@@ -149,8 +157,12 @@ void flush_particles(bool sync = true)
 void flush_lists(bool sync = true)
 {
     if (!S.nl) return;
-    CUDA_CHECK(cudaMemcpyAsync(S.d_slots, S.h_slots, sizeof(int) * (size_t)S.slot_ints * S.nl, cudaMemcpyHostToDevice, S.st));
-    scatter_lists_kernel<<<(S.nl * 32 + 127) / 128, 128, 0, S.st>>>(S.nl, S.slot_ints, S.lstride, S.d_slots, S.list, S.nnb);
+    const int *slots = S.h_slots_dev;
+    if (S.nl > SMALL_FLUSH / 4) {
+        CUDA_CHECK(cudaMemcpyAsync(S.d_slots, S.h_slots, sizeof(int) * (size_t)S.slot_ints * S.nl, cudaMemcpyHostToDevice, S.st));
+        slots = S.d_slots;
+    }
+    scatter_lists_kernel<<<(S.nl * 32 + 127) / 128, 128, 0, S.st>>>(S.nl, S.slot_ints, S.lstride, slots, S.list, S.nnb);
     CUDA_CHECK(cudaGetLastError());
     if (sync) CUDA_CHECK(cudaStreamSynchronize(S.st));
     for (int k = 0; k < S.nl; k++) S.lslot[S.h_slots[(size_t)k * S.slot_ints]] = -1;
@@ -180,11 +192,14 @@ void irr_simd_open_(int *nmaxp, int *lmaxp, int *rank)
     CUDA_CHECK(cudaMalloc((void **)&S.list, sizeof(int) * (size_t)S.lstride * S.nmax));
     CUDA_CHECK(cudaMalloc((void **)&S.nnb, sizeof(int) * (size_t)S.nmax));
     CUDA_CHECK(cudaMemsetAsync(S.nnb, 0, sizeof(int) * (size_t)S.nmax, S.st));
-    CUDA_CHECK(cudaMallocHost((void **)&S.h_rec, sizeof(double) * REC * PCAP));
+    CUDA_CHECK(cudaHostAlloc((void **)&S.h_rec, sizeof(double) * REC * PCAP, cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostGetDevicePointer((void **)&S.h_rec_dev, S.h_rec, 0));
     CUDA_CHECK(cudaMalloc((void **)&S.d_rec, sizeof(double) * REC * PCAP));
-    CUDA_CHECK(cudaMallocHost((void **)&S.h_paddr, sizeof(int) * PCAP));
+    CUDA_CHECK(cudaHostAlloc((void **)&S.h_paddr, sizeof(int) * PCAP, cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostGetDevicePointer((void **)&S.h_paddr_dev, S.h_paddr, 0));
     CUDA_CHECK(cudaMalloc((void **)&S.d_paddr, sizeof(int) * PCAP));
-    CUDA_CHECK(cudaMallocHost((void **)&S.h_slots, sizeof(int) * (size_t)S.slot_ints * LCAP));
+    CUDA_CHECK(cudaHostAlloc((void **)&S.h_slots, sizeof(int) * (size_t)S.slot_ints * LCAP, cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostGetDevicePointer((void **)&S.h_slots_dev, S.h_slots, 0));
     CUDA_CHECK(cudaMalloc((void **)&S.d_slots, sizeof(int) * (size_t)S.slot_ints * LCAP));
     CUDA_CHECK(cudaHostAlloc((void **)&S.h_addr, sizeof(int) * ICAP, cudaHostAllocMapped));
     CUDA_CHECK(cudaHostGetDevicePointer((void **)&S.h_addr_dev, S.h_addr, 0));
