@@ -117,6 +117,8 @@ class ForceLib:
             L.gpunb_b200_state_update_.argtypes = [_c_int_p, _c_int_p] + [_c_dbl_p] * 6
             L.gpunb_b200_predict_send_.argtypes = [_c_int_p, _c_dbl_p]
             L.gpunb_b200_get_predicted_.argtypes = [_c_int_p, _c_int_p, _c_dbl_p, _c_dbl_p]
+            L.gpunb_b200_predict_send_records_.argtypes = [_c_int_p, _c_dbl_p, C.c_void_p, _c_int_p]
+            L.gpunb_b200_predict_send_records_.restype = None
             for f in (L.gpunb_b200_state_all_, L.gpunb_b200_state_update_, L.gpunb_b200_predict_send_, L.gpunb_b200_get_predicted_):
                 f.restype = None
             L.gpunb_b200_regcor_.argtypes = ([_c_int_p] * 8 + [_c_dbl_p, _c_dbl_p, _c_dbl_p, _c_int_p] + [_c_dbl_p] * 4
@@ -337,6 +339,14 @@ class ForceLib:
         self._need_b200()
         self.nj = nj
         self.lib.gpunb_b200_predict_send_(C.byref(C.c_int(nj)), C.byref(C.c_double(time)))
+
+    def predict_send_records(self, nj: int, time: float, records_dev: int, stride: int):
+        """predict_send from particle records another library keeps on the same device (device address of the record of the
+        first j-particle, doubles per record) -- libirr_b200.so's table: IrrLib.particle_records()."""
+        self._need_b200()
+        self.nj = nj
+        self.lib.gpunb_b200_predict_send_records_(C.byref(C.c_int(nj)), C.byref(C.c_double(time)), C.c_void_p(records_dev),
+                                                  C.byref(C.c_int(stride)))
 
     def get_predicted(self, idx):
         self._need_b200()

@@ -49,6 +49,10 @@ class IrrLib:
             L.irr_b200_set_jp_batch_.argtypes = [_ip, _ip] + [_dp] * 6
             L.irr_b200_set_list_batch_.argtypes = [_ip, _ip, _ip, _ip]
             L.irr_b200_counters.argtypes = [_dp]
+            L.irr_b200_particle_records_.argtypes = [_ip]
+            L.irr_b200_particle_records_.restype = C.c_void_p
+            L.irr_b200_flush_.argtypes = []
+            L.irr_b200_flush_.restype = None
             for f in (L.irr_b200_set_jp_batch_, L.irr_b200_set_list_batch_, L.irr_b200_counters):
                 f.restype = None
 
@@ -100,6 +104,16 @@ class IrrLib:
         else:
             for k in range(addr.shape[0]):
                 self.lib.irr_simd_set_list_(C.byref(C.c_int(int(addr[k]))), lists[k].ctypes.data_as(_ip))
+
+    def particle_records(self):
+        """(device address of the record of address 1, doubles per record) of the particle table on the device."""
+        stride = C.c_int(0)
+        p = self.lib.irr_b200_particle_records_(C.byref(stride))
+        return int(p), int(stride.value)
+
+    def flush(self):
+        """Pending set_jp / set_list reach the device; the library's stream is drained."""
+        self.lib.irr_b200_flush_()
 
     def set_timing(self, on: bool):
         self.lib.irr_b200_set_timing(int(on))

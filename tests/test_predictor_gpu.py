@@ -52,6 +52,41 @@ def test_predict_send_equals_host_predict_plus_send(b200):
         b200.close()
 
 
+def test_predict_send_from_the_irregular_force_librarys_table(b200):
+    """One copy of the particle state on the device: gpunb_b200_predict_send_records_ predicts the regular-force snapshot
+    from the table irr_simd_set_jp_ keeps current in libirr_b200.so (X0, X0DOT, F/2, FDOT/6, BODY, T0 per particle).  The
+    snapshot is bit for bit the one predict_send builds from its own state, for particles IFIRST..NTOT of the table."""
+    from nbody6ppgpu_b200 import irr
+    ntot, ifirst = 4100, 41                           # the j-set starts behind 40 KS components
+    nj = ntot - ifirst + 1
+    rng = np.random.default_rng(21)
+    m, x0, v0 = S.plummer(ntot, 9, "kroupa")
+    f2 = 0.5 * rng.normal(size=(ntot, 3)); fd6 = rng.normal(size=(ntot, 3)) * 3.0
+    t0 = rng.integers(0, 64, size=ntot) * 2.0 ** -10
+    il = irr.IrrLib(irr.lib_path())
+    il.open(ntot, 64, 0)
+    b200.open(nj + 10, 0)
+    try:
+        addr = np.arange(1, ntot + 1, dtype=np.int32)
+        il.set_jp_batch(addr, x0, v0, f2, fd6, m, t0)
+        for time in (0.0703125, 0.078125):
+            il.flush()
+            base, stride = il.particle_records()
+            b200.predict_send_records(nj, time, base + 8 * stride * (ifirst - 1), stride)
+            idx = np.arange(0, nj, 7, dtype=np.int32)
+            gx, gv = b200.get_predicted(idx)
+            j = slice(ifirst - 1, ntot)
+            xp, vp = host_predict(x0[j], v0[j], f2[j], fd6[j], t0[j], time)
+            assert np.array_equal(gx, xp[idx]) and np.array_equal(gv, vp[idx])
+            # a block of particles advances: set_jp is all the integrator does
+            adv = rng.choice(ntot, size=200, replace=False)
+            x0[adv] += 1e-3 * rng.normal(size=(200, 3)); f2[adv] *= 1.01; t0[adv] = time
+            il.set_jp_batch(adv.astype(np.int32) + 1, x0[adv], v0[adv], f2[adv], fd6[adv], m[adv], t0[adv])
+    finally:
+        b200.close()
+        il.close(0)
+
+
 def test_ac_driver_with_device_predictor_is_bitwise_the_host_path(b200):
     m, x, v = S.plummer(512, 3, "equal")
     res = {}
