@@ -335,6 +335,8 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
         A.state_all(&nj, m.data(), (d3 *)x0.data(), (d3 *)v0.data(), (d3 *)f2.data(), (d3 *)fd6.data(), t0.data());
     }
     st->wall_init = wtime() - w_init;
+    st->wall_send = st->wall_regf = st->wall_irr = st->wall_regcor = 0.0;      // the buckets cover the run, like wall_total (the initial
+                                                                               // force polynomials are wall_init)
 
     // ---- run --------------------------------------------------------------------------------------------------------------
     double t = 0.0;
