@@ -82,7 +82,12 @@ def parse():
                     "library and the reference AVX library, with dE/E for each; prints one JSON line")
     ap.add_argument("--time-unit-probe", default="", help=argparse.SUPPRESS)      # (subprocess) one library: b200 | b200_host | ref_cuda | ref_avx
     ap.add_argument("--tu-n", type=int, default=16000)
-    ap.add_argument("--tu-t", type=float, default=1.0, help="N-body time units integrated by --time-unit (multiple of 0.125)")
+    ap.add_argument("--tu-t", type=float, default=1.0, help="N-body time units integrated by --time-unit (multiple of --tu-dtmax)")
+    ap.add_argument("--tu-dtmax", type=float, default=0.125, help="largest block step (SMAX); the run ends synchronised at multiples of it")
+    ap.add_argument("--tu-nnbopt", type=int, default=100)
+    ap.add_argument("--tu-lmax", type=int, default=400)
+    ap.add_argument("--tu-mflag", type=int, default=1)
+    ap.add_argument("--tu-arms", default="b200,b200_host,ref_cuda,ref_avx")
     return ap.parse_args()
 
 
@@ -396,8 +401,8 @@ def time_unit_probe(args):
     n, T = args.tu_n, args.tu_t
     m, x, v = S.plummer(n, 5, "kroupa")
     dev = kind == "b200"
-    st, _, _ = ac_native.run(so, irr.lib_path(), m, x, v, T, nnbopt=100, lmax=400, m_flag=1, dtmax=0.125, use_predictor=2 if dev else 0,
-                             use_regcor=2 if dev else 0)
+    st, _, _ = ac_native.run(so, irr.lib_path(), m, x, v, T, nnbopt=args.tu_nnbopt, lmax=args.tu_lmax, m_flag=args.tu_mflag,
+                             dtmax=args.tu_dtmax, use_predictor=2 if dev else 0, use_regcor=2 if dev else 0)
     libs = st["wall_send"] + st["wall_regf"] + st["wall_regcor"] + st["wall_irr"]
     emit({"library": {"b200": "libgpunb_b200.so + device-resident predictor on the irr library's particle table + gpunb_b200_regcor_ on the device-resident list store", "b200_host": "libgpunb_b200.so (reference ABI only)",
                       "ref_cuda": "reference gpunb.velocity.cu + gpupot.gpu.cu (sm_100, oracle/_ref)",
@@ -410,10 +415,10 @@ def time_unit_probe(args):
                                "irr_firr_vec": st["wall_irr"], "driver_host": st["wall_total"] - libs}})
 
 
-def run_time_unit_probe(kind, n, T, local, timeout=1500):
+def run_time_unit_probe(kind, n, T, local, timeout=1500, extra=()):
     try:
         env = dict(os.environ, GPU_LIST=str(local), OMP_NUM_THREADS=str(cpu_threads()))
-        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--time-unit-probe", kind, "--tu-n", str(n), "--tu-t", str(T)],
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--time-unit-probe", kind, "--tu-n", str(n), "--tu-t", str(T), *extra],
                            capture_output=True, text=True, timeout=timeout, env=env)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         return json.loads(lines[-1]) if lines else {"unavailable": (r.stderr or "no output")[-300:]}
@@ -437,9 +442,15 @@ def main():
         return
     if args.time_unit:
         if rank == 0:
-            arms = {k: run_time_unit_probe(k, args.tu_n, args.tu_t, local) for k in ("b200", "b200_host", "ref_cuda", "ref_avx")}
+            extra = ("--tu-dtmax", str(args.tu_dtmax), "--tu-nnbopt", str(args.tu_nnbopt), "--tu-lmax", str(args.tu_lmax), "--tu-mflag", str(args.tu_mflag))
+            arms = {k: run_time_unit_probe(k, args.tu_n, args.tu_t, local, extra=extra) for k in args.tu_arms.split(",")}
+            workload = TU_WORKLOAD.format(n=args.tu_n)
+            if (args.tu_nnbopt, args.tu_lmax, args.tu_mflag, args.tu_dtmax) != (100, 400, 1, 0.125):
+                workload = (f"Plummer N={args.tu_n} Kroupa IMF, NNBOPT={args.tu_nnbopt}, LMAX={args.tu_lmax}, m_flag={args.tu_mflag}, SMAX={args.tu_dtmax}, "
+                            "ETAI=ETAR=0.02; Ahmad-Cohen block-step driver nbody6ppgpu_b200/csrc/ac_driver.cpp (no KS, no stellar evolution)")
+            first = arms[args.tu_arms.split(",")[0]]
             emit({"metric": "wall s per N-body time unit", "unit": "s", "higher_is_better": False, "n_gpus": 1,
-                  "config": {"workload": TU_WORKLOAD.format(n=args.tu_n)}, "value": arms["b200"].get("wall_s_per_time_unit"), "arms": arms})
+                  "config": {"workload": workload}, "value": first.get("wall_s_per_time_unit"), "arms": arms})
         return
     if args.impl == "reference":
         run_reference(args, rank, world)
