@@ -11,6 +11,8 @@
 // host in fp64 (what nbint.f does).
 // Left out, like the Python twin: KS / chain regularisation, stellar evolution, tides, retention of small-step neighbours.
 #include <algorithm>
+#include <functional>
+#include <utility>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -343,15 +345,21 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
     st->e0 = energy();
     const double w_run = wtime();
     std::vector<double> frnew, frdnew, fr_old, frd_old, dtr_new;
+    std::vector<std::pair<double, int>> heap(n);
+    for (int i = 0; i < n; i++) heap[i] = std::make_pair(t0[i] + dt[i], i);
+    std::make_heap(heap.begin(), heap.end(), std::greater<std::pair<double, int>>());
     while (t < p->t_end) {
-        // next block time and its particles in ONE pass over the N next-step times (the same set as min + equality scan)
-        double tn = 1e300;
+        // next block time and its particles: a min-heap over (next step time, particle) -- O(na log N) per block step instead of
+        // the O(N) scan of the Python twin; the block is put in ascending particle order, which is the scan's order (the order of
+        // the i-block decides which particles share a warp of the pair kernel, hence the last bits of its sums)
         act.clear(); reg.clear(); regpos.clear();
-        for (int i = 0; i < n; i++) {
-            const double ti = t0[i] + dt[i];
-            if (ti < tn) { tn = ti; act.clear(); act.push_back(i); }
-            else if (ti == tn) act.push_back(i);
+        const double tn = heap.front().first;
+        while (!heap.empty() && heap.front().first == tn) {
+            std::pop_heap(heap.begin(), heap.end(), std::greater<std::pair<double, int>>());
+            act.push_back(heap.back().second);
+            heap.pop_back();
         }
+        std::sort(act.begin(), act.end());
         const int na = (int)act.size();
         st->block_steps++;
         xa.resize((size_t)3 * na); va.resize((size_t)3 * na);
@@ -377,35 +385,41 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
             }
             regular(reg, bx.data(), bv.data(), tn, false, use_regcor);
             if (use_regcor) {
-                // the device diffs the lists and returns the force swap: F_irr(new list) = F_irr(old list) + DFIRR
+                // the device diffs the lists and returns the force swap: F_irr(new list) = F_irr(old list) + DFIRR.  In chunks of
+                // 2048 rows (what one launch of the library handles): scratch stays a few MB however large the block is
                 const double w0 = wtime();
-                // scratch grows monotonically and is never cleared: only the entries in use are written and read
-                if (!resident_lists && old_rows.size() < (size_t)nr * lmax) old_rows.resize((size_t)nr * lmax);
-                idx1.resize(nr); rs2.resize(nr);
-                zf.assign((size_t)3 * nr, 0.0); zd.assign((size_t)3 * nr, 0.0); dfi.assign((size_t)3 * nr, 0.0); dfd.assign((size_t)3 * nr, 0.0);
-                nbl.resize(nr); nbg.resize(nr);
-                if (jj.size() < (size_t)2 * nr * lmax) jj.resize((size_t)2 * nr * lmax);
-                for (int q = 0; q < nr; q++) {
-                    const int i = reg[q];
-                    idx1[q] = i + 1; rs2[q] = rs[i] * rs[i];
-                    if (resident_lists) continue;
-                    int *o = &old_rows[(size_t)q * lmax];
-                    o[0] = nnb[i];
-                    for (int l = 0; l < nnb[i]; l++) o[1 + l] = nb[(size_t)i * (nnbmax + 1) + l] + 1;
-                }
-                int kk = nr, ifirst = 1, nn = n, lm = lmax, nm = nnbmax, nbsmin = 0; double smin = 0.0;
-                // a block that went through ONE gpunb_regf_ call still has its rows on the device: nothing is uploaded but the old lists
-                (nr <= MAXTHR && A.regcor_last ? A.regcor_last : A.regcor)(
-                    &kk, idx1.data(), &ifirst, &nn, &nn, &lm, rows_raw.data(), resident_lists ? nullptr : old_rows.data(), rs2.data(), nullptr, &smin, &nm,
-                    (d3 *)zf.data(), (d3 *)zd.data(), (d3 *)dfi.data(), (d3 *)dfd.data(), nbl.data(), nbg.data(), jj.data(), &nbsmin);
+                constexpr int RCH = 2048;
                 if (lnew.size() < (size_t)nr * (nnbmax + 1)) lnew.resize((size_t)nr * (nnbmax + 1));
                 cnew.assign(nr, 0);
                 fin.resize((size_t)3 * nr); fidn.resize((size_t)3 * nr);
-                for (int q = 0; q < nr; q++) {
-                    const int *row = &rows_raw[(size_t)q * lmax];
-                    cnew[q] = row[0];
-                    for (int l = 0; l < row[0] && l <= nnbmax; l++) lnew[(size_t)q * (nnbmax + 1) + l] = row[1 + l] - 1;
-                    for (int c = 0; c < 3; c++) { fin[3 * q + c] = fio[3 * q + c] + dfi[3 * q + c]; fidn[3 * q + c] = fido[3 * q + c] + dfd[3 * q + c]; }
+                if (!resident_lists && old_rows.size() < (size_t)RCH * lmax) old_rows.resize((size_t)RCH * lmax);
+                if (jj.size() < (size_t)2 * RCH * lmax) jj.resize((size_t)2 * RCH * lmax);
+                idx1.resize(RCH); rs2.resize(RCH); nbl.resize(RCH); nbg.resize(RCH);
+                for (int c0 = 0; c0 < nr; c0 += RCH) {
+                    const int nc = std::min(RCH, nr - c0);
+                    zf.assign((size_t)3 * nc, 0.0); zd.assign((size_t)3 * nc, 0.0); dfi.assign((size_t)3 * nc, 0.0); dfd.assign((size_t)3 * nc, 0.0);
+                    for (int q = 0; q < nc; q++) {
+                        const int i = reg[c0 + q];
+                        idx1[q] = i + 1; rs2[q] = rs[i] * rs[i];
+                        if (resident_lists) continue;
+                        int *o = &old_rows[(size_t)q * lmax];
+                        o[0] = nnb[i];
+                        for (int l = 0; l < nnb[i]; l++) o[1 + l] = nb[(size_t)i * (nnbmax + 1) + l] + 1;
+                    }
+                    int kk = nc, ifirst = 1, nn = n, lm = lmax, nm = nnbmax, nbsmin = 0; double smin = 0.0;
+                    int *rows_c = &rows_raw[(size_t)c0 * lmax];
+                    // a block that went through ONE gpunb_regf_ call still has its rows on the device: nothing is uploaded but the old lists
+                    (nr <= MAXTHR && A.regcor_last ? A.regcor_last : A.regcor)(
+                        &kk, idx1.data(), &ifirst, &nn, &nn, &lm, rows_c, resident_lists ? nullptr : old_rows.data(), rs2.data(), nullptr, &smin, &nm,
+                        (d3 *)zf.data(), (d3 *)zd.data(), (d3 *)dfi.data(), (d3 *)dfd.data(), nbl.data(), nbg.data(), jj.data(), &nbsmin);
+                    for (int q = 0; q < nc; q++) {
+                        const int *row = rows_c + (size_t)q * lmax;
+                        cnew[c0 + q] = row[0];
+                        for (int l = 0; l < row[0] && l <= nnbmax; l++) lnew[(size_t)(c0 + q) * (nnbmax + 1) + l] = row[1 + l] - 1;
+                        for (int c = 0; c < 3; c++) {
+                            fin[3 * (c0 + q) + c] = fio[3 * (c0 + q) + c] + dfi[3 * q + c]; fidn[3 * (c0 + q) + c] = fido[3 * (c0 + q) + c] + dfd[3 * q + c];
+                        }
+                    }
                 }
                 st->wall_regcor += wtime() - w0;
             } else {
@@ -467,6 +481,10 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
             const int i = act[q];
             const double nxt = t0r[i] + dtr[i] - tn;
             if (nxt > 0) dt[i] = std::min(dt[i], pow2_floor(nxt));
+        }
+        for (int q = 0; q < na; q++) {
+            heap.push_back(std::make_pair(t0[act[q]] + dt[act[q]], act[q]));
+            std::push_heap(heap.begin(), heap.end(), std::greater<std::pair<double, int>>());
         }
         if (use_irr) irr_push_particles(act);
         t = tn;
