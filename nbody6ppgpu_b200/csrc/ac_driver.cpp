@@ -25,6 +25,7 @@ namespace {
 
 double wtime() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + 1e-6 * tv.tv_usec; }
 constexpr int MAXTHR = 1024;      // i-particles per gpunb_regf_ call (util_gpu.F:7)
+constexpr int OMP_MIN = 2048;     // per-particle loops of a block go parallel above this many particles
 constexpr int PAD = 8;            // rows behind every array: the reference AVX library reads / writes past ni (reg.avx.cpp:204-314)
 
 typedef double d3[3];
@@ -142,12 +143,16 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
             vo[c] = (fd6 * (1.5 * s) + f2) * (2.0 * s) + v0[3 * i + c];
         }
     };
-    auto predict_all = [&](double t) { for (int i = 0; i < n; i++) predict_one(i, t, &xp[3 * i], &vp[3 * i]); };
+    auto predict_all = [&](double t) {
+#pragma omp parallel for schedule(static) if (n >= OMP_MIN)
+        for (int i = 0; i < n; i++) predict_one(i, t, &xp[3 * i], &vp[3 * i]);
+    };
     auto irr_push_particles = [&](const std::vector<int> &idx) {
         const int k = (int)idx.size();
         if (!k) return;
         addr.resize(k); upd.resize((size_t)14 * k);
         double *px = upd.data(), *pv = px + 3 * k, *pa = pv + 3 * k, *pj = pa + 3 * k, *pm = pj + 3 * k, *pt = pm + k;
+#pragma omp parallel for schedule(static) if (k >= OMP_MIN)
         for (int q = 0; q < k; q++) {
             const int i = idx[q];
             addr[q] = i + 1; pm[q] = m[i]; pt[q] = t0[i];
@@ -363,10 +368,12 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
         const int na = (int)act.size();
         st->block_steps++;
         xa.resize((size_t)3 * na); va.resize((size_t)3 * na);
+#pragma omp parallel for schedule(static) if (na >= OMP_MIN)
         for (int q = 0; q < na; q++) predict_one(act[q], tn, &xa[3 * q], &va[3 * q]);
         for (int q = 0; q < na; q++) if (t0r[act[q]] + dtr[act[q]] <= tn) { reg.push_back(act[q]); regpos.push_back(q); }
         const int nr = (int)reg.size();
         frnew.resize((size_t)3 * na); frdnew.resize((size_t)3 * na);
+#pragma omp parallel for schedule(static) if (na >= OMP_MIN)
         for (int q = 0; q < na; q++) {
             const int i = act[q];
             for (int c = 0; c < 3; c++) { frnew[3 * q + c] = fr[3 * i + c] + frd[3 * i + c] * (tn - t0r[i]); frdnew[3 * q + c] = frd[3 * i + c]; }   // intgrt.F:284-293
@@ -442,7 +449,9 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 }
             }
         }
-        // corrector (4th-order Hermite on the total force) and the new irregular steps
+        // corrector (4th-order Hermite on the total force) and the new irregular steps (particles are independent: the host
+        // side of the reference integrator is OpenMP as well)
+#pragma omp parallel for schedule(static) if (na >= OMP_MIN)
         for (int q = 0; q < na; q++) {
             const int i = act[q];
             const double d = tn - t0[i];
@@ -456,7 +465,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 fi[3 * i + c] = fia[3 * q + c]; fid[3 * i + c] = fida[3 * q + c]; f[3 * i + c] = f1[c]; fd[3 * i + c] = fd1[c];
             }
             t0[i] = tn;
-            if (!shared_state) dirty[i] = 1;
+            if (!shared_state) dirty[i] = 1;            // one byte per particle, distinct particles
             const double dt_new = aarseth(p->eta_i, f1, fd1, a2, a3, d), old = dt[i];
             double qd = dt_new < old ? std::max(pow2_floor(dt_new), dtmin) : old;
             if (dt_new >= 2.0 * old && fmod(tn, 2.0 * old) == 0.0 && 2.0 * old <= dtmax) qd = 2.0 * old;
