@@ -25,7 +25,7 @@ namespace {
 
 double wtime() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + 1e-6 * tv.tv_usec; }
 constexpr int MAXTHR = 1024;      // i-particles per gpunb_regf_ call (util_gpu.F:7)
-constexpr int OMP_MIN = 2048;     // per-particle loops of a block go parallel above this many particles
+constexpr int OMP_MIN = 512;      // per-particle loops of a block go parallel above this many particles
 constexpr int PAD = 8;            // rows behind every array: the reference AVX library reads / writes past ni (reg.avx.cpp:204-314)
 
 typedef double d3[3];

@@ -29,6 +29,10 @@ Optional device paths (this repo's libraries only; the reference libraries run t
                        swap DFIRR / DFD that turns the irregular force over the old list into the one over the new list
                        (regcor_gpu.F:267-470) -- the host neither diffs lists nor sums the changed members.
 
+``csrc/ac_driver.cpp`` (libac_driver.so, ``ac_native.py``) is the C++ twin of this file, statement by statement: behind the
+same libraries the two give the same integration bit for bit (tests/test_hermite_ac.py).  This file is the readable
+statement and the place to change the algorithm; the twin is what ``bench.py --time-unit`` times.
+
 What it deliberately leaves out: KS / chain regularisation, stellar evolution, external tides, the full RS control logic,
 retention of small-step neighbours (SMIN is not used).  Host arithmetic is numpy fp64; the driver is a measurement harness,
 not a production integrator.
