@@ -167,9 +167,16 @@ __global__ void __launch_bounds__(RC_WARPS * 32) regcor_kernel(const RegcorArgs 
                     if (rij2 > __dmul_rn(4.0, rs2)) keep = false;                      // :347-348
                 }
                 if (!keep) { k++; continue; }
-                int l2 = nnb - 1;                                                      // :351-358 ordered insertion
-                while (l2 >= 0 && !(NL[l2] < j)) { NL[l2 + 1] = NL[l2]; l2--; }
-                NL[l2 + 1] = j;
+                if (nnb == 0) {
+                    // :351-358 with NNB = 0: the Fortran compares against NLIST(1), which holds scratch (the last old member,
+                    // :304), and enters THAT instead of J unless it is smaller -- reproduced as written (oracle/regcor_oracle.c)
+                    const int s = OL[nnb0 - 1];
+                    NL[0] = s < j ? j : s;
+                } else {
+                    int l2 = nnb - 1;                                                  // :351-358 ordered insertion
+                    while (l2 >= 0 && !(NL[l2] < j)) { NL[l2 + 1] = NL[l2]; l2--; }
+                    NL[l2 + 1] = j;
+                }
                 nnb++; nbloss--; nbsmin++;
                 const Pair p = pair_terms(xi, vi, a.x, a.v, a.m, j - a.ifirst);       // :367-392
 #pragma unroll

@@ -101,10 +101,20 @@ int oracle_regcor_row(int I, int ifirst, int n, int ntot, int lmax, int nnbmax, 
                     if (rij2 > 4.0 * rs2) keep = 0;
                 }
                 if (!keep) { k++; continue; }
-                /* :351-358 ordered insertion (NLIST(1) is scratch in the Fortran and never compared) */
-                int l2 = nnb;
-                while (l2 >= 1 && !(nlist[l2] < j)) { nlist[l2 + 1] = nlist[l2]; l2--; }
-                nlist[l2 + 1] = j;
+                /* :351-358 ordered insertion.  The Fortran starts its comparison at NLIST(NNB+1); for NNB >= 1 it never looks
+                 * at NLIST(1), which holds scratch at this point (the last old member, saved at :304).  For NNB = 0 it DOES:
+                 * "IF (NLIST(1).LT.J)" fails (J is an old member, so J <= the last old member), NLIST(2) = NLIST(1) and J
+                 * goes to NLIST(1) -- the list receives the LAST OLD MEMBER instead of J while FREG / FDR are corrected for
+                 * J.  A latent slip of the reference in a rare corner (first retention into an empty new list); restated as
+                 * written, because the bar is the reference's results.  (tests/regcor_cases.py: fortran_walk shows it.) */
+                if (nnb == 0) {
+                    const int s = old[nnb0];
+                    nlist[1] = s < j ? j : s;
+                } else {
+                    int l2 = nnb;
+                    while (l2 >= 1 && !(nlist[l2] < j)) { nlist[l2 + 1] = nlist[l2]; l2--; }
+                    nlist[l2 + 1] = j;
+                }
                 nnb++; nbloss--; nbsmin++;
                 /* :367-392 */
                 const pair_t p = pair_terms(xi, vi, xj, vj, m[j - ifirst]);

@@ -50,6 +50,29 @@ def make_case(n_tot=3000, ni=257, ifirst=7, n_cm=40, lmax=128, nnb_mean=30.0, se
                 new=new, old=old, rs2=rs ** 2, step=step, smin=smin, freg=freg, fdr=fdr)
 
 
+def make_edge_case(**kw):
+    """make_case plus hand-built rows: only self in the new row (everything lost), both lists empty, identical lists, a new
+    row without self, the longest lists lmax allows."""
+    c = make_case(**kw)
+    ifirst, lmax = c["ifirst"], c["lmax"]
+    me = lambda r: int(c["index_i"][r]) - ifirst
+    new, old = c["new"], c["old"]
+    new[1, :] = 0; new[1, 0] = 1; new[1, 1] = me(1)                          # only self: NNB = 0, every old member is lost
+    new[2, :] = 0; old[2, :] = 0                                            # nothing at all
+    keep = [int(q) - ifirst for q in old[3, 1:1 + old[3, 0]]]
+    row = sorted(set(keep + [me(3)]))
+    new[3, :] = 0; new[3, 0] = len(row); new[3, 1:1 + len(row)] = row        # the old members + self: no change
+    row = [int(q) for q in new[4, 1:1 + new[4, 0]] if int(q) != me(4)]
+    new[4, :] = 0; new[4, 0] = len(row); new[4, 1:1 + len(row)] = row        # a row without self (the caller passed i not in j)
+    cap = lmax - 3
+    allj = [j for j in range(c["m"].shape[0]) if j != me(6)]
+    o = allj[:cap]
+    old[6, :] = 0; old[6, 0] = len(o); old[6, 1:1 + len(o)] = np.asarray(o) + ifirst
+    nw = sorted(allj[40:40 + cap - 1] + [me(6)])
+    new[6, :] = 0; new[6, 0] = len(nw); new[6, 1:1 + len(nw)] = nw           # the longest rows lmax allows, shifted by 40 members
+    return c
+
+
 def _pair(xi, vi, xj, vj, mj):
     a = xj - xi; dv = vj - vi
     rij2 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2]

@@ -71,3 +71,23 @@ def test_cm_body_rows_are_never_retained(oracle):
     assert cm.any()
     RC.compare_rows(out, c, list(np.nonzero(cm)[0][:60]) + list(np.nonzero(~cm)[0][:60]), RC.fortran_walk)
     assert np.array_equal(out["freg"][cm], c["freg"][cm])
+
+
+@pytest.mark.parametrize("smin_mode,nnbmax", [("case", None), ("all_small", None), ("case", 20)])
+def test_edge_rows(oracle, smin_mode, nnbmax):
+    """Hand-built rows (only self, both empty, identical, no self, longest rows) and the two ends of the retention step:
+    every lost member has a small step (all of them inside 2 RS are put back), NNB > NNBMAX at entry (none is)."""
+    c = RC.make_edge_case(seed=21, ni=120, n_tot=1500, lmax=96, nnb_mean=24.0)
+    if smin_mode == "all_small":
+        c["smin"] = 10.0
+    if nnbmax is not None:
+        c["nnbmax"] = nnbmax
+    out = run_oracle(oracle, c)
+    retained = RC.compare_rows(out, c, range(120), RC.fortran_walk)
+    assert out["nbsmin"] == retained
+    assert out["nbgain"][1] == 0 and out["nlist"][1, 0] + out["nbloss"][1] == c["old"][1, 0]      # row 1: every old member is lost or put back
+    assert out["nlist"][2, 0] == 0 and out["nbloss"][2] == 0 and out["nbgain"][2] == 0
+    assert out["nbloss"][3] == 0 and out["nbgain"][3] == 0
+    assert out["nbloss"][6] >= 40 and out["nbgain"][6] >= 39
+    if smin_mode == "all_small":
+        assert retained > 50

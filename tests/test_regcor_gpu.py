@@ -205,3 +205,26 @@ def test_rows_still_on_the_device(b200, oracle):
         b200.set_tuning(0, 4)
     finally:
         b200.close()
+
+
+@pytest.mark.parametrize("smin_mode,nnbmax", [("case", None), ("all_small", None), ("case", 20)])
+def test_edge_rows(b200, oracle, smin_mode, nnbmax):
+    """The hand-built rows of tests/test_regcor_cpu.py::test_edge_rows on the device: only self, both lists empty, identical
+    lists, no self, the longest rows lmax allows; every lost member retained / none retained."""
+    c = RC.make_edge_case(seed=21, ni=120, n_tot=1500, lmax=96, nnb_mean=24.0)
+    if smin_mode == "all_small":
+        c["smin"] = 10.0
+    if nnbmax is not None:
+        c["nnbmax"] = nnbmax
+    b200.open(c["m"].shape[0] + 10, 0)
+    try:
+        b200.send(c["m"], c["x"], c["v"])
+        dev, ora = both(b200, oracle, c)
+        same(dev, ora, c["old"])
+        # the same through the resident store
+        b200.lists_put(c["index_i"], c["old"]); b200.steps_all(c["step"])
+        dev2 = b200.regcor(c["index_i"], c["ifirst"], c["n"], c["ntot"], c["new"], None, c["rs2"], None, c["smin"], c["nnbmax"],
+                           c["freg"], c["fdr"])
+        same(dev2, ora, c["old"])
+    finally:
+        b200.close()
