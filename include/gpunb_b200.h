@@ -181,6 +181,13 @@ void  gpunb_b200_set_sub_pairs(double pairs);
  * it (default 2.5e7: the sort would add more latency than it saves; 0 = always sort).  Environment: GPUNB_B200_ISORT_PAIRS. */
 void  gpunb_b200_set_isort_pairs(double pairs);
 
+/* One process per GPU (after gpunb_b200_nccl_init): gpunb_send_ of at least min_nj particles uploads only this rank's 1/R slice
+ * of the snapshot over its own PCIe link and completes it on every GPU with one all-gather over NVLink ("send
+ * scatters instead of broadcasts"); smaller snapshots, where the all-gather's latency would exceed the saving, are uploaded
+ * whole by every rank.  Default 75000; negative: never.  Every rank must use the same value (the all-gather is collective).
+ * Environment: GPUNB_B200_SEND_SCATTER_MIN. */
+void  gpunb_b200_set_send_scatter(int min_nj);
+
 /* Work items per resident warp slot of a gpunb_regf_ call that is ONE pair-kernel launch (1 ... 4, default 4: four times
  * shorter work items against the tail of a launch that runs alone -- DESIGN.md section 3; calls split into sub-blocks
  * are not affected).  Lists are identical for every setting, sums differ in the last bits (more fp64 partials per i).

@@ -1416,6 +1416,24 @@ __global__ void predict_records_kernel(int n, const double *__restrict__ rec, in
     }
 }
 
+// Scattered gpunb_send_ (one process per GPU): every rank uploads 1/R of the snapshot over its own PCIe link into its chunk
+// of `tmp` (per rank: m[chunk] | x[chunk][3] | v[chunk][3]), an all-gather over NVLink completes `tmp` on every GPU, and
+// this kernel lays it out as the packed snapshot m[nj] | x[nj][3] | v[nj][3].
+__global__ void send_unpack_kernel(int nj, int chunk, const double *__restrict__ tmp, double *__restrict__ jraw)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nj) return;
+    const int r = j / chunk, o = j - r * chunk;
+    const double *src = tmp + (size_t)r * 7 * chunk;
+    jraw[j] = src[o];
+    double *x = jraw + nj, *v = jraw + 4 * (size_t)nj;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        x[3 * (size_t)j + c] = src[chunk + 3 * (size_t)o + c];
+        v[3 * (size_t)j + c] = src[4 * (size_t)chunk + 3 * (size_t)o + c];
+    }
+}
+
 __global__ void snapshot_gather_kernel(int n, int nj, const int *__restrict__ idx, const double *__restrict__ jraw,
                                        double *__restrict__ out, int *__restrict__ bad)
 {
@@ -1530,6 +1548,7 @@ struct Dev {
     int segcap = 0;
     double *fr = nullptr;         // [NIMAX][8] shard partial + count (multi-GPU)
     int *rows = nullptr; size_t rows_ints = 0;                                     // shard rows (in-process multi-GPU)
+    double *send_tmp = nullptr; size_t send_tmp_n = 0;                             // scattered gpunb_send_: [R][7 chunk] (NCCL mode)
     int *last_rows = nullptr; size_t last_rows_ints = 0;                           // root: device copy of the rows of the last gpunb_regf_
     int *nanflag = nullptr;       // device alias of this device's entry of L.h_nan (mapped pinned host memory)
     double *pot_part = nullptr, *pot_out = nullptr; size_t pot_part_n = 0, pot_out_n = 0;
@@ -1592,6 +1611,8 @@ struct Lib {
     int *h_nan = nullptr;          // [MAX_RANKS] NaN flags written by the tile kernels straight into host memory
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
     int regf_oversub = REGF_OVERSUB;
+    int send_scatter_min = 75000;  // one process per GPU: snapshots of at least this many particles are uploaded in R slices and
+                                   // all-gathered over NVLink (GPUNB_B200_SEND_SCATTER_MIN; < 0: never)
     int resort_every = 0;          // Hilbert order refreshed every k-th snapshot (GPUNB_B200_RESORT_EVERY); 1 = always;
                                    // 0 (default) = adaptive: kept while the tiles stay compact (one GPU; sharded runs always sort)
     unsigned long long *h_q = nullptr;                 // mapped: tile-extent sum of the last tilepack (device 0)
@@ -1688,6 +1709,7 @@ void lib_devinit(int irank)
         d.warps_resident = d.nsm * nb * WARPS;
         { const char *e = getenv("GPUNB_B200_OVERSUB"); if (e && atoi(e) >= 1 && atoi(e) <= 32) d.oversub = atoi(e); }
         { const char *e = getenv("GPUNB_B200_REGF_OVERSUB"); if (e && atoi(e) >= 1 && atoi(e) <= 32) L.regf_oversub = atoi(e); }
+        { const char *e = getenv("GPUNB_B200_SEND_SCATTER_MIN"); if (e) L.send_scatter_min = atoi(e); }
         fprintf(stderr, "# GPU initialization - rank: %d; HOST %s; NGPU %d; device: %d %s; B200-native regf[%s]: %d SMs x %d CTAs x %d warps\n",
                 irank, host, (int)ids.size(), d.id, prop.name, V.name, d.nsm, nb, WARPS);
         L.devs.push_back(d);
@@ -1944,7 +1966,8 @@ void lib_close()
         }
         dev_free(d.iperm_all); d.iperm_all_n = 0;
         dev_free(d.state); d.state_cap = d.state_n = 0; dev_free(d.upd_rec); dev_free(d.upd_idx); dev_free(d.upd_bad); d.upd_cap = 0;
-        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.last_rows); d.last_rows_ints = 0; dev_free(d.iperm); dev_free(d.iperm_identity); dev_free(d.stats); dev_free(d.wtime);
+        dev_free(d.fr); dev_free(d.rows); d.rows_ints = 0; dev_free(d.last_rows); d.last_rows_ints = 0;
+        dev_free(d.send_tmp); d.send_tmp_n = 0; dev_free(d.iperm); dev_free(d.iperm_identity); dev_free(d.stats); dev_free(d.wtime);
         dev_free(d.jidx);
         dev_free(d.qsum); d.perm_n = 0;
     }
@@ -1992,6 +2015,42 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
     set_shards(nj);
     constexpr int CHUNK = 1 << 17;                    // particles per chunk (7 MB)
     const bool direct = pinned_alias(mj, (size_t)nj) && pinned_alias(xj, (size_t)3 * nj) && pinned_alias(vj, (size_t)3 * nj);
+    if (L.sh.on && L.send_scatter_min >= 0 && nj >= L.send_scatter_min && L.sh.R > 1) {
+        // "send scatters instead of broadcasts".  Every rank holds the whole host snapshot (replicated-data callers)
+        // but uploads only its 1/R slice over its own PCIe link; the slices meet on every GPU by one all-gather over NVLink
+        // (the reference splits the j array the same way, gpunb.velocity.cu:713-715 -- there the slices stay apart, here
+        // every GPU needs every position for the Hilbert order that defines the tile ownership).
+        Dev &d = L.devs[0];
+        set_dev(d);
+        const int R = L.sh.R, r = L.sh.rank;
+        const int chunk = (nj + R - 1) / R;
+        const size_t lo = (size_t)std::min(nj, r * chunk), hi = (size_t)std::min(nj, (r + 1) * chunk), nm = hi - lo;
+        if ((size_t)R * 7 * chunk > d.send_tmp_n) {
+            CUDA_CHECK(cudaStreamSynchronize(d.st));
+            dev_free(d.send_tmp);
+            d.send_tmp_n = (size_t)R * 7 * (chunk + 1024);
+            dev_alloc(d.send_tmp, d.send_tmp_n);
+        }
+        double *mine = d.send_tmp + (size_t)r * 7 * chunk;
+        if (nm > 0) {
+            const double *sm = mj + lo, *sx = xj + 3 * lo, *sv = vj + 3 * lo;
+            if (!direct) {             // pageable caller arrays: only the slice goes through the pinned staging buffer
+                threaded_copy(h, sm, nm); threaded_copy(h + nm, sx, 3 * nm); threaded_copy(h + 4 * nm, sv, 3 * nm);
+                sm = h; sx = h + nm; sv = h + 4 * nm;
+            }
+            CUDA_CHECK(cudaMemcpyAsync(mine, sm, sizeof(double) * nm, cudaMemcpyHostToDevice, d.st));
+            CUDA_CHECK(cudaMemcpyAsync(mine + chunk, sx, sizeof(double) * 3 * nm, cudaMemcpyHostToDevice, d.st));
+            CUDA_CHECK(cudaMemcpyAsync(mine + 4 * (size_t)chunk, sv, sizeof(double) * 3 * nm, cudaMemcpyHostToDevice, d.st));
+        }
+        const int rc = L.sh.allgather(mine, d.send_tmp, (size_t)7 * chunk, NCCL_FLOAT64, L.sh.comm, d.st);
+        if (rc != 0) FATAL("gpunb_send: ncclAllGather failed: %s", L.sh.errstr ? L.sh.errstr(rc) : "?");
+        send_unpack_kernel<<<(nj + 255) / 256, 256, 0, d.st>>>(nj, chunk, d.send_tmp, d.jraw);
+        CUDA_CHECK(cudaGetLastError());
+        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
+        L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * nm;
+        finish_send(nj, wt0, "gpunb_send");
+        return;
+    }
     if (direct) {                                     // the caller's arrays are pinned: DMA from them, no staging copy
         for (Dev &d : L.devs) {
             set_dev(d);
@@ -3168,6 +3227,7 @@ void gpunb_b200_unpin_host_(void *ptr)
         }
 }
 void gpunb_b200_set_taper(int on) { L.taper = on != 0; }
+void gpunb_b200_set_send_scatter(int min_nj) { L.send_scatter_min = min_nj; }
 void gpunb_b200_set_regf_oversub(int k) { if (k >= 1 && k <= REGF_OVERSUB) L.regf_oversub = k; }
 void gpunb_b200_set_sub_pairs(double pairs) { if (pairs >= 1.0) L.sub_pairs = pairs; }
 void gpunb_b200_set_isort_pairs(double pairs) { if (pairs >= 0.0) L.isort_pairs = pairs; }

@@ -101,6 +101,8 @@ class ForceLib:
             L.gpunb_b200_unpin_host_.restype = None
             L.gpunb_b200_set_resort_every.argtypes = [C.c_int]
             L.gpunb_b200_set_resort_every.restype = None
+            L.gpunb_b200_set_send_scatter.argtypes = [C.c_int]
+            L.gpunb_b200_set_send_scatter.restype = None
             L.gpunb_b200_set_regf_oversub.argtypes = [C.c_int]
             L.gpunb_b200_set_regf_oversub.restype = None
             L.gpunb_b200_set_taper.argtypes = [C.c_int]
@@ -451,6 +453,12 @@ class ForceLib:
         """gpunb_regf_ calls below this many pairs skip the Morton sort of the i-block (default 2.5e7; 0 = always sort)."""
         self._need_b200()
         self.lib.gpunb_b200_set_isort_pairs(float(pairs))
+
+    def set_send_scatter(self, min_nj: int):
+        """One process per GPU: snapshots of at least min_nj particles are uploaded in R slices and all-gathered over NVLink
+        (negative: never).  The same value on every rank."""
+        self._need_b200()
+        self.lib.gpunb_b200_set_send_scatter(int(min_nj))
 
     def set_regf_oversub(self, k: int):
         """Work items per resident warp slot of an unsplit gpunb_regf_ call (1 ... 4, default 4)."""
