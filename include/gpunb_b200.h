@@ -184,7 +184,7 @@ void  gpunb_b200_set_isort_pairs(double pairs);
 /* One process per GPU (after gpunb_b200_nccl_init): gpunb_send_ of at least min_nj particles uploads only this rank's 1/R slice
  * of the snapshot over its own PCIe link and completes it on every GPU with one all-gather over NVLink ("send
  * scatters instead of broadcasts"); smaller snapshots, where the all-gather's latency would exceed the saving, are uploaded
- * whole by every rank.  Default 75000; negative: never.  Every rank must use the same value (the all-gather is collective).
+ * whole by every rank.  Default 40000; negative: never.  Every rank must use the same value (the all-gather is collective).
  * Environment: GPUNB_B200_SEND_SCATTER_MIN. */
 void  gpunb_b200_set_send_scatter(int min_nj);
 

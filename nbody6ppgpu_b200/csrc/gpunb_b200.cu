@@ -1611,7 +1611,7 @@ struct Lib {
     int *h_nan = nullptr;          // [MAX_RANKS] NaN flags written by the tile kernels straight into host memory
     int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
     int regf_oversub = REGF_OVERSUB;
-    int send_scatter_min = 75000;  // one process per GPU: snapshots of at least this many particles are uploaded in R slices and
+    int send_scatter_min = 40000;  // one process per GPU: snapshots of at least this many particles are uploaded in R slices and
                                    // all-gathered over NVLink (GPUNB_B200_SEND_SCATTER_MIN; < 0: never)
     int resort_every = 0;          // Hilbert order refreshed every k-th snapshot (GPUNB_B200_RESORT_EVERY); 1 = always;
                                    // 0 (default) = adaptive: kept while the tiles stay compact (one GPU; sharded runs always sort)

@@ -228,7 +228,7 @@ def main():
         nccl_bootstrap(lib, rank, world)
         check_pinned(lib, f"nccl x{world}", rank)
         # from here on gpunb_send_ uploads 1/R of the snapshot per rank and all-gathers it over NVLink (the default only above
-        # 75000 particles): staged and caller-pinned sources, then every parity check below runs behind it
+        # 40000 particles): staged and caller-pinned sources, then every parity check below runs behind it
         lib.set_send_scatter(1000)
         check_pinned(lib, f"nccl x{world} scattered send", rank)
         if not os.environ.get("WORKER_ONLY_PINNED"):
