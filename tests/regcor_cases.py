@@ -73,6 +73,31 @@ def make_edge_case(**kw):
     return c
 
 
+def make_random_case(seed=77):
+    """400 random rows over a universe of 60 particles: short lists, many empty or nearly empty ones, c.m. particles, NNB near
+    NNBMAX -- the corners of the walk and of the retention loop that a physical snapshot rarely visits."""
+    rng = np.random.default_rng(seed)
+    n_tot, ifirst, lmax = 60, 4, 24
+    m = rng.uniform(0.5, 1.5, n_tot); x = rng.normal(size=(n_tot, 3)); v = rng.normal(size=(n_tot, 3))
+    ni = 400
+    rows_j = rng.integers(0, n_tot, ni)
+    new = np.zeros((ni, lmax), dtype=np.int32); old = np.zeros((ni, lmax), dtype=np.int32)
+    for r in range(ni):
+        k_new, k_old = int(rng.integers(0, 13)), int(rng.integers(0, 13))
+        others = np.setdiff1d(np.arange(n_tot), [rows_j[r]])
+        nb = np.sort(rng.choice(others, k_new, replace=False))
+        if rng.random() < 0.8:
+            nb = np.sort(np.append(nb, rows_j[r]))                   # self included, as gpunb_regf_ returns it
+        new[r, 0] = nb.size; new[r, 1:1 + nb.size] = nb
+        ob = np.sort(rng.choice(others, k_old, replace=False)) + ifirst
+        old[r, 0] = ob.size; old[r, 1:1 + ob.size] = ob
+    step = 2.0 ** -rng.integers(1, 6, size=n_tot).astype(np.float64)
+    c = dict(m=m, x=x, v=v, index_i=(rows_j + ifirst).astype(np.int32), ifirst=ifirst, n=ifirst + n_tot - 1 - 8, ntot=ifirst + n_tot - 1,
+             lmax=lmax, nnbmax=9, new=new, old=old, rs2=rng.uniform(0.2, 6.0, ni), step=step, smin=0.125,
+             freg=rng.normal(size=(ni, 3)), fdr=rng.normal(size=(ni, 3)))
+    return c
+
+
 def _pair(xi, vi, xj, vj, mj):
     a = xj - xi; dv = vj - vi
     rij2 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2]

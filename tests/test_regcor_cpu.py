@@ -91,3 +91,15 @@ def test_edge_rows(oracle, smin_mode, nnbmax):
     assert out["nbloss"][6] >= 40 and out["nbgain"][6] >= 39
     if smin_mode == "all_small":
         assert retained > 50
+
+
+def test_random_small_lists_against_the_literal_walk(oracle):
+    """400 random rows over a universe of 60 particles (short lists, many empty or nearly empty ones, every second row with a
+    c.m. particle or NNB near NNBMAX): the corners of the walk and of the retention loop that a physical snapshot rarely
+    visits.  Oracle == literal Fortran transcription, integers and bits."""
+    c = RC.make_random_case()
+    ni = c["index_i"].shape[0]
+    out = run_oracle(oracle, c)
+    retained = RC.compare_rows(out, c, range(ni), RC.fortran_walk)
+    assert out["nbsmin"] == retained and retained > 30
+    assert (out["nlist"][:, 0] == 0).sum() > 3 and (c["old"][:, 0] == 0).sum() > 10

@@ -228,3 +228,16 @@ def test_edge_rows(b200, oracle, smin_mode, nnbmax):
         same(dev2, ora, c["old"])
     finally:
         b200.close()
+
+
+def test_random_small_lists(b200, oracle):
+    """The 400 random short rows of tests/test_regcor_cpu.py on the device."""
+    c = RC.make_random_case()
+    b200.open(c["m"].shape[0] + 10, 0)
+    try:
+        b200.send(c["m"], c["x"], c["v"])
+        dev, ora = both(b200, oracle, c)
+        same(dev, ora, c["old"])
+        assert ora["nbsmin"] > 30
+    finally:
+        b200.close()
