@@ -416,8 +416,11 @@ static void regcor_impl(bool last, int *nip, int index_i[], int *ifirstp, int *n
             if (I < ifirst || I - ifirst >= S.nj) FATAL("gpunb_b200_regcor_: particle %d outside the snapshot [%d, %d)", I, ifirst, ifirst + S.nj);
             maxI = I > maxI ? I : maxI;
         }
-        if (!old_list || RC.store) ensure_store(S, lmax, maxI);
         if (!old_list && !RC.store) FATAL("gpunb_b200_regcor_: no old lists passed and no resident list store (gpunb_b200_lists_put_)");
+        // the store is read (old_list == NULL) and committed to; a call that brings its own old lists at another lmax than the
+        // store's rows simply does not commit
+        const bool use_store = RC.store && (!old_list || lmax == RC.store_stride);
+        if (use_store) ensure_store(S, lmax, maxI);
         // ---- pack and upload -------------------------------------------------------------------------------------
         int *hi = RC.h_int;
         // layout sized by this call's rows: index | new_off | old_off | packed new | packed old
@@ -444,7 +447,7 @@ static void regcor_impl(bool last, int *nip, int index_i[], int *ifirstp, int *n
         a.ni = nr; a.ifirst = ifirst; a.n = *np; a.ntot = *ntotp; a.lmax = lmax; a.nnbmax = *nnbmaxp; a.nj = S.nj;
         a.index_i = RC.d_int; a.new_rows = last ? S.last_rows : RC.d_int; a.new_off = last ? nullptr : RC.d_int + nr;
         a.old_rows = old_list ? RC.d_int : nullptr; a.old_off = RC.d_int + 2 * nr + 1;
-        a.store = RC.store; a.store_stride = RC.store_stride;
+        a.store = use_store ? RC.store : nullptr; a.store_stride = RC.store_stride;
         a.m = S.m; a.x = S.x; a.v = S.v;
         a.step = d_step; a.smin = *sminp;
         a.rs2 = RC.d_dbl; a.fio_in = RC.d_dbl + nr; a.fio_out = RC.o_f_d;
