@@ -106,6 +106,38 @@ def combine_shards(f_parts, lists, nnbmax: int):
     return f, out
 
 
+def send_slice(rank: int, nranks: int, nj: int) -> tuple[int, int, int]:
+    """Scattered gpunb_send_ (lib_send, one process per GPU): rank r uploads particles [lo, hi) of the snapshot into its chunk of
+    the gather buffer; chunk = ceil(nj / R) particles per rank (the last chunks may be short or empty).  Returns (lo, hi, chunk)."""
+    chunk = (nj + nranks - 1) // nranks
+    lo = min(nj, rank * chunk)
+    return lo, min(nj, lo + chunk), chunk
+
+
+def send_pack(rank: int, nranks: int, m, x, v) -> np.ndarray:
+    """This rank's 7 * chunk doubles of the gather buffer: m[chunk] | x[chunk][3] | v[chunk][3] of its slice (tail unspecified)."""
+    nj = m.shape[0]
+    lo, hi, chunk = send_slice(rank, nranks, nj)
+    buf = np.full(7 * chunk, np.nan)
+    k = hi - lo
+    buf[:k] = m[lo:hi]
+    buf[chunk:chunk + 3 * k] = x[lo:hi].ravel()
+    buf[4 * chunk:4 * chunk + 3 * k] = v[lo:hi].ravel()
+    return buf
+
+
+def send_unpack(gathered: np.ndarray, nranks: int, nj: int):
+    """Mirror of send_unpack_kernel: the all-gathered buffer [R][7 chunk] -> the packed snapshot (m[nj], x[nj][3], v[nj][3])."""
+    chunk = (nj + nranks - 1) // nranks
+    g = np.asarray(gathered).reshape(nranks, 7 * chunk)
+    j = np.arange(nj)
+    r, o = j // chunk, j % chunk
+    m = g[r, o]
+    x = np.stack([g[r, chunk + 3 * o + c] for c in range(3)], axis=1)
+    v = np.stack([g[r, 4 * chunk + 3 * o + c] for c in range(3)], axis=1)
+    return m, x, v
+
+
 def nccl_bootstrap(lib, rank: int, world: int, device=None):
     """Create the library's NCCL communicator using torch.distributed only to broadcast the unique id."""
     import torch

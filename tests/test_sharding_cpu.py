@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from nbody6ppgpu_b200 import snapshots as S  # noqa: E402
-from nbody6ppgpu_b200.sharding import combine_shards, shard_members, shard_range, shard_tiles  # noqa: E402
+from nbody6ppgpu_b200.sharding import combine_shards, send_pack, send_slice, send_unpack, shard_members, shard_range, shard_tiles  # noqa: E402
 
 
 def test_shard_range_matches_reference_split():
@@ -87,3 +87,40 @@ def test_two_rank_gloo_shard_combine(tmp_path, nnbmax):
     assert (res[:, 1] < 1e-13).all()
     if nnbmax == 40:
         assert res[0, 2] > 0, "the small-nnbmax case must exercise overflow rows"
+
+
+def test_send_slices_cover_the_snapshot():
+    for nj in (1, 7, 64, 1000, 20011, 40000):
+        for R in (2, 3, 8):
+            sl = [send_slice(r, R, nj) for r in range(R)]
+            assert sl[0][0] == 0 and sl[-1][1] == nj and all(sl[r][1] == sl[r + 1][0] for r in range(R - 1))
+            assert all(hi - lo <= chunk for lo, hi, chunk in sl) and len({c for _, _, c in sl}) == 1
+
+
+def _send_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for n in (20011, 64, 5):                   # ragged: 20011 = 2 * 10006 - 1; fewer particles than ranks * chunk
+        m, x, v = S.plummer(max(n, 8), 21, "kroupa")
+        m, x, v = m[:n], x[:n], v[:n]
+        mine = torch.from_numpy(np.nan_to_num(send_pack(rank, world, m, x, v), nan=-7.0))   # every rank has the whole host snapshot,
+        parts = [torch.zeros_like(mine) for _ in range(world)]                               # uploads only its slice
+        dist.all_gather(parts, mine)
+        gm, gx, gv = send_unpack(torch.cat(parts).numpy(), world, n)
+        ok &= np.array_equal(gm, m) and np.array_equal(gx, x) and np.array_equal(gv, v)
+    res = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64)
+    gathered = [torch.zeros_like(res) for _ in range(world)]
+    dist.all_gather(gathered, res)
+    if rank == 0:
+        np.save(out, np.stack([g.numpy() for g in gathered]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_scattered_send(tmp_path):
+    """The scattered gpunb_send_ of the one-process-per-GPU mode (1/R of the snapshot per rank, all-gather, unpack) with its
+    Python mirror over gloo: every rank ends up with the complete packed snapshot, bit for bit."""
+    out = str(tmp_path / "send.npy")
+    port = 29500 + (os.getpid() % 2000) + 7
+    mp.spawn(_send_worker, args=(2, port, out), nprocs=2, join=True)
+    assert (np.load(out) == 1.0).all()
