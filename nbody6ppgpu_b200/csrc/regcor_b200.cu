@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) regcor_kernel(const RegcorArgs 
                 if (!keep) { k++; continue; }
                 if (nnb == 0) {
                     // :351-358 with NNB = 0: the Fortran compares against NLIST(1), which holds scratch (the last old member,
-                    // :304), and enters THAT instead of J unless it is smaller -- reproduced as written (oracle/regcor_oracle.c)
+                    // :304), and enters THAT instead of J unless it is smaller -- reproduced as written
                     const int s = OL[nnb0 - 1];
                     NL[0] = s < j ? j : s;
                 } else {
