@@ -2,12 +2,17 @@
  * (SURVEY.md section 8f rank 4).  TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg
  * may load it; the product path (nbody6ppgpu_b200/csrc/regcor_b200.cu) never does.
  *
- * PARITY UNPINNED: the reference for this row is Fortran (src/Main/util_gpu.F, src/Main/regcor_gpu.F) and this image has
- * no Fortran compiler, and the reference has no tests or golden vectors for it.  What pins this file
- * instead: an independent numpy statement of the same sets and sums (tests/test_regcor_cpu.py: lost = old \ new,
- * gained = new \ old as Python sets, pair forces in vectorised fp64), and a line-by-line reading of the Fortran cited
- * below.  Built with -ffp-contract=off so that every fp64 operation is the single IEEE operation the Fortran statement
- * names, in the order it names them.
+ * PARITY PINNED BY INTERPRETATION: the reference for this row is Fortran (src/Main/util_gpu.F:102-111,
+ * src/Main/regcor_gpu.F:263-459), this image has no Fortran compiler and the reference has no tests or golden vectors for
+ * it.  The reference's own TEXT is therefore executed statement by statement by oracle/f77_interp.py
+ * (a fixed-form Fortran 77 subset interpreter: IEEE double operations in the order the statements name, no contraction)
+ * on seeded rows -- oracle/make_regcor_golden.py, source read where it lies under /root/reference -- and its outputs are
+ * the golden vectors tests/golden/regcor_f77_*.npz; tests/test_regcor_cpu.py holds this file to them (integers equal, fp64
+ * bit for bit) and, where the reference is present, to the interpreter run live.  What this pin does NOT cover: a Fortran
+ * compiler's freedom to contract a*b+c into an FMA (the vectors are the unfused evaluation, which is also what the CUDA
+ * path computes).  Two further independent statements cross-check it: a hand-made GO TO transcription and plain set
+ * differences / vectorised sums (tests/regcor_cases.py).  Built with -ffp-contract=off so that every fp64 operation is the
+ * single IEEE operation the Fortran statement names, in the order it names them.
  *
  * Per row (one i-particle I of the regular block):
  *   1. util_gpu.F:102-111   the row gpunb_regf_ returned ([count, 0-based j ascending, self included]) becomes NLIST:

@@ -52,6 +52,22 @@ def test_predict_send_equals_host_predict_plus_send(b200):
         b200.close()
 
 
+def test_device_predictor_against_the_golden_vectors_of_the_interpreted_fortran(b200):
+    """gpunb_b200_state_all_ + _predict_send_ against tests/golden/xbpredall_f77.npz: the reference's own predictor statements
+    (xbpredall.f:18-26) executed by oracle/f77_interp.py.  Bit for bit."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "xbpredall_f77.npz")
+    n = g["m"].shape[0]
+    b200.open(n + 10, 0)
+    try:
+        b200.state_all(g["m"], g["x0"], g["x0dot"], g["f"], g["fdot"], g["t0"])
+        b200.predict_send(n, float(g["time"]))
+        gx, gv = b200.get_predicted(np.arange(n))
+        assert np.array_equal(gx, g["f77_x"]) and np.array_equal(gv, g["f77_xdot"])
+    finally:
+        b200.close()
+
+
 def test_predict_send_from_the_irregular_force_librarys_table(b200):
     """One copy of the particle state on the device: gpunb_b200_predict_send_records_ predicts the regular-force snapshot
     from the table irr_simd_set_jp_ keeps current in libirr_b200.so (X0, X0DOT, F/2, FDOT/6, BODY, T0 per particle).  The

@@ -1,11 +1,25 @@
-"""oracle/regcor_oracle.c (the CPU restatement of util_gpu.F:102-111 + regcor_gpu.F:267-470 that the GPU test checks the
-CUDA path against) versus two independent statements of the same Fortran: a literal GO TO transcription and plain set
-differences / vectorised sums (tests/regcor_cases.py).  The reference has no Fortran-free implementation of this row and
-no golden vectors, and this image has no Fortran compiler: parity for this row is pinned by these cross-checks only."""
+"""oracle/regcor_oracle.c (the CPU restatement of util_gpu.F:102-111 + regcor_gpu.F:263-459 that the GPU test checks the
+CUDA path against).
+
+THE PIN: the reference's own Fortran text, executed statement by statement by oracle/f77_interp.py (this image has no
+Fortran compiler).  tests/golden/regcor_f77_*.npz are its outputs on seeded rows (oracle/make_regcor_golden.py; the source
+is read under /root/reference, nothing is copied) -- they travel to machines without the reference; where the reference is
+present the interpreter also runs live on larger cases.  Beside the pin, two further independent statements of the same
+Fortran: a hand-made GO TO transcription and plain set differences / vectorised sums (tests/regcor_cases.py)."""
+import sys
+from pathlib import Path
+
 import numpy as np
 import pytest
 
 import regcor_cases as RC
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+import make_regcor_golden as MG  # noqa: E402
+import regcor_fortran as RF  # noqa: E402
+
+GOLDEN = sorted((ROOT / "tests" / "golden").glob("regcor_f77_*.npz"))
 
 
 @pytest.fixture(scope="module")
@@ -17,6 +31,45 @@ def run_oracle(oracle, c, step=True, rows=None):
     s = slice(None) if rows is None else rows
     return oracle.regcor(c["index_i"][s], c["ifirst"], c["n"], c["ntot"], c["new"][s], c["old"][s], c["m"], c["x"], c["v"],
                          c["rs2"][s], c["step"] if step else None, c["smin"], c["nnbmax"], c["freg"][s], c["fdr"][s])
+
+
+def test_golden_fixtures_are_present():
+    assert len(GOLDEN) == 5, "tests/golden/regcor_f77_*.npz missing: run oracle/make_regcor_golden.py where /root/reference exists"
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p.stem)
+def test_oracle_against_the_golden_vectors_of_the_interpreted_fortran(oracle, path):
+    """Every integer the reference's text leaves behind (NNB, NLIST, NBLOSS, NBGAIN, JJLIST, NBSMIN) equal, every fp64 result
+    (FREG, FDR, DFIRR, DFD) bit for bit."""
+    c, g = MG.load_case(path)
+    out = run_oracle(oracle, c)
+    rows = [r for r in range(c["index_i"].shape[0]) if g["f77_valid"][r]]
+    assert len(rows) >= 96
+    retained = RC.compare_rows(out, c, rows, MG.golden_walk(g))
+    assert retained == out["nbsmin"] == int(g["f77_nbsmin"].sum())
+    assert str(g["source"]).startswith("src/Main/util_gpu.F:102-111 + src/Main/regcor_gpu.F:263-459")
+
+
+@pytest.mark.skipif(not RF.available(), reason="the reference sources are not on this machine (the golden vectors cover it)")
+def test_interpreter_live_on_the_reference_text(oracle, case):
+    """Where /root/reference exists: the fixtures are what the interpreter produces from the text as it lies there today
+    (fingerprint of the interpreted statements), and the oracle equals the interpreted Fortran on the large module case, on
+    the rows without a STEP array, and on a fresh random case no fixture holds."""
+    _, g = MG.load_case(GOLDEN[0])
+    assert str(g["source_sha256"]) == RF.source_fingerprint()
+    c = case
+    out = run_oracle(oracle, c)
+    rows = [r for r in range(c["index_i"].shape[0]) if c["new"][r, 0] >= 0]
+    assert RC.compare_rows(out, c, rows, RF.interpreted_walk) == out["nbsmin"] > 0
+    out0 = run_oracle(oracle, c, step=False)
+    RC.compare_rows(out0, c, rows[:64], lambda cc, r: RF.interpreted_walk(cc, r, use_step=False))
+    c2 = RC.make_random_case(seed=1234)
+    out2 = run_oracle(oracle, c2)
+    assert RC.compare_rows(out2, c2, range(c2["index_i"].shape[0]), RF.interpreted_walk) == out2["nbsmin"] > 30
+    # and the hand transcription says the same as the text it transcribes
+    for r in rows[:40]:
+        a, b = RF.interpreted_walk(c, r), RC.fortran_walk(c, r)
+        assert all(np.array_equal(np.asarray(a[k]), np.asarray(b[k])) for k in a), r
 
 
 def test_oracle_matches_the_literal_fortran_walk(oracle, case):

@@ -7,9 +7,17 @@ import time
 import numpy as np
 import pytest
 
+import sys
+from pathlib import Path
+
 import regcor_cases as RC
 
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+import make_regcor_golden as MG  # noqa: E402
+
 pytestmark = pytest.mark.gpu
+GOLDEN = sorted((ROOT / "tests" / "golden").glob("regcor_f77_*.npz"))
 KEYS = ("nlist_used", "nbloss", "nbgain", "jj_used", "freg", "fdr", "dfirr", "dfd")
 
 
@@ -61,6 +69,23 @@ def test_device_rows_equal_the_oracle_bit_for_bit(b200, oracle):
             c1[k] = c[k][33:34]
         d1, o1 = both(b200, oracle, c1)
         same(d1, o1, c1["old"])
+    finally:
+        b200.close()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p.stem)
+def test_device_rows_against_the_golden_vectors_of_the_interpreted_fortran(b200, path):
+    """The CUDA path against what the reference's OWN Fortran text (util_gpu.F:102-111 + regcor_gpu.F:263-459, executed by
+    oracle/f77_interp.py; fixtures by oracle/make_regcor_golden.py) leaves behind: integers equal, fp64 bit for bit."""
+    c, g = MG.load_case(path)
+    b200.open(c["m"].shape[0] + 10, 0)
+    try:
+        b200.send(c["m"], c["x"], c["v"])
+        dev = b200.regcor(c["index_i"], c["ifirst"], c["n"], c["ntot"], c["new"], c["old"], c["rs2"], c["step"], c["smin"],
+                          c["nnbmax"], c["freg"], c["fdr"])
+        rows = [r for r in range(c["index_i"].shape[0]) if g["f77_valid"][r]]
+        retained = RC.compare_rows(dev, c, rows, MG.golden_walk(g))
+        assert retained == dev["nbsmin"] == int(g["f77_nbsmin"].sum())
     finally:
         b200.close()
 

@@ -53,3 +53,44 @@ def test_reference_library_reproduces_the_golden_fixtures(ref_avx, oracle):
 @pytest.mark.gpu
 def test_cuda_path_against_golden_fixtures(b200, oracle):
     check_against_golden(b200, oracle, 5e-5, 5e-5)
+
+
+def check_against_regint(lib, tol_acc, tol_jrk, tol_pot):
+    """A library behind the gpunb_* ABI against tests/golden/regint_f77.npz: the reference's own fp64 REGINT text
+    (regint.f:28-79) executed by oracle/f77_interp.py.  Lists identical (REGINT: 1-based, self skipped, fp64 '<='; the ABI:
+    0-based, self included, fp32 '<' -- no pair of this seeded case sits on the boundary); REGINT's potential includes the
+    neighbours, the ABI's excludes them."""
+    g = np.load(ROOT / "tests" / "golden" / "regint_f77.npz")
+    m, x, v, isel, lmax = g["m"], g["x"], g["v"], g["isel"], int(g["lmax"])
+    worst = {}
+    for mf in (0, 1):
+        h2 = g["rs"][isel] ** 2 / (float(g["bodym"]) if mf else 1.0)
+        lib.open(m.shape[0] + 10, 0)
+        lib.send(m, x, v)
+        acc, jrk, pot, lst = [np.array(q) for q in lib.regf(h2, g["dtr"][isel], x[isel], v[isel], lmax, lmax - 8, mf)]
+        lib.close()
+        ref = g["f77_list_m%d" % mf]
+        for r, i in enumerate(isel):
+            want = np.sort(np.append(ref[r, 1:1 + ref[r, 0]] - 1, i))
+            assert lst[r, 0] == want.size and list(lst[r, 1:1 + want.size]) == list(want), (mf, r)
+            nb = want[want != i]
+            pot[r] += (m[nb] / np.linalg.norm(x[nb] - x[i], axis=1)).sum()
+        worst[mf] = (oracle_lib.relerr(acc, g["f77_freg_m%d" % mf]), oracle_lib.relerr(jrk, g["f77_fdr_m%d" % mf]),
+                     float(np.abs(pot / g["f77_pot_m%d" % mf] - 1.0).max()))
+        assert worst[mf][0] < tol_acc and worst[mf][1] < tol_jrk and worst[mf][2] < tol_pot, (mf, worst[mf])
+    return worst
+
+
+def test_reference_library_against_the_interpreted_regint(ref_avx):
+    if ref_avx is None:
+        pytest.skip("oracle/_ref not built")
+    check_against_regint(ref_avx, 2e-5, 5e-5, 2e-5)          # the reference's FP32 accumulation
+
+
+@pytest.mark.gpu
+def test_cuda_path_against_the_interpreted_regint(b200):
+    """north_star: forces, jerks and potentials within 1e-6 of the fp64 CPU path -- here the fp64 path is the reference's
+    own REGINT text.  Jerk: the STRICT per-particle |dJ|/|J| is bounded at 1e-5 as everywhere in the suite (cancellation
+    outliers; the 1e-6 bar under the cancellation-aware norm is tests/test_regf_gpu.py's)."""
+    worst = check_against_regint(b200, 1e-6, 1e-5, 1e-6)
+    print("CUDA path vs interpreted REGINT (acc, strict jerk, pot) per m_flag:", worst)
