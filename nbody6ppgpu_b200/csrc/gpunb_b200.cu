@@ -1524,7 +1524,7 @@ struct Dev {
     int *iperm_all = nullptr; size_t iperm_all_n = 0;   // Morton order of every block of a resident sweep
     double *state = nullptr; int state_cap = 0, state_n = 0;   // device-resident predictor state (14 doubles per particle)
     double *upd_rec = nullptr; int *upd_idx = nullptr; int upd_cap = 0; int *upd_bad = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs0 = nullptr, evs1 = nullptr, evdone = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evs0 = nullptr, evs1 = nullptr, evdone = nullptr, evpush = nullptr;
     int nsm = 0, warps_resident = 0, variant = DEFAULT_VARIANT, itile = 32, oversub = OVERSUB;
     // j: full fp64 snapshot (m | x | v, packed for the current nj_total) and the tiles of this device's shard
     int raw_cap = 0, tile_cap = 0;
@@ -1621,6 +1621,8 @@ struct Lib {
     double isort_pairs = 2.5e7;    // gpunb_regf_ calls with fewer pairs skip the Morton sort of the i-block (GPUNB_B200_ISORT_PAIRS)
     int snapshots_since_sort = 0;
     bool taper = false;            // tapering sub-block sizes (GPUNB_B200_TAPER=1); measured: no gain at 4 sub-blocks
+    bool enqueue_threads = true;   // one process driving G > 1 GPUs: one host thread per device enqueues that device's copies and
+                                   // kernels (GPUNB_B200_ENQUEUE_THREADS=0: one thread for all, the A/B arm)
     bool nslot_auto = true;        // nslot not chosen by the caller (environment / gpunb_b200_set_tuning)
     int near_exact = -1;           // >= 0: overrides GPUNB_B200_NEAR_EXACT (gpunb_b200_set_near_exact)
     bool nsub_forced = false;      // tests: split even when the pair kernels would be too short to be worth it
@@ -1638,6 +1640,24 @@ template <class T> void host_alloc(T *&p, size_t n) { CUDA_CHECK(cudaMallocHost(
 template <class T> void host_free(T *&p) { if (p) CUDA_CHECK(cudaFreeHost(p)); p = nullptr; }
 
 void set_dev(const Dev &d) { CUDA_CHECK(cudaSetDevice(d.id)); }
+// counters touched by the per-device enqueue threads of the in-process multi-GPU mode
+inline void ctr_add(int k, double v)
+{
+#pragma omp atomic
+    L.ctr[k] += v;
+}
+// One host thread per device for the per-device enqueue loops (the reference drives its GPUs from one OpenMP thread each as
+// well, gpunb.velocity.cu:607-613,756): with one thread the launches of device g start ~15 us x g after those of device 0.
+// The team has the size of the library's other host-side teams (staging copies, row delivery): libgomp re-docks its threads when
+// consecutive parallel regions ask for different sizes, which cost more than the parallel enqueue saved (2 GPUs, pageable
+// arrays: 692 -> 797 us per call with teams of 2 and 4 alternating).
+inline int enqueue_team()
+{
+    const int G = (int)L.devs.size();
+    if (G <= 1 || !L.enqueue_threads) return 1;
+    if (L.host_threads < G) L.host_threads = G;
+    return L.host_threads;
+}
 int  total_ranks() { return L.sh.on ? L.sh.R : (int)L.devs.size(); }
 
 void lib_devinit(int irank)
@@ -1675,6 +1695,7 @@ void lib_devinit(int irank)
         cudaEvent_t *evs[] = {&d.ev0, &d.ev1, &d.ev2, &d.ev3, &d.evs0, &d.evs1};
         for (cudaEvent_t *ev : evs) CUDA_CHECK(cudaEventCreate(ev));
         CUDA_CHECK(cudaEventCreateWithFlags(&d.evdone, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&d.evpush, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
         int prio_least = 0, prio_greatest = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
@@ -1714,16 +1735,19 @@ void lib_devinit(int irank)
                 irank, host, (int)ids.size(), d.id, prop.name, V.name, d.nsm, nb, WARPS);
         L.devs.push_back(d);
     }
-    // in-process multi-GPU: the root device pulls shard results over NVLink P2P
-    for (size_t g = 1; g < L.devs.size(); g++) {
-        int can = 0;
-        CUDA_CHECK(cudaDeviceCanAccessPeer(&can, L.devs[0].id, L.devs[g].id));
-        if (!can) FATAL("device %d cannot access device %d (P2P needed for the j-shard combine)", L.devs[0].id, L.devs[g].id);
-        CUDA_CHECK(cudaSetDevice(L.devs[0].id));
-        cudaError_t pe = cudaDeviceEnablePeerAccess(L.devs[g].id, 0);
-        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(pe);
-        (void)cudaGetLastError();
-    }
+    // in-process multi-GPU: the root device pulls shard results over NVLink P2P, and every device pushes its slice of a
+    // scattered gpunb_send_ to every other one
+    for (size_t a = 0; a < L.devs.size(); a++)
+        for (size_t g = 0; g < L.devs.size(); g++) {
+            if (a == g) continue;
+            int can = 0;
+            CUDA_CHECK(cudaDeviceCanAccessPeer(&can, L.devs[a].id, L.devs[g].id));
+            if (!can) FATAL("device %d cannot access device %d (P2P needed for the j-shard combine)", L.devs[a].id, L.devs[g].id);
+            CUDA_CHECK(cudaSetDevice(L.devs[a].id));
+            cudaError_t pe = cudaDeviceEnablePeerAccess(L.devs[g].id, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(pe);
+            (void)cudaGetLastError();
+        }
     CUDA_CHECK(cudaSetDevice(L.devs[0].id));
     host_alloc(L.h_flag, 16);
     memset(L.h_flag, 0, 16 * sizeof(int));
@@ -1735,6 +1759,7 @@ void lib_devinit(int irank)
     }
     CUDA_CHECK(cudaSetDevice(L.devs[0].id));
     { const char *e = getenv("GPUNB_B200_NSLOT"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) { L.nslot = atoi(e); L.nslot_auto = false; } }
+    { const char *e = getenv("GPUNB_B200_ENQUEUE_THREADS"); if (e) L.enqueue_threads = atoi(e) != 0; }
     { const char *e = getenv("GPUNB_B200_NSUB");  if (e && atoi(e) >= 1 && atoi(e) <= MAX_SLOTS) L.nsub = atoi(e); }
     { const char *e = getenv("GPUNB_B200_TAPER"); if (e) L.taper = atoi(e) != 0; }
     { const char *e = getenv("GPUNB_B200_SUB_PAIRS"); if (e && atof(e) >= 1.0) L.sub_pairs = atof(e); }
@@ -1820,7 +1845,7 @@ void build_tiles(Dev &d, int n, const double *m, const double *x, const double *
     if (reuse_order && d.perm_n == n) {
         if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag, d.hbits, qsum, q_host);
         CUDA_CHECK(cudaGetLastError());
-        L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+        ctr_add(GPUNB_B200_CTR_LAUNCHES, 1);
         return;
     }
     CUDA_CHECK(cudaMemsetAsync(d.hbits, 0, sizeof(unsigned), d.st));
@@ -1835,7 +1860,7 @@ void build_tiles(Dev &d, int n, const double *m, const double *x, const double *
                                                63 - 3 * hilbert_bits(n), 63, d.st));
     if (nloc > 0) tilepack_kernel<<<(nloc + 3) / 4, 128, 0, d.st>>>(n, t0, tstride, nloc, m, x, v, d.perm, tiles, jidx, d.nanflag, d.hbits, qsum, q_host);
     CUDA_CHECK(cudaGetLastError());
-    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 4;       // + the CUB sort passes (library code, not counted)
+    ctr_add(GPUNB_B200_CTR_LAUNCHES, 4);       // + the CUB sort passes (library code, not counted)
 }
 
 // Host ranges the caller has pinned with gpunb_b200_pin_host_ (cudaHostRegister, mapped): gpunb_send_ uploads from them
@@ -2051,8 +2076,75 @@ void lib_send(int nj, const double *mj, const double *xj, const double *vj)
         finish_send(nj, wt0, "gpunb_send");
         return;
     }
+    // (pageable caller arrays on fewer than four devices keep the whole-snapshot path below: its staging copy runs on four
+    // host threads under the uploads, a slice staged by ONE thread per device is slower there -- 2 GPUs: 2.4 vs 3.7 ms)
+    if (!L.sh.on && L.devs.size() > 1 && L.send_scatter_min >= 0 && nj >= L.send_scatter_min && (direct || L.devs.size() >= 4)) {
+        // One process driving G GPUs, the same scatter: device g uploads slice g over ITS PCIe link (pageable caller arrays:
+        // staged by the device's own host thread) and pushes it to every peer over NVLink; every device then lays the G
+        // slices out as m | x | v.  Instead of G uploads of the whole snapshot out of the same host memory.
+        const int G = (int)L.devs.size();
+        const int chunk = (nj + G - 1) / G;
+        for (int g = 0; g < G; g++) {                 // the buffers the peers push into exist before anybody pushes
+            Dev &d = L.devs[g];
+            if ((size_t)G * 7 * chunk > d.send_tmp_n) {
+                set_dev(d);
+                CUDA_CHECK(cudaStreamSynchronize(d.st));
+                dev_free(d.send_tmp);
+                d.send_tmp_n = (size_t)G * 7 * (chunk + 1024);
+                dev_alloc(d.send_tmp, d.send_tmp_n);
+            }
+        }
+#pragma omp parallel for num_threads(enqueue_team()) schedule(static, 1) if (enqueue_team() > 1)
+        for (int g = 0; g < G; g++) {
+            Dev &d = L.devs[g];
+            set_dev(d);
+            const size_t lo = (size_t)std::min(nj, g * chunk), hi = (size_t)std::min(nj, (g + 1) * chunk), nm = hi - lo;
+            double *mine = d.send_tmp + (size_t)g * 7 * chunk;
+            if (nm > 0) {
+                const double *sm = mj + lo, *sx = xj + 3 * lo, *sv = vj + 3 * lo;
+                if (direct) {
+                    CUDA_CHECK(cudaMemcpyAsync(mine, sm, sizeof(double) * nm, cudaMemcpyHostToDevice, d.st));
+                    CUDA_CHECK(cudaMemcpyAsync(mine + chunk, sx, sizeof(double) * 3 * nm, cudaMemcpyHostToDevice, d.st));
+                    CUDA_CHECK(cudaMemcpyAsync(mine + 4 * (size_t)chunk, sv, sizeof(double) * 3 * nm, cudaMemcpyHostToDevice, d.st));
+                } else {
+                    // pageable: this slice's part of the pinned staging buffer, in pieces of 32768 particles whose uploads
+                    // run under the staging copy of the next piece
+                    double *hs = h + 7 * lo;
+                    for (size_t c = 0; c < nm; c += 32768) {
+                        const size_t n = std::min<size_t>(32768, nm - c);
+                        memcpy(hs + c, sm + c, sizeof(double) * n);
+                        memcpy(hs + nm + 3 * c, sx + 3 * c, sizeof(double) * 3 * n);
+                        memcpy(hs + 4 * nm + 3 * c, sv + 3 * c, sizeof(double) * 3 * n);
+                        CUDA_CHECK(cudaMemcpyAsync(mine + c, hs + c, sizeof(double) * n, cudaMemcpyHostToDevice, d.st));
+                        CUDA_CHECK(cudaMemcpyAsync(mine + chunk + 3 * c, hs + nm + 3 * c, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, d.st));
+                        CUDA_CHECK(cudaMemcpyAsync(mine + 4 * (size_t)chunk + 3 * c, hs + 4 * nm + 3 * c, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, d.st));
+                    }
+                }
+                for (int q = 1; q < G; q++) {         // staggered: at any moment the G devices push to G different peers
+                    Dev &peer = L.devs[(g + q) % G];
+                    CUDA_CHECK(cudaMemcpyPeerAsync(peer.send_tmp + (size_t)g * 7 * chunk, peer.id, mine, d.id, sizeof(double) * 7 * (size_t)chunk, d.st));
+                }
+            }
+            CUDA_CHECK(cudaEventRecord(d.evpush, d.st));
+        }
+#pragma omp parallel for num_threads(enqueue_team()) schedule(static, 1) if (enqueue_team() > 1)
+        for (int g = 0; g < G; g++) {
+            Dev &d = L.devs[g];
+            set_dev(d);
+            for (int q = 1; q < G; q++) CUDA_CHECK(cudaStreamWaitEvent(d.st, L.devs[(g + q) % G].evpush, 0));
+            send_unpack_kernel<<<(nj + 255) / 256, 256, 0, d.st>>>(nj, chunk, d.send_tmp, d.jraw);
+            CUDA_CHECK(cudaGetLastError());
+            ctr_add(GPUNB_B200_CTR_LAUNCHES, 1);
+        }
+        set_dev(L.devs[0]);
+        L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 7.0 * nj;
+        finish_send(nj, wt0, "gpunb_send");
+        return;
+    }
     if (direct) {                                     // the caller's arrays are pinned: DMA from them, no staging copy
-        for (Dev &d : L.devs) {
+#pragma omp parallel for num_threads(enqueue_team()) schedule(static, 1) if (enqueue_team() > 1)
+        for (int g = 0; g < (int)L.devs.size(); g++) {
+            Dev &d = L.devs[g];
             set_dev(d);
             CUDA_CHECK(cudaMemcpyAsync(d.jraw, mj, sizeof(double) * nj, cudaMemcpyHostToDevice, d.st));
             CUDA_CHECK(cudaMemcpyAsync(d.jraw + nj, xj, sizeof(double) * 3 * nj, cudaMemcpyHostToDevice, d.st));
@@ -2102,7 +2194,8 @@ void finish_send(int nj, double wt0, const char *who)
     else if (adaptive) reuse = L.devs[0].perm_n == nj && L.q_ref > 0.0 && L.q_last <= 1.10 * L.q_ref && L.snapshots_since_sort < 64;
     if (reuse && L.devs[0].perm_n != nj) reuse = false;
     L.snapshots_since_sort = reuse ? L.snapshots_since_sort + 1 : 1;
-    for (size_t g = 0; g < L.devs.size(); g++) {
+#pragma omp parallel for num_threads(enqueue_team()) schedule(static, 1) if (enqueue_team() > 1)
+    for (int g = 0; g < (int)L.devs.size(); g++) {
         Dev &d = L.devs[g];
         set_dev(d);
         if (adaptive && !d.qsum) { dev_alloc(d.qsum, 2); CUDA_CHECK(cudaMemsetAsync(d.qsum, 0, 2 * sizeof(unsigned long long), d.st)); }
@@ -2357,7 +2450,7 @@ void launch_isort(Dev &d, cudaStream_t st, int ni_total, int block, const double
     else if (blk_off) isort_kernel<<<nblk_off, 1024, 0, st>>>(ni_total, ni_total, NIMAX, blk_off, xi, d.hbits, iperm, iperm_host);
     else isort_kernel<<<njobs * spj, 1024, 0, st>>>(ni_total, block, sortblk, nullptr, xi, d.hbits, iperm, iperm_host);
     CUDA_CHECK(cudaGetLastError());
-    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 1;
+    ctr_add(GPUNB_B200_CTR_LAUNCHES, 1);
 }
 
 // What one launch group works on: the sorted slots [slot0, slot0 + nloc) of an i-block whose Morton order is iperm.
@@ -2416,10 +2509,10 @@ void launch_regf(Dev &d, Slot &sl, cudaStream_t lo, cudaStream_t hi, const Job &
         if (parts > 1) CUDA_CHECK(cudaEventRecord(d.slots[q].ev_start, hi));        // idle events of the unused pipeline slots
     }
     CUDA_CHECK(cudaGetLastError());
-    L.ctr[GPUNB_B200_CTR_LAUNCHES] += parts - 1;
+    ctr_add(GPUNB_B200_CTR_LAUNCHES, parts - 1);
     if (time_it) CUDA_CHECK(cudaEventRecord(d.ev2, hi));
     if (tl) CUDA_CHECK(cudaEventRecord(tl[3], hi));
-    L.ctr[GPUNB_B200_CTR_LAUNCHES] += 2;
+    ctr_add(GPUNB_B200_CTR_LAUNCHES, 2);
 }
 
 MergeArgs merge_defaults()
@@ -2482,6 +2575,9 @@ void run_job(const Job &j, const IBlock *ib, const int *const *iperm, int q, boo
             c.flags = xb_flags(sh.xbuf, xs); c.seq = seq;
         } else {                       // one process, G GPUs: root waits for every shard, pulls over P2P
             if (own_streams) FATAL("internal: in-process multi-GPU jobs run on the main streams");
+            // one enqueue thread per device; the root stream's waits on the shards follow behind the team (enqueued from a
+            // shard's thread they could land in front of the root's own pair kernel)
+#pragma omp parallel for num_threads(enqueue_team()) schedule(static, 1) if (enqueue_team() > 1)
             for (int g = 0; g < G; g++) {
                 Dev &d = L.devs[g];
                 set_dev(d);
@@ -2489,14 +2585,12 @@ void run_job(const Job &j, const IBlock *ib, const int *const *iperm, int q, boo
                 MergeArgs m = merge_defaults();
                 m.iperm = nullptr; m.res_f = d.fr; m.f_stride = 8; m.res_list = d.rows; m.sort = 0;
                 launch_regf(d, d.slots[q], d.st, d.st, j, ib[g], iperm[g], m, time_it && g == 0, g == 0 ? tl : nullptr);
-                if (g > 0) {
-                    CUDA_CHECK(cudaEventRecord(d.evdone, d.st));
-                    CUDA_CHECK(cudaStreamWaitEvent(root.st, d.evdone, 0));
-                }
+                if (g > 0) CUDA_CHECK(cudaEventRecord(d.evdone, d.st));
                 c.fr[g] = d.fr; c.rows[g] = d.rows;
             }
             c.R = G;
             set_dev(root);
+            for (int g = 1; g < G; g++) CUDA_CHECK(cudaStreamWaitEvent(root.st, L.devs[g].evdone, 0));
         }
         const int ncomb = c.kl1 - c.kl0;
         int cgrid = ncomb > 0 ? (ncomb + 3) / 4 : 1;                             // 4 warps per CTA: one i each
@@ -2575,12 +2669,13 @@ void lib_regf(int ni, const double *h2, const double *dtr, const double *xi, con
     IBlock ib[MAX_RANKS];
     const int *ipm[MAX_RANKS];
     const bool i_sorted = !(ni <= root.itile || (double)ni * L.nbody < L.isort_pairs);
+#pragma omp parallel for num_threads(enqueue_team()) schedule(static, 1) if (enqueue_team() > 1)
     for (int g = 0; g < G; g++) {
         Dev &d = L.devs[g];
         set_dev(d);
         ensure_work_buffers(d, lmax, nnbmax, g == 0, nsub, false);
         CUDA_CHECK(cudaMemcpyAsync(d.ibuf, h, sizeof(double) * 8 * ni, cudaMemcpyHostToDevice, d.st));
-        L.ctr[GPUNB_B200_CTR_H2D_BYTES] += sizeof(double) * 8.0 * ni;
+        ctr_add(GPUNB_B200_CTR_H2D_BYTES, sizeof(double) * 8.0 * ni);
         ib[g] = IBlock{d.ibuf, d.ibuf + ni, d.ibuf + 2 * (size_t)ni, d.ibuf + 5 * (size_t)ni};
         // one i-tile: the order does not matter.  Small calls (ni x nj below ~2.5e7 pairs: the pair kernel is shorter
         // than the 12 us the sort adds to the critical path of a synchronous call) keep the caller's order too:

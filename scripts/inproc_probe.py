@@ -19,7 +19,19 @@ for pin in (0, 1):
     arrs = [m, x, v, *call.outputs]
     if pin:
         assert lib.pin_host(*arrs)
-    t0 = time.perf_counter(); lib.send(m, x, v); ts = time.perf_counter() - t0
+    sends = {}
+    for mode, thr in (("whole snapshot to every device", -1), ("slice per device + NVLink pushes", 0)):
+        lib.set_send_scatter(thr)
+        lib.send(m, x, v); lib.send(m, x, v)            # first sends of this arm: allocations, sort buffers
+        t0 = time.perf_counter()
+        for _ in range(6):
+            lib.send(m, x, v)
+        ts = (time.perf_counter() - t0) / 6
+        a = [q.copy() for q in lib.regf(h2[:256], dtr[:256], x[:256], v[:256], 600, 550, 0)]
+        sends[mode] = (ts, a)
+        print(f"inproc x{G} {'pinned  ' if pin else 'pageable'} gpunb_send_ {mode:34s}: {ts * 1e3:7.3f} ms", flush=True)
+    ra, rb = sends["whole snapshot to every device"][1], sends["slice per device + NVLink pushes"][1]
+    assert all(np.array_equal(p_, q_) for p_, q_ in zip(ra, rb)), "gpunb_regf_ results differ between the two send paths"
     for ni in (1024, 2048, 64):
         for b in range(4):
             call(b * ni, ni)

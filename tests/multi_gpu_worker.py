@@ -212,6 +212,10 @@ def main():
         lib = load(); lib.devinit(0)
         assert lib.num_devices() == G
         check_pinned(lib, f"inproc x{G}")
+        # from here on gpunb_send_ scatters (device g uploads slice g, pushes it to every peer over NVLink; the default only
+        # above 40000 particles): staged and caller-pinned sources, then every parity check below runs behind it
+        lib.set_send_scatter(1000)
+        check_pinned(lib, f"inproc x{G} scattered send")
         if not os.environ.get("WORKER_ONLY_PINNED"):
             check(lib, f"inproc x{G}")
             check_regcor(lib, f"inproc x{G}")
