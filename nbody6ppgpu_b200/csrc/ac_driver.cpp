@@ -167,6 +167,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
         if (!k) return;
         addr.resize(k);
         if (irows.size() < (size_t)k * lstride) irows.resize((size_t)k * lstride);
+#pragma omp parallel for schedule(static) if (k >= OMP_MIN)
         for (int q = 0; q < k; q++) {
             const int i = idx[q];
             addr[q] = i + 1;
@@ -264,6 +265,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 st->overflow_retries++;
             }
             memcpy(&frn_[3 * (size_t)c0], acc.data(), sizeof(double) * 3 * ni); memcpy(&frdn_[3 * (size_t)c0], jrk.data(), sizeof(double) * 3 * ni);
+#pragma omp parallel for schedule(static) if (ni >= OMP_MIN)
             for (int q = 0; q < ni; q++) {
                 const int *row = &lst[(size_t)q * lmax];
                 if (raw) { memcpy(&rows_raw[(size_t)(c0 + q) * lmax], row, sizeof(int) * (row[0] + 1)); continue; }
@@ -395,6 +397,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
             std::vector<double> bx((size_t)3 * nr + 3 * PAD), bv((size_t)3 * nr + 3 * PAD);
             fr_old.resize((size_t)3 * nr); frd_old.resize((size_t)3 * nr); dtr_new.resize(nr);
             std::vector<double> fio((size_t)3 * nr), fido((size_t)3 * nr);
+#pragma omp parallel for schedule(static) if (nr >= OMP_MIN)
             for (int q = 0; q < nr; q++) for (int c = 0; c < 3; c++) {
                 bx[3 * q + c] = xa[3 * regpos[q] + c]; bv[3 * q + c] = va[3 * regpos[q] + c];
                 fio[3 * q + c] = fia[3 * regpos[q] + c]; fido[3 * q + c] = fida[3 * regpos[q] + c];
@@ -414,6 +417,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 for (int c0 = 0; c0 < nr; c0 += RCH) {
                     const int nc = std::min(RCH, nr - c0);
                     zf.assign((size_t)3 * nc, 0.0); zd.assign((size_t)3 * nc, 0.0); dfi.assign((size_t)3 * nc, 0.0); dfd.assign((size_t)3 * nc, 0.0);
+#pragma omp parallel for schedule(static) if (nc >= OMP_MIN)
                     for (int q = 0; q < nc; q++) {
                         const int i = reg[c0 + q];
                         idx1[q] = i + 1; rs2[q] = rs[i] * rs[i];
@@ -428,6 +432,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                     (nr <= MAXTHR && A.regcor_last ? A.regcor_last : A.regcor)(
                         &kk, idx1.data(), &ifirst, &nn, &nn, &lm, rows_c, resident_lists ? nullptr : old_rows.data(), rs2.data(), nullptr, &smin, &nm,
                         (d3 *)zf.data(), (d3 *)zd.data(), (d3 *)dfi.data(), (d3 *)dfd.data(), nbl.data(), nbg.data(), jj.data(), &nbsmin);
+#pragma omp parallel for schedule(static) if (nc >= OMP_MIN)
                     for (int q = 0; q < nc; q++) {
                         const int *row = rows_c + (size_t)q * lmax;
                         cnew[c0 + q] = row[0];
@@ -439,10 +444,12 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 }
                 st->wall_regcor += wtime() - w0;
             } else {
+#pragma omp parallel for schedule(static) if (nr >= OMP_MIN)
                 for (int q = 0; q < nr; q++) { const int i = reg[q]; nnb[i] = cnew[q]; memcpy(&nb[(size_t)i * (nnbmax + 1)], &lnew[(size_t)q * (nnbmax + 1)], sizeof(int) * cnew[q]); }
                 if (use_irr) irr_push_lists(reg);
                 irregular(reg, tn, fin, fidn, have_snapshot);
             }
+#pragma omp parallel for schedule(static) if (nr >= OMP_MIN)
             for (int q = 0; q < nr; q++) {
                 const int i = reg[q];
                 double fol[3], fdol[3], a2r[3], a3r[3];
@@ -482,6 +489,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
         }
         st->irr_steps += na;
         if (nr) {
+#pragma omp parallel for schedule(static) if (nr >= OMP_MIN)
             for (int q = 0; q < nr; q++) {
                 const int i = reg[q];
                 for (int c = 0; c < 3; c++) { fr[3 * i + c] = frn_[3 * q + c]; frd[3 * i + c] = frdn_[3 * q + c]; }
@@ -493,12 +501,14 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 dtr[i] = std::max(qr, dt[i]);
             }
             adjust_rs(reg, cnew);
-            if (use_irr) irr_push_lists(reg);
+            if (use_irr && use_regcor) irr_push_lists(reg);       // the host-list branch above has pushed the new lists already
         }
         for (int q = 0; q < na; q++) {          // an irregular step never exceeds the distance to the particle's next regular time
             const int i = act[q];
             const double nxt = t0r[i] + dtr[i] - tn;
-            if (nxt > 0) dt[i] = std::min(dt[i], pow2_floor(nxt));
+            // pow2_floor(nxt) > nxt / 2 (or it is the cap dtmax >= dt): a step of at most nxt / 2 is never cut -- the rule for
+            // most particles, and log2 / exp2 are the expensive part of this loop
+            if (nxt > 0 && dt[i] > 0.5 * nxt) dt[i] = std::min(dt[i], pow2_floor(nxt));
         }
         {
             double key = -1.0; std::vector<int> *bucket = nullptr;          // most particles of a block keep their step

@@ -386,7 +386,7 @@ class AhmadCohen:
             qr = np.where(dbl, 2.0 * oldr, qr)
             self.dtr[reg] = np.maximum(qr, self.dt[reg])
             self._adjust_rs(reg, cnew)
-            if use_irr:
+            if use_irr and self.use_regcor:            # the host-list branch above has pushed the new lists already
                 self._irr_push_lists(reg)
         else:
             # the regular force of non-regular actives stays a linear extrapolation from t0r
