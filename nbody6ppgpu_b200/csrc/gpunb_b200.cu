@@ -64,6 +64,7 @@
 #include <fcntl.h>
 #include <sched.h>
 #include <sys/mman.h>
+#include <omp.h>
 #include "../../include/gpunb_b200.h"
 #include "internal.h"
 
@@ -1609,7 +1610,8 @@ struct Lib {
     int *h_iperm = nullptr, *h_iperm_dev = nullptr;   // [NIMAX] sorted slot -> i of the current block
     int *h_flag = nullptr;
     int *h_nan = nullptr;          // [MAX_RANKS] NaN flags written by the tile kernels straight into host memory
-    int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB, host_threads = 4;
+    int nslot = DEFAULT_NSLOT, nsub = DEFAULT_NSUB;
+    int host_threads = 0;          // host-side OpenMP team size; 0 until lib_devinit: the caller's default team (internal.h), or GPUNB_B200_HOST_THREADS
     int regf_oversub = REGF_OVERSUB;
     int send_scatter_min = 40000;  // one process per GPU: snapshots of at least this many particles are uploaded in R slices and
                                    // all-gathered over NVLink (GPUNB_B200_SEND_SCATTER_MIN; < 0: never)
@@ -1651,12 +1653,13 @@ inline void ctr_add(int k, double v)
 // The team has the size of the library's other host-side teams (staging copies, row delivery): libgomp re-docks its threads when
 // consecutive parallel regions ask for different sizes, which cost more than the parallel enqueue saved (2 GPUs, pageable
 // arrays: 692 -> 797 us per call with teams of 2 and 4 alternating).
+int host_team() { return L.host_threads > 0 ? L.host_threads : std::max(1, std::min(omp_get_max_threads(), 64)); }
 inline int enqueue_team()
 {
     const int G = (int)L.devs.size();
     if (G <= 1 || !L.enqueue_threads) return 1;
-    if (L.host_threads < G) L.host_threads = G;
-    return L.host_threads;
+    if (host_team() < G) L.host_threads = G;
+    return host_team();
 }
 int  total_ranks() { return L.sh.on ? L.sh.R : (int)L.devs.size(); }
 
@@ -1767,6 +1770,7 @@ void lib_devinit(int irank)
     { const char *e = getenv("GPUNB_B200_RESORT_EVERY"); if (e && atoi(e) >= 0) L.resort_every = atoi(e); }
     CUDA_CHECK(cudaHostAlloc((void **)&L.h_q, sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
     *L.h_q = 0ull;
+    L.host_threads = std::max(1, std::min(omp_get_max_threads(), 64));
     { const char *e = getenv("GPUNB_B200_HOST_THREADS"); if (e && atoi(e) >= 1 && atoi(e) <= 64) L.host_threads = atoi(e); }
     L.devinit = true;
 }
@@ -2019,7 +2023,7 @@ void set_shards(int nj)
 }
 void threaded_copy(double *dst, const double *src, size_t n)
 {
-    const int T = L.host_threads;
+    const int T = host_team();
     if (T <= 1 || n < 65536) { memcpy(dst, src, sizeof(double) * n); return; }
 #pragma omp parallel for num_threads(T) schedule(static)
     for (int t = 0; t < T; t++) {
@@ -2611,7 +2615,7 @@ void scatter_rows(const int *order, int k0, int k1, int lmax, double *acc, doubl
 {   // the rows were just written by the device, so they are cold for the CPU: a few host threads hide the DRAM latency
     // (the reference's host side is OpenMP as well, gpunb.velocity.cu:607-613,756)
     double bytes = 0;
-#pragma omp parallel for num_threads(L.host_threads) schedule(static) reduction(+ : bytes) if (L.host_threads > 1 && k1 - k0 >= 64)
+#pragma omp parallel for num_threads(host_team()) schedule(static) reduction(+ : bytes) if (host_team() > 1 && k1 - k0 >= 64)
     for (int k = k0; k < k1; k++) {
         const int i = order ? order[k] : k;
         const double *f = L.h_f + 7 * (size_t)i;
@@ -3061,6 +3065,8 @@ void lib_pot(int irank, int istart, int ni, int n, const double *m, const double
 }  // namespace
 
 // regcor_b200.cu works on the snapshot the last send left on the root device
+int gpunb_b200_internal_host_team() { return host_team(); }
+
 bool gpunb_b200_internal_snapshot(GpunbSnapshotView *out)
 {
     if (!L.is_open || L.devs.empty() || L.devs[0].nj_total <= 0 || !L.devs[0].jraw) return false;

@@ -19,3 +19,9 @@ struct GpunbSnapshotView {
 };
 GPUNB_HIDDEN bool gpunb_b200_internal_snapshot(GpunbSnapshotView *out);      // false: library closed or nothing sent yet
 GPUNB_HIDDEN void gpunb_b200_internal_regcor_close();                        // frees the buffers of regcor_b200.cu (gpunb_close_)
+// Size of every host-side OpenMP team of the library (staging copies, row delivery, list packing, per-device enqueue): the
+// CALLER's default team size unless GPUNB_B200_HOST_THREADS says otherwise.  libgomp re-docks its threads whenever
+// consecutive parallel regions ask for different team sizes; inside an OpenMP host program (NBODY6++ is one, and so is the
+// reference library: every region of gpunb.velocity.cu / reg.avx.cpp runs with the default team) teams of 4 between the
+// caller's teams of 16 cost 0.2 s per N-body time unit at N = 16k (profiles/r2zk_host_team_ab.txt).
+GPUNB_HIDDEN int gpunb_b200_internal_host_team();

@@ -356,7 +356,7 @@ size_t pack_rows(int n, int lmax, const int *rows, int *dst, int *off, int base)
         used += (size_t)c + 1;
     }
     off[n] = base + (int)used;
-#pragma omp parallel for num_threads(4) schedule(static) if (n >= 256)
+#pragma omp parallel for num_threads(gpunb_b200_internal_host_team()) schedule(static) if (n >= 256)
     for (int r = 0; r < n; r++)
         memcpy(dst + (off[r] - base), rows + (size_t)r * lmax, sizeof(int) * (size_t)(off[r + 1] - off[r]));
     return used;
@@ -461,7 +461,7 @@ static void regcor_impl(bool last, int *nip, int index_i[], int *ifirstp, int *n
         const double tp3 = now_us();
         // ---- results: only the entries in use cross PCIe (the kernel wrote them into mapped pinned memory) ----------
         size_t out_ints = 0;
-#pragma omp parallel for num_threads(4) schedule(static) reduction(+ : out_ints, total_smin) if (nr >= 256)
+#pragma omp parallel for num_threads(gpunb_b200_internal_host_team()) schedule(static) reduction(+ : out_ints, total_smin) if (nr >= 256)
         for (int r = 0; r < nr; r++) {
             const int *oc = RC.o_cnt + 4 * (size_t)r;
             const int *onl = RC.o_nlist + (size_t)r * lmax;
