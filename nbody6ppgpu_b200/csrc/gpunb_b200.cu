@@ -3432,6 +3432,9 @@ int gpunb_b200_nccl_init(int rank, int nranks, const unsigned char id128[128])
     CUDA_CHECK(cudaStreamSynchronize(d.st));
     if (rank == 0) shm_unlink(shm_name);
     sh.on = true;
+    // R processes share the node's cores: the host-side teams shrink accordingly (never below the 4 threads a staging copy
+    // needs to keep a PCIe link busy) unless GPUNB_B200_HOST_THREADS fixed their size
+    if (!getenv("GPUNB_B200_HOST_THREADS")) L.host_threads = std::max(1, std::min(L.host_threads, std::max(4, omp_get_max_threads() / nranks)));
     return 0;
 }
 
