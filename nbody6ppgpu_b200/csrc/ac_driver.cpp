@@ -21,9 +21,13 @@
 #include <vector>
 #include <dlfcn.h>
 #include <sys/time.h>
+#include <time.h>
 
 namespace {
 
+// AC_DRIVER_PHASES=1: where the driver's own time goes, printed to stderr at the end of the run (a dozen clock reads per block step)
+static double PH[16];
+static inline double pt() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 double wtime() { struct timeval tv; gettimeofday(&tv, nullptr); return tv.tv_sec + 1e-6 * tv.tv_usec; }
 constexpr int MAXTHR = 1024;      // i-particles per gpunb_regf_ call (util_gpu.F:7)
 constexpr int OMP_MIN = 512;      // per-particle loops of a block go parallel above this many particles
@@ -344,12 +348,16 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
         int nj = n;
         A.state_all(&nj, m.data(), (d3 *)x0.data(), (d3 *)v0.data(), (d3 *)f2.data(), (d3 *)fd6.data(), t0.data());
     }
+    // the raw rows of the largest possible regular block (every particle): allocated and touched here, not inside the timed run
+    // (at N = 262 144 the first regular block of the run otherwise pays 0.5 s for 629 MB of fresh pages)
+    if (use_regcor) rows_raw.assign((size_t)n * lmax, 0);
     st->wall_init = wtime() - w_init;
     st->wall_send = st->wall_regf = st->wall_irr = st->wall_regcor = 0.0;      // the buckets cover the run, like wall_total (the initial
                                                                                // force polynomials are wall_init)
 
     // ---- run --------------------------------------------------------------------------------------------------------------
     double t = 0.0;
+    memset(PH, 0, sizeof(PH));
     st->e0 = energy();
     const double w_run = wtime();
     std::vector<double> frnew, frdnew, fr_old, frd_old, dtr_new;
@@ -369,6 +377,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
     };
     for (int i = 0; i < n; i++) due_at(t0[i] + dt[i]).push_back(i);
     while (t < p->t_end) {
+        double P0 = pt();
         reg.clear(); regpos.clear();
         const double tn = due.begin()->first;
         act.swap(due.begin()->second);
@@ -377,6 +386,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
         due.erase(due.begin());
         std::sort(act.begin(), act.end());
         const int na = (int)act.size();
+        PH[0] += pt() - P0; P0 = pt();
         st->block_steps++;
         xa.resize((size_t)3 * na); va.resize((size_t)3 * na);
 #pragma omp parallel for schedule(static) if (na >= OMP_MIN)
@@ -390,8 +400,11 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
             for (int c = 0; c < 3; c++) { frnew[3 * q + c] = fr[3 * i + c] + frd[3 * i + c] * (tn - t0r[i]); frdnew[3 * q + c] = frd[3 * i + c]; }   // intgrt.F:284-293
         }
         bool have_snapshot = false;
+        PH[1] += pt() - P0; P0 = pt();
         if (!use_irr || (nr && !predictor)) { predict_all(tn); have_snapshot = true; }
-        irregular(act, tn, fia, fida, have_snapshot);          // over the lists held now (the old lists of the regular particles)
+        PH[2] += pt() - P0; P0 = pt();
+        irregular(act, tn, fia, fida, have_snapshot);
+        PH[3] += pt() - P0; P0 = pt();          // over the lists held now (the old lists of the regular particles)
         if (nr) {
             st->reg_blocks++; st->reg_steps += nr;
             std::vector<double> bx((size_t)3 * nr + 3 * PAD), bv((size_t)3 * nr + 3 * PAD);
@@ -402,7 +415,9 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 bx[3 * q + c] = xa[3 * regpos[q] + c]; bv[3 * q + c] = va[3 * regpos[q] + c];
                 fio[3 * q + c] = fia[3 * regpos[q] + c]; fido[3 * q + c] = fida[3 * regpos[q] + c];
             }
+            PH[9] += pt() - P0; P0 = pt();
             regular(reg, bx.data(), bv.data(), tn, false, use_regcor);
+            PH[10] += pt() - P0; P0 = pt();
             if (use_regcor) {
                 // the device diffs the lists and returns the force swap: F_irr(new list) = F_irr(old list) + DFIRR.  In chunks of
                 // 2048 rows (what one launch of the library handles): scratch stays a few MB however large the block is
@@ -449,6 +464,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 if (use_irr) irr_push_lists(reg);
                 irregular(reg, tn, fin, fidn, have_snapshot);
             }
+            PH[12] += pt() - P0; P0 = pt();
 #pragma omp parallel for schedule(static) if (nr >= OMP_MIN)
             for (int q = 0; q < nr; q++) {
                 const int i = reg[q];
@@ -465,6 +481,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 }
             }
         }
+        PH[4] += pt() - P0; P0 = pt();
         // corrector (4th-order Hermite on the total force) and the new irregular steps (particles are independent: the host
         // side of the reference integrator is OpenMP as well)
 #pragma omp parallel for schedule(static) if (na >= OMP_MIN)
@@ -488,6 +505,7 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
             dt[i] = qd;
         }
         st->irr_steps += na;
+        PH[5] += pt() - P0; P0 = pt();
         if (nr) {
 #pragma omp parallel for schedule(static) if (nr >= OMP_MIN)
             for (int q = 0; q < nr; q++) {
@@ -500,9 +518,11 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 if (dtr_new[q] >= 2.0 * oldr && fmod(tn, 2.0 * oldr) == 0.0 && 2.0 * oldr <= dtmax) qr = 2.0 * oldr;
                 dtr[i] = std::max(qr, dt[i]);
             }
+            PH[11] += pt() - P0; P0 = pt();
             adjust_rs(reg, cnew);
             if (use_irr && use_regcor) irr_push_lists(reg);       // the host-list branch above has pushed the new lists already
         }
+        PH[6] += pt() - P0; P0 = pt();
         for (int q = 0; q < na; q++) {          // an irregular step never exceeds the distance to the particle's next regular time
             const int i = act[q];
             const double nxt = t0r[i] + dtr[i] - tn;
@@ -518,10 +538,13 @@ int ac_driver_run(const char *gpunb_so, const char *irr_so, int n, const double 
                 bucket->push_back(act[q]);
             }
         }
+        PH[7] += pt() - P0; P0 = pt();
         if (use_irr) irr_push_particles(act);
+        PH[8] += pt() - P0;
         t = tn;
     }
     st->wall_total = wtime() - w_run;
+    if (getenv("AC_DRIVER_PHASES")) fprintf(stderr, "PHASES pop+sort %.3f predict+frnew %.3f predict_all %.3f irregular(call) %.3f | reg: gather %.3f regular() %.3f lists+new-irregular %.3f regular-polynomial %.3f | corrector %.3f reg-update-loop %.3f adjust+push_lists %.3f cap+bucket %.3f push_particles %.3f\n", PH[0], PH[1], PH[2], PH[3], PH[9], PH[10], PH[12], PH[4], PH[5], PH[11], PH[6], PH[7], PH[8]);
     st->t = t;
     st->e1 = energy();
     double s = 0; for (int i = 0; i < n; i++) s += nnb[i];
